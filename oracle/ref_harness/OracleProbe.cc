@@ -1,0 +1,58 @@
+// OracleProbe.cc -- TEST INFRASTRUCTURE (not product code).
+//
+// Reference-calling glue: a `main` that loads HEAD.fastb/.qualp/.bci exactly as
+// the reference's DF driver does (10X/DF.cc:464-469 expands the barcode index to
+// a per-read barcode ordinal) and calls the reference's own
+// buildReadQGraph48 (paths/long/BuildReadQGraph48.cc:1688) with the argument
+// values StageBuildGraph uses (10X/runstages/RunStages.cc:404-406).  It contains
+// no re-implementation of the hot path; it is compiled against the UNMODIFIED
+// reference sources under /root/reference by oracle/build_ref.sh into
+// oracle/_ref/ (git-ignored).
+//
+// Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [MIN_QUAL=7]
+//                    [MIN_FREQ=3] [MIN_BC=2]
+//   OUT/reads.fastb must exist (re-opened at BuildReadQGraph48.cc:1763).
+// Outputs: OUT/a.hbv, OUT/tmp.paths (PATHS=True), OUT/kmers.kvec (when env
+//   SN_KEEP_KVEC is set; needs the optional guard patch), OUT/stats/*.json,
+//   OUT/fwd.xlat-free: the HBV itself carries the canonical edge numbering.
+// Prints one line "ORACLE_SECONDS <wall seconds of the buildReadQGraph48 call>".
+#include "MainTools.h"
+#include "Basevector.h"
+#include "feudal/ObjectManager.h"
+#include "feudal/PQVec.h"
+#include "paths/HyperBasevector.h"
+#include "paths/long/ReadPath.h"
+#include "paths/long/BuildReadQGraph48.h"
+#include <chrono>
+
+int main(int argc, char** argv)
+{   RunTime();
+    BeginCommandArguments;
+    CommandArgument_String(HEAD);
+    CommandArgument_String(OUT);
+    CommandArgument_Bool_OrDefault(PATHS, True);
+    CommandArgument_Int_OrDefault(MIN_QUAL, 7);
+    CommandArgument_Int_OrDefault(MIN_FREQ, 3);
+    CommandArgument_Int_OrDefault(MIN_BC, 2);
+    EndCommandArguments;
+
+    vecbvec reads(HEAD + ".fastb");
+    ObjectManager<VecPQVec> quals(HEAD + ".qualp");
+    vec<int64_t> bci;
+    BinaryReader::readFile(HEAD + ".bci", &bci);
+    vec<int32_t> bc(bci.back(), -1);
+    for (int b = 0; b < bci.isize() - 1; b++)
+        for (int64_t j = bci[b]; j < bci[b + 1]; j++) bc[j] = b;
+
+    HyperBasevector hbv;
+    ReadPathVec paths;
+    auto t0 = std::chrono::steady_clock::now();
+    buildReadQGraph48(OUT, "/reads", "", reads, quals, False, False,
+                      MIN_QUAL, MIN_FREQ, 0, MIN_BC, &bc, .75, 0, "",
+                      True, False, &hbv, PATHS ? &paths : nullptr, 0.9, False);
+    auto t1 = std::chrono::steady_clock::now();
+    BinaryWriter::writeFile(OUT + "/a.hbv", hbv);
+    std::cout << "ORACLE_SECONDS "
+              << std::chrono::duration<double>(t1 - t0).count() << std::endl;
+    return 0;
+}

@@ -1,0 +1,203 @@
+"""Seeded synthetic linked-read generator.
+
+Test/bench infrastructure for the hot path: produces the inputs the reference's
+``buildReadQGraph48`` consumes (reads as base codes, Phred quals, per-read barcode
+ordinal in ``.bci`` order) plus, for the small configs, the 9-line barcode-sorted
+pseudo-FASTQ that the reference's own ``ParseBarcodedFastqs`` ingests
+(10X/ParseBarcodedFastqs.cc:3-9,56-146).
+
+Model: haplotype A = i.i.d. uniform ACGT of length G; haplotype B = A with one SNP
+per 1000 bp window; pairs drawn uniformly (haplotype, start, insert U[300,500),
+strand flip p=0.5); R1 = first L bases of the fragment, R2 = first L bases of its
+reverse complement; substitution errors with probability 0.001 + 0.02 (j/L)^3 at
+read position j, an erroneous base gets Q in {2,12,20}, a correct one Q37 (5 % Q30);
+each pair gets a uniform barcode id, ``unbarcoded_frac`` of the pairs carry no
+barcode.  Record order = unbarcoded pairs first, then pairs sorted by barcode, which
+is the order ParseBarcodedFastqs writes (``:284-303``).
+"""
+from __future__ import annotations
+
+import gzip
+import numpy as np
+
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def make_genome(G: int, seed: int):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    hap_a = rng.integers(0, 4, size=G, dtype=np.uint8)
+    hap_b = hap_a.copy()
+    nwin = G // 1000
+    if nwin:
+        pos = np.arange(nwin, dtype=np.int64) * 1000 + rng.integers(0, 1000, size=nwin)
+        hap_b[pos] = (hap_a[pos] + rng.integers(1, 4, size=nwin, dtype=np.uint8)) & 3
+    return hap_a, hap_b
+
+
+def make_reads(G: int, n_pairs: int, n_bc: int, seed: int, L: int = 150,
+               unbarcoded_frac: float = 0.02, chunk: int = 200_000):
+    """Returns (bases[n_reads,L] u8 codes, quals[n_reads,L] u8, bc[n_reads] i32 ordinal,
+    bc_ids[n_reads] i64 raw barcode id or -1)."""
+    hap = np.stack(make_genome(G, seed))
+    rng = np.random.Generator(np.random.Philox(key=seed + 1))
+    bcid = rng.integers(0, n_bc, size=n_pairs, dtype=np.int64)
+    unb = rng.random(n_pairs) < unbarcoded_frac
+    bcid[unb] = -1
+    order = np.argsort(bcid, kind="stable")          # -1 (unbarcoded) first, then by barcode
+    bcid = bcid[order]
+    # dense ordinal: 0 = unbarcoded, 1.. in order of first appearance (ParseBarcodedFastqs.cc:107-114)
+    new = np.ones(n_pairs, dtype=bool)
+    new[1:] = bcid[1:] != bcid[:-1]
+    new &= bcid >= 0
+    ordinal = np.cumsum(new).astype(np.int32)
+    ordinal[bcid < 0] = 0
+
+    n_reads = 2 * n_pairs
+    bases = np.empty((n_reads, L), dtype=np.uint8)
+    quals = np.empty((n_reads, L), dtype=np.uint8)
+    perr = (0.001 + 0.02 * (np.arange(L) / L) ** 3).astype(np.float32)
+    ar = np.arange(L, dtype=np.int64)
+    for c0 in range(0, n_pairs, chunk):
+        c1 = min(n_pairs, c0 + chunk)
+        m = c1 - c0
+        crng = np.random.Generator(np.random.Philox(key=[seed + 2, c0]))
+        h = crng.integers(0, 2, size=m)
+        ins = crng.integers(300, 500, size=m)
+        start = (crng.random(m) * (G - ins)).astype(np.int64)
+        flip = crng.random(m) < 0.5
+        fwd = hap[h[:, None], start[:, None] + ar[None, :]]
+        rev = 3 - hap[h[:, None], (start + ins - 1)[:, None] - ar[None, :]]
+        r1 = np.where(flip[:, None], rev, fwd)
+        r2 = np.where(flip[:, None], fwd, rev)
+        blk = np.empty((2 * m, L), dtype=np.uint8)
+        blk[0::2] = r1
+        blk[1::2] = r2
+        err = crng.random((2 * m, L), dtype=np.float32) < perr[None, :]
+        sub = crng.integers(1, 4, size=(2 * m, L), dtype=np.uint8)
+        blk = np.where(err, (blk + sub) & 3, blk).astype(np.uint8)
+        q = np.where(crng.random((2 * m, L), dtype=np.float32) < 0.05, 30, 37).astype(np.uint8)
+        qerr = np.array([2, 12, 20], dtype=np.uint8)[crng.integers(0, 3, size=(2 * m, L))]
+        q = np.where(err, qerr, q).astype(np.uint8)
+        bases[2 * c0:2 * c1] = blk
+        quals[2 * c0:2 * c1] = q
+    bc = np.repeat(ordinal, 2)
+    return bases, quals, bc, np.repeat(bcid, 2)
+
+
+def barcode_string(i: int) -> str:
+    s = []
+    for _ in range(16):
+        s.append("ACGT"[i & 3])
+        i >>= 2
+    return "".join(reversed(s))
+
+
+def write_fasth(path: str, bases, quals, bc_ids):
+    """9-line barcode-sorted pseudo-FASTQ (ParseBarcodedFastqs.cc:3-9)."""
+    n_pairs = bases.shape[0] // 2
+    L = bases.shape[1]
+    with gzip.open(path, "wb", compresslevel=1) as f:
+        bq = b"I" * 16
+        for p in range(n_pairs):
+            r1 = BASES[bases[2 * p]].tobytes()
+            r2 = BASES[bases[2 * p + 1]].tobytes()
+            q1 = (quals[2 * p] + 33).astype(np.uint8).tobytes()
+            q2 = (quals[2 * p + 1] + 33).astype(np.uint8).tobytes()
+            b = bc_ids[2 * p]
+            bcs = (barcode_string(int(b)) + "-1").encode() if b >= 0 else b"NNNNNNNNNNNNNNNN"
+            f.write(b"@p%d\n" % p + r1 + b"\n" + q1 + b"\n" + r2 + b"\n" + q2 + b"\n" +
+                    bcs + b"\n" + bq + b"\nACGTACGT\nIIIIIIII\n")
+
+
+CONFIGS = {
+    # name: (G, pairs, nBC, seed)   -- SURVEY.md §8(d) table
+    "tiny": (5_000, 1_000, 50, 7),
+    "C1": (50_000, 10_000, 500, 1234),
+    "mid": (2_000_000, 373_333, 50_000, 20261017),
+    "C2": (63_000_000, 4_000_000, 1_000_000, 20261017),
+}
+
+
+def make_stress(seed: int, n_pairs: int = 6000, n_bc: int = 40):
+    """Small adversarial data set for parity tests: repeats, inverted repeats (even-length
+    palindromes), homopolymers, tandem repeats, a circular contig (perfect circle of
+    k-mers), ragged read lengths (20..150), low-quality tails and unbarcoded reads.
+    Returns ragged (bases, quals, off, bc, bc_ids) with reads as concatenated codes."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+
+    def rnd(n):
+        return rng.integers(0, 4, size=n, dtype=np.uint8)
+
+    def rc(s):
+        return (3 - s[::-1]).astype(np.uint8)
+
+    unit = rnd(700)
+    pal_half = rnd(60)
+    contigs = []
+    g = [rnd(3000), unit, rnd(500), unit, rnd(800), rc(unit), rnd(400),
+         pal_half, rc(pal_half), rnd(600),                      # exact even palindrome of 120
+         np.zeros(90, np.uint8), rnd(300), np.full(70, 3, np.uint8), rnd(300),   # homopolymers
+         np.tile(rnd(2), 60), rnd(300), np.tile(rnd(7), 30), rnd(300), np.tile(rnd(31), 6), rnd(900),
+         np.tile(rnd(48), 4), rnd(500), np.tile(rnd(24), 8), rnd(1000)]
+    contigs.append(np.concatenate(g))
+    circ = rnd(400)
+    contigs.append(np.concatenate([circ, circ, circ]))           # reads only ever see the circle
+    contigs.append(np.concatenate([np.tile(rnd(5), 80)]))        # pure tandem repeat contig
+    small = rnd(130)
+    contigs.append(small)                                        # contig shorter than a read
+    lens = np.array([len(c) for c in contigs])
+    weights = np.array([0.75, 0.15, 0.05, 0.05])
+    bases, quals = [], []
+    bcid = rng.integers(0, n_bc, size=n_pairs, dtype=np.int64)
+    bcid[rng.random(n_pairs) < 0.05] = -1
+    order = np.argsort(bcid, kind="stable")
+    bcid = bcid[order]
+    new = np.ones(n_pairs, dtype=bool)
+    new[1:] = bcid[1:] != bcid[:-1]
+    new &= bcid >= 0
+    ordinal = np.cumsum(new).astype(np.int32)
+    ordinal[bcid < 0] = 0
+    for p in range(n_pairs):
+        ci = rng.choice(4, p=weights)
+        c = contigs[ci]
+        for _ in range(2):
+            L = int(rng.choice([150, 150, 150, 150, 120, 97, 60, 49, 48, 47, 20]))
+            L = min(L, len(c))
+            if ci == 1:
+                s = int(rng.integers(0, 400))
+            else:
+                s = int(rng.integers(0, len(c) - L + 1))
+            r = c[s:s + L].copy()
+            if rng.random() < 0.5:
+                r = rc(r)
+            perr = 0.002 + 0.03 * (np.arange(L) / 150.0) ** 3
+            err = rng.random(L) < (perr if ci != 1 else 0.0)   # circle contig stays error-free
+            r[err] = (r[err] + rng.integers(1, 4, size=int(err.sum()))) & 3
+            q = np.where(rng.random(L) < 0.05, 30, 37).astype(np.uint8)
+            q[err] = np.array([2, 12, 20], dtype=np.uint8)[rng.integers(0, 3, size=int(err.sum()))]
+            if rng.random() < 0.15:                      # low-quality tail
+                t = int(rng.integers(1, L + 1))
+                q[L - t:] = rng.integers(2, 7, size=t)
+            if rng.random() < 0.05:                      # low-quality spot in the middle
+                q[int(rng.integers(0, L))] = 3
+            bases.append(r.astype(np.uint8))
+            quals.append(q)
+    off = np.zeros(len(bases) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(b) for b in bases])
+    return (np.concatenate(bases), np.concatenate(quals), off, np.repeat(ordinal, 2), np.repeat(bcid, 2))
+
+
+def write_fasth_ragged(path: str, bases, quals, off, bc_ids):
+    n_pairs = (len(off) - 1) // 2
+    with gzip.open(path, "wb", compresslevel=1) as f:
+        bq = b"I" * 16
+        for p in range(n_pairs):
+            a0, a1, a2 = int(off[2 * p]), int(off[2 * p + 1]), int(off[2 * p + 2])
+            r1 = BASES[bases[a0:a1]].tobytes()
+            r2 = BASES[bases[a1:a2]].tobytes()
+            q1 = (quals[a0:a1] + 33).astype(np.uint8).tobytes()
+            q2 = (quals[a1:a2] + 33).astype(np.uint8).tobytes()
+            b = bc_ids[2 * p]
+            bcs = (barcode_string(int(b)) + "-1").encode() if b >= 0 else b"NNNNNNNNNNNNNNNN"
+            f.write(b"@p%d\n" % p + r1 + b"\n" + q1 + b"\n" + r2 + b"\n" + q2 + b"\n" +
+                    bcs + b"\n" + bq + b"\nACGTACGT\nIIIIIIII\n")
