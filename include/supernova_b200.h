@@ -1,0 +1,149 @@
+/*
+ * supernova_b200.h -- C ABI of the B200-native k-mer count -> unipath graph
+ * (HyperBasevector) -> ReadPath hot path.
+ *
+ * Drop-in boundary (boundary B2): these entry points sit directly
+ * under the reference's C++ call
+ *     buildReadQGraph48(work_dir, read_head, "", reads, quals, False, False, minQual,
+ *                       minFreq, ignBcBelow, minBC, &bc, .75, 0, "", True, False,
+ *                       &hbv, &paths)
+ *   lib/assembly/src/paths/long/BuildReadQGraph48.h:28-40, called from
+ *   StageBuildGraph, lib/assembly/src/10X/runstages/RunStages.cc:404-406
+ * and replace what it does between "reads/quals/barcodes in memory" and
+ * "a.hbv + tmp.paths on disk".  Plain pointers and sizes only; every buffer handed
+ * in is HOST memory in the reference's own in-memory/on-disk layout; every function
+ * returns 0 on success or a negative sn_status and leaves a message in
+ * sn_last_error().  No exceptions cross the ABI.  There is no CPU fallback: without a
+ * CUDA device sn_ctx_create fails.
+ */
+#ifndef SUPERNOVA_B200_H_
+#define SUPERNOVA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sn_ctx sn_ctx;
+
+enum sn_status {
+    SN_OK = 0,
+    SN_ERR_CUDA = -1,        /* a CUDA call failed (message has the call and the error) */
+    SN_ERR_ARG = -2,         /* invalid argument / unsupported configuration            */
+    SN_ERR_STATE = -3,       /* stage called out of order                               */
+    SN_ERR_IO = -4,          /* file could not be read / written                        */
+    SN_ERR_DATA = -5         /* inconsistent input (e.g. PQVec length != read length)   */
+};
+
+/* Thresholds of Kmerizer / GoodLenTailFinder; the values StageBuildGraph passes are
+ * K=48 (fixed), minQual=7, minFreq=3, minBC=2, ignBcBelow=0
+ * (10X/DF.cc:138-141, 10X/runstages/RunStages.cc:405). */
+typedef struct sn_params {
+    uint32_t min_qual;
+    uint32_t min_freq;
+    uint32_t min_bc;         /* 0, 1 or 2 */
+    int64_t  ign_bc_below;   /* reads with id below this count as barcode -1 */
+} sn_params;
+
+/* k-mer record of sn_get_kmers == the {KMer<48>, KDef} part of a kmers.kvec entry
+ * (kmers/ReadPather.h:100-150): w[] MSB-first 2-bit k-mer, count_ctx = count:24 | ctx<<24
+ * with ctx the context BEFORE recomputeAdjacencies.  Sorted by k-mer. */
+typedef struct sn_kmer_rec { uint32_t w[3]; uint32_t count_ctx; } sn_kmer_rec;
+
+typedef struct sn_counts {
+    uint64_t n_reads, n_bases;
+    uint64_t n_kmer_occurrences;   /* records emitted by Kmerizer::map                */
+    uint64_t n_kmers_distinct;     /* before the frequency / barcode filter           */
+    uint64_t n_kmers;              /* dictionary size (pVec->size())                  */
+    uint64_t n_edges;              /* unipath edges (before HBV doubling)             */
+    uint64_t n_edge_bases;
+    uint64_t n_hbv_vertices, n_hbv_edges;
+    uint64_t n_path_edges;         /* total ReadPath entries                          */
+} sn_counts;
+
+int  sn_ctx_create(sn_ctx** out, int device);
+void sn_ctx_destroy(sn_ctx* ctx);
+const char* sn_last_error(const sn_ctx* ctx);       /* ctx may be NULL: last create error */
+int  sn_device_count(void);
+
+/* ---- ingest: replaces vecbvec reads / VecPQVec quals / vec<int32_t> bc ------------ */
+/* bases   : the variable-data block of a .fastb (feudal/FieldVec.h:596-598): 2 bits per
+ *           base, 4 bases per byte LSB first, each read starting on a byte boundary.
+ * base_off: n_reads+1 byte offsets into bases.   len: bases per read.
+ * pq      : the variable-data block of a .qualp (PQVec blocks, feudal/PQVec.cc:87-127).
+ * pq_off  : n_reads+1 byte offsets into pq.
+ * bc      : per-read barcode ordinal as expanded in 10X/DF.cc:464-469, or NULL.        */
+int sn_load_reads(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
+                  const uint32_t* len, const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc);
+/* same with one unpacked Phred byte per base (qual_off = n_reads+1 element offsets)   */
+int sn_load_reads_q8(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
+                     const uint32_t* len, const uint8_t* quals, const uint64_t* qual_off, const int32_t* bc);
+/* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */
+int sn_load_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
+
+/* ---- stages (must run in this order) -------------------------------------------------- */
+/* createDict up to the KmerVec (BuildReadQGraph48.cc:218-292): good lengths, k-mer records,
+ * sort, count, filter.                                                                  */
+int sn_count_kmers(sn_ctx* ctx, const sn_params* params);
+/* recomputeAdjacencies + buildEdges (BuildReadQGraph48.cc:320-321, 514-541)             */
+int sn_build_edges(sn_ctx* ctx);
+/* buildHBVFromEdges + Involution (paths/long/HBVFromEdges.cc:244-296)                   */
+int sn_build_hbv(sn_ctx* ctx);
+/* pathReads with useNewAligner=True (BuildReadQGraph48.cc:1440-1469)                    */
+int sn_path_reads(sn_ctx* ctx);
+
+/* ---- results ------------------------------------------------------------------------- */
+int sn_get_counts(const sn_ctx* ctx, sn_counts* out);
+int sn_get_good_lengths(sn_ctx* ctx, uint32_t* out /* n_reads */);
+int sn_get_kmers(sn_ctx* ctx, sn_kmer_rec* out /* n_kmers */);
+/* dictionary after the graph stages: pruned context, unipath id and offset per k-mer      */
+int sn_get_kmer_graph_info(sn_ctx* ctx, uint8_t* ctx_pruned, uint32_t* edge, uint32_t* offset);
+/* unipath edges: len[n_edges], byte offsets off[n_edges+1], packed bases (fastb layout)   */
+int sn_get_edges(sn_ctx* ctx, uint32_t* len, uint64_t* off, uint8_t* packed /* off[n_edges] bytes */);
+int sn_get_edges_bytes(const sn_ctx* ctx, uint64_t* packed_bytes);
+/* HBV: CSR adjacency.  from_start/to_start: n_vertices+1; from_v/from_e/to_v/to_e: n_hbv_edges */
+int sn_get_hbv(sn_ctx* ctx, uint32_t* from_start, int32_t* from_v, int32_t* from_e,
+               uint32_t* to_start, int32_t* to_v, int32_t* to_e,
+               int32_t* fwd_xlat /* n_edges */, int32_t* rev_xlat /* n_edges */, int32_t* inv /* n_hbv_edges */);
+/* ReadPaths: offset[n_reads], path_off[n_reads+1], edges[n_path_edges]                    */
+int sn_get_paths(sn_ctx* ctx, int32_t* offset, uint64_t* path_off, int32_t* edges);
+
+/* ---- files in the reference's formats -------------------------------------------------- */
+int sn_write_hbv(sn_ctx* ctx, const char* path);             /* a.hbv                              */
+int sn_write_paths(sn_ctx* ctx, const char* path);           /* tmp.paths (feudal ReadPathVec)     */
+int sn_write_edges_bv(sn_ctx* ctx, const char* path);        /* vec<basevector> (== MSPEDGES file) */
+int sn_write_inv(sn_ctx* ctx, const char* path);             /* a.inv  (vec<int>)                  */
+int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_kmer_count.json    */
+
+/* One call == buildReadQGraph48: the four stages, then work_dir/a.hbv (when write_hbv),
+ * work_dir/tmp.paths (when with_paths) and work_dir/stats/histogram_kmer_count.json.      */
+int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* params, int with_paths, int write_files);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+/* Device time (CUDA events on the context's stream) of the most recent run of a stage or
+ * kernel group, in milliseconds; names: "goodlen","extract","sort","reduce","index","prune",
+ * "edges","path","h2d","hbv_host".  Returns a negative value for an unknown name.          */
+double sn_stage_ms(const sn_ctx* ctx, const char* name);
+/* number of kernel launches issued by this context so far */
+uint64_t sn_kernel_launches(const sn_ctx* ctx);
+
+/* ---- host-side format helpers (no device needed) ------------------------------------------ */
+/* PQVec codec; out must hold at least 2*n+8 bytes; returns bytes written */
+uint64_t sn_pqvec_encode(const uint8_t* quals, uint32_t n, uint8_t* out);
+uint32_t sn_pqvec_decode(const uint8_t* pq, uint64_t pq_bytes, uint8_t* out, uint32_t cap);
+/* Pack n_reads reads given as one base code (0..3) per byte into the .fastb variable-data
+ * layout and PQVec-encode their quals with `threads` host threads.  Buffers are malloc'ed
+ * and owned by the caller (release with sn_free). */
+int sn_pack_reads(uint64_t n_reads, const uint8_t* codes, const uint8_t* quals, const uint64_t* off, int threads,
+                  uint8_t** bases, uint64_t** base_off, uint32_t** len, uint8_t** pq, uint64_t** pq_off);
+void sn_free(void* p);
+/* write the reference's input files from the in-memory layout above */
+int sn_write_read_files(const char* fastb, const char* qualp, const char* bci, uint64_t n_reads,
+                        const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,
+                        const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERNOVA_B200_H_ */

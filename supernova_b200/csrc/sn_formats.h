@@ -1,0 +1,49 @@
+// sn_formats.h -- host-side readers/writers for the on-disk formats the hot path
+// must keep: feudal .fastb / .qualp / ReadPathVec, BINWRITE .bci,
+// vec<basevector>, a.hbv.  New C++17 code; byte layouts verified against files
+// written by the reference's own binaries (tests/test_formats.py).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace snf {
+
+struct Fastb {                       // feudal/FeudalControlBlock.h:159-165, feudal/FieldVec.h:586-607
+    std::vector<uint8_t> var;        // packed bases, 4 per byte, each read byte aligned
+    std::vector<uint64_t> off;       // n+1 byte offsets into var
+    std::vector<uint32_t> len;       // bases per read
+};
+struct Qualp {                       // feudal/PQVec.cc:87-127
+    std::vector<uint8_t> var;        // PQVec blocks, 0-terminated per read
+    std::vector<uint64_t> off;       // n+1
+};
+
+bool read_fastb(const std::string& path, Fastb& out, std::string& err);
+bool read_qualp(const std::string& path, Qualp& out, std::string& err);
+bool read_bci(const std::string& path, std::vector<int64_t>& bci, std::string& err);
+bool write_fastb(const std::string& path, const Fastb& in, std::string& err);
+bool write_qualp(const std::string& path, const Qualp& in, std::string& err);
+bool write_bci(const std::string& path, const std::vector<int64_t>& bci, std::string& err);
+
+// PQVecEncoder (feudal/PQVec.cc:17-127): appends the encoding of q[0..n) to out.
+void pqvec_encode(const uint8_t* q, uint32_t n, std::vector<uint8_t>& out);
+// decoder (feudal/PQVec.cc:129-187); returns the number of quals written
+uint32_t pqvec_decode(const uint8_t* p, const uint8_t* pend, uint8_t* out, uint32_t cap);
+// expand a .bci barcode index to the per-read ordinal DF passes down (10X/DF.cc:464-469)
+void expand_bci(const std::vector<int64_t>& bci, std::vector<int32_t>& bc);
+
+// vec<basevector> (BINWRITE; feudal/BinaryStream.h:486-493, feudal/FieldVec.h:596-598)
+bool write_bv(const std::string& path, const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n, std::string& err);
+bool read_bv(const std::string& path, Fastb& out, std::string& err);
+
+// a.hbv (paths/HyperBasevector.cc:121-125, graph/DigraphTemplate.h:3091-3097)
+bool write_hbv(const std::string& path, int32_t K, const std::vector<std::vector<int32_t>>& from,
+               const std::vector<std::vector<int32_t>>& from_eo, const std::vector<std::vector<int32_t>>& to_eo,
+               const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges, std::string& err);
+// feudal ReadPathVec (paths/long/ReadPath.h:61-63, feudal/FeudalFileWriter.cc:100-121)
+bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err);
+// vec<int> (a.inv)
+bool write_vec_int(const std::string& path, const std::vector<int32_t>& v, std::string& err);
+
+}  // namespace snf

@@ -1,0 +1,413 @@
+// sn_kernels.cuh -- the CUDA kernels of the hot path (sm_100a), in pipeline order:
+//   a1  k_pqvec_goodlen / k_q8_goodlen   PQVec decode + good-length scan
+//   a2  k_extract                         canonical (k,k+1)-mer records from 2-bit reads
+//   a4  radix_sort_kmers (sn_prims.cuh)   128-bit records by 96-bit k-mer
+//   a5  k_reduce                          run-length count / ctx OR / barcode rule / filter
+//   a6  k_build_index, k_prune            dictionary prefix index, adjacency prune
+//   a7  k_classify, k_walk_count, k_circle_count, k_walk_emit, k_fix_offsets, k_pack_edges
+//   a10-a12 k_path_reads                  ReadPath threading + extension
+// Reference citations live with the per-item logic in sn_kmer.cuh / sn_graph.cuh /
+// sn_path.cuh; this file is thread mapping, staging and memory layout.
+#pragma once
+#include "sn_prims.cuh"
+#include "sn_kmer.cuh"
+#include "sn_graph.cuh"
+#include "sn_path.cuh"
+
+namespace sn {
+
+// ---------------------------------------------------------------------------
+// a1. PQVec decode (feudal/PQVec.cc:129-187 block format: [nQs u8][nBits:3|minQ:6]
+// [nQs x nBits packed, LSB first] ... 0) fused with GoodLenTailFinder
+// (BuildReadQGraph48.cc:65-89).  One read per thread; quals are written once as u8
+// for the pathing stage.  goodLen = right end of the right-most run of >= K quals
+// >= minQual (what the backwards scan of the reference finds first).
+// Also accumulates the number of k-mer occurrences Kmerizer::map will emit.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
+                                                       const uint32_t* __restrict__ len, const uint64_t* __restrict__ qoff,
+                                                       uint8_t* __restrict__ quals, uint32_t min_qual,
+                                                       uint32_t* __restrict__ goodlen, unsigned long long* occ_total, uint32_t* bad_reads)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t occ = 0;
+    if (r < n_reads) {
+        const uint8_t* p = pq + pq_off[r];
+        const uint8_t* pend = pq + pq_off[r + 1];
+        uint8_t* out = quals + qoff[r];
+        uint32_t L = len[r], i = 0, run = 0, gl = 0;
+        while (p < pend) {
+            uint32_t nq = *p++;
+            if (!nq) break;
+            uint32_t b0 = *p++;
+            uint32_t nbits = b0 & 7u, minq = b0 >> 3;
+            uint64_t acc = *p++;
+            minq |= (uint32_t)(acc & 1u) << 5; acc >>= 1;
+            uint32_t have = 7;
+            uint32_t mask = (1u << nbits) - 1u;
+            for (uint32_t k = 0; k < nq; ++k) {
+                uint32_t q = minq;
+                if (nbits) {
+                    if (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
+                    q += (uint32_t)acc & mask; acc >>= nbits; have -= nbits;
+                }
+                if (i < L) {
+                    out[i] = (uint8_t)q;
+                    run = q >= min_qual ? run + 1 : 0;
+                    ++i;
+                    if (run >= SN_K) gl = i;
+                }
+            }
+        }
+        if (i != L) atomicAdd(bad_reads, 1u);      // PQVec length disagrees with the fastb length
+        goodlen[r] = gl;
+        occ = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
+    }
+    // block reduce, one atomic per block
+    __shared__ uint32_t sm[8];
+    for (int o = 16; o > 0; o >>= 1) occ += __shfl_down_sync(SN_FULL, occ, o);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = occ;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; if (t) atomicAdd(occ_total, (unsigned long long)t); }
+}
+
+// same, for callers that already hold one u8 per base
+__global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
+                                                    const uint32_t* __restrict__ len, uint32_t min_qual,
+                                                    uint32_t* __restrict__ goodlen, unsigned long long* occ_total)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t occ = 0;
+    if (r < n_reads) {
+        const uint8_t* q = quals + qoff[r];
+        uint32_t L = len[r], run = 0, gl = 0;
+        for (uint32_t i = 0; i < L; ++i) { run = q[i] >= min_qual ? run + 1 : 0; if (run >= SN_K) gl = i + 1; }
+        goodlen[r] = gl;
+        occ = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
+    }
+    __shared__ uint32_t sm[8];
+    for (int o = 16; o > 0; o >>= 1) occ += __shfl_down_sync(SN_FULL, occ, o);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = occ;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; if (t) atomicAdd(occ_total, (unsigned long long)t); }
+}
+
+// ---------------------------------------------------------------------------
+// a2. Kmerizer::map (BuildReadQGraph48.cc:155-172).  A CTA stages the packed bases of
+// EX_READS consecutive reads in shared memory with 16-byte loads, then its threads walk
+// the tile's k-mer occurrences in order: occurrence x of the tile -> thread x % 256, so a
+// warp writes 32 consecutive 16-byte records (512 B, fully coalesced).  The output
+// range of the tile is reserved with one atomicAdd per CTA (record order does not
+// matter: the sort follows and the reduction is order independent).
+// record = {w0,w1,w2 of the canonical k-mer, ctx<<24 | bc24} ; bc24 = 0xFFFFFF for "-1".
+// ---------------------------------------------------------------------------
+#define SN_EX_READS 128
+#define SN_EX_BYTES (SN_EX_READS * (SN_MAX_READ_LEN / 4) + 48)
+
+__global__ void __launch_bounds__(256) k_extract(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+                                                 const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc,
+                                                 int64_t ign_bc_below, uint4* __restrict__ out, unsigned long long* cursor)
+{
+    __shared__ __align__(16) uint8_t sb[SN_EX_BYTES];
+    __shared__ uint32_t pref[SN_EX_READS + 1];
+    __shared__ uint32_t s_gl[SN_EX_READS];
+    __shared__ uint32_t s_rel[SN_EX_READS];
+    __shared__ uint32_t s_bc[SN_EX_READS];
+    __shared__ uint32_t wsum[8];
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.x * SN_EX_READS;
+    const uint32_t nr = (uint32_t)min((uint64_t)SN_EX_READS, n_reads - r0);
+    const uint64_t lo = boff[r0], hi = boff[r0 + nr];
+    const uint64_t lo_al = lo & ~15ull;
+    const uint32_t shift = (uint32_t)(lo - lo_al);
+    // stage packed bases (16-byte vector loads; the allocation is padded)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(bases + lo_al);
+        uint4* dst = reinterpret_cast<uint4*>(sb);
+        uint32_t nv = (uint32_t)((hi - lo_al + 13 + 15) >> 4);      // +13: kmer_from_packed may touch 13 bytes
+        for (uint32_t i = tid; i < nv; i += 256) dst[i] = src[i];
+    }
+    // per-read counts and their exclusive prefix (128 reads: threads 0..127)
+    uint32_t cnt = 0;
+    if (tid < nr) {
+        uint32_t gl = goodlen[r0 + tid];
+        s_gl[tid] = gl;
+        s_rel[tid] = (uint32_t)(boff[r0 + tid] - lo) + shift;
+        int32_t b = -1;
+        if (bc && (int64_t)(r0 + tid) >= ign_bc_below) b = bc[r0 + tid];
+        s_bc[tid] = b < 0 ? 0xFFFFFFu : (uint32_t)b;
+        cnt = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
+    }
+    {
+        uint32_t x = cnt, lane = tid & 31u, w = tid >> 5;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (uint32_t k = 0; k < w; ++k) wb += wsum[k];
+        if (tid < SN_EX_READS) pref[tid] = wb + x - cnt;
+        if (tid == SN_EX_READS - 1) pref[SN_EX_READS] = wb + x;
+    }
+    __syncthreads();
+    const uint32_t T = pref[SN_EX_READS];
+    if (tid == 0) s_base = T ? atomicAdd(cursor, (unsigned long long)T) : 0ull;
+    __syncthreads();
+    const uint64_t base = s_base;
+    for (uint32_t x = tid; x < T; x += 256) {
+        // read of occurrence x: largest rr with pref[rr] <= x
+        uint32_t a = 0, b = SN_EX_READS;
+        while (b - a > 1) { uint32_t m = (a + b) >> 1; if (pref[m] <= x) a = m; else b = m; }
+        const uint32_t rr = a, i = x - pref[rr], gl = s_gl[rr];
+        const uint8_t* rp = sb + s_rel[rr];
+        Kmer k = kmer_from_packed(rp, i);
+        uint32_t ctx = 0;
+        if (i > 0) ctx |= 16u << packed_base(rp, i - 1);
+        if (i + SN_K < gl) ctx |= 1u << packed_base(rp, i + SN_K);
+        Kmer rc;
+        if (kmer_form(k, &rc) == REV) { k = rc; ctx = ctx_rc(ctx); }
+        out[base + x] = make_uint4(k.w0, k.w1, k.w2, (ctx << 24) | s_bc[rr]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// a5. Kmerizer::reduce / summarizeEntries / areIgnoredBarcodes / areEnoughBarcodes
+// (BuildReadQGraph48.cc:91-137,174-181) over the sorted records, fused with the
+// ordered compaction of the surviving k-mers into the dictionary (tile look-back).
+// The head record of every run walks its run: count (saturating 2^24-1), OR of
+// contexts, min/max barcode > 0 (>= 2 distinct <=> min != max), "ignored" flag.
+// ---------------------------------------------------------------------------
+#define SN_RD_THREADS 256
+#define SN_RD_ITEMS 8
+#define SN_RD_TILE (SN_RD_THREADS * SN_RD_ITEMS)
+
+__device__ __forceinline__ bool same_kmer(const uint4& a, const uint4& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+__global__ void __launch_bounds__(SN_RD_THREADS) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
+                                                          DictEntry* __restrict__ out, uint64_t* status, uint32_t* tile_counter,
+                                                          uint32_t* n_out, unsigned long long* n_distinct)
+{
+    __shared__ uint32_t words[SN_RD_ITEMS * 8];
+    __shared__ uint32_t wpref[SN_RD_ITEMS * 8 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tbase = (uint64_t)tile * SN_RD_TILE;
+    uint4 kk[SN_RD_ITEMS]; uint32_t cc[SN_RD_ITEMS]; bool ok[SN_RD_ITEMS];
+    uint32_t heads = 0;
+#pragma unroll
+    for (int j = 0; j < SN_RD_ITEMS; ++j) {
+        uint64_t idx = tbase + (uint64_t)j * SN_RD_THREADS + tid;
+        ok[j] = false; cc[j] = 0;
+        if (idx < n) {
+            uint4 k = keys[idx];
+            kk[j] = k;
+            bool head = idx == 0 || !same_kmer(keys[idx - 1], k);
+            if (head) {
+                ++heads;
+                uint32_t count = 0, ctx = 0, minbc = 0xFFFFFFFFu, maxbc = 0; bool ign = false;
+                uint64_t p = idx; uint4 r = k;
+                for (;;) {
+                    ++count; ctx |= r.w >> 24;
+                    uint32_t b = r.w & 0xFFFFFFu;
+                    if (b == 0xFFFFFFu) ign = true;
+                    else if (b) { minbc = min(minbc, b); maxbc = max(maxbc, b); }
+                    if (++p >= n) break;
+                    r = keys[p];
+                    if (!same_kmer(r, k)) break;
+                }
+                bool enough = min_bc == 0 || (min_bc == 1 ? maxbc != 0 : (maxbc != 0 && minbc != maxbc));
+                bool bc_test = !has_bc || ign || enough;
+                ok[j] = count >= min_freq && bc_test;
+                cc[j] = min(count, 0xFFFFFFu) | (ctx << 24);
+            }
+        }
+        uint32_t bal = __ballot_sync(SN_FULL, ok[j]);
+        if (lane == 0) words[j * 8 + warp] = bal;
+    }
+    // distinct k-mer count (stat only)
+    for (int o = 16; o > 0; o >>= 1) heads += __shfl_down_sync(SN_FULL, heads, o);
+    if (lane == 0 && heads) atomicAdd(n_distinct, (unsigned long long)heads);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+        for (int i = 0; i < SN_RD_ITEMS * 8; ++i) { wpref[i] = s; s += __popc(words[i]); }
+        wpref[SN_RD_ITEMS * 8] = s;
+        uint64_t prev = tile_lookback(status, 1, 0, tile, s);
+        s_base = prev;
+        if (tbase + SN_RD_TILE >= n) *n_out = (uint32_t)(prev + s);      // last tile knows the total
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
+#pragma unroll
+    for (int j = 0; j < SN_RD_ITEMS; ++j) {
+        if (ok[j]) {
+            uint32_t w = words[j * 8 + warp];
+            uint64_t pos = base + wpref[j * 8 + warp] + __popc(w & lanemask_lt());
+            DictEntry e;
+            e.w0 = kk[j].x; e.w1 = kk[j].y; e.w2 = kk[j].z; e.cc = cc[j];
+            e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = cc[j] >> 24; e.pad = 0;
+            out[pos] = e;
+        }
+    }
+}
+// ---------------------------------------------------------------------------
+// a6. dictionary prefix index + recomputeAdjacencies
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_index(const DictEntry* __restrict__ tab, uint32_t n, uint32_t* __restrict__ idx)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > (1u << SN_IDX_BITS)) return;
+    if (b == (1u << SN_IDX_BITS)) { idx[b] = n; return; }
+    uint32_t key = b << (32 - SN_IDX_BITS);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (tab[mid].w0 < key) lo = mid + 1; else hi = mid; }
+    idx[b] = lo;
+}
+__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    tab[i].ctx = prune_ctx(d, i);
+}
+
+// ---------------------------------------------------------------------------
+// a7. unipath edges.  own_n[i] = number of k-mers of the edge that entry i owns
+// (0 = owns none).  Singles own themselves; an edge with >= 2 k-mers is walked from
+// both of its end entries and owned by the end with the smaller index; a circle is
+// owned by its smallest entry.
+// ---------------------------------------------------------------------------
+#define SN_T_CIRCLE 4
+__global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
+                                                  uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    int t = classify_entry(d, i);
+    etype[i] = (uint8_t)t;
+    own_n[i] = t == T_SINGLE ? 1u : 0u;
+    is_end[i] = (t == T_END_DOWN || t == T_END_UP) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_scatter_flagged(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ list)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) list[pos[i]] = i;
+}
+__global__ void __launch_bounds__(128) k_walk_count(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
+                                                    const uint32_t* __restrict__ ends, uint32_t n_ends, const uint8_t* __restrict__ etype,
+                                                    uint32_t* __restrict__ own_n, uint8_t* __restrict__ visited)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ends) return;
+    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    uint32_t i = ends[t], last = i;
+    visited[i] = 1;
+    uint32_t nk = walk_edge(d, i, etype[i], [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
+    if (i <= last) own_n[i] = nk;       // the other end walks the same edge; the smaller index owns it
+}
+__global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
+                                                     uint8_t* __restrict__ etype, const uint8_t* __restrict__ visited, uint32_t* __restrict__ own_n,
+                                                     uint32_t* n_circle_members)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (etype[i] != T_INTERIOR || visited[i]) return;
+    atomicAdd(n_circle_members, 1u);
+    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    uint32_t nk = walk_circle(d, i, [](uint32_t, uint32_t, uint32_t) {});
+    if (nk) { own_n[i] = nk; etype[i] = SN_T_CIRCLE; }
+}
+__global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, uint32_t n, uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = own_n[i];
+    ebases[i] = k ? k + (SN_K - 1) : 0u;
+    eflag[i] = k ? 1u : 0u;
+}
+// owner walks its edge again: bases (one per byte, walk orientation) into `tmp`, and
+// (edge id, step) into every entry on the edge; then the whole-edge canonical form
+// (EdgeBuilder::addEdge :480-485 / extend :457-464) decides whether the edge is
+// stored reverse-complemented.
+__global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n,
+                                                   const uint32_t* __restrict__ owners, uint32_t n_owners, const uint8_t* __restrict__ etype,
+                                                   const uint64_t* __restrict__ base_off, uint8_t* __restrict__ tmp,
+                                                   uint32_t* __restrict__ elen, uint8_t* __restrict__ eflip, uint64_t* __restrict__ etmp_off)
+{
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_owners) return;
+    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    uint32_t i = owners[e];
+    int t = etype[i];
+    uint8_t* s = tmp + base_off[i];
+    Kmer k = entry_kmer(tab[i]);
+    if (t == T_END_UP) k = kmer_rc(k);
+    for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(k, b);
+    tab[i].edge = e; tab[i].off = 0;
+    uint32_t nk = 1;
+    auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { s[SN_K - 1 + step] = (uint8_t)c; tab[j].edge = e; tab[j].off = step; };
+    if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
+    else if (t == SN_T_CIRCLE) nk = walk_circle(d, i, visit);
+    uint32_t len = nk + SN_K - 1;
+    elen[e] = len;
+    etmp_off[e] = base_off[i];
+    eflip[e] = seq_form_u8(s, len) == REV ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_fix_offsets(DictEntry* tab, uint32_t n, const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t e = tab[i].edge;
+    if (e != SN_NULL_EDGE && eflip[e]) tab[i].off = (elen[e] - (SN_K - 1)) - 1 - tab[i].off;
+}
+__global__ void __launch_bounds__(256) k_edge_bytes(const uint32_t* __restrict__ elen, uint32_t n_edges, uint32_t* __restrict__ ebytes)
+{
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges) ebytes[e] = (elen[e] + 3) >> 2;
+}
+// one thread per output byte of the packed edge store (fastb layout)
+__global__ void __launch_bounds__(256) k_pack_edges(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off,
+                                                    const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip,
+                                                    const uint64_t* __restrict__ eoff, uint32_t n_edges, uint64_t total_bytes, uint8_t* __restrict__ packed)
+{
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total_bytes) return;
+    uint32_t lo = 0, hi = n_edges;                     // largest e with eoff[e] <= x
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (eoff[m] <= x) lo = m; else hi = m; }
+    uint32_t e = lo, len = elen[e];
+    uint32_t b0 = (uint32_t)(x - eoff[e]) * 4;
+    const uint8_t* s = tmp + etmp_off[e];
+    uint32_t v = 0;
+    for (uint32_t j = 0; j < 4 && b0 + j < len; ++j) {
+        uint32_t c = eflip[e] ? (s[len - 1 - (b0 + j)] ^ 3u) : s[b0 + j];
+        v |= c << (2 * j);
+    }
+    packed[x] = (uint8_t)v;
+}
+
+// ---------------------------------------------------------------------------
+// a10-a13. ReadPath threading, one read per thread.  mode 0: lengths + offsets only;
+// mode 1: also the edge lists at path_off[r].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_path_reads(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+                                                    const uint32_t* __restrict__ len, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
+                                                    DictView d, EdgeStore es, HbvView h, int mode,
+                                                    uint32_t* __restrict__ plen, int32_t* __restrict__ poffset,
+                                                    const uint64_t* __restrict__ path_off, int32_t* __restrict__ pedges, uint32_t* overflow)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    Part parts[SN_MAX_PARTS];
+    RPath path;
+    path_one_read(d, es, h, bases + boff[r], quals + qoff[r], len[r], parts, path);
+    if (path.overflow) atomicAdd(overflow, 1u);
+    if (mode == 0) { plen[r] = path.n; poffset[r] = path.offset; }
+    else { int32_t* o = pedges + path_off[r]; for (uint32_t i = 0; i < path.n; ++i) o[i] = path.e[i]; }
+}
+
+}  // namespace sn

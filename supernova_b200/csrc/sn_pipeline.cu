@@ -1,0 +1,735 @@
+// sn_pipeline.cu -- host orchestration + extern "C" ABI (include/supernova_b200.h) of the
+// B200-native hot path.  Mirrors the call sequence of buildReadQGraph48
+// (paths/long/BuildReadQGraph48.cc:1688-1774): createDict -> buildEdges ->
+// buildHBVFromEdges -> pathReads.  Everything heavy runs in the kernels of
+// sn_kernels.cuh; the host keeps sizes, allocations and the sequential HBV numbering.
+#include "../../include/supernova_b200.h"
+#include "sn_kernels.cuh"
+#include "sn_formats.h"
+#include "sn_hbv.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+#include <sys/stat.h>
+
+using namespace sn;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t alloc(size_t n) { release(); if (!n) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; return e; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Timer { cudaEvent_t a = nullptr, b = nullptr; bool used = false; };
+
+}  // namespace
+
+struct sn_ctx {
+    int device = 0, num_sms = 148;
+    cudaStream_t st = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    std::map<std::string, Timer> timers;
+    std::map<std::string, double> host_ms;
+    sn_params params{7, 3, 2, 0};
+    sn_counts cnt{};
+    int stage = 0;       // 0 none, 1 reads, 2 counted, 3 edges, 4 hbv, 5 paths
+
+    // reads
+    DevBuf bases, boff, len, quals, qoff, bc, pq, pqoff, goodlen;
+    bool have_bc = false, have_pq = false;
+    // dictionary
+    DevBuf dict, idx;
+    // edges (device) + host copy
+    DevBuf ebases, eoff, elen;
+    snh::Edges hedges;
+    // hbv
+    snh::Hbv hbv;
+    DevBuf d_fwd, d_rev, d_toleft, d_toright, d_src, d_from_start, d_from_v, d_from_e, d_to_start, d_to_v, d_to_e;
+    // paths
+    DevBuf plen, poffset, path_off, pedges;
+    std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
+    DevBuf counters;     // small scratch of u64 counters
+};
+
+namespace {
+
+int fail(sn_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return fail(c, SN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+#define KCHECK(name) do { ++c->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+    return fail(c, SN_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); } while (0)
+
+void t_begin(sn_ctx* c, const char* name)
+{
+    Timer& t = c->timers[name];
+    if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+    cudaEventRecord(t.a, c->st); t.used = false;
+}
+void t_end(sn_ctx* c, const char* name) { Timer& t = c->timers[name]; cudaEventRecord(t.b, c->st); t.used = true; }
+
+inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+// exclusive scan helper that owns its temporaries; out has n+1 entries; total returned through *total (host, after sync)
+int scan_u32(sn_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
+{
+    DevBuf tmp;
+    CU(tmp.alloc(scan_tmp_words(n) * 8 + 16));
+    exclusive_scan_u32_u64(in, n, out, tmp.as<uint64_t>(), c->st);
+    c->launches += n ? 3 : 0;
+    CU(cudaGetLastError());
+    if (total) { CU(cudaMemcpyAsync(total, out + n, 8, cudaMemcpyDeviceToHost, c->st)); }
+    CU(cudaStreamSynchronize(c->st));      // tmp is released on return
+    return SN_OK;
+}
+
+int upload(sn_ctx* c, DevBuf& b, const void* src, size_t bytes, size_t pad = 0)
+{
+    CU(b.alloc(bytes + pad));
+    if (pad) CU(cudaMemsetAsync((char*)b.p + bytes, 0, pad, c->st));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->st));
+    return SN_OK;
+}
+
+int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off, const uint32_t* len, const int32_t* bc)
+{
+    if (!n_reads || !bases || !base_off || !len) return fail(c, SN_ERR_ARG, "sn_load_reads: empty or NULL input");
+    if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
+    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->cnt.n_reads = n_reads;
+    t_begin(c, "h2d");
+    int r;
+    if ((r = upload(c, c->bases, bases, base_off[n_reads], 64))) return r;
+    if ((r = upload(c, c->boff, base_off, 8 * (n_reads + 1)))) return r;
+    if ((r = upload(c, c->len, len, 4 * n_reads))) return r;
+    c->have_bc = bc != nullptr;
+    if (bc) {
+        // barcode ordinals travel in 24 bits of the k-mer record (0xFFFFFF is reserved for "-1")
+        int32_t mx = 0; for (uint64_t i = 0; i < n_reads; ++i) mx = std::max(mx, bc[i]);
+        if (mx >= 0xFFFFFF) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
+        if ((r = upload(c, c->bc, bc, 4 * n_reads))) return r;
+    }
+    return SN_OK;
+}
+
+int finish_load(sn_ctx* c)
+{
+    t_end(c, "h2d");
+    uint64_t n = c->cnt.n_reads;
+    // element offsets of the unpacked quals = exclusive scan of the read lengths
+    CU(c->qoff.alloc(8 * (n + 1)));
+    uint64_t total = 0;
+    int r = scan_u32(c, c->len.as<uint32_t>(), n, c->qoff.as<uint64_t>(), &total);
+    if (r) return r;
+    c->cnt.n_bases = total;
+    // longest read must fit the per-thread buffers of the pathing kernel
+    std::vector<uint32_t> hl(n);
+    CU(cudaMemcpy(hl.data(), c->len.p, 4 * n, cudaMemcpyDeviceToHost));
+    uint32_t mx = 0; for (uint32_t v : hl) mx = std::max(mx, v);
+    if (mx > SN_MAX_READ_LEN) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    c->stage = 1;
+    return SN_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int sn_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int sn_ctx_create(sn_ctx** out, int device)
+{
+    if (!out) return SN_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SN_ERR_CUDA, std::string("no CUDA device: the hot path has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= n) return fail(nullptr, SN_ERR_ARG, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, SN_ERR_CUDA, cudaGetErrorString(e));
+    sn_ctx* c = new sn_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, SN_ERR_CUDA, cudaGetErrorString(e)); }
+    if ((e = c->counters.alloc(256)) != cudaSuccess) { delete c; return fail(nullptr, SN_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = c;
+    return SN_OK;
+}
+void sn_ctx_destroy(sn_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    for (auto& kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+const char* sn_last_error(const sn_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+uint64_t sn_kernel_launches(const sn_ctx* c) { return c ? c->launches : 0; }
+double sn_stage_ms(const sn_ctx* c, const char* name)
+{
+    if (!c || !name) return -1.0;
+    auto h = c->host_ms.find(name);
+    if (h != c->host_ms.end()) return h->second;
+    auto it = c->timers.find(name);
+    if (it == c->timers.end() || !it->second.used) return -1.0;
+    cudaEventSynchronize(it->second.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int sn_load_reads(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,
+                  const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc)
+{
+    if (!c) return SN_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int r = load_common(c, n_reads, bases, base_off, len, bc);
+    if (r) return r;
+    if (!pq || !pq_off) return fail(c, SN_ERR_ARG, "sn_load_reads: NULL quals");
+    if ((r = upload(c, c->pq, pq, pq_off[n_reads], 16))) return r;
+    if ((r = upload(c, c->pqoff, pq_off, 8 * (n_reads + 1)))) return r;
+    c->have_pq = true;
+    c->quals.release();
+    return finish_load(c);
+}
+int sn_load_reads_q8(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,
+                     const uint8_t* quals, const uint64_t* qual_off, const int32_t* bc)
+{
+    if (!c) return SN_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int r = load_common(c, n_reads, bases, base_off, len, bc);
+    if (r) return r;
+    if (!quals || !qual_off) return fail(c, SN_ERR_ARG, "sn_load_reads_q8: NULL quals");
+    if ((r = upload(c, c->quals, quals, qual_off[n_reads], 16))) return r;
+    c->have_pq = false;
+    c->pq.release(); c->pqoff.release();
+    return finish_load(c);
+}
+int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const char* bci)
+{
+    if (!c || !fastb || !qualp) return SN_ERR_ARG;
+    snf::Fastb fb; snf::Qualp qp; std::vector<int64_t> bi; std::vector<int32_t> bc; std::string err;
+    if (!snf::read_fastb(fastb, fb, err) || !snf::read_qualp(qualp, qp, err)) return fail(c, SN_ERR_IO, err);
+    if (fb.len.size() + 1 != qp.off.size()) return fail(c, SN_ERR_DATA, "fastb and qualp hold different numbers of reads");
+    if (bci) {
+        if (!snf::read_bci(bci, bi, err)) return fail(c, SN_ERR_IO, err);
+        snf::expand_bci(bi, bc);
+        if (bc.size() != fb.len.size()) return fail(c, SN_ERR_DATA, "bci.back() != number of reads");
+    }
+    return sn_load_reads(c, fb.len.size(), fb.var.data(), fb.off.data(), fb.len.data(), qp.var.data(), qp.off.data(), bci ? bc.data() : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+int sn_count_kmers(sn_ctx* c, const sn_params* p)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_count_kmers: no reads loaded");
+    CU(cudaSetDevice(c->device));
+    if (p) c->params = *p;
+    if (c->params.min_bc > 2) return fail(c, SN_ERR_ARG, "min_bc > 2 is not supported (the reference pipeline fixes MIN_BC=2, 10X/DF.cc:140)");
+    if (c->params.min_freq == 0) c->params.min_freq = 1;
+    const uint64_t n = c->cnt.n_reads;
+    unsigned long long* occ = c->counters.as<unsigned long long>();        // [0] occurrences, [1] cursor, [2] distinct
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [0] bad reads, [1] tile counter, [2] n_out
+    CU(cudaMemsetAsync(c->counters.p, 0, 256, c->st));
+    CU(c->goodlen.alloc(4 * n));
+    // a1
+    t_begin(c, "goodlen");
+    if (c->have_pq) {
+        CU(c->quals.alloc(c->cnt.n_bases + 16));
+        k_pqvec_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>(), c->len.as<uint32_t>(),
+            c->qoff.as<uint64_t>(), c->quals.as<uint8_t>(), c->params.min_qual, c->goodlen.as<uint32_t>(), occ, u32c);
+        KCHECK("k_pqvec_goodlen");
+    } else {
+        k_q8_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->len.as<uint32_t>(),
+            c->params.min_qual, c->goodlen.as<uint32_t>(), occ);
+        KCHECK("k_q8_goodlen");
+    }
+    t_end(c, "goodlen");
+    unsigned long long h_occ = 0; uint32_t h_bad = 0;
+    CU(cudaMemcpyAsync(&h_occ, occ, 8, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&h_bad, u32c, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_bad) return fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count");
+    c->cnt.n_kmer_occurrences = h_occ;
+    if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads (minimizer buckets / more GPUs)");
+    const uint32_t n_occ = (uint32_t)h_occ;
+    c->dict.release(); c->idx.release();
+    c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
+    DevBuf ka, kb, tmp;
+    if (n_occ) {
+        CU(ka.alloc((size_t)n_occ * 16));
+        CU(kb.alloc((size_t)n_occ * 16 * (c->params.min_freq >= 2 ? 1 : 2)));
+        CU(tmp.alloc(radix_sort_tmp_bytes(n_occ) + (size_t)blocks_for(n_occ, SN_RD_TILE) * 8 + 64));
+        // a2
+        t_begin(c, "extract");
+        k_extract<<<blocks_for(n, SN_EX_READS), 256, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+            c->have_bc ? c->bc.as<int32_t>() : nullptr, c->params.ign_bc_below, ka.as<uint4>(), occ + 1);
+        KCHECK("k_extract");
+        t_end(c, "extract");
+        // a4
+        t_begin(c, "sort");
+        cudaError_t e = radix_sort_kmers(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
+        c->launches += 2 + SN_RS_PASSES;
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
+        t_end(c, "sort");
+        // a5 (dictionary is compacted into kb, which is no longer needed by the sort)
+        t_begin(c, "reduce");
+        uint64_t* status = tmp.as<uint64_t>();
+        uint32_t nt = blocks_for(n_occ, SN_RD_TILE);
+        CU(cudaMemsetAsync(status, 0, (size_t)nt * 8, c->st));
+        k_reduce<<<nt, SN_RD_THREADS, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
+            kb.as<DictEntry>(), status, u32c + 1, u32c + 2, occ + 2);
+        KCHECK("k_reduce");
+        t_end(c, "reduce");
+        uint32_t h_n = 0; unsigned long long h_d = 0;
+        CU(cudaMemcpyAsync(&h_n, u32c + 2, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
+        ka.release();
+        CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
+        CU(cudaMemcpyAsync(c->dict.p, kb.p, (size_t)h_n * sizeof(DictEntry), cudaMemcpyDeviceToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    } else {
+        CU(c->dict.alloc(64));
+    }
+    // prefix index
+    t_begin(c, "index");
+    CU(c->idx.alloc(((1ull << SN_IDX_BITS) + 1) * 4));
+    k_build_index<<<blocks_for((1ull << SN_IDX_BITS) + 1, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), (uint32_t)c->cnt.n_kmers, c->idx.as<uint32_t>());
+    KCHECK("k_build_index");
+    t_end(c, "index");
+    CU(cudaStreamSynchronize(c->st));
+    c->stage = 2;
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------
+int sn_build_edges(sn_ctx* c)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 2) return fail(c, SN_ERR_STATE, "sn_build_edges: run sn_count_kmers first");
+    CU(cudaSetDevice(c->device));
+    const uint32_t n = (uint32_t)c->cnt.n_kmers;
+    c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
+    c->hedges = snh::Edges();
+    c->ebases.release(); c->eoff.release(); c->elen.release();
+    if (!n) { c->hedges.off.assign(1, 0); c->hedges.packed.assign(16, 0); c->stage = 3; return SN_OK; }
+    DictEntry* tab = c->dict.as<DictEntry>();
+    const uint32_t* idx = c->idx.as<uint32_t>();
+    t_begin(c, "prune");
+    k_prune<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n);
+    KCHECK("k_prune");
+    t_end(c, "prune");
+
+    t_begin(c, "edges");
+    DevBuf etype, own_n, flag, pos, list, visited;
+    CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(pos.alloc(8ull * (n + 1))); CU(visited.alloc(n));
+    CU(cudaMemsetAsync(visited.p, 0, n, c->st));
+    k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
+    KCHECK("k_classify");
+    uint64_t n_ends = 0;
+    int r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_ends);
+    if (r) return r;
+    if (n_ends) {
+        CU(list.alloc(4 * n_ends));
+        k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
+        KCHECK("k_scatter_flagged");
+        k_walk_count<<<blocks_for(n_ends, 128), 128, 0, c->st>>>(tab, idx, n, list.as<uint32_t>(), (uint32_t)n_ends, etype.as<uint8_t>(),
+            own_n.as<uint32_t>(), visited.as<uint8_t>());
+        KCHECK("k_walk_count");
+    }
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
+    CU(cudaMemsetAsync(u32c + 4, 0, 4, c->st));
+    k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), visited.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
+    KCHECK("k_circle_count");
+    // allocation: bases per owner -> offsets in the unpacked scratch; owner rank -> edge id
+    DevBuf ebases_u32, base_off;
+    CU(ebases_u32.alloc(4ull * n)); CU(base_off.alloc(8ull * (n + 1)));
+    k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), n, ebases_u32.as<uint32_t>(), flag.as<uint32_t>());
+    KCHECK("k_edge_sizes");
+    uint64_t total_bases = 0, n_edges = 0;
+    if ((r = scan_u32(c, ebases_u32.as<uint32_t>(), n, base_off.as<uint64_t>(), &total_bases))) return r;
+    if ((r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_edges))) return r;
+    if (n_edges >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
+    CU(list.alloc(4 * n_edges + 16));
+    k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
+    KCHECK("k_scatter_flagged");
+    DevBuf tmpb, eflip, etmp_off, ebytes;
+    CU(tmpb.alloc(total_bases + 16)); CU(eflip.alloc(n_edges + 16)); CU(etmp_off.alloc(8 * n_edges + 16)); CU(ebytes.alloc(4 * n_edges + 16));
+    CU(c->elen.alloc(4 * n_edges + 16)); CU(c->eoff.alloc(8 * (n_edges + 1)));
+    k_walk_emit<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, idx, n, list.as<uint32_t>(), (uint32_t)n_edges, etype.as<uint8_t>(),
+        base_off.as<uint64_t>(), tmpb.as<uint8_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(), etmp_off.as<uint64_t>());
+    KCHECK("k_walk_emit");
+    k_fix_offsets<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, n, c->elen.as<uint32_t>(), eflip.as<uint8_t>());
+    KCHECK("k_fix_offsets");
+    k_edge_bytes<<<blocks_for(n_edges, 256), 256, 0, c->st>>>(c->elen.as<uint32_t>(), (uint32_t)n_edges, ebytes.as<uint32_t>());
+    KCHECK("k_edge_bytes");
+    uint64_t total_bytes = 0;
+    if ((r = scan_u32(c, ebytes.as<uint32_t>(), n_edges, c->eoff.as<uint64_t>(), &total_bytes))) return r;
+    CU(c->ebases.alloc(total_bytes + 64));
+    CU(cudaMemsetAsync((char*)c->ebases.p + total_bytes, 0, 64, c->st));
+    k_pack_edges<<<blocks_for(total_bytes, 256), 256, 0, c->st>>>(tmpb.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(),
+        c->eoff.as<uint64_t>(), (uint32_t)n_edges, total_bytes, c->ebases.as<uint8_t>());
+    KCHECK("k_pack_edges");
+    t_end(c, "edges");
+    // every dictionary entry must now sit on exactly one edge
+    c->cnt.n_edges = n_edges; c->cnt.n_edge_bases = total_bases;
+    c->hedges.len.resize(n_edges); c->hedges.off.resize(n_edges + 1); c->hedges.packed.assign(total_bytes + 16, 0);
+    CU(cudaMemcpyAsync(c->hedges.len.data(), c->elen.p, 4 * n_edges, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->hedges.off.data(), c->eoff.p, 8 * (n_edges + 1), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->hedges.packed.data(), c->ebases.p, total_bytes, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    uint64_t kmers_on_edges = total_bases - (uint64_t)(SN_K - 1) * n_edges;
+    if (kmers_on_edges != n)
+        return fail(c, SN_ERR_DATA, "edge stage covered " + std::to_string(kmers_on_edges) + " of " + std::to_string(n) + " dictionary k-mers");
+    c->stage = 3;
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------
+int sn_build_hbv(sn_ctx* c)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 3) return fail(c, SN_ERR_STATE, "sn_build_hbv: run sn_build_edges first");
+    CU(cudaSetDevice(c->device));
+    auto t0 = std::chrono::steady_clock::now();
+    try { snh::build_hbv(c->hedges, c->hbv); }
+    catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
+    c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const snh::Hbv& H = c->hbv;
+    const size_t nV = H.from.size(), nH = H.src.size(), nE = H.fwd.size();
+    c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
+    std::vector<uint32_t> fs(nV + 1, 0), ts(nV + 1, 0);
+    std::vector<int32_t> fv, fe, tv, te; fv.reserve(nH); fe.reserve(nH); tv.reserve(nH); te.reserve(nH);
+    for (size_t v = 0; v < nV; ++v) {
+        fs[v + 1] = fs[v] + (uint32_t)H.from[v].size(); ts[v + 1] = ts[v] + (uint32_t)H.to[v].size();
+        fv.insert(fv.end(), H.from[v].begin(), H.from[v].end()); fe.insert(fe.end(), H.from_eo[v].begin(), H.from_eo[v].end());
+        tv.insert(tv.end(), H.to[v].begin(), H.to[v].end()); te.insert(te.end(), H.to_eo[v].begin(), H.to_eo[v].end());
+    }
+    int r;
+    if ((r = upload(c, c->d_fwd, H.fwd.data(), 4 * nE, 16))) return r;
+    if ((r = upload(c, c->d_rev, H.rev.data(), 4 * nE, 16))) return r;
+    if ((r = upload(c, c->d_toleft, H.to_left.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_toright, H.to_right.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_src, H.src.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_from_start, fs.data(), 4 * (nV + 1), 16))) return r;
+    if ((r = upload(c, c->d_to_start, ts.data(), 4 * (nV + 1), 16))) return r;
+    if ((r = upload(c, c->d_from_v, fv.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_from_e, fe.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_to_v, tv.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_to_e, te.data(), 4 * nH, 16))) return r;
+    CU(cudaStreamSynchronize(c->st));
+    c->stage = 4;
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------
+int sn_path_reads(sn_ctx* c)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 4) return fail(c, SN_ERR_STATE, "sn_path_reads: run sn_build_hbv first");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = c->cnt.n_reads;
+    DictView d; d.tab = c->dict.as<DictEntry>(); d.idx = c->idx.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers;
+    EdgeStore es; es.bases = c->ebases.as<uint8_t>(); es.off = c->eoff.as<uint64_t>(); es.len = c->elen.as<uint32_t>();
+    HbvView h;
+    h.fwd_xlat = c->d_fwd.as<int32_t>(); h.rev_xlat = c->d_rev.as<int32_t>();
+    h.to_left = c->d_toleft.as<int32_t>(); h.to_right = c->d_toright.as<int32_t>(); h.src = c->d_src.as<uint32_t>();
+    h.from_start = c->d_from_start.as<uint32_t>(); h.from_v = c->d_from_v.as<int32_t>(); h.from_e = c->d_from_e.as<int32_t>();
+    h.to_start = c->d_to_start.as<uint32_t>(); h.to_v = c->d_to_v.as<int32_t>(); h.to_e = c->d_to_e.as<int32_t>();
+    CU(c->plen.alloc(4 * n)); CU(c->poffset.alloc(4 * n)); CU(c->path_off.alloc(8 * (n + 1)));
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
+    CU(cudaMemsetAsync(u32c + 5, 0, 4, c->st));
+    c->paths_on_host = false;
+    t_begin(c, "path");
+    if (c->cnt.n_kmers == 0) {
+        CU(cudaMemsetAsync(c->plen.p, 0, 4 * n, c->st)); CU(cudaMemsetAsync(c->poffset.p, 0, 4 * n, c->st));
+    } else {
+        k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
+            c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), d, es, h, 0, c->plen.as<uint32_t>(), c->poffset.as<int32_t>(), nullptr, nullptr, u32c + 5);
+        KCHECK("k_path_reads(count)");
+    }
+    uint64_t total = 0;
+    int r = scan_u32(c, c->plen.as<uint32_t>(), n, c->path_off.as<uint64_t>(), &total);
+    if (r) return r;
+    CU(c->pedges.alloc(4 * total + 16));
+    if (total) {
+        k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
+            c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), d, es, h, 1, nullptr, nullptr, c->path_off.as<uint64_t>(), c->pedges.as<int32_t>(), u32c + 5);
+        KCHECK("k_path_reads(emit)");
+    }
+    t_end(c, "path");
+    uint32_t h_over = 0;
+    CU(cudaMemcpyAsync(&h_over, u32c + 5, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_over) return fail(c, SN_ERR_DATA, "a ReadPath exceeded " + std::to_string(SN_MAX_PATH) + " edges");
+    c->cnt.n_path_edges = total;
+    c->stage = 5;
+    return SN_OK;
+}
+
+// ---------------------------------------------------------------------------
+int sn_get_counts(const sn_ctx* c, sn_counts* out) { if (!c || !out) return SN_ERR_ARG; *out = c->cnt; return SN_OK; }
+
+int sn_get_good_lengths(sn_ctx* c, uint32_t* out)
+{
+    if (!c || !out) return SN_ERR_ARG;
+    if (c->stage < 2) return fail(c, SN_ERR_STATE, "good lengths are available after sn_count_kmers");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy(out, c->goodlen.p, 4 * c->cnt.n_reads, cudaMemcpyDeviceToHost));
+    return SN_OK;
+}
+int sn_get_kmers(sn_ctx* c, sn_kmer_rec* out)
+{
+    if (!c || !out) return SN_ERR_ARG;
+    if (c->stage < 2) return fail(c, SN_ERR_STATE, "no dictionary yet");
+    CU(cudaSetDevice(c->device));
+    if (c->cnt.n_kmers)
+        CU(cudaMemcpy2D(out, sizeof(sn_kmer_rec), c->dict.p, sizeof(DictEntry), sizeof(sn_kmer_rec), c->cnt.n_kmers, cudaMemcpyDeviceToHost));
+    return SN_OK;
+}
+int sn_get_kmer_graph_info(sn_ctx* c, uint8_t* ctx_pruned, uint32_t* edge, uint32_t* offset)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
+    CU(cudaSetDevice(c->device));
+    size_t n = c->cnt.n_kmers;
+    std::vector<DictEntry> h(n);
+    if (n) CU(cudaMemcpy(h.data(), c->dict.p, n * sizeof(DictEntry), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        if (ctx_pruned) ctx_pruned[i] = (uint8_t)h[i].ctx;
+        if (edge) edge[i] = h[i].edge;
+        if (offset) offset[i] = h[i].off;
+    }
+    return SN_OK;
+}
+int sn_get_edges_bytes(const sn_ctx* c, uint64_t* packed_bytes)
+{
+    if (!c || !packed_bytes) return SN_ERR_ARG;
+    *packed_bytes = c->hedges.off.empty() ? 0 : c->hedges.off.back();
+    return SN_OK;
+}
+int sn_get_edges(sn_ctx* c, uint32_t* len, uint64_t* off, uint8_t* packed)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
+    const snh::Edges& E = c->hedges;
+    if (len && E.n()) memcpy(len, E.len.data(), 4 * E.n());
+    if (off) memcpy(off, E.off.data(), 8 * E.off.size());
+    if (packed && !E.off.empty()) memcpy(packed, E.packed.data(), E.off.back());
+    return SN_OK;
+}
+int sn_get_hbv(sn_ctx* c, uint32_t* from_start, int32_t* from_v, int32_t* from_e, uint32_t* to_start, int32_t* to_v, int32_t* to_e,
+               int32_t* fwd_xlat, int32_t* rev_xlat, int32_t* inv)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    const snh::Hbv& H = c->hbv;
+    size_t nV = H.from.size(), f = 0, t = 0;
+    for (size_t v = 0; v < nV; ++v) {
+        if (from_start) from_start[v] = (uint32_t)f;
+        if (to_start) to_start[v] = (uint32_t)t;
+        for (size_t i = 0; i < H.from[v].size(); ++i, ++f) { if (from_v) from_v[f] = H.from[v][i]; if (from_e) from_e[f] = H.from_eo[v][i]; }
+        for (size_t i = 0; i < H.to[v].size(); ++i, ++t) { if (to_v) to_v[t] = H.to[v][i]; if (to_e) to_e[t] = H.to_eo[v][i]; }
+    }
+    if (from_start) from_start[nV] = (uint32_t)f;
+    if (to_start) to_start[nV] = (uint32_t)t;
+    if (fwd_xlat && !H.fwd.empty()) memcpy(fwd_xlat, H.fwd.data(), 4 * H.fwd.size());
+    if (rev_xlat && !H.rev.empty()) memcpy(rev_xlat, H.rev.data(), 4 * H.rev.size());
+    if (inv && !H.inv.empty()) memcpy(inv, H.inv.data(), 4 * H.inv.size());
+    return SN_OK;
+}
+static int fetch_paths(sn_ctx* c)
+{
+    if (c->stage < 5) return fail(c, SN_ERR_STATE, "run sn_path_reads first");
+    if (c->paths_on_host) return SN_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t n = c->cnt.n_reads, m = c->cnt.n_path_edges;
+    c->h_poffset.resize(n); c->h_path_off.resize(n + 1); c->h_pedges.resize(m);
+    CU(cudaMemcpy(c->h_poffset.data(), c->poffset.p, 4 * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(c->h_path_off.data(), c->path_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+    if (m) CU(cudaMemcpy(c->h_pedges.data(), c->pedges.p, 4 * m, cudaMemcpyDeviceToHost));
+    c->paths_on_host = true;
+    return SN_OK;
+}
+int sn_get_paths(sn_ctx* c, int32_t* offset, uint64_t* path_off, int32_t* edges)
+{
+    if (!c) return SN_ERR_ARG;
+    int r = fetch_paths(c); if (r) return r;
+    if (offset) memcpy(offset, c->h_poffset.data(), 4 * c->h_poffset.size());
+    if (path_off) memcpy(path_off, c->h_path_off.data(), 8 * c->h_path_off.size());
+    if (edges && !c->h_pedges.empty()) memcpy(edges, c->h_pedges.data(), 4 * c->h_pedges.size());
+    return SN_OK;
+}
+
+int sn_write_hbv(sn_ctx* c, const char* path)
+{
+    if (!c || !path) return SN_ERR_ARG;
+    if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    std::string err; const snh::Hbv& H = c->hbv;
+    if (!snf::write_hbv(path, H.K, H.from, H.from_eo, H.to_eo, H.epacked.data(), H.eoff.data(), H.elen.data(), H.elen.size(), err))
+        return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+int sn_write_paths(sn_ctx* c, const char* path)
+{
+    if (!c || !path) return SN_ERR_ARG;
+    int r = fetch_paths(c); if (r) return r;
+    std::string err;
+    if (!snf::write_paths(path, c->cnt.n_reads, c->h_poffset.data(), c->h_path_off.data(), c->h_pedges.data(), err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+int sn_write_edges_bv(sn_ctx* c, const char* path)
+{
+    if (!c || !path) return SN_ERR_ARG;
+    if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
+    std::string err; const snh::Edges& E = c->hedges;
+    if (!snf::write_bv(path, E.packed.data(), E.off.data(), E.len.data(), E.n(), err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+int sn_write_inv(sn_ctx* c, const char* path)
+{
+    if (!c || !path) return SN_ERR_ARG;
+    if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    std::string err;
+    if (!snf::write_vec_int(path, c->hbv.inv, err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+// WriteKmerSpectrum (BuildReadQGraph48.cc:199-216) + WriteHistToJson (10X/MakeHist.cc:68-92)
+int sn_write_kmer_spectrum(sn_ctx* c, const char* json)
+{
+    if (!c || !json) return SN_ERR_ARG;
+    if (c->stage < 2) return fail(c, SN_ERR_STATE, "run sn_count_kmers first");
+    CU(cudaSetDevice(c->device));
+    size_t n = c->cnt.n_kmers;
+    std::vector<uint32_t> cc(n);
+    if (n) CU(cudaMemcpy2D(cc.data(), 4, (const char*)c->dict.p + 12, sizeof(DictEntry), 4, n, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> spec;
+    for (uint32_t v : cc) { uint32_t k = v & 0xFFFFFFu; if (spec.size() <= k) spec.resize(k + 1, 0); spec[k]++; }
+    int64_t maxc = (int64_t)spec.size() - 1;
+    FILE* f = fopen(json, "w");
+    if (!f) return fail(c, SN_ERR_IO, std::string("cannot create ") + json);
+    fprintf(f, "{\n\t\"description\": \"kmer_count\",\n\t\"stage\": \"DF\",\n\t\"binsize\": 1,\n\t\"min\": 0,\n\t\"max\": %lld,\n\t\"numbins\": %zu,\n\t\"vals\": [",
+            (long long)maxc, spec.size());
+    for (size_t i = 0; i < spec.size(); ++i) fprintf(f, "%lld%s", (long long)spec[i], i + 1 == spec.size() ? "" : ",");
+    fprintf(f, "]\n}\n");
+    fclose(f);
+    return SN_OK;
+}
+
+int sn_build_read_qgraph48(sn_ctx* c, const char* work_dir, const sn_params* params, int with_paths, int write_files)
+{
+    if (!c) return SN_ERR_ARG;
+    int r;
+    if ((r = sn_count_kmers(c, params))) return r;
+    if ((r = sn_build_edges(c))) return r;
+    if ((r = sn_build_hbv(c))) return r;
+    if (with_paths && (r = sn_path_reads(c))) return r;
+    if (write_files) {
+        if (!work_dir) return fail(c, SN_ERR_ARG, "work_dir is NULL");
+        std::string wd(work_dir);
+        mkdir((wd + "/stats").c_str(), 0777);
+        if ((r = sn_write_kmer_spectrum(c, (wd + "/stats/histogram_kmer_count.json").c_str()))) return r;
+        if ((r = sn_write_hbv(c, (wd + "/a.hbv").c_str()))) return r;
+        if (with_paths && (r = sn_write_paths(c, (wd + "/tmp.paths").c_str()))) return r;
+    }
+    return SN_OK;
+}
+
+// ---- host-only helpers -------------------------------------------------------------------
+uint64_t sn_pqvec_encode(const uint8_t* quals, uint32_t n, uint8_t* out)
+{
+    std::vector<uint8_t> v; snf::pqvec_encode(quals, n, v);
+    memcpy(out, v.data(), v.size());
+    return v.size();
+}
+uint32_t sn_pqvec_decode(const uint8_t* pq, uint64_t pq_bytes, uint8_t* out, uint32_t cap) { return snf::pqvec_decode(pq, pq + pq_bytes, out, cap); }
+void sn_free(void* p) { free(p); }
+
+int sn_pack_reads(uint64_t n, const uint8_t* codes, const uint8_t* quals, const uint64_t* off, int threads,
+                  uint8_t** bases, uint64_t** base_off, uint32_t** len, uint8_t** pq, uint64_t** pq_off)
+{
+    if (!codes || !quals || !off || !bases || !base_off || !len || !pq || !pq_off) return SN_ERR_ARG;
+    if (threads < 1) threads = 1;
+    uint64_t* bo = (uint64_t*)malloc(8 * (n + 1)); uint32_t* ln = (uint32_t*)malloc(4 * (n ? n : 1)); uint64_t* po = (uint64_t*)malloc(8 * (n + 1));
+    bo[0] = 0;
+    for (uint64_t r = 0; r < n; ++r) { ln[r] = (uint32_t)(off[r + 1] - off[r]); bo[r + 1] = bo[r] + (ln[r] + 3) / 4; }
+    uint8_t* bs = (uint8_t*)calloc(bo[n] + 64, 1);
+    std::vector<std::vector<uint8_t>> chunks(threads);
+    std::vector<std::vector<uint64_t>> sizes(threads);
+    auto work = [&](int t) {
+        uint64_t a = n * t / threads, b = n * (t + 1) / threads;
+        sizes[t].reserve(b - a);
+        for (uint64_t r = a; r < b; ++r) {
+            const uint8_t* s = codes + off[r]; uint8_t* d = bs + bo[r];
+            for (uint32_t i = 0; i < ln[r]; ++i) d[i >> 2] |= (uint8_t)((s[i] & 3u) << (2 * (i & 3)));
+            size_t before = chunks[t].size();
+            snf::pqvec_encode(quals + off[r], ln[r], chunks[t]);
+            sizes[t].push_back(chunks[t].size() - before);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+    uint64_t tot = 0; for (auto& v : chunks) tot += v.size();
+    uint8_t* pqb = (uint8_t*)malloc(tot + 64);
+    uint64_t at = 0, r = 0; po[0] = 0;
+    for (int t = 0; t < threads; ++t) {
+        memcpy(pqb + at, chunks[t].data(), chunks[t].size()); at += chunks[t].size();
+        for (uint64_t s : sizes[t]) { po[r + 1] = po[r] + s; ++r; }
+    }
+    memset(pqb + tot, 0, 64);
+    *bases = bs; *base_off = bo; *len = ln; *pq = pqb; *pq_off = po;
+    return SN_OK;
+}
+int sn_write_read_files(const char* fastb, const char* qualp, const char* bci, uint64_t n,
+                        const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,
+                        const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc)
+{
+    std::string err;
+    if (fastb) {
+        snf::Fastb fb; fb.var.assign(bases, bases + base_off[n]); fb.off.assign(base_off, base_off + n + 1); fb.len.assign(len, len + n);
+        if (!snf::write_fastb(fastb, fb, err)) { g_create_error = err; return SN_ERR_IO; }
+    }
+    if (qualp) {
+        snf::Qualp qp; qp.var.assign(pq, pq + pq_off[n]); qp.off.assign(pq_off, pq_off + n + 1);
+        if (!snf::write_qualp(qualp, qp, err)) { g_create_error = err; return SN_ERR_IO; }
+    }
+    if (bci) {
+        // inverse of the expansion in 10X/DF.cc:464-469: bci[b] = first read of barcode ordinal b
+        std::vector<int64_t> bi; bi.push_back(0);
+        int32_t cur = 0;
+        for (uint64_t r = 0; r < n; ++r) {
+            int32_t b = bc ? bc[r] : 0;
+            if (b < cur) { g_create_error = "barcode ordinals are not sorted"; return SN_ERR_DATA; }
+            while (cur < b) { bi.push_back((int64_t)r); ++cur; }
+        }
+        bi.push_back((int64_t)n);
+        if (!snf::write_bci(bci, bi, err)) { g_create_error = err; return SN_ERR_IO; }
+    }
+    return SN_OK;
+}
+
+}  // extern "C"

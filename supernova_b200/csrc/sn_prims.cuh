@@ -1,0 +1,301 @@
+// sn_prims.cuh -- device-wide primitives written for this hot path (no CUB/Thrust):
+//   * tile look-back (decoupled single-pass prefix over tiles)
+//   * exclusive scan  (u32 -> u64)
+//   * LSD radix sort of 128-bit records {w0,w1,w2,aux} by the 96-bit k-mer, one
+//     read + one write of every record per 8-bit digit pass ("onesweep" shape:
+//     all digit histograms in one upfront pass, per-tile offsets by look-back).
+// Integer / byte work only; every kernel is HBM-bound by design and sized as
+// persistent-ish grids of 256-thread CTAs (multiples of the 148 SMs are chosen by
+// the launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sn {
+
+#define SN_FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// ---------------------------------------------------------------------------
+// Tile look-back.  status word (u64) = flag(2 bits) << 62 | value(62 bits).
+// A tile first publishes its AGGREGATE, then walks predecessors until it meets
+// a PREFIX, then publishes its own inclusive PREFIX.  The word is self-contained
+// (value and flag travel in one 64-bit store), so relaxed gpu-scope accesses suffice.
+// Tiles take their ids from an atomic counter, so every predecessor is already
+// resident and the spin cannot deadlock.
+// ---------------------------------------------------------------------------
+#define SN_ST_INVALID 0ull
+#define SN_ST_AGG 1ull
+#define SN_ST_PREFIX 2ull
+#define SN_ST_VMASK 0x3FFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t flag, uint64_t v)
+{ uint64_t x = (flag << 62) | v; asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(x) : "memory"); }
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p)
+{ uint64_t x; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory"); return x; }
+
+// exclusive prefix of `aggregate` over tiles [0,tile); `status` has `stride` words per tile.
+__device__ __forceinline__ uint64_t tile_lookback(uint64_t* status, uint32_t stride, uint32_t slot, uint32_t tile, uint64_t aggregate)
+{
+    if (tile == 0) { st_status(status + slot, SN_ST_PREFIX, aggregate); return 0; }
+    st_status(status + (size_t)tile * stride + slot, SN_ST_AGG, aggregate);
+    uint64_t excl = 0;
+    for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
+        uint64_t s;
+        do { s = ld_status(status + (size_t)t * stride + slot); } while ((s >> 62) == SN_ST_INVALID);
+        excl += s & SN_ST_VMASK;
+        if ((s >> 62) == SN_ST_PREFIX) break;
+    }
+    st_status(status + (size_t)tile * stride + slot, SN_ST_PREFIX, excl + aggregate);
+    return excl;
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan u32 -> u64 (three small kernels; inputs here are per-read or
+// per-dictionary-entry counts, far smaller than the k-mer stream).
+// ---------------------------------------------------------------------------
+#define SN_SCAN_THREADS 256
+#define SN_SCAN_ITEMS 8
+#define SN_SCAN_TILE (SN_SCAN_THREADS * SN_SCAN_ITEMS)
+
+__device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* total, uint64_t* sm /*>=8*/)
+{
+    // inclusive warp scan, then scan of warp totals
+    uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+    uint64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) sm[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint64_t t = lane < (blockDim.x >> 5) ? sm[lane] : 0;
+        uint64_t xs = t;
+        for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(SN_FULL, xs, o); if (lane >= (uint32_t)o) xs += y; }
+        if (lane < (blockDim.x >> 5)) sm[lane] = xs - t;
+        if (lane == 31) sm[32] = xs;
+    }
+    __syncthreads();
+    uint64_t r = sm[w] + x - v;
+    if (total) *total = sm[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ tile_sums)
+{
+    __shared__ uint64_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * SN_SCAN_TILE;
+    uint64_t s = 0;
+    for (int j = 0; j < SN_SCAN_ITEMS; ++j) { uint64_t i = base + (uint64_t)j * SN_SCAN_THREADS + threadIdx.x; if (i < n) s += in[i]; }
+    uint64_t tot; block_excl_scan_u64(s, &tot, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+// single block: exclusive scan of tile sums in place; total written to tile_sums[ntiles]
+__global__ void __launch_bounds__(1024) k_scan_spine(uint64_t* tile_sums, uint64_t ntiles)
+{
+    __shared__ uint64_t sm[33];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t b = 0; b < ntiles; b += blockDim.x) {
+        uint64_t i = b + threadIdx.x;
+        uint64_t v = i < ntiles ? tile_sums[i] : 0;
+        uint64_t tot; uint64_t e = block_excl_scan_u64(v, &tot, sm);
+        uint64_t c = carry;
+        if (i < ntiles) tile_sums[i] = c + e;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+__global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ out)
+{
+    __shared__ uint64_t sm[33];
+    uint64_t base = (uint64_t)blockIdx.x * SN_SCAN_TILE + (uint64_t)threadIdx.x * SN_SCAN_ITEMS;   // blocked
+    uint32_t v[SN_SCAN_ITEMS]; uint64_t s = 0;
+    for (int j = 0; j < SN_SCAN_ITEMS; ++j) { uint64_t i = base + j; v[j] = i < n ? in[i] : 0; s += v[j]; }
+    uint64_t e = block_excl_scan_u64(s, nullptr, sm) + tile_sums[blockIdx.x];
+    for (int j = 0; j < SN_SCAN_ITEMS; ++j) { uint64_t i = base + j; if (i < n) out[i] = e; e += v[j]; }
+}
+
+// out[i] = sum_{j<i} in[j]; out[n] = total.  `tmp` needs (ceil(n/TILE)+1) u64.
+inline uint64_t scan_tmp_words(uint64_t n) { return (n + SN_SCAN_TILE - 1) / SN_SCAN_TILE + 1; }
+inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* tmp, cudaStream_t st)
+{
+    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(uint64_t), st); return; }
+    uint64_t nt = (n + SN_SCAN_TILE - 1) / SN_SCAN_TILE;
+    k_scan_tile_sums<<<(unsigned)nt, SN_SCAN_THREADS, 0, st>>>(in, n, tmp);
+    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nt);
+    k_scan_apply<<<(unsigned)nt, SN_SCAN_THREADS, 0, st>>>(in, n, tmp, out);
+    cudaMemcpyAsync(out + n, tmp + nt, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st);
+}
+
+// ---------------------------------------------------------------------------
+// radix sort of uint4 records by (x,y,z) = (w0,w1,w2), LSD, 8-bit digits.
+// ---------------------------------------------------------------------------
+#define SN_RS_THREADS 256
+#define SN_RS_ITEMS 16
+#define SN_RS_TILE (SN_RS_THREADS * SN_RS_ITEMS)
+#define SN_RS_PASSES 12
+
+__device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
+{
+    uint32_t w = pass < 4 ? k.z : (pass < 8 ? k.y : k.x);
+    return (w >> (8 * (pass & 3))) & 0xFFu;
+}
+
+// all 12 digit histograms in one pass over the records (they are invariant under
+// the permutations the later passes apply).  hist[pass*256 + digit], u32 counts.
+__global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t sh[SN_RS_PASSES * 256];
+    for (int i = threadIdx.x; i < SN_RS_PASSES * 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 k = keys[i];
+#pragma unroll
+        for (int p = 0; p < SN_RS_PASSES; ++p) atomicAdd(&sh[p * 256 + rs_digit(k, p)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SN_RS_PASSES * 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// exclusive scan of each pass's 256 bins, in place (one block of 256 threads per pass)
+__global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
+{
+    __shared__ uint32_t sm[256];
+    uint32_t* h = hist + blockIdx.x * 256;
+    uint32_t v = h[threadIdx.x];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        uint32_t y = threadIdx.x >= (uint32_t)o ? sm[threadIdx.x - o] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += y;
+        __syncthreads();
+    }
+    h[threadIdx.x] = sm[threadIdx.x] - v;
+}
+
+struct RsSmem {
+    uint4 keys[SN_RS_TILE];            // 64 KB reorder buffer
+    uint32_t warp_cnt[8][256];         // per-warp digit counters -> exclusive warp offsets
+    uint32_t tile_start[256];          // exclusive scan of the tile's digit totals
+    uint32_t gdst[256];                // global destination of smem slot s with digit d: gdst[d] + s
+    uint32_t scan_tmp[8];
+    uint32_t tile_id;
+};
+
+// One digit pass: read each record once, write it once.
+__global__ void __launch_bounds__(SN_RS_THREADS, 2)
+k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, int pass,
+             const uint32_t* __restrict__ ghist /* exclusive starts, this pass */, uint64_t* status, uint32_t* tile_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem& S = *reinterpret_cast<RsSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) S.tile_id = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < 8 * 256; i += SN_RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile_id;
+    const uint64_t tile_base = (uint64_t)tile * SN_RS_TILE;
+    const uint32_t valid = (uint32_t)min((uint64_t)SN_RS_TILE, (uint64_t)n - tile_base);
+
+    // warp-striped load: warp w owns [w*512, (w+1)*512); item j of lane l is w*512 + j*32 + l
+    uint4 key[SN_RS_ITEMS];
+    uint32_t rank[SN_RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SN_RS_ITEMS; ++j) {
+        uint32_t li = warp * (32 * SN_RS_ITEMS) + j * 32 + lane;
+        if (li < valid) key[j] = in[tile_base + li];
+        else key[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);   // sorts last, never written
+    }
+    // stable in-warp ranking by digit: match_any groups equal digits, the group leader
+    // bumps the warp's private counter for that digit.
+#pragma unroll
+    for (int j = 0; j < SN_RS_ITEMS; ++j) {
+        uint32_t d = rs_digit(key[j], pass);
+        uint32_t peers = __match_any_sync(SN_FULL, d);
+        uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) { base = S.warp_cnt[warp][d]; S.warp_cnt[warp][d] = base + __popc(peers); }
+        base = __shfl_sync(SN_FULL, base, leader);
+        rank[j] = base + __popc(peers & lanemask_lt());
+    }
+    __syncthreads();
+    // thread d: exclusive scan of digit d over the 8 warps, tile total, look-back
+    uint32_t tot = 0;
+    {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { uint32_t c = S.warp_cnt[w][tid]; S.warp_cnt[w][tid] = tot; tot += c; }
+    }
+    uint32_t prev = (uint32_t)tile_lookback(status, 256, tid, tile, tot);
+    // exclusive scan of tile totals over digits (256 threads)
+    {
+        uint32_t x = tot;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) S.scan_tmp[warp] = x;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) if (w < (int)warp) wbase += S.scan_tmp[w];
+        uint32_t excl = wbase + x - tot;
+        S.tile_start[tid] = excl;
+        S.gdst[tid] = ghist[tid] + prev - excl;     // may wrap below zero; the later + s brings it back (mod 2^32)
+    }
+    __syncthreads();
+    // scatter into the smem reorder buffer
+#pragma unroll
+    for (int j = 0; j < SN_RS_ITEMS; ++j) {
+        uint32_t d = rs_digit(key[j], pass);
+        uint32_t pos = S.tile_start[d] + S.warp_cnt[warp][d] + rank[j];
+        S.keys[pos] = key[j];
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive slots of one digit are consecutive in global memory
+#pragma unroll
+    for (int j = 0; j < SN_RS_ITEMS; ++j) {
+        uint32_t s = j * SN_RS_THREADS + tid;
+        if (s < valid) {
+            uint4 k = S.keys[s];
+            uint32_t d = rs_digit(k, pass);
+            out[(uint32_t)(S.gdst[d] + s)] = k;
+        }
+    }
+}
+
+inline size_t radix_sort_tmp_bytes(uint32_t n)
+{
+    uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
+    return (size_t)SN_RS_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
+}
+// Sorts n (< 2^32) records.  Result ends in `a` (12 passes ping-pong a->b->a...).
+inline cudaError_t radix_sort_kmers(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
+    uint32_t* hist = (uint32_t*)tmp;
+    uint32_t* counters = hist + SN_RS_PASSES * 256;
+    uint64_t* status = (uint64_t*)(counters + 16);
+    cudaMemsetAsync(hist, 0, (SN_RS_PASSES * 256 + 16) * 4, st);
+    int hb = num_sms * 8;
+    k_rs_histogram<<<hb, 256, 0, st>>>(a, n, hist);
+    k_rs_scan_hist<<<SN_RS_PASSES, 256, 0, st>>>(hist);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    uint4* src = a; uint4* dst = b;
+    for (int p = 0; p < SN_RS_PASSES; ++p) {
+        cudaMemsetAsync(status, 0, (size_t)nt * 256 * 8, st);
+        k_rs_scatter<<<nt, SN_RS_THREADS, sizeof(RsSmem), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
+        uint4* t = src; src = dst; dst = t;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sn

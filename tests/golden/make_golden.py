@@ -1,0 +1,50 @@
+"""Generates the committed golden fixtures by running the REFERENCE's own binaries
+(oracle/_ref, built from /root/reference by oracle/build_ref.sh) in this container.
+For each data set: the input files written by the reference's ParseBarcodedFastqs
+(reads.fastb/.qualp/.bci) and the outputs of its buildReadQGraph48 (kmers.kvec reduced to
+the sorted {k-mer,count,ctx} records, a.hbv, tmp.paths, histogram_kmer_count.json).
+
+    python tests/golden/make_golden.py        # needs oracle/_ref
+"""
+import gzip
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import datasets  # noqa: E402
+import refrun  # noqa: E402
+from supernova_b200 import synth  # noqa: E402
+
+SETS = ["tiny", "stress1"]
+
+
+def main():
+    assert refrun.have_ref(), "build oracle/_ref first (bash oracle/build_ref.sh)"
+    for name in SETS:
+        codes, quals, off, bc, ids = datasets.get(name)
+        wd = tempfile.mkdtemp()
+        synth.write_fasth_ragged(wd + "/reads.fastq.gz", codes, quals, off, ids)
+        refrun.parse_fastqs(wd, wd + "/reads.fastq.gz")
+        refrun.run_probe(wd)
+        out = os.path.join(HERE, name)
+        os.makedirs(out, exist_ok=True)
+        for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths"):
+            with open(os.path.join(wd, f), "rb") as src, gzip.GzipFile(os.path.join(out, f + ".gz"), "wb", mtime=0) as dst:
+                dst.write(src.read())
+        shutil.copy(wd + "/stats/histogram_kmer_count.json", out + "/histogram_kmer_count.json")
+        kv = refrun.read_kvec(wd + "/kmers.kvec")
+        np.save(out + "/kvec_sorted.npy", kv)
+        shutil.rmtree(wd)
+        print(name, "->", out, kv.shape)
+
+
+if __name__ == "__main__":
+    main()

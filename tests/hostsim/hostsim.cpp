@@ -1,0 +1,186 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE.  Runs the host+device (`SN_HD`)
+// per-item logic of the product kernels (sn_kmer.cuh / sn_graph.cuh / sn_path.cuh) in
+// plain loops on the CPU, stage by stage exactly as the kernels in sn_kernels.cuh
+// apply it, so that the graph and pathing logic can be checked against the oracle on a
+// box without a GPU.  It is NOT a fallback: nothing in the product links this file.
+#include "../../supernova_b200/csrc/sn_kmer.cuh"
+#include "../../supernova_b200/csrc/sn_graph.cuh"
+#include "../../supernova_b200/csrc/sn_path.cuh"
+#include "../../supernova_b200/csrc/sn_hbv.h"
+#include "../../supernova_b200/csrc/sn_formats.h"
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sn;
+
+struct Sim {
+    std::vector<DictEntry> tab;
+    std::vector<uint32_t> idx;
+    snh::Edges edges;
+    snh::Hbv hbv;
+    std::vector<uint32_t> fs, ts; std::vector<int32_t> fv, fe, tv, te;
+    std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
+    DictView view() const { DictView d; d.tab = tab.data(); d.idx = idx.data(); d.n = (uint32_t)tab.size(); return d; }
+};
+
+extern "C" {
+
+// a2 for one read: emits records {w0,w1,w2,ctx<<24|bc24} like k_extract
+uint32_t hs_extract_read(const uint8_t* packed, uint32_t goodlen, int32_t bc, uint32_t* out)
+{
+    if (goodlen < SN_K + 1) return 0;
+    uint32_t n = goodlen - SN_K + 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        Kmer k = kmer_from_packed(packed, i);
+        uint32_t ctx = 0;
+        if (i > 0) ctx |= 16u << packed_base(packed, i - 1);
+        if (i + SN_K < goodlen) ctx |= 1u << packed_base(packed, i + SN_K);
+        Kmer rc;
+        if (kmer_form(k, &rc) == REV) { k = rc; ctx = ctx_rc(ctx); }
+        out[4 * i] = k.w0; out[4 * i + 1] = k.w1; out[4 * i + 2] = k.w2;
+        out[4 * i + 3] = (ctx << 24) | (bc < 0 ? 0xFFFFFFu : (uint32_t)bc);
+    }
+    return n;
+}
+
+Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted */)
+{
+    Sim* s = new Sim();
+    s->tab.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        DictEntry& e = s->tab[i];
+        e.w0 = recs[4 * i]; e.w1 = recs[4 * i + 1]; e.w2 = recs[4 * i + 2]; e.cc = recs[4 * i + 3];
+        e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = e.cc >> 24; e.pad = 0;
+    }
+    s->idx.resize((1u << SN_IDX_BITS) + 1);
+    for (uint32_t b = 0; b <= (1u << SN_IDX_BITS); ++b) {          // k_build_index
+        if (b == (1u << SN_IDX_BITS)) { s->idx[b] = (uint32_t)n; break; }
+        uint32_t key = b << (32 - SN_IDX_BITS), lo = 0, hi = (uint32_t)n;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s->tab[mid].w0 < key) lo = mid + 1; else hi = mid; }
+        s->idx[b] = lo;
+    }
+    return s;
+}
+void hs_free(Sim* s) { delete s; }
+
+void hs_prune(Sim* s)
+{
+    DictView d = s->view();
+    std::vector<uint32_t> ctx(s->tab.size());
+    for (uint32_t i = 0; i < s->tab.size(); ++i) ctx[i] = prune_ctx(d, i);      // k_prune
+    for (uint32_t i = 0; i < s->tab.size(); ++i) s->tab[i].ctx = ctx[i];
+}
+
+// k_classify .. k_pack_edges
+int hs_edges(Sim* s)
+{
+    DictView d = s->view();
+    const uint32_t n = (uint32_t)s->tab.size();
+    std::vector<uint8_t> etype(n), visited(n, 0);
+    std::vector<uint32_t> own_n(n, 0);
+    for (uint32_t i = 0; i < n; ++i) { int t = classify_entry(d, i); etype[i] = (uint8_t)t; own_n[i] = t == T_SINGLE ? 1u : 0u; }
+    for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_END_DOWN || etype[i] == T_END_UP) {          // k_walk_count
+        uint32_t last = i; visited[i] = 1;
+        uint32_t nk = walk_edge(d, i, etype[i], [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
+        if (i <= last) own_n[i] = nk;
+    }
+    for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_INTERIOR && !visited[i]) {                     // k_circle_count
+        uint32_t nk = walk_circle(d, i, [](uint32_t, uint32_t, uint32_t) {});
+        if (nk) { own_n[i] = nk; etype[i] = 4; }
+    }
+    std::vector<uint32_t> owners; std::vector<uint64_t> base_off(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) { base_off[i + 1] = base_off[i] + (own_n[i] ? own_n[i] + SN_K - 1 : 0); if (own_n[i]) owners.push_back(i); }
+    std::vector<uint8_t> tmp(base_off[n] + 16);
+    const uint32_t nE = (uint32_t)owners.size();
+    std::vector<uint32_t> elen(nE); std::vector<uint8_t> eflip(nE); std::vector<uint64_t> etmp(nE);
+    for (uint32_t e = 0; e < nE; ++e) {                                                              // k_walk_emit
+        uint32_t i = owners[e]; int t = etype[i];
+        uint8_t* sq = tmp.data() + base_off[i];
+        Kmer k = entry_kmer(s->tab[i]);
+        if (t == T_END_UP) k = kmer_rc(k);
+        for (int b = 0; b < SN_K; ++b) sq[b] = (uint8_t)kmer_base(k, b);
+        s->tab[i].edge = e; s->tab[i].off = 0;
+        uint32_t nk = 1;
+        auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { sq[SN_K - 1 + step] = (uint8_t)c; s->tab[j].edge = e; s->tab[j].off = step; };
+        if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
+        else if (t == 4) nk = walk_circle(d, i, visit);
+        elen[e] = nk + SN_K - 1; etmp[e] = base_off[i];
+        eflip[e] = seq_form_u8(sq, elen[e]) == REV ? 1 : 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {                                                               // k_fix_offsets
+        uint32_t e = s->tab[i].edge;
+        if (e == SN_NULL_EDGE) return -1;
+        if (eflip[e]) s->tab[i].off = (elen[e] - (SN_K - 1)) - 1 - s->tab[i].off;
+    }
+    snh::Edges& E = s->edges;
+    E.len = elen; E.off.assign(nE + 1, 0);
+    for (uint32_t e = 0; e < nE; ++e) E.off[e + 1] = E.off[e] + (elen[e] + 3) / 4;
+    E.packed.assign(E.off[nE] + 16, 0);
+    for (uint32_t e = 0; e < nE; ++e)                                                                // k_pack_edges
+        for (uint32_t b = 0; b < elen[e]; ++b) {
+            const uint8_t* sq = tmp.data() + etmp[e];
+            uint32_t c = eflip[e] ? (sq[elen[e] - 1 - b] ^ 3u) : sq[b];
+            E.packed[E.off[e] + (b >> 2)] |= (uint8_t)(c << (2 * (b & 3)));
+        }
+    return 0;
+}
+uint64_t hs_n_edges(Sim* s) { return s->edges.n(); }
+uint64_t hs_edges_bytes(Sim* s) { return s->edges.off.back(); }
+void hs_get_edges(Sim* s, uint32_t* len, uint64_t* off, uint8_t* packed)
+{
+    memcpy(len, s->edges.len.data(), 4 * s->edges.n()); memcpy(off, s->edges.off.data(), 8 * s->edges.off.size());
+    memcpy(packed, s->edges.packed.data(), s->edges.off.back());
+}
+void hs_get_graph_info(Sim* s, uint8_t* ctx, uint32_t* edge, uint32_t* off)
+{ for (size_t i = 0; i < s->tab.size(); ++i) { ctx[i] = (uint8_t)s->tab[i].ctx; edge[i] = s->tab[i].edge; off[i] = s->tab[i].off; } }
+
+int hs_hbv(Sim* s, const char* hbv_path)
+{
+    snh::build_hbv(s->edges, s->hbv);
+    const snh::Hbv& H = s->hbv;
+    size_t nV = H.from.size();
+    s->fs.assign(nV + 1, 0); s->ts.assign(nV + 1, 0); s->fv.clear(); s->fe.clear(); s->tv.clear(); s->te.clear();
+    for (size_t v = 0; v < nV; ++v) {
+        s->fs[v + 1] = s->fs[v] + (uint32_t)H.from[v].size(); s->ts[v + 1] = s->ts[v] + (uint32_t)H.to[v].size();
+        s->fv.insert(s->fv.end(), H.from[v].begin(), H.from[v].end()); s->fe.insert(s->fe.end(), H.from_eo[v].begin(), H.from_eo[v].end());
+        s->tv.insert(s->tv.end(), H.to[v].begin(), H.to[v].end()); s->te.insert(s->te.end(), H.to_eo[v].begin(), H.to_eo[v].end());
+    }
+    if (hbv_path) {
+        std::string err;
+        if (!snf::write_hbv(hbv_path, H.K, H.from, H.from_eo, H.to_eo, H.epacked.data(), H.eoff.data(), H.elen.data(), H.elen.size(), err)) return -1;
+    }
+    return 0;
+}
+
+// k_path_reads over all reads; reads in fastb packing, quals one byte per base
+int hs_paths(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t* boff, const uint32_t* len,
+             const uint8_t* quals, const uint64_t* qoff, const char* paths_file)
+{
+    DictView d = s->view();
+    EdgeStore es; es.bases = s->edges.packed.data(); es.off = s->edges.off.data(); es.len = s->edges.len.data();
+    const snh::Hbv& H = s->hbv;
+    HbvView h; h.fwd_xlat = H.fwd.data(); h.rev_xlat = H.rev.data(); h.to_left = H.to_left.data(); h.to_right = H.to_right.data();
+    h.src = H.src.data(); h.from_start = s->fs.data(); h.from_v = s->fv.data(); h.from_e = s->fe.data();
+    h.to_start = s->ts.data(); h.to_v = s->tv.data(); h.to_e = s->te.data();
+    s->poffset.assign(n_reads, 0); s->poff.assign(n_reads + 1, 0); s->pedges.clear();
+    std::vector<Part> parts(SN_MAX_PARTS);
+    RPath* path = new RPath();
+    int overflow = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        path_one_read(d, es, h, bases + boff[r], quals + qoff[r], len[r], parts.data(), *path);
+        if (path->overflow) ++overflow;
+        s->poffset[r] = path->offset;
+        s->pedges.insert(s->pedges.end(), path->e, path->e + path->n);
+        s->poff[r + 1] = s->pedges.size();
+    }
+    delete path;
+    if (paths_file) {
+        std::string err;
+        if (!snf::write_paths(paths_file, n_reads, s->poffset.data(), s->poff.data(), s->pedges.data(), err)) return -1;
+    }
+    return overflow ? -2 : 0;
+}
+
+}  // extern "C"

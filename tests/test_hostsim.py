@@ -1,0 +1,87 @@
+"""CPU: the product's host+device per-item logic (sn_kmer.cuh / sn_graph.cuh / sn_path.cuh,
+the code the CUDA kernels execute per k-mer / per read) run in loops on the CPU and compared
+with the oracle and the golden vectors.  tests/hostsim is a test harness, not a fallback."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+from oracle.oracle import Oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def sb(built):
+    import supernova_b200
+    return supernova_b200
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1", "stress2", "C1"])
+def test_graph_and_paths_logic(sb, name, tmp_path):
+    from hostsim import HostSim
+    codes, quals, off, bc, _ = datasets.get(name)
+    o = Oracle(codes, quals, off, bc).run()
+    km = o.kmers()
+    recs = np.stack([km[:, 0], km[:, 1], km[:, 2], km[:, 3] | (km[:, 4] << 24)], axis=1).astype(np.uint32)
+    hs = HostSim(recs)
+    hs.prune()
+    ctx, _, _ = hs.graph_info()
+    assert np.array_equal(ctx, km[:, 5].astype(np.uint8))
+    ln, eo, packed = hs.edges()
+    assert sorted(datasets.unpack_edges(ln, eo, packed)) == sorted(o.edges())
+    # every k-mer sits at (edge, off) where the edge really spells it (either strand)
+    _, edge, eoff = hs.graph_info()
+    assert (edge < len(ln)).all() and (eoff + 48 <= ln[edge]).all()
+    hs.hbv(str(tmp_path / "h.hbv"))
+    o.write_hbv(str(tmp_path / "o.hbv"))
+    assert open(tmp_path / "h.hbv", "rb").read() == open(tmp_path / "o.hbv", "rb").read()
+    pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=2)
+    hs.paths(pb, boff, pl, quals, off, str(tmp_path / "h.paths"))
+    o.write_paths(str(tmp_path / "o.paths"))
+    assert open(tmp_path / "h.paths", "rb").read() == open(tmp_path / "o.paths", "rb").read()
+    if name in ("tiny", "stress1"):
+        with gzip.open(os.path.join(GOLD, name, "tmp.paths.gz"), "rb") as f:
+            assert open(tmp_path / "h.paths", "rb").read() == f.read()
+
+
+def test_extract_logic_matches_oracle_occurrences(sb):
+    """k_extract's per-occurrence logic: the multiset of (canonical k-mer, ctx, bc) records."""
+    import ctypes as C
+    from hostsim import lib
+    codes, quals, off, bc, _ = datasets.get("stress3")
+    o = Oracle(codes, quals, off, bc).stage("count")
+    gl = o.good_len()
+    pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=2)
+    padded = np.concatenate([pb, np.zeros(32, np.uint8)])
+    recs = []
+    buf = np.zeros((256, 4), np.uint32)
+    for r in range(len(pl)):
+        n = lib().hs_extract_read(padded.ctypes.data + int(boff[r]), int(gl[r]), int(bc[r]), buf.ctypes.data)
+        if n:
+            recs.append(buf[:n].copy())
+    recs = np.concatenate(recs)
+    assert len(recs) == o.n_occ
+    # reduce on the CPU with numpy and compare with the oracle's table (count >= 3, >= 2 barcodes)
+    order = np.lexsort((recs[:, 2], recs[:, 1], recs[:, 0]))
+    recs = recs[order]
+    key = recs[:, :3]
+    head = np.ones(len(recs), bool)
+    head[1:] = (key[1:] != key[:-1]).any(axis=1)
+    gid = np.cumsum(head) - 1
+    cnt = np.bincount(gid)
+    ctx = np.zeros(gid[-1] + 1, np.uint32)
+    np.bitwise_or.at(ctx, gid, recs[:, 3] >> 24)
+    bcv = (recs[:, 3] & 0xFFFFFF).astype(np.int64)
+    mn = np.full(gid[-1] + 1, 1 << 30)
+    mx = np.zeros(gid[-1] + 1, np.int64)
+    pos = bcv > 0
+    np.minimum.at(mn, gid[pos], bcv[pos])
+    np.maximum.at(mx, gid[pos], bcv[pos])
+    valid = (cnt >= 3) & (mx > 0) & (mn != mx)
+    ok = o.kmers()
+    assert np.array_equal(key[head][valid], ok[:, :3])
+    assert np.array_equal(cnt[valid], ok[:, 3])
+    assert np.array_equal(ctx[valid], ok[:, 4])

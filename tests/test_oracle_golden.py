@@ -1,0 +1,72 @@
+"""CPU: the C oracle (oracle/sn_oracle.c) against the committed golden vectors produced by
+the reference's own binaries (tests/golden/make_golden.py), and -- when oracle/_ref is
+present -- against the reference run live on more inputs.  This is what pins the oracle."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+import refrun
+from oracle.oracle import Oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gz(path):
+    with gzip.open(path, "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_oracle_matches_golden(name, tmp_path):
+    codes, quals, off, bc, _ = datasets.get(name)
+    o = Oracle(codes, quals, off, bc).run()
+    kv = np.load(os.path.join(GOLD, name, "kvec_sorted.npy"))
+    km = o.kmers()
+    assert np.array_equal(km[:, :5], kv)                       # k-mer, count, context (pre-prune)
+    o.write_hbv(str(tmp_path / "o.hbv"))
+    o.write_paths(str(tmp_path / "o.paths"))
+    assert open(tmp_path / "o.hbv", "rb").read() == gz(os.path.join(GOLD, name, "a.hbv.gz"))
+    assert open(tmp_path / "o.paths", "rb").read() == gz(os.path.join(GOLD, name, "tmp.paths.gz"))
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_golden_spectrum(name):
+    import json
+    codes, quals, off, bc, _ = datasets.get(name)
+    o = Oracle(codes, quals, off, bc).stage("count")
+    spec = json.load(open(os.path.join(GOLD, name, "histogram_kmer_count.json")))["vals"]
+    counts = np.bincount(o.kmers()[:, 3].astype(np.int64), minlength=len(spec))
+    assert counts.tolist() == spec
+
+
+def test_oracle_invariants():
+    """Invariants the reference's own (Rust) tests state for this path:
+    every k-mer of an edge is a dictionary k-mer, edges partition the dictionary,
+    rc(rc(x)) == x through the involution."""
+    codes, quals, off, bc, _ = datasets.get("stress2")
+    o = Oracle(codes, quals, off, bc).run(with_paths=False)
+    km = o.kmers()
+    edges = o.edges()
+    assert sum(len(e) - 47 for e in edges) == km.shape[0]
+    inv = o.involution()
+    assert np.array_equal(inv[inv], np.arange(len(inv)))
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("name", ["stress2", "stress3", "C1"])
+def test_oracle_matches_reference_live(name, tmp_path):
+    from supernova_b200 import synth
+    codes, quals, off, bc, ids = datasets.get(name)
+    wd = str(tmp_path)
+    synth.write_fasth_ragged(wd + "/reads.fastq.gz", codes, quals, off, ids)
+    refrun.parse_fastqs(wd, wd + "/reads.fastq.gz")
+    refrun.run_probe(wd)
+    o = Oracle(codes, quals, off, bc).run()
+    assert np.array_equal(o.kmers()[:, :5], refrun.read_kvec(wd + "/kmers.kvec"))
+    o.write_hbv(wd + "/o.hbv")
+    o.write_paths(wd + "/o.paths")
+    assert open(wd + "/o.hbv", "rb").read() == open(wd + "/a.hbv", "rb").read()
+    assert open(wd + "/o.paths", "rb").read() == open(wd + "/tmp.paths", "rb").read()
