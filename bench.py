@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- Gbp of reads per second through k-mer count + de Bruijn/HBV build
+(BASELINE.json metric), one pass of the hot path over one batch of synthetic reads per step.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3              # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1      # the reference's own CPU path
+    torchrun ... bench.py --gpus N ...                         # one rank per GPU
+
+Workload at N=1: BASELINE.json configs[1] ("C2"): 1.2 Gbp of synthetic 150 bp linked reads
+(4.0 M pairs, 63 Mbp diploid, seed 20261017), K=48.
+`value`  : reads already resident in HBM (packed, as sn_load_reads leaves them) ->
+           HBV (edges + graph) in host memory; device time by CUDA events on the
+           context's stream, max over ranks.
+`e2e`    : the same through the C ABI from HOST (pinned) buffers: H2D of the step's
+           inputs and D2H of its results inside the timed region.
+`cpu_baseline`: the reference's own buildReadQGraph48 (oracle/_ref, compiled from the
+           reference sources) on a bounded sample of the same workload: the same generator
+           at 1/12 scale (5.25 Mbp genome, 100 Mbp of reads, same 19x coverage).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (G, pairs, nBC, seed)
+    "C2": (63_000_000, 4_000_000, 1_000_000, 20261017),
+    "mid": (2_000_000, 373_333, 50_000, 20261017),
+    "C1": (50_000, 10_000, 500, 1234),
+}
+SAMPLE_DIV = 12          # cpu_baseline sample = the workload's generator at 1/12 scale
+ALG_BYTES_PER_BASE = 24.2  # algorithmic HBM bytes per input base, count+HBV
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                              timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def gen_workload(name, rank, scale_div=1):
+    from supernova_b200 import synth
+    G, pairs, nbc, seed = WORKLOADS[name]
+    G, pairs, nbc = G // scale_div, pairs // scale_div, max(2, nbc // scale_div)
+    workers = min(os.cpu_count() or 1, 32)
+    # ranks > 0 draw different read pairs from the same genome (weak scaling: fixed work per GPU)
+    b, q, bc, ids = synth.make_reads(G, pairs, nbc, seed, workers=workers, shard=rank)
+    n, L = b.shape
+    off = np.arange(n + 1, dtype=np.uint64) * L
+    return b.ravel(), q.ravel(), off, bc, dict(G=G, pairs=pairs, n_bc=nbc, seed=seed, read_len=L)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref/OracleProbe =
+    buildReadQGraph48 compiled from /root/reference) on a bounded sample, all host threads."""
+    if rank != 0:
+        return
+    import supernova_b200 as sb
+    import refrun
+    if not refrun.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are not built (run oracle/build_ref.sh where /root/reference exists)"}))
+        return
+    codes, quals, off, bc, meta = gen_workload(args.workload, 0, SAMPLE_DIV)
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    gbp = codes.size / 1e9
+    wd = tempfile.mkdtemp(prefix="sn_ref_")
+    sb.write_read_files(wd + "/reads", pb, boff, ln, pq, pqoff, bc)
+    secs = []
+    for i in range(args.warmup + args.steps):
+        s, _ = refrun.run_probe(wd, paths=False, keep_kvec=False)
+        if i >= args.warmup:
+            secs.append(s)
+    t = sum(secs)
+    val = gbp * len(secs) / t
+    cores = os.cpu_count()
+    sample = f"same generator at 1/{SAMPLE_DIV} scale: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV (PATHS=False)"
+    line = {"metric": "Gbp reads/sec through k-mer count + DBG (HBV) build", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload + " (bounded sample)", "K": 48, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(args):
+    import supernova_b200 as sb
+    import refrun
+    codes, quals, off, bc, meta = gen_workload(args.workload, 0, SAMPLE_DIV)
+    gbp = codes.size / 1e9
+    sample = f"same generator at 1/{SAMPLE_DIV} scale: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV"
+    if refrun.have_ref():
+        pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+        wd = tempfile.mkdtemp(prefix="sn_cpu_")
+        sb.write_read_files(wd + "/reads", pb, boff, ln, pq, pqoff, bc)
+        secs, _ = refrun.run_probe(wd, paths=False, keep_kvec=False)
+        return {"value": gbp / secs, "unit": "Gbp/s", "cores": os.cpu_count(), "kind": "reference", "sample": sample, "seconds": secs}
+    from oracle.oracle import Oracle          # the one place bench may execute oracle/: the reported CPU baseline
+    t0 = time.time()
+    Oracle(codes, quals, off, bc).run(with_paths=False)
+    secs = time.time() - t0
+    return {"value": gbp / secs, "unit": "Gbp/s", "cores": 1, "kind": "port", "sample": sample, "seconds": secs}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-paths", action="store_true", help="skip the extra ReadPath-inclusive measurement")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import supernova_b200 as sb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- inputs: synthetic reads in the reference's in-memory layout, pinned ----------------
+    codes, quals, off, bc, meta = gen_workload(args.workload, rank)
+    n_bases = int(codes.size)
+    gbp = n_bases / 1e9
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    del codes, quals
+    host = [torch.from_numpy(x).pin_memory() for x in (pb, boff, ln, pq, pqoff, np.ascontiguousarray(bc, np.int32))]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    ptrs = [t.data_ptr() for t in host]
+    n_reads = len(ln)
+
+    ctx = sb.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
+    params = sb.Params()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(with_paths=False):
+        ctx.build_read_qgraph48(None, params, with_paths=with_paths, write_files=False)
+
+    def step_e2e():
+        ctx.load_reads_ptr(n_reads, *ptrs)
+        ctx.build_read_qgraph48(None, params, with_paths=False, write_files=False)
+        return ctx.hbv()           # D2H/marshalling of the result the caller consumes (edges are already on the host)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.kernel_launches()
+        e0.record(stream)
+        stage = {}
+        for _ in range(steps):
+            fn()
+            for k, v in ctx.stage_ms().items():
+                if v >= 0:
+                    stage[k] = stage.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.kernel_launches() - l0, {k: v / steps for k, v in stage.items()}
+
+    ctx.load_reads_ptr(n_reads, *ptrs)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches, stage = timed(step_resident, args.steps)
+    clocks = sampler.summary()
+    counts = ctx.counts()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    d2h_bytes = int(counts["n_edges"] * 12 + 8 + (counts["n_edge_bases"] + 3) // 4 + counts["n_hbv_edges"] * 28 + counts["n_hbv_vertices"] * 8)
+    paths_extra = None
+    if not args.no_paths:
+        step_resident(True)
+        ms_p, _, stage_p = timed(lambda: step_resident(True), max(1, args.steps // 2))
+        paths_extra = {"value": world * gbp * max(1, args.steps // 2) / (ms_p / 1e3), "unit": "Gbp/s", "path_ms": stage_p.get("path"),
+                       "n_path_edges": ctx.counts()["n_path_edges"]}
+
+    total_gbp = gbp * world
+    value = total_gbp * args.steps / (ms / 1e3)
+    e2e = total_gbp * args.steps / (ms_e2e / 1e3)
+    peak, peak_src = peaks()
+    n_occ = counts["n_kmer_occurrences"]
+    sort_ms = stage.get("sort", 0.0)
+    per_launch_ms = sort_ms / 12.0 if sort_ms else None
+    achieved = (32.0 * n_occ / 1e9) / (per_launch_ms / 1e3) if per_launch_ms else None
+    roof = {"bound": "hbm", "kernel": "k_rs_scatter (one 8-bit digit pass of the 128-bit k-mer record sort; 12 launches per step)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": None, "algorithmic_bytes_per_launch": 32 * n_occ, "launch_ms": per_launch_ms, "peak_source": peak_src,
+            "pipeline_algorithmic_frac": (ALG_BYTES_PER_BASE * value / world) / peak}
+    tr = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("k_rs_scatter_dram_bytes_per_launch")
+        except Exception:
+            pass
+    line = {"metric": "Gbp reads/sec through k-mer count + DBG (HBV) build", "value": value, "unit": "Gbp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {meta['pairs']} pairs x 2 x {meta['read_len']} bp per GPU, {meta['G']} bp diploid genome, seed {meta['seed']}",
+                       "K": 48, "min_qual": 7, "min_freq": 3, "min_bc": 2, "gbp_per_gpu": gbp,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks, independent read shards of one genome (no exchange in this round)",
+                       "l2": "inputs (%.1f GB of k-mer records per step) are larger than L2" % (16 * n_occ / 1e9)},
+            "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}
+    if paths_extra:
+        line["with_readpaths"] = paths_extra
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,11 +122,13 @@ int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* p
 
 /* ---- measurement ------------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) of the most recent run of a stage or
- * kernel group, in milliseconds; names: "goodlen","extract","sort","reduce","index","prune",
+ * kernel group, in milliseconds; names: "goodlen","extract","sort_hist","sort","reduce","index","prune",
  * "edges","path","h2d","hbv_host".  Returns a negative value for an unknown name.          */
 double sn_stage_ms(const sn_ctx* ctx, const char* name);
 /* number of kernel launches issued by this context so far */
 uint64_t sn_kernel_launches(const sn_ctx* ctx);
+/* the cudaStream_t every kernel and copy of this context is issued on (for event timing) */
+void* sn_stream(const sn_ctx* ctx);
 
 /* ---- host-side format helpers (no device needed) ------------------------------------------ */
 /* PQVec codec; out must hold at least 2*n+8 bytes; returns bytes written */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("h2d", "goodlen", "extract", "sort", "reduce", "index", "prune", "edges", "hbv_host", "path")
+STAGES = ("h2d", "goodlen", "extract", "sort_hist", "sort", "reduce", "index", "prune", "edges", "hbv_dev", "hbv_host", "path")
 
 
 class SnError(RuntimeError):
@@ -64,6 +64,8 @@ def lib():
         L.sn_stage_ms.restype = C.c_double
         L.sn_kernel_launches.argtypes = [vp]
         L.sn_kernel_launches.restype = u64
+        L.sn_stream.argtypes = [vp]
+        L.sn_stream.restype = vp
         L.sn_pqvec_encode.argtypes = [vp, C.c_uint32, vp]
         L.sn_pqvec_encode.restype = u64
         L.sn_pqvec_decode.argtypes = [vp, u64, vp, C.c_uint32]
@@ -270,3 +272,6 @@ class Context:
 
     def kernel_launches(self):
         return int(self.L.sn_kernel_launches(self.h))
+
+    def stream_ptr(self):
+        return int(self.L.sn_stream(self.h) or 0)

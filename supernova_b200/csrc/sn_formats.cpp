@@ -51,7 +51,13 @@ bool write_feudal(const std::string& path, uint32_t n, uint8_t size_fixed, uint8
     return true;
 }
 const char MAGIC[9] = "BINWRITE";
-unsigned ceil_lg2(unsigned x) { unsigned b = 0; while ((1u << b) < x) ++b; return b; }   // math/PowerOf2.h
+unsigned ceil_lg2(unsigned x)                                          // math/PowerOf2.h ceilLg2, x in 1..64
+{
+    static const unsigned char T[65] = {0,0,1,2,2,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,5,
+                                        6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6,6};
+    if (x <= 64) return T[x];
+    unsigned b = 0; while ((1u << b) < x) ++b; return b;
+}
 unsigned block_size(unsigned nqs, unsigned nbits) { return (nqs * nbits + 17 + 7) >> 3; }   // feudal/PQVec.h:57-58
 }  // namespace
 
@@ -212,19 +218,22 @@ bool read_bv(const std::string& path, Fastb& out, std::string& err)
     }
     return true;
 }
-static void put_vvi(FILE* f, const std::vector<std::vector<int32_t>>& v)
-{
-    uint64_t n = v.size(); fwrite(&n, 8, 1, f);
-    for (const auto& x : v) { uint64_t m = x.size(); fwrite(&m, 8, 1, f); if (m) fwrite(x.data(), 4, m, f); }
+static void put_csr(FILE* f, uint64_t n, const uint32_t* start, const int32_t* vals)
+{   // vec<vec<int>>: u64 count, then per inner vector u64 count + ints (feudal/BinaryStream.h:486-493)
+    std::vector<uint8_t> buf; buf.reserve(8 + n * 12 + 4ull * start[n]);
+    auto put = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; buf.insert(buf.end(), b, b + k); };
+    put(&n, 8);
+    for (uint64_t v = 0; v < n; ++v) { uint64_t m = start[v + 1] - start[v]; put(&m, 8); if (m) put(vals + start[v], 4 * m); }
+    fwrite(buf.data(), 1, buf.size(), f);
 }
-bool write_hbv(const std::string& path, int32_t K, const std::vector<std::vector<int32_t>>& from,
-               const std::vector<std::vector<int32_t>>& from_eo, const std::vector<std::vector<int32_t>>& to_eo,
+bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32_t* from_start, const int32_t* from_v,
+               const int32_t* from_e, const uint32_t* to_start, const int32_t* to_e,
                const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges, std::string& err)
 {
     File fh;
     if (!fh.open(path, "wb")) { err = "cannot create " + path; return false; }
     fwrite(MAGIC, 1, 8, fh.f); fwrite(&K, 4, 1, fh.f);
-    put_vvi(fh.f, from); put_vvi(fh.f, from_eo); put_vvi(fh.f, to_eo);
+    put_csr(fh.f, n_vert, from_start, from_v); put_csr(fh.f, n_vert, from_start, from_e); put_csr(fh.f, n_vert, to_start, to_e);
     fwrite(&n_edges, 8, 1, fh.f);
     for (uint64_t e = 0; e < n_edges; ++e) { fwrite(&len[e], 4, 1, fh.f); fwrite(packed + off[e], 1, (len[e] + 3) / 4, fh.f); }
     return true;

@@ -38,8 +38,9 @@ bool write_bv(const std::string& path, const uint8_t* packed, const uint64_t* of
 bool read_bv(const std::string& path, Fastb& out, std::string& err);
 
 // a.hbv (paths/HyperBasevector.cc:121-125, graph/DigraphTemplate.h:3091-3097)
-bool write_hbv(const std::string& path, int32_t K, const std::vector<std::vector<int32_t>>& from,
-               const std::vector<std::vector<int32_t>>& from_eo, const std::vector<std::vector<int32_t>>& to_eo,
+// adjacency given in CSR form: from_start/to_start have n_vert+1 entries
+bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32_t* from_start, const int32_t* from_v,
+               const int32_t* from_e, const uint32_t* to_start, const int32_t* to_e,
                const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges, std::string& err);
 // feudal ReadPathVec (paths/long/ReadPath.h:61-63, feudal/FeudalFileWriter.cc:100-121)
 bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err);

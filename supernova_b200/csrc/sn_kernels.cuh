@@ -391,6 +391,67 @@ __global__ void __launch_bounds__(256) k_pack_edges(const uint8_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// a8. vertex discovery for buildHBVFromEdges (paths/long/HBVFromEdges.cc:124-168,277):
+// per edge, the four (K-1)-mer end keys {fwd,rc} x {start,end} (two for a palindromic
+// edge) as sortable records, plus an order record (length desc, first 32 bases) for the
+// canonical edge order.  Both record sets go through radix_sort_kmers; k_hbv_mark /
+// k_hbv_assign turn runs of equal keys into vertex groups.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int seq_form_packed(const uint8_t* s, uint32_t len)
+{
+    if (len & 1) return (packed_base(s, len / 2) & 2) ? REV : FWD;
+    uint32_t i = 0, j = len;
+    while (i != j) {
+        uint32_t f = packed_base(s, i), r = packed_base(s, --j) ^ 3u;
+        if (f < r) return FWD;
+        if (r < f) return REV;
+        ++i;
+    }
+    return PAL;
+}
+__global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ elen,
+                                                  uint32_t n_edges, uint4* __restrict__ order_rec, uint4* __restrict__ end_rec, uint8_t* __restrict__ pal)
+{
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const uint8_t* s = ebases + eoff[e];
+    uint32_t len = elen[e];
+    bool p = seq_form_packed(s, len) == PAL;
+    pal[e] = p ? 1 : 0;
+    Kmer kf = kmer_from_packed(s, 0), kl = kmer_from_packed(s, len - SN_K);
+    order_rec[e] = make_uint4(~len, kf.w0, kf.w1, e);
+    Kmer a = kf; a.w2 &= ~3u;                          // first K-1 bases
+    Kmer b = kmer_succ(kl, 0);                          // last K-1 bases
+    Kmer rl = kmer_rc(kl); rl.w2 &= ~3u;                // first K-1 bases of the reverse complement
+    Kmer rf = kmer_succ(kmer_rc(kf), 0);                // last K-1 bases of the reverse complement
+    const uint4 inval = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    end_rec[4ull * e + 0] = make_uint4(a.w0, a.w1, a.w2, (e << 2) | 0u);
+    end_rec[4ull * e + 1] = make_uint4(b.w0, b.w1, b.w2, (e << 2) | 1u);
+    end_rec[4ull * e + 2] = p ? inval : make_uint4(rl.w0, rl.w1, rl.w2, (e << 2) | 2u);
+    end_rec[4ull * e + 3] = p ? inval : make_uint4(rf.w0, rf.w1, rf.w2, (e << 2) | 3u);
+}
+__global__ void __launch_bounds__(256) k_hbv_mark(const uint4* __restrict__ rec, uint32_t n, uint32_t* __restrict__ flag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = rec[i];
+    bool valid = r.w != 0xFFFFFFFFu;
+    flag[i] = (valid && (i == 0 || !same_kmer(rec[i - 1], r))) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_hbv_assign(const uint4* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos,
+                                                    int32_t* __restrict__ end_group, uint32_t* __restrict__ items, uint32_t* __restrict__ gstart)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = rec[i];
+    if (r.w == 0xFFFFFFFFu) return;
+    uint32_t g = (uint32_t)pos[i] + flag[i] - 1u;
+    end_group[r.w] = (int32_t)g;
+    items[i] = r.w;
+    if (flag[i]) gstart[g] = i;
+}
+
+// ---------------------------------------------------------------------------
 // a10-a13. ReadPath threading, one read per thread.  mode 0: lengths + offsets only;
 // mode 1: also the edge lists at path_off[r].
 // ---------------------------------------------------------------------------

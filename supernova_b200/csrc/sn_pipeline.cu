@@ -185,6 +185,7 @@ void sn_ctx_destroy(sn_ctx* c)
 }
 const char* sn_last_error(const sn_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 uint64_t sn_kernel_launches(const sn_ctx* c) { return c ? c->launches : 0; }
+void* sn_stream(const sn_ctx* c) { return c ? (void*)c->st : nullptr; }
 double sn_stage_ms(const sn_ctx* c, const char* name)
 {
     if (!c || !name) return -1.0;
@@ -288,9 +289,14 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         KCHECK("k_extract");
         t_end(c, "extract");
         // a4
+        t_begin(c, "sort_hist");
+        cudaError_t e = radix_sort_histograms(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
+        c->launches += 2;
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort histograms: ") + cudaGetErrorString(e));
+        t_end(c, "sort_hist");
         t_begin(c, "sort");
-        cudaError_t e = radix_sort_kmers(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
-        c->launches += 2 + SN_RS_PASSES;
+        e = radix_sort_passes(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->st);
+        c->launches += SN_RS_PASSES;
         if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
         t_end(c, "sort");
         // a5 (dictionary is compacted into kb, which is no longer needed by the sort)
@@ -414,32 +420,66 @@ int sn_build_hbv(sn_ctx* c)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "sn_build_hbv: run sn_build_edges first");
     CU(cudaSetDevice(c->device));
+    // a8 on the device: end keys, canonical pre-order, vertex groups
+    snh::HbvPre pre;
+    const uint32_t nE32 = (uint32_t)c->cnt.n_edges;
+    if (nE32) {
+        t_begin(c, "hbv_dev");
+        const uint32_t n4 = 4 * nE32;
+        DevBuf ord_a, ord_b, end_a, end_b, tmp, pal, flag, pos, egrp, items, gstart;
+        CU(ord_a.alloc(16ull * nE32)); CU(ord_b.alloc(16ull * nE32)); CU(end_a.alloc(16ull * n4)); CU(end_b.alloc(16ull * n4));
+        CU(tmp.alloc(radix_sort_tmp_bytes(n4))); CU(pal.alloc(nE32)); CU(flag.alloc(4ull * n4)); CU(pos.alloc(8ull * (n4 + 1)));
+        CU(egrp.alloc(4ull * n4)); CU(items.alloc(4ull * n4)); CU(gstart.alloc(4ull * (n4 + 1)));
+        CU(cudaMemsetAsync(egrp.p, 0xFF, 4ull * n4, c->st));
+        k_hbv_keys<<<blocks_for(nE32, 128), 128, 0, c->st>>>(c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), c->elen.as<uint32_t>(), nE32,
+            ord_a.as<uint4>(), end_a.as<uint4>(), pal.as<uint8_t>());
+        KCHECK("k_hbv_keys");
+        cudaError_t e = radix_sort_kmers(ord_a.as<uint4>(), ord_b.as<uint4>(), nE32, tmp.p, c->num_sms, c->st);
+        if (e == cudaSuccess) e = radix_sort_kmers(end_a.as<uint4>(), end_b.as<uint4>(), n4, tmp.p, c->num_sms, c->st);
+        c->launches += 2 * (2 + SN_RS_PASSES);
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv sort: ") + cudaGetErrorString(e));
+        k_hbv_mark<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>());
+        KCHECK("k_hbv_mark");
+        uint64_t n_groups = 0;
+        int r0 = scan_u32(c, flag.as<uint32_t>(), n4, pos.as<uint64_t>(), &n_groups);
+        if (r0) return r0;
+        k_hbv_assign<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>(), pos.as<uint64_t>(),
+            egrp.as<int32_t>(), items.as<uint32_t>(), gstart.as<uint32_t>());
+        KCHECK("k_hbv_assign");
+        t_end(c, "hbv_dev");
+        pre.order.resize(nE32); pre.pal.resize(nE32); pre.end_group.resize(n4); pre.group_start.resize(n_groups + 1);
+        std::vector<uint32_t> items_h(n4);
+        CU(cudaMemcpy2DAsync(pre.order.data(), 4, (const char*)ord_a.p + 12, 16, 4, nE32, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(pre.pal.data(), pal.p, nE32, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(pre.end_group.data(), egrp.p, 4ull * n4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(pre.group_start.data(), gstart.p, 4ull * n_groups, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(items_h.data(), items.p, 4ull * n4, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        uint64_t npal = 0; for (uint8_t p : pre.pal) npal += p;
+        const uint64_t nvalid = (uint64_t)n4 - 2 * npal;       // invalid (palindrome rc) records sort last
+        pre.group_start[n_groups] = (uint32_t)nvalid;
+        items_h.resize(nvalid);
+        pre.group_items.swap(items_h);
+    }
     auto t0 = std::chrono::steady_clock::now();
-    try { snh::build_hbv(c->hedges, c->hbv); }
+    try { snh::build_hbv(c->hedges, pre, c->hbv); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     const snh::Hbv& H = c->hbv;
-    const size_t nV = H.from.size(), nH = H.src.size(), nE = H.fwd.size();
+    const size_t nV = (size_t)H.n_vert, nH = H.src.size(), nE = H.fwd.size();
     c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
-    std::vector<uint32_t> fs(nV + 1, 0), ts(nV + 1, 0);
-    std::vector<int32_t> fv, fe, tv, te; fv.reserve(nH); fe.reserve(nH); tv.reserve(nH); te.reserve(nH);
-    for (size_t v = 0; v < nV; ++v) {
-        fs[v + 1] = fs[v] + (uint32_t)H.from[v].size(); ts[v + 1] = ts[v] + (uint32_t)H.to[v].size();
-        fv.insert(fv.end(), H.from[v].begin(), H.from[v].end()); fe.insert(fe.end(), H.from_eo[v].begin(), H.from_eo[v].end());
-        tv.insert(tv.end(), H.to[v].begin(), H.to[v].end()); te.insert(te.end(), H.to_eo[v].begin(), H.to_eo[v].end());
-    }
     int r;
     if ((r = upload(c, c->d_fwd, H.fwd.data(), 4 * nE, 16))) return r;
     if ((r = upload(c, c->d_rev, H.rev.data(), 4 * nE, 16))) return r;
     if ((r = upload(c, c->d_toleft, H.to_left.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_toright, H.to_right.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_src, H.src.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_from_start, fs.data(), 4 * (nV + 1), 16))) return r;
-    if ((r = upload(c, c->d_to_start, ts.data(), 4 * (nV + 1), 16))) return r;
-    if ((r = upload(c, c->d_from_v, fv.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_from_e, fe.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_to_v, tv.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_to_e, te.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_from_start, H.from_start.data(), 4 * (nV + 1), 16))) return r;
+    if ((r = upload(c, c->d_to_start, H.to_start.data(), 4 * (nV + 1), 16))) return r;
+    if ((r = upload(c, c->d_from_v, H.from_v.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_from_e, H.from_e.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_to_v, H.to_v.data(), 4 * nH, 16))) return r;
+    if ((r = upload(c, c->d_to_e, H.to_e.data(), 4 * nH, 16))) return r;
     CU(cudaStreamSynchronize(c->st));
     c->stage = 4;
     return SN_OK;
@@ -547,15 +587,15 @@ int sn_get_hbv(sn_ctx* c, uint32_t* from_start, int32_t* from_v, int32_t* from_e
     if (!c) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
     const snh::Hbv& H = c->hbv;
-    size_t nV = H.from.size(), f = 0, t = 0;
-    for (size_t v = 0; v < nV; ++v) {
-        if (from_start) from_start[v] = (uint32_t)f;
-        if (to_start) to_start[v] = (uint32_t)t;
-        for (size_t i = 0; i < H.from[v].size(); ++i, ++f) { if (from_v) from_v[f] = H.from[v][i]; if (from_e) from_e[f] = H.from_eo[v][i]; }
-        for (size_t i = 0; i < H.to[v].size(); ++i, ++t) { if (to_v) to_v[t] = H.to[v][i]; if (to_e) to_e[t] = H.to_eo[v][i]; }
+    size_t nV = (size_t)H.n_vert, nH = H.src.size();
+    if (from_start) memcpy(from_start, H.from_start.data(), 4 * (nV + 1));
+    if (to_start) memcpy(to_start, H.to_start.data(), 4 * (nV + 1));
+    if (nH) {
+        if (from_v) memcpy(from_v, H.from_v.data(), 4 * nH);
+        if (from_e) memcpy(from_e, H.from_e.data(), 4 * nH);
+        if (to_v) memcpy(to_v, H.to_v.data(), 4 * nH);
+        if (to_e) memcpy(to_e, H.to_e.data(), 4 * nH);
     }
-    if (from_start) from_start[nV] = (uint32_t)f;
-    if (to_start) to_start[nV] = (uint32_t)t;
     if (fwd_xlat && !H.fwd.empty()) memcpy(fwd_xlat, H.fwd.data(), 4 * H.fwd.size());
     if (rev_xlat && !H.rev.empty()) memcpy(rev_xlat, H.rev.data(), 4 * H.rev.size());
     if (inv && !H.inv.empty()) memcpy(inv, H.inv.data(), 4 * H.inv.size());
@@ -589,7 +629,10 @@ int sn_write_hbv(sn_ctx* c, const char* path)
     if (!c || !path) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
     std::string err; const snh::Hbv& H = c->hbv;
-    if (!snf::write_hbv(path, H.K, H.from, H.from_eo, H.to_eo, H.epacked.data(), H.eoff.data(), H.elen.data(), H.elen.size(), err))
+    std::vector<uint8_t> ep; std::vector<uint64_t> eo; std::vector<uint32_t> el;
+    snh::hbv_edge_sequences(c->hedges, H, ep, eo, el);
+    if (!snf::write_hbv(path, H.K, (uint64_t)H.n_vert, H.from_start.data(), H.from_v.data(), H.from_e.data(), H.to_start.data(), H.to_e.data(),
+                        ep.data(), eo.data(), el.data(), el.size(), err))
         return fail(c, SN_ERR_IO, err);
     return SN_OK;
 }

@@ -271,18 +271,25 @@ inline size_t radix_sort_tmp_bytes(uint32_t n)
     uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
     return (size_t)SN_RS_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
 }
-// Sorts n (< 2^32) records.  Result ends in `a` (12 passes ping-pong a->b->a...).
-inline cudaError_t radix_sort_kmers(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+// Sorts n (< 2^32) records in two steps so the caller can time them apart:
+// radix_sort_histograms (one read of the records) then radix_sort_passes (12 digit passes,
+// each one read + one write).  Result ends in `a` (12 passes ping-pong a->b->a...).
+inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    uint32_t* hist = (uint32_t*)tmp;
+    cudaMemsetAsync(hist, 0, (SN_RS_PASSES * 256 + 16) * 4, st);
+    k_rs_histogram<<<num_sms * 8, 256, 0, st>>>(a, n, hist);
+    k_rs_scan_hist<<<SN_RS_PASSES, 256, 0, st>>>(hist);
+    return cudaGetLastError();
+}
+inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
     uint32_t* hist = (uint32_t*)tmp;
     uint32_t* counters = hist + SN_RS_PASSES * 256;
     uint64_t* status = (uint64_t*)(counters + 16);
-    cudaMemsetAsync(hist, 0, (SN_RS_PASSES * 256 + 16) * 4, st);
-    int hb = num_sms * 8;
-    k_rs_histogram<<<hb, 256, 0, st>>>(a, n, hist);
-    k_rs_scan_hist<<<SN_RS_PASSES, 256, 0, st>>>(hist);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
@@ -296,6 +303,13 @@ inline cudaError_t radix_sort_kmers(uint4* a, uint4* b, uint32_t n, void* tmp, i
         uint4* t = src; src = dst; dst = t;
     }
     return cudaGetLastError();
+}
+
+inline cudaError_t radix_sort_kmers(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+{
+    cudaError_t e = radix_sort_histograms(a, n, tmp, num_sms, st);
+    if (e != cudaSuccess) return e;
+    return radix_sort_passes(a, b, n, tmp, st);
 }
 
 }  // namespace sn

@@ -34,12 +34,46 @@ def make_genome(G: int, seed: int):
     return hap_a, hap_b
 
 
+_HAP = None
+
+
+def _gen_chunk(args):
+    """Reads of pairs [c0,c1): an independent Philox stream keyed by (seed+2, c0)."""
+    G, seed, L, c0, c1, shard = args
+    hap = _HAP
+    perr = (0.001 + 0.02 * (np.arange(L) / L) ** 3).astype(np.float32)
+    ar = np.arange(L, dtype=np.int64)
+    m = c1 - c0
+    crng = np.random.Generator(np.random.Philox(key=[seed + 2 + 7919 * shard, c0]))
+    h = crng.integers(0, 2, size=m)
+    ins = crng.integers(300, 500, size=m)
+    start = (crng.random(m) * (G - ins)).astype(np.int64)
+    flip = crng.random(m) < 0.5
+    fwd = hap[h[:, None], start[:, None] + ar[None, :]]
+    rev = 3 - hap[h[:, None], (start + ins - 1)[:, None] - ar[None, :]]
+    r1 = np.where(flip[:, None], rev, fwd)
+    r2 = np.where(flip[:, None], fwd, rev)
+    blk = np.empty((2 * m, L), dtype=np.uint8)
+    blk[0::2] = r1
+    blk[1::2] = r2
+    err = crng.random((2 * m, L), dtype=np.float32) < perr[None, :]
+    sub = crng.integers(1, 4, size=(2 * m, L), dtype=np.uint8)
+    blk = np.where(err, (blk + sub) & 3, blk).astype(np.uint8)
+    q = np.where(crng.random((2 * m, L), dtype=np.float32) < 0.05, 30, 37).astype(np.uint8)
+    qerr = np.array([2, 12, 20], dtype=np.uint8)[crng.integers(0, 3, size=(2 * m, L))]
+    q = np.where(err, qerr, q).astype(np.uint8)
+    return blk, q
+
+
 def make_reads(G: int, n_pairs: int, n_bc: int, seed: int, L: int = 150,
-               unbarcoded_frac: float = 0.02, chunk: int = 200_000):
+               unbarcoded_frac: float = 0.02, chunk: int = 100_000, workers: int = 1, shard: int = 0):
     """Returns (bases[n_reads,L] u8 codes, quals[n_reads,L] u8, bc[n_reads] i32 ordinal,
-    bc_ids[n_reads] i64 raw barcode id or -1)."""
-    hap = np.stack(make_genome(G, seed))
-    rng = np.random.Generator(np.random.Philox(key=seed + 1))
+    bc_ids[n_reads] i64 raw barcode id or -1).  `workers` > 1 generates the chunks in forked
+    processes; the result does not depend on it.  `shard` > 0 draws a different, independent
+    set of pairs (and barcodes) from the SAME genome (multi-GPU read shards)."""
+    global _HAP
+    _HAP = np.stack(make_genome(G, seed))
+    rng = np.random.Generator(np.random.Philox(key=seed + 1 + 7919 * shard))
     bcid = rng.integers(0, n_bc, size=n_pairs, dtype=np.int64)
     unb = rng.random(n_pairs) < unbarcoded_frac
     bcid[unb] = -1
@@ -55,31 +89,19 @@ def make_reads(G: int, n_pairs: int, n_bc: int, seed: int, L: int = 150,
     n_reads = 2 * n_pairs
     bases = np.empty((n_reads, L), dtype=np.uint8)
     quals = np.empty((n_reads, L), dtype=np.uint8)
-    perr = (0.001 + 0.02 * (np.arange(L) / L) ** 3).astype(np.float32)
-    ar = np.arange(L, dtype=np.int64)
-    for c0 in range(0, n_pairs, chunk):
-        c1 = min(n_pairs, c0 + chunk)
-        m = c1 - c0
-        crng = np.random.Generator(np.random.Philox(key=[seed + 2, c0]))
-        h = crng.integers(0, 2, size=m)
-        ins = crng.integers(300, 500, size=m)
-        start = (crng.random(m) * (G - ins)).astype(np.int64)
-        flip = crng.random(m) < 0.5
-        fwd = hap[h[:, None], start[:, None] + ar[None, :]]
-        rev = 3 - hap[h[:, None], (start + ins - 1)[:, None] - ar[None, :]]
-        r1 = np.where(flip[:, None], rev, fwd)
-        r2 = np.where(flip[:, None], fwd, rev)
-        blk = np.empty((2 * m, L), dtype=np.uint8)
-        blk[0::2] = r1
-        blk[1::2] = r2
-        err = crng.random((2 * m, L), dtype=np.float32) < perr[None, :]
-        sub = crng.integers(1, 4, size=(2 * m, L), dtype=np.uint8)
-        blk = np.where(err, (blk + sub) & 3, blk).astype(np.uint8)
-        q = np.where(crng.random((2 * m, L), dtype=np.float32) < 0.05, 30, 37).astype(np.uint8)
-        qerr = np.array([2, 12, 20], dtype=np.uint8)[crng.integers(0, 3, size=(2 * m, L))]
-        q = np.where(err, qerr, q).astype(np.uint8)
-        bases[2 * c0:2 * c1] = blk
-        quals[2 * c0:2 * c1] = q
+    jobs = [(G, seed, L, c0, min(n_pairs, c0 + chunk), shard) for c0 in range(0, n_pairs, chunk)]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            for (g, s, l, c0, c1, sh), (blk, q) in zip(jobs, pool.imap(_gen_chunk, jobs)):
+                bases[2 * c0:2 * c1] = blk
+                quals[2 * c0:2 * c1] = q
+    else:
+        for job in jobs:
+            blk, q = _gen_chunk(job)
+            bases[2 * job[3]:2 * job[4]] = blk
+            quals[2 * job[3]:2 * job[4]] = q
+    _HAP = None
     bc = np.repeat(ordinal, 2)
     return bases, quals, bc, np.repeat(bcid, 2)
 

@@ -20,7 +20,6 @@ struct Sim {
     std::vector<uint32_t> idx;
     snh::Edges edges;
     snh::Hbv hbv;
-    std::vector<uint32_t> fs, ts; std::vector<int32_t> fv, fe, tv, te;
     std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
     DictView view() const { DictView d; d.tab = tab.data(); d.idx = idx.data(); d.n = (uint32_t)tab.size(); return d; }
 };
@@ -140,16 +139,12 @@ int hs_hbv(Sim* s, const char* hbv_path)
 {
     snh::build_hbv(s->edges, s->hbv);
     const snh::Hbv& H = s->hbv;
-    size_t nV = H.from.size();
-    s->fs.assign(nV + 1, 0); s->ts.assign(nV + 1, 0); s->fv.clear(); s->fe.clear(); s->tv.clear(); s->te.clear();
-    for (size_t v = 0; v < nV; ++v) {
-        s->fs[v + 1] = s->fs[v] + (uint32_t)H.from[v].size(); s->ts[v + 1] = s->ts[v] + (uint32_t)H.to[v].size();
-        s->fv.insert(s->fv.end(), H.from[v].begin(), H.from[v].end()); s->fe.insert(s->fe.end(), H.from_eo[v].begin(), H.from_eo[v].end());
-        s->tv.insert(s->tv.end(), H.to[v].begin(), H.to[v].end()); s->te.insert(s->te.end(), H.to_eo[v].begin(), H.to_eo[v].end());
-    }
     if (hbv_path) {
         std::string err;
-        if (!snf::write_hbv(hbv_path, H.K, H.from, H.from_eo, H.to_eo, H.epacked.data(), H.eoff.data(), H.elen.data(), H.elen.size(), err)) return -1;
+        std::vector<uint8_t> ep; std::vector<uint64_t> eo; std::vector<uint32_t> el;
+        snh::hbv_edge_sequences(s->edges, H, ep, eo, el);
+        if (!snf::write_hbv(hbv_path, H.K, (uint64_t)H.n_vert, H.from_start.data(), H.from_v.data(), H.from_e.data(), H.to_start.data(),
+                            H.to_e.data(), ep.data(), eo.data(), el.data(), el.size(), err)) return -1;
     }
     return 0;
 }
@@ -162,8 +157,8 @@ int hs_paths(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t* bof
     EdgeStore es; es.bases = s->edges.packed.data(); es.off = s->edges.off.data(); es.len = s->edges.len.data();
     const snh::Hbv& H = s->hbv;
     HbvView h; h.fwd_xlat = H.fwd.data(); h.rev_xlat = H.rev.data(); h.to_left = H.to_left.data(); h.to_right = H.to_right.data();
-    h.src = H.src.data(); h.from_start = s->fs.data(); h.from_v = s->fv.data(); h.from_e = s->fe.data();
-    h.to_start = s->ts.data(); h.to_v = s->tv.data(); h.to_e = s->te.data();
+    h.src = H.src.data(); h.from_start = H.from_start.data(); h.from_v = H.from_v.data(); h.from_e = H.from_e.data();
+    h.to_start = H.to_start.data(); h.to_v = H.to_v.data(); h.to_e = H.to_e.data();
     s->poffset.assign(n_reads, 0); s->poff.assign(n_reads + 1, 0); s->pedges.clear();
     std::vector<Part> parts(SN_MAX_PARTS);
     RPath* path = new RPath();
