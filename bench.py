@@ -39,6 +39,7 @@ WORKLOADS = {
     "C1": (50_000, 10_000, 500, 1234),
 }
 SAMPLE_DIV = 12          # cpu_baseline sample = the workload's generator at 1/12 scale
+SORT_PASSES = 4           # 8-bit digit passes over the 32-bit k-mer hash (sn_prims.cuh RS_HASH32)
 ALG_BYTES_PER_BASE = 24.2  # algorithmic HBM bytes per input base, count+HBV
 
 
@@ -245,9 +246,9 @@ def main():
     peak, peak_src = peaks()
     n_occ = counts["n_kmer_occurrences"]
     sort_ms = stage.get("sort", 0.0)
-    per_launch_ms = sort_ms / 12.0 if sort_ms else None
+    per_launch_ms = sort_ms / SORT_PASSES if sort_ms else None
     achieved = (32.0 * n_occ / 1e9) / (per_launch_ms / 1e3) if per_launch_ms else None
-    roof = {"bound": "hbm", "kernel": "k_rs_scatter (one 8-bit digit pass of the 128-bit k-mer record sort; 12 launches per step)",
+    roof = {"bound": "hbm", "kernel": "k_rs_scatter<RS_HASH32> (one 8-bit digit pass of the 128-bit k-mer record sort; %d launches per step)" % SORT_PASSES,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": None, "algorithmic_bytes_per_launch": 32 * n_occ, "launch_ms": per_launch_ms, "peak_source": peak_src,
             "pipeline_algorithmic_frac": (ALG_BYTES_PER_BASE * value / world) / peak}

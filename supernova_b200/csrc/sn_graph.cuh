@@ -89,16 +89,16 @@ SN_HD uint32_t walk_edge(const DictView& d, uint32_t i, int type, F&& f)
     return n;
 }
 
-// simpleCircle (:348-372) restricted to the circle's minimum entry: entry i walks its
-// successors; it gives up (returns 0) as soon as it meets an entry with a smaller
-// index (the table is sorted, so index order == k-mer order and only the minimum
-// k-mer of a circle completes the walk -- which is where canonicalizeCircle
-// (:375-397) rotates the circle to anyway).  Returns the number of k-mers.
+// simpleCircle (:348-372).  Leader election: every k-mer of a smooth circle walks its
+// successors and gives up (returns 0) as soon as it meets an entry with a smaller table index,
+// so exactly one walker per circle completes the loop (`elect` = true).  With `elect` = false
+// the walk always completes (used by the owner to emit the edge).  f(step, entry, base) is
+// called for every k-mer after the first.  Returns the number of k-mers.
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
 template <class F>
-SN_HD uint32_t walk_circle(const DictView& d, uint32_t i, F&& f)
+SN_HD uint32_t walk_circle(const DictView& d, uint32_t i, bool elect, F&& f)
 {
     const DictEntry& e = d.tab[i];
     Kmer k = entry_kmer(e);
@@ -110,7 +110,7 @@ SN_HD uint32_t walk_circle(const DictView& d, uint32_t i, F&& f)
         uint32_t nctx;
         uint32_t j = oriented_lookup(d, nx, &nctx);
         if (j == i) break;
-        if (j < i) return 0;
+        if (elect && j < i) return 0;
         f(n, j, c);
         k = nx; ctx = nctx; ++n;
     }

@@ -19,14 +19,15 @@ namespace sn {
 // ---------------------------------------------------------------------------
 // a1. PQVec decode (feudal/PQVec.cc:129-187 block format: [nQs u8][nBits:3|minQ:6]
 // [nQs x nBits packed, LSB first] ... 0) fused with GoodLenTailFinder
-// (BuildReadQGraph48.cc:65-89).  One read per thread; quals are written once as u8
-// for the pathing stage.  goodLen = right end of the right-most run of >= K quals
-// >= minQual (what the backwards scan of the reference finds first).
-// Also accumulates the number of k-mer occurrences Kmerizer::map will emit.
+// (BuildReadQGraph48.cc:65-89).  One read per thread; nothing but the good length leaves the
+// thread (the pathing kernel decodes the quals of its read again on demand -- 0.31 B/base of
+// PQVec is cheaper to re-read than 1 B/base of unpacked quals is to write and read).
+// goodLen = right end of the right-most run of >= K quals >= minQual (what the backwards scan
+// of the reference finds first).  Also accumulates the number of k-mer occurrences
+// Kmerizer::map will emit.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
-                                                       const uint32_t* __restrict__ len, const uint64_t* __restrict__ qoff,
-                                                       uint8_t* __restrict__ quals, uint32_t min_qual,
+                                                       const uint32_t* __restrict__ len, uint32_t min_qual,
                                                        uint32_t* __restrict__ goodlen, unsigned long long* occ_total, uint32_t* bad_reads)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,7 +35,6 @@ __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const u
     if (r < n_reads) {
         const uint8_t* p = pq + pq_off[r];
         const uint8_t* pend = pq + pq_off[r + 1];
-        uint8_t* out = quals + qoff[r];
         uint32_t L = len[r], i = 0, run = 0, gl = 0;
         while (p < pend) {
             uint32_t nq = *p++;
@@ -45,14 +45,13 @@ __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const u
             minq |= (uint32_t)(acc & 1u) << 5; acc >>= 1;
             uint32_t have = 7;
             uint32_t mask = (1u << nbits) - 1u;
-            for (uint32_t k = 0; k < nq; ++k) {
-                uint32_t q = minq;
-                if (nbits) {
+            if (!nbits) {                                   // a block of nq equal quals
+                if (minq >= min_qual) { run += nq; if (run >= SN_K) gl = i + nq; } else run = 0;
+                i += nq;
+            } else {
+                for (uint32_t k = 0; k < nq; ++k) {
                     if (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
-                    q += (uint32_t)acc & mask; acc >>= nbits; have -= nbits;
-                }
-                if (i < L) {
-                    out[i] = (uint8_t)q;
+                    uint32_t q = minq + ((uint32_t)acc & mask); acc >>= nbits; have -= nbits;
                     run = q >= min_qual ? run + 1 : 0;
                     ++i;
                     if (run >= SN_K) gl = i;
@@ -172,22 +171,74 @@ __global__ void __launch_bounds__(256) k_extract(uint64_t n_reads, const uint8_t
 
 // ---------------------------------------------------------------------------
 // a5. Kmerizer::reduce / summarizeEntries / areIgnoredBarcodes / areEnoughBarcodes
-// (BuildReadQGraph48.cc:91-137,174-181) over the sorted records, fused with the
-// ordered compaction of the surviving k-mers into the dictionary (tile look-back).
-// The head record of every run walks its run: count (saturating 2^24-1), OR of
-// contexts, min/max barcode > 0 (>= 2 distinct <=> min != max), "ignored" flag.
+// (BuildReadQGraph48.cc:91-137,174-181) over the records sorted by kmer_hash, fused with
+// the ordered compaction of the surviving k-mers into the dictionary (tile look-back).
+// The first record of every run of EQUAL HASH owns the run.  Almost always the run is one
+// k-mer: count (saturating 2^24-1), OR of contexts, min/max barcode > 0 (>= 2 distinct <=>
+// min != max), "ignored" flag in one walk.  When distinct k-mers collide in a run the owner
+// re-walks it once per k-mer in increasing k-mer order, so the dictionary comes out ordered
+// by (hash, k-mer).
 // ---------------------------------------------------------------------------
 #define SN_RD_THREADS 256
 #define SN_RD_ITEMS 8
 #define SN_RD_TILE (SN_RD_THREADS * SN_RD_ITEMS)
 
 __device__ __forceinline__ bool same_kmer(const uint4& a, const uint4& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+__device__ __forceinline__ bool kmer_lt(const uint4& a, const uint4& b)
+{ return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); }
+
+struct RunStat { uint32_t count, ctx, minbc, maxbc; bool ign; };
+__device__ __forceinline__ void stat_init(RunStat& s) { s.count = 0; s.ctx = 0; s.minbc = 0xFFFFFFFFu; s.maxbc = 0; s.ign = false; }
+__device__ __forceinline__ void stat_add(RunStat& s, uint32_t aux)
+{
+    ++s.count; s.ctx |= aux >> 24;
+    uint32_t b = aux & 0xFFFFFFu;
+    if (b == 0xFFFFFFu) s.ign = true;
+    else if (b) { s.minbc = min(s.minbc, b); s.maxbc = max(s.maxbc, b); }
+}
+__device__ __forceinline__ bool stat_valid(const RunStat& s, uint32_t min_freq, uint32_t min_bc, int has_bc)
+{
+    bool enough = min_bc == 0 || (min_bc == 1 ? s.maxbc != 0 : (s.maxbc != 0 && s.minbc != s.maxbc));
+    return s.count >= min_freq && (!has_bc || s.ign || enough);
+}
+__device__ __forceinline__ DictEntry make_entry(const uint4& k, const RunStat& s, uint32_t h)
+{
+    DictEntry e;
+    e.w0 = k.x; e.w1 = k.y; e.w2 = k.z; e.cc = min(s.count, 0xFFFFFFu) | (s.ctx << 24);
+    e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = s.ctx; e.h = h;
+    return e;
+}
+// Slow path: the run [p0,p1) of equal hash holds more than one k-mer.  Visits the distinct
+// k-mers in increasing order; emits the valid ones at out[pos...] when out != nullptr.
+// Returns the number of valid k-mers.
+__device__ __noinline__ uint32_t reduce_mixed_run(const uint4* __restrict__ keys, uint64_t p0, uint64_t p1, uint32_t h,
+                                                  uint32_t min_freq, uint32_t min_bc, int has_bc, DictEntry* out, uint64_t pos, uint32_t* n_distinct)
+{
+    uint32_t nvalid = 0, ndist = 0;
+    uint4 cur = keys[p0];
+    for (uint64_t p = p0 + 1; p < p1; ++p) { uint4 r = keys[p]; if (kmer_lt(r, cur)) cur = r; }     // smallest k-mer
+    for (;;) {
+        RunStat st; stat_init(st);
+        bool have_next = false; uint4 next = cur;
+        for (uint64_t p = p0; p < p1; ++p) {
+            uint4 r = keys[p];
+            if (same_kmer(r, cur)) stat_add(st, r.w);
+            else if (kmer_lt(cur, r) && (!have_next || kmer_lt(r, next))) { next = r; have_next = true; }
+        }
+        ++ndist;
+        if (stat_valid(st, min_freq, min_bc, has_bc)) { if (out) out[pos + nvalid] = make_entry(cur, st, h); ++nvalid; }
+        if (!have_next) break;
+        cur = next;
+    }
+    if (n_distinct) *n_distinct = ndist;
+    return nvalid;
+}
 
 __global__ void __launch_bounds__(SN_RD_THREADS) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
                                                           DictEntry* __restrict__ out, uint64_t* status, uint32_t* tile_counter,
                                                           uint32_t* n_out, unsigned long long* n_distinct)
 {
-    __shared__ uint32_t words[SN_RD_ITEMS * 8];
+    __shared__ uint32_t wtot[SN_RD_ITEMS * 8];
     __shared__ uint32_t wpref[SN_RD_ITEMS * 8 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_base;
@@ -196,45 +247,59 @@ __global__ void __launch_bounds__(SN_RD_THREADS) k_reduce(const uint4* __restric
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t tbase = (uint64_t)tile * SN_RD_TILE;
-    uint4 kk[SN_RD_ITEMS]; uint32_t cc[SN_RD_ITEMS]; bool ok[SN_RD_ITEMS];
-    uint32_t heads = 0;
-#pragma unroll
+    // per item (kept in shared memory so the walk loop is not unrolled 8x into registers):
+    // cc = count|ctx<<24 of a clean run; nv = entries its run contributes | mixed flag << 31
+    __shared__ uint32_t s_cc[SN_RD_ITEMS][SN_RD_THREADS], s_nv[SN_RD_ITEMS][SN_RD_THREADS], s_incl[SN_RD_ITEMS][SN_RD_THREADS];
+#define cc(j) s_cc[j][tid]
+#define nv(j) s_nv[j][tid]
+#define incl(j) s_incl[j][tid]
+    uint32_t distinct = 0;
+#pragma unroll 1
     for (int j = 0; j < SN_RD_ITEMS; ++j) {
         uint64_t idx = tbase + (uint64_t)j * SN_RD_THREADS + tid;
-        ok[j] = false; cc[j] = 0;
+        nv(j) = 0; cc(j) = 0;
         if (idx < n) {
             uint4 k = keys[idx];
-            kk[j] = k;
-            bool head = idx == 0 || !same_kmer(keys[idx - 1], k);
+            // a run head is first of all the first record of its k-mer (cheap 96-bit compare);
+            // hashes are only computed where the k-mer changes
+            bool head = idx == 0;
+            uint32_t h = 0;
+            if (!head) { uint4 pv = keys[idx - 1]; if (!same_kmer(pv, k)) { h = rs_hash(k); head = rs_hash(pv) != h; } }
+            else h = rs_hash(k);
             if (head) {
-                ++heads;
-                uint32_t count = 0, ctx = 0, minbc = 0xFFFFFFFFu, maxbc = 0; bool ign = false;
-                uint64_t p = idx; uint4 r = k;
-                for (;;) {
-                    ++count; ctx |= r.w >> 24;
-                    uint32_t b = r.w & 0xFFFFFFu;
-                    if (b == 0xFFFFFFu) ign = true;
-                    else if (b) { minbc = min(minbc, b); maxbc = max(maxbc, b); }
-                    if (++p >= n) break;
-                    r = keys[p];
-                    if (!same_kmer(r, k)) break;
+                RunStat st; stat_init(st);
+                bool mixed = false;
+                uint64_t p = idx + 1;
+                stat_add(st, k.w);
+                while (p < n) {                             // the run is [idx, p)
+                    uint4 r = keys[p];
+                    if (same_kmer(r, k)) { stat_add(st, r.w); ++p; continue; }
+                    if (rs_hash(r) != h) break;             // next hash: end of the run
+                    mixed = true; ++p;                      // a different k-mer with the same hash
                 }
-                bool enough = min_bc == 0 || (min_bc == 1 ? maxbc != 0 : (maxbc != 0 && minbc != maxbc));
-                bool bc_test = !has_bc || ign || enough;
-                ok[j] = count >= min_freq && bc_test;
-                cc[j] = min(count, 0xFFFFFFu) | (ctx << 24);
+                if (!mixed) {
+                    nv(j) = stat_valid(st, min_freq, min_bc, has_bc) ? 1u : 0u; ++distinct;
+                    cc(j) = min(st.count, 0xFFFFFFu) | (st.ctx << 24);
+                } else {
+                    uint32_t nd = 0;
+                    uint32_t v = reduce_mixed_run(keys, idx, p, h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
+                    nv(j) = v | (v ? 0x80000000u : 0u);
+                    distinct += nd;
+                }
             }
         }
-        uint32_t bal = __ballot_sync(SN_FULL, ok[j]);
-        if (lane == 0) words[j * 8 + warp] = bal;
+        // inclusive warp scan of the number of entries each record's run contributes
+        uint32_t x = nv(j) & 0x7FFFFFFFu;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+        incl(j) = x;
+        if (lane == 31) wtot[j * 8 + warp] = x;
     }
-    // distinct k-mer count (stat only)
-    for (int o = 16; o > 0; o >>= 1) heads += __shfl_down_sync(SN_FULL, heads, o);
-    if (lane == 0 && heads) atomicAdd(n_distinct, (unsigned long long)heads);
+    for (int o = 16; o > 0; o >>= 1) distinct += __shfl_down_sync(SN_FULL, distinct, o);
+    if (lane == 0 && distinct) atomicAdd(n_distinct, (unsigned long long)distinct);
     __syncthreads();
     if (tid == 0) {
         uint32_t s = 0;
-        for (int i = 0; i < SN_RD_ITEMS * 8; ++i) { wpref[i] = s; s += __popc(words[i]); }
+        for (int i = 0; i < SN_RD_ITEMS * 8; ++i) { wpref[i] = s; s += wtot[i]; }
         wpref[SN_RD_ITEMS * 8] = s;
         uint64_t prev = tile_lookback(status, 1, 0, tile, s);
         s_base = prev;
@@ -242,18 +307,31 @@ __global__ void __launch_bounds__(SN_RD_THREADS) k_reduce(const uint4* __restric
     }
     __syncthreads();
     const uint64_t base = s_base;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < SN_RD_ITEMS; ++j) {
-        if (ok[j]) {
-            uint32_t w = words[j * 8 + warp];
-            uint64_t pos = base + wpref[j * 8 + warp] + __popc(w & lanemask_lt());
-            DictEntry e;
-            e.w0 = kk[j].x; e.w1 = kk[j].y; e.w2 = kk[j].z; e.cc = cc[j];
-            e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = cc[j] >> 24; e.pad = 0;
-            out[pos] = e;
+        uint32_t cnt = nv(j) & 0x7FFFFFFFu;
+        if (cnt) {
+            uint64_t idx = tbase + (uint64_t)j * SN_RD_THREADS + tid;
+            uint64_t pos = base + wpref[j * 8 + warp] + (incl(j) - cnt);
+            uint4 k = keys[idx];
+            uint32_t h = rs_hash(k);
+            if (!(nv(j) >> 31)) {
+                DictEntry e;
+                e.w0 = k.x; e.w1 = k.y; e.w2 = k.z; e.cc = cc(j);
+                e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = cc(j) >> 24; e.h = h;
+                out[pos] = e;
+            } else {
+                uint64_t p = idx + 1;
+                while (p < n && rs_hash(keys[p]) == h) ++p;
+                reduce_mixed_run(keys, idx, p, h, min_freq, min_bc, has_bc, out, pos, nullptr);
+            }
         }
     }
 }
+#undef cc
+#undef nv
+#undef incl
+
 // ---------------------------------------------------------------------------
 // a6. dictionary prefix index + recomputeAdjacencies
 // ---------------------------------------------------------------------------
@@ -264,7 +342,7 @@ __global__ void __launch_bounds__(256) k_build_index(const DictEntry* __restrict
     if (b == (1u << SN_IDX_BITS)) { idx[b] = n; return; }
     uint32_t key = b << (32 - SN_IDX_BITS);
     uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (tab[mid].w0 < key) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (tab[mid].h < key) lo = mid + 1; else hi = mid; }
     idx[b] = lo;
 }
 __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n)
@@ -319,8 +397,11 @@ __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restric
     if (etype[i] != T_INTERIOR || visited[i]) return;
     atomicAdd(n_circle_members, 1u);
     DictView d; d.tab = tab; d.idx = idx; d.n = n;
-    uint32_t nk = walk_circle(d, i, [](uint32_t, uint32_t, uint32_t) {});
-    if (nk) { own_n[i] = nk; etype[i] = SN_T_CIRCLE; }
+    // the walker with the smallest table index completes the loop; the circle is then owned by
+    // its smallest K-MER, where canonicalizeCircle (BuildReadQGraph48.cc:375-397) starts it
+    uint32_t m = i; Kmer mk = entry_kmer(tab[i]);
+    uint32_t nk = walk_circle(d, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(tab[j]); if (q < mk) { mk = q; m = j; } });
+    if (nk) { own_n[m] = nk; etype[m] = SN_T_CIRCLE; }
 }
 __global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, uint32_t n, uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
 {
@@ -352,7 +433,7 @@ __global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const uint32_
     uint32_t nk = 1;
     auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { s[SN_K - 1 + step] = (uint8_t)c; tab[j].edge = e; tab[j].off = step; };
     if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
-    else if (t == SN_T_CIRCLE) nk = walk_circle(d, i, visit);
+    else if (t == SN_T_CIRCLE) nk = walk_circle(d, i, false, visit);
     uint32_t len = nk + SN_K - 1;
     elen[e] = len;
     etmp_off[e] = base_off[i];
@@ -453,10 +534,12 @@ __global__ void __launch_bounds__(256) k_hbv_assign(const uint4* __restrict__ re
 
 // ---------------------------------------------------------------------------
 // a10-a13. ReadPath threading, one read per thread.  mode 0: lengths + offsets only;
-// mode 1: also the edge lists at path_off[r].
+// mode 1: also the edge lists at path_off[r].  Quals come either unpacked (quals/qoff) or as
+// the PQVec stream (pq/pq_off), decoded into a per-thread buffer.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_path_reads(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                     const uint32_t* __restrict__ len, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
+                                                    const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
                                                     DictView d, EdgeStore es, HbvView h, int mode,
                                                     uint32_t* __restrict__ plen, int32_t* __restrict__ poffset,
                                                     const uint64_t* __restrict__ path_off, int32_t* __restrict__ pedges, uint32_t* overflow)
@@ -465,7 +548,11 @@ __global__ void __launch_bounds__(128) k_path_reads(uint64_t n_reads, const uint
     if (r >= n_reads) return;
     Part parts[SN_MAX_PARTS];
     RPath path;
-    path_one_read(d, es, h, bases + boff[r], quals + qoff[r], len[r], parts, path);
+    uint8_t qbuf[SN_MAX_READ_LEN];
+    const uint8_t* q;
+    if (pq) { pqvec_decode(pq + pq_off[r], pq + pq_off[r + 1], qbuf, SN_MAX_READ_LEN); q = qbuf; }
+    else q = quals + qoff[r];
+    path_one_read(d, es, h, bases + boff[r], q, len[r], parts, path);
     if (path.overflow) atomicAdd(overflow, 1u);
     if (mode == 0) { plen[r] = path.n; poffset[r] = path.offset; }
     else { int32_t* o = pedges + path_off[r]; for (uint32_t i = 0; i < path.n; ++i) o[i] = path.e[i]; }

@@ -98,35 +98,58 @@ SN_HD Kmer kmer_from_packed(const uint8_t* p, uint64_t pos)
     return k;
 }
 
-// --- dictionary entry (32 B, one sector) --------------------------------------
-// The valid-k-mer table is sorted by k-mer and doubles as the reference's KmerDict
-// (kmers/ReadPather.h:222-388): w0..w2 + cc (count:24 | ctx<<24, == the kmers.kvec
-// KDef word, context BEFORE recomputeAdjacencies) are immutable after counting;
-// ctx (after pruning), edge and off are filled by the graph stages.
+// --- dictionary ------------------------------------------------------------------
+// 32-bit mix of the 96-bit k-mer.  The k-mer stream is SORTED BY THIS HASH (4 radix digit
+// passes instead of 12 for the full key); equal k-mers share a hash, so they land in one run of
+// equal hashes and k_reduce separates the (rare) distinct k-mers that collide inside a run.
+SN_HD uint32_t kmer_hash(const Kmer& k)
+{
+    uint32_t h = k.w0 * 0x9E3779B1u;
+    h = ((h ^ (h >> 15)) + k.w1) * 0x85EBCA77u;
+    h = ((h ^ (h >> 13)) + k.w2) * 0xC2B2AE3Du;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// Dictionary entry (32 B = one DRAM sector).  The valid-k-mer table doubles as the
+// reference's KmerDict (kmers/ReadPather.h:222-388).  It is ordered by (hash, k-mer); a
+// prefix index over the top SN_IDX_BITS bits of the hash turns a lookup into one index load
+// plus a short binary search.  w0..w2 + cc (count:24 | ctx<<24, == the kmers.kvec KDef word,
+// context BEFORE recomputeAdjacencies) and h are immutable after counting; ctx (after
+// pruning), edge and off are filled by the graph stages.
 struct __attribute__((aligned(32))) DictEntry {
     uint32_t w0, w1, w2, cc;
-    uint32_t edge, off, ctx, pad;
+    uint32_t edge, off, ctx, h;
 };
 #define SN_NULL_EDGE 0xFFFFFFFFu
-#define SN_IDX_BITS 24        // prefix index over the top bits of w0
+#define SN_IDX_BITS 24        // prefix index over the top bits of the hash
 
 struct DictView {
     const DictEntry* tab;
-    const uint32_t* idx;      // (1<<SN_IDX_BITS)+1 lower bounds by top bits of w0
+    const uint32_t* idx;      // (1<<SN_IDX_BITS)+1 lower bounds by top bits of h
     uint32_t n;
 };
 
+// (h,k) < entry ?  /  == entry ?
+SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
+{
+    if (h != e.h) return h < e.h ? -1 : 1;
+    if (k.w0 != e.w0) return k.w0 < e.w0 ? -1 : 1;
+    if (k.w1 != e.w1) return k.w1 < e.w1 ? -1 : 1;
+    if (k.w2 != e.w2) return k.w2 < e.w2 ? -1 : 1;
+    return 0;
+}
 // KmerDict::findEntryCanonical : returns index or SN_NULL_EDGE
 SN_HD uint32_t dict_find_canonical(const DictView& d, const Kmer& k)
 {
-    uint32_t b = k.w0 >> (32 - SN_IDX_BITS);
+    uint32_t h = kmer_hash(k);
+    uint32_t b = h >> (32 - SN_IDX_BITS);
     uint32_t lo = d.idx[b], hi = d.idx[b + 1];
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        const DictEntry& e = d.tab[mid];
-        Kmer m; m.w0 = e.w0; m.w1 = e.w1; m.w2 = e.w2;
-        if (m == k) return mid;
-        if (m < k) lo = mid + 1; else hi = mid;
+        int c = dict_cmp(h, k, d.tab[mid]);
+        if (c == 0) return mid;
+        if (c > 0) lo = mid + 1; else hi = mid;
     }
     return SN_NULL_EDGE;
 }

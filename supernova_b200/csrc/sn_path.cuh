@@ -44,6 +44,33 @@ SN_HD uint32_t hbv_len(const EdgeStore& es, const HbvView& h, int32_t e) { retur
 SN_HD uint32_t hbv_base(const EdgeStore& es, const HbvView& h, int32_t e, uint32_t p)
 { uint32_t s = h.src[e]; return edge_base(es, s >> 1, s & 1u, p); }
 
+// PQVec block stream -> one Phred byte per base (feudal/PQVec.cc:129-187; block format
+// [nQs u8][nBits:3 | minQ:6][nQs x nBits packed, LSB first] ... 0).  Returns the number of
+// quals the stream holds (writes at most `cap`).
+SN_HD uint32_t pqvec_decode(const uint8_t* p, const uint8_t* pend, uint8_t* out, uint32_t cap)
+{
+    uint32_t i = 0;
+    while (p < pend) {
+        uint32_t nq = *p++;
+        if (!nq) break;
+        uint32_t b0 = *p++;
+        uint32_t nbits = b0 & 7u, minq = b0 >> 3;
+        uint64_t acc = *p++;
+        minq |= (uint32_t)(acc & 1u) << 5; acc >>= 1;
+        uint32_t have = 7, mask = (1u << nbits) - 1u;
+        for (uint32_t k = 0; k < nq; ++k) {
+            uint32_t q = minq;
+            if (nbits) {
+                if (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
+                q += (uint32_t)acc & mask; acc >>= nbits; have -= nbits;
+            }
+            if (i < cap) out[i] = (uint8_t)q;
+            ++i;
+        }
+    }
+    return i;
+}
+
 // a10 Pather::path (:705-747).  Returns the number of parts.
 SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t* rd, uint32_t n, Part* parts)
 {

@@ -26,13 +26,26 @@ namespace {
 
 std::string g_create_error;
 
+// Device buffer that keeps its allocation across steps: alloc() only goes to cudaMalloc when
+// the request outgrows the capacity (cudaMalloc/cudaFree of multi-GB buffers cost
+// milliseconds each and serialise the device).
 struct DevBuf {
-    void* p = nullptr; size_t bytes = 0;
+    void* p = nullptr; size_t bytes = 0, cap = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-    cudaError_t alloc(size_t n) { release(); if (!n) n = 16; cudaError_t e = cudaMalloc(&p, n); if (e == cudaSuccess) bytes = n; return e; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; cap = 0; }
+    cudaError_t alloc(size_t n)
+    {
+        if (!n) n = 16;
+        if (p && cap >= n) { bytes = n; return cudaSuccess; }
+        release();
+        size_t want = n + n / 16;                      // a little headroom so step-to-step jitter does not reallocate
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = n; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) { bytes = n; cap = want; }
+        return e;
+    }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -66,6 +79,7 @@ struct sn_ctx {
     DevBuf plen, poffset, path_off, pedges;
     std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
     DevBuf counters;     // small scratch of u64 counters
+    std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
 };
 
 namespace {
@@ -90,13 +104,13 @@ inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + pe
 // exclusive scan helper that owns its temporaries; out has n+1 entries; total returned through *total (host, after sync)
 int scan_u32(sn_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
 {
-    DevBuf tmp;
+    DevBuf& tmp = c->pool["scan_tmp"];
     CU(tmp.alloc(scan_tmp_words(n) * 8 + 16));
     exclusive_scan_u32_u64(in, n, out, tmp.as<uint64_t>(), c->st);
     c->launches += n ? 3 : 0;
     CU(cudaGetLastError());
     if (total) { CU(cudaMemcpyAsync(total, out + n, 8, cudaMemcpyDeviceToHost, c->st)); }
-    CU(cudaStreamSynchronize(c->st));      // tmp is released on return
+    CU(cudaStreamSynchronize(c->st));
     return SN_OK;
 }
 
@@ -257,9 +271,8 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     // a1
     t_begin(c, "goodlen");
     if (c->have_pq) {
-        CU(c->quals.alloc(c->cnt.n_bases + 16));
         k_pqvec_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->qoff.as<uint64_t>(), c->quals.as<uint8_t>(), c->params.min_qual, c->goodlen.as<uint32_t>(), occ, u32c);
+            c->params.min_qual, c->goodlen.as<uint32_t>(), occ, u32c);
         KCHECK("k_pqvec_goodlen");
     } else {
         k_q8_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->len.as<uint32_t>(),
@@ -277,7 +290,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     const uint32_t n_occ = (uint32_t)h_occ;
     c->dict.release(); c->idx.release();
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
-    DevBuf ka, kb, tmp;
+    DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
     if (n_occ) {
         CU(ka.alloc((size_t)n_occ * 16));
         CU(kb.alloc((size_t)n_occ * 16 * (c->params.min_freq >= 2 ? 1 : 2)));
@@ -290,13 +303,13 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         t_end(c, "extract");
         // a4
         t_begin(c, "sort_hist");
-        cudaError_t e = radix_sort_histograms(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
+        cudaError_t e = radix_sort_histograms<RS_HASH32>(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
         c->launches += 2;
         if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort histograms: ") + cudaGetErrorString(e));
         t_end(c, "sort_hist");
         t_begin(c, "sort");
-        e = radix_sort_passes(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->st);
-        c->launches += SN_RS_PASSES;
+        e = radix_sort_passes<RS_HASH32>(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->st);
+        c->launches += RsMode<RS_HASH32>::PASSES;
         if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
         t_end(c, "sort");
         // a5 (dictionary is compacted into kb, which is no longer needed by the sort)
@@ -313,7 +326,6 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
         c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
-        ka.release();
         CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
         CU(cudaMemcpyAsync(c->dict.p, kb.p, (size_t)h_n * sizeof(DictEntry), cudaMemcpyDeviceToDevice, c->st));
         CU(cudaStreamSynchronize(c->st));
@@ -350,7 +362,7 @@ int sn_build_edges(sn_ctx* c)
     t_end(c, "prune");
 
     t_begin(c, "edges");
-    DevBuf etype, own_n, flag, pos, list, visited;
+    DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &pos = c->pool["pos"], &list = c->pool["list"], &visited = c->pool["visited"];
     CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(pos.alloc(8ull * (n + 1))); CU(visited.alloc(n));
     CU(cudaMemsetAsync(visited.p, 0, n, c->st));
     k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
@@ -371,7 +383,7 @@ int sn_build_edges(sn_ctx* c)
     k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), visited.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
     KCHECK("k_circle_count");
     // allocation: bases per owner -> offsets in the unpacked scratch; owner rank -> edge id
-    DevBuf ebases_u32, base_off;
+    DevBuf &ebases_u32 = c->pool["ebases_u32"], &base_off = c->pool["base_off"];
     CU(ebases_u32.alloc(4ull * n)); CU(base_off.alloc(8ull * (n + 1)));
     k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), n, ebases_u32.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_edge_sizes");
@@ -382,7 +394,7 @@ int sn_build_edges(sn_ctx* c)
     CU(list.alloc(4 * n_edges + 16));
     k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
     KCHECK("k_scatter_flagged");
-    DevBuf tmpb, eflip, etmp_off, ebytes;
+    DevBuf &tmpb = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"], &ebytes = c->pool["ebytes"];
     CU(tmpb.alloc(total_bases + 16)); CU(eflip.alloc(n_edges + 16)); CU(etmp_off.alloc(8 * n_edges + 16)); CU(ebytes.alloc(4 * n_edges + 16));
     CU(c->elen.alloc(4 * n_edges + 16)); CU(c->eoff.alloc(8 * (n_edges + 1)));
     k_walk_emit<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, idx, n, list.as<uint32_t>(), (uint32_t)n_edges, etype.as<uint8_t>(),
@@ -426,7 +438,8 @@ int sn_build_hbv(sn_ctx* c)
     if (nE32) {
         t_begin(c, "hbv_dev");
         const uint32_t n4 = 4 * nE32;
-        DevBuf ord_a, ord_b, end_a, end_b, tmp, pal, flag, pos, egrp, items, gstart;
+        DevBuf &ord_a = c->pool["ord_a"], &ord_b = c->pool["ord_b"], &end_a = c->pool["end_a"], &end_b = c->pool["end_b"], &tmp = c->pool["hbv_tmp"],
+               &pal = c->pool["pal"], &flag = c->pool["hflag"], &pos = c->pool["hpos"], &egrp = c->pool["egrp"], &items = c->pool["items"], &gstart = c->pool["gstart"];
         CU(ord_a.alloc(16ull * nE32)); CU(ord_b.alloc(16ull * nE32)); CU(end_a.alloc(16ull * n4)); CU(end_b.alloc(16ull * n4));
         CU(tmp.alloc(radix_sort_tmp_bytes(n4))); CU(pal.alloc(nE32)); CU(flag.alloc(4ull * n4)); CU(pos.alloc(8ull * (n4 + 1)));
         CU(egrp.alloc(4ull * n4)); CU(items.alloc(4ull * n4)); CU(gstart.alloc(4ull * (n4 + 1)));
@@ -434,9 +447,9 @@ int sn_build_hbv(sn_ctx* c)
         k_hbv_keys<<<blocks_for(nE32, 128), 128, 0, c->st>>>(c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), c->elen.as<uint32_t>(), nE32,
             ord_a.as<uint4>(), end_a.as<uint4>(), pal.as<uint8_t>());
         KCHECK("k_hbv_keys");
-        cudaError_t e = radix_sort_kmers(ord_a.as<uint4>(), ord_b.as<uint4>(), nE32, tmp.p, c->num_sms, c->st);
-        if (e == cudaSuccess) e = radix_sort_kmers(end_a.as<uint4>(), end_b.as<uint4>(), n4, tmp.p, c->num_sms, c->st);
-        c->launches += 2 * (2 + SN_RS_PASSES);
+        cudaError_t e = radix_sort<RS_KEY96>(ord_a.as<uint4>(), ord_b.as<uint4>(), nE32, tmp.p, c->num_sms, c->st);
+        if (e == cudaSuccess) e = radix_sort<RS_KEY96>(end_a.as<uint4>(), end_b.as<uint4>(), n4, tmp.p, c->num_sms, c->st);
+        c->launches += 2 * (2 + RsMode<RS_KEY96>::PASSES);
         if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv sort: ") + cudaGetErrorString(e));
         k_hbv_mark<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>());
         KCHECK("k_hbv_mark");
@@ -508,7 +521,8 @@ int sn_path_reads(sn_ctx* c)
         CU(cudaMemsetAsync(c->plen.p, 0, 4 * n, c->st)); CU(cudaMemsetAsync(c->poffset.p, 0, 4 * n, c->st));
     } else {
         k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), d, es, h, 0, c->plen.as<uint32_t>(), c->poffset.as<int32_t>(), nullptr, nullptr, u32c + 5);
+            c->have_pq ? nullptr : c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->have_pq ? c->pq.as<uint8_t>() : nullptr, c->pqoff.as<uint64_t>(),
+            d, es, h, 0, c->plen.as<uint32_t>(), c->poffset.as<int32_t>(), nullptr, nullptr, u32c + 5);
         KCHECK("k_path_reads(count)");
     }
     uint64_t total = 0;
@@ -517,7 +531,8 @@ int sn_path_reads(sn_ctx* c)
     CU(c->pedges.alloc(4 * total + 16));
     if (total) {
         k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), d, es, h, 1, nullptr, nullptr, c->path_off.as<uint64_t>(), c->pedges.as<int32_t>(), u32c + 5);
+            c->have_pq ? nullptr : c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->have_pq ? c->pq.as<uint8_t>() : nullptr, c->pqoff.as<uint64_t>(),
+            d, es, h, 1, nullptr, nullptr, c->path_off.as<uint64_t>(), c->pedges.as<int32_t>(), u32c + 5);
         KCHECK("k_path_reads(emit)");
     }
     t_end(c, "path");
@@ -541,13 +556,25 @@ int sn_get_good_lengths(sn_ctx* c, uint32_t* out)
     CU(cudaMemcpy(out, c->goodlen.p, 4 * c->cnt.n_reads, cudaMemcpyDeviceToHost));
     return SN_OK;
 }
+// The dictionary lives in (hash, k-mer) order; the two getters below hand it out sorted by
+// k-mer (the order of a sorted kmers.kvec), which is an export/debug path, not a hot one.
+static int fetch_dict_sorted(sn_ctx* c, std::vector<DictEntry>& h)
+{
+    size_t n = c->cnt.n_kmers;
+    h.resize(n);
+    if (n) CU(cudaMemcpy(h.data(), c->dict.p, n * sizeof(DictEntry), cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end(), [](const DictEntry& a, const DictEntry& b) {
+        return a.w0 != b.w0 ? a.w0 < b.w0 : (a.w1 != b.w1 ? a.w1 < b.w1 : a.w2 < b.w2); });
+    return SN_OK;
+}
 int sn_get_kmers(sn_ctx* c, sn_kmer_rec* out)
 {
     if (!c || !out) return SN_ERR_ARG;
     if (c->stage < 2) return fail(c, SN_ERR_STATE, "no dictionary yet");
     CU(cudaSetDevice(c->device));
-    if (c->cnt.n_kmers)
-        CU(cudaMemcpy2D(out, sizeof(sn_kmer_rec), c->dict.p, sizeof(DictEntry), sizeof(sn_kmer_rec), c->cnt.n_kmers, cudaMemcpyDeviceToHost));
+    std::vector<DictEntry> h;
+    int r = fetch_dict_sorted(c, h); if (r) return r;
+    for (size_t i = 0; i < h.size(); ++i) { out[i].w[0] = h[i].w0; out[i].w[1] = h[i].w1; out[i].w[2] = h[i].w2; out[i].count_ctx = h[i].cc; }
     return SN_OK;
 }
 int sn_get_kmer_graph_info(sn_ctx* c, uint8_t* ctx_pruned, uint32_t* edge, uint32_t* offset)
@@ -555,10 +582,9 @@ int sn_get_kmer_graph_info(sn_ctx* c, uint8_t* ctx_pruned, uint32_t* edge, uint3
     if (!c) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
     CU(cudaSetDevice(c->device));
-    size_t n = c->cnt.n_kmers;
-    std::vector<DictEntry> h(n);
-    if (n) CU(cudaMemcpy(h.data(), c->dict.p, n * sizeof(DictEntry), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) {
+    std::vector<DictEntry> h;
+    int r = fetch_dict_sorted(c, h); if (r) return r;
+    for (size_t i = 0; i < h.size(); ++i) {
         if (ctx_pruned) ctx_pruned[i] = (uint8_t)h[i].ctx;
         if (edge) edge[i] = h[i].edge;
         if (offset) offset[i] = h[i].off;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "sn_kmer.cuh"
 
 namespace sn {
 
@@ -133,33 +134,50 @@ inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out
 }
 
 // ---------------------------------------------------------------------------
-// radix sort of uint4 records by (x,y,z) = (w0,w1,w2), LSD, 8-bit digits.
+// LSD radix sort of uint4 records {x,y,z,w} = {w0,w1,w2,aux}, 8-bit digits, two key modes:
+//   RS_KEY96  : the 96-bit (x,y,z) key, 12 passes            (HBV end keys, exports)
+//   RS_HASH32 : kmer_hash(x,y,z), 4 passes                    (the k-mer stream)
+// Every pass reads each record once and writes it once.
 // ---------------------------------------------------------------------------
-#define SN_RS_THREADS 256
-#define SN_RS_ITEMS 16
+#define SN_RS_THREADS 512
+#define SN_RS_WARPS (SN_RS_THREADS / 32)
+#define SN_RS_ITEMS 8
 #define SN_RS_TILE (SN_RS_THREADS * SN_RS_ITEMS)
-#define SN_RS_PASSES 12
+enum { RS_KEY96 = 0, RS_HASH32 = 1 };
+template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : 4; };
+#define SN_RS_MAX_PASSES 12
 
+__device__ __forceinline__ uint32_t rs_hash(const uint4& k) { Kmer q; q.w0 = k.x; q.w1 = k.y; q.w2 = k.z; return kmer_hash(q); }
+template <int MODE>
 __device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
 {
+    if (MODE == RS_HASH32) return (rs_hash(k) >> (8 * pass)) & 0xFFu;
     uint32_t w = pass < 4 ? k.z : (pass < 8 ? k.y : k.x);
     return (w >> (8 * (pass & 3))) & 0xFFu;
 }
 
-// all 12 digit histograms in one pass over the records (they are invariant under
-// the permutations the later passes apply).  hist[pass*256 + digit], u32 counts.
+// all digit histograms in one pass over the records (they are invariant under the
+// permutations the later passes apply).  hist[pass*256 + digit], u32 counts.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t sh[SN_RS_PASSES * 256];
-    for (int i = threadIdx.x; i < SN_RS_PASSES * 256; i += blockDim.x) sh[i] = 0;
+    constexpr int P = RsMode<MODE>::PASSES;
+    __shared__ uint32_t sh[P * 256];
+    for (int i = threadIdx.x; i < P * 256; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint4 k = keys[i];
+        if (MODE == RS_HASH32) {
+            uint32_t h = rs_hash(k);
 #pragma unroll
-        for (int p = 0; p < SN_RS_PASSES; ++p) atomicAdd(&sh[p * 256 + rs_digit(k, p)], 1u);
+            for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + ((h >> (8 * p)) & 0xFFu)], 1u);
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + rs_digit<MODE>(k, p)], 1u);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SN_RS_PASSES * 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    for (int i = threadIdx.x; i < P * 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 // exclusive scan of each pass's 256 bins, in place (one block of 256 threads per pass)
 __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
@@ -179,15 +197,16 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
 }
 
 struct RsSmem {
-    uint4 keys[SN_RS_TILE];            // 64 KB reorder buffer
-    uint32_t warp_cnt[8][256];         // per-warp digit counters -> exclusive warp offsets
-    uint32_t tile_start[256];          // exclusive scan of the tile's digit totals
-    uint32_t gdst[256];                // global destination of smem slot s with digit d: gdst[d] + s
+    uint4 keys[SN_RS_TILE];                    // 64 KB reorder buffer
+    uint32_t warp_cnt[SN_RS_WARPS][256];       // per-warp digit counters -> exclusive warp offsets
+    uint32_t tile_start[256];                  // exclusive scan of the tile's digit totals
+    uint32_t gdst[256];                        // global destination of smem slot s with digit d: gdst[d] + s
     uint32_t scan_tmp[8];
     uint32_t tile_id;
 };
 
 // One digit pass: read each record once, write it once.
+template <int MODE>
 __global__ void __launch_bounds__(SN_RS_THREADS, 2)
 k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, int pass,
              const uint32_t* __restrict__ ghist /* exclusive starts, this pass */, uint64_t* status, uint32_t* tile_counter)
@@ -197,60 +216,62 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) S.tile_id = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < 8 * 256; i += SN_RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    for (int i = tid; i < SN_RS_WARPS * 256; i += SN_RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile_id;
     const uint64_t tile_base = (uint64_t)tile * SN_RS_TILE;
     const uint32_t valid = (uint32_t)min((uint64_t)SN_RS_TILE, (uint64_t)n - tile_base);
 
-    // warp-striped load: warp w owns [w*512, (w+1)*512); item j of lane l is w*512 + j*32 + l
+    // warp-striped load: warp w owns [w*256, (w+1)*256); item j of lane l is w*256 + j*32 + l.
+    // Records past the end get digit 255 and the highest ranks of it: they are never written.
     uint4 key[SN_RS_ITEMS];
-    uint32_t rank[SN_RS_ITEMS];
+    uint32_t dr[SN_RS_ITEMS];                  // digit | rank << 8
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
         uint32_t li = warp * (32 * SN_RS_ITEMS) + j * 32 + lane;
-        if (li < valid) key[j] = in[tile_base + li];
-        else key[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);   // sorts last, never written
+        if (li < valid) { key[j] = in[tile_base + li]; dr[j] = rs_digit<MODE>(key[j], pass); }
+        else { key[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); dr[j] = 0xFFu; }
     }
     // stable in-warp ranking by digit: match_any groups equal digits, the group leader
     // bumps the warp's private counter for that digit.
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
-        uint32_t d = rs_digit(key[j], pass);
+        uint32_t d = dr[j];
         uint32_t peers = __match_any_sync(SN_FULL, d);
         uint32_t leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if (lane == leader) { base = S.warp_cnt[warp][d]; S.warp_cnt[warp][d] = base + __popc(peers); }
         base = __shfl_sync(SN_FULL, base, leader);
-        rank[j] = base + __popc(peers & lanemask_lt());
+        dr[j] = d | ((base + __popc(peers & lanemask_lt())) << 8);
     }
     __syncthreads();
-    // thread d: exclusive scan of digit d over the 8 warps, tile total, look-back
-    uint32_t tot = 0;
-    {
+    // thread d (< 256): exclusive scan of digit d over the warps, tile total, look-back
+    uint32_t tot = 0, prev = 0;
+    if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { uint32_t c = S.warp_cnt[w][tid]; S.warp_cnt[w][tid] = tot; tot += c; }
-    }
-    uint32_t prev = (uint32_t)tile_lookback(status, 256, tid, tile, tot);
-    // exclusive scan of tile totals over digits (256 threads)
-    {
+        for (int w = 0; w < SN_RS_WARPS; ++w) { uint32_t c = S.warp_cnt[w][tid]; S.warp_cnt[w][tid] = tot; tot += c; }
+        prev = (uint32_t)tile_lookback(status, 256, tid, tile, tot);
+        // exclusive scan of the tile totals over the 256 digits (8 warps)
         uint32_t x = tot;
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
         if (lane == 31) S.scan_tmp[warp] = x;
-        __syncthreads();
+        tot = x - tot;                             // exclusive within the warp
+    }
+    __syncthreads();
+    if (tid < 256) {
         uint32_t wbase = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) if (w < (int)warp) wbase += S.scan_tmp[w];
-        uint32_t excl = wbase + x - tot;
+        uint32_t excl = wbase + tot;
         S.tile_start[tid] = excl;
-        S.gdst[tid] = ghist[tid] + prev - excl;     // may wrap below zero; the later + s brings it back (mod 2^32)
+        S.gdst[tid] = ghist[tid] + prev - excl;    // may wrap below zero; the later + s brings it back (mod 2^32)
     }
     __syncthreads();
     // scatter into the smem reorder buffer
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
-        uint32_t d = rs_digit(key[j], pass);
-        uint32_t pos = S.tile_start[d] + S.warp_cnt[warp][d] + rank[j];
+        uint32_t d = dr[j] & 0xFFu;
+        uint32_t pos = S.tile_start[d] + S.warp_cnt[warp][d] + (dr[j] >> 8);
         S.keys[pos] = key[j];
     }
     __syncthreads();
@@ -260,7 +281,7 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
         uint32_t s = j * SN_RS_THREADS + tid;
         if (s < valid) {
             uint4 k = S.keys[s];
-            uint32_t d = rs_digit(k, pass);
+            uint32_t d = rs_digit<MODE>(k, pass);
             out[(uint32_t)(S.gdst[d] + s)] = k;
         }
     }
@@ -269,47 +290,49 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
 inline size_t radix_sort_tmp_bytes(uint32_t n)
 {
     uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
-    return (size_t)SN_RS_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
+    return (size_t)SN_RS_MAX_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
 }
 // Sorts n (< 2^32) records in two steps so the caller can time them apart:
-// radix_sort_histograms (one read of the records) then radix_sort_passes (12 digit passes,
-// each one read + one write).  Result ends in `a` (12 passes ping-pong a->b->a...).
+// radix_sort_histograms (one read of the records) then radix_sort_passes (PASSES digit passes,
+// each one read + one write).  The result ends in `a` (even number of ping-pong passes).
+template <int MODE>
 inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     uint32_t* hist = (uint32_t*)tmp;
-    cudaMemsetAsync(hist, 0, (SN_RS_PASSES * 256 + 16) * 4, st);
-    k_rs_histogram<<<num_sms * 8, 256, 0, st>>>(a, n, hist);
-    k_rs_scan_hist<<<SN_RS_PASSES, 256, 0, st>>>(hist);
+    cudaMemsetAsync(hist, 0, (SN_RS_MAX_PASSES * 256 + 16) * 4, st);
+    k_rs_histogram<MODE><<<num_sms * 8, 256, 0, st>>>(a, n, hist);
+    k_rs_scan_hist<<<RsMode<MODE>::PASSES, 256, 0, st>>>(hist);
     return cudaGetLastError();
 }
+template <int MODE>
 inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
     uint32_t* hist = (uint32_t*)tmp;
-    uint32_t* counters = hist + SN_RS_PASSES * 256;
+    uint32_t* counters = hist + SN_RS_MAX_PASSES * 256;
     uint64_t* status = (uint64_t*)(counters + 16);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
+        cudaError_t e = cudaFuncSetAttribute(k_rs_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     uint4* src = a; uint4* dst = b;
-    for (int p = 0; p < SN_RS_PASSES; ++p) {
+    for (int p = 0; p < RsMode<MODE>::PASSES; ++p) {
         cudaMemsetAsync(status, 0, (size_t)nt * 256 * 8, st);
-        k_rs_scatter<<<nt, SN_RS_THREADS, sizeof(RsSmem), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
+        k_rs_scatter<MODE><<<nt, SN_RS_THREADS, sizeof(RsSmem), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
         uint4* t = src; src = dst; dst = t;
     }
     return cudaGetLastError();
 }
-
-inline cudaError_t radix_sort_kmers(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+template <int MODE>
+inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
 {
-    cudaError_t e = radix_sort_histograms(a, n, tmp, num_sms, st);
+    cudaError_t e = radix_sort_histograms<MODE>(a, n, tmp, num_sms, st);
     if (e != cudaSuccess) return e;
-    return radix_sort_passes(a, b, n, tmp, st);
+    return radix_sort_passes<MODE>(a, b, n, tmp, st);
 }
 
 }  // namespace sn

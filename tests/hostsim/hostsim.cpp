@@ -18,6 +18,7 @@ using namespace sn;
 struct Sim {
     std::vector<DictEntry> tab;
     std::vector<uint32_t> idx;
+    std::vector<uint32_t> perm;      // perm[i] = position in `tab` of the i-th input (k-mer sorted) record
     snh::Edges edges;
     snh::Hbv hbv;
     std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
@@ -44,20 +45,27 @@ uint32_t hs_extract_read(const uint8_t* packed, uint32_t goodlen, int32_t bc, ui
     return n;
 }
 
-Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted */)
+Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted by k-mer */)
 {
     Sim* s = new Sim();
-    s->tab.resize(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        DictEntry& e = s->tab[i];
+    // what k_reduce leaves behind: the dictionary in (hash, k-mer) order
+    std::vector<uint32_t> order(n);
+    std::vector<uint32_t> hs(n);
+    for (uint64_t i = 0; i < n; ++i) { Kmer k; k.w0 = recs[4 * i]; k.w1 = recs[4 * i + 1]; k.w2 = recs[4 * i + 2]; hs[i] = kmer_hash(k); order[i] = (uint32_t)i; }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hs[a] < hs[b]; });
+    s->tab.resize(n); s->perm.resize(n);
+    for (uint64_t p = 0; p < n; ++p) {
+        uint64_t i = order[p];
+        s->perm[i] = (uint32_t)p;
+        DictEntry& e = s->tab[p];
         e.w0 = recs[4 * i]; e.w1 = recs[4 * i + 1]; e.w2 = recs[4 * i + 2]; e.cc = recs[4 * i + 3];
-        e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = e.cc >> 24; e.pad = 0;
+        e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = e.cc >> 24; e.h = hs[i];
     }
     s->idx.resize((1u << SN_IDX_BITS) + 1);
     for (uint32_t b = 0; b <= (1u << SN_IDX_BITS); ++b) {          // k_build_index
         if (b == (1u << SN_IDX_BITS)) { s->idx[b] = (uint32_t)n; break; }
         uint32_t key = b << (32 - SN_IDX_BITS), lo = 0, hi = (uint32_t)n;
-        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s->tab[mid].w0 < key) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s->tab[mid].h < key) lo = mid + 1; else hi = mid; }
         s->idx[b] = lo;
     }
     return s;
@@ -86,8 +94,9 @@ int hs_edges(Sim* s)
         if (i <= last) own_n[i] = nk;
     }
     for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_INTERIOR && !visited[i]) {                     // k_circle_count
-        uint32_t nk = walk_circle(d, i, [](uint32_t, uint32_t, uint32_t) {});
-        if (nk) { own_n[i] = nk; etype[i] = 4; }
+        uint32_t m = i; Kmer mk = entry_kmer(s->tab[i]);
+        uint32_t nk = walk_circle(d, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(s->tab[j]); if (q < mk) { mk = q; m = j; } });
+        if (nk) { own_n[m] = nk; etype[m] = 4; }
     }
     std::vector<uint32_t> owners; std::vector<uint64_t> base_off(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) { base_off[i + 1] = base_off[i] + (own_n[i] ? own_n[i] + SN_K - 1 : 0); if (own_n[i]) owners.push_back(i); }
@@ -104,7 +113,7 @@ int hs_edges(Sim* s)
         uint32_t nk = 1;
         auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { sq[SN_K - 1 + step] = (uint8_t)c; s->tab[j].edge = e; s->tab[j].off = step; };
         if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
-        else if (t == 4) nk = walk_circle(d, i, visit);
+        else if (t == 4) nk = walk_circle(d, i, false, visit);
         elen[e] = nk + SN_K - 1; etmp[e] = base_off[i];
         eflip[e] = seq_form_u8(sq, elen[e]) == REV ? 1 : 0;
     }
@@ -133,7 +142,7 @@ void hs_get_edges(Sim* s, uint32_t* len, uint64_t* off, uint8_t* packed)
     memcpy(packed, s->edges.packed.data(), s->edges.off.back());
 }
 void hs_get_graph_info(Sim* s, uint8_t* ctx, uint32_t* edge, uint32_t* off)
-{ for (size_t i = 0; i < s->tab.size(); ++i) { ctx[i] = (uint8_t)s->tab[i].ctx; edge[i] = s->tab[i].edge; off[i] = s->tab[i].off; } }
+{ for (size_t i = 0; i < s->tab.size(); ++i) { const DictEntry& e = s->tab[s->perm[i]]; ctx[i] = (uint8_t)e.ctx; edge[i] = e.edge; off[i] = e.off; } }
 
 int hs_hbv(Sim* s, const char* hbv_path)
 {
