@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c2.json; cut -c1-600 gpurun_out/bench_c2.json
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c2.json; cut -c1-300 gpurun_out/bench_c2.json

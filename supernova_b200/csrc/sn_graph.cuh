@@ -23,96 +23,87 @@ SN_HD uint32_t prune_ctx(const DictView& d, uint32_t i)
     return ctx;
 }
 
-// EdgeBuilder::lookup (:466-476): entry index of `k` and its context expressed in
-// the orientation of `k`.  The neighbour is guaranteed present after pruning.
-SN_HD uint32_t oriented_lookup(const DictView& d, const Kmer& k, uint32_t* ctx)
-{
-    bool rc;
-    uint32_t j = dict_find(d, k, &rc);
-    uint32_t c = (j == SN_NULL_EDGE) ? 0u : d.tab[j].ctx;
-    *ctx = rc ? ctx_rc(c) : c;
-    return j;
-}
+enum EntryType { T_SINGLE = 0, T_INTERIOR = 1, T_END_DOWN = 2, T_END_UP = 3, T_CIRCLE = 4 };
 
-// "extension possible" toward the successor side of oriented k-mer (k, ctx):
-// exactly one successor, successor not a palindrome, successor has exactly one
-// predecessor (:419-428; the upstream test :408-417 is this one on the RC strand).
-SN_HD bool down_possible(const DictView& d, const Kmer& k, uint32_t ctx)
+// Unipath links.  For every dictionary entry two links are stored, one per side of its
+// canonical k-mer: x = "down" (successor side), y = "up" (predecessor side, i.e. the successor
+// side of the reverse complement).  A link exists exactly when EdgeBuilder would extend across
+// it (:408-428, :445-456); it holds the neighbour's table index << 1 | the orientation (1 = RC
+// of the stored k-mer) in which a walk arriving over this link sees the neighbour.  Walking an
+// edge is then one dependent 8-byte load per k-mer instead of a dictionary probe.
+#define SN_NO_LINK 0xFFFFFFFFu
+struct Link2 { uint32_t x, y; };
+
+SN_HD uint32_t compute_link(const DictView& d, const Kmer& k, uint32_t ctx)
 {
     uint32_t s = ctx_succ(ctx);
-    if (!mask_single(s)) return false;
+    if (!mask_single(s)) return SN_NO_LINK;
     Kmer nx = kmer_succ(k, mask_code(s));
-    if (kmer_is_pal(nx)) return false;
-    uint32_t nctx;
-    oriented_lookup(d, nx, &nctx);
-    return mask_single(ctx_pred(nctx));
+    Kmer rc;
+    int form = kmer_form(nx, &rc);
+    if (form == PAL) return SN_NO_LINK;
+    uint32_t j = dict_find_canonical(d, form == REV ? rc : nx);
+    if (j == SN_NULL_EDGE) return SN_NO_LINK;               // cannot happen after pruning
+    uint32_t c = d.tab[j].ctx;
+    uint32_t nctx = form == REV ? ctx_rc(c) : c;
+    if (!mask_single(ctx_pred(nctx))) return SN_NO_LINK;
+    return (j << 1) | (form == REV ? 1u : 0u);
 }
 
-enum EntryType { T_SINGLE = 0, T_INTERIOR = 1, T_END_DOWN = 2, T_END_UP = 3 };
-
-// EdgeBuilder::buildEdge dispatch (:335-345)
-SN_HD int classify_entry(const DictView& d, uint32_t i)
+// EdgeBuilder::buildEdge dispatch (:335-345) expressed through the links
+SN_HD int classify_links(const DictView& d, uint32_t i, Link2* out)
 {
     const DictEntry& e = d.tab[i];
     Kmer k = entry_kmer(e);
+    out->x = SN_NO_LINK; out->y = SN_NO_LINK;
     if (kmer_is_pal(k)) return T_SINGLE;
-    bool up = down_possible(d, kmer_rc(k), ctx_rc(e.ctx));
-    bool down = down_possible(d, k, e.ctx);
+    out->x = compute_link(d, k, e.ctx);
+    out->y = compute_link(d, kmer_rc(k), ctx_rc(e.ctx));
+    bool down = out->x != SN_NO_LINK, up = out->y != SN_NO_LINK;
     if (up) return down ? T_INTERIOR : T_END_UP;
     return down ? T_END_DOWN : T_SINGLE;
 }
 
-// EdgeBuilder::extend (:445-456) as a visitor: walks from the end entry `i` in the
-// direction given by its type and calls f(step, entry_index, appended_base) for every
-// k-mer after the first.  Returns the number of k-mers on the edge.
+// base appended to the edge sequence when a walk steps onto entry j seen in orientation o:
+// the last base of the oriented k-mer
+SN_HD uint32_t step_base(const DictEntry& e, uint32_t o) { return o ? ((e.w0 >> 30) ^ 3u) : (e.w2 & 3u); }
+
+// EdgeBuilder::extend (:445-456) over the links: starts at entry i in orientation o and calls
+// f(step, entry, orientation) for every k-mer after the first.  Returns the number of k-mers.
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
 template <class F>
-SN_HD uint32_t walk_edge(const DictView& d, uint32_t i, int type, F&& f)
+SN_HD uint32_t walk_links(const Link2* links, uint32_t i, uint32_t o, F&& f)
 {
-    const DictEntry& e = d.tab[i];
-    Kmer k = entry_kmer(e);
-    uint32_t ctx = e.ctx;
-    if (type == T_END_UP) { k = kmer_rc(k); ctx = ctx_rc(ctx); }
-    uint32_t n = 1;
-    while (mask_single(ctx_succ(ctx))) {
-        uint32_t c = mask_code(ctx_succ(ctx));
-        Kmer nx = kmer_succ(k, c);
-        if (kmer_is_pal(nx)) break;
-        uint32_t nctx;
-        uint32_t j = oriented_lookup(d, nx, &nctx);
-        if (!mask_single(ctx_pred(nctx))) break;
-        f(n, j, c);
-        k = nx; ctx = nctx; ++n;
+    uint32_t cur = i, n = 1;
+    for (;;) {
+        uint32_t l = o ? links[cur].y : links[cur].x;
+        if (l == SN_NO_LINK) break;
+        cur = l >> 1; o = l & 1u;
+        f(n, cur, o);
+        ++n;
     }
     return n;
 }
-
 // simpleCircle (:348-372).  Leader election: every k-mer of a smooth circle walks its
 // successors and gives up (returns 0) as soon as it meets an entry with a smaller table index,
 // so exactly one walker per circle completes the loop (`elect` = true).  With `elect` = false
-// the walk always completes (used by the owner to emit the edge).  f(step, entry, base) is
-// called for every k-mer after the first.  Returns the number of k-mers.
+// the walk always completes (used by the owner to emit the edge).
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
 template <class F>
-SN_HD uint32_t walk_circle(const DictView& d, uint32_t i, bool elect, F&& f)
+SN_HD uint32_t walk_circle_links(const Link2* links, uint32_t i, bool elect, F&& f)
 {
-    const DictEntry& e = d.tab[i];
-    Kmer k = entry_kmer(e);
-    uint32_t ctx = e.ctx;
-    uint32_t n = 1;
+    uint32_t cur = i, o = 0, n = 1;
     for (;;) {
-        uint32_t c = mask_code(ctx_succ(ctx));
-        Kmer nx = kmer_succ(k, c);
-        uint32_t nctx;
-        uint32_t j = oriented_lookup(d, nx, &nctx);
-        if (j == i) break;
-        if (elect && j < i) return 0;
-        f(n, j, c);
-        k = nx; ctx = nctx; ++n;
+        uint32_t l = o ? links[cur].y : links[cur].x;
+        cur = l >> 1; o = l & 1u;
+        if (cur == i) break;
+        if (elect && cur < i) return 0;
+        f(n, cur, o);
+        ++n;
     }
     return n;
 }

@@ -234,103 +234,173 @@ __device__ __noinline__ uint32_t reduce_mixed_run(const uint4* __restrict__ keys
     return nvalid;
 }
 
-__global__ void __launch_bounds__(SN_RD_THREADS) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
-                                                          DictEntry* __restrict__ out, uint64_t* status, uint32_t* tile_counter,
-                                                          uint32_t* n_out, unsigned long long* n_distinct)
+// Aggregate of a (partial) run, combined with shuffles.
+struct Agg { uint32_t count, ctx_flags, minbc, maxbc; };      // ctx_flags: ctx | ign<<8 | mixed<<9
+__device__ __forceinline__ Agg agg_combine(const Agg& a, const Agg& b)
+{ Agg r; r.count = a.count + b.count; r.ctx_flags = a.ctx_flags | b.ctx_flags; r.minbc = min(a.minbc, b.minbc); r.maxbc = max(a.maxbc, b.maxbc); return r; }
+__device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int d)
+{ Agg r; r.count = __shfl_up_sync(SN_FULL, a.count, d); r.ctx_flags = __shfl_up_sync(SN_FULL, a.ctx_flags, d);
+  r.minbc = __shfl_up_sync(SN_FULL, a.minbc, d); r.maxbc = __shfl_up_sync(SN_FULL, a.maxbc, d); return r; }
+__device__ __forceinline__ Agg agg_bcast(const Agg& a, int src)
+{ Agg r; r.count = __shfl_sync(SN_FULL, a.count, src); r.ctx_flags = __shfl_sync(SN_FULL, a.ctx_flags, src);
+  r.minbc = __shfl_sync(SN_FULL, a.minbc, src); r.maxbc = __shfl_sync(SN_FULL, a.maxbc, src); return r; }
+__device__ __forceinline__ bool agg_valid(const Agg& s, uint32_t min_freq, uint32_t min_bc, int has_bc)
 {
-    __shared__ uint32_t wtot[SN_RD_ITEMS * 8];
-    __shared__ uint32_t wpref[SN_RD_ITEMS * 8 + 1];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t tbase = (uint64_t)tile * SN_RD_TILE;
-    // per item (kept in shared memory so the walk loop is not unrolled 8x into registers):
-    // cc = count|ctx<<24 of a clean run; nv = entries its run contributes | mixed flag << 31
-    __shared__ uint32_t s_cc[SN_RD_ITEMS][SN_RD_THREADS], s_nv[SN_RD_ITEMS][SN_RD_THREADS], s_incl[SN_RD_ITEMS][SN_RD_THREADS];
-#define cc(j) s_cc[j][tid]
-#define nv(j) s_nv[j][tid]
-#define incl(j) s_incl[j][tid]
-    uint32_t distinct = 0;
-#pragma unroll 1
-    for (int j = 0; j < SN_RD_ITEMS; ++j) {
-        uint64_t idx = tbase + (uint64_t)j * SN_RD_THREADS + tid;
-        nv(j) = 0; cc(j) = 0;
-        if (idx < n) {
-            uint4 k = keys[idx];
-            // a run head is first of all the first record of its k-mer (cheap 96-bit compare);
-            // hashes are only computed where the k-mer changes
-            bool head = idx == 0;
-            uint32_t h = 0;
-            if (!head) { uint4 pv = keys[idx - 1]; if (!same_kmer(pv, k)) { h = rs_hash(k); head = rs_hash(pv) != h; } }
-            else h = rs_hash(k);
-            if (head) {
-                RunStat st; stat_init(st);
-                bool mixed = false;
-                uint64_t p = idx + 1;
-                stat_add(st, k.w);
-                while (p < n) {                             // the run is [idx, p)
-                    uint4 r = keys[p];
-                    if (same_kmer(r, k)) { stat_add(st, r.w); ++p; continue; }
-                    if (rs_hash(r) != h) break;             // next hash: end of the run
-                    mixed = true; ++p;                      // a different k-mer with the same hash
-                }
-                if (!mixed) {
-                    nv(j) = stat_valid(st, min_freq, min_bc, has_bc) ? 1u : 0u; ++distinct;
-                    cc(j) = min(st.count, 0xFFFFFFu) | (st.ctx << 24);
-                } else {
-                    uint32_t nd = 0;
-                    uint32_t v = reduce_mixed_run(keys, idx, p, h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
-                    nv(j) = v | (v ? 0x80000000u : 0u);
-                    distinct += nd;
-                }
-            }
-        }
-        // inclusive warp scan of the number of entries each record's run contributes
-        uint32_t x = nv(j) & 0x7FFFFFFFu;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
-        incl(j) = x;
-        if (lane == 31) wtot[j * 8 + warp] = x;
-    }
-    for (int o = 16; o > 0; o >>= 1) distinct += __shfl_down_sync(SN_FULL, distinct, o);
-    if (lane == 0 && distinct) atomicAdd(n_distinct, (unsigned long long)distinct);
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t s = 0;
-        for (int i = 0; i < SN_RD_ITEMS * 8; ++i) { wpref[i] = s; s += wtot[i]; }
-        wpref[SN_RD_ITEMS * 8] = s;
-        uint64_t prev = tile_lookback(status, 1, 0, tile, s);
-        s_base = prev;
-        if (tbase + SN_RD_TILE >= n) *n_out = (uint32_t)(prev + s);      // last tile knows the total
-    }
-    __syncthreads();
-    const uint64_t base = s_base;
-#pragma unroll 1
-    for (int j = 0; j < SN_RD_ITEMS; ++j) {
-        uint32_t cnt = nv(j) & 0x7FFFFFFFu;
-        if (cnt) {
-            uint64_t idx = tbase + (uint64_t)j * SN_RD_THREADS + tid;
-            uint64_t pos = base + wpref[j * 8 + warp] + (incl(j) - cnt);
-            uint4 k = keys[idx];
-            uint32_t h = rs_hash(k);
-            if (!(nv(j) >> 31)) {
-                DictEntry e;
-                e.w0 = k.x; e.w1 = k.y; e.w2 = k.z; e.cc = cc(j);
-                e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = cc(j) >> 24; e.h = h;
-                out[pos] = e;
-            } else {
-                uint64_t p = idx + 1;
-                while (p < n && rs_hash(keys[p]) == h) ++p;
-                reduce_mixed_run(keys, idx, p, h, min_freq, min_bc, has_bc, out, pos, nullptr);
-            }
-        }
-    }
+    bool enough = min_bc == 0 || (min_bc == 1 ? s.maxbc != 0 : (s.maxbc != 0 && s.minbc != s.maxbc));
+    return s.count >= min_freq && (!has_bc || ((s.ctx_flags >> 8) & 1u) || enough);
 }
-#undef cc
-#undef nv
-#undef incl
+
+// Warp-streaming reduce-by-key ("warp-ballot run-length counting").  Each warp owns the runs of
+// equal hash whose FIRST record lies in its chunk of SN_RD_CHUNK records; it streams 32 records
+// per step (one coalesced 512-byte load), finds run heads with a ballot, reduces every run with
+// a segmented shuffle scan, carries the open run across steps (and past the end of the chunk),
+// and writes the surviving k-mers, in order, to its private staging slots; per-warp counts are
+// scanned and k_reduce_gather compacts the stage into the dictionary.
+#define SN_RD_CHUNK 1024
+#define SN_RD_WARPS 8
+__global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
+                                                             DictEntry* __restrict__ stage, uint32_t cap_per_warp, uint32_t* __restrict__ warp_count,
+                                                             unsigned long long* n_distinct, uint32_t* overflow)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t w = (uint64_t)blockIdx.x * SN_RD_WARPS + (threadIdx.x >> 5);
+    const uint64_t a = w * SN_RD_CHUNK;
+    if (a >= n) return;
+    const uint64_t b = min((uint64_t)n, a + SN_RD_CHUNK);
+    DictEntry* out = stage + w * cap_per_warp;
+    const uint4 SENT = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);   // never a canonical k-mer
+    uint4 prev_last = a > 0 ? keys[a - 1] : SENT;
+    bool started = false;          // an owned run has begun
+    bool open = false;             // carry holds an owned, unfinished run
+    Agg carry; carry.count = 0; carry.ctx_flags = 0; carry.minbc = 0xFFFFFFFFu; carry.maxbc = 0;
+    uint4 carry_key = SENT; uint64_t carry_start = 0;
+    uint32_t cursor = 0, distinct = 0;
+    // software pipeline: the records of the next two steps are already in flight
+    uint4 nx1 = (a + lane < n) ? keys[a + lane] : SENT;
+    uint4 nx2 = (a + 32 + lane < n) ? keys[a + 32 + lane] : SENT;
+    for (uint64_t pos = a;; pos += 32) {
+        const uint64_t idx = pos + lane;
+        const bool inb = idx < n;
+        uint4 r = nx1;
+        nx1 = nx2;
+        nx2 = (idx + 64 < n) ? keys[idx + 64] : SENT;
+        uint4 pv;
+        pv.x = __shfl_up_sync(SN_FULL, r.x, 1); pv.y = __shfl_up_sync(SN_FULL, r.y, 1); pv.z = __shfl_up_sync(SN_FULL, r.z, 1); pv.w = 0;
+        if (lane == 0) pv = prev_last;
+        const bool kh = !same_kmer(pv, r);                              // first record of its k-mer
+        bool hh = false;                                               // first record of its hash run
+        if (kh) hh = idx == 0 || !inb || rs_hash(pv) != rs_hash(r);
+        if (idx > n) hh = false;                                       // only the first sentinel closes the last run
+        const uint32_t hmask = __ballot_sync(SN_FULL, hh);
+        // ownership window of this step: from the first owned head on (skip the tail of a
+        // foreign run at the start of the chunk), up to the first head at or past `b`
+        const uint32_t fmask = __ballot_sync(SN_FULL, hh && idx >= b);
+        const uint32_t f = fmask ? (uint32_t)__ffs(fmask) - 1u : 32u;   // lanes >= f belong to the next warp
+        uint32_t first = 0;
+        if (!started) { if (!hmask) { prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
+                                      if (pos + 32 >= n + 1) break; continue; }
+                        first = (uint32_t)__ffs(hmask) - 1u; }
+        const bool active = lane >= first && lane < f;
+        Agg v; v.count = active ? 1u : 0u;
+        v.ctx_flags = active ? ((r.w >> 24) | ((r.w & 0xFFFFFFu) == 0xFFFFFFu ? 0x100u : 0u) | ((kh && !hh) ? 0x200u : 0u)) : 0u;
+        { uint32_t bcv = r.w & 0xFFFFFFu; bool pos_bc = active && bcv != 0 && bcv != 0xFFFFFFu;
+          v.minbc = pos_bc ? bcv : 0xFFFFFFFFu; v.maxbc = pos_bc ? bcv : 0u; }
+        // segmented inclusive scan; segments start at run heads
+        const uint32_t seg_heads = hmask & ((2u << lane) - 1u);          // heads at or before this lane
+        const int seg_start = seg_heads ? 31 - __clz(seg_heads) : -1;     // -1: the run continues from the carry
+        const uint32_t dist = (uint32_t)((int)lane - (seg_start < 0 ? 0 : seg_start));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { Agg u = agg_shfl_up(v, d); if ((uint32_t)d <= dist) v = agg_combine(u, v); }
+        if (seg_start < 0 && open) v = agg_combine(carry, v);
+        // a run ends at lane l when lane l+1 is a head (or the ownership window closes there)
+        const uint32_t nextmask = (hmask >> 1) | (f < 32 && f > 0 ? (1u << (f - 1)) : 0u);
+        const bool ends_here = active && lane < 31 && ((nextmask >> lane) & 1u);
+        // the carried run ends when lane 0 is a head (or is already foreign)
+        const bool carry_ends = open && (((hmask | (f == 0 ? 1u : 0u)) & 1u) != 0);
+        // --- emission, in order: carried run first, then the runs that end inside this step ---
+        if (carry_ends) {
+            bool mixed = (carry.ctx_flags >> 9) & 1u;
+            if (!mixed) {
+                ++distinct;
+                if (agg_valid(carry, min_freq, min_bc, has_bc)) {
+                    if (cursor < cap_per_warp) { if (lane == 0) { RunStat st; st.count = carry.count; st.ctx = carry.ctx_flags & 0xFFu; out[cursor] = make_entry(carry_key, st, rs_hash(carry_key)); } }
+                    else if (lane == 0) atomicAdd(overflow, 1u);
+                    ++cursor;
+                }
+            } else {
+                uint32_t nd = 0, nvld = 0;
+                if (lane == 0) {
+                    uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
+                    nvld = reduce_mixed_run(keys, carry_start, pos, rs_hash(carry_key), min_freq, min_bc, has_bc, nullptr, 0, &nd);
+                    if (nvld <= room) reduce_mixed_run(keys, carry_start, pos, rs_hash(carry_key), min_freq, min_bc, has_bc, out, cursor, nullptr);
+                    else atomicAdd(overflow, 1u);
+                }
+                cursor += __shfl_sync(SN_FULL, nvld, 0); distinct += __shfl_sync(SN_FULL, nd, 0);
+            }
+            open = false;
+        }
+        {
+            const bool mixed = (v.ctx_flags >> 9) & 1u;
+            const bool emit_ok = ends_here && !mixed && agg_valid(v, min_freq, min_bc, has_bc);
+            const uint32_t emask = __ballot_sync(SN_FULL, emit_ok);
+            const uint32_t mmask = __ballot_sync(SN_FULL, ends_here && mixed);
+            distinct += __popc(__ballot_sync(SN_FULL, ends_here && !mixed));
+            if (!mmask) {
+                if (emit_ok) {
+                    uint32_t p = cursor + __popc(emask & lanemask_lt());
+                    if (p < cap_per_warp) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[p] = make_entry(r, st, rs_hash(r)); }
+                    else atomicAdd(overflow, 1u);
+                }
+                cursor += __popc(emask);
+            } else {
+                // rare: a run with colliding k-mers ends in this step -> go through the ending lanes one by one
+                uint32_t todo = emask | mmask;
+                while (todo) {
+                    const uint32_t l = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
+                    uint32_t nvld = 0, nd = 0;
+                    if (lane == l) {
+                        uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
+                        if (!mixed) { nvld = 1; if (room) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[cursor] = make_entry(r, st, rs_hash(r)); } else atomicAdd(overflow, 1u); }
+                        else {
+                            const uint64_t start = seg_start < 0 ? carry_start : pos + (uint32_t)seg_start;
+                            nvld = reduce_mixed_run(keys, start, idx + 1, rs_hash(r), min_freq, min_bc, has_bc, nullptr, 0, &nd);
+                            if (nvld <= room) reduce_mixed_run(keys, start, idx + 1, rs_hash(r), min_freq, min_bc, has_bc, out, cursor, nullptr);
+                            else atomicAdd(overflow, 1u);
+                        }
+                    }
+                    cursor += __shfl_sync(SN_FULL, nvld, l); distinct += __shfl_sync(SN_FULL, nd, l);
+                }
+            }
+        }
+        started = true;
+        if (f < 32) break;                                              // the next warp's first run starts here
+        // the run open at lane 31 is carried into the next step
+        {
+            const uint32_t last_head = hmask ? 31u - (uint32_t)__clz(hmask) : 32u;
+            const bool had_open = open;                                   // still true only if the carried run did not end
+            Agg c31 = agg_bcast(v, 31);
+            if (last_head < 32) {
+                carry = c31; open = true;
+                carry_key.x = __shfl_sync(SN_FULL, r.x, last_head); carry_key.y = __shfl_sync(SN_FULL, r.y, last_head); carry_key.z = __shfl_sync(SN_FULL, r.z, last_head);
+                carry_start = pos + last_head;
+            } else if (had_open) carry = c31;                            // the carried run swallowed the whole step
+        }
+        prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
+        if (pos + 32 >= (uint64_t)n + 1) break;                           // the sentinel lane has been processed
+    }
+    if (lane == 0) { warp_count[w] = cursor; if (distinct) atomicAdd(n_distinct, (unsigned long long)distinct); }
+}
+// compacts the per-warp staging slots into the dictionary: one warp per source warp
+__global__ void __launch_bounds__(256) k_reduce_gather(const DictEntry* __restrict__ stage, uint32_t cap_per_warp, const uint32_t* __restrict__ warp_count,
+                                                       const uint64_t* __restrict__ warp_off, uint64_t n_warps, DictEntry* __restrict__ dict)
+{
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_warps) return;
+    const uint32_t lane = threadIdx.x & 31u, cnt = warp_count[w];
+    const uint4* src = reinterpret_cast<const uint4*>(stage + w * cap_per_warp);
+    uint4* dst = reinterpret_cast<uint4*>(dict + warp_off[w]);
+    for (uint32_t i = lane; i < 2 * cnt; i += 32) dst[i] = src[i];
+}
 
 // ---------------------------------------------------------------------------
 // a6. dictionary prefix index + recomputeAdjacencies
@@ -359,14 +429,15 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* _
 // both of its end entries and owned by the end with the smaller index; a circle is
 // owned by its smallest entry.
 // ---------------------------------------------------------------------------
-#define SN_T_CIRCLE 4
 __global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
-                                                  uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
+                                                  Link2* __restrict__ links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     DictView d; d.tab = tab; d.idx = idx; d.n = n;
-    int t = classify_entry(d, i);
+    Link2 l;
+    int t = classify_links(d, i, &l);
+    links[i] = l;
     etype[i] = (uint8_t)t;
     own_n[i] = t == T_SINGLE ? 1u : 0u;
     is_end[i] = (t == T_END_DOWN || t == T_END_UP) ? 1u : 0u;
@@ -376,19 +447,17 @@ __global__ void __launch_bounds__(256) k_scatter_flagged(const uint32_t* __restr
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) list[pos[i]] = i;
 }
-__global__ void __launch_bounds__(128) k_walk_count(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
-                                                    const uint32_t* __restrict__ ends, uint32_t n_ends, const uint8_t* __restrict__ etype,
-                                                    uint32_t* __restrict__ own_n, uint8_t* __restrict__ visited)
+__global__ void __launch_bounds__(128) k_walk_count(const Link2* __restrict__ links, const uint32_t* __restrict__ ends, uint32_t n_ends,
+                                                    const uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint8_t* __restrict__ visited)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_ends) return;
-    DictView d; d.tab = tab; d.idx = idx; d.n = n;
     uint32_t i = ends[t], last = i;
     visited[i] = 1;
-    uint32_t nk = walk_edge(d, i, etype[i], [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
+    uint32_t nk = walk_links(links, i, etype[i] == T_END_UP ? 1u : 0u, [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
     if (i <= last) own_n[i] = nk;       // the other end walks the same edge; the smaller index owns it
 }
-__global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
+__global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const Link2* __restrict__ links, uint32_t n,
                                                      uint8_t* __restrict__ etype, const uint8_t* __restrict__ visited, uint32_t* __restrict__ own_n,
                                                      uint32_t* n_circle_members)
 {
@@ -396,12 +465,11 @@ __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restric
     if (i >= n) return;
     if (etype[i] != T_INTERIOR || visited[i]) return;
     atomicAdd(n_circle_members, 1u);
-    DictView d; d.tab = tab; d.idx = idx; d.n = n;
     // the walker with the smallest table index completes the loop; the circle is then owned by
     // its smallest K-MER, where canonicalizeCircle (BuildReadQGraph48.cc:375-397) starts it
     uint32_t m = i; Kmer mk = entry_kmer(tab[i]);
-    uint32_t nk = walk_circle(d, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(tab[j]); if (q < mk) { mk = q; m = j; } });
-    if (nk) { own_n[m] = nk; etype[m] = SN_T_CIRCLE; }
+    uint32_t nk = walk_circle_links(links, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(tab[j]); if (q < mk) { mk = q; m = j; } });
+    if (nk) { own_n[m] = nk; etype[m] = T_CIRCLE; }
 }
 __global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, uint32_t n, uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
 {
@@ -415,14 +483,13 @@ __global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__
 // (edge id, step) into every entry on the edge; then the whole-edge canonical form
 // (EdgeBuilder::addEdge :480-485 / extend :457-464) decides whether the edge is
 // stored reverse-complemented.
-__global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n,
+__global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const Link2* __restrict__ links,
                                                    const uint32_t* __restrict__ owners, uint32_t n_owners, const uint8_t* __restrict__ etype,
                                                    const uint64_t* __restrict__ base_off, uint8_t* __restrict__ tmp,
                                                    uint32_t* __restrict__ elen, uint8_t* __restrict__ eflip, uint64_t* __restrict__ etmp_off)
 {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_owners) return;
-    DictView d; d.tab = tab; d.idx = idx; d.n = n;
     uint32_t i = owners[e];
     int t = etype[i];
     uint8_t* s = tmp + base_off[i];
@@ -431,9 +498,9 @@ __global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const uint32_
     for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(k, b);
     tab[i].edge = e; tab[i].off = 0;
     uint32_t nk = 1;
-    auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { s[SN_K - 1 + step] = (uint8_t)c; tab[j].edge = e; tab[j].off = step; };
-    if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
-    else if (t == SN_T_CIRCLE) nk = walk_circle(d, i, false, visit);
+    auto visit = [&](uint32_t step, uint32_t j, uint32_t o) { s[SN_K - 1 + step] = (uint8_t)step_base(tab[j], o); tab[j].edge = e; tab[j].off = step; };
+    if (t == T_END_DOWN || t == T_END_UP) nk = walk_links(links, i, t == T_END_UP ? 1u : 0u, visit);
+    else if (t == T_CIRCLE) nk = walk_circle_links(links, i, false, visit);
     uint32_t len = nk + SN_K - 1;
     elen[e] = len;
     etmp_off[e] = base_off[i];

@@ -292,9 +292,11 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
     DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
     if (n_occ) {
+        const uint64_t n_warps = ((uint64_t)n_occ + SN_RD_CHUNK - 1) / SN_RD_CHUNK;
+        const uint32_t cap_per_warp = SN_RD_CHUNK / c->params.min_freq + 10;
         CU(ka.alloc((size_t)n_occ * 16));
-        CU(kb.alloc((size_t)n_occ * 16 * (c->params.min_freq >= 2 ? 1 : 2)));
-        CU(tmp.alloc(radix_sort_tmp_bytes(n_occ) + (size_t)blocks_for(n_occ, SN_RD_TILE) * 8 + 64));
+        CU(kb.alloc(std::max((size_t)n_occ * 16, (size_t)n_warps * cap_per_warp * sizeof(DictEntry))));
+        CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
         // a2
         t_begin(c, "extract");
         k_extract<<<blocks_for(n, SN_EX_READS), 256, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
@@ -312,23 +314,28 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         c->launches += RsMode<RS_HASH32>::PASSES;
         if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
         t_end(c, "sort");
-        // a5 (dictionary is compacted into kb, which is no longer needed by the sort)
+        // a5: per-warp staging in kb (free again after the sort), then an ordered gather into the dictionary
         t_begin(c, "reduce");
-        uint64_t* status = tmp.as<uint64_t>();
-        uint32_t nt = blocks_for(n_occ, SN_RD_TILE);
-        CU(cudaMemsetAsync(status, 0, (size_t)nt * 8, c->st));
-        k_reduce<<<nt, SN_RD_THREADS, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
-            kb.as<DictEntry>(), status, u32c + 1, u32c + 2, occ + 2);
+        DevBuf &wcount = c->pool["warp_count"], &woff = c->pool["warp_off"];
+        CU(wcount.alloc(4 * n_warps)); CU(woff.alloc(8 * (n_warps + 1)));
+        k_reduce<<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
+            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
         KCHECK("k_reduce");
-        t_end(c, "reduce");
-        uint32_t h_n = 0; unsigned long long h_d = 0;
-        CU(cudaMemcpyAsync(&h_n, u32c + 2, 4, cudaMemcpyDeviceToHost, c->st));
+        uint64_t h_n = 0;
+        int r = scan_u32(c, wcount.as<uint32_t>(), n_warps, woff.as<uint64_t>(), &h_n);
+        if (r) return r;
+        uint32_t h_over = 0; unsigned long long h_d = 0;
+        CU(cudaMemcpyAsync(&h_over, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
+        if (h_over) return fail(c, SN_ERR_DATA, "k_reduce staging overflow (pathological hash collisions)");
+        if (h_n >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
         c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
         CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
-        CU(cudaMemcpyAsync(c->dict.p, kb.p, (size_t)h_n * sizeof(DictEntry), cudaMemcpyDeviceToDevice, c->st));
-        CU(cudaStreamSynchronize(c->st));
+        k_reduce_gather<<<blocks_for(n_warps * 32, 256), 256, 0, c->st>>>(kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), woff.as<uint64_t>(),
+            n_warps, c->dict.as<DictEntry>());
+        KCHECK("k_reduce_gather");
+        t_end(c, "reduce");
     } else {
         CU(c->dict.alloc(64));
     }
@@ -365,7 +372,9 @@ int sn_build_edges(sn_ctx* c)
     DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &pos = c->pool["pos"], &list = c->pool["list"], &visited = c->pool["visited"];
     CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(pos.alloc(8ull * (n + 1))); CU(visited.alloc(n));
     CU(cudaMemsetAsync(visited.p, 0, n, c->st));
-    k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
+    DevBuf& links = c->pool["links"];
+    CU(links.alloc(8ull * n));
+    k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>(), etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_classify");
     uint64_t n_ends = 0;
     int r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_ends);
@@ -374,13 +383,13 @@ int sn_build_edges(sn_ctx* c)
         CU(list.alloc(4 * n_ends));
         k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
         KCHECK("k_scatter_flagged");
-        k_walk_count<<<blocks_for(n_ends, 128), 128, 0, c->st>>>(tab, idx, n, list.as<uint32_t>(), (uint32_t)n_ends, etype.as<uint8_t>(),
+        k_walk_count<<<blocks_for(n_ends, 128), 128, 0, c->st>>>(links.as<Link2>(), list.as<uint32_t>(), (uint32_t)n_ends, etype.as<uint8_t>(),
             own_n.as<uint32_t>(), visited.as<uint8_t>());
         KCHECK("k_walk_count");
     }
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
     CU(cudaMemsetAsync(u32c + 4, 0, 4, c->st));
-    k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, idx, n, etype.as<uint8_t>(), visited.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
+    k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), n, etype.as<uint8_t>(), visited.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
     KCHECK("k_circle_count");
     // allocation: bases per owner -> offsets in the unpacked scratch; owner rank -> edge id
     DevBuf &ebases_u32 = c->pool["ebases_u32"], &base_off = c->pool["base_off"];
@@ -397,7 +406,7 @@ int sn_build_edges(sn_ctx* c)
     DevBuf &tmpb = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"], &ebytes = c->pool["ebytes"];
     CU(tmpb.alloc(total_bases + 16)); CU(eflip.alloc(n_edges + 16)); CU(etmp_off.alloc(8 * n_edges + 16)); CU(ebytes.alloc(4 * n_edges + 16));
     CU(c->elen.alloc(4 * n_edges + 16)); CU(c->eoff.alloc(8 * (n_edges + 1)));
-    k_walk_emit<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, idx, n, list.as<uint32_t>(), (uint32_t)n_edges, etype.as<uint8_t>(),
+    k_walk_emit<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), list.as<uint32_t>(), (uint32_t)n_edges, etype.as<uint8_t>(),
         base_off.as<uint64_t>(), tmpb.as<uint8_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(), etmp_off.as<uint64_t>());
     KCHECK("k_walk_emit");
     k_fix_offsets<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, n, c->elen.as<uint32_t>(), eflip.as<uint8_t>());

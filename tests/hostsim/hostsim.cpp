@@ -87,16 +87,17 @@ int hs_edges(Sim* s)
     const uint32_t n = (uint32_t)s->tab.size();
     std::vector<uint8_t> etype(n), visited(n, 0);
     std::vector<uint32_t> own_n(n, 0);
-    for (uint32_t i = 0; i < n; ++i) { int t = classify_entry(d, i); etype[i] = (uint8_t)t; own_n[i] = t == T_SINGLE ? 1u : 0u; }
+    std::vector<Link2> links(n);
+    for (uint32_t i = 0; i < n; ++i) { int t = classify_links(d, i, &links[i]); etype[i] = (uint8_t)t; own_n[i] = t == T_SINGLE ? 1u : 0u; }   // k_classify
     for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_END_DOWN || etype[i] == T_END_UP) {          // k_walk_count
         uint32_t last = i; visited[i] = 1;
-        uint32_t nk = walk_edge(d, i, etype[i], [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
+        uint32_t nk = walk_links(links.data(), i, etype[i] == T_END_UP ? 1u : 0u, [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
         if (i <= last) own_n[i] = nk;
     }
     for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_INTERIOR && !visited[i]) {                     // k_circle_count
         uint32_t m = i; Kmer mk = entry_kmer(s->tab[i]);
-        uint32_t nk = walk_circle(d, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(s->tab[j]); if (q < mk) { mk = q; m = j; } });
-        if (nk) { own_n[m] = nk; etype[m] = 4; }
+        uint32_t nk = walk_circle_links(links.data(), i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(s->tab[j]); if (q < mk) { mk = q; m = j; } });
+        if (nk) { own_n[m] = nk; etype[m] = T_CIRCLE; }
     }
     std::vector<uint32_t> owners; std::vector<uint64_t> base_off(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) { base_off[i + 1] = base_off[i] + (own_n[i] ? own_n[i] + SN_K - 1 : 0); if (own_n[i]) owners.push_back(i); }
@@ -111,9 +112,9 @@ int hs_edges(Sim* s)
         for (int b = 0; b < SN_K; ++b) sq[b] = (uint8_t)kmer_base(k, b);
         s->tab[i].edge = e; s->tab[i].off = 0;
         uint32_t nk = 1;
-        auto visit = [&](uint32_t step, uint32_t j, uint32_t c) { sq[SN_K - 1 + step] = (uint8_t)c; s->tab[j].edge = e; s->tab[j].off = step; };
-        if (t == T_END_DOWN || t == T_END_UP) nk = walk_edge(d, i, t, visit);
-        else if (t == 4) nk = walk_circle(d, i, false, visit);
+        auto visit = [&](uint32_t step, uint32_t j, uint32_t o) { sq[SN_K - 1 + step] = (uint8_t)step_base(s->tab[j], o); s->tab[j].edge = e; s->tab[j].off = step; };
+        if (t == T_END_DOWN || t == T_END_UP) nk = walk_links(links.data(), i, t == T_END_UP ? 1u : 0u, visit);
+        else if (t == T_CIRCLE) nk = walk_circle_links(links.data(), i, false, visit);
         elen[e] = nk + SN_K - 1; etmp[e] = base_off[i];
         eflip[e] = seq_form_u8(sq, elen[e]) == REV ? 1 : 0;
     }
