@@ -1,4 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c2.json; cut -c1-300 gpurun_out/bench_c2.json
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-paths 2>&1 | tail -1 > gpurun_out/bench_c2.json; cut -c1-200 gpurun_out/bench_c2.json
+SN_RS_THREADS=512 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-paths 2>&1 | tail -1 > gpurun_out/bench_c2_512.json; cut -c1-200 gpurun_out/bench_c2_512.json

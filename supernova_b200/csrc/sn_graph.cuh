@@ -9,17 +9,33 @@ namespace sn {
 
 SN_HD Kmer entry_kmer(const DictEntry& e) { Kmer k; k.w0 = e.w0; k.w1 = e.w1; k.w2 = e.w2; return k; }
 
+#define SN_NO_LINK 0xFFFFFFFFu
+struct Link2 { uint32_t x, y; };
+
 // a6: AdjProc::operator() -- drop every pred/succ bit whose neighbour k-mer is not
 // in the dictionary.  Reads only immutable keys of other entries; writes own ctx.
-SN_HD uint32_t prune_ctx(const DictView& d, uint32_t i)
+// While it is looking the neighbours up anyway it remembers, per side, the table index
+// (<< 1 | orientation) of the neighbour when exactly one survives: the candidate unipath
+// links that classify_links validates without searching again.
+SN_HD uint32_t prune_ctx(const DictView& d, uint32_t i, Link2* cand)
 {
     const DictEntry& e = d.tab[i];
     Kmer k = entry_kmer(e);
     uint32_t ctx = e.cc >> 24;
+    uint32_t ns = 0, np = 0, ls = SN_NO_LINK, lp = SN_NO_LINK;
     for (uint32_t c = 0; c < 4; ++c)
-        if (ctx & (1u << c)) { if (dict_find(d, kmer_succ(k, c), nullptr) == SN_NULL_EDGE) ctx &= ~(1u << c); }
+        if (ctx & (1u << c)) {
+            bool rc; uint32_t j = dict_find(d, kmer_succ(k, c), &rc);
+            if (j == SN_NULL_EDGE) ctx &= ~(1u << c); else { ++ns; ls = (j << 1) | (rc ? 1u : 0u); }
+        }
+    // the predecessor side is the successor side of the reverse complement: a walk that leaves
+    // through it sees the neighbour in the orientation of succ(rc(k)) = rc(pred(k))
     for (uint32_t c = 0; c < 4; ++c)
-        if (ctx & (16u << c)) { if (dict_find(d, kmer_pred(k, c), nullptr) == SN_NULL_EDGE) ctx &= ~(16u << c); }
+        if (ctx & (16u << c)) {
+            bool rc; uint32_t j = dict_find(d, kmer_pred(k, c), &rc);
+            if (j == SN_NULL_EDGE) ctx &= ~(16u << c); else { ++np; lp = (j << 1) | (rc ? 0u : 1u); }
+        }
+    if (cand) { cand->x = ns == 1 ? ls : SN_NO_LINK; cand->y = np == 1 ? lp : SN_NO_LINK; }
     return ctx;
 }
 
@@ -31,34 +47,25 @@ enum EntryType { T_SINGLE = 0, T_INTERIOR = 1, T_END_DOWN = 2, T_END_UP = 3, T_C
 // it (:408-428, :445-456); it holds the neighbour's table index << 1 | the orientation (1 = RC
 // of the stored k-mer) in which a walk arriving over this link sees the neighbour.  Walking an
 // edge is then one dependent 8-byte load per k-mer instead of a dictionary probe.
-#define SN_NO_LINK 0xFFFFFFFFu
-struct Link2 { uint32_t x, y; };
-
-SN_HD uint32_t compute_link(const DictView& d, const Kmer& k, uint32_t ctx)
+// A candidate link (the single surviving neighbour on one side, found by prune_ctx) is a
+// unipath link exactly when EdgeBuilder would extend across it (:408-428, :445-456): the
+// neighbour is not a palindrome and, seen in walk orientation, has exactly one predecessor.
+SN_HD uint32_t validate_link(const DictView& d, uint32_t cand)
 {
-    uint32_t s = ctx_succ(ctx);
-    if (!mask_single(s)) return SN_NO_LINK;
-    Kmer nx = kmer_succ(k, mask_code(s));
-    Kmer rc;
-    int form = kmer_form(nx, &rc);
-    if (form == PAL) return SN_NO_LINK;
-    uint32_t j = dict_find_canonical(d, form == REV ? rc : nx);
-    if (j == SN_NULL_EDGE) return SN_NO_LINK;               // cannot happen after pruning
-    uint32_t c = d.tab[j].ctx;
-    uint32_t nctx = form == REV ? ctx_rc(c) : c;
-    if (!mask_single(ctx_pred(nctx))) return SN_NO_LINK;
-    return (j << 1) | (form == REV ? 1u : 0u);
+    if (cand == SN_NO_LINK) return SN_NO_LINK;
+    const DictEntry& nb = d.tab[cand >> 1];
+    if (kmer_is_pal(entry_kmer(nb))) return SN_NO_LINK;
+    uint32_t nctx = (cand & 1u) ? ctx_rc(nb.ctx) : nb.ctx;
+    return mask_single(ctx_pred(nctx)) ? cand : SN_NO_LINK;
 }
 
 // EdgeBuilder::buildEdge dispatch (:335-345) expressed through the links
-SN_HD int classify_links(const DictView& d, uint32_t i, Link2* out)
+SN_HD int classify_links(const DictView& d, uint32_t i, const Link2& cand, Link2* out)
 {
-    const DictEntry& e = d.tab[i];
-    Kmer k = entry_kmer(e);
     out->x = SN_NO_LINK; out->y = SN_NO_LINK;
-    if (kmer_is_pal(k)) return T_SINGLE;
-    out->x = compute_link(d, k, e.ctx);
-    out->y = compute_link(d, kmer_rc(k), ctx_rc(e.ctx));
+    if (kmer_is_pal(entry_kmer(d.tab[i]))) return T_SINGLE;
+    out->x = validate_link(d, cand.x);
+    out->y = validate_link(d, cand.y);
     bool down = out->x != SN_NO_LINK, up = out->y != SN_NO_LINK;
     if (up) return down ? T_INTERIOR : T_END_UP;
     return down ? T_END_DOWN : T_SINGLE;

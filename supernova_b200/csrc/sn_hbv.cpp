@@ -158,58 +158,74 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
             it[j + 1] = x;
         }
     }
-    // HBVBuilder::add / processQueue (:189-228) with digraphE::AddEdge (graph/DigraphTemplate.h:2572-2582)
+    // HBVBuilder::add / processQueue (:189-228).  The loop only assigns ids; the sorted
+    // adjacency lists of digraphE::AddEdge are rebuilt afterwards from to_left/to_right.
     std::vector<int32_t> vid(nV, -1);
-    std::vector<uint8_t> fcnt(nV, 0), tcnt(nV, 0);
-    std::vector<int32_t> fv(4 * (size_t)nV), fe(4 * (size_t)nV), tv(4 * (size_t)nV), te(4 * (size_t)nV);
-    auto add_sorted = [](int32_t* v, int32_t* eo, uint8_t& n, int32_t w, int32_t e) {
-        if (n >= 4) throw std::runtime_error("HBV: more than 4 edges on one side of a vertex");
-        int i = 0; while (i < n && v[i] <= w) ++i;                    // upper_bound
-        for (int j = n; j > i; --j) { v[j] = v[j - 1]; eo[j] = eo[j - 1]; }
-        v[i] = w; eo[i] = e; ++n;
-    };
-    auto done = [&](uint32_t e, uint32_t rc) { return (rc ? H.rev : H.fwd)[e] != -1; };
-    H.src.reserve(2 * nE); H.to_left.reserve(2 * nE); H.to_right.reserve(2 * nE);
-    std::vector<uint32_t> Q; Q.reserve(1024);
-    int32_t nextV = 0;
+    std::vector<int32_t> xlat(2 * nE, -1);             // [2*e + rc] -> HBV edge id
+    H.src.resize(2 * nE); H.to_left.resize(2 * nE); H.to_right.resize(2 * nE);
+    std::vector<uint32_t> Q(2 * nE + 16);
+    int32_t nextV = 0; uint32_t nH = 0;
     for (uint32_t pass = 0; pass < 2; ++pass)
         for (uint64_t oi = 0; oi < nE; ++oi) {
-            uint32_t e0 = order[oi];
-            if (done(e0, pass)) continue;
-            Q.clear(); Q.push_back((e0 << 1) | pass);
-            for (size_t qh = 0; qh < Q.size(); ++qh) {
-                uint32_t e = Q[qh] >> 1, rc = Q[qh] & 1;
-                if (done(e, rc)) continue;
+            const uint32_t e0 = order[oi];
+            if (xlat[2 * (size_t)e0 + pass] != -1) continue;
+            size_t qh = 0, qt = 0;
+            Q[qt++] = (e0 << 1) | pass;
+            while (qh < qt) {
+                const uint32_t it = Q[qh++];
+                if (xlat[it] != -1) continue;
+                const uint32_t e = it >> 1, rc = it & 1;
                 // (a palindromic edge is only ever processed with rc=0: its rev id is set with its fwd id)
-                int32_t g1 = end_group[4 * (size_t)e + 2 * rc + 0], g2 = end_group[4 * (size_t)e + 2 * rc + 1];
+                const int32_t g1 = end_group[4 * (size_t)e + 2 * rc + 0], g2 = end_group[4 * (size_t)e + 2 * rc + 1];
                 if (g1 < 0 || g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
                 if (vid[g1] == -1) vid[g1] = nextV++;
                 if (vid[g2] == -1) vid[g2] = nextV++;
-                int32_t v1 = vid[g1], v2 = vid[g2];
-                int32_t id = (int32_t)H.src.size();
-                H.src.push_back((e << 1) | rc);
-                add_sorted(&fv[4 * (size_t)v1], &fe[4 * (size_t)v1], fcnt[v1], v2, id);
-                add_sorted(&tv[4 * (size_t)v2], &te[4 * (size_t)v2], tcnt[v2], v1, id);
-                H.to_left.push_back(v1); H.to_right.push_back(v2);
-                if (!rc || pal[e]) H.fwd[e] = id;
-                if (rc || pal[e]) H.rev[e] = id;
+                const int32_t id = (int32_t)nH++;
+                H.src[id] = it; H.to_left[id] = vid[g1]; H.to_right[id] = vid[g2];
+                xlat[it] = id;
+                if (pal[e]) xlat[it ^ 1u] = id;
+                if (qt + 16 > Q.size()) {                           // keep the FIFO compact
+                    std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
+                    if (qt + 16 > Q.size()) Q.resize(2 * Q.size());
+                }
                 for (int32_t g : {g1, g2})
                     for (uint32_t x = gstart[g]; x < gstart[g + 1]; ++x) {
-                        uint32_t it = gitems[x];
-                        if (!done(it >> 2, (it >> 1) & 1)) Q.push_back(((it >> 2) << 1) | ((it >> 1) & 1));
+                        const uint32_t t2 = gitems[x] >> 1;              // edge << 1 | rc
+                        if (xlat[t2] == -1) Q[qt++] = t2;
                     }
             }
         }
     if (nextV != nV) throw std::runtime_error("HBV: vertex numbering did not reach every vertex");
     H.n_vert = nV;
+    H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);
+    for (uint64_t e = 0; e < nE; ++e) { H.fwd[e] = xlat[2 * e]; H.rev[e] = xlat[2 * e + 1]; }
+    // digraphE::AddEdge (graph/DigraphTemplate.h:2572-2582) inserts edge id n at upper_bound of the
+    // neighbour vertex: every list ends up sorted by (neighbour, id).  Counting sort by vertex
+    // (ids ascending), then order each short list by neighbour, stably.
     H.from_start.assign(nV + 1, 0); H.to_start.assign(nV + 1, 0);
-    for (int32_t v = 0; v < nV; ++v) { H.from_start[v + 1] = H.from_start[v] + fcnt[v]; H.to_start[v + 1] = H.to_start[v] + tcnt[v]; }
-    const size_t nH = H.src.size();
+    for (uint32_t h = 0; h < nH; ++h) { ++H.from_start[H.to_left[h] + 1]; ++H.to_start[H.to_right[h] + 1]; }
+    for (int32_t v = 0; v < nV; ++v) { H.from_start[v + 1] += H.from_start[v]; H.to_start[v + 1] += H.to_start[v]; }
     H.from_v.resize(nH); H.from_e.resize(nH); H.to_v.resize(nH); H.to_e.resize(nH);
-    for (int32_t v = 0; v < nV; ++v) {
-        for (int i = 0; i < fcnt[v]; ++i) { H.from_v[H.from_start[v] + i] = fv[4 * (size_t)v + i]; H.from_e[H.from_start[v] + i] = fe[4 * (size_t)v + i]; }
-        for (int i = 0; i < tcnt[v]; ++i) { H.to_v[H.to_start[v] + i] = tv[4 * (size_t)v + i]; H.to_e[H.to_start[v] + i] = te[4 * (size_t)v + i]; }
+    {
+        std::vector<uint32_t> fc(H.from_start.begin(), H.from_start.end() - 1), tc(H.to_start.begin(), H.to_start.end() - 1);
+        for (uint32_t h = 0; h < nH; ++h) {
+            uint32_t a = fc[H.to_left[h]]++; H.from_v[a] = H.to_right[h]; H.from_e[a] = (int32_t)h;
+            uint32_t b = tc[H.to_right[h]]++; H.to_v[b] = H.to_left[h]; H.to_e[b] = (int32_t)h;
+        }
     }
+    auto order_lists = [&](const std::vector<uint32_t>& start, std::vector<int32_t>& nb, std::vector<int32_t>& eo) {
+        for (int32_t v = 0; v < nV; ++v) {
+            uint32_t s = start[v], n = start[v + 1] - s;
+            if (n > 4) throw std::runtime_error("HBV: more than 4 edges on one side of a vertex");
+            for (uint32_t i = 1; i < n; ++i) {                       // stable insertion sort by neighbour
+                int32_t w = nb[s + i], e = eo[s + i]; uint32_t j = i;
+                while (j > 0 && nb[s + j - 1] > w) { nb[s + j] = nb[s + j - 1]; eo[s + j] = eo[s + j - 1]; --j; }
+                nb[s + j] = w; eo[s + j] = e;
+            }
+        }
+    };
+    order_lists(H.from_start, H.from_v, H.from_e);
+    order_lists(H.to_start, H.to_v, H.to_e);
     // Involution: the reverse complement of HBV edge fwd[e] is rev[e]
     H.inv.assign(nH, -1);
     for (uint64_t e = 0; e < nE; ++e) { H.inv[H.fwd[e]] = H.rev[e]; H.inv[H.rev[e]] = H.fwd[e]; }

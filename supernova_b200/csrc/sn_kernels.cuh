@@ -415,12 +415,14 @@ __global__ void __launch_bounds__(256) k_build_index(const DictEntry* __restrict
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (tab[mid].h < key) lo = mid + 1; else hi = mid; }
     idx[b] = lo;
 }
-__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n)
+__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n, Link2* __restrict__ cand)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     DictView d; d.tab = tab; d.idx = idx; d.n = n;
-    tab[i].ctx = prune_ctx(d, i);
+    Link2 l;
+    tab[i].ctx = prune_ctx(d, i, &l);
+    cand[i] = l;
 }
 
 // ---------------------------------------------------------------------------
@@ -430,13 +432,13 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* _
 // owned by its smallest entry.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
-                                                  Link2* __restrict__ links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
+                                                  Link2* links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     DictView d; d.tab = tab; d.idx = idx; d.n = n;
     Link2 l;
-    int t = classify_links(d, i, &l);
+    int t = classify_links(d, i, links[i], &l);          // links[] holds prune's candidates on entry
     links[i] = l;
     etype[i] = (uint8_t)t;
     own_n[i] = t == T_SINGLE ? 1u : 0u;

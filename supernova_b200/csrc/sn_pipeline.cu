@@ -288,7 +288,6 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     c->cnt.n_kmer_occurrences = h_occ;
     if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads (minimizer buckets / more GPUs)");
     const uint32_t n_occ = (uint32_t)h_occ;
-    c->dict.release(); c->idx.release();
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
     DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
     if (n_occ) {
@@ -359,12 +358,13 @@ int sn_build_edges(sn_ctx* c)
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
     c->hedges = snh::Edges();
-    c->ebases.release(); c->eoff.release(); c->elen.release();
     if (!n) { c->hedges.off.assign(1, 0); c->hedges.packed.assign(16, 0); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
     const uint32_t* idx = c->idx.as<uint32_t>();
     t_begin(c, "prune");
-    k_prune<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n);
+    DevBuf& links = c->pool["links"];
+    CU(links.alloc(8ull * n));
+    k_prune<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>());
     KCHECK("k_prune");
     t_end(c, "prune");
 
@@ -372,8 +372,6 @@ int sn_build_edges(sn_ctx* c)
     DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &pos = c->pool["pos"], &list = c->pool["list"], &visited = c->pool["visited"];
     CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(pos.alloc(8ull * (n + 1))); CU(visited.alloc(n));
     CU(cudaMemsetAsync(visited.p, 0, n, c->st));
-    DevBuf& links = c->pool["links"];
-    CU(links.alloc(8ull * n));
     k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>(), etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_classify");
     uint64_t n_ends = 0;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "sn_kmer.cuh"
 
 namespace sn {
@@ -38,19 +39,41 @@ __device__ __forceinline__ uint64_t ld_status(const uint64_t* p)
 { uint64_t x; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory"); return x; }
 
 // exclusive prefix of `aggregate` over tiles [0,tile); `status` has `stride` words per tile.
-__device__ __forceinline__ uint64_t tile_lookback(uint64_t* status, uint32_t stride, uint32_t slot, uint32_t tile, uint64_t aggregate)
+// The walk over the predecessors is windowed: SN_LB_WINDOW status words are requested at
+// once, so the latency of the (L2) loads overlaps instead of adding up tile by tile.
+#define SN_LB_WINDOW 8
+__device__ __forceinline__ void lookback_publish(uint64_t* status, uint32_t stride, uint32_t slot, uint32_t tile, uint64_t aggregate)
 {
-    if (tile == 0) { st_status(status + slot, SN_ST_PREFIX, aggregate); return 0; }
-    st_status(status + (size_t)tile * stride + slot, SN_ST_AGG, aggregate);
+    if (tile == 0) st_status(status + slot, SN_ST_PREFIX, aggregate);
+    else st_status(status + (size_t)tile * stride + slot, SN_ST_AGG, aggregate);
+}
+__device__ __forceinline__ uint64_t lookback_walk(uint64_t* status, uint32_t stride, uint32_t slot, uint32_t tile, uint64_t aggregate)
+{
+    if (tile == 0) return 0;
     uint64_t excl = 0;
-    for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
-        uint64_t s;
-        do { s = ld_status(status + (size_t)t * stride + slot); } while ((s >> 62) == SN_ST_INVALID);
-        excl += s & SN_ST_VMASK;
-        if ((s >> 62) == SN_ST_PREFIX) break;
+    int64_t t = (int64_t)tile - 1;
+    bool done = false;
+    while (!done && t >= 0) {
+        uint64_t s[SN_LB_WINDOW];
+#pragma unroll
+        for (int i = 0; i < SN_LB_WINDOW; ++i) if (t - i >= 0) s[i] = ld_status(status + (size_t)(t - i) * stride + slot);
+#pragma unroll
+        for (int i = 0; i < SN_LB_WINDOW; ++i) {
+            if (!done && t - i >= 0) {
+                while ((s[i] >> 62) == SN_ST_INVALID) s[i] = ld_status(status + (size_t)(t - i) * stride + slot);
+                excl += s[i] & SN_ST_VMASK;
+                if ((s[i] >> 62) == SN_ST_PREFIX) done = true;
+            }
+        }
+        t -= SN_LB_WINDOW;
     }
     st_status(status + (size_t)tile * stride + slot, SN_ST_PREFIX, excl + aggregate);
     return excl;
+}
+__device__ __forceinline__ uint64_t tile_lookback(uint64_t* status, uint32_t stride, uint32_t slot, uint32_t tile, uint64_t aggregate)
+{
+    lookback_publish(status, stride, slot, tile, aggregate);
+    return lookback_walk(status, stride, slot, tile, aggregate);
 }
 
 // ---------------------------------------------------------------------------
@@ -139,13 +162,11 @@ inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out
 //   RS_HASH32 : kmer_hash(x,y,z), 4 passes                    (the k-mer stream)
 // Every pass reads each record once and writes it once.
 // ---------------------------------------------------------------------------
-#define SN_RS_THREADS 512
-#define SN_RS_WARPS (SN_RS_THREADS / 32)
 #define SN_RS_ITEMS 8
-#define SN_RS_TILE (SN_RS_THREADS * SN_RS_ITEMS)
 enum { RS_KEY96 = 0, RS_HASH32 = 1 };
 template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : 4; };
 #define SN_RS_MAX_PASSES 12
+#define SN_RS_MIN_TILE (256 * SN_RS_ITEMS)
 
 __device__ __forceinline__ uint32_t rs_hash(const uint4& k) { Kmer q; q.w0 = k.x; q.w1 = k.y; q.w2 = k.z; return kmer_hash(q); }
 template <int MODE>
@@ -196,9 +217,10 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
     h[threadIdx.x] = sm[threadIdx.x] - v;
 }
 
+template <int THREADS>
 struct RsSmem {
-    uint4 keys[SN_RS_TILE];                    // 64 KB reorder buffer
-    uint32_t warp_cnt[SN_RS_WARPS][256];       // per-warp digit counters -> exclusive warp offsets
+    uint4 keys[THREADS * SN_RS_ITEMS];         // reorder buffer
+    uint32_t warp_cnt[THREADS / 32][256];      // per-warp digit counters -> exclusive warp offsets
     uint32_t tile_start[256];                  // exclusive scan of the tile's digit totals
     uint32_t gdst[256];                        // global destination of smem slot s with digit d: gdst[d] + s
     uint32_t scan_tmp[8];
@@ -206,21 +228,23 @@ struct RsSmem {
 };
 
 // One digit pass: read each record once, write it once.
-template <int MODE>
-__global__ void __launch_bounds__(SN_RS_THREADS, 2)
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, int pass,
              const uint32_t* __restrict__ ghist /* exclusive starts, this pass */, uint64_t* status, uint32_t* tile_counter)
 {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * SN_RS_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem& S = *reinterpret_cast<RsSmem*>(smem_raw);
+    RsSmem<THREADS>& S = *reinterpret_cast<RsSmem<THREADS>*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) S.tile_id = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < SN_RS_WARPS * 256; i += SN_RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * 256; i += THREADS) (&S.warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile_id;
-    const uint64_t tile_base = (uint64_t)tile * SN_RS_TILE;
-    const uint32_t valid = (uint32_t)min((uint64_t)SN_RS_TILE, (uint64_t)n - tile_base);
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint32_t valid = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_base);
 
     // warp-striped load: warp w owns [w*256, (w+1)*256); item j of lane l is w*256 + j*32 + l.
     // Records past the end get digit 255 and the highest ranks of it: they are never written.
@@ -232,12 +256,18 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
         if (li < valid) { key[j] = in[tile_base + li]; dr[j] = rs_digit<MODE>(key[j], pass); }
         else { key[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); dr[j] = 0xFFu; }
     }
-    // stable in-warp ranking by digit: match_any groups equal digits, the group leader
-    // bumps the warp's private counter for that digit.
+    // stable in-warp ranking by digit ("warp-wide radix partitioning"): eight ballots, one per
+    // digit bit, give every lane the mask of lanes holding the same digit; the lowest such
+    // lane bumps the warp's private counter for that digit.
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
         uint32_t d = dr[j];
-        uint32_t peers = __match_any_sync(SN_FULL, d);
+        uint32_t peers = SN_FULL;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            uint32_t bal = __ballot_sync(SN_FULL, (d >> bit) & 1u);
+            peers &= ((d >> bit) & 1u) ? bal : ~bal;
+        }
         uint32_t leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if (lane == leader) { base = S.warp_cnt[warp][d]; S.warp_cnt[warp][d] = base + __popc(peers); }
@@ -245,40 +275,44 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
         dr[j] = d | ((base + __popc(peers & lanemask_lt())) << 8);
     }
     __syncthreads();
-    // thread d (< 256): exclusive scan of digit d over the warps, tile total, look-back
-    uint32_t tot = 0, prev = 0;
+    // thread d (< 256): exclusive scan of digit d over the warps -> tile total, published at once
+    // as this tile's AGGREGATE; then the exclusive scan of the totals over the 256 digits
+    uint32_t tot = 0, texcl = 0;
     if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < SN_RS_WARPS; ++w) { uint32_t c = S.warp_cnt[w][tid]; S.warp_cnt[w][tid] = tot; tot += c; }
-        prev = (uint32_t)tile_lookback(status, 256, tid, tile, tot);
-        // exclusive scan of the tile totals over the 256 digits (8 warps)
+        for (int w = 0; w < WARPS; ++w) { uint32_t c = S.warp_cnt[w][tid]; S.warp_cnt[w][tid] = tot; tot += c; }
+        lookback_publish(status, 256, tid, tile, tot);
         uint32_t x = tot;
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
         if (lane == 31) S.scan_tmp[warp] = x;
-        tot = x - tot;                             // exclusive within the warp
+        texcl = x - tot;                           // exclusive within the warp
     }
     __syncthreads();
     if (tid < 256) {
         uint32_t wbase = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) if (w < (int)warp) wbase += S.scan_tmp[w];
-        uint32_t excl = wbase + tot;
-        S.tile_start[tid] = excl;
-        S.gdst[tid] = ghist[tid] + prev - excl;    // may wrap below zero; the later + s brings it back (mod 2^32)
+        texcl += wbase;
+        S.tile_start[tid] = texcl;
     }
     __syncthreads();
-    // scatter into the smem reorder buffer
+    // scatter into the smem reorder buffer (frees the key registers before the look-back)
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
         uint32_t d = dr[j] & 0xFFu;
         uint32_t pos = S.tile_start[d] + S.warp_cnt[warp][d] + (dr[j] >> 8);
         S.keys[pos] = key[j];
     }
+    // look-back over the predecessor tiles for this digit's global offset
+    if (tid < 256) {
+        uint32_t prev = (uint32_t)lookback_walk(status, 256, tid, tile, tot);
+        S.gdst[tid] = ghist[tid] + prev - texcl;   // may wrap below zero; the later + s brings it back (mod 2^32)
+    }
     __syncthreads();
     // coalesced write-out: consecutive slots of one digit are consecutive in global memory
 #pragma unroll
     for (int j = 0; j < SN_RS_ITEMS; ++j) {
-        uint32_t s = j * SN_RS_THREADS + tid;
+        uint32_t s = j * THREADS + tid;
         if (s < valid) {
             uint4 k = S.keys[s];
             uint32_t d = rs_digit<MODE>(k, pass);
@@ -289,7 +323,7 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
 
 inline size_t radix_sort_tmp_bytes(uint32_t n)
 {
-    uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
+    uint32_t nt = (n + SN_RS_MIN_TILE - 1) / SN_RS_MIN_TILE;
     return (size_t)SN_RS_MAX_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
 }
 // Sorts n (< 2^32) records in two steps so the caller can time them apart:
@@ -305,27 +339,39 @@ inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, 
     k_rs_scan_hist<<<RsMode<MODE>::PASSES, 256, 0, st>>>(hist);
     return cudaGetLastError();
 }
-template <int MODE>
-inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
+inline int rs_threads()
 {
-    if (n == 0) return cudaSuccess;
-    uint32_t nt = (n + SN_RS_TILE - 1) / SN_RS_TILE;
+    static int t = 0;
+    if (!t) { const char* e = getenv("SN_RS_THREADS"); t = e ? atoi(e) : 512; if (t != 256 && t != 512) t = 512; }
+    return t;
+}
+template <int MODE, int THREADS>
+inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
+{
+    constexpr int TILE = THREADS * SN_RS_ITEMS;
+    uint32_t nt = (n + TILE - 1) / TILE;
     uint32_t* hist = (uint32_t*)tmp;
     uint32_t* counters = hist + SN_RS_MAX_PASSES * 256;
     uint64_t* status = (uint64_t*)(counters + 16);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_rs_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
+        cudaError_t e = cudaFuncSetAttribute(k_rs_scatter<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<THREADS>));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     uint4* src = a; uint4* dst = b;
     for (int p = 0; p < RsMode<MODE>::PASSES; ++p) {
         cudaMemsetAsync(status, 0, (size_t)nt * 256 * 8, st);
-        k_rs_scatter<MODE><<<nt, SN_RS_THREADS, sizeof(RsSmem), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
+        k_rs_scatter<MODE, THREADS><<<nt, THREADS, sizeof(RsSmem<THREADS>), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
         uint4* t = src; src = dst; dst = t;
     }
     return cudaGetLastError();
+}
+template <int MODE>
+inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    return rs_threads() == 512 ? radix_sort_passes_t<MODE, 512>(a, b, n, tmp, st) : radix_sort_passes_t<MODE, 256>(a, b, n, tmp, st);
 }
 template <int MODE>
 inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)

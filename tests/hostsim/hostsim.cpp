@@ -17,6 +17,7 @@ using namespace sn;
 
 struct Sim {
     std::vector<DictEntry> tab;
+    std::vector<Link2> cand;
     std::vector<uint32_t> idx;
     std::vector<uint32_t> perm;      // perm[i] = position in `tab` of the i-th input (k-mer sorted) record
     snh::Edges edges;
@@ -76,7 +77,8 @@ void hs_prune(Sim* s)
 {
     DictView d = s->view();
     std::vector<uint32_t> ctx(s->tab.size());
-    for (uint32_t i = 0; i < s->tab.size(); ++i) ctx[i] = prune_ctx(d, i);      // k_prune
+    s->cand.resize(s->tab.size());
+    for (uint32_t i = 0; i < s->tab.size(); ++i) ctx[i] = prune_ctx(d, i, &s->cand[i]);      // k_prune
     for (uint32_t i = 0; i < s->tab.size(); ++i) s->tab[i].ctx = ctx[i];
 }
 
@@ -88,7 +90,7 @@ int hs_edges(Sim* s)
     std::vector<uint8_t> etype(n), visited(n, 0);
     std::vector<uint32_t> own_n(n, 0);
     std::vector<Link2> links(n);
-    for (uint32_t i = 0; i < n; ++i) { int t = classify_links(d, i, &links[i]); etype[i] = (uint8_t)t; own_n[i] = t == T_SINGLE ? 1u : 0u; }   // k_classify
+    for (uint32_t i = 0; i < n; ++i) { int t = classify_links(d, i, s->cand[i], &links[i]); etype[i] = (uint8_t)t; own_n[i] = t == T_SINGLE ? 1u : 0u; }   // k_classify
     for (uint32_t i = 0; i < n; ++i) if (etype[i] == T_END_DOWN || etype[i] == T_END_UP) {          // k_walk_count
         uint32_t last = i; visited[i] = 1;
         uint32_t nk = walk_links(links.data(), i, etype[i] == T_END_UP ? 1u : 0u, [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
