@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-paths 2>&1 | tail -1 > gpurun_out/bench_c2.json; cut -c1-200 gpurun_out/bench_c2.json
-SN_RS_THREADS=512 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-paths 2>&1 | tail -1 > gpurun_out/bench_c2_512.json; cut -c1-200 gpurun_out/bench_c2_512.json
+ncu --set full --clock-control none --import-source on -k regex:'k_rs_scatter|k_reduce$' -s 1 -c 3 -o gpurun_out/prof_mid3 python bench.py --workload mid --steps 1 --warmup 0 --no-cpu-baseline --no-paths > gpurun_out/ncu_full_mid3.log 2>&1
+tail -2 gpurun_out/ncu_full_mid3.log | cut -c1-200

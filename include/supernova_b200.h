@@ -120,6 +120,23 @@ int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_
  * work_dir/tmp.paths (when with_paths) and work_dir/stats/histogram_kmer_count.json.      */
 int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* params, int with_paths, int write_files);
 
+/* ---- multi-GPU (one context per rank; the caller issues the collectives) ------------------------
+ * The k-mer stream is range-partitioned over the ranks by owner(k) = (hash(k) * nparts) >> 32.
+ *   1. sn_mg_partition_records : good lengths + k-mer records of this rank's reads, grouped by
+ *      owner; part_counts[nparts] records per owner, *dev_records the DEVICE buffer holding them
+ *      back to back (16 bytes per record).
+ *   2. caller: alltoallv of the records into sn_mg_recv_buffer(total received).
+ *   3. sn_mg_count_received    : sort + count + filter of the received records -> this rank's
+ *      slice of the dictionary (*dev_dict, n_kmers entries of 32 bytes, DEVICE).
+ *   4. caller: allgather of the slices, in rank order, into sn_mg_dictionary_buffer(total).
+ *   5. sn_mg_install_dictionary: adopts the gathered dictionary; sn_build_edges / sn_build_hbv /
+ *      sn_path_reads then run as on one GPU (graph replicated, reads stay sharded).            */
+int   sn_mg_partition_records(sn_ctx* ctx, const sn_params* params, uint32_t nparts, uint64_t* part_counts, void** dev_records);
+void* sn_mg_recv_buffer(sn_ctx* ctx, uint64_t n_records);
+int   sn_mg_count_received(sn_ctx* ctx, uint64_t n_records, uint64_t* n_kmers, void** dev_dict);
+void* sn_mg_dictionary_buffer(sn_ctx* ctx, uint64_t n_total);
+int   sn_mg_install_dictionary(sn_ctx* ctx, uint64_t n_total);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) of the most recent run of a stage or
  * kernel group, in milliseconds; names: "goodlen","extract","sort_hist","sort","reduce","index","prune",

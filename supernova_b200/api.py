@@ -74,6 +74,13 @@ def lib():
         L.sn_free.argtypes = [vp]
         L.sn_write_read_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64, vp, vp, vp, vp, vp, vp]
         L.sn_device_count.restype = i32
+        L.sn_mg_partition_records.argtypes = [vp, C.POINTER(Params), C.c_uint32, vp, C.POINTER(vp)]
+        L.sn_mg_recv_buffer.argtypes = [vp, u64]
+        L.sn_mg_recv_buffer.restype = vp
+        L.sn_mg_count_received.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(vp)]
+        L.sn_mg_dictionary_buffer.argtypes = [vp, u64]
+        L.sn_mg_dictionary_buffer.restype = vp
+        L.sn_mg_install_dictionary.argtypes = [vp, u64]
         _LIB = L
     return _LIB
 
@@ -205,6 +212,35 @@ class Context:
         wf = (work_dir is not None) if write_files is None else write_files
         self._ck(self.L.sn_build_read_qgraph48(self.h, None if work_dir is None else work_dir.encode(), C.byref(p),
                                                int(with_paths), int(wf)))
+
+    # ---- multi-GPU pieces (see supernova_b200/multigpu.py) --------------------------------
+    def mg_partition_records(self, params, nparts):
+        p = params or Params()
+        counts = (C.c_uint64 * nparts)()
+        ptr = C.c_void_p()
+        self._ck(self.L.sn_mg_partition_records(self.h, C.byref(p), nparts, counts, C.byref(ptr)))
+        return [int(x) for x in counts], int(ptr.value or 0)
+
+    def mg_recv_buffer(self, n_records):
+        p = self.L.sn_mg_recv_buffer(self.h, n_records)
+        if not p:
+            raise SnError(self.L.sn_last_error(self.h).decode())
+        return int(p)
+
+    def mg_count_received(self, n_records):
+        nk = C.c_uint64()
+        ptr = C.c_void_p()
+        self._ck(self.L.sn_mg_count_received(self.h, n_records, C.byref(nk), C.byref(ptr)))
+        return int(nk.value), int(ptr.value or 0)
+
+    def mg_dictionary_buffer(self, n_total):
+        p = self.L.sn_mg_dictionary_buffer(self.h, n_total)
+        if not p:
+            raise SnError(self.L.sn_last_error(self.h).decode())
+        return int(p)
+
+    def mg_install_dictionary(self, n_total):
+        self._ck(self.L.sn_mg_install_dictionary(self.h, n_total))
 
     # ---- results ----------------------------------------------------------------------
     def counts(self):

@@ -255,20 +255,22 @@ int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
 }
 
 // ---------------------------------------------------------------------------
-int sn_count_kmers(sn_ctx* c, const sn_params* p)
+// ---- pieces of the count stage (shared by the single-GPU call and the multi-GPU calls) ----
+static int count_set_params(sn_ctx* c, const sn_params* p)
 {
-    if (!c) return SN_ERR_ARG;
-    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_count_kmers: no reads loaded");
-    CU(cudaSetDevice(c->device));
     if (p) c->params = *p;
     if (c->params.min_bc > 2) return fail(c, SN_ERR_ARG, "min_bc > 2 is not supported (the reference pipeline fixes MIN_BC=2, 10X/DF.cc:140)");
     if (c->params.min_freq == 0) c->params.min_freq = 1;
+    return SN_OK;
+}
+// a1 + a2: good lengths, then the k-mer records of this context's reads into pool["keys_a"]
+static int count_extract(sn_ctx* c, uint32_t* n_occ_out)
+{
     const uint64_t n = c->cnt.n_reads;
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [0] occurrences, [1] cursor, [2] distinct
-    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [0] bad reads, [1] tile counter, [2] n_out
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [0] bad reads, [3] reduce overflow
     CU(cudaMemsetAsync(c->counters.p, 0, 256, c->st));
     CU(c->goodlen.alloc(4 * n));
-    // a1
     t_begin(c, "goodlen");
     if (c->have_pq) {
         k_pqvec_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>(), c->len.as<uint32_t>(),
@@ -286,59 +288,68 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     CU(cudaStreamSynchronize(c->st));
     if (h_bad) return fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count");
     c->cnt.n_kmer_occurrences = h_occ;
-    if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads (minimizer buckets / more GPUs)");
+    if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads over more GPUs");
     const uint32_t n_occ = (uint32_t)h_occ;
+    *n_occ_out = n_occ;
+    if (!n_occ) return SN_OK;
+    DevBuf& ka = c->pool["keys_a"];
+    CU(ka.alloc((size_t)n_occ * 16));
+    t_begin(c, "extract");
+    k_extract<<<blocks_for(n, SN_EX_READS), 256, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+        c->have_bc ? c->bc.as<int32_t>() : nullptr, c->params.ign_bc_below, ka.as<uint4>(), occ + 1);
+    KCHECK("k_extract");
+    t_end(c, "extract");
+    return SN_OK;
+}
+// a4 + a5: sorts the n_occ records in pool["keys_a"] by hash and reduces them into c->dict
+static int count_sort_reduce(sn_ctx* c, uint32_t n_occ)
+{
+    unsigned long long* occ = c->counters.as<unsigned long long>();
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
+    if (!n_occ) { CU(c->dict.alloc(64)); return SN_OK; }
     DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
-    if (n_occ) {
-        const uint64_t n_warps = ((uint64_t)n_occ + SN_RD_CHUNK - 1) / SN_RD_CHUNK;
-        const uint32_t cap_per_warp = SN_RD_CHUNK / c->params.min_freq + 10;
-        CU(ka.alloc((size_t)n_occ * 16));
-        CU(kb.alloc(std::max((size_t)n_occ * 16, (size_t)n_warps * cap_per_warp * sizeof(DictEntry))));
-        CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
-        // a2
-        t_begin(c, "extract");
-        k_extract<<<blocks_for(n, SN_EX_READS), 256, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            c->have_bc ? c->bc.as<int32_t>() : nullptr, c->params.ign_bc_below, ka.as<uint4>(), occ + 1);
-        KCHECK("k_extract");
-        t_end(c, "extract");
-        // a4
-        t_begin(c, "sort_hist");
-        cudaError_t e = radix_sort_histograms<RS_HASH32>(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
-        c->launches += 2;
-        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort histograms: ") + cudaGetErrorString(e));
-        t_end(c, "sort_hist");
-        t_begin(c, "sort");
-        e = radix_sort_passes<RS_HASH32>(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, c->st);
-        c->launches += RsMode<RS_HASH32>::PASSES;
-        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
-        t_end(c, "sort");
-        // a5: per-warp staging in kb (free again after the sort), then an ordered gather into the dictionary
-        t_begin(c, "reduce");
-        DevBuf &wcount = c->pool["warp_count"], &woff = c->pool["warp_off"];
-        CU(wcount.alloc(4 * n_warps)); CU(woff.alloc(8 * (n_warps + 1)));
-        k_reduce<<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
-            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
-        KCHECK("k_reduce");
-        uint64_t h_n = 0;
-        int r = scan_u32(c, wcount.as<uint32_t>(), n_warps, woff.as<uint64_t>(), &h_n);
-        if (r) return r;
-        uint32_t h_over = 0; unsigned long long h_d = 0;
-        CU(cudaMemcpyAsync(&h_over, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaStreamSynchronize(c->st));
-        if (h_over) return fail(c, SN_ERR_DATA, "k_reduce staging overflow (pathological hash collisions)");
-        if (h_n >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
-        c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
-        CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
-        k_reduce_gather<<<blocks_for(n_warps * 32, 256), 256, 0, c->st>>>(kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), woff.as<uint64_t>(),
-            n_warps, c->dict.as<DictEntry>());
-        KCHECK("k_reduce_gather");
-        t_end(c, "reduce");
-    } else {
-        CU(c->dict.alloc(64));
-    }
-    // prefix index
+    const uint64_t n_warps = ((uint64_t)n_occ + SN_RD_CHUNK - 1) / SN_RD_CHUNK;
+    const uint32_t cap_per_warp = SN_RD_CHUNK / c->params.min_freq + 10;
+    CU(kb.alloc(std::max((size_t)n_occ * 16, (size_t)n_warps * cap_per_warp * sizeof(DictEntry))));
+    CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
+    t_begin(c, "sort_hist");
+    cudaError_t e = radix_sort_histograms<RS_HASH32>(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
+    c->launches += 2;
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort histograms: ") + cudaGetErrorString(e));
+    t_end(c, "sort_hist");
+    t_begin(c, "sort");
+    e = radix_sort_passes<RS_HASH32>(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, 0, c->st);
+    c->launches += RsMode<RS_HASH32>::PASSES;
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
+    t_end(c, "sort");
+    // per-warp staging in kb (free again after the sort), then an ordered gather into the dictionary
+    t_begin(c, "reduce");
+    DevBuf &wcount = c->pool["warp_count"], &woff = c->pool["warp_off"];
+    CU(wcount.alloc(4 * n_warps)); CU(woff.alloc(8 * (n_warps + 1)));
+    CU(cudaMemsetAsync(occ + 2, 0, 8, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
+    k_reduce<<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
+        c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
+    KCHECK("k_reduce");
+    uint64_t h_n = 0;
+    int r = scan_u32(c, wcount.as<uint32_t>(), n_warps, woff.as<uint64_t>(), &h_n);
+    if (r) return r;
+    uint32_t h_over = 0; unsigned long long h_d = 0;
+    CU(cudaMemcpyAsync(&h_over, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_over) return fail(c, SN_ERR_DATA, "k_reduce staging overflow (pathological hash collisions)");
+    if (h_n >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
+    c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
+    CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
+    k_reduce_gather<<<blocks_for(n_warps * 32, 256), 256, 0, c->st>>>(kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), woff.as<uint64_t>(),
+        n_warps, c->dict.as<DictEntry>());
+    KCHECK("k_reduce_gather");
+    t_end(c, "reduce");
+    return SN_OK;
+}
+static int count_build_index(sn_ctx* c)
+{
     t_begin(c, "index");
     CU(c->idx.alloc(((1ull << SN_IDX_BITS) + 1) * 4));
     k_build_index<<<blocks_for((1ull << SN_IDX_BITS) + 1, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), (uint32_t)c->cnt.n_kmers, c->idx.as<uint32_t>());
@@ -347,6 +358,88 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     CU(cudaStreamSynchronize(c->st));
     c->stage = 2;
     return SN_OK;
+}
+
+int sn_count_kmers(sn_ctx* c, const sn_params* p)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_count_kmers: no reads loaded");
+    CU(cudaSetDevice(c->device));
+    int r; uint32_t n_occ = 0;
+    if ((r = count_set_params(c, p))) return r;
+    if ((r = count_extract(c, &n_occ))) return r;
+    if ((r = count_sort_reduce(c, n_occ))) return r;
+    return count_build_index(c);
+}
+
+// ---- multi-GPU: the k-mer stream is range-partitioned by hash over the ranks ---------------
+// owner(k) = (kmer_hash(k) * nparts) >> 32, monotone in the hash, so the per-rank dictionaries
+// concatenated in rank order are globally ordered by (hash, k-mer).  The collectives
+// themselves (one alltoallv of records, one allgather of dictionaries) are issued by the
+// caller on these device buffers (torch.distributed / NCCL in supernova_b200/multigpu.py).
+int sn_mg_partition_records(sn_ctx* c, const sn_params* p, uint32_t nparts, uint64_t* part_counts, void** dev_records)
+{
+    if (!c || !part_counts || !dev_records || nparts == 0 || nparts > 256) return SN_ERR_ARG;
+    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition_records: no reads loaded");
+    CU(cudaSetDevice(c->device));
+    int r; uint32_t n_occ = 0;
+    if ((r = count_set_params(c, p))) return r;
+    if ((r = count_extract(c, &n_occ))) return r;
+    for (uint32_t i = 0; i < nparts; ++i) part_counts[i] = 0;
+    DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
+    *dev_records = nullptr;
+    if (!n_occ) return SN_OK;
+    CU(kb.alloc((size_t)n_occ * 16));
+    CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
+    t_begin(c, "partition");
+    uint32_t hist[256];
+    cudaError_t e = radix_partition_by_owner(ka.as<uint4>(), kb.as<uint4>(), n_occ, nparts, tmp.p, c->num_sms, hist, c->st);
+    c->launches += 3;
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("owner partition: ") + cudaGetErrorString(e));
+    t_end(c, "partition");
+    for (uint32_t i = 0; i < nparts; ++i) part_counts[i] = (i + 1 < 256 ? hist[i + 1] : n_occ) - hist[i];
+    part_counts[nparts - 1] = n_occ - hist[nparts - 1];
+    *dev_records = kb.p;
+    return SN_OK;
+}
+void* sn_mg_recv_buffer(sn_ctx* c, uint64_t n_records)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    DevBuf& ka = c->pool["keys_a"];
+    if (ka.alloc((size_t)std::max<uint64_t>(n_records, 1) * 16) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
+    return ka.p;
+}
+int sn_mg_count_received(sn_ctx* c, uint64_t n_records, uint64_t* n_kmers, void** dev_dict)
+{
+    if (!c || !n_kmers || !dev_dict) return SN_ERR_ARG;
+    if (n_records >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 received records");
+    CU(cudaSetDevice(c->device));
+    int r = count_sort_reduce(c, (uint32_t)n_records);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->st));
+    *n_kmers = c->cnt.n_kmers; *dev_dict = c->dict.p;
+    return SN_OK;
+}
+void* sn_mg_dictionary_buffer(sn_ctx* c, uint64_t n_total)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    DevBuf& full = c->pool["dict_full"];
+    if (full.alloc((size_t)n_total * sizeof(DictEntry) + 64) != cudaSuccess) { c->err = "cannot allocate the gathered dictionary"; return nullptr; }
+    return full.p;
+}
+int sn_mg_install_dictionary(sn_ctx* c, uint64_t n_total)
+{
+    if (!c) return SN_ERR_ARG;
+    if (n_total >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers");
+    CU(cudaSetDevice(c->device));
+    DevBuf& full = c->pool["dict_full"];
+    if (n_total && (!full.p || full.bytes < n_total * sizeof(DictEntry))) return fail(c, SN_ERR_STATE, "call sn_mg_dictionary_buffer first");
+    CU(c->dict.alloc((size_t)n_total * sizeof(DictEntry) + 64));
+    if (n_total) CU(cudaMemcpyAsync(c->dict.p, full.p, n_total * sizeof(DictEntry), cudaMemcpyDeviceToDevice, c->st));
+    c->cnt.n_kmers = n_total;
+    return count_build_index(c);
 }
 
 // ---------------------------------------------------------------------------

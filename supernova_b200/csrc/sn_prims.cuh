@@ -163,8 +163,8 @@ inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out
 // Every pass reads each record once and writes it once.
 // ---------------------------------------------------------------------------
 #define SN_RS_ITEMS 8
-enum { RS_KEY96 = 0, RS_HASH32 = 1 };
-template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : 4; };
+enum { RS_KEY96 = 0, RS_HASH32 = 1, RS_OWNER = 2 };   // RS_OWNER: one pass, digit = owner rank (pass argument = number of ranks)
+template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : (MODE == RS_HASH32 ? 4 : 1); };
 #define SN_RS_MAX_PASSES 12
 #define SN_RS_MIN_TILE (256 * SN_RS_ITEMS)
 
@@ -173,6 +173,7 @@ template <int MODE>
 __device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
 {
     if (MODE == RS_HASH32) return (rs_hash(k) >> (8 * pass)) & 0xFFu;
+    if (MODE == RS_OWNER) return (uint32_t)(((uint64_t)rs_hash(k) * (uint32_t)pass) >> 32);
     uint32_t w = pass < 4 ? k.z : (pass < 8 ? k.y : k.x);
     return (w >> (8 * (pass & 3))) & 0xFFu;
 }
@@ -180,7 +181,7 @@ __device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
 // all digit histograms in one pass over the records (they are invariant under the
 // permutations the later passes apply).  hist[pass*256 + digit], u32 counts.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist)
+__global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist, int arg)
 {
     constexpr int P = RsMode<MODE>::PASSES;
     __shared__ uint32_t sh[P * 256];
@@ -192,6 +193,8 @@ __global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ 
             uint32_t h = rs_hash(k);
 #pragma unroll
             for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + ((h >> (8 * p)) & 0xFFu)], 1u);
+        } else if (MODE == RS_OWNER) {
+            atomicAdd(&sh[rs_digit<MODE>(k, arg)], 1u);
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + rs_digit<MODE>(k, p)], 1u);
@@ -335,7 +338,7 @@ inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, 
     if (n == 0) return cudaSuccess;
     uint32_t* hist = (uint32_t*)tmp;
     cudaMemsetAsync(hist, 0, (SN_RS_MAX_PASSES * 256 + 16) * 4, st);
-    k_rs_histogram<MODE><<<num_sms * 8, 256, 0, st>>>(a, n, hist);
+    k_rs_histogram<MODE><<<num_sms * 8, 256, 0, st>>>(a, n, hist, 0);
     k_rs_scan_hist<<<RsMode<MODE>::PASSES, 256, 0, st>>>(hist);
     return cudaGetLastError();
 }
@@ -346,7 +349,7 @@ inline int rs_threads()
     return t;
 }
 template <int MODE, int THREADS>
-inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
+inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
 {
     constexpr int TILE = THREADS * SN_RS_ITEMS;
     uint32_t nt = (n + TILE - 1) / TILE;
@@ -362,23 +365,37 @@ inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp
     uint4* src = a; uint4* dst = b;
     for (int p = 0; p < RsMode<MODE>::PASSES; ++p) {
         cudaMemsetAsync(status, 0, (size_t)nt * 256 * 8, st);
-        k_rs_scatter<MODE, THREADS><<<nt, THREADS, sizeof(RsSmem<THREADS>), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
+        k_rs_scatter<MODE, THREADS><<<nt, THREADS, sizeof(RsSmem<THREADS>), st>>>(src, dst, n, MODE == RS_OWNER ? arg : p, hist + p * 256, status, counters + p);
         uint4* t = src; src = dst; dst = t;
     }
     return cudaGetLastError();
 }
 template <int MODE>
-inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, cudaStream_t st)
+inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    return rs_threads() == 512 ? radix_sort_passes_t<MODE, 512>(a, b, n, tmp, st) : radix_sort_passes_t<MODE, 256>(a, b, n, tmp, st);
+    return rs_threads() == 512 ? radix_sort_passes_t<MODE, 512>(a, b, n, tmp, arg, st) : radix_sort_passes_t<MODE, 256>(a, b, n, tmp, arg, st);
 }
 template <int MODE>
 inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
 {
     cudaError_t e = radix_sort_histograms<MODE>(a, n, tmp, num_sms, st);
     if (e != cudaSuccess) return e;
-    return radix_sort_passes<MODE>(a, b, n, tmp, st);
+    return radix_sort_passes<MODE>(a, b, n, tmp, 0, st);
+}
+// One scatter pass that groups the records by owner rank (multi-GPU exchange); b receives the
+// records, host_starts[256] the exclusive start of every owner's range.
+inline cudaError_t radix_partition_by_owner(uint4* a, uint4* b, uint32_t n, uint32_t nparts, void* tmp, int num_sms, uint32_t* host_starts, cudaStream_t st)
+{
+    uint32_t* hist = (uint32_t*)tmp;
+    cudaMemsetAsync(hist, 0, (SN_RS_MAX_PASSES * 256 + 16) * 4, st);
+    k_rs_histogram<RS_OWNER><<<num_sms * 8, 256, 0, st>>>(a, n, hist, (int)nparts);
+    k_rs_scan_hist<<<1, 256, 0, st>>>(hist);
+    cudaError_t e = radix_sort_passes<RS_OWNER>(a, b, n, tmp, (int)nparts, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(host_starts, hist, 256 * 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
 }
 
 }  // namespace sn
