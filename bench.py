@@ -177,6 +177,8 @@ def main():
 
     # ---- inputs: synthetic reads in the reference's in-memory layout, pinned ----------------
     codes, quals, off, bc, meta = gen_workload(args.workload, rank)
+    if world > 1:
+        bc = np.where(bc > 0, bc + rank * meta["n_bc"], 0).astype(np.int32)     # barcode ordinals are global across shards
     n_bases = int(codes.size)
     gbp = n_bases / 1e9
     pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
@@ -195,12 +197,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dev = torch.device("cuda", local_rank)
+
+    def run_path(with_paths):
+        if world == 1:
+            ctx.build_read_qgraph48(None, params, with_paths=with_paths, write_files=False)
+        else:       # reads sharded over the ranks: one alltoallv of k-mer records, one allgather of dictionary slices
+            from supernova_b200 import multigpu
+            multigpu.build_distributed(ctx, dist, dev, params, with_paths=with_paths)
+
     def step_resident(with_paths=False):
-        ctx.build_read_qgraph48(None, params, with_paths=with_paths, write_files=False)
+        run_path(with_paths)
 
     def step_e2e():
         ctx.load_reads_ptr(n_reads, *ptrs)
-        ctx.build_read_qgraph48(None, params, with_paths=False, write_files=False)
+        run_path(False)
         return ctx.hbv()           # D2H/marshalling of the result the caller consumes (edges are already on the host)
 
     def timed(fn, steps):
@@ -263,7 +274,7 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {meta['pairs']} pairs x 2 x {meta['read_len']} bp per GPU, {meta['G']} bp diploid genome, seed {meta['seed']}",
                        "K": 48, "min_qual": 7, "min_freq": 3, "min_bc": 2, "gbp_per_gpu": gbp,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks, independent read shards of one genome (no exchange in this round)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks: reads sharded, k-mer records routed by hash range with one NCCL alltoallv, dictionary slices allgathered, graph replicated",
                        "l2": "inputs (%.1f GB of k-mer records per step) are larger than L2" % (16 * n_occ / 1e9)},
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}

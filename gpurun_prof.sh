@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:'k_rs_scatter|k_reduce$' -s 1 -c 3 -o gpurun_out/prof_mid3 python bench.py --workload mid --steps 1 --warmup 0 --no-cpu-baseline --no-paths > gpurun_out/ncu_full_mid3.log 2>&1
-tail -2 gpurun_out/ncu_full_mid3.log | cut -c1-200
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 1 2>&1 | tail -2 > gpurun_out/bench_n2.json; cut -c1-400 gpurun_out/bench_n2.json
