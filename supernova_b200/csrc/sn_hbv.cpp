@@ -3,6 +3,11 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
+#include <functional>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace snh {
 namespace {
@@ -66,6 +71,16 @@ inline int cmp_packed(const uint8_t* x, const uint8_t* y, uint32_t len)
         if (x[i] != y[i]) { int sh = __builtin_ctz((unsigned)(x[i] ^ y[i])) & ~1; uint32_t p = (x[i] >> sh) & 3, q = (y[i] >> sh) & 3; return p < q ? -1 : 1; }
     return 0;
 }
+// static range split over a few host threads (the per-item work here is independent)
+void parallel_ranges(uint64_t n, const std::function<void(uint64_t, uint64_t)>& fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = n < 65536 ? 1u : std::min(8u, hw ? hw : 1u);
+    if (nt <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, n * t / nt, n * (t + 1) / nt);
+    for (auto& x : th) x.join();
+}
 inline uint64_t mix(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33; return h; }
 
 }  // namespace
@@ -78,6 +93,10 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
     H.from_start.assign(1, 0); H.to_start.assign(1, 0);
     if (!nE) return;
     const uint8_t* P = E.packed.data();
+    const bool timing = getenv("SN_HBV_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](const char* what) { if (timing) { double t = now(); fprintf(stderr, "[hbv] %-10s %.2f ms\n", what, t - t0); t0 = t; } };
     // BVComp (HBVFromEdges.cc:106-111): longer first, then lexicographic on bases
     auto bvcomp = [&](uint32_t a, uint32_t b) {
         if (E.len[a] != E.len[b]) return E.len[a] > E.len[b];
@@ -94,14 +113,17 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
         auto same_prefix = [&](uint32_t a, uint32_t b) {
             return E.len[a] == E.len[b] && load64(P + E.off[a]) == load64(P + E.off[b]);
         };
+        std::vector<std::pair<uint64_t, uint64_t>> ties;
         for (uint64_t i = 0; i < nE;) {
             uint64_t j = i + 1;
             while (j < nE && same_prefix(order[i], order[j])) ++j;
-            if (j - i > 1) std::sort(order.begin() + i, order.begin() + j, bvcomp);
+            if (j - i > 1) ties.emplace_back(i, j);
             i = j;
         }
+        for (auto& t : ties) std::sort(order.begin() + t.first, order.begin() + t.second, bvcomp);
     }
     for (uint64_t i = 0; i < nE; ++i) rank[order[i]] = (uint32_t)i;
+    lap("order");
     // VertexDictBuilder (:124-168): 4 ends per edge (2 for a palindromic edge); a vertex is a
     // distinct (K-1)-mer.  item = edge<<2 | rc<<1 | distal.
     std::vector<uint8_t> pal;
@@ -147,58 +169,78 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
         }
     }
     const int32_t nV = (int32_t)gstart.size() - 1;
-    // inside a vertex: EEComp order (:113-121) = edge rank, rc, pos (pos 0 < pos len-(K-1))
-    for (int32_t g = 0; g < nV; ++g) {
-        uint32_t* it = &gitems[gstart[g]]; int n = (int)(gstart[g + 1] - gstart[g]);
-        if (n > 8) throw std::runtime_error("HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
-        for (int i = 1; i < n; ++i) {
-            uint32_t x = it[i]; uint64_t kx = ((uint64_t)rank[x >> 2] << 2) | (x & 3);
-            int j = i - 1;
-            while (j >= 0 && (((uint64_t)rank[it[j] >> 2] << 2) | (it[j] & 3)) > kx) { it[j + 1] = it[j]; --j; }
-            it[j + 1] = x;
+    lap("groups");
+    // inside a vertex: EEComp order (:113-121) = edge rank, rc, pos (pos 0 < pos len-(K-1)).
+    // One 64-byte record per vertex for the numbering loop: id, item count, items (edge<<1|rc).
+    struct alignas(64) GroupRec { int32_t vid; uint32_t n; uint32_t items[8]; uint32_t pad[6]; };
+    std::vector<GroupRec> groups(nV);
+    bool too_many = false;
+    parallel_ranges((uint64_t)nV, [&](uint64_t g0, uint64_t g1) {
+        for (uint64_t g = g0; g < g1; ++g) {
+            uint32_t* it = &gitems[gstart[g]]; int n = (int)(gstart[g + 1] - gstart[g]);
+            if (n > 8) { too_many = true; n = 8; }
+            for (int i = 1; i < n; ++i) {
+                uint32_t x = it[i]; uint64_t kx = ((uint64_t)rank[x >> 2] << 2) | (x & 3);
+                int j = i - 1;
+                while (j >= 0 && (((uint64_t)rank[it[j] >> 2] << 2) | (it[j] & 3)) > kx) { it[j + 1] = it[j]; --j; }
+                it[j + 1] = x;
+            }
+            GroupRec& r = groups[g]; r.vid = -1; r.n = (uint32_t)n;
+            for (int i = 0; i < n; ++i) r.items[i] = it[i] >> 1;
         }
-    }
+    });
+    if (too_many) throw std::runtime_error("HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
+    lap("groupsort");
     // HBVBuilder::add / processQueue (:189-228).  The loop only assigns ids; the sorted
     // adjacency lists of digraphE::AddEdge are rebuilt afterwards from to_left/to_right.
-    std::vector<int32_t> vid(nV, -1);
-    std::vector<int32_t> xlat(2 * nE, -1);             // [2*e + rc] -> HBV edge id
+    // per (edge, rc): its two vertex groups and its HBV id, one 16-byte record
+    struct ERec { int32_t g1, g2, id; uint32_t pal; };
+    std::vector<ERec> er(2 * nE);
+    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) {
+        for (uint64_t e = e0; e < e1; ++e)
+            for (uint32_t rc = 0; rc < 2; ++rc) {
+                ERec& r = er[2 * e + rc];
+                r.g1 = end_group[4 * e + 2 * rc + 0]; r.g2 = end_group[4 * e + 2 * rc + 1]; r.id = -1; r.pal = pal[e];
+            }
+    });
     H.src.resize(2 * nE); H.to_left.resize(2 * nE); H.to_right.resize(2 * nE);
     std::vector<uint32_t> Q(2 * nE + 16);
     int32_t nextV = 0; uint32_t nH = 0;
     for (uint32_t pass = 0; pass < 2; ++pass)
         for (uint64_t oi = 0; oi < nE; ++oi) {
             const uint32_t e0 = order[oi];
-            if (xlat[2 * (size_t)e0 + pass] != -1) continue;
+            if (er[2 * (size_t)e0 + pass].id != -1) continue;
             size_t qh = 0, qt = 0;
             Q[qt++] = (e0 << 1) | pass;
+            er[2 * (size_t)e0 + pass].id = -2;
+            // An item is queued at most once (id -2 = queued): the reference queues duplicates and
+            // skips them when popped, so an item is processed at its FIRST position either way.
             while (qh < qt) {
                 const uint32_t it = Q[qh++];
-                if (xlat[it] != -1) continue;
-                const uint32_t e = it >> 1, rc = it & 1;
+                ERec& r = er[it];
+                if (r.id != -2) continue;                           // palindrome twin already numbered
                 // (a palindromic edge is only ever processed with rc=0: its rev id is set with its fwd id)
-                const int32_t g1 = end_group[4 * (size_t)e + 2 * rc + 0], g2 = end_group[4 * (size_t)e + 2 * rc + 1];
-                if (g1 < 0 || g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
-                if (vid[g1] == -1) vid[g1] = nextV++;
-                if (vid[g2] == -1) vid[g2] = nextV++;
+                if (r.g1 < 0 || r.g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
+                GroupRec& G1 = groups[r.g1]; GroupRec& G2 = groups[r.g2];
+                if (G1.vid == -1) G1.vid = nextV++;
+                if (G2.vid == -1) G2.vid = nextV++;
                 const int32_t id = (int32_t)nH++;
-                H.src[id] = it; H.to_left[id] = vid[g1]; H.to_right[id] = vid[g2];
-                xlat[it] = id;
-                if (pal[e]) xlat[it ^ 1u] = id;
+                H.src[id] = it; H.to_left[id] = G1.vid; H.to_right[id] = G2.vid;
+                r.id = id;
+                if (r.pal) er[it ^ 1u].id = id;
                 if (qt + 16 > Q.size()) {                           // keep the FIFO compact
                     std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
                     if (qt + 16 > Q.size()) Q.resize(2 * Q.size());
                 }
-                for (int32_t g : {g1, g2})
-                    for (uint32_t x = gstart[g]; x < gstart[g + 1]; ++x) {
-                        const uint32_t t2 = gitems[x] >> 1;              // edge << 1 | rc
-                        if (xlat[t2] == -1) Q[qt++] = t2;
-                    }
+                for (uint32_t x = 0; x < G1.n; ++x) { const uint32_t t2 = G1.items[x]; if (er[t2].id == -1) { er[t2].id = -2; Q[qt++] = t2; } }
+                for (uint32_t x = 0; x < G2.n; ++x) { const uint32_t t2 = G2.items[x]; if (er[t2].id == -1) { er[t2].id = -2; Q[qt++] = t2; } }
             }
         }
     if (nextV != nV) throw std::runtime_error("HBV: vertex numbering did not reach every vertex");
+    lap("bfs");
     H.n_vert = nV;
     H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);
-    for (uint64_t e = 0; e < nE; ++e) { H.fwd[e] = xlat[2 * e]; H.rev[e] = xlat[2 * e + 1]; }
+    for (uint64_t e = 0; e < nE; ++e) { H.fwd[e] = er[2 * e].id; H.rev[e] = er[2 * e + 1].id; }
     // digraphE::AddEdge (graph/DigraphTemplate.h:2572-2582) inserts edge id n at upper_bound of the
     // neighbour vertex: every list ends up sorted by (neighbour, id).  Counting sort by vertex
     // (ids ascending), then order each short list by neighbour, stably.
@@ -213,22 +255,27 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
             uint32_t b = tc[H.to_right[h]]++; H.to_v[b] = H.to_left[h]; H.to_e[b] = (int32_t)h;
         }
     }
+    bool over4 = false;
     auto order_lists = [&](const std::vector<uint32_t>& start, std::vector<int32_t>& nb, std::vector<int32_t>& eo) {
-        for (int32_t v = 0; v < nV; ++v) {
+      parallel_ranges((uint64_t)nV, [&](uint64_t v0, uint64_t v1) {
+        for (uint64_t v = v0; v < v1; ++v) {
             uint32_t s = start[v], n = start[v + 1] - s;
-            if (n > 4) throw std::runtime_error("HBV: more than 4 edges on one side of a vertex");
+            if (n > 4) over4 = true;
             for (uint32_t i = 1; i < n; ++i) {                       // stable insertion sort by neighbour
                 int32_t w = nb[s + i], e = eo[s + i]; uint32_t j = i;
                 while (j > 0 && nb[s + j - 1] > w) { nb[s + j] = nb[s + j - 1]; eo[s + j] = eo[s + j - 1]; --j; }
                 nb[s + j] = w; eo[s + j] = e;
             }
         }
+      });
     };
     order_lists(H.from_start, H.from_v, H.from_e);
     order_lists(H.to_start, H.to_v, H.to_e);
+    if (over4) throw std::runtime_error("HBV: more than 4 edges on one side of a vertex");
     // Involution: the reverse complement of HBV edge fwd[e] is rev[e]
     H.inv.assign(nH, -1);
     for (uint64_t e = 0; e < nE; ++e) { H.inv[H.fwd[e]] = H.rev[e]; H.inv[H.rev[e]] = H.fwd[e]; }
+    lap("csr+inv");
 }
 
 void hbv_edge_sequences(const Edges& E, const Hbv& H, std::vector<uint8_t>& epacked, std::vector<uint64_t>& eoff, std::vector<uint32_t>& elen)

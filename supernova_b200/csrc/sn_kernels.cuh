@@ -258,7 +258,8 @@ __device__ __forceinline__ bool agg_valid(const Agg& s, uint32_t min_freq, uint3
 // scanned and k_reduce_gather compacts the stage into the dictionary.
 #define SN_RD_CHUNK 1024
 #define SN_RD_WARPS 8
-__global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
+template <int MINB>
+__global__ void __launch_bounds__(SN_RD_WARPS * 32, MINB) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
                                                              DictEntry* __restrict__ stage, uint32_t cap_per_warp, uint32_t* __restrict__ warp_count,
                                                              unsigned long long* n_distinct, uint32_t* overflow)
 {
@@ -270,10 +271,11 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
     DictEntry* out = stage + w * cap_per_warp;
     const uint4 SENT = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);   // never a canonical k-mer
     uint4 prev_last = a > 0 ? keys[a - 1] : SENT;
+    uint32_t prev_h = rs_hash(prev_last);
     bool started = false;          // an owned run has begun
     bool open = false;             // carry holds an owned, unfinished run
     Agg carry; carry.count = 0; carry.ctx_flags = 0; carry.minbc = 0xFFFFFFFFu; carry.maxbc = 0;
-    uint4 carry_key = SENT; uint64_t carry_start = 0;
+    uint4 carry_key = SENT; uint64_t carry_start = 0; uint32_t carry_h = 0;
     uint32_t cursor = 0, distinct = 0;
     // software pipeline: the records of the next two steps are already in flight
     uint4 nx1 = (a + lane < n) ? keys[a + lane] : SENT;
@@ -287,9 +289,11 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
         uint4 pv;
         pv.x = __shfl_up_sync(SN_FULL, r.x, 1); pv.y = __shfl_up_sync(SN_FULL, r.y, 1); pv.z = __shfl_up_sync(SN_FULL, r.z, 1); pv.w = 0;
         if (lane == 0) pv = prev_last;
+        const uint32_t h = rs_hash(r);                                  // one hash per record, shared by every later use
+        uint32_t ph = __shfl_up_sync(SN_FULL, h, 1);
+        if (lane == 0) ph = prev_h;
         const bool kh = !same_kmer(pv, r);                              // first record of its k-mer
-        bool hh = false;                                               // first record of its hash run
-        if (kh) hh = idx == 0 || !inb || rs_hash(pv) != rs_hash(r);
+        bool hh = kh && (idx == 0 || !inb || ph != h);                  // first record of its hash run
         if (idx > n) hh = false;                                       // only the first sentinel closes the last run
         const uint32_t hmask = __ballot_sync(SN_FULL, hh);
         // ownership window of this step: from the first owned head on (skip the tail of a
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
         const uint32_t f = fmask ? (uint32_t)__ffs(fmask) - 1u : 32u;   // lanes >= f belong to the next warp
         uint32_t first = 0;
         if (!started) { if (!hmask) { prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
+                                      prev_h = __shfl_sync(SN_FULL, h, 31);
                                       if (pos + 32 >= n + 1) break; continue; }
                         first = (uint32_t)__ffs(hmask) - 1u; }
         const bool active = lane >= first && lane < f;
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
             if (!mixed) {
                 ++distinct;
                 if (agg_valid(carry, min_freq, min_bc, has_bc)) {
-                    if (cursor < cap_per_warp) { if (lane == 0) { RunStat st; st.count = carry.count; st.ctx = carry.ctx_flags & 0xFFu; out[cursor] = make_entry(carry_key, st, rs_hash(carry_key)); } }
+                    if (cursor < cap_per_warp) { if (lane == 0) { RunStat st; st.count = carry.count; st.ctx = carry.ctx_flags & 0xFFu; out[cursor] = make_entry(carry_key, st, carry_h); } }
                     else if (lane == 0) atomicAdd(overflow, 1u);
                     ++cursor;
                 }
@@ -331,8 +336,8 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
                 uint32_t nd = 0, nvld = 0;
                 if (lane == 0) {
                     uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
-                    nvld = reduce_mixed_run(keys, carry_start, pos, rs_hash(carry_key), min_freq, min_bc, has_bc, nullptr, 0, &nd);
-                    if (nvld <= room) reduce_mixed_run(keys, carry_start, pos, rs_hash(carry_key), min_freq, min_bc, has_bc, out, cursor, nullptr);
+                    nvld = reduce_mixed_run(keys, carry_start, pos, carry_h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
+                    if (nvld <= room) reduce_mixed_run(keys, carry_start, pos, carry_h, min_freq, min_bc, has_bc, out, cursor, nullptr);
                     else atomicAdd(overflow, 1u);
                 }
                 cursor += __shfl_sync(SN_FULL, nvld, 0); distinct += __shfl_sync(SN_FULL, nd, 0);
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
             if (!mmask) {
                 if (emit_ok) {
                     uint32_t p = cursor + __popc(emask & lanemask_lt());
-                    if (p < cap_per_warp) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[p] = make_entry(r, st, rs_hash(r)); }
+                    if (p < cap_per_warp) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[p] = make_entry(r, st, h); }
                     else atomicAdd(overflow, 1u);
                 }
                 cursor += __popc(emask);
@@ -360,11 +365,11 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
                     uint32_t nvld = 0, nd = 0;
                     if (lane == l) {
                         uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
-                        if (!mixed) { nvld = 1; if (room) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[cursor] = make_entry(r, st, rs_hash(r)); } else atomicAdd(overflow, 1u); }
+                        if (!mixed) { nvld = 1; if (room) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[cursor] = make_entry(r, st, h); } else atomicAdd(overflow, 1u); }
                         else {
                             const uint64_t start = seg_start < 0 ? carry_start : pos + (uint32_t)seg_start;
-                            nvld = reduce_mixed_run(keys, start, idx + 1, rs_hash(r), min_freq, min_bc, has_bc, nullptr, 0, &nd);
-                            if (nvld <= room) reduce_mixed_run(keys, start, idx + 1, rs_hash(r), min_freq, min_bc, has_bc, out, cursor, nullptr);
+                            nvld = reduce_mixed_run(keys, start, idx + 1, h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
+                            if (nvld <= room) reduce_mixed_run(keys, start, idx + 1, h, min_freq, min_bc, has_bc, out, cursor, nullptr);
                             else atomicAdd(overflow, 1u);
                         }
                     }
@@ -382,10 +387,12 @@ __global__ void __launch_bounds__(SN_RD_WARPS * 32, 3) k_reduce(const uint4* __r
             if (last_head < 32) {
                 carry = c31; open = true;
                 carry_key.x = __shfl_sync(SN_FULL, r.x, last_head); carry_key.y = __shfl_sync(SN_FULL, r.y, last_head); carry_key.z = __shfl_sync(SN_FULL, r.z, last_head);
+                carry_h = __shfl_sync(SN_FULL, h, last_head);
                 carry_start = pos + last_head;
             } else if (had_open) carry = c31;                            // the carried run swallowed the whole step
         }
         prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
+        prev_h = __shfl_sync(SN_FULL, h, 31);
         if (pos + 32 >= (uint64_t)n + 1) break;                           // the sentinel lane has been processed
     }
     if (lane == 0) { warp_count[w] = cursor; if (distinct) atomicAdd(n_distinct, (unsigned long long)distinct); }

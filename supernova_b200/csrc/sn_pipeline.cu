@@ -328,8 +328,13 @@ static int count_sort_reduce(sn_ctx* c, uint32_t n_occ)
     DevBuf &wcount = c->pool["warp_count"], &woff = c->pool["warp_off"];
     CU(wcount.alloc(4 * n_warps)); CU(woff.alloc(8 * (n_warps + 1)));
     CU(cudaMemsetAsync(occ + 2, 0, 8, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
-    k_reduce<<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
-        c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
+    static const int rd_minb = getenv("SN_RD_MINB") ? atoi(getenv("SN_RD_MINB")) : 3;
+    if (rd_minb == 2)
+        k_reduce<2><<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
+            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
+    else
+        k_reduce<3><<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
+            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
     KCHECK("k_reduce");
     uint64_t h_n = 0;
     int r = scan_u32(c, wcount.as<uint32_t>(), n_warps, woff.as<uint64_t>(), &h_n);
