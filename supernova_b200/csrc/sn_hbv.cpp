@@ -232,8 +232,17 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
                     std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
                     if (qt + 16 > Q.size()) Q.resize(2 * Q.size());
                 }
-                for (uint32_t x = 0; x < G1.n; ++x) { const uint32_t t2 = G1.items[x]; if (er[t2].id == -1) { er[t2].id = -2; Q[qt++] = t2; } }
-                for (uint32_t x = 0; x < G2.n; ++x) { const uint32_t t2 = G2.items[x]; if (er[t2].id == -1) { er[t2].id = -2; Q[qt++] = t2; } }
+                // the loop is bound by cache misses on the vertex records: fetch them when an item is queued
+                for (uint32_t x = 0; x < G1.n; ++x) { const uint32_t t2 = G1.items[x]; ERec& q = er[t2];
+                    if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } }
+                for (uint32_t x = 0; x < G2.n; ++x) { const uint32_t t2 = G2.items[x]; ERec& q = er[t2];
+                    if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } }
+                if (qh + 4 < qt) {                                   // and the item records of what those vertices will push
+                    const ERec& nx = er[Q[qh + 4]];
+                    const GroupRec& A = groups[nx.g1]; const GroupRec& B = groups[nx.g2];
+                    for (uint32_t x = 0; x < A.n; ++x) __builtin_prefetch(&er[A.items[x]]);
+                    for (uint32_t x = 0; x < B.n; ++x) __builtin_prefetch(&er[B.items[x]]);
+                }
             }
         }
     if (nextV != nV) throw std::runtime_error("HBV: vertex numbering did not reach every vertex");

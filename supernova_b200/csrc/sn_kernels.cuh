@@ -609,29 +609,60 @@ __global__ void __launch_bounds__(256) k_hbv_assign(const uint4* __restrict__ re
 }
 
 // ---------------------------------------------------------------------------
-// a10-a13. ReadPath threading, one read per thread.  mode 0: lengths + offsets only;
-// mode 1: also the edge lists at path_off[r].  Quals come either unpacked (quals/qoff) or as
-// the PQVec stream (pq/pq_off), decoded into a per-thread buffer.
+// a10-a13. ReadPath threading, one read per thread.  k_path_reads computes every path once:
+// length and offset always, the first SN_PATH_INLINE edges into a fixed-stride scratch.  After
+// the scan of the lengths k_path_finish copies the short paths (nearly all) to their final
+// place and re-threads only the reads whose path did not fit the scratch.  Quals come either
+// unpacked (quals/qoff) or as the PQVec stream (pq/pq_off), decoded into a per-thread buffer.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_path_reads(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
-                                                    const uint32_t* __restrict__ len, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
-                                                    const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
-                                                    DictView d, EdgeStore es, HbvView h, int mode,
-                                                    uint32_t* __restrict__ plen, int32_t* __restrict__ poffset,
-                                                    const uint64_t* __restrict__ path_off, int32_t* __restrict__ pedges, uint32_t* overflow)
+#define SN_PATH_INLINE 4
+struct PathInputs {
+    uint64_t n_reads;
+    const uint8_t* bases; const uint64_t* boff; const uint32_t* len;
+    const uint8_t* quals; const uint64_t* qoff;          // unpacked quals, or
+    const uint8_t* pq; const uint64_t* pq_off;           // PQVec stream
+};
+__device__ __forceinline__ void thread_path(const PathInputs& in, uint64_t r, const DictView& d, const EdgeStore& es, const HbvView& h,
+                                            Part* parts, RPath& path, uint8_t* qbuf)
+{
+    const uint8_t* q;
+    if (in.pq) { pqvec_decode(in.pq + in.pq_off[r], in.pq + in.pq_off[r + 1], qbuf, SN_MAX_READ_LEN); q = qbuf; }
+    else q = in.quals + in.qoff[r];
+    path_one_read(d, es, h, in.bases + in.boff[r], q, in.len[r], parts, path);
+}
+__global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, EdgeStore es, HbvView h,
+                                                    uint32_t* __restrict__ plen, int32_t* __restrict__ poffset, int32_t* __restrict__ scratch, uint32_t* overflow)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
+    if (r >= in.n_reads) return;
     Part parts[SN_MAX_PARTS];
     RPath path;
     uint8_t qbuf[SN_MAX_READ_LEN];
-    const uint8_t* q;
-    if (pq) { pqvec_decode(pq + pq_off[r], pq + pq_off[r + 1], qbuf, SN_MAX_READ_LEN); q = qbuf; }
-    else q = quals + qoff[r];
-    path_one_read(d, es, h, bases + boff[r], q, len[r], parts, path);
+    thread_path(in, r, d, es, h, parts, path, qbuf);
     if (path.overflow) atomicAdd(overflow, 1u);
-    if (mode == 0) { plen[r] = path.n; poffset[r] = path.offset; }
-    else { int32_t* o = pedges + path_off[r]; for (uint32_t i = 0; i < path.n; ++i) o[i] = path.e[i]; }
+    plen[r] = path.n; poffset[r] = path.offset;
+    int4 v = make_int4(path.n > 0 ? path.e[0] : 0, path.n > 1 ? path.e[1] : 0, path.n > 2 ? path.e[2] : 0, path.n > 3 ? path.e[3] : 0);
+    reinterpret_cast<int4*>(scratch)[r] = v;
+}
+__global__ void __launch_bounds__(128) k_path_finish(PathInputs in, DictView d, EdgeStore es, HbvView h,
+                                                     const uint32_t* __restrict__ plen, const int32_t* __restrict__ scratch,
+                                                     const uint64_t* __restrict__ path_off, int32_t* __restrict__ pedges)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= in.n_reads) return;
+    uint32_t n = plen[r];
+    if (!n) return;
+    int32_t* o = pedges + path_off[r];
+    if (n <= SN_PATH_INLINE) {
+        int4 v = reinterpret_cast<const int4*>(scratch)[r];
+        o[0] = v.x; if (n > 1) o[1] = v.y; if (n > 2) o[2] = v.z; if (n > 3) o[3] = v.w;
+        return;
+    }
+    Part parts[SN_MAX_PARTS];
+    RPath path;
+    uint8_t qbuf[SN_MAX_READ_LEN];
+    thread_path(in, r, d, es, h, parts, path, qbuf);
+    for (uint32_t i = 0; i < path.n; ++i) o[i] = path.e[i];
 }
 
 }  // namespace sn

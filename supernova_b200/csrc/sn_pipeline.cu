@@ -618,27 +618,29 @@ int sn_path_reads(sn_ctx* c)
     h.from_start = c->d_from_start.as<uint32_t>(); h.from_v = c->d_from_v.as<int32_t>(); h.from_e = c->d_from_e.as<int32_t>();
     h.to_start = c->d_to_start.as<uint32_t>(); h.to_v = c->d_to_v.as<int32_t>(); h.to_e = c->d_to_e.as<int32_t>();
     CU(c->plen.alloc(4 * n)); CU(c->poffset.alloc(4 * n)); CU(c->path_off.alloc(8 * (n + 1)));
+    DevBuf& scratch = c->pool["path_scratch"];
+    CU(scratch.alloc(16 * n));
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
     CU(cudaMemsetAsync(u32c + 5, 0, 4, c->st));
     c->paths_on_host = false;
+    PathInputs in;
+    in.n_reads = n; in.bases = c->bases.as<uint8_t>(); in.boff = c->boff.as<uint64_t>(); in.len = c->len.as<uint32_t>();
+    in.quals = c->have_pq ? nullptr : c->quals.as<uint8_t>(); in.qoff = c->qoff.as<uint64_t>();
+    in.pq = c->have_pq ? c->pq.as<uint8_t>() : nullptr; in.pq_off = c->pqoff.as<uint64_t>();
     t_begin(c, "path");
     if (c->cnt.n_kmers == 0) {
         CU(cudaMemsetAsync(c->plen.p, 0, 4 * n, c->st)); CU(cudaMemsetAsync(c->poffset.p, 0, 4 * n, c->st));
     } else {
-        k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->have_pq ? nullptr : c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->have_pq ? c->pq.as<uint8_t>() : nullptr, c->pqoff.as<uint64_t>(),
-            d, es, h, 0, c->plen.as<uint32_t>(), c->poffset.as<int32_t>(), nullptr, nullptr, u32c + 5);
-        KCHECK("k_path_reads(count)");
+        k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(in, d, es, h, c->plen.as<uint32_t>(), c->poffset.as<int32_t>(), scratch.as<int32_t>(), u32c + 5);
+        KCHECK("k_path_reads");
     }
     uint64_t total = 0;
     int r = scan_u32(c, c->plen.as<uint32_t>(), n, c->path_off.as<uint64_t>(), &total);
     if (r) return r;
     CU(c->pedges.alloc(4 * total + 16));
     if (total) {
-        k_path_reads<<<blocks_for(n, 128), 128, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->have_pq ? nullptr : c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->have_pq ? c->pq.as<uint8_t>() : nullptr, c->pqoff.as<uint64_t>(),
-            d, es, h, 1, nullptr, nullptr, c->path_off.as<uint64_t>(), c->pedges.as<int32_t>(), u32c + 5);
-        KCHECK("k_path_reads(emit)");
+        k_path_finish<<<blocks_for(n, 128), 128, 0, c->st>>>(in, d, es, h, c->plen.as<uint32_t>(), scratch.as<int32_t>(), c->path_off.as<uint64_t>(), c->pedges.as<int32_t>());
+        KCHECK("k_path_finish");
     }
     t_end(c, "path");
     uint32_t h_over = 0;
