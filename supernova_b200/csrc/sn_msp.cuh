@@ -1,0 +1,449 @@
+// sn_msp.cuh -- minimizer sharding ("MSP") of the k-mer stream and the per-bucket k-mer count.
+//
+// What it replaces in the reference:
+//   * tada MSP: `simple_scan` / `compute_pvals` / `Bsp::new` (lib/tada/src/msp/mod.rs:17-134,
+//     lib/tada/src/cmd_msp.rs:129-146): reads are cut into super-k-mers, maximal runs of
+//     consecutive k-mers sharing their minimizer, and every super-k-mer goes to the shard its
+//     minimizer names.  Every occurrence of a canonical k-mer carries the same minimizer
+//     (`check_consistent_shard`, lib/tada/src/kmer/mod.rs:1102-1150), so a shard can be counted
+//     on its own (`process_kmer_shard_opt`, lib/tada/src/utils.rs:322-408).
+//   * C++ createDict: Kmerizer::map / MapReduceEngine::run / Kmerizer::reduce
+//     (paths/long/BuildReadQGraph48.cc:91-137,155-181; MapReduceEngine.h:417-584): the k-mer
+//     occurrences the super-k-mers expand to are exactly the records Kmerizer::map emits
+//     (bases [0,goodLen) only, reads with goodLen < K+1 dropped, contexts never look past
+//     goodLen-1), and a bucket is reduced with Kmerizer::reduce's rule.
+//
+// The on-device format is private (".msp ... are private and may change").
+// Differences from tada's: P = 16 (not 8) with the order of the p-mers given by a 32-bit mix of
+// the canonical p-mer instead of a frequency permutation -- 2^31 possible minimizers spread
+// evenly over up to 2^24 buckets, where 4^8 p-mers could not -- and fixed 32-byte records.
+//
+//   SkRec (32 B):  w0 = bc24 | (nk-1) << 24 | hasL << 30 | hasR << 31
+//                  w1 = bucket hash (mix of the minimizer; bucket = w1 >> (32 - bits))
+//                  w2..w7 = bases, fastb packing (base j at bits 2*(j%16) of word j/16):
+//                           [left neighbour if hasL] the nk+K-1 bases of the run [right neighbour if hasR]
+//   A run never holds more than W = K-P+1 = 33 k-mers (one p-mer position can be the minimum of
+//   at most W windows), so nk+K-1+2 <= 82 bases <= 96.
+//
+// HBM traffic: the reads are scanned twice (histogram, then scatter: 0.25 B/base each), the
+// super-k-mers are written once and read once (~0.38 B per k-mer occurrence instead of the
+// 16 B records x 4 sort passes of a key sort); the k-mers themselves only ever exist in
+// shared memory, in the per-bucket hash table of k_bucket_count.
+#pragma once
+#include "sn_kmer.cuh"
+
+namespace sn {
+
+#define SN_P 16
+#define SN_W (SN_K - SN_P + 1)          // p-mers per k-mer window
+#define SN_SK_WORDS 8
+
+// order of the p-mers: a bijective mix of the canonical 16-mer (equal value <=> equal p-mer)
+SN_HD uint32_t pmer_order(uint32_t canon)
+{
+    uint32_t m = canon * 0x9E3779B1u;
+    m ^= m >> 15; m *= 0x85EBCA77u; m ^= m >> 13;
+    return m;
+}
+// bucket hash of a minimizer: the minimum of W order values is small, so mix again
+SN_HD uint32_t bucket_hash(uint32_t minval)
+{
+    uint32_t h = minval ^ 0x5bd1e995u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// Cuts the good part [0,gl) of one read into super-k-mers.  `ring` holds the order values of
+// the last W p-mers (element i at ring[(i % W) * ring_stride]).  emit(start, nk, minval) is
+// called for every run, in read order; k-mers [start, start+nk).
+// Leftmost minimum on ties, like tada's pmin (msp/mod.rs:41-58).
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class F>
+SN_HD void msp_scan(const uint8_t* rp, uint32_t gl, uint32_t* ring, uint32_t ring_stride, F&& emit)
+{
+    if (gl < SN_K + 1) return;
+    uint32_t fwd = 0, rc = 0;
+    uint32_t curmin = 0xFFFFFFFFu, curpos = 0;       // minimum of the current window and its p-mer index
+    bool have = false;
+    uint32_t sk_start = 0, sk_pos = 0, sk_min = 0;
+    for (uint32_t j = 0; j < gl; ++j) {
+        const uint32_t b = packed_base(rp, j);
+        fwd = (fwd << 2) | b;
+        rc = (rc >> 2) | ((3u - b) << 30);
+        if (j < SN_P - 1) continue;
+        const uint32_t pidx = j - (SN_P - 1);
+        const uint32_t m = pmer_order(fwd < rc ? fwd : rc);
+        ring[(pidx % SN_W) * ring_stride] = m;
+        if (!have || m < curmin) { curmin = m; curpos = pidx; have = true; }
+        if (pidx < SN_W - 1) continue;
+        const uint32_t i = pidx - (SN_W - 1);          // k-mer whose window [i, i+W) just completed
+        if (curpos < i) {                              // the minimum left the window: rescan it
+            curmin = 0xFFFFFFFFu; have = false;
+            for (uint32_t q = i; q <= pidx; ++q) {
+                uint32_t v = ring[(q % SN_W) * ring_stride];
+                if (!have || v < curmin) { curmin = v; curpos = q; have = true; }
+            }
+        }
+        if (i == 0) { sk_start = 0; sk_pos = curpos; sk_min = curmin; }
+        else if (curpos != sk_pos || i - sk_start >= SN_W) {
+            emit(sk_start, i - sk_start, sk_min);
+            sk_start = i; sk_pos = curpos; sk_min = curmin;
+        }
+    }
+    emit(sk_start, gl - SN_K + 1 - sk_start, sk_min);
+}
+
+// Builds the record of the run [start, start+nk) of a read with good length gl.
+// `rp` may have any byte alignment; up to 28 bytes past the last needed base may be read.
+SN_HD void sk_build(const uint8_t* rp, uint32_t gl, uint32_t start, uint32_t nk, uint32_t bc24, uint32_t bhash, uint32_t* w /*8*/)
+{
+    const uint32_t hasL = start > 0 ? 1u : 0u;
+    const uint32_t hasR = start + nk + SN_K - 1 < gl ? 1u : 0u;
+    const uint32_t s0 = start - hasL, nb = nk + SN_K - 1 + hasL + hasR;
+    w[0] = bc24 | ((nk - 1) << 24) | (hasL << 30) | (hasR << 31);
+    w[1] = bhash;
+    const uint8_t* q = rp + (s0 >> 2);
+    const uint32_t sh = 2 * (s0 & 3);
+    uint32_t x[7];
+    for (int i = 0; i < 7; ++i) {
+        const uint8_t* p = q + 4 * i;
+        x[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    for (int i = 0; i < 6; ++i) {
+        uint32_t v = sh ? (x[i] >> sh) | (x[i + 1] << (32 - sh)) : x[i];
+        const uint32_t first = 16u * i;                // first base of this word
+        if (first >= nb) v = 0;
+        else if (nb - first < 16) v &= (1u << (2 * (nb - first))) - 1u;
+        w[2 + i] = v;
+    }
+}
+
+SN_HD uint32_t sk_nk(uint32_t w0) { return ((w0 >> 24) & 0x3Fu) + 1u; }
+
+// Occurrence i (0 <= i < nk) of a record: canonical k-mer + context as Kmerizer::map emits them
+// (BuildReadQGraph48.cc:155-172).  `w` = the 8 words of the record.
+SN_HD void sk_occurrence(const uint32_t* w, uint32_t i, Kmer* out, uint32_t* ctx_out)
+{
+    const uint32_t w0 = w[0];
+    const uint32_t hasL = (w0 >> 30) & 1u, hasR = w0 >> 31, nk = sk_nk(w0);
+    const uint32_t p = hasL + i;                       // first base of the k-mer
+    const uint32_t q = p >> 4, sh = 2 * (p & 15);
+    const uint32_t* b = w + 2;
+    uint32_t l0, l1, l2;
+    if (sh) { l0 = (b[q] >> sh) | (b[q + 1] << (32 - sh)); l1 = (b[q + 1] >> sh) | (b[q + 2] << (32 - sh)); l2 = (b[q + 2] >> sh) | (b[q + 3] << (32 - sh)); }
+    else { l0 = b[q]; l1 = b[q + 1]; l2 = b[q + 2]; }
+    Kmer k; k.w0 = rev2(l0); k.w1 = rev2(l1); k.w2 = rev2(l2);
+    uint32_t ctx = 0;
+    if (i > 0 || hasL) { uint32_t j = p - 1; ctx |= 16u << ((b[j >> 4] >> (2 * (j & 15))) & 3u); }
+    if (i + 1 < nk || hasR) { uint32_t j = p + SN_K; ctx |= 1u << ((b[j >> 4] >> (2 * (j & 15))) & 3u); }
+    Kmer r;
+    if (kmer_form(k, &r) == REV) { k = r; ctx = ctx_rc(ctx); }
+    *out = k; *ctx_out = ctx;
+}
+
+// number of bucket bits for n_occ k-mer occurrences: ~2048 occurrences per bucket
+inline int msp_bucket_bits(uint64_t n_occ)
+{
+    int b = 4;
+    while (b < 24 && (n_occ >> b) > 2048) ++b;
+    return b;
+}
+
+}  // namespace sn
+
+#if defined(__CUDACC__)
+#include "sn_prims.cuh"
+namespace sn {
+
+// ---------------------------------------------------------------------------
+// k_msp_scan: one read per thread; a CTA stages the packed bases of its 128 reads in shared
+// memory with 16-byte loads (as k_extract does).  EMIT = false: histogram of the super-k-mers
+// per bucket.  EMIT = true: every super-k-mer record goes straight to its place in the
+// bucket-ordered record array (bucket start + a per-bucket cursor).
+// ---------------------------------------------------------------------------
+#define SN_MS_READS 128
+#define SN_MS_BYTES (SN_MS_READS * (256 / 4) + 64)
+
+template <bool EMIT>
+__global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+                                                            const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
+                                                            int bits, uint32_t* __restrict__ counter /* hist or cursor, 2^bits */,
+                                                            const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs)
+{
+    __shared__ __align__(16) uint8_t sb[SN_MS_BYTES];
+    __shared__ uint32_t ring[SN_W * SN_MS_READS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.x * SN_MS_READS;
+    const uint32_t nr = (uint32_t)min((uint64_t)SN_MS_READS, n_reads - r0);
+    const uint64_t lo = boff[r0], hi = boff[r0 + nr];
+    const uint64_t lo_al = lo & ~15ull;
+    const uint32_t shift = (uint32_t)(lo - lo_al);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(bases + lo_al);
+        uint4* dst = reinterpret_cast<uint4*>(sb);
+        uint32_t nv = (uint32_t)((hi - lo_al + 32 + 15) >> 4);       // +32: sk_build reads ahead (the allocation is padded)
+        if (nv > SN_MS_BYTES / 16) nv = SN_MS_BYTES / 16;
+        for (uint32_t i = tid; i < nv; i += SN_MS_READS) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (tid >= nr) return;
+    const uint64_t r = r0 + tid;
+    const uint32_t gl = goodlen[r];
+    if (gl < SN_K + 1) return;
+    const uint8_t* rp = sb + (uint32_t)(boff[r] - lo) + shift;
+    uint32_t bc24 = 0xFFFFFFu;
+    if (EMIT) {
+        int32_t b = -1;
+        if (bc && (int64_t)r >= ign_bc_below) b = bc[r];
+        bc24 = b < 0 ? 0xFFFFFFu : (uint32_t)b;
+    }
+    const int sh = 32 - bits;
+    msp_scan(rp, gl, ring + tid, SN_MS_READS, [&](uint32_t start, uint32_t nk, uint32_t minval) {
+        const uint32_t bh = bucket_hash(minval);
+        const uint32_t bkt = bh >> sh;
+        if (!EMIT) atomicAdd(&counter[bkt], 1u);
+        else {
+            const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
+            uint32_t w[SN_SK_WORDS];
+            sk_build(rp, gl, start, nk, bc24, bh, w);
+            recs[2 * pos] = make_uint4(w[0], w[1], w[2], w[3]);
+            recs[2 * pos + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------
+// k_bucket_count: Kmerizer::reduce / summarizeEntries / areIgnoredBarcodes / areEnoughBarcodes
+// (BuildReadQGraph48.cc:91-137,174-181) for one bucket per CTA.  The bucket's super-k-mer
+// records are staged in shared memory by the TMA (one cp.async.bulk per chunk, completion on an
+// mbarrier), expanded to their k-mer occurrences, and aggregated in a shared-memory hash table:
+//   tag[s]  : 0 = empty, else hash | 1 of the k-mer that claimed slot s (atomicCAS)
+//   k0..k2  : the k-mer;  cnt: occurrences;  flg: ctx | ign << 8 | (>= 2 barcodes) << 9;  bc0: first barcode > 0
+// Insertion runs in two phases per batch so that no thread ever compares against a key that is
+// still being written: phase A claims or finds a slot by tag, the barrier publishes the keys,
+// phase B verifies the key (a tag collision between different k-mers sends the item back to
+// phase A one slot further) and accumulates.  The claimer initialises count/ctx/barcode with
+// plain stores, so a k-mer seen once costs one atomic; every further occurrence costs one
+// atomicAdd plus an atomicOr/CAS only while it still changes the slot.
+// If the table fills beyond 3/4 the bucket is redone in 2, 4, ... rounds, round r taking the
+// k-mers with ((hash >> 16) & (R-1)) == r.  Survivors leave as 16-byte records
+// {w0,w1,w2, count:24 | ctx << 24} appended to `out` (one global atomic per bucket and round).
+// ---------------------------------------------------------------------------
+#define SN_BC_THREADS 256
+#define SN_BC_SLOTS 2048
+#define SN_BC_CHUNK 256          // records staged per TMA copy
+#define SN_BC_ITEMS 4
+
+struct BcSmem {
+    uint4 rec[2 * SN_BC_CHUNK];                 // 8 KB staging
+    uint32_t pref[SN_BC_CHUNK + 1];
+    uint32_t tag[SN_BC_SLOTS], k0[SN_BC_SLOTS], k1[SN_BC_SLOTS], k2[SN_BC_SLOTS], cnt[SN_BC_SLOTS], flg[SN_BC_SLOTS], bc0[SN_BC_SLOTS];
+    unsigned long long mbar;
+    uint32_t fill, over, wsum[SN_BC_THREADS / 32 + 1], scan_total;
+    unsigned long long out_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SN_BC_THREADS, 3)
+k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets,
+               uint32_t min_freq, uint32_t min_bc, int has_bc,
+               uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor, unsigned long long* n_distinct, uint32_t* err)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BcSmem& S = *reinterpret_cast<BcSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t bkt = blockIdx.x;
+    if (bkt >= n_buckets) return;
+    const uint64_t r0 = bucket_off[bkt], r1 = bucket_off[bkt + 1];
+    if (r0 == r1) return;
+    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    uint32_t phase = 0;
+    uint32_t R = 1;
+    for (;;) {                                                            // retried with more rounds if the table overflows
+        bool overflowed = false;
+        for (uint32_t round = 0; round < R && !overflowed; ++round) {
+            for (uint32_t s = tid; s < SN_BC_SLOTS; s += SN_BC_THREADS) S.tag[s] = 0;
+            if (tid == 0) { S.fill = 0; S.over = 0; S.scan_total = 0; }
+            __syncthreads();
+            for (uint64_t c0 = r0; c0 < r1 && !overflowed; c0 += SN_BC_CHUNK) {
+                const uint32_t nc = (uint32_t)min((uint64_t)SN_BC_CHUNK, r1 - c0);
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the staging buffer are done (barrier above)
+                    mbar_expect_tx(&S.mbar, nc * 32u);
+                    tma_load_1d(S.rec, recs + 2 * c0, nc * 32u, &S.mbar);
+                }
+                mbar_wait(&S.mbar, phase); phase ^= 1u;
+                // exclusive prefix of the k-mers per record
+                {
+                    uint32_t v = tid < nc ? sk_nk(S.rec[2 * tid].x) : 0u, x = v;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+                    if (lane == 31) S.wsum[warp] = x;
+                    __syncthreads();
+                    uint32_t wb = 0;
+                    for (uint32_t k = 0; k < warp; ++k) wb += S.wsum[k];
+                    S.pref[tid] = wb + x - v;
+                    if (tid == SN_BC_THREADS - 1) S.pref[SN_BC_CHUNK] = wb + x;
+                    __syncthreads();
+                }
+                const uint32_t T = S.pref[SN_BC_CHUNK];
+                const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
+                for (uint32_t x0 = 0; x0 < T && !overflowed; x0 += SN_BC_THREADS * SN_BC_ITEMS) {
+                    // st: 0 = done / nothing to do, 1 = probing from slot, 2 = found by tag (verify the key in phase B)
+                    Kmer key[SN_BC_ITEMS]; uint32_t tg[SN_BC_ITEMS], slot[SN_BC_ITEMS], fl[SN_BC_ITEMS], bcv[SN_BC_ITEMS], st[SN_BC_ITEMS];
+#pragma unroll
+                    for (int j = 0; j < SN_BC_ITEMS; ++j) {
+                        const uint32_t x = x0 + j * SN_BC_THREADS + tid;
+                        st[j] = 0;
+                        if (x < T) {
+                            uint32_t a = 0, b = nc;                       // record of occurrence x: largest a with pref[a] <= x
+                            while (b - a > 1) { uint32_t m = (a + b) >> 1; if (S.pref[m] <= x) a = m; else b = m; }
+                            const uint32_t* w = recw + 8 * a;
+                            uint32_t ctx;
+                            sk_occurrence(w, x - S.pref[a], &key[j], &ctx);
+                            const uint32_t h = kmer_hash(key[j]);
+                            if (((h >> 16) & (R - 1u)) == round) {
+                                const uint32_t bv = w[0] & 0xFFFFFFu;
+                                tg[j] = h | 1u; slot[j] = h & (SN_BC_SLOTS - 1u);
+                                fl[j] = ctx | (bv == 0xFFFFFFu ? 0x100u : 0u);
+                                bcv[j] = (bv != 0xFFFFFFu) ? bv : 0u;     // barcode ordinal > 0, or 0 = none
+                                st[j] = 1;
+                            }
+                        }
+                    }
+                    for (;;) {
+                        // ---- phase A: claim an empty slot (and initialise it) or find the k-mer's slot by tag ----
+#pragma unroll
+                        for (int j = 0; j < SN_BC_ITEMS; ++j) {
+                            if (st[j] != 1) continue;
+                            uint32_t s = slot[j], probes = 0;
+                            for (;;) {
+                                uint32_t t = S.tag[s];
+                                if (t == 0u) {
+                                    t = atomicCAS(&S.tag[s], 0u, tg[j]);
+                                    if (t == 0u) {
+                                        S.k0[s] = key[j].w0; S.k1[s] = key[j].w1; S.k2[s] = key[j].w2;
+                                        S.cnt[s] = 1u; S.flg[s] = fl[j]; S.bc0[s] = bcv[j];
+                                        st[j] = 0; atomicAdd(&S.fill, 1u); break;
+                                    }
+                                }
+                                if (t == tg[j]) { st[j] = 2; break; }
+                                s = (s + 1u) & (SN_BC_SLOTS - 1u);
+                                if (++probes >= SN_BC_SLOTS) { S.over = 1u; st[j] = 0; break; }
+                            }
+                            slot[j] = s;
+                        }
+                        __syncthreads();
+                        // ---- phase B: verify the key, accumulate ----
+                        bool pending = false;
+#pragma unroll
+                        for (int j = 0; j < SN_BC_ITEMS; ++j) {
+                            if (st[j] != 2) continue;
+                            const uint32_t s = slot[j];
+                            if (S.k0[s] != key[j].w0 || S.k1[s] != key[j].w1 || S.k2[s] != key[j].w2) {
+                                st[j] = 1; slot[j] = (s + 1u) & (SN_BC_SLOTS - 1u); pending = true;      // tag collision: keep probing
+                                continue;
+                            }
+                            atomicAdd(&S.cnt[s], 1u);
+                            const uint32_t f = S.flg[s];
+                            if ((f & fl[j]) != fl[j]) atomicOr(&S.flg[s], fl[j]);
+                            if (bcv[j] != 0u && !(f & 0x200u)) {
+                                uint32_t b0 = S.bc0[s];
+                                if (b0 == 0u) b0 = atomicCAS(&S.bc0[s], 0u, bcv[j]);
+                                if (b0 != 0u && b0 != bcv[j]) atomicOr(&S.flg[s], 0x200u);
+                            }
+                            st[j] = 0;
+                        }
+                        if (!__syncthreads_or(pending ? 1 : 0)) break;
+                    }
+                    if (S.over || S.fill > (SN_BC_SLOTS * 3) / 4) overflowed = true;     // uniform: every thread reads before the barrier below
+                    __syncthreads();
+                }
+            }
+            if (overflowed) break;
+            // ---- emission: valid slots -> out ----
+            uint32_t vmask = 0, nvalid = 0, ndist = 0;
+#pragma unroll
+            for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
+                const uint32_t s = j * SN_BC_THREADS + tid;
+                if (S.tag[s] != 0u) {
+                    ++ndist;
+                    const uint32_t c = S.cnt[s], f = S.flg[s];
+                    const bool enough = min_bc == 0 || (min_bc == 1 ? S.bc0[s] != 0u : (f & 0x200u) != 0u);
+                    if (c >= min_freq && (!has_bc || (f & 0x100u) || enough)) { vmask |= 1u << j; ++nvalid; }
+                }
+            }
+            uint32_t x = nvalid, d = ndist;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(SN_FULL, d, o);
+            if (lane == 31) S.wsum[warp] = x;
+            if (lane == 0 && d) atomicAdd(&S.scan_total, d);
+            __syncthreads();
+            uint32_t wb = 0, tot = 0;
+            for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) { if (k < warp) wb += S.wsum[k]; tot += S.wsum[k]; }
+            if (tid == 0) {
+                S.out_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
+                if (S.scan_total) atomicAdd(n_distinct, (unsigned long long)S.scan_total);
+                S.scan_total = 0;
+            }
+            __syncthreads();
+            uint64_t pos = S.out_base + wb + x - nvalid;
+            if (S.out_base + tot > out_cap) { if (tid == 0) atomicOr(err, 1u); }
+            else {
+#pragma unroll
+                for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j)
+                    if (vmask & (1u << j)) {
+                        const uint32_t s = j * SN_BC_THREADS + tid;
+                        out[pos++] = make_uint4(S.k0[s], S.k1[s], S.k2[s], min(S.cnt[s], 0xFFFFFFu) | ((S.flg[s] & 0xFFu) << 24));
+                    }
+            }
+            __syncthreads();
+        }
+        if (!overflowed) break;
+        if (R >= 65536u) { if (tid == 0) atomicOr(err, 2u); break; }
+        R <<= 1;
+        __syncthreads();
+    }
+}
+
+// survivors sorted by kmer_hash (stable LSD passes) -> dictionary entries in (hash, k-mer) order:
+// inside a run of equal hash (rare) every record takes the rank of its k-mer.
+__global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = surv[i];
+    const uint32_t h = rs_hash(r);
+    uint32_t pos = i;
+    const bool tie_prev = i > 0 && rs_hash(surv[i - 1]) == h, tie_next = i + 1 < n && rs_hash(surv[i + 1]) == h;
+    if (tie_prev || tie_next) {
+        uint32_t a = i, b = i + 1;
+        while (a > 0 && rs_hash(surv[a - 1]) == h) --a;
+        while (b < n && rs_hash(surv[b]) == h) ++b;
+        uint32_t rank = 0;
+        for (uint32_t j = a; j < b; ++j) { const uint4 q = surv[j]; if (q.x != r.x ? q.x < r.x : (q.y != r.y ? q.y < r.y : q.z < r.z)) ++rank; }
+        pos = a + rank;
+    }
+    DictEntry e;
+    e.w0 = r.x; e.w1 = r.y; e.w2 = r.z; e.cc = r.w; e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = r.w >> 24; e.h = h;
+    dict[pos] = e;
+}
+
+}  // namespace sn
+#endif

@@ -5,6 +5,7 @@
 // sn_kernels.cuh; the host keeps sizes, allocations and the sequential HBV numbering.
 #include "../../include/supernova_b200.h"
 #include "sn_kernels.cuh"
+#include "sn_msp.cuh"
 #include "sn_formats.h"
 #include "sn_hbv.h"
 
@@ -263,8 +264,8 @@ static int count_set_params(sn_ctx* c, const sn_params* p)
     if (c->params.min_freq == 0) c->params.min_freq = 1;
     return SN_OK;
 }
-// a1 + a2: good lengths, then the k-mer records of this context's reads into pool["keys_a"]
-static int count_extract(sn_ctx* c, uint32_t* n_occ_out)
+// a1: good lengths and the number of k-mer occurrences Kmerizer::map will emit
+static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
 {
     const uint64_t n = c->cnt.n_reads;
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [0] occurrences, [1] cursor, [2] distinct
@@ -289,6 +290,17 @@ static int count_extract(sn_ctx* c, uint32_t* n_occ_out)
     if (h_bad) return fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count");
     c->cnt.n_kmer_occurrences = h_occ;
     if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads over more GPUs");
+    *n_occ_out = h_occ;
+    return SN_OK;
+}
+// a2 (multi-GPU record path): the k-mer records of this context's reads into pool["keys_a"]
+static int count_extract(sn_ctx* c, uint32_t* n_occ_out)
+{
+    const uint64_t n = c->cnt.n_reads;
+    unsigned long long* occ = c->counters.as<unsigned long long>();
+    uint64_t h_occ = 0;
+    int r0 = count_goodlen(c, &h_occ);
+    if (r0) return r0;
     const uint32_t n_occ = (uint32_t)h_occ;
     *n_occ_out = n_occ;
     if (!n_occ) return SN_OK;
@@ -353,6 +365,75 @@ static int count_sort_reduce(sn_ctx* c, uint32_t n_occ)
     t_end(c, "reduce");
     return SN_OK;
 }
+// a14 (MSP): cuts this context's reads into super-k-mers and groups them by minimizer bucket:
+// pool["sk_recs"] (32-byte records, bucket order) and pool["sk_off"] (2^bits + 1 record offsets).
+static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
+{
+    const uint64_t n = c->cnt.n_reads;
+    const uint64_t nb = 1ull << bits;
+    DevBuf &hist = c->pool["sk_hist"], &off = c->pool["sk_off"], &recs = c->pool["sk_recs"];
+    CU(hist.alloc(4 * nb)); CU(off.alloc(8 * (nb + 1)));
+    const int32_t* bc = c->have_bc ? c->bc.as<int32_t>() : nullptr;
+    t_begin(c, "msp_hist");
+    CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
+    k_msp_scan<false><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
+    KCHECK("k_msp_scan<hist>");
+    uint64_t n_sk = 0;
+    int r = scan_u32(c, hist.as<uint32_t>(), nb, off.as<uint64_t>(), &n_sk);
+    if (r) return r;
+    t_end(c, "msp_hist");
+    *n_sk_out = n_sk;
+    CU(recs.alloc(32 * n_sk + 64));
+    t_begin(c, "msp_scatter");
+    CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));                 // now the per-bucket cursors
+    k_msp_scan<true><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>());
+    KCHECK("k_msp_scan<scatter>");
+    t_end(c, "msp_scatter");
+    return SN_OK;
+}
+// a15 / a4 + a5: per-bucket count + filter of bucket-ordered super-k-mer records, then the surviving
+// k-mers sorted by hash into c->dict.  `occ_bound` bounds the k-mer occurrences the records hold.
+static int msp_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint64_t occ_bound)
+{
+    unsigned long long* occ = c->counters.as<unsigned long long>();        // [2] distinct, [3] survivor cursor
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [3] error flags
+    c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
+    if (!occ_bound) { CU(c->dict.alloc(64)); return SN_OK; }
+    const uint64_t cap = occ_bound / c->params.min_freq + 16;
+    if (cap >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 candidate k-mers in one context");
+    DevBuf &sa = c->pool["surv_a"], &sb = c->pool["surv_b"], &tmp = c->pool["sort_tmp"];
+    CU(sa.alloc(16 * cap));
+    static bool attr_set = false;
+    if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem))); attr_set = true; }
+    t_begin(c, "bucket_count");
+    CU(cudaMemsetAsync(occ + 2, 0, 16, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
+    k_bucket_count<<<n_buckets, SN_BC_THREADS, sizeof(BcSmem), c->st>>>(recs, off, n_buckets, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
+        sa.as<uint4>(), cap, occ + 3, occ + 2, u32c + 3);
+    KCHECK("k_bucket_count");
+    t_end(c, "bucket_count");
+    unsigned long long h[2] = {0, 0}; uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(h, occ + 2, 16, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&h_err, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_err & 1u) return fail(c, SN_ERR_DATA, "k_bucket_count: more surviving k-mers than occurrences / min_freq (internal error)");
+    if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table in 65536 rounds (pathological hash collisions)");
+    const uint64_t n_surv = h[1];
+    if (n_surv >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
+    c->cnt.n_kmers = n_surv; c->cnt.n_kmers_distinct = h[0];
+    CU(c->dict.alloc((size_t)n_surv * sizeof(DictEntry) + 64));
+    if (!n_surv) return SN_OK;
+    t_begin(c, "sort");
+    CU(sb.alloc(16 * n_surv)); CU(tmp.alloc(radix_sort_tmp_bytes((uint32_t)n_surv)));
+    cudaError_t e = radix_sort<RS_HASH32>(sa.as<uint4>(), sb.as<uint4>(), (uint32_t)n_surv, tmp.p, c->num_sms, c->st);
+    c->launches += 2 + RsMode<RS_HASH32>::PASSES;
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("survivor sort: ") + cudaGetErrorString(e));
+    k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(sa.as<uint4>(), (uint32_t)n_surv, c->dict.as<DictEntry>());
+    KCHECK("k_make_dict");
+    t_end(c, "sort");
+    return SN_OK;
+}
 static int count_build_index(sn_ctx* c)
 {
     t_begin(c, "index");
@@ -370,10 +451,12 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_count_kmers: no reads loaded");
     CU(cudaSetDevice(c->device));
-    int r; uint32_t n_occ = 0;
+    int r; uint64_t n_occ = 0, n_sk = 0;
     if ((r = count_set_params(c, p))) return r;
-    if ((r = count_extract(c, &n_occ))) return r;
-    if ((r = count_sort_reduce(c, n_occ))) return r;
+    if ((r = count_goodlen(c, &n_occ))) return r;
+    const int bits = msp_bucket_bits(n_occ);
+    if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
+    if ((r = msp_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, n_occ))) return r;
     return count_build_index(c);
 }
 

@@ -6,6 +6,7 @@
 #include "../../supernova_b200/csrc/sn_kmer.cuh"
 #include "../../supernova_b200/csrc/sn_graph.cuh"
 #include "../../supernova_b200/csrc/sn_path.cuh"
+#include "../../supernova_b200/csrc/sn_msp.cuh"
 #include "../../supernova_b200/csrc/sn_hbv.h"
 #include "../../supernova_b200/csrc/sn_formats.h"
 #include <algorithm>
@@ -43,6 +44,32 @@ uint32_t hs_extract_read(const uint8_t* packed, uint32_t goodlen, int32_t bc, ui
         out[4 * i] = k.w0; out[4 * i + 1] = k.w1; out[4 * i + 2] = k.w2;
         out[4 * i + 3] = (ctx << 24) | (bc < 0 ? 0xFFFFFFu : (uint32_t)bc);
     }
+    return n;
+}
+
+// a14 for one read, as k_msp_scan<true> + k_bucket_count's expansion apply it: the read is cut
+// into super-k-mer records (sk_out, 8 words each) and every record is expanded again into k-mer
+// records {w0,w1,w2,ctx<<24|bc24} (out) with the record's bucket hash per occurrence (bh_out).
+// Returns the number of k-mer records; *n_sk the number of super-k-mers.
+uint32_t hs_msp_read(const uint8_t* packed, uint32_t goodlen, int32_t bc, uint32_t* out, uint32_t* bh_out, uint32_t* sk_out, uint32_t* n_sk)
+{
+    uint32_t ring[SN_W];
+    uint32_t n = 0, ns = 0;
+    const uint32_t bc24 = bc < 0 ? 0xFFFFFFu : (uint32_t)bc;
+    msp_scan(packed, goodlen, ring, 1, [&](uint32_t start, uint32_t nk, uint32_t minval) {
+        uint32_t w[SN_SK_WORDS];
+        sk_build(packed, goodlen, start, nk, bc24, bucket_hash(minval), w);
+        for (int i = 0; i < SN_SK_WORDS; ++i) sk_out[SN_SK_WORDS * ns + i] = w[i];
+        ++ns;
+        for (uint32_t i = 0; i < sk_nk(w[0]); ++i) {
+            Kmer k; uint32_t ctx;
+            sk_occurrence(w, i, &k, &ctx);
+            out[4 * n] = k.w0; out[4 * n + 1] = k.w1; out[4 * n + 2] = k.w2; out[4 * n + 3] = (ctx << 24) | (w[0] & 0xFFFFFFu);
+            bh_out[n] = w[1];
+            ++n;
+        }
+    });
+    *n_sk = ns;
     return n;
 }
 

@@ -14,7 +14,7 @@ def lib():
     if _L is None:
         so = os.path.join(HERE, "libhostsim.so")
         src = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(ROOT, "supernova_b200", "csrc", f) for f in
-                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h")]
+                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so] + src[:3])
         L = C.CDLL(so)
@@ -34,6 +34,8 @@ def lib():
         L.hs_paths.argtypes = [vp, u64, vp, vp, vp, vp, vp, C.c_char_p]
         L.hs_extract_read.argtypes = [vp, C.c_uint32, C.c_int32, vp]
         L.hs_extract_read.restype = C.c_uint32
+        L.hs_msp_read.argtypes = [vp, C.c_uint32, C.c_int32, vp, vp, vp, vp]
+        L.hs_msp_read.restype = C.c_uint32
         _L = L
     return _L
 

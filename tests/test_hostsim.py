@@ -85,3 +85,36 @@ def test_extract_logic_matches_oracle_occurrences(sb):
     assert np.array_equal(key[head][valid], ok[:, :3])
     assert np.array_equal(cnt[valid], ok[:, 3])
     assert np.array_equal(ctx[valid], ok[:, 4])
+
+
+@pytest.mark.parametrize("name", ["stress1", "stress3", "tiny"])
+def test_msp_superkmers_expand_to_the_extract_records(sb, name):
+    """k_msp_scan + sk_occurrence: per read, the super-k-mer records expand to exactly the records
+    Kmerizer::map emits (same order), a run holds <= K-P+1 k-mers, and every occurrence of a
+    canonical k-mer carries the same bucket hash (tada's check_consistent_shard,
+    lib/tada/src/kmer/mod.rs:1102-1150)."""
+    from hostsim import lib
+    codes, quals, off, bc, _ = datasets.get(name)
+    gl = Oracle(codes, quals, off, bc).stage("count").good_len()
+    pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=2)
+    padded = np.concatenate([pb, np.zeros(64, np.uint8)])
+    a = np.zeros((256, 4), np.uint32); b = np.zeros((256, 4), np.uint32); bh = np.zeros(256, np.uint32)
+    sk = np.zeros((256, 8), np.uint32); nsk = np.zeros(1, np.uint32)
+    all_recs, all_bh, tot_sk = [], [], 0
+    for r in range(len(pl)):
+        p = padded.ctypes.data + int(boff[r])
+        n = lib().hs_extract_read(p, int(gl[r]), int(bc[r]), a.ctypes.data)
+        m = lib().hs_msp_read(p, int(gl[r]), int(bc[r]), b.ctypes.data, bh.ctypes.data, sk.ctypes.data, nsk.ctypes.data)
+        assert n == m
+        assert np.array_equal(a[:n], b[:n]), r
+        if n:
+            k = int(nsk[0]); tot_sk += k
+            nk = ((sk[:k, 0] >> 24) & 0x3F) + 1
+            assert nk.sum() == n and nk.max() <= 33
+            all_recs.append(b[:n, :3].copy()); all_bh.append(bh[:n].copy())
+    recs = np.concatenate(all_recs); bhs = np.concatenate(all_bh)
+    order = np.lexsort((recs[:, 2], recs[:, 1], recs[:, 0]))
+    recs, bhs = recs[order], bhs[order]
+    same = (recs[1:] == recs[:-1]).all(axis=1)
+    assert np.array_equal(bhs[1:][same], bhs[:-1][same]), "a canonical k-mer was sent to two buckets"
+    assert tot_sk * 6 < len(recs)            # super-k-mers are much fewer than k-mers (~17 k-mers each on clean reads)
