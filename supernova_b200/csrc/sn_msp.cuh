@@ -22,8 +22,7 @@
 //                  w1 = bucket hash (mix of the minimizer; bucket = w1 >> (32 - bits))
 //                  w2..w7 = bases, fastb packing (base j at bits 2*(j%16) of word j/16):
 //                           [left neighbour if hasL] the nk+K-1 bases of the run [right neighbour if hasR]
-//   A run never holds more than W = K-P+1 = 33 k-mers (one p-mer position can be the minimum of
-//   at most W windows), so nk+K-1+2 <= 82 bases <= 96.
+//   A run is cut after 47 k-mers, so nk+K-1+2 <= 96 bases always fit.
 //
 // HBM traffic: the reads are scanned twice (histogram, then scatter: 0.25 B/base each), the
 // super-k-mers are written once and read once (~0.38 B per k-mer occurrence instead of the
@@ -53,10 +52,18 @@ SN_HD uint32_t bucket_hash(uint32_t minval)
     return h;
 }
 
-// Cuts the good part [0,gl) of one read into super-k-mers.  `ring` holds the order values of
-// the last W p-mers (element i at ring[(i % W) * ring_stride]).  emit(start, nk, minval) is
-// called for every run, in read order; k-mers [start, start+nk).
-// Leftmost minimum on ties, like tada's pmin (msp/mod.rs:41-58).
+// Cuts the good part [0,gl) of one read into super-k-mers: maximal runs of consecutive k-mers
+// with the same minimizer VALUE (pmer_order is a bijection, so that is the same canonical
+// p-mer), cut after SN_SK_MAXK k-mers.  emit(start, nk, minval) is called for every run, in
+// read order; k-mers [start, start+nk).
+// The minimum over the W p-mers of each k-mer window is a sliding-window minimum computed
+// without data-dependent branches (van Herk / Gil-Werman): p-mers are taken in blocks of W; a
+// window is the suffix of one block plus the prefix of the next.  `ring` (W words, element t at
+// ring[t * ring_stride]) holds the suffix minima of the last complete block in the slots not
+// yet overwritten by the order values of the current block; when a block completes one
+// backward sweep turns it into suffix minima in place.  All threads of a warp run the same
+// iterations (thread per read), so the kernel does not diverge on the minimizer logic.
+#define SN_SK_MAXK 47
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
@@ -64,32 +71,32 @@ template <class F>
 SN_HD void msp_scan(const uint8_t* rp, uint32_t gl, uint32_t* ring, uint32_t ring_stride, F&& emit)
 {
     if (gl < SN_K + 1) return;
-    uint32_t fwd = 0, rc = 0;
-    uint32_t curmin = 0xFFFFFFFFu, curpos = 0;       // minimum of the current window and its p-mer index
-    bool have = false;
-    uint32_t sk_start = 0, sk_pos = 0, sk_min = 0;
+    uint32_t fwd = 0, rc = 0, byte = 0;
+    uint32_t r = 0;                                  // index of the current p-mer inside its block
+    uint32_t pm = 0;                                 // prefix minimum of the current block
+    uint32_t sk_start = 0, sk_min = 0;
     for (uint32_t j = 0; j < gl; ++j) {
-        const uint32_t b = packed_base(rp, j);
+        if ((j & 3u) == 0) byte = rp[j >> 2];
+        const uint32_t b = (byte >> (2 * (j & 3u))) & 3u;
         fwd = (fwd << 2) | b;
         rc = (rc >> 2) | ((3u - b) << 30);
         if (j < SN_P - 1) continue;
-        const uint32_t pidx = j - (SN_P - 1);
         const uint32_t m = pmer_order(fwd < rc ? fwd : rc);
-        ring[(pidx % SN_W) * ring_stride] = m;
-        if (!have || m < curmin) { curmin = m; curpos = pidx; have = true; }
-        if (pidx < SN_W - 1) continue;
-        const uint32_t i = pidx - (SN_W - 1);          // k-mer whose window [i, i+W) just completed
-        if (curpos < i) {                              // the minimum left the window: rescan it
-            curmin = 0xFFFFFFFFu; have = false;
-            for (uint32_t q = i; q <= pidx; ++q) {
-                uint32_t v = ring[(q % SN_W) * ring_stride];
-                if (!have || v < curmin) { curmin = v; curpos = q; have = true; }
-            }
-        }
-        if (i == 0) { sk_start = 0; sk_pos = curpos; sk_min = curmin; }
-        else if (curpos != sk_pos || i - sk_start >= SN_W) {
+        pm = (r == 0 || m < pm) ? m : pm;
+        uint32_t minval = pm;
+        if (r != SN_W - 1) { const uint32_t sfx = ring[(r + 1) * ring_stride]; minval = sfx < pm ? sfx : pm; }
+        ring[r * ring_stride] = m;
+        if (r == SN_W - 1) {                         // block complete: suffix minima in place
+            uint32_t sm = m;
+            for (int t = SN_W - 2; t >= 0; --t) { const uint32_t v = ring[t * ring_stride]; sm = v < sm ? v : sm; ring[t * ring_stride] = sm; }
+            r = 0;
+        } else ++r;
+        if (j < SN_K - 1) continue;                   // the first window completes with p-mer W-1 (base K-1)
+        const uint32_t i = j - (SN_K - 1);
+        if (i == 0) { sk_start = 0; sk_min = minval; }
+        else if (minval != sk_min || i - sk_start >= SN_SK_MAXK) {
             emit(sk_start, i - sk_start, sk_min);
-            sk_start = i; sk_pos = curpos; sk_min = curmin;
+            sk_start = i; sk_min = minval;
         }
     }
     emit(sk_start, gl - SN_K + 1 - sk_start, sk_min);
@@ -165,6 +172,7 @@ namespace sn {
 // ---------------------------------------------------------------------------
 #define SN_MS_READS 128
 #define SN_MS_BYTES (SN_MS_READS * (256 / 4) + 64)
+#define SN_MS_QUEUE 12
 
 template <bool EMIT>
 __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
 {
     __shared__ __align__(16) uint8_t sb[SN_MS_BYTES];
     __shared__ uint32_t ring[SN_W * SN_MS_READS];
+    __shared__ uint32_t qv[SN_MS_QUEUE * SN_MS_READS], qs[SN_MS_QUEUE * SN_MS_READS];
     const uint32_t tid = threadIdx.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * SN_MS_READS;
     const uint32_t nr = (uint32_t)min((uint64_t)SN_MS_READS, n_reads - r0);
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
         bc24 = b < 0 ? 0xFFFFFFu : (uint32_t)b;
     }
     const int sh = 32 - bits;
-    msp_scan(rp, gl, ring + tid, SN_MS_READS, [&](uint32_t start, uint32_t nk, uint32_t minval) {
+    auto process = [&](uint32_t start, uint32_t nk, uint32_t minval) {
         const uint32_t bh = bucket_hash(minval);
         const uint32_t bkt = bh >> sh;
         if (!EMIT) atomicAdd(&counter[bkt], 1u);
@@ -211,7 +220,15 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
             recs[2 * pos] = make_uint4(w[0], w[1], w[2], w[3]);
             recs[2 * pos + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
+    };
+    // the runs are queued while the read is scanned and handled afterwards, so that the scan loop
+    // itself stays free of divergent work (a run ends at a different base in every lane)
+    uint32_t nq = 0;
+    msp_scan(rp, gl, ring + tid, SN_MS_READS, [&](uint32_t start, uint32_t nk, uint32_t minval) {
+        if (nq < SN_MS_QUEUE) { qv[nq * SN_MS_READS + tid] = minval; qs[nq * SN_MS_READS + tid] = start | (nk << 16); ++nq; }
+        else process(start, nk, minval);
     });
+    for (uint32_t e = 0; e < nq; ++e) { const uint32_t x = qs[e * SN_MS_READS + tid]; process(x & 0xFFFFu, x >> 16, qv[e * SN_MS_READS + tid]); }
 }
 
 // ---------------------------------------------------------------------------
@@ -221,14 +238,18 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
 // mbarrier), expanded to their k-mer occurrences, and aggregated in a shared-memory hash table:
 //   tag[s]  : 0 = empty, else hash | 1 of the k-mer that claimed slot s (atomicCAS)
 //   k0..k2  : the k-mer;  cnt: occurrences;  flg: ctx | ign << 8 | (>= 2 barcodes) << 9;  bc0: first barcode > 0
+//   list[]  : the claimed slots in claim order (emission and clean-up touch only these)
+// Every thread expands a CONTIGUOUS range of the chunk's occurrences: one search for its first
+// occurrence, then the k-mer and its reverse complement are rolled base by base
+// (kmer_succ / kmer_pred) along the record.
 // Insertion runs in two phases per batch so that no thread ever compares against a key that is
 // still being written: phase A claims or finds a slot by tag, the barrier publishes the keys,
 // phase B verifies the key (a tag collision between different k-mers sends the item back to
 // phase A one slot further) and accumulates.  The claimer initialises count/ctx/barcode with
-// plain stores, so a k-mer seen once costs one atomic; every further occurrence costs one
+// plain stores, so a k-mer seen once costs one CAS; every further occurrence costs one
 // atomicAdd plus an atomicOr/CAS only while it still changes the slot.
-// If the table fills beyond 3/4 the bucket is redone in 2, 4, ... rounds, round r taking the
-// k-mers with ((hash >> 16) & (R-1)) == r.  Survivors leave as 16-byte records
+// If the table fills beyond 3/4 the pass is split in two by one more bit of the hash (see the
+// pass loop).  Survivors leave as 16-byte records
 // {w0,w1,w2, count:24 | ctx << 24} appended to `out` (one global atomic per bucket and round).
 // ---------------------------------------------------------------------------
 #define SN_BC_THREADS 256
@@ -240,8 +261,9 @@ struct BcSmem {
     uint4 rec[2 * SN_BC_CHUNK];                 // 8 KB staging
     uint32_t pref[SN_BC_CHUNK + 1];
     uint32_t tag[SN_BC_SLOTS], k0[SN_BC_SLOTS], k1[SN_BC_SLOTS], k2[SN_BC_SLOTS], cnt[SN_BC_SLOTS], flg[SN_BC_SLOTS], bc0[SN_BC_SLOTS];
+    uint16_t list[SN_BC_SLOTS];
     unsigned long long mbar;
-    uint32_t fill, over, wsum[SN_BC_THREADS / 32 + 1], scan_total;
+    uint32_t fill, over, wsum[SN_BC_THREADS / 32 + 1], ndist;
     unsigned long long out_base;
 };
 
@@ -261,11 +283,51 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// rolling expansion of one record: the k-mer at occurrence i in read orientation, its reverse
+// complement, and what is needed to step to occurrence i+1
+struct SkCursor {
+    const uint32_t* w;      // the record (8 words, shared memory)
+    uint32_t i, nk, p;      // occurrence, occurrences in the record, first base of the k-mer
+    uint32_t hasL, hasR, bcv, ign;
+    Kmer f, r;              // k-mer and reverse complement (MSB-first words)
+};
+__device__ __forceinline__ uint32_t sk_base(const uint32_t* w, uint32_t j) { return (w[2 + (j >> 4)] >> (2 * (j & 15))) & 3u; }
+__device__ __forceinline__ void skc_open(SkCursor& c, const uint32_t* w, uint32_t i)
+{
+    const uint32_t w0 = w[0];
+    c.w = w; c.i = i; c.nk = sk_nk(w0); c.hasL = (w0 >> 30) & 1u; c.hasR = w0 >> 31;
+    const uint32_t bv = w0 & 0xFFFFFFu;
+    c.ign = bv == 0xFFFFFFu ? 0x100u : 0u; c.bcv = bv == 0xFFFFFFu ? 0u : bv;
+    c.p = c.hasL + i;
+    const uint32_t q = c.p >> 4, sh = 2 * (c.p & 15);
+    const uint32_t* b = w + 2;
+    uint32_t l0 = __funnelshift_r(b[q], b[q + 1], sh), l1 = __funnelshift_r(b[q + 1], b[q + 2], sh), l2 = __funnelshift_r(b[q + 2], q + 3 < 6 ? b[q + 3] : 0u, sh);
+    c.f.w0 = rev2(l0); c.f.w1 = rev2(l1); c.f.w2 = rev2(l2);
+    c.r = kmer_rc(c.f);
+}
+// canonical k-mer + context of the current occurrence (Kmerizer::map, BuildReadQGraph48.cc:155-172)
+__device__ __forceinline__ void skc_get(const SkCursor& c, Kmer* key, uint32_t* ctx_out, uint32_t* next_base)
+{
+    uint32_t ctx = 0;
+    if (c.i > 0 || c.hasL) ctx |= 16u << sk_base(c.w, c.p - 1);
+    const uint32_t nb = sk_base(c.w, c.p + SN_K);      // always inside the 96-base field
+    if (c.i + 1 < c.nk || c.hasR) ctx |= 1u << nb;
+    *next_base = nb;
+    if (c.r < c.f) { *key = c.r; ctx = ctx_rc(ctx); } else *key = c.f;
+    *ctx_out = ctx;
+}
+__device__ __forceinline__ void skc_step(SkCursor& c, uint32_t next_base)
+{
+    c.f = kmer_succ(c.f, next_base); c.r = kmer_pred(c.r, 3u - next_base);
+    ++c.i; ++c.p;
+}
+
 __global__ void __launch_bounds__(SN_BC_THREADS, 3)
 k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets,
                uint32_t min_freq, uint32_t min_bc, int has_bc,
                uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor, unsigned long long* n_distinct, uint32_t* err)
 {
+    static_assert(SN_BC_CHUNK == SN_BC_THREADS, "one staged record per thread in the prefix scan");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BcSmem& S = *reinterpret_cast<BcSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -273,19 +335,23 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     if (bkt >= n_buckets) return;
     const uint64_t r0 = bucket_off[bkt], r1 = bucket_off[bkt + 1];
     if (r0 == r1) return;
-    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.fill = 0; S.over = 0; S.ndist = 0; }
+    for (uint32_t s = tid; s < SN_BC_SLOTS; s += SN_BC_THREADS) S.tag[s] = 0;
+    __syncthreads();
     uint32_t phase = 0;
-    uint32_t R = 1;
-    for (;;) {                                                            // retried with more rounds if the table overflows
+    const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
+    // A pass takes the k-mers with ((hash >> 16) & (2^depth - 1)) == sub.  If the table overflows
+    // the pass is abandoned and split into its two halves (depth+1: sub, sub | 2^depth); the
+    // passes are walked depth first, so every k-mer is emitted by exactly one successful pass.
+    uint32_t depth = 0, sub = 0;
+    for (;;) {
         bool overflowed = false;
-        for (uint32_t round = 0; round < R && !overflowed; ++round) {
-            for (uint32_t s = tid; s < SN_BC_SLOTS; s += SN_BC_THREADS) S.tag[s] = 0;
-            if (tid == 0) { S.fill = 0; S.over = 0; S.scan_total = 0; }
-            __syncthreads();
+        const uint32_t R = 1u << depth, round = sub;
+        {
             for (uint64_t c0 = r0; c0 < r1 && !overflowed; c0 += SN_BC_CHUNK) {
                 const uint32_t nc = (uint32_t)min((uint64_t)SN_BC_CHUNK, r1 - c0);
                 if (tid == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the staging buffer are done (barrier above)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the staging buffer finished at the last barrier
                     mbar_expect_tx(&S.mbar, nc * 32u);
                     tma_load_1d(S.rec, recs + 2 * c0, nc * 32u, &S.mbar);
                 }
@@ -297,33 +363,42 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                     if (lane == 31) S.wsum[warp] = x;
                     __syncthreads();
                     uint32_t wb = 0;
-                    for (uint32_t k = 0; k < warp; ++k) wb += S.wsum[k];
+#pragma unroll
+                    for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) wb += k < warp ? S.wsum[k] : 0u;
                     S.pref[tid] = wb + x - v;
                     if (tid == SN_BC_THREADS - 1) S.pref[SN_BC_CHUNK] = wb + x;
                     __syncthreads();
                 }
                 const uint32_t T = S.pref[SN_BC_CHUNK];
-                const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
-                for (uint32_t x0 = 0; x0 < T && !overflowed; x0 += SN_BC_THREADS * SN_BC_ITEMS) {
+                const uint32_t C = (T + SN_BC_THREADS - 1) / SN_BC_THREADS;      // consecutive occurrences per thread
+                uint32_t x = tid * C;
+                const uint32_t xe = min(x + C, T);
+                SkCursor cur; uint32_t rec_i = 0;
+                if (x < xe) {
+                    uint32_t a = 0, b = nc;                                   // record of occurrence x: largest a with pref[a] <= x
+                    while (b - a > 1) { uint32_t m = (a + b) >> 1; if (S.pref[m] <= x) a = m; else b = m; }
+                    rec_i = a;
+                    skc_open(cur, recw + 8 * a, x - S.pref[a]);
+                }
+                for (uint32_t x0 = 0; x0 < C && !overflowed; x0 += SN_BC_ITEMS) {
                     // st: 0 = done / nothing to do, 1 = probing from slot, 2 = found by tag (verify the key in phase B)
                     Kmer key[SN_BC_ITEMS]; uint32_t tg[SN_BC_ITEMS], slot[SN_BC_ITEMS], fl[SN_BC_ITEMS], bcv[SN_BC_ITEMS], st[SN_BC_ITEMS];
 #pragma unroll
                     for (int j = 0; j < SN_BC_ITEMS; ++j) {
-                        const uint32_t x = x0 + j * SN_BC_THREADS + tid;
                         st[j] = 0;
-                        if (x < T) {
-                            uint32_t a = 0, b = nc;                       // record of occurrence x: largest a with pref[a] <= x
-                            while (b - a > 1) { uint32_t m = (a + b) >> 1; if (S.pref[m] <= x) a = m; else b = m; }
-                            const uint32_t* w = recw + 8 * a;
-                            uint32_t ctx;
-                            sk_occurrence(w, x - S.pref[a], &key[j], &ctx);
+                        if (x < xe) {
+                            uint32_t ctx, nb;
+                            skc_get(cur, &key[j], &ctx, &nb);
                             const uint32_t h = kmer_hash(key[j]);
                             if (((h >> 16) & (R - 1u)) == round) {
-                                const uint32_t bv = w[0] & 0xFFFFFFu;
                                 tg[j] = h | 1u; slot[j] = h & (SN_BC_SLOTS - 1u);
-                                fl[j] = ctx | (bv == 0xFFFFFFu ? 0x100u : 0u);
-                                bcv[j] = (bv != 0xFFFFFFu) ? bv : 0u;     // barcode ordinal > 0, or 0 = none
+                                fl[j] = ctx | cur.ign; bcv[j] = cur.bcv;
                                 st[j] = 1;
+                            }
+                            ++x;
+                            if (x < xe) {
+                                if (cur.i + 1 < cur.nk) skc_step(cur, nb);
+                                else { ++rec_i; skc_open(cur, recw + 8 * rec_i, 0); }
                             }
                         }
                     }
@@ -340,7 +415,8 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                                     if (t == 0u) {
                                         S.k0[s] = key[j].w0; S.k1[s] = key[j].w1; S.k2[s] = key[j].w2;
                                         S.cnt[s] = 1u; S.flg[s] = fl[j]; S.bc0[s] = bcv[j];
-                                        st[j] = 0; atomicAdd(&S.fill, 1u); break;
+                                        S.list[atomicAdd(&S.fill, 1u)] = (uint16_t)s;
+                                        st[j] = 0; break;
                                     }
                                 }
                                 if (t == tg[j]) { st[j] = 2; break; }
@@ -376,50 +452,61 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                     __syncthreads();
                 }
             }
-            if (overflowed) break;
-            // ---- emission: valid slots -> out ----
-            uint32_t vmask = 0, nvalid = 0, ndist = 0;
+            // ---- emission: valid slots -> out; the table is cleaned through the claim list ----
+            const uint32_t nfill = S.fill;
+            uint32_t vmask = 0, nvalid = 0;
+            if (!overflowed) {
 #pragma unroll
-            for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
-                const uint32_t s = j * SN_BC_THREADS + tid;
-                if (S.tag[s] != 0u) {
-                    ++ndist;
-                    const uint32_t c = S.cnt[s], f = S.flg[s];
-                    const bool enough = min_bc == 0 || (min_bc == 1 ? S.bc0[s] != 0u : (f & 0x200u) != 0u);
-                    if (c >= min_freq && (!has_bc || (f & 0x100u) || enough)) { vmask |= 1u << j; ++nvalid; }
+                for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
+                    const uint32_t e = j * SN_BC_THREADS + tid;
+                    if (e < nfill) {
+                        const uint32_t s = S.list[e];
+                        const uint32_t c = S.cnt[s], f = S.flg[s];
+                        const bool enough = min_bc == 0 || (min_bc == 1 ? S.bc0[s] != 0u : (f & 0x200u) != 0u);
+                        if (c >= min_freq && (!has_bc || (f & 0x100u) || enough)) { vmask |= 1u << j; ++nvalid; }
+                    }
                 }
             }
-            uint32_t x = nvalid, d = ndist;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
-            for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(SN_FULL, d, o);
-            if (lane == 31) S.wsum[warp] = x;
-            if (lane == 0 && d) atomicAdd(&S.scan_total, d);
+            uint32_t xs = nvalid;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, xs, o); if (lane >= (uint32_t)o) xs += y; }
+            if (lane == 31) S.wsum[warp] = xs;
             __syncthreads();
             uint32_t wb = 0, tot = 0;
-            for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) { if (k < warp) wb += S.wsum[k]; tot += S.wsum[k]; }
+#pragma unroll
+            for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) { const uint32_t v = S.wsum[k]; wb += k < warp ? v : 0u; tot += v; }
             if (tid == 0) {
                 S.out_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
-                if (S.scan_total) atomicAdd(n_distinct, (unsigned long long)S.scan_total);
-                S.scan_total = 0;
+                if (!overflowed) S.ndist += nfill;
             }
             __syncthreads();
-            uint64_t pos = S.out_base + wb + x - nvalid;
-            if (S.out_base + tot > out_cap) { if (tid == 0) atomicOr(err, 1u); }
-            else {
+            const uint64_t obase = S.out_base;
+            const bool fits = obase + tot <= out_cap;
+            if (!fits && tid == 0) atomicOr(err, 1u);
+            uint64_t pos = obase + wb + xs - nvalid;
 #pragma unroll
-                for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j)
-                    if (vmask & (1u << j)) {
-                        const uint32_t s = j * SN_BC_THREADS + tid;
+            for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
+                const uint32_t e = j * SN_BC_THREADS + tid;
+                if (e < nfill) {
+                    const uint32_t s = S.list[e];
+                    if (fits && (vmask & (1u << j)))
                         out[pos++] = make_uint4(S.k0[s], S.k1[s], S.k2[s], min(S.cnt[s], 0xFFFFFFu) | ((S.flg[s] & 0xFFu) << 24));
-                    }
+                    S.tag[s] = 0;
+                }
             }
+            __syncthreads();
+            if (tid == 0) { S.fill = 0; S.over = 0; }
             __syncthreads();
         }
-        if (!overflowed) break;
-        if (R >= 65536u) { if (tid == 0) atomicOr(err, 2u); break; }
-        R <<= 1;
-        __syncthreads();
+        if (overflowed) {
+            if (depth >= 16u) { if (tid == 0) atomicOr(err, 2u); break; }
+            ++depth;                                                        // first half: same sub
+            continue;
+        }
+        while (depth > 0u && ((sub >> (depth - 1u)) & 1u)) { --depth; sub &= ~(1u << depth); }   // second halves done: back up
+        if (depth == 0u) break;
+        sub |= 1u << (depth - 1u);                                          // sibling half
     }
+    if (tid == 0 && S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
 }
 
 // survivors sorted by kmer_hash (stable LSD passes) -> dictionary entries in (hash, k-mer) order:

@@ -454,7 +454,8 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     int r; uint64_t n_occ = 0, n_sk = 0;
     if ((r = count_set_params(c, p))) return r;
     if ((r = count_goodlen(c, &n_occ))) return r;
-    const int bits = msp_bucket_bits(n_occ);
+    int bits = msp_bucket_bits(n_occ);
+    if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
     if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
     if ((r = msp_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, n_occ))) return r;
     return count_build_index(c);
