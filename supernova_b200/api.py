@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "extract", "partition", "sort_hist", "sort", "reduce", "index", "prune", "edges", "hbv_dev", "hbv_host", "path")
+STAGES = ("h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "extract", "partition", "sort_hist", "sort", "reduce", "index", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
 
 
 class SnError(RuntimeError):

@@ -8,6 +8,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <string>
 
 namespace snh {
 namespace {
@@ -85,7 +87,96 @@ inline uint64_t mix(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^=
 
 }  // namespace
 
-void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
+// HBVBuilder::add / processQueue (HBVFromEdges.cc:189-228) from one start item: FIFO breadth-first
+// numbering of everything reachable.  Vertices are numbered from nextV, HBV edges from nH (both
+// advanced).  An item is queued at most once (id -2 = queued): the reference queues duplicates
+// and skips them when popped, so an item is processed at its FIRST position either way.
+// (A palindromic edge is only ever processed with rc=0: its rev id is set with its fwd id.)
+static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV, uint32_t& nH,
+                     uint32_t* src, int32_t* to_left, int32_t* to_right, std::vector<uint32_t>& Q)
+{
+    size_t qh = 0, qt = 0;
+    if (Q.size() < 64) Q.resize(64);
+    Q[qt++] = start;
+    er[start].id = -2;
+    while (qh < qt) {
+        const uint32_t it = Q[qh++];
+        ERec& r = er[it];
+        if (r.id != -2) continue;                           // palindrome twin already numbered
+        if (r.g1 < 0 || r.g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
+        GroupRec& G1 = groups[r.g1]; GroupRec& G2 = groups[r.g2];
+        if (G1.vid == -1) G1.vid = nextV++;
+        if (G2.vid == -1) G2.vid = nextV++;
+        const int32_t id = (int32_t)nH++;
+        src[id] = it; to_left[id] = G1.vid; to_right[id] = G2.vid;
+        r.id = id;
+        if (r.pal) er[it ^ 1u].id = id;
+        if (qt + 16 > Q.size()) {                           // keep the FIFO compact
+            std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
+            if (qt + 16 > Q.size()) Q.resize(2 * Q.size());
+        }
+        // a vertex pushes its items once (pad[0] = expanded); the loop is bound by cache misses on the
+        // vertex and item records, so they are fetched as soon as an item is queued
+        if (!G1.pad[0]) { G1.pad[0] = 1;
+            for (uint32_t x = 0; x < G1.n; ++x) { const uint32_t t2 = G1.items[x]; ERec& q = er[t2];
+                if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } } }
+        if (!G2.pad[0]) { G2.pad[0] = 1;
+            for (uint32_t x = 0; x < G2.n; ++x) { const uint32_t t2 = G2.items[x]; ERec& q = er[t2];
+                if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } } }
+        if (qh + 4 < qt) {                                   // and the item records of what those vertices will push
+            const ERec& nx = er[Q[qh + 4]];
+            const GroupRec& A = groups[nx.g1]; const GroupRec& B = groups[nx.g2];
+            if (!A.pad[0]) for (uint32_t x = 0; x < A.n; ++x) __builtin_prefetch(&er[A.items[x]]);
+            if (!B.pad[0]) for (uint32_t x = 0; x < B.n; ++x) __builtin_prefetch(&er[B.items[x]]);
+        }
+    }
+}
+
+// The device found the connected components, the item the reference's outer loop
+// (HBVFromEdges.cc:277-285) reaches first in each, and -- from their sizes -- the first vertex and
+// edge id of every component, so the components are numbered independently, in parallel, with
+// their final ids.
+void number_hbv(const HbvComponents& C, GroupRec* groups, ERec* er, uint64_t nE, Hbv& H, unsigned threads)
+{
+    H = Hbv();
+    const uint64_t nH = C.n_comp ? C.base_e[C.n_comp] : 0, nV = C.n_comp ? C.base_v[C.n_comp] : 0;
+    H.n_vert = (int32_t)nV;
+    H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);
+    H.fwd.assign(nE, -1); H.rev.assign(nE, -1);
+    if (!threads) threads = 1;
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> bad{0};
+    std::string what;
+    auto worker = [&]() {
+        std::vector<uint32_t> Q(1024);
+        try {
+            for (;;) {
+                const uint64_t c0 = next.fetch_add(256);
+                if (c0 >= C.n_comp || bad.load()) break;
+                const uint64_t c1 = std::min<uint64_t>(C.n_comp, c0 + 256);
+                for (uint64_t c = c0; c < c1; ++c) {
+                    int32_t nextV = (int32_t)C.base_v[c]; uint32_t nh = (uint32_t)C.base_e[c];
+                    bfs_from(groups, er, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                    if ((uint64_t)nextV != C.base_v[c + 1] || (uint64_t)nh != C.base_e[c + 1])
+                        throw std::runtime_error("HBV: a component was not numbered completely");
+                }
+            }
+        } catch (const std::exception& ex) { if (!bad.exchange(1)) what = ex.what(); }
+    };
+    if (threads <= 1 || C.n_comp < 1024) worker();
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < threads; ++t) th.emplace_back(worker);
+        for (auto& x : th) x.join();
+    }
+    if (bad.load()) throw std::runtime_error(what);
+    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { H.fwd[e] = er[2 * e].id; H.rev[e] = er[2 * e + 1].id; } });
+}
+
+// Host-only construction (vertex discovery with a hash table, sequential numbering, adjacency):
+// what tests/hostsim runs on a CPU box.  The product uses the device stages of sn_hbvdev.cuh with
+// number_hbv in between.
+void build_hbv(const Edges& E, Hbv& H)
 {
     const uint64_t nE = E.n();
     H = Hbv();
@@ -93,10 +184,6 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
     H.from_start.assign(1, 0); H.to_start.assign(1, 0);
     if (!nE) return;
     const uint8_t* P = E.packed.data();
-    const bool timing = getenv("SN_HBV_TIMING") != nullptr;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t0 = now();
-    auto lap = [&](const char* what) { if (timing) { double t = now(); fprintf(stderr, "[hbv] %-10s %.2f ms\n", what, t - t0); t0 = t; } };
     // BVComp (HBVFromEdges.cc:106-111): longer first, then lexicographic on bases
     auto bvcomp = [&](uint32_t a, uint32_t b) {
         if (E.len[a] != E.len[b]) return E.len[a] > E.len[b];
@@ -104,34 +191,15 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
         return c ? c < 0 : a < b;
     };
     std::vector<uint32_t> order(nE), rank(nE);
-    if (pre.empty()) {
-        std::iota(order.begin(), order.end(), 0u);
-        std::sort(order.begin(), order.end(), bvcomp);
-    } else {
-        // device pre-order by (length desc, first 32 bases): only runs of equal prefix need the full comparison
-        order = pre.order;
-        auto same_prefix = [&](uint32_t a, uint32_t b) {
-            return E.len[a] == E.len[b] && load64(P + E.off[a]) == load64(P + E.off[b]);
-        };
-        std::vector<std::pair<uint64_t, uint64_t>> ties;
-        for (uint64_t i = 0; i < nE;) {
-            uint64_t j = i + 1;
-            while (j < nE && same_prefix(order[i], order[j])) ++j;
-            if (j - i > 1) ties.emplace_back(i, j);
-            i = j;
-        }
-        for (auto& t : ties) std::sort(order.begin() + t.first, order.begin() + t.second, bvcomp);
-    }
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), bvcomp);
     for (uint64_t i = 0; i < nE; ++i) rank[order[i]] = (uint32_t)i;
-    lap("order");
     // VertexDictBuilder (:124-168): 4 ends per edge (2 for a palindromic edge); a vertex is a
     // distinct (K-1)-mer.  item = edge<<2 | rc<<1 | distal.
-    std::vector<uint8_t> pal;
-    std::vector<int32_t> end_group;
+    std::vector<uint8_t> pal(nE);
+    std::vector<int32_t> end_group(4 * nE, -1);
     std::vector<uint32_t> gstart, gitems;
-    if (!pre.empty()) { pal = pre.pal; end_group = pre.end_group; gstart = pre.group_start; gitems = pre.group_items; }
-    else {
-        pal.resize(nE); end_group.assign(4 * nE, -1);
+    {
         uint64_t cap = 16; while (cap < 8 * nE) cap <<= 1;
         std::vector<int32_t> slot_group(cap, -1);
         std::vector<Sub> gkey; gkey.reserve(2 * nE);
@@ -169,84 +237,31 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
         }
     }
     const int32_t nV = (int32_t)gstart.size() - 1;
-    lap("groups");
-    // inside a vertex: EEComp order (:113-121) = edge rank, rc, pos (pos 0 < pos len-(K-1)).
-    // One 64-byte record per vertex for the numbering loop: id, item count, items (edge<<1|rc).
-    struct alignas(64) GroupRec { int32_t vid; uint32_t n; uint32_t items[8]; uint32_t pad[6]; };
+    // inside a vertex: EEComp order (:113-121) = edge rank, rc, pos (pos 0 < pos len-(K-1))
     std::vector<GroupRec> groups(nV);
-    bool too_many = false;
-    parallel_ranges((uint64_t)nV, [&](uint64_t g0, uint64_t g1) {
-        for (uint64_t g = g0; g < g1; ++g) {
-            uint32_t* it = &gitems[gstart[g]]; int n = (int)(gstart[g + 1] - gstart[g]);
-            if (n > 8) { too_many = true; n = 8; }
-            for (int i = 1; i < n; ++i) {
-                uint32_t x = it[i]; uint64_t kx = ((uint64_t)rank[x >> 2] << 2) | (x & 3);
-                int j = i - 1;
-                while (j >= 0 && (((uint64_t)rank[it[j] >> 2] << 2) | (it[j] & 3)) > kx) { it[j + 1] = it[j]; --j; }
-                it[j + 1] = x;
-            }
-            GroupRec& r = groups[g]; r.vid = -1; r.n = (uint32_t)n;
-            for (int i = 0; i < n; ++i) r.items[i] = it[i] >> 1;
-        }
-    });
-    if (too_many) throw std::runtime_error("HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
-    lap("groupsort");
-    // HBVBuilder::add / processQueue (:189-228).  The loop only assigns ids; the sorted
-    // adjacency lists of digraphE::AddEdge are rebuilt afterwards from to_left/to_right.
-    // per (edge, rc): its two vertex groups and its HBV id, one 16-byte record
-    struct ERec { int32_t g1, g2, id; uint32_t pal; };
+    for (int32_t g = 0; g < nV; ++g) {
+        uint32_t* it = &gitems[gstart[g]]; int n = (int)(gstart[g + 1] - gstart[g]);
+        if (n > 8) throw std::runtime_error("HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
+        std::sort(it, it + n, [&](uint32_t x, uint32_t y) { return ((((uint64_t)rank[x >> 2]) << 2) | (x & 3)) < ((((uint64_t)rank[y >> 2]) << 2) | (y & 3)); });
+        GroupRec& r = groups[g]; memset(&r, 0, sizeof r); r.vid = -1; r.n = (uint32_t)n;
+        for (int i = 0; i < n; ++i) r.items[i] = it[i] >> 1;
+    }
     std::vector<ERec> er(2 * nE);
-    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) {
-        for (uint64_t e = e0; e < e1; ++e)
-            for (uint32_t rc = 0; rc < 2; ++rc) {
-                ERec& r = er[2 * e + rc];
-                r.g1 = end_group[4 * e + 2 * rc + 0]; r.g2 = end_group[4 * e + 2 * rc + 1]; r.id = -1; r.pal = pal[e];
-            }
-    });
+    for (uint64_t e = 0; e < nE; ++e)
+        for (uint32_t rc = 0; rc < 2; ++rc) {
+            ERec& r = er[2 * e + rc];
+            r.g1 = end_group[4 * e + 2 * rc + 0]; r.g2 = end_group[4 * e + 2 * rc + 1]; r.id = -1; r.pal = pal[e];
+        }
     H.src.resize(2 * nE); H.to_left.resize(2 * nE); H.to_right.resize(2 * nE);
-    std::vector<uint32_t> Q(2 * nE + 16);
+    std::vector<uint32_t> Q(1024);
     int32_t nextV = 0; uint32_t nH = 0;
-    for (uint32_t pass = 0; pass < 2; ++pass)
+    for (uint32_t pass = 0; pass < 2; ++pass)                 // buildHBVFromEdges' outer loop (:277-285)
         for (uint64_t oi = 0; oi < nE; ++oi) {
-            const uint32_t e0 = order[oi];
-            if (er[2 * (size_t)e0 + pass].id != -1) continue;
-            size_t qh = 0, qt = 0;
-            Q[qt++] = (e0 << 1) | pass;
-            er[2 * (size_t)e0 + pass].id = -2;
-            // An item is queued at most once (id -2 = queued): the reference queues duplicates and
-            // skips them when popped, so an item is processed at its FIRST position either way.
-            while (qh < qt) {
-                const uint32_t it = Q[qh++];
-                ERec& r = er[it];
-                if (r.id != -2) continue;                           // palindrome twin already numbered
-                // (a palindromic edge is only ever processed with rc=0: its rev id is set with its fwd id)
-                if (r.g1 < 0 || r.g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
-                GroupRec& G1 = groups[r.g1]; GroupRec& G2 = groups[r.g2];
-                if (G1.vid == -1) G1.vid = nextV++;
-                if (G2.vid == -1) G2.vid = nextV++;
-                const int32_t id = (int32_t)nH++;
-                H.src[id] = it; H.to_left[id] = G1.vid; H.to_right[id] = G2.vid;
-                r.id = id;
-                if (r.pal) er[it ^ 1u].id = id;
-                if (qt + 16 > Q.size()) {                           // keep the FIFO compact
-                    std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
-                    if (qt + 16 > Q.size()) Q.resize(2 * Q.size());
-                }
-                // the loop is bound by cache misses on the vertex records: fetch them when an item is queued
-                for (uint32_t x = 0; x < G1.n; ++x) { const uint32_t t2 = G1.items[x]; ERec& q = er[t2];
-                    if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } }
-                for (uint32_t x = 0; x < G2.n; ++x) { const uint32_t t2 = G2.items[x]; ERec& q = er[t2];
-                    if (q.id == -1) { q.id = -2; Q[qt++] = t2; __builtin_prefetch(&groups[q.g1]); __builtin_prefetch(&groups[q.g2]); } }
-                if (qh + 4 < qt) {                                   // and the item records of what those vertices will push
-                    const ERec& nx = er[Q[qh + 4]];
-                    const GroupRec& A = groups[nx.g1]; const GroupRec& B = groups[nx.g2];
-                    for (uint32_t x = 0; x < A.n; ++x) __builtin_prefetch(&er[A.items[x]]);
-                    for (uint32_t x = 0; x < B.n; ++x) __builtin_prefetch(&er[B.items[x]]);
-                }
-            }
+            const uint32_t it = (order[oi] << 1) | pass;
+            if (er[it].id != -1) continue;
+            bfs_from(groups.data(), er.data(), it, nextV, nH, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
         }
     if (nextV != nV) throw std::runtime_error("HBV: vertex numbering did not reach every vertex");
-    lap("bfs");
     H.n_vert = nV;
     H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);
     for (uint64_t e = 0; e < nE; ++e) { H.fwd[e] = er[2 * e].id; H.rev[e] = er[2 * e + 1].id; }
@@ -266,8 +281,7 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
     }
     bool over4 = false;
     auto order_lists = [&](const std::vector<uint32_t>& start, std::vector<int32_t>& nb, std::vector<int32_t>& eo) {
-      parallel_ranges((uint64_t)nV, [&](uint64_t v0, uint64_t v1) {
-        for (uint64_t v = v0; v < v1; ++v) {
+        for (int32_t v = 0; v < nV; ++v) {
             uint32_t s = start[v], n = start[v + 1] - s;
             if (n > 4) over4 = true;
             for (uint32_t i = 1; i < n; ++i) {                       // stable insertion sort by neighbour
@@ -276,7 +290,6 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
                 nb[s + j] = w; eo[s + j] = e;
             }
         }
-      });
     };
     order_lists(H.from_start, H.from_v, H.from_e);
     order_lists(H.to_start, H.to_v, H.to_e);
@@ -284,7 +297,6 @@ void build_hbv(const Edges& E, const HbvPre& pre, Hbv& H)
     // Involution: the reverse complement of HBV edge fwd[e] is rev[e]
     H.inv.assign(nH, -1);
     for (uint64_t e = 0; e < nE; ++e) { H.inv[H.fwd[e]] = H.rev[e]; H.inv[H.rev[e]] = H.fwd[e]; }
-    lap("csr+inv");
 }
 
 void hbv_edge_sequences(const Edges& E, const Hbv& H, std::vector<uint8_t>& epacked, std::vector<uint64_t>& eoff, std::vector<uint32_t>& elen)

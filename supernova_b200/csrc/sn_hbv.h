@@ -1,9 +1,8 @@
 // sn_hbv.h -- HyperBasevector construction from unipath edges (host side of a8/a9).
-// Vertex discovery groups the 4E (K-1)-mer edge ends with an open-addressing hash table;
-// numbering reproduces the reference's FIFO breadth-first order
-// (paths/long/HBVFromEdges.cc:199-228), which is inherently sequential and tiny next to the
-// k-mer stream, so it runs on the host between the device edge stage and the device pathing
-// stage (DESIGN.md "HBV numbering").
+// The numbering reproduces the reference's FIFO breadth-first order
+// (paths/long/HBVFromEdges.cc:199-228); a FIFO traversal is sequential inside one connected
+// component, so it runs on the host, all components in parallel, between the device stages that
+// prepare it (vertex discovery, orders, components) and finish it (adjacency, involution).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -30,21 +29,23 @@ struct Hbv {
     std::vector<int32_t> inv;           // HyperBasevector::Involution (paths/HyperBasevector.cc:685-697)
 };
 
-// Vertex discovery precomputed on the device (k_hbv_keys / sort / k_hbv_mark): which group
-// (= distinct (K-1)-mer) each edge end belongs to, the members of every group, a
-// (length desc, first 32 bases) pre-order of the edges, and the palindrome flags.  When it is
-// empty build_hbv derives the same things on the host.
-struct HbvPre {
-    std::vector<uint32_t> order;        // edge ids sorted by (len desc, first 32 bases); ties unresolved
-    std::vector<uint8_t> pal;           // whole-edge canonical form == PALINDROME
-    std::vector<int32_t> end_group;     // [4*e + 2*rc + distal] -> group or -1
-    std::vector<uint32_t> group_start;  // n_groups+1
-    std::vector<uint32_t> group_items;  // edge<<2 | rc<<1 | distal, grouped
-    bool empty() const { return end_group.empty(); }
+// Records of the numbering loop.  GroupRec: one vertex (= distinct (K-1)-mer) with its edge ends
+// in EEComp order (items = unipath << 1 | rc), one cache line.  ERec: one oriented unipath with
+// its two vertices.  On the product path both are produced on the device (sn_hbvdev.cuh).
+struct alignas(64) GroupRec { int32_t vid; uint32_t n; uint32_t items[8]; uint32_t pad[6]; };   // pad[0]: items already pushed
+struct ERec { int32_t g1, g2, id; uint32_t pal; };
+// connected components in the order the reference's outer loop discovers them
+struct HbvComponents {
+    uint64_t n_comp = 0;
+    const uint32_t* start_item = nullptr;   // n_comp: unipath << 1 | rc
+    const uint64_t* base_v = nullptr;       // n_comp + 1: first vertex id of each component
+    const uint64_t* base_e = nullptr;       // n_comp + 1: first HBV edge id
 };
-
-void build_hbv(const Edges& edges, const HbvPre& pre, Hbv& out);
-inline void build_hbv(const Edges& edges, Hbv& out) { build_hbv(edges, HbvPre(), out); }
+// numbering (HBVBuilder::processQueue) of all components with `threads` host threads: fills
+// n_vert, src, to_left, to_right, fwd, rev
+void number_hbv(const HbvComponents& comps, GroupRec* groups, ERec* er, uint64_t n_unipaths, Hbv& out, unsigned threads);
+// host-only construction of the whole HBV (tests/hostsim)
+void build_hbv(const Edges& edges, Hbv& out);
 // sequences of the HBV edges (edges_), fastb packing: epacked (padded), eoff[n+1], elen[n]
 void hbv_edge_sequences(const Edges& edges, const Hbv& h, std::vector<uint8_t>& epacked, std::vector<uint64_t>& eoff, std::vector<uint32_t>& elen);
 

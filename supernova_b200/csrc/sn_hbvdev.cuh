@@ -1,0 +1,197 @@
+// sn_hbvdev.cuh -- device side of buildHBVFromEdges (paths/long/HBVFromEdges.cc:28-296) around
+// the one step that is sequential by definition, the FIFO numbering of HBVBuilder::processQueue
+// (:199-228):
+//   before it  k_hbv_rank      exact BVComp order (:106-111) of the edges from the device pre-order
+//              k_hbv_groups    per vertex: its edge ends in EEComp order (:113-121), one 64-byte record
+//              k_hbv_erec      per oriented edge: its two vertices
+//              k_hbv_union / k_hbv_flatten / k_hbv_compstats / k_hbv_roots / k_hbv_compgather
+//                              connected components of the graph; for each the first item the reference's
+//                              outer loop (:277-285) would reach, its vertex and edge counts -> id bases,
+//                              so the host can number all components IN PARALLEL with final ids
+//   after it   k_hbv_csr_rec + sort + k_hbv_csr_emit   the sorted adjacency lists digraphE::AddEdge
+//                              (graph/DigraphTemplate.h:2572-2582) maintains; k_hbv_inv the involution
+//                              (paths/HyperBasevector.cc:685-697)
+#pragma once
+#include "sn_prims.cuh"
+#include "sn_hbv.h"
+
+namespace sn {
+
+// lexicographic comparison of two equally long fastb-packed sequences (byte aligned)
+__device__ __forceinline__ int cmp_packed_dev(const uint8_t* x, const uint8_t* y, uint32_t len)
+{
+    const uint32_t nb = (len + 3) / 4;
+    for (uint32_t i = 0; i < nb; ++i) {
+        const uint32_t a = x[i], b = y[i];
+        if (a != b) { const int sh = (__ffs(a ^ b) - 1) & ~1; return ((a >> sh) & 3u) < ((b >> sh) & 3u) ? -1 : 1; }
+    }
+    return 0;
+}
+// ord: records {~len, first 16 bases, next 16 bases, edge} sorted by key.  Ties (same length, same
+// first 32 bases -- the two branches of a SNP bubble, for one) are ordered by the full sequence.
+__global__ void __launch_bounds__(128) k_hbv_rank(const uint4* __restrict__ ord, uint32_t n, const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff,
+                                                  const uint32_t* __restrict__ elen, uint32_t* __restrict__ order, uint32_t* __restrict__ rank)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = ord[i];
+    auto same = [&](uint32_t j) { const uint4 q = ord[j]; return q.x == r.x && q.y == r.y && q.z == r.z; };
+    uint32_t pos = i;
+    if ((i > 0 && same(i - 1)) || (i + 1 < n && same(i + 1))) {
+        uint32_t a = i, b = i + 1;
+        while (a > 0 && same(a - 1)) --a;
+        while (b < n && same(b)) ++b;
+        const uint32_t len = elen[r.w];
+        const uint8_t* mine = ebases + eoff[r.w];
+        uint32_t before = 0;
+        for (uint32_t j = a; j < b; ++j) {
+            if (j == i) continue;
+            const uint32_t e = ord[j].w;
+            const int c = cmp_packed_dev(ebases + eoff[e], mine, len);
+            if (c < 0 || (c == 0 && e < r.w)) ++before;
+        }
+        pos = a + before;
+    }
+    order[pos] = r.w; rank[r.w] = pos;
+}
+
+// items: edge<<2 | rc<<1 | distal, grouped by vertex (gstart).  EEComp order = (edge rank, rc, pos).
+__global__ void __launch_bounds__(128) k_hbv_groups(const uint32_t* __restrict__ items, const uint32_t* __restrict__ gstart, uint32_t n_groups, uint32_t n_valid,
+                                                    const uint32_t* __restrict__ rank, snh::GroupRec* __restrict__ groups, uint32_t* err)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t s = gstart[g], e = g + 1 < n_groups ? gstart[g + 1] : n_valid;
+    uint32_t n = e - s;
+    if (n > 8) { atomicOr(err, 1u); n = 8; }
+    uint32_t it[8]; unsigned long long key[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < (int)n) { it[i] = items[s + i]; key[i] = ((unsigned long long)rank[it[i] >> 2] << 2) | (it[i] & 3u); }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        if (i >= (int)n) break;
+#pragma unroll
+        for (int j = i; j > 0; --j)
+            if (key[j - 1] > key[j]) { unsigned long long tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk; uint32_t ti = it[j]; it[j] = it[j - 1]; it[j - 1] = ti; }
+    }
+    uint4* o = reinterpret_cast<uint4*>(groups + g);
+    o[0] = make_uint4(0xFFFFFFFFu /* vid = -1 */, n, n > 0 ? it[0] >> 1 : 0u, n > 1 ? it[1] >> 1 : 0u);
+    o[1] = make_uint4(n > 2 ? it[2] >> 1 : 0u, n > 3 ? it[3] >> 1 : 0u, n > 4 ? it[4] >> 1 : 0u, n > 5 ? it[5] >> 1 : 0u);
+    o[2] = make_uint4(n > 6 ? it[6] >> 1 : 0u, n > 7 ? it[7] >> 1 : 0u, 0u, 0u);
+    o[3] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void __launch_bounds__(256) k_hbv_erec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, uint32_t n_items, snh::ERec* __restrict__ er)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const uint32_t e = t >> 1, rc = t & 1u;
+    reinterpret_cast<uint4*>(er)[t] = make_uint4((uint32_t)egrp[4 * e + 2 * rc], (uint32_t)egrp[4 * e + 2 * rc + 1], 0xFFFFFFFFu, pal[e]);
+}
+
+// ---- connected components (lock-free union-find, smaller root wins) --------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x)
+{
+    for (;;) {
+        const uint32_t p = *(volatile uint32_t*)(parent + x);
+        if (p == x) return x;
+        const uint32_t gp = *(volatile uint32_t*)(parent + p);
+        if (gp != p) parent[x] = gp;                   // path halving (benign race: only ever moves towards the root)
+        x = p;
+    }
+}
+__global__ void __launch_bounds__(256) k_hbv_uf_init(uint32_t* parent, uint32_t n, unsigned long long* ckey, uint32_t* cnt_v, uint32_t* cnt_e)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    parent[g] = g; ckey[g] = ~0ull; cnt_v[g] = 0; cnt_e[g] = 0;
+}
+__global__ void __launch_bounds__(256) k_hbv_union(const snh::ERec* __restrict__ er, uint32_t n_items, uint32_t* parent)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const int32_t g1 = er[t].g1, g2 = er[t].g2;
+    if (g1 < 0 || g2 < 0) return;                     // reverse item of a palindromic edge: it is the forward item
+    uint32_t a = (uint32_t)g1, b = (uint32_t)g2;
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) break;
+        if (a < b) { const uint32_t x = a; a = b; b = x; }
+        if (atomicCAS(parent + a, a, b) == a) break;   // hang the larger root under the smaller
+    }
+}
+__global__ void __launch_bounds__(256) k_hbv_flatten(uint32_t* parent, uint32_t n, uint32_t* __restrict__ comp, uint32_t* cnt_v)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const uint32_t r = uf_find(parent, g);
+    comp[g] = r;
+    atomicAdd(cnt_v + r, 1u);
+}
+// per component: number of HBV edges, and the first item of the reference's outer loop
+// (pass 0 = forward items in edge order, pass 1 = reverse items): min of (rc, rank)
+__global__ void __launch_bounds__(256) k_hbv_compstats(const snh::ERec* __restrict__ er, uint32_t n_items, const uint32_t* __restrict__ comp,
+                                                       const uint32_t* __restrict__ rank, unsigned long long* ckey, uint32_t* cnt_e)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const int32_t g1 = er[t].g1;
+    if (g1 < 0 || er[t].g2 < 0) return;
+    const uint32_t r = comp[g1];
+    atomicMin(ckey + r, ((unsigned long long)(t & 1u) << 32) | rank[t >> 1]);
+    atomicAdd(cnt_e + r, 1u);
+}
+__global__ void __launch_bounds__(256) k_hbv_rootflag(const uint32_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ flag)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) flag[g] = comp[g] == g ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_hbv_roots(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n,
+                                                   const unsigned long long* __restrict__ ckey, uint4* __restrict__ rec)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n || !flag[g]) return;
+    const unsigned long long k = ckey[g];
+    rec[pos[g]] = make_uint4(0u, (uint32_t)(k >> 32), (uint32_t)k, g);
+}
+// rec sorted by (rc, rank): component i -> its start item (edge << 1 | rc) and sizes
+__global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __restrict__ rec, uint32_t n_comp, const uint32_t* __restrict__ order,
+                                                        const uint32_t* __restrict__ cnt_v, const uint32_t* __restrict__ cnt_e,
+                                                        uint32_t* __restrict__ start_item, uint32_t* __restrict__ cv, uint32_t* __restrict__ ce)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_comp) return;
+    const uint4 r = rec[i];
+    start_item[i] = (order[r.z] << 1) | r.y;
+    cv[i] = cnt_v[r.w]; ce[i] = cnt_e[r.w];
+}
+
+// ---- after the numbering: adjacency lists and involution ----------------------------------------
+__global__ void __launch_bounds__(256) k_hbv_csr_rec(const int32_t* __restrict__ to_left, const int32_t* __restrict__ to_right, uint32_t n_h,
+                                                     uint4* __restrict__ rec_from, uint4* __restrict__ rec_to)
+{
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_h) return;
+    const uint32_t l = (uint32_t)to_left[h], r = (uint32_t)to_right[h];
+    rec_from[h] = make_uint4(l, r, h, 0u);             // from_[l] gets (r, h), lists sorted by (neighbour, id)
+    rec_to[h] = make_uint4(r, l, h, 0u);
+}
+__global__ void __launch_bounds__(256) k_hbv_csr_emit(const uint4* __restrict__ rec, uint32_t n_h, uint32_t n_v, uint32_t* __restrict__ start,
+                                                      int32_t* __restrict__ nb, int32_t* __restrict__ eo)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_h) { const uint4 r = rec[i]; nb[i] = (int32_t)r.y; eo[i] = (int32_t)r.z; }
+    if (i <= n_v) {                                    // start[v] = first record with vertex >= v
+        uint32_t lo = 0, hi = n_h;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rec[mid].x < i) lo = mid + 1; else hi = mid; }
+        start[i] = lo;
+    }
+}
+__global__ void __launch_bounds__(256) k_hbv_inv(const int32_t* __restrict__ fwd, const int32_t* __restrict__ rev, uint32_t n_e, int32_t* __restrict__ inv)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_e) return;
+    const int32_t f = fwd[e], r = rev[e];
+    inv[f] = r; inv[r] = f;
+}
+
+}  // namespace sn

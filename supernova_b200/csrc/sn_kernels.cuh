@@ -567,7 +567,7 @@ __device__ __forceinline__ int seq_form_packed(const uint8_t* s, uint32_t len)
     return PAL;
 }
 __global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ elen,
-                                                  uint32_t n_edges, uint4* __restrict__ order_rec, uint4* __restrict__ end_rec, uint8_t* __restrict__ pal)
+                                                  uint32_t n_edges, uint4* __restrict__ order_rec, uint4* __restrict__ end_rec, uint8_t* __restrict__ pal, uint32_t* n_pal)
 {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ eb
     uint32_t len = elen[e];
     bool p = seq_form_packed(s, len) == PAL;
     pal[e] = p ? 1 : 0;
+    if (p) atomicAdd(n_pal, 1u);
     Kmer kf = kmer_from_packed(s, 0), kl = kmer_from_packed(s, len - SN_K);
     order_rec[e] = make_uint4(~len, kf.w0, kf.w1, e);
     Kmer a = kf; a.w2 &= ~3u;                          // first K-1 bases

@@ -6,6 +6,7 @@
 #include "../../include/supernova_b200.h"
 #include "sn_kernels.cuh"
 #include "sn_msp.cuh"
+#include "sn_hbvdev.cuh"
 #include "sn_formats.h"
 #include "sn_hbv.h"
 
@@ -50,6 +51,25 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// pinned host buffer, kept across steps like DevBuf
+struct HostBuf {
+    void* p = nullptr; size_t cap = 0;
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete; HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t alloc(size_t n)
+    {
+        if (!n) n = 64;
+        if (p && cap >= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n + n / 8);
+        if (e == cudaSuccess) cap = n + n / 8;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Timer { cudaEvent_t a = nullptr, b = nullptr; bool used = false; };
 
 }  // namespace
@@ -81,6 +101,7 @@ struct sn_ctx {
     std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
     DevBuf counters;     // small scratch of u64 counters
     std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
+    std::map<std::string, HostBuf> hpool;    // pinned staging, kept across steps
 };
 
 namespace {
@@ -621,68 +642,153 @@ int sn_build_hbv(sn_ctx* c)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "sn_build_hbv: run sn_build_edges first");
     CU(cudaSetDevice(c->device));
-    // a8 on the device: end keys, canonical pre-order, vertex groups
-    snh::HbvPre pre;
-    const uint32_t nE32 = (uint32_t)c->cnt.n_edges;
-    if (nE32) {
-        t_begin(c, "hbv_dev");
-        const uint32_t n4 = 4 * nE32;
-        DevBuf &ord_a = c->pool["ord_a"], &ord_b = c->pool["ord_b"], &end_a = c->pool["end_a"], &end_b = c->pool["end_b"], &tmp = c->pool["hbv_tmp"],
-               &pal = c->pool["pal"], &flag = c->pool["hflag"], &pos = c->pool["hpos"], &egrp = c->pool["egrp"], &items = c->pool["items"], &gstart = c->pool["gstart"];
-        CU(ord_a.alloc(16ull * nE32)); CU(ord_b.alloc(16ull * nE32)); CU(end_a.alloc(16ull * n4)); CU(end_b.alloc(16ull * n4));
-        CU(tmp.alloc(radix_sort_tmp_bytes(n4))); CU(pal.alloc(nE32)); CU(flag.alloc(4ull * n4)); CU(pos.alloc(8ull * (n4 + 1)));
-        CU(egrp.alloc(4ull * n4)); CU(items.alloc(4ull * n4)); CU(gstart.alloc(4ull * (n4 + 1)));
-        CU(cudaMemsetAsync(egrp.p, 0xFF, 4ull * n4, c->st));
-        k_hbv_keys<<<blocks_for(nE32, 128), 128, 0, c->st>>>(c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), c->elen.as<uint32_t>(), nE32,
-            ord_a.as<uint4>(), end_a.as<uint4>(), pal.as<uint8_t>());
-        KCHECK("k_hbv_keys");
-        cudaError_t e = radix_sort<RS_KEY96>(ord_a.as<uint4>(), ord_b.as<uint4>(), nE32, tmp.p, c->num_sms, c->st);
-        if (e == cudaSuccess) e = radix_sort<RS_KEY96>(end_a.as<uint4>(), end_b.as<uint4>(), n4, tmp.p, c->num_sms, c->st);
-        c->launches += 2 * (2 + RsMode<RS_KEY96>::PASSES);
-        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv sort: ") + cudaGetErrorString(e));
-        k_hbv_mark<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>());
-        KCHECK("k_hbv_mark");
-        uint64_t n_groups = 0;
-        int r0 = scan_u32(c, flag.as<uint32_t>(), n4, pos.as<uint64_t>(), &n_groups);
-        if (r0) return r0;
-        k_hbv_assign<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>(), pos.as<uint64_t>(),
-            egrp.as<int32_t>(), items.as<uint32_t>(), gstart.as<uint32_t>());
-        KCHECK("k_hbv_assign");
-        t_end(c, "hbv_dev");
-        pre.order.resize(nE32); pre.pal.resize(nE32); pre.end_group.resize(n4); pre.group_start.resize(n_groups + 1);
-        std::vector<uint32_t> items_h(n4);
-        CU(cudaMemcpy2DAsync(pre.order.data(), 4, (const char*)ord_a.p + 12, 16, 4, nE32, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(pre.pal.data(), pal.p, nE32, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(pre.end_group.data(), egrp.p, 4ull * n4, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(pre.group_start.data(), gstart.p, 4ull * n_groups, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(items_h.data(), items.p, 4ull * n4, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaStreamSynchronize(c->st));
-        uint64_t npal = 0; for (uint8_t p : pre.pal) npal += p;
-        const uint64_t nvalid = (uint64_t)n4 - 2 * npal;       // invalid (palindrome rc) records sort last
-        pre.group_start[n_groups] = (uint32_t)nvalid;
-        items_h.resize(nvalid);
-        pre.group_items.swap(items_h);
-    }
+    const uint32_t nE = (uint32_t)c->cnt.n_edges;
+    c->hbv = snh::Hbv();
+    c->hbv.fwd.assign(nE, -1); c->hbv.rev.assign(nE, -1);
+    c->hbv.from_start.assign(1, 0); c->hbv.to_start.assign(1, 0);
+    c->cnt.n_hbv_vertices = 0; c->cnt.n_hbv_edges = 0;
+    if (!nE) { c->stage = 4; return SN_OK; }
+    if (nE >= (1u << 29)) return fail(c, SN_ERR_ARG, "more than 2^29 unipath edges");
+    const uint32_t n4 = 4 * nE, n_items = 2 * nE;
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);        // [6] npal, [7] error flags
+    DevBuf &ord_a = c->pool["ord_a"], &ord_b = c->pool["ord_b"], &end_a = c->pool["end_a"], &end_b = c->pool["end_b"], &tmp = c->pool["hbv_tmp"],
+           &pal = c->pool["pal"], &flag = c->pool["hflag"], &pos = c->pool["hpos"], &egrp = c->pool["egrp"], &items = c->pool["items"], &gstart = c->pool["gstart"],
+           &order = c->pool["hbv_order"], &rank = c->pool["hbv_rank"], &groups = c->pool["hbv_groups"], &er = c->pool["hbv_er"],
+           &parent = c->pool["hbv_parent"], &comp = c->pool["hbv_comp"], &ckey = c->pool["hbv_ckey"], &cntv = c->pool["hbv_cntv"], &cnte = c->pool["hbv_cnte"],
+           &crec_a = c->pool["hbv_crec_a"], &crec_b = c->pool["hbv_crec_b"], &cstart = c->pool["hbv_cstart"], &cv = c->pool["hbv_cv"], &ce = c->pool["hbv_ce"],
+           &basev = c->pool["hbv_basev"], &basee = c->pool["hbv_basee"];
+    // ---- a8 on the device: end keys, exact edge order, vertex groups --------------------------------
+    t_begin(c, "hbv_dev");
+    CU(ord_a.alloc(16ull * nE)); CU(ord_b.alloc(16ull * nE)); CU(end_a.alloc(16ull * n4)); CU(end_b.alloc(16ull * n4));
+    CU(tmp.alloc(radix_sort_tmp_bytes(n4))); CU(pal.alloc(nE)); CU(flag.alloc(4ull * n4)); CU(pos.alloc(8ull * (n4 + 1)));
+    CU(egrp.alloc(4ull * n4)); CU(items.alloc(4ull * n4)); CU(gstart.alloc(4ull * (n4 + 1)));
+    CU(order.alloc(4ull * nE)); CU(rank.alloc(4ull * nE)); CU(er.alloc(16ull * n_items));
+    CU(cudaMemsetAsync(egrp.p, 0xFF, 4ull * n4, c->st));
+    CU(cudaMemsetAsync(u32c + 6, 0, 8, c->st));
+    k_hbv_keys<<<blocks_for(nE, 128), 128, 0, c->st>>>(c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), c->elen.as<uint32_t>(), nE,
+        ord_a.as<uint4>(), end_a.as<uint4>(), pal.as<uint8_t>(), u32c + 6);
+    KCHECK("k_hbv_keys");
+    cudaError_t e = radix_sort<RS_KEY96>(ord_a.as<uint4>(), ord_b.as<uint4>(), nE, tmp.p, c->num_sms, c->st);
+    if (e == cudaSuccess) e = radix_sort<RS_KEY96>(end_a.as<uint4>(), end_b.as<uint4>(), n4, tmp.p, c->num_sms, c->st);
+    c->launches += 2 * (2 + RsMode<RS_KEY96>::PASSES);
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv sort: ") + cudaGetErrorString(e));
+    k_hbv_rank<<<blocks_for(nE, 128), 128, 0, c->st>>>(ord_a.as<uint4>(), nE, c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), c->elen.as<uint32_t>(),
+        order.as<uint32_t>(), rank.as<uint32_t>());
+    KCHECK("k_hbv_rank");
+    k_hbv_mark<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>());
+    KCHECK("k_hbv_mark");
+    uint64_t n_groups = 0;
+    int r0 = scan_u32(c, flag.as<uint32_t>(), n4, pos.as<uint64_t>(), &n_groups);
+    if (r0) return r0;
+    uint32_t h_npal = 0;
+    CU(cudaMemcpy(&h_npal, u32c + 6, 4, cudaMemcpyDeviceToHost));
+    const uint32_t n_valid = n4 - 2 * h_npal;                  // the invalid (palindrome rc) end records sort last
+    const uint32_t nV = (uint32_t)n_groups;
+    k_hbv_assign<<<blocks_for(n4, 256), 256, 0, c->st>>>(end_a.as<uint4>(), n4, flag.as<uint32_t>(), pos.as<uint64_t>(),
+        egrp.as<int32_t>(), items.as<uint32_t>(), gstart.as<uint32_t>());
+    KCHECK("k_hbv_assign");
+    CU(groups.alloc(64ull * nV));
+    k_hbv_groups<<<blocks_for(nV, 128), 128, 0, c->st>>>(items.as<uint32_t>(), gstart.as<uint32_t>(), nV, n_valid, rank.as<uint32_t>(),
+        groups.as<snh::GroupRec>(), u32c + 7);
+    KCHECK("k_hbv_groups");
+    k_hbv_erec<<<blocks_for(n_items, 256), 256, 0, c->st>>>(egrp.as<int32_t>(), pal.as<uint8_t>(), n_items, er.as<snh::ERec>());
+    KCHECK("k_hbv_erec");
+    // the numbering loop's records travel to pinned host memory while the components are analysed
+    HostBuf &h_groups = c->hpool["hbv_groups"], &h_er = c->hpool["hbv_er"], &h_comp = c->hpool["hbv_comp"];
+    CU(h_groups.alloc(64ull * nV)); CU(h_er.alloc(16ull * n_items));
+    CU(cudaMemcpyAsync(h_groups.p, groups.p, 64ull * nV, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(h_er.p, er.p, 16ull * n_items, cudaMemcpyDeviceToHost, c->st));
+    // ---- connected components, their discovery order and id bases ----------------------------------------
+    CU(parent.alloc(4ull * nV)); CU(comp.alloc(4ull * nV)); CU(ckey.alloc(8ull * nV)); CU(cntv.alloc(4ull * nV)); CU(cnte.alloc(4ull * nV));
+    k_hbv_uf_init<<<blocks_for(nV, 256), 256, 0, c->st>>>(parent.as<uint32_t>(), nV, ckey.as<unsigned long long>(), cntv.as<uint32_t>(), cnte.as<uint32_t>());
+    KCHECK("k_hbv_uf_init");
+    k_hbv_union<<<blocks_for(n_items, 256), 256, 0, c->st>>>(er.as<snh::ERec>(), n_items, parent.as<uint32_t>());
+    KCHECK("k_hbv_union");
+    k_hbv_flatten<<<blocks_for(nV, 256), 256, 0, c->st>>>(parent.as<uint32_t>(), nV, comp.as<uint32_t>(), cntv.as<uint32_t>());
+    KCHECK("k_hbv_flatten");
+    k_hbv_compstats<<<blocks_for(n_items, 256), 256, 0, c->st>>>(er.as<snh::ERec>(), n_items, comp.as<uint32_t>(), rank.as<uint32_t>(),
+        ckey.as<unsigned long long>(), cnte.as<uint32_t>());
+    KCHECK("k_hbv_compstats");
+    k_hbv_rootflag<<<blocks_for(nV, 256), 256, 0, c->st>>>(comp.as<uint32_t>(), nV, flag.as<uint32_t>());
+    KCHECK("k_hbv_rootflag");
+    uint64_t n_comp = 0;
+    if ((r0 = scan_u32(c, flag.as<uint32_t>(), nV, pos.as<uint64_t>(), &n_comp))) return r0;
+    CU(crec_a.alloc(16 * n_comp + 16)); CU(crec_b.alloc(16 * n_comp + 16)); CU(cstart.alloc(4 * n_comp + 16)); CU(cv.alloc(4 * n_comp + 16)); CU(ce.alloc(4 * n_comp + 16));
+    CU(basev.alloc(8 * (n_comp + 1))); CU(basee.alloc(8 * (n_comp + 1)));
+    k_hbv_roots<<<blocks_for(nV, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), nV, ckey.as<unsigned long long>(), crec_a.as<uint4>());
+    KCHECK("k_hbv_roots");
+    e = radix_sort<RS_KEY96>(crec_a.as<uint4>(), crec_b.as<uint4>(), (uint32_t)n_comp, tmp.p, c->num_sms, c->st);
+    c->launches += 2 + RsMode<RS_KEY96>::PASSES;
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv component sort: ") + cudaGetErrorString(e));
+    k_hbv_compgather<<<blocks_for(n_comp, 256), 256, 0, c->st>>>(crec_a.as<uint4>(), (uint32_t)n_comp, order.as<uint32_t>(), cntv.as<uint32_t>(), cnte.as<uint32_t>(),
+        cstart.as<uint32_t>(), cv.as<uint32_t>(), ce.as<uint32_t>());
+    KCHECK("k_hbv_compgather");
+    uint64_t tot_v = 0, tot_h = 0;
+    if ((r0 = scan_u32(c, cv.as<uint32_t>(), n_comp, basev.as<uint64_t>(), &tot_v))) return r0;
+    if ((r0 = scan_u32(c, ce.as<uint32_t>(), n_comp, basee.as<uint64_t>(), &tot_h))) return r0;
+    t_end(c, "hbv_dev");
+    CU(h_comp.alloc(4 * n_comp + 16 * (n_comp + 1) + 64));
+    uint64_t* h_basev = h_comp.as<uint64_t>(); uint64_t* h_basee = h_basev + (n_comp + 1); uint32_t* h_cstart = reinterpret_cast<uint32_t*>(h_basee + (n_comp + 1));
+    CU(cudaMemcpyAsync(h_basev, basev.p, 8 * (n_comp + 1), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(h_basee, basee.p, 8 * (n_comp + 1), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(h_cstart, cstart.p, 4 * n_comp, cudaMemcpyDeviceToHost, c->st));
+    uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(&h_err, u32c + 7, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_err) return fail(c, SN_ERR_DATA, "HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
+    if (tot_v != nV) return fail(c, SN_ERR_DATA, "HBV: component vertex counts do not add up");
+    // ---- the FIFO numbering, all components in parallel on the host ----------------------------------
     auto t0 = std::chrono::steady_clock::now();
-    try { snh::build_hbv(c->hedges, pre, c->hbv); }
+    snh::HbvComponents comps; comps.n_comp = n_comp; comps.start_item = h_cstart; comps.base_v = h_basev; comps.base_e = h_basee;
+    static const unsigned hbv_threads = [] { const char* e = getenv("SN_HBV_THREADS"); unsigned n = e ? (unsigned)atoi(e) : std::min(32u, std::thread::hardware_concurrency()); return n ? n : 1u; }();
+    try { snh::number_hbv(comps, h_groups.as<snh::GroupRec>(), h_er.as<snh::ERec>(), nE, c->hbv, hbv_threads); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    const snh::Hbv& H = c->hbv;
-    const size_t nV = (size_t)H.n_vert, nH = H.src.size(), nE = H.fwd.size();
+    snh::Hbv& H = c->hbv;
+    const size_t nH = H.src.size();
     c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
+    // ---- adjacency lists and involution on the device; the graph stays there for the pathing stage ----
+    t_begin(c, "hbv_csr");
     int r;
-    if ((r = upload(c, c->d_fwd, H.fwd.data(), 4 * nE, 16))) return r;
-    if ((r = upload(c, c->d_rev, H.rev.data(), 4 * nE, 16))) return r;
+    if ((r = upload(c, c->d_fwd, H.fwd.data(), 4ull * nE, 16))) return r;
+    if ((r = upload(c, c->d_rev, H.rev.data(), 4ull * nE, 16))) return r;
     if ((r = upload(c, c->d_toleft, H.to_left.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_toright, H.to_right.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_src, H.src.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_from_start, H.from_start.data(), 4 * (nV + 1), 16))) return r;
-    if ((r = upload(c, c->d_to_start, H.to_start.data(), 4 * (nV + 1), 16))) return r;
-    if ((r = upload(c, c->d_from_v, H.from_v.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_from_e, H.from_e.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_to_v, H.to_v.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_to_e, H.to_e.data(), 4 * nH, 16))) return r;
+    CU(c->d_from_start.alloc(4ull * (nV + 1) + 16)); CU(c->d_to_start.alloc(4ull * (nV + 1) + 16));
+    CU(c->d_from_v.alloc(4 * nH + 16)); CU(c->d_from_e.alloc(4 * nH + 16)); CU(c->d_to_v.alloc(4 * nH + 16)); CU(c->d_to_e.alloc(4 * nH + 16));
+    DevBuf &ra = c->pool["hbv_csr_a"], &rb = c->pool["hbv_csr_b"], &rs = c->pool["hbv_csr_s"], &dinv = c->pool["hbv_inv"];
+    CU(ra.alloc(16 * nH + 16)); CU(rb.alloc(16 * nH + 16)); CU(rs.alloc(16 * nH + 16)); CU(dinv.alloc(4 * nH + 16));
+    CU(tmp.alloc(radix_sort_tmp_bytes((uint32_t)nH)));
+    k_hbv_csr_rec<<<blocks_for(nH, 256), 256, 0, c->st>>>(c->d_toleft.as<int32_t>(), c->d_toright.as<int32_t>(), (uint32_t)nH, ra.as<uint4>(), rb.as<uint4>());
+    KCHECK("k_hbv_csr_rec");
+    const unsigned csr_blocks = blocks_for(std::max<uint64_t>(nH, (uint64_t)nV + 1), 256);
+    e = radix_sort<RS_KEY96>(ra.as<uint4>(), rs.as<uint4>(), (uint32_t)nH, tmp.p, c->num_sms, c->st);
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv adjacency sort: ") + cudaGetErrorString(e));
+    k_hbv_csr_emit<<<csr_blocks, 256, 0, c->st>>>(ra.as<uint4>(), (uint32_t)nH, nV, c->d_from_start.as<uint32_t>(), c->d_from_v.as<int32_t>(), c->d_from_e.as<int32_t>());
+    KCHECK("k_hbv_csr_emit");
+    e = radix_sort<RS_KEY96>(rb.as<uint4>(), rs.as<uint4>(), (uint32_t)nH, tmp.p, c->num_sms, c->st);
+    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv adjacency sort: ") + cudaGetErrorString(e));
+    k_hbv_csr_emit<<<csr_blocks, 256, 0, c->st>>>(rb.as<uint4>(), (uint32_t)nH, nV, c->d_to_start.as<uint32_t>(), c->d_to_v.as<int32_t>(), c->d_to_e.as<int32_t>());
+    KCHECK("k_hbv_csr_emit");
+    c->launches += 2 * (2 + RsMode<RS_KEY96>::PASSES);
+    k_hbv_inv<<<blocks_for(nE, 256), 256, 0, c->st>>>(c->d_fwd.as<int32_t>(), c->d_rev.as<int32_t>(), nE, dinv.as<int32_t>());
+    KCHECK("k_hbv_inv");
+    t_end(c, "hbv_csr");
+    H.from_start.resize(nV + 1); H.to_start.resize(nV + 1);
+    H.from_v.resize(nH); H.from_e.resize(nH); H.to_v.resize(nH); H.to_e.resize(nH); H.inv.resize(nH);
+    CU(cudaMemcpyAsync(H.from_start.data(), c->d_from_start.p, 4ull * (nV + 1), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.to_start.data(), c->d_to_start.p, 4ull * (nV + 1), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.from_v.data(), c->d_from_v.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.from_e.data(), c->d_from_e.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.to_v.data(), c->d_to_v.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.to_e.data(), c->d_to_e.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.inv.data(), dinv.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    // every side of a vertex holds at most 4 edges (one per base)
+    for (uint32_t v = 0; v < nV; ++v)
+        if (H.from_start[v + 1] - H.from_start[v] > 4 || H.to_start[v + 1] - H.to_start[v] > 4)
+            return fail(c, SN_ERR_DATA, "HBV: more than 4 edges on one side of a vertex");
     c->stage = 4;
     return SN_OK;
 }
