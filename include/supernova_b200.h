@@ -121,26 +121,36 @@ int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_
 int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* params, int with_paths, int write_files);
 
 /* ---- multi-GPU (one context per rank; the caller issues the collectives) ------------------------
- * The k-mer stream is range-partitioned over the ranks by owner(k) = (hash(k) * nparts) >> 32.
- *   1. sn_mg_partition_records : good lengths + k-mer records of this rank's reads, grouped by
- *      owner; part_counts[nparts] records per owner, *dev_records the DEVICE buffer holding them
- *      back to back (16 bytes per record).
- *   2. caller: alltoallv of the records into sn_mg_recv_buffer(total received).
- *   3. sn_mg_count_received    : sort + count + filter of the received records -> this rank's
- *      slice of the dictionary (*dev_dict, n_kmers entries of 32 bytes, DEVICE).
- *   4. caller: allgather of the slices, in rank order, into sn_mg_dictionary_buffer(total).
- *   5. sn_mg_install_dictionary: adopts the gathered dictionary; sn_build_edges / sn_build_hbv /
- *      sn_path_reads then run as on one GPU (graph replicated, reads stay sharded).            */
-int   sn_mg_partition_records(sn_ctx* ctx, const sn_params* params, uint32_t nparts, uint64_t* part_counts, void** dev_records);
-void* sn_mg_recv_buffer(sn_ctx* ctx, uint64_t n_records);
-int   sn_mg_count_received(sn_ctx* ctx, uint64_t n_records, uint64_t* n_kmers, void** dev_dict);
-void* sn_mg_dictionary_buffer(sn_ctx* ctx, uint64_t n_total);
-int   sn_mg_install_dictionary(sn_ctx* ctx, uint64_t n_total);
+ * Reads are sharded over the ranks; the super-k-mer stream (MSP, lib/tada/src/msp/mod.rs) is
+ * range-partitioned by minimizer bucket: owner(bucket) = (bucket * nparts) >> bits, the role of
+ * `shard % total_chunks` in lib/tada/src/cmd_shard_asm.rs:40.
+ *   1. sn_mg_good_lengths  : a1 on this rank's reads; *n_occ = its k-mer occurrences.  The caller
+ *      sums n_occ over the ranks and derives `bits` (sn_msp_bucket_bits) -- equal on every rank.
+ *   2. sn_mg_partition     : super-k-mer records of this rank's reads in bucket order;
+ *      part_records[nparts] records per owner, *dev_records the DEVICE buffer holding them back
+ *      to back (32 bytes per record), *dev_counts the DEVICE u32 count of every bucket (2^bits).
+ *   3. caller: alltoallv of the records into sn_mg_recv_records(total received) and of the
+ *      per-bucket counts of each owner's bucket range into sn_mg_recv_counts(nparts * range).
+ *   4. sn_mg_count_received: per-bucket count + filter of the received records (n_seg = nparts
+ *      source segments, n_buckets = this rank's bucket range) -> its surviving k-mers
+ *      (*dev_survivors, 16 bytes each: w0,w1,w2,count:24|ctx<<24, DEVICE).
+ *   5. caller: allgather of the survivors into sn_mg_survivor_buffer(total).
+ *   6. sn_mg_install_survivors: sorts the gathered k-mers into the dictionary;
+ *      sn_build_edges / sn_build_hbv / sn_path_reads then run as on one GPU (graph replicated,
+ *      reads stay sharded).                                                                    */
+int   sn_msp_bucket_bits(uint64_t n_occ_total);
+int   sn_mg_good_lengths(sn_ctx* ctx, const sn_params* params, uint64_t* n_occ);
+int   sn_mg_partition(sn_ctx* ctx, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts);
+void* sn_mg_recv_records(sn_ctx* ctx, uint64_t n_records);
+void* sn_mg_recv_counts(sn_ctx* ctx, uint64_t n_counts);
+int   sn_mg_count_received(sn_ctx* ctx, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors);
+void* sn_mg_survivor_buffer(sn_ctx* ctx, uint64_t n_total);
+int   sn_mg_install_survivors(sn_ctx* ctx, uint64_t n_total);
 
 /* ---- measurement ------------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) of the most recent run of a stage or
- * kernel group, in milliseconds; names: "goodlen","extract","sort_hist","sort","reduce","index","prune",
- * "edges","path","h2d","hbv_host".  Returns a negative value for an unknown name.          */
+ * kernel group, in milliseconds; names: "h2d","goodlen","msp_hist","msp_scatter","bucket_count","sort","index",
+ * "prune","edges","hbv_dev","hbv_host","hbv_csr","path".  Returns a negative value for an unknown name.          */
 double sn_stage_ms(const sn_ctx* ctx, const char* name);
 /* number of kernel launches issued by this context so far */
 uint64_t sn_kernel_launches(const sn_ctx* ctx);

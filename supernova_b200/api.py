@@ -74,13 +74,15 @@ def lib():
         L.sn_free.argtypes = [vp]
         L.sn_write_read_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64, vp, vp, vp, vp, vp, vp]
         L.sn_device_count.restype = i32
-        L.sn_mg_partition_records.argtypes = [vp, C.POINTER(Params), C.c_uint32, vp, C.POINTER(vp)]
-        L.sn_mg_recv_buffer.argtypes = [vp, u64]
-        L.sn_mg_recv_buffer.restype = vp
-        L.sn_mg_count_received.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(vp)]
-        L.sn_mg_dictionary_buffer.argtypes = [vp, u64]
-        L.sn_mg_dictionary_buffer.restype = vp
-        L.sn_mg_install_dictionary.argtypes = [vp, u64]
+        L.sn_msp_bucket_bits.argtypes = [u64]
+        L.sn_msp_bucket_bits.restype = i32
+        L.sn_mg_good_lengths.argtypes = [vp, C.POINTER(Params), C.POINTER(u64)]
+        L.sn_mg_partition.argtypes = [vp, i32, C.c_uint32, vp, C.POINTER(vp), C.POINTER(vp)]
+        for f in ("sn_mg_recv_records", "sn_mg_recv_counts", "sn_mg_survivor_buffer"):
+            getattr(L, f).argtypes = [vp, u64]
+            getattr(L, f).restype = vp
+        L.sn_mg_count_received.argtypes = [vp, C.c_uint32, C.c_uint32, u64, C.POINTER(u64), C.POINTER(vp)]
+        L.sn_mg_install_survivors.argtypes = [vp, u64]
         _LIB = L
     return _LIB
 
@@ -214,33 +216,41 @@ class Context:
                                                int(with_paths), int(wf)))
 
     # ---- multi-GPU pieces (see supernova_b200/multigpu.py) --------------------------------
-    def mg_partition_records(self, params, nparts):
+    def mg_good_lengths(self, params=None):
         p = params or Params()
+        n = C.c_uint64()
+        self._ck(self.L.sn_mg_good_lengths(self.h, C.byref(p), C.byref(n)))
+        return int(n.value)
+
+    def mg_partition(self, bits, nparts):
         counts = (C.c_uint64 * nparts)()
-        ptr = C.c_void_p()
-        self._ck(self.L.sn_mg_partition_records(self.h, C.byref(p), nparts, counts, C.byref(ptr)))
-        return [int(x) for x in counts], int(ptr.value or 0)
+        rec, cnt = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.sn_mg_partition(self.h, bits, nparts, counts, C.byref(rec), C.byref(cnt)))
+        return [int(x) for x in counts], int(rec.value or 0), int(cnt.value or 0)
 
-    def mg_recv_buffer(self, n_records):
-        p = self.L.sn_mg_recv_buffer(self.h, n_records)
+    def _mg_buf(self, fn, n):
+        p = getattr(self.L, fn)(self.h, n)
         if not p:
             raise SnError(self.L.sn_last_error(self.h).decode())
         return int(p)
 
-    def mg_count_received(self, n_records):
-        nk = C.c_uint64()
+    def mg_recv_records(self, n_records):
+        return self._mg_buf("sn_mg_recv_records", n_records)
+
+    def mg_recv_counts(self, n_counts):
+        return self._mg_buf("sn_mg_recv_counts", n_counts)
+
+    def mg_count_received(self, n_seg, n_buckets, n_records):
+        ns = C.c_uint64()
         ptr = C.c_void_p()
-        self._ck(self.L.sn_mg_count_received(self.h, n_records, C.byref(nk), C.byref(ptr)))
-        return int(nk.value), int(ptr.value or 0)
+        self._ck(self.L.sn_mg_count_received(self.h, n_seg, n_buckets, n_records, C.byref(ns), C.byref(ptr)))
+        return int(ns.value), int(ptr.value or 0)
 
-    def mg_dictionary_buffer(self, n_total):
-        p = self.L.sn_mg_dictionary_buffer(self.h, n_total)
-        if not p:
-            raise SnError(self.L.sn_last_error(self.h).decode())
-        return int(p)
+    def mg_survivor_buffer(self, n_total):
+        return self._mg_buf("sn_mg_survivor_buffer", n_total)
 
-    def mg_install_dictionary(self, n_total):
-        self._ck(self.L.sn_mg_install_dictionary(self.h, n_total))
+    def mg_install_survivors(self, n_total):
+        self._ck(self.L.sn_mg_install_survivors(self.h, n_total))
 
     # ---- results ----------------------------------------------------------------------
     def counts(self):

@@ -1,8 +1,7 @@
 // sn_kernels.cuh -- the CUDA kernels of the hot path (sm_100a), in pipeline order:
 //   a1  k_pqvec_goodlen / k_q8_goodlen   PQVec decode + good-length scan
-//   a2  k_extract                         canonical (k,k+1)-mer records from 2-bit reads
-//   a4  radix_sort_kmers (sn_prims.cuh)   128-bit records by 96-bit k-mer
-//   a5  k_reduce                          run-length count / ctx OR / barcode rule / filter
+//   a2-a5, a14-a15  sn_msp.cuh            super-k-mers by minimizer bucket, per-bucket count + filter,
+//                                         survivors sorted by hash (sn_prims.cuh) into the dictionary
 //   a6  k_build_index, k_prune            dictionary prefix index, adjacency prune
 //   a7  k_classify, k_walk_count, k_circle_count, k_walk_emit, k_fix_offsets, k_pack_edges
 //   a10-a12 k_path_reads                  ReadPath threading + extension
@@ -70,6 +69,21 @@ __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const u
     if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; if (t) atomicAdd(occ_total, (unsigned long long)t); }
 }
 
+// input limits checked on the device: total bases, longest read, largest barcode ordinal
+__global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, const uint32_t* __restrict__ len, const int32_t* __restrict__ bc,
+                                                    unsigned long long* total_bases, uint32_t* max_len, int32_t* max_bc)
+{
+    uint64_t sum = 0; uint32_t ml = 0; int32_t mb = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = len[r]; sum += l; ml = max(ml, l);
+        if (bc) mb = max(mb, bc[r]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(SN_FULL, sum, o); ml = max(ml, __shfl_down_sync(SN_FULL, ml, o)); mb = max(mb, __shfl_down_sync(SN_FULL, mb, o));
+    }
+    if (lane_id() == 0) { atomicAdd(total_bases, (unsigned long long)sum); atomicMax(max_len, ml); atomicMax(max_bc, mb); }
+}
+
 // same, for callers that already hold one u8 per base
 __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
                                                     const uint32_t* __restrict__ len, uint32_t min_qual,
@@ -91,323 +105,7 @@ __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint
     if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; if (t) atomicAdd(occ_total, (unsigned long long)t); }
 }
 
-// ---------------------------------------------------------------------------
-// a2. Kmerizer::map (BuildReadQGraph48.cc:155-172).  A CTA stages the packed bases of
-// EX_READS consecutive reads in shared memory with 16-byte loads, then its threads walk
-// the tile's k-mer occurrences in order: occurrence x of the tile -> thread x % 256, so a
-// warp writes 32 consecutive 16-byte records (512 B, fully coalesced).  The output
-// range of the tile is reserved with one atomicAdd per CTA (record order does not
-// matter: the sort follows and the reduction is order independent).
-// record = {w0,w1,w2 of the canonical k-mer, ctx<<24 | bc24} ; bc24 = 0xFFFFFF for "-1".
-// ---------------------------------------------------------------------------
-#define SN_EX_READS 128
-#define SN_EX_BYTES (SN_EX_READS * (SN_MAX_READ_LEN / 4) + 48)
-
-__global__ void __launch_bounds__(256) k_extract(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
-                                                 const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc,
-                                                 int64_t ign_bc_below, uint4* __restrict__ out, unsigned long long* cursor)
-{
-    __shared__ __align__(16) uint8_t sb[SN_EX_BYTES];
-    __shared__ uint32_t pref[SN_EX_READS + 1];
-    __shared__ uint32_t s_gl[SN_EX_READS];
-    __shared__ uint32_t s_rel[SN_EX_READS];
-    __shared__ uint32_t s_bc[SN_EX_READS];
-    __shared__ uint32_t wsum[8];
-    __shared__ unsigned long long s_base;
-    const uint32_t tid = threadIdx.x;
-    const uint64_t r0 = (uint64_t)blockIdx.x * SN_EX_READS;
-    const uint32_t nr = (uint32_t)min((uint64_t)SN_EX_READS, n_reads - r0);
-    const uint64_t lo = boff[r0], hi = boff[r0 + nr];
-    const uint64_t lo_al = lo & ~15ull;
-    const uint32_t shift = (uint32_t)(lo - lo_al);
-    // stage packed bases (16-byte vector loads; the allocation is padded)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(bases + lo_al);
-        uint4* dst = reinterpret_cast<uint4*>(sb);
-        uint32_t nv = (uint32_t)((hi - lo_al + 13 + 15) >> 4);      // +13: kmer_from_packed may touch 13 bytes
-        for (uint32_t i = tid; i < nv; i += 256) dst[i] = src[i];
-    }
-    // per-read counts and their exclusive prefix (128 reads: threads 0..127)
-    uint32_t cnt = 0;
-    if (tid < nr) {
-        uint32_t gl = goodlen[r0 + tid];
-        s_gl[tid] = gl;
-        s_rel[tid] = (uint32_t)(boff[r0 + tid] - lo) + shift;
-        int32_t b = -1;
-        if (bc && (int64_t)(r0 + tid) >= ign_bc_below) b = bc[r0 + tid];
-        s_bc[tid] = b < 0 ? 0xFFFFFFu : (uint32_t)b;
-        cnt = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
-    }
-    {
-        uint32_t x = cnt, lane = tid & 31u, w = tid >> 5;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
-        if (lane == 31) wsum[w] = x;
-        __syncthreads();
-        uint32_t wb = 0;
-        for (uint32_t k = 0; k < w; ++k) wb += wsum[k];
-        if (tid < SN_EX_READS) pref[tid] = wb + x - cnt;
-        if (tid == SN_EX_READS - 1) pref[SN_EX_READS] = wb + x;
-    }
-    __syncthreads();
-    const uint32_t T = pref[SN_EX_READS];
-    if (tid == 0) s_base = T ? atomicAdd(cursor, (unsigned long long)T) : 0ull;
-    __syncthreads();
-    const uint64_t base = s_base;
-    for (uint32_t x = tid; x < T; x += 256) {
-        // read of occurrence x: largest rr with pref[rr] <= x
-        uint32_t a = 0, b = SN_EX_READS;
-        while (b - a > 1) { uint32_t m = (a + b) >> 1; if (pref[m] <= x) a = m; else b = m; }
-        const uint32_t rr = a, i = x - pref[rr], gl = s_gl[rr];
-        const uint8_t* rp = sb + s_rel[rr];
-        Kmer k = kmer_from_packed(rp, i);
-        uint32_t ctx = 0;
-        if (i > 0) ctx |= 16u << packed_base(rp, i - 1);
-        if (i + SN_K < gl) ctx |= 1u << packed_base(rp, i + SN_K);
-        Kmer rc;
-        if (kmer_form(k, &rc) == REV) { k = rc; ctx = ctx_rc(ctx); }
-        out[base + x] = make_uint4(k.w0, k.w1, k.w2, (ctx << 24) | s_bc[rr]);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// a5. Kmerizer::reduce / summarizeEntries / areIgnoredBarcodes / areEnoughBarcodes
-// (BuildReadQGraph48.cc:91-137,174-181) over the records sorted by kmer_hash, fused with
-// the ordered compaction of the surviving k-mers into the dictionary (tile look-back).
-// The first record of every run of EQUAL HASH owns the run.  Almost always the run is one
-// k-mer: count (saturating 2^24-1), OR of contexts, min/max barcode > 0 (>= 2 distinct <=>
-// min != max), "ignored" flag in one walk.  When distinct k-mers collide in a run the owner
-// re-walks it once per k-mer in increasing k-mer order, so the dictionary comes out ordered
-// by (hash, k-mer).
-// ---------------------------------------------------------------------------
-#define SN_RD_THREADS 256
-#define SN_RD_ITEMS 8
-#define SN_RD_TILE (SN_RD_THREADS * SN_RD_ITEMS)
-
 __device__ __forceinline__ bool same_kmer(const uint4& a, const uint4& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
-__device__ __forceinline__ bool kmer_lt(const uint4& a, const uint4& b)
-{ return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); }
-
-struct RunStat { uint32_t count, ctx, minbc, maxbc; bool ign; };
-__device__ __forceinline__ void stat_init(RunStat& s) { s.count = 0; s.ctx = 0; s.minbc = 0xFFFFFFFFu; s.maxbc = 0; s.ign = false; }
-__device__ __forceinline__ void stat_add(RunStat& s, uint32_t aux)
-{
-    ++s.count; s.ctx |= aux >> 24;
-    uint32_t b = aux & 0xFFFFFFu;
-    if (b == 0xFFFFFFu) s.ign = true;
-    else if (b) { s.minbc = min(s.minbc, b); s.maxbc = max(s.maxbc, b); }
-}
-__device__ __forceinline__ bool stat_valid(const RunStat& s, uint32_t min_freq, uint32_t min_bc, int has_bc)
-{
-    bool enough = min_bc == 0 || (min_bc == 1 ? s.maxbc != 0 : (s.maxbc != 0 && s.minbc != s.maxbc));
-    return s.count >= min_freq && (!has_bc || s.ign || enough);
-}
-__device__ __forceinline__ DictEntry make_entry(const uint4& k, const RunStat& s, uint32_t h)
-{
-    DictEntry e;
-    e.w0 = k.x; e.w1 = k.y; e.w2 = k.z; e.cc = min(s.count, 0xFFFFFFu) | (s.ctx << 24);
-    e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = s.ctx; e.h = h;
-    return e;
-}
-// Slow path: the run [p0,p1) of equal hash holds more than one k-mer.  Visits the distinct
-// k-mers in increasing order; emits the valid ones at out[pos...] when out != nullptr.
-// Returns the number of valid k-mers.
-__device__ __noinline__ uint32_t reduce_mixed_run(const uint4* __restrict__ keys, uint64_t p0, uint64_t p1, uint32_t h,
-                                                  uint32_t min_freq, uint32_t min_bc, int has_bc, DictEntry* out, uint64_t pos, uint32_t* n_distinct)
-{
-    uint32_t nvalid = 0, ndist = 0;
-    uint4 cur = keys[p0];
-    for (uint64_t p = p0 + 1; p < p1; ++p) { uint4 r = keys[p]; if (kmer_lt(r, cur)) cur = r; }     // smallest k-mer
-    for (;;) {
-        RunStat st; stat_init(st);
-        bool have_next = false; uint4 next = cur;
-        for (uint64_t p = p0; p < p1; ++p) {
-            uint4 r = keys[p];
-            if (same_kmer(r, cur)) stat_add(st, r.w);
-            else if (kmer_lt(cur, r) && (!have_next || kmer_lt(r, next))) { next = r; have_next = true; }
-        }
-        ++ndist;
-        if (stat_valid(st, min_freq, min_bc, has_bc)) { if (out) out[pos + nvalid] = make_entry(cur, st, h); ++nvalid; }
-        if (!have_next) break;
-        cur = next;
-    }
-    if (n_distinct) *n_distinct = ndist;
-    return nvalid;
-}
-
-// Aggregate of a (partial) run, combined with shuffles.
-struct Agg { uint32_t count, ctx_flags, minbc, maxbc; };      // ctx_flags: ctx | ign<<8 | mixed<<9
-__device__ __forceinline__ Agg agg_combine(const Agg& a, const Agg& b)
-{ Agg r; r.count = a.count + b.count; r.ctx_flags = a.ctx_flags | b.ctx_flags; r.minbc = min(a.minbc, b.minbc); r.maxbc = max(a.maxbc, b.maxbc); return r; }
-__device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int d)
-{ Agg r; r.count = __shfl_up_sync(SN_FULL, a.count, d); r.ctx_flags = __shfl_up_sync(SN_FULL, a.ctx_flags, d);
-  r.minbc = __shfl_up_sync(SN_FULL, a.minbc, d); r.maxbc = __shfl_up_sync(SN_FULL, a.maxbc, d); return r; }
-__device__ __forceinline__ Agg agg_bcast(const Agg& a, int src)
-{ Agg r; r.count = __shfl_sync(SN_FULL, a.count, src); r.ctx_flags = __shfl_sync(SN_FULL, a.ctx_flags, src);
-  r.minbc = __shfl_sync(SN_FULL, a.minbc, src); r.maxbc = __shfl_sync(SN_FULL, a.maxbc, src); return r; }
-__device__ __forceinline__ bool agg_valid(const Agg& s, uint32_t min_freq, uint32_t min_bc, int has_bc)
-{
-    bool enough = min_bc == 0 || (min_bc == 1 ? s.maxbc != 0 : (s.maxbc != 0 && s.minbc != s.maxbc));
-    return s.count >= min_freq && (!has_bc || ((s.ctx_flags >> 8) & 1u) || enough);
-}
-
-// Warp-streaming reduce-by-key ("warp-ballot run-length counting").  Each warp owns the runs of
-// equal hash whose FIRST record lies in its chunk of SN_RD_CHUNK records; it streams 32 records
-// per step (one coalesced 512-byte load), finds run heads with a ballot, reduces every run with
-// a segmented shuffle scan, carries the open run across steps (and past the end of the chunk),
-// and writes the surviving k-mers, in order, to its private staging slots; per-warp counts are
-// scanned and k_reduce_gather compacts the stage into the dictionary.
-#define SN_RD_CHUNK 1024
-#define SN_RD_WARPS 8
-template <int MINB>
-__global__ void __launch_bounds__(SN_RD_WARPS * 32, MINB) k_reduce(const uint4* __restrict__ keys, uint32_t n, uint32_t min_freq, uint32_t min_bc, int has_bc,
-                                                             DictEntry* __restrict__ stage, uint32_t cap_per_warp, uint32_t* __restrict__ warp_count,
-                                                             unsigned long long* n_distinct, uint32_t* overflow)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t w = (uint64_t)blockIdx.x * SN_RD_WARPS + (threadIdx.x >> 5);
-    const uint64_t a = w * SN_RD_CHUNK;
-    if (a >= n) return;
-    const uint64_t b = min((uint64_t)n, a + SN_RD_CHUNK);
-    DictEntry* out = stage + w * cap_per_warp;
-    const uint4 SENT = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);   // never a canonical k-mer
-    uint4 prev_last = a > 0 ? keys[a - 1] : SENT;
-    uint32_t prev_h = rs_hash(prev_last);
-    bool started = false;          // an owned run has begun
-    bool open = false;             // carry holds an owned, unfinished run
-    Agg carry; carry.count = 0; carry.ctx_flags = 0; carry.minbc = 0xFFFFFFFFu; carry.maxbc = 0;
-    uint4 carry_key = SENT; uint64_t carry_start = 0; uint32_t carry_h = 0;
-    uint32_t cursor = 0, distinct = 0;
-    // software pipeline: the records of the next two steps are already in flight
-    uint4 nx1 = (a + lane < n) ? keys[a + lane] : SENT;
-    uint4 nx2 = (a + 32 + lane < n) ? keys[a + 32 + lane] : SENT;
-    for (uint64_t pos = a;; pos += 32) {
-        const uint64_t idx = pos + lane;
-        const bool inb = idx < n;
-        uint4 r = nx1;
-        nx1 = nx2;
-        nx2 = (idx + 64 < n) ? keys[idx + 64] : SENT;
-        uint4 pv;
-        pv.x = __shfl_up_sync(SN_FULL, r.x, 1); pv.y = __shfl_up_sync(SN_FULL, r.y, 1); pv.z = __shfl_up_sync(SN_FULL, r.z, 1); pv.w = 0;
-        if (lane == 0) pv = prev_last;
-        const uint32_t h = rs_hash(r);                                  // one hash per record, shared by every later use
-        uint32_t ph = __shfl_up_sync(SN_FULL, h, 1);
-        if (lane == 0) ph = prev_h;
-        const bool kh = !same_kmer(pv, r);                              // first record of its k-mer
-        bool hh = kh && (idx == 0 || !inb || ph != h);                  // first record of its hash run
-        if (idx > n) hh = false;                                       // only the first sentinel closes the last run
-        const uint32_t hmask = __ballot_sync(SN_FULL, hh);
-        // ownership window of this step: from the first owned head on (skip the tail of a
-        // foreign run at the start of the chunk), up to the first head at or past `b`
-        const uint32_t fmask = __ballot_sync(SN_FULL, hh && idx >= b);
-        const uint32_t f = fmask ? (uint32_t)__ffs(fmask) - 1u : 32u;   // lanes >= f belong to the next warp
-        uint32_t first = 0;
-        if (!started) { if (!hmask) { prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
-                                      prev_h = __shfl_sync(SN_FULL, h, 31);
-                                      if (pos + 32 >= n + 1) break; continue; }
-                        first = (uint32_t)__ffs(hmask) - 1u; }
-        const bool active = lane >= first && lane < f;
-        Agg v; v.count = active ? 1u : 0u;
-        v.ctx_flags = active ? ((r.w >> 24) | ((r.w & 0xFFFFFFu) == 0xFFFFFFu ? 0x100u : 0u) | ((kh && !hh) ? 0x200u : 0u)) : 0u;
-        { uint32_t bcv = r.w & 0xFFFFFFu; bool pos_bc = active && bcv != 0 && bcv != 0xFFFFFFu;
-          v.minbc = pos_bc ? bcv : 0xFFFFFFFFu; v.maxbc = pos_bc ? bcv : 0u; }
-        // segmented inclusive scan; segments start at run heads
-        const uint32_t seg_heads = hmask & ((2u << lane) - 1u);          // heads at or before this lane
-        const int seg_start = seg_heads ? 31 - __clz(seg_heads) : -1;     // -1: the run continues from the carry
-        const uint32_t dist = (uint32_t)((int)lane - (seg_start < 0 ? 0 : seg_start));
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { Agg u = agg_shfl_up(v, d); if ((uint32_t)d <= dist) v = agg_combine(u, v); }
-        if (seg_start < 0 && open) v = agg_combine(carry, v);
-        // a run ends at lane l when lane l+1 is a head (or the ownership window closes there)
-        const uint32_t nextmask = (hmask >> 1) | (f < 32 && f > 0 ? (1u << (f - 1)) : 0u);
-        const bool ends_here = active && lane < 31 && ((nextmask >> lane) & 1u);
-        // the carried run ends when lane 0 is a head (or is already foreign)
-        const bool carry_ends = open && (((hmask | (f == 0 ? 1u : 0u)) & 1u) != 0);
-        // --- emission, in order: carried run first, then the runs that end inside this step ---
-        if (carry_ends) {
-            bool mixed = (carry.ctx_flags >> 9) & 1u;
-            if (!mixed) {
-                ++distinct;
-                if (agg_valid(carry, min_freq, min_bc, has_bc)) {
-                    if (cursor < cap_per_warp) { if (lane == 0) { RunStat st; st.count = carry.count; st.ctx = carry.ctx_flags & 0xFFu; out[cursor] = make_entry(carry_key, st, carry_h); } }
-                    else if (lane == 0) atomicAdd(overflow, 1u);
-                    ++cursor;
-                }
-            } else {
-                uint32_t nd = 0, nvld = 0;
-                if (lane == 0) {
-                    uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
-                    nvld = reduce_mixed_run(keys, carry_start, pos, carry_h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
-                    if (nvld <= room) reduce_mixed_run(keys, carry_start, pos, carry_h, min_freq, min_bc, has_bc, out, cursor, nullptr);
-                    else atomicAdd(overflow, 1u);
-                }
-                cursor += __shfl_sync(SN_FULL, nvld, 0); distinct += __shfl_sync(SN_FULL, nd, 0);
-            }
-            open = false;
-        }
-        {
-            const bool mixed = (v.ctx_flags >> 9) & 1u;
-            const bool emit_ok = ends_here && !mixed && agg_valid(v, min_freq, min_bc, has_bc);
-            const uint32_t emask = __ballot_sync(SN_FULL, emit_ok);
-            const uint32_t mmask = __ballot_sync(SN_FULL, ends_here && mixed);
-            distinct += __popc(__ballot_sync(SN_FULL, ends_here && !mixed));
-            if (!mmask) {
-                if (emit_ok) {
-                    uint32_t p = cursor + __popc(emask & lanemask_lt());
-                    if (p < cap_per_warp) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[p] = make_entry(r, st, h); }
-                    else atomicAdd(overflow, 1u);
-                }
-                cursor += __popc(emask);
-            } else {
-                // rare: a run with colliding k-mers ends in this step -> go through the ending lanes one by one
-                uint32_t todo = emask | mmask;
-                while (todo) {
-                    const uint32_t l = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
-                    uint32_t nvld = 0, nd = 0;
-                    if (lane == l) {
-                        uint32_t room = cursor < cap_per_warp ? cap_per_warp - cursor : 0;
-                        if (!mixed) { nvld = 1; if (room) { RunStat st; st.count = v.count; st.ctx = v.ctx_flags & 0xFFu; out[cursor] = make_entry(r, st, h); } else atomicAdd(overflow, 1u); }
-                        else {
-                            const uint64_t start = seg_start < 0 ? carry_start : pos + (uint32_t)seg_start;
-                            nvld = reduce_mixed_run(keys, start, idx + 1, h, min_freq, min_bc, has_bc, nullptr, 0, &nd);
-                            if (nvld <= room) reduce_mixed_run(keys, start, idx + 1, h, min_freq, min_bc, has_bc, out, cursor, nullptr);
-                            else atomicAdd(overflow, 1u);
-                        }
-                    }
-                    cursor += __shfl_sync(SN_FULL, nvld, l); distinct += __shfl_sync(SN_FULL, nd, l);
-                }
-            }
-        }
-        started = true;
-        if (f < 32) break;                                              // the next warp's first run starts here
-        // the run open at lane 31 is carried into the next step
-        {
-            const uint32_t last_head = hmask ? 31u - (uint32_t)__clz(hmask) : 32u;
-            const bool had_open = open;                                   // still true only if the carried run did not end
-            Agg c31 = agg_bcast(v, 31);
-            if (last_head < 32) {
-                carry = c31; open = true;
-                carry_key.x = __shfl_sync(SN_FULL, r.x, last_head); carry_key.y = __shfl_sync(SN_FULL, r.y, last_head); carry_key.z = __shfl_sync(SN_FULL, r.z, last_head);
-                carry_h = __shfl_sync(SN_FULL, h, last_head);
-                carry_start = pos + last_head;
-            } else if (had_open) carry = c31;                            // the carried run swallowed the whole step
-        }
-        prev_last.x = __shfl_sync(SN_FULL, r.x, 31); prev_last.y = __shfl_sync(SN_FULL, r.y, 31); prev_last.z = __shfl_sync(SN_FULL, r.z, 31);
-        prev_h = __shfl_sync(SN_FULL, h, 31);
-        if (pos + 32 >= (uint64_t)n + 1) break;                           // the sentinel lane has been processed
-    }
-    if (lane == 0) { warp_count[w] = cursor; if (distinct) atomicAdd(n_distinct, (unsigned long long)distinct); }
-}
-// compacts the per-warp staging slots into the dictionary: one warp per source warp
-__global__ void __launch_bounds__(256) k_reduce_gather(const DictEntry* __restrict__ stage, uint32_t cap_per_warp, const uint32_t* __restrict__ warp_count,
-                                                       const uint64_t* __restrict__ warp_off, uint64_t n_warps, DictEntry* __restrict__ dict)
-{
-    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_warps) return;
-    const uint32_t lane = threadIdx.x & 31u, cnt = warp_count[w];
-    const uint4* src = reinterpret_cast<const uint4*>(stage + w * cap_per_warp);
-    uint4* dst = reinterpret_cast<uint4*>(dict + warp_off[w]);
-    for (uint32_t i = lane; i < 2 * cnt; i += 32) dst[i] = src[i];
-}
 
 // ---------------------------------------------------------------------------
 // a6. dictionary prefix index + recomputeAdjacencies

@@ -323,7 +323,7 @@ __device__ __forceinline__ void skc_step(SkCursor& c, uint32_t next_base)
 }
 
 __global__ void __launch_bounds__(SN_BC_THREADS, 3)
-k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets,
+k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg,
                uint32_t min_freq, uint32_t min_bc, int has_bc,
                uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor, unsigned long long* n_distinct, uint32_t* err)
 {
@@ -333,8 +333,14 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bkt = blockIdx.x;
     if (bkt >= n_buckets) return;
-    const uint64_t r0 = bucket_off[bkt], r1 = bucket_off[bkt + 1];
-    if (r0 == r1) return;
+    // the bucket's records: one range per segment (one segment on a single GPU; one per source
+    // rank after the multi-GPU exchange).  bucket_off is the exclusive scan of the counts laid out
+    // segment-major, so segment s holds records [off[s*n_buckets + bkt], off[s*n_buckets + bkt + 1]).
+    {
+        bool any = false;
+        for (uint32_t sg = 0; sg < n_seg; ++sg) any = any || bucket_off[(uint64_t)sg * n_buckets + bkt] != bucket_off[(uint64_t)sg * n_buckets + bkt + 1];
+        if (!any) return;
+    }
     if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.fill = 0; S.over = 0; S.ndist = 0; }
     for (uint32_t s = tid; s < SN_BC_SLOTS; s += SN_BC_THREADS) S.tag[s] = 0;
     __syncthreads();
@@ -347,7 +353,8 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     for (;;) {
         bool overflowed = false;
         const uint32_t R = 1u << depth, round = sub;
-        {
+        for (uint32_t sg = 0; sg < n_seg && !overflowed; ++sg) {
+            const uint64_t r0 = bucket_off[(uint64_t)sg * n_buckets + bkt], r1 = bucket_off[(uint64_t)sg * n_buckets + bkt + 1];
             for (uint64_t c0 = r0; c0 < r1 && !overflowed; c0 += SN_BC_CHUNK) {
                 const uint32_t nc = (uint32_t)min((uint64_t)SN_BC_CHUNK, r1 - c0);
                 if (tid == 0) {
@@ -452,6 +459,8 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                     __syncthreads();
                 }
             }
+        }
+        {
             // ---- emission: valid slots -> out; the table is cleaned through the claim list ----
             const uint32_t nfill = S.fill;
             uint32_t vmask = 0, nvalid = 0;
@@ -507,6 +516,15 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
         sub |= 1u << (depth - 1u);                                          // sibling half
     }
     if (tid == 0 && S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
+}
+
+// k-mer occurrences held by n records
+__global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, uint64_t n, unsigned long long* total)
+{
+    unsigned long long s = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += sk_nk(recs[2 * i].x);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(SN_FULL, s, o);
+    if (lane_id() == 0 && s) atomicAdd(total, s);
 }
 
 // survivors sorted by kmer_hash (stable LSD passes) -> dictionary entries in (hash, k-mer) order:

@@ -156,30 +156,36 @@ int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_
     if ((r = upload(c, c->boff, base_off, 8 * (n_reads + 1)))) return r;
     if ((r = upload(c, c->len, len, 4 * n_reads))) return r;
     c->have_bc = bc != nullptr;
-    if (bc) {
-        // barcode ordinals travel in 24 bits of the k-mer record (0xFFFFFF is reserved for "-1")
-        int32_t mx = 0; for (uint64_t i = 0; i < n_reads; ++i) mx = std::max(mx, bc[i]);
-        if (mx >= 0xFFFFFF) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
-        if ((r = upload(c, c->bc, bc, 4 * n_reads))) return r;
-    }
+    if (bc && (r = upload(c, c->bc, bc, 4 * n_reads))) return r;
     return SN_OK;
 }
 
 int finish_load(sn_ctx* c)
 {
     t_end(c, "h2d");
-    uint64_t n = c->cnt.n_reads;
-    // element offsets of the unpacked quals = exclusive scan of the read lengths
-    CU(c->qoff.alloc(8 * (n + 1)));
-    uint64_t total = 0;
-    int r = scan_u32(c, c->len.as<uint32_t>(), n, c->qoff.as<uint64_t>(), &total);
-    if (r) return r;
-    c->cnt.n_bases = total;
+    const uint64_t n = c->cnt.n_reads;
+    // limits are checked on the device (no pass over the caller's arrays on the host):
+    // total bases, longest read, largest barcode ordinal
+    unsigned long long* cnt64 = c->counters.as<unsigned long long>() + 16;     // [16] bases, [17] max len | max bc
+    CU(cudaMemsetAsync(cnt64, 0, 16, c->st));
+    k_read_stats<<<std::min(blocks_for(n, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(n, c->len.as<uint32_t>(), c->have_bc ? c->bc.as<int32_t>() : nullptr,
+        cnt64, reinterpret_cast<uint32_t*>(cnt64 + 1), reinterpret_cast<int32_t*>(cnt64 + 1) + 1);
+    KCHECK("k_read_stats");
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, cnt64, 16, cudaMemcpyDeviceToHost, c->st));
+    if (!c->have_pq) {
+        // element offsets of the unpacked quals = exclusive scan of the read lengths
+        CU(c->qoff.alloc(8 * (n + 1)));
+        int r = scan_u32(c, c->len.as<uint32_t>(), n, c->qoff.as<uint64_t>(), nullptr);
+        if (r) return r;
+    }
+    CU(cudaStreamSynchronize(c->st));                  // the caller's buffers are free again when this returns
+    c->cnt.n_bases = h[0];
+    const uint32_t max_len = (uint32_t)(h[1] & 0xFFFFFFFFu); const int32_t max_bc = (int32_t)(h[1] >> 32);
     // longest read must fit the per-thread buffers of the pathing kernel
-    std::vector<uint32_t> hl(n);
-    CU(cudaMemcpy(hl.data(), c->len.p, 4 * n, cudaMemcpyDeviceToHost));
-    uint32_t mx = 0; for (uint32_t v : hl) mx = std::max(mx, v);
-    if (mx > SN_MAX_READ_LEN) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    if (max_len > SN_MAX_READ_LEN) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    // barcode ordinals travel in 24 bits of a super-k-mer record (0xFFFFFF is reserved for "-1")
+    if (max_bc >= 0xFFFFFF) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
     c->stage = 1;
     return SN_OK;
 }
@@ -189,6 +195,7 @@ int finish_load(sn_ctx* c)
 // =============================================================================
 extern "C" {
 
+int sn_msp_bucket_bits(uint64_t n_occ_total) { return msp_bucket_bits(n_occ_total); }
 int sn_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 int sn_ctx_create(sn_ctx** out, int device)
@@ -314,78 +321,6 @@ static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
     *n_occ_out = h_occ;
     return SN_OK;
 }
-// a2 (multi-GPU record path): the k-mer records of this context's reads into pool["keys_a"]
-static int count_extract(sn_ctx* c, uint32_t* n_occ_out)
-{
-    const uint64_t n = c->cnt.n_reads;
-    unsigned long long* occ = c->counters.as<unsigned long long>();
-    uint64_t h_occ = 0;
-    int r0 = count_goodlen(c, &h_occ);
-    if (r0) return r0;
-    const uint32_t n_occ = (uint32_t)h_occ;
-    *n_occ_out = n_occ;
-    if (!n_occ) return SN_OK;
-    DevBuf& ka = c->pool["keys_a"];
-    CU(ka.alloc((size_t)n_occ * 16));
-    t_begin(c, "extract");
-    k_extract<<<blocks_for(n, SN_EX_READS), 256, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-        c->have_bc ? c->bc.as<int32_t>() : nullptr, c->params.ign_bc_below, ka.as<uint4>(), occ + 1);
-    KCHECK("k_extract");
-    t_end(c, "extract");
-    return SN_OK;
-}
-// a4 + a5: sorts the n_occ records in pool["keys_a"] by hash and reduces them into c->dict
-static int count_sort_reduce(sn_ctx* c, uint32_t n_occ)
-{
-    unsigned long long* occ = c->counters.as<unsigned long long>();
-    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);
-    c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
-    if (!n_occ) { CU(c->dict.alloc(64)); return SN_OK; }
-    DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
-    const uint64_t n_warps = ((uint64_t)n_occ + SN_RD_CHUNK - 1) / SN_RD_CHUNK;
-    const uint32_t cap_per_warp = SN_RD_CHUNK / c->params.min_freq + 10;
-    CU(kb.alloc(std::max((size_t)n_occ * 16, (size_t)n_warps * cap_per_warp * sizeof(DictEntry))));
-    CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
-    t_begin(c, "sort_hist");
-    cudaError_t e = radix_sort_histograms<RS_HASH32>(ka.as<uint4>(), n_occ, tmp.p, c->num_sms, c->st);
-    c->launches += 2;
-    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort histograms: ") + cudaGetErrorString(e));
-    t_end(c, "sort_hist");
-    t_begin(c, "sort");
-    e = radix_sort_passes<RS_HASH32>(ka.as<uint4>(), kb.as<uint4>(), n_occ, tmp.p, 0, c->st);
-    c->launches += RsMode<RS_HASH32>::PASSES;
-    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e));
-    t_end(c, "sort");
-    // per-warp staging in kb (free again after the sort), then an ordered gather into the dictionary
-    t_begin(c, "reduce");
-    DevBuf &wcount = c->pool["warp_count"], &woff = c->pool["warp_off"];
-    CU(wcount.alloc(4 * n_warps)); CU(woff.alloc(8 * (n_warps + 1)));
-    CU(cudaMemsetAsync(occ + 2, 0, 8, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
-    static const int rd_minb = getenv("SN_RD_MINB") ? atoi(getenv("SN_RD_MINB")) : 3;
-    if (rd_minb == 2)
-        k_reduce<2><<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
-            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
-    else
-        k_reduce<3><<<blocks_for(n_warps, SN_RD_WARPS), SN_RD_WARPS * 32, 0, c->st>>>(ka.as<uint4>(), n_occ, c->params.min_freq, c->params.min_bc,
-            c->have_bc ? 1 : 0, kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), occ + 2, u32c + 3);
-    KCHECK("k_reduce");
-    uint64_t h_n = 0;
-    int r = scan_u32(c, wcount.as<uint32_t>(), n_warps, woff.as<uint64_t>(), &h_n);
-    if (r) return r;
-    uint32_t h_over = 0; unsigned long long h_d = 0;
-    CU(cudaMemcpyAsync(&h_over, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(&h_d, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    if (h_over) return fail(c, SN_ERR_DATA, "k_reduce staging overflow (pathological hash collisions)");
-    if (h_n >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
-    c->cnt.n_kmers = h_n; c->cnt.n_kmers_distinct = h_d;
-    CU(c->dict.alloc((size_t)h_n * sizeof(DictEntry) + 64));
-    k_reduce_gather<<<blocks_for(n_warps * 32, 256), 256, 0, c->st>>>(kb.as<DictEntry>(), cap_per_warp, wcount.as<uint32_t>(), woff.as<uint64_t>(),
-        n_warps, c->dict.as<DictEntry>());
-    KCHECK("k_reduce_gather");
-    t_end(c, "reduce");
-    return SN_OK;
-}
 // a14 (MSP): cuts this context's reads into super-k-mers and groups them by minimizer bucket:
 // pool["sk_recs"] (32-byte records, bucket order) and pool["sk_off"] (2^bits + 1 record offsets).
 static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
@@ -414,24 +349,25 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
     t_end(c, "msp_scatter");
     return SN_OK;
 }
-// a15 / a4 + a5: per-bucket count + filter of bucket-ordered super-k-mer records, then the surviving
-// k-mers sorted by hash into c->dict.  `occ_bound` bounds the k-mer occurrences the records hold.
-static int msp_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint64_t occ_bound)
+// a15 / a4 + a5: per-bucket count + filter of bucket-ordered super-k-mer records (n_seg ranges per
+// bucket, see k_bucket_count); the surviving k-mers land, unordered, in `surv`.
+// `occ_bound` bounds the k-mer occurrences the records hold.
+static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound, DevBuf& surv, uint64_t* n_surv_out)
 {
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [2] distinct, [3] survivor cursor
     uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [3] error flags
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
-    if (!occ_bound) { CU(c->dict.alloc(64)); return SN_OK; }
+    *n_surv_out = 0;
+    if (!occ_bound) return SN_OK;
     const uint64_t cap = occ_bound / c->params.min_freq + 16;
     if (cap >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 candidate k-mers in one context");
-    DevBuf &sa = c->pool["surv_a"], &sb = c->pool["surv_b"], &tmp = c->pool["sort_tmp"];
-    CU(sa.alloc(16 * cap));
+    CU(surv.alloc(16 * cap));
     static bool attr_set = false;
     if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem))); attr_set = true; }
     t_begin(c, "bucket_count");
     CU(cudaMemsetAsync(occ + 2, 0, 16, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
-    k_bucket_count<<<n_buckets, SN_BC_THREADS, sizeof(BcSmem), c->st>>>(recs, off, n_buckets, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
-        sa.as<uint4>(), cap, occ + 3, occ + 2, u32c + 3);
+    k_bucket_count<<<n_buckets, SN_BC_THREADS, sizeof(BcSmem), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
+        surv.as<uint4>(), cap, occ + 3, occ + 2, u32c + 3);
     KCHECK("k_bucket_count");
     t_end(c, "bucket_count");
     unsigned long long h[2] = {0, 0}; uint32_t h_err = 0;
@@ -439,18 +375,25 @@ static int msp_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t
     CU(cudaMemcpyAsync(&h_err, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     if (h_err & 1u) return fail(c, SN_ERR_DATA, "k_bucket_count: more surviving k-mers than occurrences / min_freq (internal error)");
-    if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table in 65536 rounds (pathological hash collisions)");
-    const uint64_t n_surv = h[1];
+    if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table after 16 splits (pathological hash collisions)");
+    c->cnt.n_kmers_distinct = h[0];
+    *n_surv_out = h[1];
+    return SN_OK;
+}
+// the surviving k-mers in `surv`, sorted by hash into c->dict (ordered by (hash, k-mer))
+static int msp_finish_dict(sn_ctx* c, DevBuf& surv, uint64_t n_surv)
+{
     if (n_surv >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
-    c->cnt.n_kmers = n_surv; c->cnt.n_kmers_distinct = h[0];
+    c->cnt.n_kmers = n_surv;
     CU(c->dict.alloc((size_t)n_surv * sizeof(DictEntry) + 64));
     if (!n_surv) return SN_OK;
+    DevBuf &sb = c->pool["surv_b"], &tmp = c->pool["sort_tmp"];
     t_begin(c, "sort");
     CU(sb.alloc(16 * n_surv)); CU(tmp.alloc(radix_sort_tmp_bytes((uint32_t)n_surv)));
-    cudaError_t e = radix_sort<RS_HASH32>(sa.as<uint4>(), sb.as<uint4>(), (uint32_t)n_surv, tmp.p, c->num_sms, c->st);
+    cudaError_t e = radix_sort<RS_HASH32>(surv.as<uint4>(), sb.as<uint4>(), (uint32_t)n_surv, tmp.p, c->num_sms, c->st);
     c->launches += 2 + RsMode<RS_HASH32>::PASSES;
     if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("survivor sort: ") + cudaGetErrorString(e));
-    k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(sa.as<uint4>(), (uint32_t)n_surv, c->dict.as<DictEntry>());
+    k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv.as<uint4>(), (uint32_t)n_surv, c->dict.as<DictEntry>());
     KCHECK("k_make_dict");
     t_end(c, "sort");
     return SN_OK;
@@ -478,77 +421,101 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     int bits = msp_bucket_bits(n_occ);
     if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
     if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
-    if ((r = msp_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, n_occ))) return r;
+    uint64_t n_surv = 0;
+    if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, c->pool["surv_a"], &n_surv))) return r;
+    if ((r = msp_finish_dict(c, c->pool["surv_a"], n_surv))) return r;
     return count_build_index(c);
 }
 
-// ---- multi-GPU: the k-mer stream is range-partitioned by hash over the ranks ---------------
-// owner(k) = (kmer_hash(k) * nparts) >> 32, monotone in the hash, so the per-rank dictionaries
-// concatenated in rank order are globally ordered by (hash, k-mer).  The collectives
-// themselves (one alltoallv of records, one allgather of dictionaries) are issued by the
-// caller on these device buffers (torch.distributed / NCCL in supernova_b200/multigpu.py).
-int sn_mg_partition_records(sn_ctx* c, const sn_params* p, uint32_t nparts, uint64_t* part_counts, void** dev_records)
+// ---- multi-GPU: the super-k-mer stream is range-partitioned by minimizer bucket over the ranks ----
+// owner(bucket) = (bucket * nparts) >> bits, so a rank's buckets are one contiguous range of the
+// bucket-ordered record array.  The collectives themselves (one alltoallv of super-k-mer records
+// plus their per-bucket counts, one allgather of the surviving k-mers) are issued by the caller on
+// these device buffers (torch.distributed / NCCL in supernova_b200/multigpu.py).
+static uint32_t mg_first_bucket(uint32_t owner, uint32_t nparts, int bits) { return (uint32_t)((((uint64_t)owner << bits) + nparts - 1) / nparts); }
+
+int sn_mg_good_lengths(sn_ctx* c, const sn_params* p, uint64_t* n_occ)
 {
-    if (!c || !part_counts || !dev_records || nparts == 0 || nparts > 256) return SN_ERR_ARG;
-    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition_records: no reads loaded");
+    if (!c || !n_occ) return SN_ERR_ARG;
+    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_good_lengths: no reads loaded");
     CU(cudaSetDevice(c->device));
-    int r; uint32_t n_occ = 0;
+    int r;
     if ((r = count_set_params(c, p))) return r;
-    if ((r = count_extract(c, &n_occ))) return r;
-    for (uint32_t i = 0; i < nparts; ++i) part_counts[i] = 0;
-    DevBuf &ka = c->pool["keys_a"], &kb = c->pool["keys_b"], &tmp = c->pool["sort_tmp"];
-    *dev_records = nullptr;
-    if (!n_occ) return SN_OK;
-    CU(kb.alloc((size_t)n_occ * 16));
-    CU(tmp.alloc(radix_sort_tmp_bytes(n_occ)));
-    t_begin(c, "partition");
-    uint32_t hist[256];
-    cudaError_t e = radix_partition_by_owner(ka.as<uint4>(), kb.as<uint4>(), n_occ, nparts, tmp.p, c->num_sms, hist, c->st);
-    c->launches += 3;
-    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("owner partition: ") + cudaGetErrorString(e));
-    t_end(c, "partition");
-    for (uint32_t i = 0; i < nparts; ++i) part_counts[i] = (i + 1 < 256 ? hist[i + 1] : n_occ) - hist[i];
-    part_counts[nparts - 1] = n_occ - hist[nparts - 1];
-    *dev_records = kb.p;
-    return SN_OK;
+    return count_goodlen(c, n_occ);
 }
-void* sn_mg_recv_buffer(sn_ctx* c, uint64_t n_records)
+int sn_mg_partition(sn_ctx* c, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts)
 {
-    if (!c) return nullptr;
-    cudaSetDevice(c->device);
-    DevBuf& ka = c->pool["keys_a"];
-    if (ka.alloc((size_t)std::max<uint64_t>(n_records, 1) * 16) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
-    return ka.p;
-}
-int sn_mg_count_received(sn_ctx* c, uint64_t n_records, uint64_t* n_kmers, void** dev_dict)
-{
-    if (!c || !n_kmers || !dev_dict) return SN_ERR_ARG;
-    if (n_records >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 received records");
+    if (!c || !part_records || !dev_records || !dev_counts || nparts == 0 || bits < 1 || bits > 24 || nparts > (1u << bits)) return SN_ERR_ARG;
+    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition: no reads loaded");
     CU(cudaSetDevice(c->device));
-    int r = count_sort_reduce(c, (uint32_t)n_records);
+    uint64_t n_sk = 0;
+    int r = msp_partition(c, bits, &n_sk);
     if (r) return r;
+    const uint64_t* off = c->pool["sk_off"].as<uint64_t>();
+    std::vector<uint64_t> cut(nparts + 1);
+    for (uint32_t o = 0; o <= nparts; ++o) CU(cudaMemcpyAsync(&cut[o], off + mg_first_bucket(o, nparts, bits), 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
-    *n_kmers = c->cnt.n_kmers; *dev_dict = c->dict.p;
+    for (uint32_t o = 0; o < nparts; ++o) part_records[o] = cut[o + 1] - cut[o];
+    *dev_records = c->pool["sk_recs"].p;
+    *dev_counts = c->pool["sk_hist"].p;           // after the scatter the per-bucket cursors equal the per-bucket counts
     return SN_OK;
 }
-void* sn_mg_dictionary_buffer(sn_ctx* c, uint64_t n_total)
+void* sn_mg_recv_records(sn_ctx* c, uint64_t n_records)
 {
     if (!c) return nullptr;
     cudaSetDevice(c->device);
-    DevBuf& full = c->pool["dict_full"];
-    if (full.alloc((size_t)n_total * sizeof(DictEntry) + 64) != cudaSuccess) { c->err = "cannot allocate the gathered dictionary"; return nullptr; }
-    return full.p;
+    DevBuf& b = c->pool["mg_recs"];
+    if (b.alloc(std::max<uint64_t>(n_records, 1) * 32 + 64) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
+    return b.p;
 }
-int sn_mg_install_dictionary(sn_ctx* c, uint64_t n_total)
+void* sn_mg_recv_counts(sn_ctx* c, uint64_t n_counts)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    DevBuf& b = c->pool["mg_counts"];
+    if (b.alloc(std::max<uint64_t>(n_counts, 1) * 4) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
+    return b.p;
+}
+int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors)
+{
+    if (!c || !n_survivors || !dev_survivors || !n_seg || !n_buckets) return SN_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    DevBuf &recs = c->pool["mg_recs"], &cnts = c->pool["mg_counts"], &off = c->pool["mg_off"];
+    const uint64_t n_cnt = (uint64_t)n_seg * n_buckets;
+    if (!recs.p || !cnts.p || cnts.bytes < 4 * n_cnt) return fail(c, SN_ERR_STATE, "sn_mg_count_received: receive buffers not set");
+    CU(off.alloc(8 * (n_cnt + 1)));
+    uint64_t total = 0;
+    int r = scan_u32(c, cnts.as<uint32_t>(), n_cnt, off.as<uint64_t>(), &total);
+    if (r) return r;
+    if (total != n_records) return fail(c, SN_ERR_DATA, "received per-bucket counts do not add up to the received records");
+    // k-mer occurrences held by the received records (bounds the survivors)
+    unsigned long long* occ = c->counters.as<unsigned long long>();
+    CU(cudaMemsetAsync(occ + 4, 0, 8, c->st));
+    if (n_records) { k_sum_nk<<<std::min(blocks_for(n_records, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(recs.as<uint4>(), n_records, occ + 4); KCHECK("k_sum_nk"); }
+    unsigned long long h_occ = 0;
+    CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    uint64_t n_surv = 0;
+    if ((r = msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, c->pool["surv_a"], &n_surv))) return r;
+    *n_survivors = n_surv; *dev_survivors = c->pool["surv_a"].p;
+    return SN_OK;
+}
+void* sn_mg_survivor_buffer(sn_ctx* c, uint64_t n_total)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    DevBuf& b = c->pool["surv_g"];
+    if (b.alloc(std::max<uint64_t>(n_total, 1) * 16) != cudaSuccess) { c->err = "cannot allocate the gathered k-mers"; return nullptr; }
+    return b.p;
+}
+int sn_mg_install_survivors(sn_ctx* c, uint64_t n_total)
 {
     if (!c) return SN_ERR_ARG;
-    if (n_total >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers");
     CU(cudaSetDevice(c->device));
-    DevBuf& full = c->pool["dict_full"];
-    if (n_total && (!full.p || full.bytes < n_total * sizeof(DictEntry))) return fail(c, SN_ERR_STATE, "call sn_mg_dictionary_buffer first");
-    CU(c->dict.alloc((size_t)n_total * sizeof(DictEntry) + 64));
-    if (n_total) CU(cudaMemcpyAsync(c->dict.p, full.p, n_total * sizeof(DictEntry), cudaMemcpyDeviceToDevice, c->st));
-    c->cnt.n_kmers = n_total;
+    DevBuf& g = c->pool["surv_g"];
+    if (n_total && (!g.p || g.bytes < 16 * n_total)) return fail(c, SN_ERR_STATE, "call sn_mg_survivor_buffer first");
+    int r = msp_finish_dict(c, g, n_total);
+    if (r) return r;
     return count_build_index(c);
 }
 

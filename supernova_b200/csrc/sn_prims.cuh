@@ -163,8 +163,8 @@ inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out
 // Every pass reads each record once and writes it once.
 // ---------------------------------------------------------------------------
 #define SN_RS_ITEMS 8
-enum { RS_KEY96 = 0, RS_HASH32 = 1, RS_OWNER = 2 };   // RS_OWNER: one pass, digit = owner rank (pass argument = number of ranks)
-template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : (MODE == RS_HASH32 ? 4 : 1); };
+enum { RS_KEY96 = 0, RS_HASH32 = 1 };
+template <int MODE> struct RsMode { static constexpr int PASSES = MODE == RS_KEY96 ? 12 : 4; };
 #define SN_RS_MAX_PASSES 12
 #define SN_RS_MIN_TILE (256 * SN_RS_ITEMS)
 
@@ -173,7 +173,6 @@ template <int MODE>
 __device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
 {
     if (MODE == RS_HASH32) return (rs_hash(k) >> (8 * pass)) & 0xFFu;
-    if (MODE == RS_OWNER) return (uint32_t)(((uint64_t)rs_hash(k) * (uint32_t)pass) >> 32);
     uint32_t w = pass < 4 ? k.z : (pass < 8 ? k.y : k.x);
     return (w >> (8 * (pass & 3))) & 0xFFu;
 }
@@ -193,8 +192,6 @@ __global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ 
             uint32_t h = rs_hash(k);
 #pragma unroll
             for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + ((h >> (8 * p)) & 0xFFu)], 1u);
-        } else if (MODE == RS_OWNER) {
-            atomicAdd(&sh[rs_digit<MODE>(k, arg)], 1u);
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + rs_digit<MODE>(k, p)], 1u);
@@ -365,7 +362,7 @@ inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp
     uint4* src = a; uint4* dst = b;
     for (int p = 0; p < RsMode<MODE>::PASSES; ++p) {
         cudaMemsetAsync(status, 0, (size_t)nt * 256 * 8, st);
-        k_rs_scatter<MODE, THREADS><<<nt, THREADS, sizeof(RsSmem<THREADS>), st>>>(src, dst, n, MODE == RS_OWNER ? arg : p, hist + p * 256, status, counters + p);
+        k_rs_scatter<MODE, THREADS><<<nt, THREADS, sizeof(RsSmem<THREADS>), st>>>(src, dst, n, p, hist + p * 256, status, counters + p);
         uint4* t = src; src = dst; dst = t;
     }
     return cudaGetLastError();
@@ -383,19 +380,4 @@ inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num
     if (e != cudaSuccess) return e;
     return radix_sort_passes<MODE>(a, b, n, tmp, 0, st);
 }
-// One scatter pass that groups the records by owner rank (multi-GPU exchange); b receives the
-// records, host_starts[256] the exclusive start of every owner's range.
-inline cudaError_t radix_partition_by_owner(uint4* a, uint4* b, uint32_t n, uint32_t nparts, void* tmp, int num_sms, uint32_t* host_starts, cudaStream_t st)
-{
-    uint32_t* hist = (uint32_t*)tmp;
-    cudaMemsetAsync(hist, 0, (SN_RS_MAX_PASSES * 256 + 16) * 4, st);
-    k_rs_histogram<RS_OWNER><<<num_sms * 8, 256, 0, st>>>(a, n, hist, (int)nparts);
-    k_rs_scan_hist<<<1, 256, 0, st>>>(hist);
-    cudaError_t e = radix_sort_passes<RS_OWNER>(a, b, n, tmp, (int)nparts, st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(host_starts, hist, 256 * 4, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(st);
-}
-
 }  // namespace sn

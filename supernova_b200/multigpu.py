@@ -2,21 +2,25 @@
 the two collectives SURVEY.md §8(e) asks for.
 
     rank r holds 1/N of the reads
-    1. k-mer records of the local reads, grouped by owner = (hash * N) >> 32    [device]
-    2. ONE alltoallv routes every record to its owner                            [NCCL / NVLink]
-    3. owner sorts, counts, filters -> its slice of the dictionary                [device]
-    4. ONE allgather of the slices (rank order == global (hash, k-mer) order)     [NCCL / NVLink]
-    5. prune / unipath edges / HBV replicated on every rank; ReadPaths of the local reads
+    1. good lengths; the k-mer occurrences of all ranks fix the number of minimizer buckets  [allreduce of one number]
+    2. super-k-mer records of the local reads in bucket order (MSP)                          [device]
+    3. ONE alltoallv routes every record to the owner of its bucket,
+       owner(bucket) = bucket * N >> bits (plus the per-bucket counts of the same ranges)    [NCCL / NVLink]
+    4. owner counts and filters its buckets -> its surviving k-mers                           [device]
+    5. ONE allgather of the survivors; every rank sorts them into the dictionary              [NCCL / NVLink]
+    6. prune / unipath edges / HBV replicated on every rank; ReadPaths of the local reads
 
-The exchange helpers are backend agnostic (NCCL on GPUs, gloo on CPU tensors in the tests).
+A super-k-mer record is 32 bytes for ~14 k-mers, so the exchange moves ~2.3 bytes per k-mer
+occurrence (a k-mer record would be 16).  The exchange helpers are backend agnostic (NCCL on
+GPUs, gloo on CPU tensors in the tests).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-REC_WORDS = 4        # a k-mer record is 4 x u32
-ENTRY_WORDS = 8      # a dictionary entry is 8 x u32
+SK_WORDS = 8         # a super-k-mer record is 8 x u32
+SURV_WORDS = 4       # a surviving k-mer is 4 x u32: w0, w1, w2, count:24 | ctx << 24
 
 
 def kmer_hash(w0, w1, w2):
@@ -34,9 +38,21 @@ def kmer_hash(w0, w1, w2):
     return h
 
 
-def owner_of(h, nparts):
-    """Range partition of the 32-bit hash space: monotone in h."""
-    return ((np.asarray(h, dtype=np.uint64) * np.uint64(nparts)) >> np.uint64(32)).astype(np.int64)
+def bucket_bits(n_occ_total):
+    """python twin of sn::msp_bucket_bits: ~2048 k-mer occurrences per bucket."""
+    b = 4
+    while b < 24 and (int(n_occ_total) >> b) > 2048:
+        b += 1
+    return b
+
+
+def first_bucket(owner, nparts, bits):
+    """owner(bucket) = bucket * nparts >> bits  <=>  owner o holds [first_bucket(o), first_bucket(o+1))."""
+    return ((owner << bits) + nparts - 1) // nparts
+
+
+def owner_of_bucket(bucket, nparts, bits):
+    return (np.asarray(bucket, dtype=np.uint64) * np.uint64(nparts)) >> np.uint64(bits)
 
 
 class _DevArray:
@@ -83,29 +99,43 @@ def build_distributed(ctx, dist, device, params=None, with_paths=False):
     """Runs the hot path for this rank's context; returns the per-rank counts dict."""
     from .api import Params
     params = params or Params()
-    n = dist.get_world_size()
-    send_counts, send_ptr = ctx.mg_partition_records(params, n)
+    n, rank = dist.get_world_size(), dist.get_rank()
+    # 1. good lengths; global number of k-mer occurrences -> bucket bits (equal on every rank)
+    occ = torch.tensor([ctx.mg_good_lengths(params)], dtype=torch.int64, device=device)
+    dist.all_reduce(occ)
+    bits = bucket_bits(int(occ.item()))
+    while (1 << bits) < n:
+        bits += 1
+    # 2. super-k-mers of the local reads, bucket order
+    send_counts, rec_ptr, cnt_ptr = ctx.mg_partition(bits, n)
+    fb = [first_bucket(o, n, bits) for o in range(n + 1)]
+    nbl = fb[rank + 1] - fb[rank]
+    # 3. the alltoallv (records + the per-bucket counts of the same bucket ranges)
     recv_counts = exchange_counts(dist, send_counts, device)
     n_send, n_recv = sum(send_counts), sum(recv_counts)
-    recv_ptr = ctx.mg_recv_buffer(n_recv)
-    send_t = dev_tensor(send_ptr, n_send * REC_WORDS, device)
-    recv_t = dev_tensor(recv_ptr, n_recv * REC_WORDS, device)
-    exchange_records(dist, send_t, send_counts, recv_t, recv_counts, REC_WORDS)
+    send_t = dev_tensor(rec_ptr, n_send * SK_WORDS, device)
+    recv_t = dev_tensor(ctx.mg_recv_records(n_recv), n_recv * SK_WORDS, device)
+    exchange_records(dist, send_t, send_counts, recv_t, recv_counts, SK_WORDS)
+    cnt_send = dev_tensor(cnt_ptr, 1 << bits, device)
+    cnt_recv = dev_tensor(ctx.mg_recv_counts(n * nbl), n * nbl, device)
+    dist.all_to_all_single(cnt_recv, cnt_send, output_split_sizes=[nbl] * n, input_split_sizes=[fb[o + 1] - fb[o] for o in range(n)])
     torch.cuda.synchronize(device)
-    n_k, dict_ptr = ctx.mg_count_received(n_recv)
+    # 4. count + filter of this rank's buckets
+    n_s, surv_ptr = ctx.mg_count_received(n, nbl, n_recv)
+    # 5. the allgather of the surviving k-mers
     sizes_t = torch.zeros(n, dtype=torch.int64, device=device)
-    sizes_t[dist.get_rank()] = n_k
+    sizes_t[rank] = n_s
     dist.all_reduce(sizes_t)
     sizes = [int(x) for x in sizes_t.tolist()]
     total = sum(sizes)
-    full_ptr = ctx.mg_dictionary_buffer(total)
-    full_t = dev_tensor(full_ptr, total * ENTRY_WORDS, device)
-    local_t = dev_tensor(dict_ptr, n_k * ENTRY_WORDS, device)
-    gather_slices(dist, local_t, full_t, sizes, ENTRY_WORDS)
+    full_t = dev_tensor(ctx.mg_survivor_buffer(total), total * SURV_WORDS, device)
+    local_t = dev_tensor(surv_ptr, n_s * SURV_WORDS, device)
+    gather_slices(dist, local_t, full_t, sizes, SURV_WORDS)
     torch.cuda.synchronize(device)
-    ctx.mg_install_dictionary(total)
+    ctx.mg_install_survivors(total)
+    # 6. the graph, replicated
     ctx.build_edges()
     ctx.build_hbv()
     if with_paths:
         ctx.path_reads()
-    return dict(n_send=n_send, n_recv=n_recv, slice=n_k, total=total)
+    return dict(bits=bits, n_send=n_send, n_recv=n_recv, survivors=n_s, total=total)

@@ -73,6 +73,22 @@ uint32_t hs_msp_read(const uint8_t* packed, uint32_t goodlen, int32_t bc, uint32
     return n;
 }
 
+// what k_bucket_count's cursor expands: n super-k-mer records -> their k-mer records
+uint64_t hs_sk_expand(const uint32_t* sk, uint64_t n, uint32_t* out)
+{
+    uint64_t m = 0;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint32_t* w = sk + SN_SK_WORDS * r;
+        for (uint32_t i = 0; i < sk_nk(w[0]); ++i) {
+            Kmer k; uint32_t ctx;
+            sk_occurrence(w, i, &k, &ctx);
+            out[4 * m] = k.w0; out[4 * m + 1] = k.w1; out[4 * m + 2] = k.w2; out[4 * m + 3] = (ctx << 24) | (w[0] & 0xFFFFFFu);
+            ++m;
+        }
+    }
+    return m;
+}
+
 Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted by k-mer */)
 {
     Sim* s = new Sim();

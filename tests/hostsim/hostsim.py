@@ -36,6 +36,8 @@ def lib():
         L.hs_extract_read.restype = C.c_uint32
         L.hs_msp_read.argtypes = [vp, C.c_uint32, C.c_int32, vp, vp, vp, vp]
         L.hs_msp_read.restype = C.c_uint32
+        L.hs_sk_expand.argtypes = [vp, u64, vp]
+        L.hs_sk_expand.restype = u64
         _L = L
     return _L
 

@@ -1,7 +1,7 @@
-"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path -- hash-range ownership,
-the alltoallv of k-mer records and the uneven allgather of dictionary slices
-(supernova_b200/multigpu.py) -- on records produced by the product's own extraction logic run
-on the CPU (tests/hostsim).  The union must equal the oracle's dictionary of all reads."""
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path -- bucket-range ownership,
+the alltoallv of super-k-mer records with their per-bucket counts and the uneven allgather of the
+surviving k-mers (supernova_b200/multigpu.py) -- on records produced by the product's own MSP
+logic run on the CPU (tests/hostsim).  The union must equal the oracle's dictionary of all reads."""
 import os
 import socket
 import sys
@@ -46,12 +46,9 @@ def _reduce_numpy(recs):
     np.maximum.at(mx, gid[pos], bcv[pos])
     valid = (cnt >= 3) & (mx > 0) & (mn != mx)
     k = key[head][valid]
-    out = np.zeros((len(k), 8), np.uint32)
+    out = np.zeros((len(k), 4), np.uint32)
     out[:, :3] = k
     out[:, 3] = np.minimum(cnt[valid], 0xFFFFFF) | (ctx[valid] << 24)
-    out[:, 4] = 0xFFFFFFFF
-    out[:, 6] = ctx[valid]
-    out[:, 7] = h[head][valid]
     return out
 
 
@@ -73,39 +70,56 @@ def _worker(rank, world, port, q):
     o = Oracle(codes, quals, off, bc).stage("count")
     gl = o.good_len()
     pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=1)
-    padded = np.concatenate([pb, np.zeros(32, np.uint8)])
-    buf = np.zeros((256, 4), np.uint32)
-    recs = [np.zeros((0, 4), np.uint32)]
+    padded = np.concatenate([pb, np.zeros(64, np.uint8)])
+    buf = np.zeros((256, 4), np.uint32); bh = np.zeros(256, np.uint32); skb = np.zeros((256, 8), np.uint32); nsk = np.zeros(1, np.uint32)
+    sk = [np.zeros((0, 8), np.uint32)]
     for r in range(lo, hi):
-        m = lib().hs_extract_read(padded.ctypes.data + int(boff[r]), int(gl[r]), int(bc[r]), buf.ctypes.data)
+        m = lib().hs_msp_read(padded.ctypes.data + int(boff[r]), int(gl[r]), int(bc[r]), buf.ctypes.data, bh.ctypes.data, skb.ctypes.data, nsk.ctypes.data)
         if m:
-            recs.append(buf[:m].copy())
-    recs = np.concatenate(recs)
-    # 1. group by owner
-    own = mg.owner_of(mg.kmer_hash(recs[:, 0], recs[:, 1], recs[:, 2]), world)
-    order = np.argsort(own, kind="stable")
-    recs, own = recs[order], own[order]
-    send_counts = np.bincount(own, minlength=world).tolist()
-    # 2. the alltoallv
+            sk.append(skb[:int(nsk[0])].copy())
+    sk = np.concatenate(sk)
+    # 1. bucket order; owner = bucket * world >> bits
+    bits = mg.bucket_bits(o.n_occ)
+    bkt = (sk[:, 1] >> np.uint32(32 - bits)).astype(np.int64)
+    order = np.argsort(bkt, kind="stable")
+    sk, bkt = sk[order], bkt[order]
+    hist = np.bincount(bkt, minlength=1 << bits).astype(np.int32)
+    fb = [mg.first_bucket(w, world, bits) for w in range(world + 1)]
+    assert (mg.owner_of_bucket(bkt, world, bits) == np.searchsorted(np.array(fb[1:]), bkt, side="right")).all()
+    send_counts = [int(hist[fb[w]:fb[w + 1]].sum()) for w in range(world)]
+    nbl = fb[rank + 1] - fb[rank]
+    # 2. the alltoallv: records, and the per-bucket counts of the same bucket ranges
     recv_counts = mg.exchange_counts(dist, send_counts, "cpu")
-    send_t = torch.from_numpy(recs.astype(np.int32).ravel().copy())
-    recv_t = torch.empty(sum(recv_counts) * mg.REC_WORDS, dtype=torch.int32)
-    mg.exchange_records(dist, send_t, send_counts, recv_t, recv_counts, mg.REC_WORDS)
-    got = recv_t.numpy().view(np.uint32).reshape(-1, 4)
-    assert (mg.owner_of(mg.kmer_hash(got[:, 0], got[:, 1], got[:, 2]), world) == rank).all()
-    # 3. this rank's slice
-    sl = _reduce_numpy(got)
+    send_t = torch.from_numpy(sk.astype(np.int32).ravel().copy())
+    recv_t = torch.empty(sum(recv_counts) * mg.SK_WORDS, dtype=torch.int32)
+    mg.exchange_records(dist, send_t, send_counts, recv_t, recv_counts, mg.SK_WORDS)
+    cnt_recv = torch.empty(world * nbl, dtype=torch.int32)
+    dist.all_to_all_single(cnt_recv, torch.from_numpy(hist.copy()), output_split_sizes=[nbl] * world,
+                           input_split_sizes=[fb[w + 1] - fb[w] for w in range(world)])
+    got = recv_t.numpy().view(np.uint32).reshape(-1, 8)
+    gb = (got[:, 1] >> np.uint32(32 - bits)).astype(np.int64)
+    assert ((gb >= fb[rank]) & (gb < fb[rank + 1])).all()
+    # the received counts, scanned segment-major, delimit every (source, bucket) range of the receive buffer
+    off = np.concatenate([[0], np.cumsum(cnt_recv.numpy().astype(np.int64))])
+    assert off[-1] == len(got)
+    for s_ in range(world):
+        for j in (0, nbl // 2, nbl - 1):
+            seg = gb[off[s_ * nbl + j]:off[s_ * nbl + j + 1]]
+            assert (seg == fb[rank] + j).all()
+    # 3. this rank's surviving k-mers
+    krec = np.zeros((int((((got[:, 0] >> 24) & 0x3F) + 1).sum()), 4), np.uint32)
+    m = lib().hs_sk_expand(np.ascontiguousarray(got).ctypes.data, len(got), krec.ctypes.data)
+    assert m == len(krec)
+    sl = _reduce_numpy(krec)
     # 4. the allgather
     sizes_t = torch.zeros(world, dtype=torch.int64)
     sizes_t[rank] = len(sl)
     dist.all_reduce(sizes_t)
     sizes = [int(x) for x in sizes_t.tolist()]
-    full_t = torch.empty(sum(sizes) * mg.ENTRY_WORDS, dtype=torch.int32)
-    mg.gather_slices(dist, torch.from_numpy(sl.astype(np.int32).ravel().copy()), full_t, sizes, mg.ENTRY_WORDS)
-    full = full_t.numpy().view(np.uint32).reshape(-1, 8)
-    # the gathered dictionary is globally ordered by (hash, k-mer) and equals the oracle's
-    hk = full[:, 7].astype(np.uint64)
-    assert (np.diff(hk.astype(np.int64)) >= 0).all()
+    full_t = torch.empty(sum(sizes) * mg.SURV_WORDS, dtype=torch.int32)
+    mg.gather_slices(dist, torch.from_numpy(sl.astype(np.int32).ravel().copy()), full_t, sizes, mg.SURV_WORDS)
+    full = full_t.numpy().view(np.uint32).reshape(-1, 4)
+    # the gathered k-mers are the oracle's dictionary
     ok = o.kmers()
     idx = np.lexsort((full[:, 2], full[:, 1], full[:, 0]))
     res = np.array_equal(full[idx][:, :3], ok[:, :3]) and np.array_equal(full[idx][:, 3], ok[:, 3] | (ok[:, 4] << 24))
@@ -129,16 +143,21 @@ def test_two_rank_exchange_matches_oracle(built):
     assert out[0][2] == out[1][2] > 0
 
 
-def test_owner_is_monotone_and_balanced():
+def test_bucket_ownership_is_a_balanced_range_partition(built):
     sys.path.insert(0, ROOT)
+    import supernova_b200 as sb
     from supernova_b200 import multigpu as mg
-    rng = np.random.default_rng(1)
-    w = rng.integers(0, 2 ** 32, size=(200000, 3), dtype=np.uint64)
-    h = mg.kmer_hash(w[:, 0], w[:, 1], w[:, 2])
-    for n in (1, 2, 3, 8):
-        o = mg.owner_of(h, n)
-        assert o.min() >= 0 and o.max() <= n - 1
-        srt = np.argsort(h)
-        assert (np.diff(o[srt]) >= 0).all()
-        cnt = np.bincount(o, minlength=n)
-        assert cnt.max() < 1.05 * cnt.mean() + 50
+    for n_occ in (0, 1, 2048 << 4, (2048 << 4) + 16, 790_041_546, 1 << 40, 1 << 60):
+        assert sb.lib().sn_msp_bucket_bits(n_occ) == mg.bucket_bits(n_occ)
+    for bits in (4, 10, 19):
+        b = np.arange(1 << bits)
+        for n in (1, 2, 3, 8):
+            o = mg.owner_of_bucket(b, n, bits)
+            assert o.min() == 0 and o.max() == n - 1 and (np.diff(o.astype(np.int64)) >= 0).all()
+            fb = [mg.first_bucket(w, n, bits) for w in range(n + 1)]
+            assert fb[0] == 0 and fb[-1] == 1 << bits
+            for w in range(n):
+                assert (o[fb[w]:fb[w + 1]] == w).all()
+            cnt = np.bincount(o.astype(np.int64), minlength=n)
+            assert cnt.max() - cnt.min() <= 1
+    assert mg.bucket_bits(0) == 4 and mg.bucket_bits(790_041_546) == 19 and mg.bucket_bits(1 << 60) == 24
