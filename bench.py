@@ -39,8 +39,7 @@ WORKLOADS = {
     "C1": (50_000, 10_000, 500, 1234),
 }
 SAMPLE_DIV = 12          # cpu_baseline sample = the workload's generator at 1/12 scale
-SORT_PASSES = 4           # 8-bit digit passes over the 32-bit k-mer hash (sn_prims.cuh RS_HASH32)
-ALG_BYTES_PER_BASE = 24.2  # algorithmic HBM bytes per input base, count+HBV
+ALG_BYTES_PER_BASE = 24.2  # algorithmic HBM bytes per input base, count+HBV (key-sort model)
 
 
 def peaks():
@@ -202,7 +201,7 @@ def main():
     def run_path(with_paths):
         if world == 1:
             ctx.build_read_qgraph48(None, params, with_paths=with_paths, write_files=False)
-        else:       # reads sharded over the ranks: one alltoallv of k-mer records, one allgather of dictionary slices
+        else:       # reads sharded over the ranks: one alltoallv of super-k-mer records, one allgather of surviving k-mers
             from supernova_b200 import multigpu
             multigpu.build_distributed(ctx, dist, dev, params, with_paths=with_paths)
 
@@ -256,17 +255,24 @@ def main():
     e2e = total_gbp * args.steps / (ms_e2e / 1e3)
     peak, peak_src = peaks()
     n_occ = counts["n_kmer_occurrences"]
-    sort_ms = stage.get("sort", 0.0)
-    per_launch_ms = sort_ms / SORT_PASSES if sort_ms else None
-    achieved = (32.0 * n_occ / 1e9) / (per_launch_ms / 1e3) if per_launch_ms else None
-    roof = {"bound": "hbm", "kernel": "k_rs_scatter<RS_HASH32> (one 8-bit digit pass of the 128-bit k-mer record sort; %d launches per step)" % SORT_PASSES,
+    # dominant kernel: k_bucket_count (per-bucket k-mer count in shared memory).  Its algorithmic HBM
+    # bytes per launch: every super-k-mer record read once (32 B) + every surviving k-mer written once
+    # (16 B) -- DESIGN.md §4.  It is bound by instruction issue / shared-memory atomics, not by HBM:
+    # the k-mer occurrences it aggregates (16 B each in a key sort) never reach HBM at all.
+    bc_ms = stage.get("bucket_count", 0.0)
+    alg_bytes = 32 * counts["n_superkmers"] + 16 * counts["n_kmers"]
+    achieved = (alg_bytes / 1e9) / (bc_ms / 1e3) if bc_ms else None
+    roof = {"bound": "hbm", "kernel": "k_bucket_count (one CTA per minimizer bucket: TMA-staged super-k-mers -> shared-memory hash table -> surviving k-mers; 1 launch per step)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "algorithmic_bytes_per_launch": 32 * n_occ, "launch_ms": per_launch_ms, "peak_source": peak_src,
+            "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": bc_ms, "peak_source": peak_src,
+            "kmer_occurrences_per_s": (n_occ / (bc_ms / 1e3)) if bc_ms else None,
+            "equivalent_key_stream_gbs": (16.0 * n_occ / 1e9) / (bc_ms / 1e3) if bc_ms else None,
+            "note": "issue-bound (ncu: profiles/); frac is small by design: the 16-byte k-mer records a sort-based count would stream through HBM stay on chip",
             "pipeline_algorithmic_frac": (ALG_BYTES_PER_BASE * value / world) / peak}
     tr = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("k_rs_scatter_dram_bytes_per_launch")
+            roof["traffic"] = json.load(open(tr)).get("k_bucket_count_dram_bytes_per_launch")
         except Exception:
             pass
     line = {"metric": "Gbp reads/sec through k-mer count + DBG (HBV) build", "value": value, "unit": "Gbp/s", "n_gpus": world,
@@ -274,8 +280,8 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {meta['pairs']} pairs x 2 x {meta['read_len']} bp per GPU, {meta['G']} bp diploid genome, seed {meta['seed']}",
                        "K": 48, "min_qual": 7, "min_freq": 3, "min_bc": 2, "gbp_per_gpu": gbp,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks: reads sharded, k-mer records routed by hash range with one NCCL alltoallv, dictionary slices allgathered, graph replicated",
-                       "l2": "inputs (%.1f GB of k-mer records per step) are larger than L2" % (16 * n_occ / 1e9)},
+                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks: reads sharded, super-k-mers routed by minimizer bucket range with one NCCL alltoallv, surviving k-mers allgathered, graph replicated",
+                       "l2": "inputs per step (%.2f GB of packed reads, %.2f GB of super-k-mer records) are larger than L2" % (h2d_bytes / 1e9, 32 * counts["n_superkmers"] / 1e9)},
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}
     if paths_extra:

@@ -60,6 +60,7 @@ typedef struct sn_counts {
     uint64_t n_edge_bases;
     uint64_t n_hbv_vertices, n_hbv_edges;
     uint64_t n_path_edges;         /* total ReadPath entries                          */
+    uint64_t n_superkmers;         /* super-k-mer records this context counted (MSP)  */
 } sn_counts;
 
 int  sn_ctx_create(sn_ctx** out, int device);

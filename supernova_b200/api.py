@@ -28,7 +28,7 @@ class Params(C.Structure):
 
 class Counts(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_kmer_occurrences", "n_kmers_distinct", "n_kmers",
-                                          "n_edges", "n_edge_bases", "n_hbv_vertices", "n_hbv_edges", "n_path_edges")]
+                                          "n_edges", "n_edge_bases", "n_hbv_vertices", "n_hbv_edges", "n_path_edges", "n_superkmers")]
 
 
 def lib():

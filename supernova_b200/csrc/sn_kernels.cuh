@@ -3,7 +3,7 @@
 //   a2-a5, a14-a15  sn_msp.cuh            super-k-mers by minimizer bucket, per-bucket count + filter,
 //                                         survivors sorted by hash (sn_prims.cuh) into the dictionary
 //   a6  k_build_index, k_prune            dictionary prefix index, adjacency prune
-//   a7  k_classify, k_walk_count, k_circle_count, k_walk_emit, k_fix_offsets, k_pack_edges
+//   a7  k_classify, k_seg_walk, k_end_hop, k_owner_hop, k_seg_emit, k_circle_count, k_edge_form, k_fix_offsets, k_pack_edges
 //   a10-a12 k_path_reads                  ReadPath threading + extension
 // Reference citations live with the per-item logic in sn_kmer.cuh / sn_graph.cuh /
 // sn_path.cuh; this file is thread mapping, staging and memory layout.
@@ -127,17 +127,35 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* _
     DictView d; d.tab = tab; d.idx = idx; d.n = n;
     Link2 l;
     tab[i].ctx = prune_ctx(d, i, &l);
+    tab[i].edge = SN_NULL_EDGE; tab[i].off = 0;        // the edge stage below starts from a clean table (it may be run again)
     cand[i] = l;
 }
 
 // ---------------------------------------------------------------------------
 // a7. unipath edges.  own_n[i] = number of k-mers of the edge that entry i owns
-// (0 = owns none).  Singles own themselves; an edge with >= 2 k-mers is walked from
-// both of its end entries and owned by the end with the smaller index; a circle is
-// owned by its smallest entry.
+// (0 = owns none).  Singles own themselves; an edge with >= 2 k-mers is owned by the one of
+// its two end entries with the smaller index; a circle is owned by its smallest k-mer.
+//
+// An edge is a chain of unipath links, and following a chain is one dependent random load
+// per k-mer: walking a whole edge from its end costs (edge length) x (DRAM latency), and the
+// longest edge alone would set the run time of the stage.  The chains are therefore cut at
+// STOPS -- the edge ends plus every interior k-mer whose index hashes to 0 mod 64:
+//   k_seg_walk   every stop walks to the next stop on each side (~64 steps, all segments in parallel)
+//                and records {next stop, arrival orientation, steps}
+//   k_end_hop    every edge end hops from stop to stop (L/64 steps over a small, L2-resident table)
+//                to the far end -> length and owner of the edge
+//   k_owner_hop  after allocation the owner hops again and leaves {edge, offset, orientation} at
+//                every stop of its edge
+//   k_seg_emit   every stop of an edge writes its own k-mer and the k-mers up to the next stop:
+//                bases into the edge scratch, (edge, offset) into the dictionary
+// Interior k-mers that no edge end reaches are circles (k_circle_count, after the edges above).
 // ---------------------------------------------------------------------------
+#define SN_STOP_SHIFT 26          // interior entry i is a stop iff (i * 0x9E3779B1) >> 26 == 0 (1 in 64)
+__device__ __forceinline__ bool stop_sampled(uint32_t i) { return ((i * 0x9E3779B1u) >> SN_STOP_SHIFT) == 0u; }
+struct Seg { uint32_t next; uint32_t steps_o; };        // next stop (stop id, SN_NO_LINK = none on this side); steps << 1 | arrival orientation
+
 __global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
-                                                  Link2* links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_end)
+                                                  Link2* links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_stop)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -147,30 +165,59 @@ __global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ 
     links[i] = l;
     etype[i] = (uint8_t)t;
     own_n[i] = t == T_SINGLE ? 1u : 0u;
-    is_end[i] = (t == T_END_DOWN || t == T_END_UP) ? 1u : 0u;
+    is_stop[i] = (t == T_END_DOWN || t == T_END_UP || (t == T_INTERIOR && stop_sampled(i))) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) k_scatter_flagged(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ list)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) list[pos[i]] = i;
 }
-__global__ void __launch_bounds__(128) k_walk_count(const Link2* __restrict__ links, const uint32_t* __restrict__ ends, uint32_t n_ends,
-                                                    const uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint8_t* __restrict__ visited)
+// thread per (stop, side): side 0 leaves through the down link, side 1 through the up link
+__global__ void __launch_bounds__(128) k_seg_walk(const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
+                                                  const uint64_t* __restrict__ stop_pos, Seg* __restrict__ segs)
 {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_ends) return;
-    uint32_t i = ends[t], last = i;
-    visited[i] = 1;
-    uint32_t nk = walk_links(links, i, etype[i] == T_END_UP ? 1u : 0u, [&](uint32_t, uint32_t j, uint32_t) { visited[j] = 1; last = j; });
-    if (i <= last) own_n[i] = nk;       // the other end walks the same edge; the smaller index owns it
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_stops) return;
+    const uint32_t s = stops[t >> 1];
+    uint32_t o = t & 1u, cur = s, steps = 0;
+    Seg out; out.next = SN_NO_LINK; out.steps_o = 0;
+    Link2 lk = links[cur];
+    for (;;) {
+        const uint32_t l = o ? lk.y : lk.x;
+        if (l == SN_NO_LINK) break;                       // only at the start: this side of an edge end is closed
+        cur = l >> 1; o = l & 1u; ++steps;
+        lk = links[cur];
+        const uint32_t cont = o ? lk.y : lk.x;
+        if (cont == SN_NO_LINK || stop_sampled(cur) || cur == s) {      // an edge end, a sampled interior, or once around a circle
+            out.next = (uint32_t)stop_pos[cur]; out.steps_o = (steps << 1) | o;
+            break;
+        }
+    }
+    segs[t] = out;
+}
+// thread per stop that is an edge end: hop to the far end of the edge
+__global__ void __launch_bounds__(128) k_end_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ stops, uint32_t n_stops,
+                                                 const uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n)
+{
+    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sid >= n_stops) return;
+    const uint32_t i = stops[sid];
+    const int t = etype[i];
+    if (t != T_END_DOWN && t != T_END_UP) return;
+    uint32_t cur = sid, o = t == T_END_UP ? 1u : 0u, nk = 1;
+    for (;;) {
+        const Seg sg = segs[2 * cur + o];
+        if (sg.next == SN_NO_LINK) break;
+        nk += sg.steps_o >> 1; cur = sg.next; o = sg.steps_o & 1u;
+    }
+    if (i <= stops[cur]) own_n[i] = nk;                  // the other end walks the same edge; the smaller index owns it
 }
 __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const Link2* __restrict__ links, uint32_t n,
-                                                     uint8_t* __restrict__ etype, const uint8_t* __restrict__ visited, uint32_t* __restrict__ own_n,
-                                                     uint32_t* n_circle_members)
+                                                     uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* n_circle_members)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (etype[i] != T_INTERIOR || visited[i]) return;
+    if (etype[i] != T_INTERIOR || tab[i].edge != SN_NULL_EDGE) return;     // on an edge with ends: done
     atomicAdd(n_circle_members, 1u);
     // the walker with the smallest table index completes the loop; the circle is then owned by
     // its smallest K-MER, where canonicalizeCircle (BuildReadQGraph48.cc:375-397) starts it
@@ -178,40 +225,93 @@ __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restric
     uint32_t nk = walk_circle_links(links, i, true, [&](uint32_t, uint32_t j, uint32_t) { Kmer q = entry_kmer(tab[j]); if (q < mk) { mk = q; m = j; } });
     if (nk) { own_n[m] = nk; etype[m] = T_CIRCLE; }
 }
-__global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, uint32_t n, uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
+// counts the interior entries no edge end reached (cheap: one byte + one sector per interior entry)
+__global__ void __launch_bounds__(256) k_count_unreached(const DictEntry* __restrict__ tab, const uint8_t* __restrict__ etype, uint32_t n, uint32_t* count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool u = i < n && etype[i] == T_INTERIOR && tab[i].edge == SN_NULL_EDGE;
+    uint32_t m = __ballot_sync(SN_FULL, u);
+    if (m && lane_id() == 0) atomicAdd(count, (uint32_t)__popc(m));
+}
+// phase 0: every owner so far (singles, edges with ends); phase 1: the circle owners only
+__global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ etype, int circles_only, uint32_t n,
+                                                    uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k = own_n[i];
+    if (circles_only && etype[i] != T_CIRCLE) k = 0;
     ebases[i] = k ? k + (SN_K - 1) : 0u;
     eflag[i] = k ? 1u : 0u;
 }
-// owner walks its edge again: bases (one per byte, walk orientation) into `tmp`, and
-// (edge id, step) into every entry on the edge; then the whole-edge canonical form
-// (EdgeBuilder::addEdge :480-485 / extend :457-464) decides whether the edge is
-// stored reverse-complemented.
-__global__ void __launch_bounds__(128) k_walk_emit(DictEntry* tab, const Link2* __restrict__ links,
-                                                   const uint32_t* __restrict__ owners, uint32_t n_owners, const uint8_t* __restrict__ etype,
-                                                   const uint64_t* __restrict__ base_off, uint8_t* __restrict__ tmp,
-                                                   uint32_t* __restrict__ elen, uint8_t* __restrict__ eflip, uint64_t* __restrict__ etmp_off)
+// thread per edge (owner list): singles and circles are written here in one go (a circle is walked by
+// its owner -- circles are rare); the owner of an edge with ends hops over its stops and leaves
+// {edge, offset, walk orientation} at each for k_seg_emit.
+struct StopInfo { uint32_t edge, off_o; };               // off_o = offset << 1 | orientation
+__global__ void __launch_bounds__(128) k_owner_hop(DictEntry* tab, const Link2* __restrict__ links, const Seg* __restrict__ segs,
+                                                   const uint64_t* __restrict__ stop_pos, const uint32_t* __restrict__ owners, uint32_t n_owners, uint32_t edge0,
+                                                   const uint8_t* __restrict__ etype, const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint64_t base_shift,
+                                                   uint8_t* __restrict__ tmp, uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, StopInfo* __restrict__ sinfo)
 {
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_owners) return;
-    uint32_t i = owners[e];
-    int t = etype[i];
-    uint8_t* s = tmp + base_off[i];
-    Kmer k = entry_kmer(tab[i]);
-    if (t == T_END_UP) k = kmer_rc(k);
-    for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(k, b);
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_owners) return;
+    const uint32_t i = owners[k], e = edge0 + k;
+    const int t = etype[i];
+    const uint32_t nk = own_n[i];
+    const uint64_t boff = base_off[i] + base_shift;
+    elen[e] = nk + SN_K - 1;
+    etmp_off[e] = boff;
+    if (t == T_END_DOWN || t == T_END_UP) {
+        uint32_t cur = (uint32_t)stop_pos[i], o = t == T_END_UP ? 1u : 0u, off = 0;
+        for (;;) {
+            StopInfo si; si.edge = e; si.off_o = (off << 1) | o;
+            sinfo[cur] = si;
+            const Seg sg = segs[2 * cur + o];
+            if (sg.next == SN_NO_LINK) break;
+            off += sg.steps_o >> 1; cur = sg.next; o = sg.steps_o & 1u;
+        }
+        return;
+    }
+    uint8_t* s = tmp + boff;
+    Kmer km = entry_kmer(tab[i]);
+    for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(km, b);
     tab[i].edge = e; tab[i].off = 0;
-    uint32_t nk = 1;
-    auto visit = [&](uint32_t step, uint32_t j, uint32_t o) { s[SN_K - 1 + step] = (uint8_t)step_base(tab[j], o); tab[j].edge = e; tab[j].off = step; };
-    if (t == T_END_DOWN || t == T_END_UP) nk = walk_links(links, i, t == T_END_UP ? 1u : 0u, visit);
-    else if (t == T_CIRCLE) nk = walk_circle_links(links, i, false, visit);
-    uint32_t len = nk + SN_K - 1;
-    elen[e] = len;
-    etmp_off[e] = base_off[i];
-    eflip[e] = seq_form_u8(s, len) == REV ? 1 : 0;
+    if (t == T_CIRCLE)
+        walk_circle_links(links, i, false, [&](uint32_t step, uint32_t j, uint32_t o) { s[SN_K - 1 + step] = (uint8_t)step_base(tab[j], o); tab[j].edge = e; tab[j].off = step; });
+}
+// thread per stop on an edge with ends: its own k-mer, then the k-mers up to (not including) the next stop
+__global__ void __launch_bounds__(128) k_seg_emit(DictEntry* tab, const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
+                                                  const StopInfo* __restrict__ sinfo, const Seg* __restrict__ segs, const uint64_t* __restrict__ etmp_off, uint8_t* __restrict__ tmp)
+{
+    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sid >= n_stops) return;
+    const StopInfo si = sinfo[sid];
+    if (si.edge == SN_NULL_EDGE) return;                  // a stop on a circle
+    uint32_t cur = stops[sid], o = si.off_o & 1u, off = si.off_o >> 1;
+    uint8_t* s = tmp + etmp_off[si.edge];
+    if (off == 0) {                                       // the owner end: all K bases of its k-mer, in walk orientation
+        Kmer km = entry_kmer(tab[cur]);
+        if (o) km = kmer_rc(km);
+        for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(km, b);
+    } else s[SN_K - 1 + off] = (uint8_t)step_base(tab[cur], o);
+    tab[cur].edge = si.edge; tab[cur].off = off;
+    const Seg sg = segs[2 * sid + o];
+    if (sg.next == SN_NO_LINK) return;
+    const uint32_t steps = sg.steps_o >> 1;
+    for (uint32_t k = 1; k < steps; ++k) {
+        const Link2 lk = links[cur];
+        const uint32_t l = o ? lk.y : lk.x;
+        cur = l >> 1; o = l & 1u;
+        s[SN_K - 1 + off + k] = (uint8_t)step_base(tab[cur], o);
+        tab[cur].edge = si.edge; tab[cur].off = off + k;
+    }
+}
+// whole-edge canonical form (EdgeBuilder::addEdge :480-485 / extend :457-464): is the edge stored reverse-complemented?
+__global__ void __launch_bounds__(128) k_edge_form(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
+                                                   uint32_t n_edges, uint8_t* __restrict__ eflip)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges) eflip[e] = seq_form_u8(tmp + etmp_off[e], elen[e]) == REV ? 1 : 0;
 }
 __global__ void __launch_bounds__(256) k_fix_offsets(DictEntry* tab, uint32_t n, const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip)
 {

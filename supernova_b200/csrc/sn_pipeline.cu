@@ -421,6 +421,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     int bits = msp_bucket_bits(n_occ);
     if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
     if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
+    c->cnt.n_superkmers = n_sk;
     uint64_t n_surv = 0;
     if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, c->pool["surv_a"], &n_surv))) return r;
     if ((r = msp_finish_dict(c, c->pool["surv_a"], n_surv))) return r;
@@ -497,6 +498,7 @@ int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t
     CU(cudaStreamSynchronize(c->st));
     uint64_t n_surv = 0;
     if ((r = msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, c->pool["surv_a"], &n_surv))) return r;
+    c->cnt.n_superkmers = n_records;
     *n_survivors = n_surv; *dev_survivors = c->pool["surv_a"].p;
     return SN_OK;
 }
@@ -539,44 +541,78 @@ int sn_build_edges(sn_ctx* c)
     t_end(c, "prune");
 
     t_begin(c, "edges");
-    DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &pos = c->pool["pos"], &list = c->pool["list"], &visited = c->pool["visited"];
-    CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(pos.alloc(8ull * (n + 1))); CU(visited.alloc(n));
-    CU(cudaMemsetAsync(visited.p, 0, n, c->st));
+    DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &stop_pos = c->pool["stop_pos"], &pos = c->pool["pos"],
+           &stops = c->pool["stops"], &owners = c->pool["owners"], &segs = c->pool["segs"], &sinfo = c->pool["sinfo"];
+    CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(stop_pos.alloc(8ull * (n + 1))); CU(pos.alloc(8ull * (n + 1)));
     k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>(), etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_classify");
-    uint64_t n_ends = 0;
-    int r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_ends);
+    // stops = edge ends + sampled interiors; segments between neighbouring stops; ends hop to the far end
+    uint64_t n_stops = 0;
+    int r = scan_u32(c, flag.as<uint32_t>(), n, stop_pos.as<uint64_t>(), &n_stops);
     if (r) return r;
-    if (n_ends) {
-        CU(list.alloc(4 * n_ends));
-        k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
+    CU(stops.alloc(4 * n_stops + 16)); CU(segs.alloc(16 * n_stops + 16)); CU(sinfo.alloc(8 * n_stops + 16));
+    if (n_stops) {
+        k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), stop_pos.as<uint64_t>(), n, stops.as<uint32_t>());
         KCHECK("k_scatter_flagged");
-        k_walk_count<<<blocks_for(n_ends, 128), 128, 0, c->st>>>(links.as<Link2>(), list.as<uint32_t>(), (uint32_t)n_ends, etype.as<uint8_t>(),
-            own_n.as<uint32_t>(), visited.as<uint8_t>());
-        KCHECK("k_walk_count");
+        CU(cudaMemsetAsync(sinfo.p, 0xFF, 8 * n_stops, c->st));
+        k_seg_walk<<<blocks_for(2 * n_stops, 128), 128, 0, c->st>>>(links.as<Link2>(), stops.as<uint32_t>(), (uint32_t)n_stops, stop_pos.as<uint64_t>(), segs.as<Seg>());
+        KCHECK("k_seg_walk");
+        k_end_hop<<<blocks_for(n_stops, 128), 128, 0, c->st>>>(segs.as<Seg>(), stops.as<uint32_t>(), (uint32_t)n_stops, etype.as<uint8_t>(), own_n.as<uint32_t>());
+        KCHECK("k_end_hop");
     }
-    uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
-    CU(cudaMemsetAsync(u32c + 4, 0, 4, c->st));
-    k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), n, etype.as<uint8_t>(), visited.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
-    KCHECK("k_circle_count");
-    // allocation: bases per owner -> offsets in the unpacked scratch; owner rank -> edge id
+    // allocation, first the singles and the edges with ends: bases per owner -> offsets in the
+    // unpacked scratch; owner rank -> edge id
     DevBuf &ebases_u32 = c->pool["ebases_u32"], &base_off = c->pool["base_off"];
     CU(ebases_u32.alloc(4ull * n)); CU(base_off.alloc(8ull * (n + 1)));
-    k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), n, ebases_u32.as<uint32_t>(), flag.as<uint32_t>());
+    k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), etype.as<uint8_t>(), 0, n, ebases_u32.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_edge_sizes");
     uint64_t total_bases = 0, n_edges = 0;
     if ((r = scan_u32(c, ebases_u32.as<uint32_t>(), n, base_off.as<uint64_t>(), &total_bases))) return r;
     if ((r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_edges))) return r;
-    if (n_edges >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
-    CU(list.alloc(4 * n_edges + 16));
-    k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, list.as<uint32_t>());
-    KCHECK("k_scatter_flagged");
+    // every k-mer sits on exactly one edge: what the edges so far do not hold lies on circles
+    const uint64_t n_unreached = (uint64_t)n - (total_bases - (uint64_t)(SN_K - 1) * n_edges);
+    const uint64_t edge_cap = n_edges + n_unreached;
+    if (edge_cap >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
+    CU(owners.alloc(4 * edge_cap + 16));
     DevBuf &tmpb = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"], &ebytes = c->pool["ebytes"];
-    CU(tmpb.alloc(total_bases + 16)); CU(eflip.alloc(n_edges + 16)); CU(etmp_off.alloc(8 * n_edges + 16)); CU(ebytes.alloc(4 * n_edges + 16));
-    CU(c->elen.alloc(4 * n_edges + 16)); CU(c->eoff.alloc(8 * (n_edges + 1)));
-    k_walk_emit<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), list.as<uint32_t>(), (uint32_t)n_edges, etype.as<uint8_t>(),
-        base_off.as<uint64_t>(), tmpb.as<uint8_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(), etmp_off.as<uint64_t>());
-    KCHECK("k_walk_emit");
+    CU(tmpb.alloc(total_bases + n_unreached * SN_K + 16)); CU(eflip.alloc(edge_cap + 16)); CU(etmp_off.alloc(8 * edge_cap + 16)); CU(ebytes.alloc(4 * edge_cap + 16));
+    CU(c->elen.alloc(4 * edge_cap + 16)); CU(c->eoff.alloc(8 * (edge_cap + 1)));
+    if (n_edges) {
+        k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, owners.as<uint32_t>());
+        KCHECK("k_scatter_flagged");
+        k_owner_hop<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), segs.as<Seg>(), stop_pos.as<uint64_t>(), owners.as<uint32_t>(), (uint32_t)n_edges, 0u,
+            etype.as<uint8_t>(), own_n.as<uint32_t>(), base_off.as<uint64_t>(), 0ull, tmpb.as<uint8_t>(), c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>());
+        KCHECK("k_owner_hop");
+        if (n_stops) {
+            k_seg_emit<<<blocks_for(n_stops, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), stops.as<uint32_t>(), (uint32_t)n_stops, sinfo.as<StopInfo>(), segs.as<Seg>(),
+                etmp_off.as<uint64_t>(), tmpb.as<uint8_t>());
+            KCHECK("k_seg_emit");
+        }
+    }
+    if (n_unreached) {
+        // circles (simpleCircle / canonicalizeCircle, BuildReadQGraph48.cc:348-397): rare; numbered after the edges above
+        uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
+        CU(cudaMemsetAsync(u32c + 4, 0, 4, c->st));
+        k_circle_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), n, etype.as<uint8_t>(), own_n.as<uint32_t>(), u32c + 4);
+        KCHECK("k_circle_count");
+        k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), etype.as<uint8_t>(), 1, n, ebases_u32.as<uint32_t>(), flag.as<uint32_t>());
+        KCHECK("k_edge_sizes");
+        uint64_t circle_bases = 0, n_circles = 0;
+        if ((r = scan_u32(c, ebases_u32.as<uint32_t>(), n, base_off.as<uint64_t>(), &circle_bases))) return r;
+        if ((r = scan_u32(c, flag.as<uint32_t>(), n, pos.as<uint64_t>(), &n_circles))) return r;
+        if (n_circles > n_unreached || circle_bases > n_unreached * SN_K) return fail(c, SN_ERR_DATA, "circle stage: inconsistent sizes");
+        if (n_circles) {
+            k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(flag.as<uint32_t>(), pos.as<uint64_t>(), n, owners.as<uint32_t>() + n_edges);
+            KCHECK("k_scatter_flagged");
+            k_owner_hop<<<blocks_for(n_circles, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), segs.as<Seg>(), stop_pos.as<uint64_t>(), owners.as<uint32_t>() + n_edges,
+                (uint32_t)n_circles, (uint32_t)n_edges, etype.as<uint8_t>(), own_n.as<uint32_t>(), base_off.as<uint64_t>(), total_bases, tmpb.as<uint8_t>(),
+                c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>());
+            KCHECK("k_owner_hop");
+        }
+        total_bases += circle_bases; n_edges += n_circles;
+    }
+    k_edge_form<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(tmpb.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), (uint32_t)n_edges, eflip.as<uint8_t>());
+    KCHECK("k_edge_form");
     k_fix_offsets<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, n, c->elen.as<uint32_t>(), eflip.as<uint8_t>());
     KCHECK("k_fix_offsets");
     k_edge_bytes<<<blocks_for(n_edges, 256), 256, 0, c->st>>>(c->elen.as<uint32_t>(), (uint32_t)n_edges, ebytes.as<uint32_t>());
