@@ -114,7 +114,7 @@ SN_HD uint32_t kmer_hash(const Kmer& k)
 // Dictionary entry (32 B = one DRAM sector).  The valid-k-mer table doubles as the
 // reference's KmerDict (kmers/ReadPather.h:222-388).  It is ordered by (hash, k-mer); a
 // prefix index over the top SN_IDX_BITS bits of the hash turns a lookup into one index load
-// plus a short binary search.  w0..w2 + cc (count:24 | ctx<<24, == the kmers.kvec KDef word,
+// plus an interpolated probe (dict_find_canonical).  w0..w2 + cc (count:24 | ctx<<24, == the kmers.kvec KDef word,
 // context BEFORE recomputeAdjacencies) and h are immutable after counting; ctx (after
 // pruning), edge and off are filled by the graph stages.
 struct __attribute__((aligned(32))) DictEntry {
@@ -139,17 +139,26 @@ SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
     if (k.w2 != e.w2) return k.w2 < e.w2 ? -1 : 1;
     return 0;
 }
-// KmerDict::findEntryCanonical : returns index or SN_NULL_EDGE
+// KmerDict::findEntryCanonical : returns index or SN_NULL_EDGE.
+// The table is sorted by a uniform hash, so inside the bucket of the top SN_IDX_BITS bits the
+// position of h is close to where its remaining bits interpolate: the search starts there and
+// walks a step or two.  A random DRAM access moves a whole 128-byte line (4 entries), and the
+// small prefix index stays L2-resident, so a lookup costs little more than one line.
 SN_HD uint32_t dict_find_canonical(const DictView& d, const Kmer& k)
 {
-    uint32_t h = kmer_hash(k);
-    uint32_t b = h >> (32 - SN_IDX_BITS);
-    uint32_t lo = d.idx[b], hi = d.idx[b + 1];
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        int c = dict_cmp(h, k, d.tab[mid]);
-        if (c == 0) return mid;
-        if (c > 0) lo = mid + 1; else hi = mid;
+    const uint32_t h = kmer_hash(k);
+    const uint32_t b = h >> (32 - SN_IDX_BITS);
+    const uint32_t lo = d.idx[b], hi = d.idx[b + 1];
+    if (lo >= hi) return SN_NULL_EDGE;
+    const uint32_t rem = h & ((1u << (32 - SN_IDX_BITS)) - 1u);
+    uint32_t i = lo + (uint32_t)(((uint64_t)rem * (hi - lo)) >> (32 - SN_IDX_BITS));      // < hi
+    if (d.tab[i].h < h) { do ++i; while (i < hi && d.tab[i].h < h); }
+    else while (i > lo && d.tab[i - 1].h >= h) --i;
+    // i = first entry of the bucket with hash >= h; equal hashes are ordered by k-mer
+    for (; i < hi; ++i) {
+        const int c = dict_cmp(h, k, d.tab[i]);
+        if (c == 0) return i;
+        if (c < 0) break;
     }
     return SN_NULL_EDGE;
 }
