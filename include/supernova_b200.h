@@ -133,10 +133,12 @@ int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* p
  *   3. caller: alltoallv of the records into sn_mg_recv_records(total received) and of the
  *      per-bucket counts of each owner's bucket range into sn_mg_recv_counts(nparts * range).
  *   4. sn_mg_count_received: per-bucket count + filter of the received records (n_seg = nparts
- *      source segments, n_buckets = this rank's bucket range) -> its surviving k-mers
- *      (*dev_survivors, 16 bytes each: w0,w1,w2,count:24|ctx<<24, DEVICE).
- *   5. caller: allgather of the survivors into sn_mg_survivor_buffer(total).
- *   6. sn_mg_install_survivors: sorts the gathered k-mers into the dictionary;
+ *      source segments, n_buckets = this rank's bucket range) -> its surviving k-mers in (bucket,
+ *      hash, k-mer) order (*dev_survivors, 16 bytes each: w0,w1,w2,count:24|ctx<<24, DEVICE) and
+ *      how many each bucket kept (*dev_bucket_counts, u32[n_buckets], DEVICE).
+ *   5. caller: allgather, in rank order, of the survivors into sn_mg_survivor_buffer(total) and of
+ *      the bucket counts into sn_mg_bucket_count_buffer(bits) -- rank order is bucket order.
+ *   6. sn_mg_install_survivors: the gathered k-mers become the dictionary (no sort needed);
  *      sn_build_edges / sn_build_hbv / sn_path_reads then run as on one GPU (graph replicated,
  *      reads stay sharded).                                                                    */
 int   sn_msp_bucket_bits(uint64_t n_occ_total);
@@ -144,13 +146,15 @@ int   sn_mg_good_lengths(sn_ctx* ctx, const sn_params* params, uint64_t* n_occ);
 int   sn_mg_partition(sn_ctx* ctx, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts);
 void* sn_mg_recv_records(sn_ctx* ctx, uint64_t n_records);
 void* sn_mg_recv_counts(sn_ctx* ctx, uint64_t n_counts);
-int   sn_mg_count_received(sn_ctx* ctx, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors);
+int   sn_mg_count_received(sn_ctx* ctx, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors,
+                           void** dev_survivors, void** dev_bucket_counts);
 void* sn_mg_survivor_buffer(sn_ctx* ctx, uint64_t n_total);
-int   sn_mg_install_survivors(sn_ctx* ctx, uint64_t n_total);
+void* sn_mg_bucket_count_buffer(sn_ctx* ctx, int bits);
+int   sn_mg_install_survivors(sn_ctx* ctx, uint64_t n_total, int bits);
 
 /* ---- measurement ------------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) of the most recent run of a stage or
- * kernel group, in milliseconds; names: "h2d","goodlen","msp_hist","msp_scatter","bucket_count","sort","index",
+ * kernel group, in milliseconds; names: "h2d","goodlen","msp_hist","msp_scatter","bucket_count","make_dict",
  * "prune","edges","hbv_dev","hbv_host","hbv_csr","path".  Returns a negative value for an unknown name.          */
 double sn_stage_ms(const sn_ctx* ctx, const char* name);
 /* number of kernel launches issued by this context so far */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "extract", "partition", "sort_hist", "sort", "reduce", "index", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
+STAGES = ("h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
 
 
 class SnError(RuntimeError):
@@ -81,8 +81,10 @@ def lib():
         for f in ("sn_mg_recv_records", "sn_mg_recv_counts", "sn_mg_survivor_buffer"):
             getattr(L, f).argtypes = [vp, u64]
             getattr(L, f).restype = vp
-        L.sn_mg_count_received.argtypes = [vp, C.c_uint32, C.c_uint32, u64, C.POINTER(u64), C.POINTER(vp)]
-        L.sn_mg_install_survivors.argtypes = [vp, u64]
+        L.sn_mg_bucket_count_buffer.argtypes = [vp, i32]
+        L.sn_mg_bucket_count_buffer.restype = vp
+        L.sn_mg_count_received.argtypes = [vp, C.c_uint32, C.c_uint32, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
+        L.sn_mg_install_survivors.argtypes = [vp, u64, i32]
         _LIB = L
     return _LIB
 
@@ -242,15 +244,18 @@ class Context:
 
     def mg_count_received(self, n_seg, n_buckets, n_records):
         ns = C.c_uint64()
-        ptr = C.c_void_p()
-        self._ck(self.L.sn_mg_count_received(self.h, n_seg, n_buckets, n_records, C.byref(ns), C.byref(ptr)))
-        return int(ns.value), int(ptr.value or 0)
+        ptr, cnt = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.sn_mg_count_received(self.h, n_seg, n_buckets, n_records, C.byref(ns), C.byref(ptr), C.byref(cnt)))
+        return int(ns.value), int(ptr.value or 0), int(cnt.value or 0)
 
     def mg_survivor_buffer(self, n_total):
         return self._mg_buf("sn_mg_survivor_buffer", n_total)
 
-    def mg_install_survivors(self, n_total):
-        self._ck(self.L.sn_mg_install_survivors(self.h, n_total))
+    def mg_bucket_count_buffer(self, bits):
+        return self._mg_buf("sn_mg_bucket_count_buffer", bits)
+
+    def mg_install_survivors(self, n_total, bits):
+        self._ck(self.L.sn_mg_install_survivors(self.h, n_total, bits))
 
     # ---- results ----------------------------------------------------------------------
     def counts(self):

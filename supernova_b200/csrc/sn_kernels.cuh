@@ -2,7 +2,7 @@
 //   a1  k_pqvec_goodlen / k_q8_goodlen   PQVec decode + good-length scan
 //   a2-a5, a14-a15  sn_msp.cuh            super-k-mers by minimizer bucket, per-bucket count + filter,
 //                                         survivors sorted by hash (sn_prims.cuh) into the dictionary
-//   a6  k_build_index, k_prune            dictionary prefix index, adjacency prune
+//   a6  k_prune                           adjacency prune
 //   a7  k_classify, k_seg_walk, k_end_hop, k_owner_hop, k_seg_emit, k_circle_count, k_edge_form, k_fix_offsets, k_pack_edges
 //   a10-a12 k_path_reads                  ReadPath threading + extension
 // Reference citations live with the per-item logic in sn_kmer.cuh / sn_graph.cuh /
@@ -108,23 +108,13 @@ __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint
 __device__ __forceinline__ bool same_kmer(const uint4& a, const uint4& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
 // ---------------------------------------------------------------------------
-// a6. dictionary prefix index + recomputeAdjacencies
+// a6. recomputeAdjacencies
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build_index(const DictEntry* __restrict__ tab, uint32_t n, uint32_t* __restrict__ idx)
-{
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > (1u << SN_IDX_BITS)) return;
-    if (b == (1u << SN_IDX_BITS)) { idx[b] = n; return; }
-    uint32_t key = b << (32 - SN_IDX_BITS);
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (tab[mid].h < key) lo = mid + 1; else hi = mid; }
-    idx[b] = lo;
-}
-__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* __restrict__ idx, uint32_t n, Link2* __restrict__ cand)
+__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2* __restrict__ cand)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = d.n;
     if (i >= n) return;
-    DictView d; d.tab = tab; d.idx = idx; d.n = n;
     Link2 l;
     tab[i].ctx = prune_ctx(d, i, &l);
     tab[i].edge = SN_NULL_EDGE; tab[i].off = 0;        // the edge stage below starts from a clean table (it may be run again)
@@ -154,12 +144,11 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, const uint32_t* _
 __device__ __forceinline__ bool stop_sampled(uint32_t i) { return ((i * 0x9E3779B1u) >> SN_STOP_SHIFT) == 0u; }
 struct Seg { uint32_t next; uint32_t steps_o; };        // next stop (stop id, SN_NO_LINK = none on this side); steps << 1 | arrival orientation
 
-__global__ void __launch_bounds__(256) k_classify(const DictEntry* __restrict__ tab, const uint32_t* __restrict__ idx, uint32_t n,
+__global__ void __launch_bounds__(256) k_classify(DictView d,
                                                   Link2* links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_stop)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    DictView d; d.tab = tab; d.idx = idx; d.n = n;
+    if (i >= d.n) return;
     Link2 l;
     int t = classify_links(d, i, links[i], &l);          // links[] holds prune's candidates on entry
     links[i] = l;

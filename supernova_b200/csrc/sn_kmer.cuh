@@ -98,10 +98,108 @@ SN_HD Kmer kmer_from_packed(const uint8_t* p, uint64_t pos)
     return k;
 }
 
+// --- minimizers (MSP, lib/tada/src/msp/mod.rs) ---------------------------------------------------
+// The minimizer of a k-mer is the smallest of its W = K-P+1 canonical p-mers under a hashed order;
+// k-mer and reverse complement share it, so it names one bucket for every occurrence of a
+// canonical k-mer (check_consistent_shard, lib/tada/src/kmer/mod.rs:1102-1150).
+#define SN_P 16
+#define SN_W (SN_K - SN_P + 1)          // p-mers per k-mer window
+
+// order of the p-mers: a bijective mix of the canonical 16-mer (equal value <=> equal p-mer)
+SN_HD uint32_t pmer_order(uint32_t canon)
+{
+    uint32_t m = canon * 0x9E3779B1u;
+    m ^= m >> 15; m *= 0x85EBCA77u; m ^= m >> 13;
+    return m;
+}
+// bucket hash of a minimizer: the minimum of W order values is small, so mix again
+SN_HD uint32_t bucket_hash(uint32_t minval)
+{
+    uint32_t h = minval ^ 0x5bd1e995u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// p-mers are kept MSB-first in 32 bits (P = 16): fwd = bases j..j+15, rc = its reverse complement
+SN_HD uint32_t pmer_rc(uint32_t fwd) { return ~rev2(fwd); }
+SN_HD uint32_t pmer_value(uint32_t fwd, uint32_t rc) { return pmer_order(fwd < rc ? fwd : rc); }
+// minimum order value over the W p-mers of a k-mer
+SN_HD uint32_t kmer_minimizer(const Kmer& k)
+{
+    uint32_t fwd = k.w0, rc = pmer_rc(k.w0);
+    uint32_t m = pmer_value(fwd, rc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = SN_P; j < SN_K; ++j) {
+        const uint32_t b = kmer_base(k, j);
+        fwd = (fwd << 2) | b; rc = (rc >> 2) | ((3u - b) << 30);
+        const uint32_t v = pmer_value(fwd, rc);
+        m = v < m ? v : m;
+    }
+    return m;
+}
+// the same, prepared for the 8 neighbours of k: a successor drops the first p-mer and gains one,
+// a predecessor drops the last and gains one
+struct KmerMin { uint32_t min_wo_first, min_wo_last, first_fwd, first_rc, last_fwd, last_rc; };
+SN_HD KmerMin kmer_minimizer_nb(const Kmer& k)
+{
+    KmerMin r;
+    uint32_t fwd = k.w0, rc = pmer_rc(k.w0);
+    r.first_fwd = fwd; r.first_rc = rc;
+    uint32_t v = pmer_value(fwd, rc);
+    r.min_wo_last = v; r.min_wo_first = 0xFFFFFFFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = SN_P; j < SN_K; ++j) {
+        const uint32_t b = kmer_base(k, j);
+        fwd = (fwd << 2) | b; rc = (rc >> 2) | ((3u - b) << 30);
+        v = pmer_value(fwd, rc);
+        r.min_wo_first = v < r.min_wo_first ? v : r.min_wo_first;
+        if (j < SN_K - 1) r.min_wo_last = v < r.min_wo_last ? v : r.min_wo_last;
+    }
+    r.last_fwd = fwd; r.last_rc = rc;
+    return r;
+}
+SN_HD uint32_t succ_minimizer(const KmerMin& m, uint32_t c)
+{ const uint32_t v = pmer_value((m.last_fwd << 2) | c, (m.last_rc >> 2) | ((3u - c) << 30)); return v < m.min_wo_first ? v : m.min_wo_first; }
+SN_HD uint32_t pred_minimizer(const KmerMin& m, uint32_t c)
+{ const uint32_t v = pmer_value((m.first_fwd >> 2) | (c << 30), (m.first_rc << 2) | (3u - c)); return v < m.min_wo_last ? v : m.min_wo_last; }
+
+// minimizer of a k-mer that slides along a sequence one base at a time (read threading): the
+// full pass over the W p-mers is only repeated when the minimum leaves the window
+struct MinState { uint32_t minval; int pos; uint32_t last_fwd, last_rc; };
+SN_HD MinState min_state_init(const Kmer& k)
+{
+    MinState st;
+    uint32_t fwd = k.w0, rc = pmer_rc(k.w0);
+    st.minval = pmer_value(fwd, rc); st.pos = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = SN_P; j < SN_K; ++j) {
+        const uint32_t b = kmer_base(k, j);
+        fwd = (fwd << 2) | b; rc = (rc >> 2) | ((3u - b) << 30);
+        const uint32_t v = pmer_value(fwd, rc);
+        if (v <= st.minval) { st.minval = v; st.pos = j - (SN_P - 1); }
+    }
+    st.last_fwd = fwd; st.last_rc = rc;
+    return st;
+}
+// k = the k-mer after the slide (already holding the new last base c)
+SN_HD void min_state_slide(MinState& st, const Kmer& k, uint32_t c)
+{
+    st.last_fwd = (st.last_fwd << 2) | c; st.last_rc = (st.last_rc >> 2) | ((3u - c) << 30);
+    const uint32_t v = pmer_value(st.last_fwd, st.last_rc);
+    --st.pos;
+    if (v <= st.minval) { st.minval = v; st.pos = SN_W - 1; }
+    else if (st.pos < 0) st = min_state_init(k);
+}
+
 // --- dictionary ------------------------------------------------------------------
-// 32-bit mix of the 96-bit k-mer.  The k-mer stream is SORTED BY THIS HASH (4 radix digit
-// passes instead of 12 for the full key); equal k-mers share a hash, so they land in one run of
-// equal hashes and k_reduce separates the (rare) distinct k-mers that collide inside a run.
+// 32-bit mix of the 96-bit k-mer: orders the k-mers inside a bucket and picks the slot in the
+// shared-memory table of k_bucket_count.
 SN_HD uint32_t kmer_hash(const Kmer& k)
 {
     uint32_t h = k.w0 * 0x9E3779B1u;
@@ -112,22 +210,23 @@ SN_HD uint32_t kmer_hash(const Kmer& k)
 }
 
 // Dictionary entry (32 B = one DRAM sector).  The valid-k-mer table doubles as the
-// reference's KmerDict (kmers/ReadPather.h:222-388).  It is ordered by (hash, k-mer); a
-// prefix index over the top SN_IDX_BITS bits of the hash turns a lookup into one index load
-// plus an interpolated probe (dict_find_canonical).  w0..w2 + cc (count:24 | ctx<<24, == the kmers.kvec KDef word,
-// context BEFORE recomputeAdjacencies) and h are immutable after counting; ctx (after
-// pruning), edge and off are filled by the graph stages.
+// reference's KmerDict (kmers/ReadPather.h:222-388).  It is ordered by (minimizer bucket, hash,
+// k-mer): the order k_bucket_count produces, and the one that keeps the graph stages local --
+// neighbouring k-mers of a read or a unipath share their minimizer ~94% of the time, so a
+// k-mer's neighbours, and the next k-mers of a walk, sit in the same few KB.  w0..w2 + cc
+// (count:24 | ctx<<24, == the kmers.kvec KDef word, context BEFORE recomputeAdjacencies) and h are
+// immutable after counting; ctx (after pruning), edge and off are filled by the graph stages.
 struct __attribute__((aligned(32))) DictEntry {
     uint32_t w0, w1, w2, cc;
     uint32_t edge, off, ctx, h;
 };
 #define SN_NULL_EDGE 0xFFFFFFFFu
-#define SN_IDX_BITS 24        // prefix index over the top bits of the hash
 
 struct DictView {
     const DictEntry* tab;
-    const uint32_t* idx;      // (1<<SN_IDX_BITS)+1 lower bounds by top bits of h
+    const uint32_t* boff;     // (1 << bits) + 1: first entry of every minimizer bucket
     uint32_t n;
+    int bits;
 };
 
 // (h,k) < entry ?  /  == entry ?
@@ -139,19 +238,15 @@ SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
     if (k.w2 != e.w2) return k.w2 < e.w2 ? -1 : 1;
     return 0;
 }
-// KmerDict::findEntryCanonical : returns index or SN_NULL_EDGE.
-// The table is sorted by a uniform hash, so inside the bucket of the top SN_IDX_BITS bits the
-// position of h is close to where its remaining bits interpolate: the search starts there and
-// walks a step or two.  A random DRAM access moves a whole 128-byte line (4 entries), and the
-// small prefix index stays L2-resident, so a lookup costs little more than one line.
-SN_HD uint32_t dict_find_canonical(const DictView& d, const Kmer& k)
+// lookup of a canonical k-mer whose minimizer is known.  Inside the bucket the entries are sorted
+// by a uniform hash, so the search starts where the hash interpolates and walks a step or two.
+SN_HD uint32_t dict_find_in_bucket(const DictView& d, uint32_t minimizer, const Kmer& k)
 {
-    const uint32_t h = kmer_hash(k);
-    const uint32_t b = h >> (32 - SN_IDX_BITS);
-    const uint32_t lo = d.idx[b], hi = d.idx[b + 1];
+    const uint32_t b = bucket_hash(minimizer) >> (32 - d.bits);
+    const uint32_t lo = d.boff[b], hi = d.boff[b + 1];
     if (lo >= hi) return SN_NULL_EDGE;
-    const uint32_t rem = h & ((1u << (32 - SN_IDX_BITS)) - 1u);
-    uint32_t i = lo + (uint32_t)(((uint64_t)rem * (hi - lo)) >> (32 - SN_IDX_BITS));      // < hi
+    const uint32_t h = kmer_hash(k);
+    uint32_t i = lo + (uint32_t)(((uint64_t)h * (hi - lo)) >> 32);      // < hi
     if (d.tab[i].h < h) { do ++i; while (i < hi && d.tab[i].h < h); }
     else while (i > lo && d.tab[i - 1].h >= h) --i;
     // i = first entry of the bucket with hash >= h; equal hashes are ordered by k-mer
@@ -161,6 +256,16 @@ SN_HD uint32_t dict_find_canonical(const DictView& d, const Kmer& k)
         if (c < 0) break;
     }
     return SN_NULL_EDGE;
+}
+// KmerDict::findEntryCanonical : returns index or SN_NULL_EDGE
+SN_HD uint32_t dict_find_canonical(const DictView& d, const Kmer& k) { return dict_find_in_bucket(d, kmer_minimizer(k), k); }
+// the same with the minimizer already known (it is the same for k and its reverse complement)
+SN_HD uint32_t dict_find_min(const DictView& d, const Kmer& k, uint32_t minimizer, bool* was_rc)
+{
+    Kmer r;
+    int f = kmer_form(k, &r);
+    if (was_rc) *was_rc = (f == REV);
+    return dict_find_in_bucket(d, minimizer, f == REV ? r : k);
 }
 // KmerDict::findEntry (kmers/ReadPather.h:238-241): canonicalise, then look up.
 // *was_rc tells whether the stored k-mer is the RC of the query.

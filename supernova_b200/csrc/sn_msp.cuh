@@ -33,24 +33,7 @@
 
 namespace sn {
 
-#define SN_P 16
-#define SN_W (SN_K - SN_P + 1)          // p-mers per k-mer window
 #define SN_SK_WORDS 8
-
-// order of the p-mers: a bijective mix of the canonical 16-mer (equal value <=> equal p-mer)
-SN_HD uint32_t pmer_order(uint32_t canon)
-{
-    uint32_t m = canon * 0x9E3779B1u;
-    m ^= m >> 15; m *= 0x85EBCA77u; m ^= m >> 13;
-    return m;
-}
-// bucket hash of a minimizer: the minimum of W order values is small, so mix again
-SN_HD uint32_t bucket_hash(uint32_t minval)
-{
-    uint32_t h = minval ^ 0x5bd1e995u;
-    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-    return h;
-}
 
 // Cuts the good part [0,gl) of one read into super-k-mers: maximal runs of consecutive k-mers
 // with the same minimizer VALUE (pmer_order is a bijection, so that is the same canonical
@@ -252,13 +235,10 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
 // pass loop).  Survivors leave as 16-byte records
 // {w0,w1,w2, count:24 | ctx << 24} appended to `out` (one global atomic per bucket and round).
 // ---------------------------------------------------------------------------
-#define SN_BC_THREADS 256
-#define SN_BC_SLOTS 2048
-#define SN_BC_CHUNK 256          // records staged per TMA copy
-#define SN_BC_ITEMS 4
-
+template <int SN_BC_THREADS, int SN_BC_SLOTS>
 struct BcSmem {
-    uint4 rec[2 * SN_BC_CHUNK];                 // 8 KB staging
+    static constexpr int SN_BC_CHUNK = SN_BC_THREADS;    // records staged per TMA copy: one per thread in the prefix scan
+    uint4 rec[2 * SN_BC_CHUNK];                 // staging
     uint32_t pref[SN_BC_CHUNK + 1];
     uint32_t tag[SN_BC_SLOTS], k0[SN_BC_SLOTS], k1[SN_BC_SLOTS], k2[SN_BC_SLOTS], cnt[SN_BC_SLOTS], flg[SN_BC_SLOTS], bc0[SN_BC_SLOTS];
     uint16_t list[SN_BC_SLOTS];
@@ -322,14 +302,17 @@ __device__ __forceinline__ void skc_step(SkCursor& c, uint32_t next_base)
     ++c.i; ++c.p;
 }
 
-__global__ void __launch_bounds__(SN_BC_THREADS, 3)
+template <int SN_BC_THREADS, int SN_BC_SLOTS, int SN_BC_ITEMS, int MINB>
+__global__ void __launch_bounds__(SN_BC_THREADS, MINB)
 k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg,
                uint32_t min_freq, uint32_t min_bc, int has_bc,
-               uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor, unsigned long long* n_distinct, uint32_t* err)
+               uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor,
+               uint64_t* __restrict__ seg_base, uint32_t* __restrict__ seg_cnt /* per bucket: where its survivors went; zeroed by the caller */,
+               unsigned long long* n_distinct, uint32_t* err)
 {
-    static_assert(SN_BC_CHUNK == SN_BC_THREADS, "one staged record per thread in the prefix scan");
+    constexpr int SN_BC_CHUNK = SN_BC_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BcSmem& S = *reinterpret_cast<BcSmem*>(smem_raw);
+    BcSmem<SN_BC_THREADS, SN_BC_SLOTS>& S = *reinterpret_cast<BcSmem<SN_BC_THREADS, SN_BC_SLOTS>*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t bkt = blockIdx.x;
     if (bkt >= n_buckets) return;
@@ -346,13 +329,18 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     __syncthreads();
     uint32_t phase = 0;
     const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
-    // A pass takes the k-mers with ((hash >> 16) & (2^depth - 1)) == sub.  If the table overflows
-    // the pass is abandoned and split into its two halves (depth+1: sub, sub | 2^depth); the
-    // passes are walked depth first, so every k-mer is emitted by exactly one successful pass.
-    uint32_t depth = 0, sub = 0;
+    // A pass takes the k-mers whose hash starts with the `depth` bits `sub` (depth 0: all of them).
+    // If the table overflows the pass is abandoned and split into its two halves (depth+1: 2*sub,
+    // 2*sub+1).  The halves are walked depth first, i.e. in increasing hash order, and every pass
+    // leaves its survivors sorted by (hash, k-mer), so the bucket comes out sorted.  A bucket that
+    // fits one pass (the normal case) reserves its output range when the pass is done; a split
+    // bucket walks its passes twice: mode 1 only counts the survivors, then the range is
+    // reserved, mode 2 writes them.
+    uint32_t depth = 0, sub = 0, mode = 0;
+    uint32_t total = 0, run = 0;                      // survivors of the bucket / written so far (mode 2)
+    uint64_t base = 0;                                // the bucket's range in `out`
     for (;;) {
         bool overflowed = false;
-        const uint32_t R = 1u << depth, round = sub;
         for (uint32_t sg = 0; sg < n_seg && !overflowed; ++sg) {
             const uint64_t r0 = bucket_off[(uint64_t)sg * n_buckets + bkt], r1 = bucket_off[(uint64_t)sg * n_buckets + bkt + 1];
             for (uint64_t c0 = r0; c0 < r1 && !overflowed; c0 += SN_BC_CHUNK) {
@@ -397,7 +385,7 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                             uint32_t ctx, nb;
                             skc_get(cur, &key[j], &ctx, &nb);
                             const uint32_t h = kmer_hash(key[j]);
-                            if (((h >> 16) & (R - 1u)) == round) {
+                            if (depth == 0u || (h >> (32u - depth)) == sub) {
                                 tg[j] = h | 1u; slot[j] = h & (SN_BC_SLOTS - 1u);
                                 fl[j] = ctx | cur.ign; bcv[j] = cur.bcv;
                                 st[j] = 1;
@@ -460,62 +448,136 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
                 }
             }
         }
-        {
-            // ---- emission: valid slots -> out; the table is cleaned through the claim list ----
-            const uint32_t nfill = S.fill;
-            uint32_t vmask = 0, nvalid = 0;
-            if (!overflowed) {
-#pragma unroll
-                for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
-                    const uint32_t e = j * SN_BC_THREADS + tid;
-                    if (e < nfill) {
-                        const uint32_t s = S.list[e];
-                        const uint32_t c = S.cnt[s], f = S.flg[s];
-                        const bool enough = min_bc == 0 || (min_bc == 1 ? S.bc0[s] != 0u : (f & 0x200u) != 0u);
-                        if (c >= min_freq && (!has_bc || (f & 0x100u) || enough)) { vmask |= 1u << j; ++nvalid; }
-                    }
-                }
-            }
-            uint32_t xs = nvalid;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, xs, o); if (lane >= (uint32_t)o) xs += y; }
-            if (lane == 31) S.wsum[warp] = xs;
-            __syncthreads();
-            uint32_t wb = 0, tot = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) { const uint32_t v = S.wsum[k]; wb += k < warp ? v : 0u; tot += v; }
-            if (tid == 0) {
-                S.out_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
-                if (!overflowed) S.ndist += nfill;
-            }
-            __syncthreads();
-            const uint64_t obase = S.out_base;
-            const bool fits = obase + tot <= out_cap;
-            if (!fits && tid == 0) atomicOr(err, 1u);
-            uint64_t pos = obase + wb + xs - nvalid;
+        // ---- a pass is over: which of the claimed slots hold valid k-mers? ----
+        const uint32_t nfill = S.fill;
+        uint32_t vmask = 0, nvalid = 0;
+        if (!overflowed) {
 #pragma unroll
             for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) {
                 const uint32_t e = j * SN_BC_THREADS + tid;
                 if (e < nfill) {
                     const uint32_t s = S.list[e];
-                    if (fits && (vmask & (1u << j)))
-                        out[pos++] = make_uint4(S.k0[s], S.k1[s], S.k2[s], min(S.cnt[s], 0xFFFFFFu) | ((S.flg[s] & 0xFFu) << 24));
-                    S.tag[s] = 0;
+                    const uint32_t c = S.cnt[s], f = S.flg[s];
+                    const bool enough = min_bc == 0 || (min_bc == 1 ? S.bc0[s] != 0u : (f & 0x200u) != 0u);
+                    if (c >= min_freq && (!has_bc || (f & 0x100u) || enough)) { vmask |= 1u << j; ++nvalid; }
                 }
             }
-            __syncthreads();
-            if (tid == 0) { S.fill = 0; S.over = 0; }
-            __syncthreads();
         }
+        uint32_t xs = nvalid;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, xs, o); if (lane >= (uint32_t)o) xs += y; }
+        if (lane == 31) S.wsum[warp] = xs;
+        __syncthreads();
+        uint32_t wb = 0, tot = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) { const uint32_t v = S.wsum[k]; wb += k < warp ? v : 0u; tot += v; }
+        if (!overflowed) {
+            if (mode != 2u && tid == 0) S.ndist += nfill;
+            if (mode == 0u) {                                               // the whole bucket in one pass: reserve its range now
+                if (tid == 0) S.out_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
+                __syncthreads();
+                base = S.out_base; total = tot;
+            }
+            if (mode == 1u) total += tot;
+            else if (tot) {
+                // ---- order the pass's survivors by (hash, k-mer) in shared memory and write them ----
+                // The hashes are uniform, so a counting sort on their top bits (SN_BC_THREADS bins) leaves
+                // about one survivor per bin; inside a bin the rank is settled by comparing.
+                // Parked in arrays that are free now: slot list + bin members in the staging buffer,
+                // hashes in the tag array, bin counters in the prefix array.
+                constexpr int NB = SN_BC_THREADS, NB_SHIFT = 32 - (SN_BC_THREADS == 128 ? 7 : (SN_BC_THREADS == 256 ? 8 : 9));
+                constexpr int PER = (SN_BC_SLOTS * 3 / 4 + SN_BC_THREADS - 1) / SN_BC_THREADS;
+                uint16_t* vs = reinterpret_cast<uint16_t*>(S.rec);
+                uint16_t* members = vs + (SN_BC_SLOTS * 3) / 4 + 2;
+                {
+                    uint32_t p = wb + xs - nvalid;
+#pragma unroll
+                    for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j)
+                        if (vmask & (1u << j)) {
+                            const uint32_t s = S.list[j * SN_BC_THREADS + tid];
+                            Kmer k; k.w0 = S.k0[s]; k.w1 = S.k1[s]; k.w2 = S.k2[s];
+                            vs[p] = (uint16_t)s; S.tag[p] = kmer_hash(k); ++p;
+                        }
+                }
+                S.pref[tid] = 0;
+                __syncthreads();
+                uint32_t rin[PER];                                           // arrival order inside the bin
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const uint32_t e = j * SN_BC_THREADS + tid; if (e < tot) rin[j] = atomicAdd(&S.pref[S.tag[e] >> NB_SHIFT], 1u); }
+                __syncthreads();
+                {                                                           // exclusive scan of the NB bin counts (one per thread)
+                    const uint32_t v = S.pref[tid]; uint32_t x = v;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+                    if (lane == 31) S.wsum[warp] = x;
+                    __syncthreads();
+                    uint32_t wbase = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < SN_BC_THREADS / 32; ++k) wbase += k < warp ? S.wsum[k] : 0u;
+                    S.pref[tid] = wbase + x - v;
+                    if (tid == NB - 1) S.pref[NB] = wbase + x;
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const uint32_t e = j * SN_BC_THREADS + tid; if (e < tot) members[S.pref[S.tag[e] >> NB_SHIFT] + rin[j]] = (uint16_t)e; }
+                __syncthreads();
+                const uint64_t obase = base + run;
+                if (obase + tot > out_cap) { if (tid == 0) atomicOr(err, 1u); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < PER; ++j) {
+                        const uint32_t e = j * SN_BC_THREADS + tid;
+                        if (e < tot) {
+                            const uint32_t h = S.tag[e], s = vs[e], bin = h >> NB_SHIFT;
+                            const uint32_t m0 = S.pref[bin], m1 = S.pref[bin + 1];
+                            uint32_t rank = m0;
+                            for (uint32_t m = m0; m < m1; ++m) {
+                                const uint32_t u = members[m];
+                                if (u == e) continue;
+                                const uint32_t hu = S.tag[u];
+                                if (hu < h) ++rank;
+                                else if (hu == h) {                         // same 32-bit hash: the k-mer decides
+                                    const uint32_t su = vs[u];
+                                    const uint32_t a0 = S.k0[su], b0 = S.k0[s], a1 = S.k1[su], b1 = S.k1[s];
+                                    if (a0 != b0 ? a0 < b0 : (a1 != b1 ? a1 < b1 : S.k2[su] < S.k2[s])) ++rank;
+                                }
+                            }
+                            out[obase + rank] = make_uint4(S.k0[s], S.k1[s], S.k2[s], min(S.cnt[s], 0xFFFFFFu) | ((S.flg[s] & 0xFFu) << 24));
+                        }
+                    }
+                }
+                run += tot;
+            }
+            if (mode == 0u) break;
+        }
+        // clean the table through the claim list for the next pass
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SN_BC_SLOTS / SN_BC_THREADS; ++j) { const uint32_t e = j * SN_BC_THREADS + tid; if (e < nfill) S.tag[S.list[e]] = 0; }
+        if (!overflowed) for (uint32_t e = tid; e < tot; e += SN_BC_THREADS) S.tag[e] = 0;      // the survivors' hashes were parked there
+        __syncthreads();
+        if (tid == 0) { S.fill = 0; S.over = 0; }
+        __syncthreads();
         if (overflowed) {
-            if (depth >= 16u) { if (tid == 0) atomicOr(err, 2u); break; }
-            ++depth;                                                        // first half: same sub
+            if (depth >= 20u) { if (tid == 0) atomicOr(err, 2u); total = 0; break; }
+            if (mode == 0u) mode = 1u;
+            ++depth; sub <<= 1;                                             // lower half first
             continue;
         }
-        while (depth > 0u && ((sub >> (depth - 1u)) & 1u)) { --depth; sub &= ~(1u << depth); }   // second halves done: back up
-        if (depth == 0u) break;
-        sub |= 1u << (depth - 1u);                                          // sibling half
+        while (depth > 0u && (sub & 1u)) { --depth; sub >>= 1; }            // upper halves done: back up
+        if (depth == 0u) {
+            if (mode == 2u) break;
+            // every pass counted: reserve the bucket's range, then walk the passes again and write
+            if (tid == 0) S.out_base = total ? atomicAdd(out_cursor, (unsigned long long)total) : 0ull;
+            __syncthreads();
+            base = S.out_base;
+            mode = 2u; run = 0; depth = 1; sub = 0;                          // (the root pass is known to overflow)
+            continue;
+        }
+        sub |= 1u;                                                          // sibling half
     }
-    if (tid == 0 && S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
+    if (tid == 0) {
+        seg_base[bkt] = base; seg_cnt[bkt] = total;
+        if (S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
+    }
 }
 
 // k-mer occurrences held by n records
@@ -527,28 +589,32 @@ __global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, 
     if (lane_id() == 0 && s) atomicAdd(total, s);
 }
 
-// survivors sorted by kmer_hash (stable LSD passes) -> dictionary entries in (hash, k-mer) order:
-// inside a run of equal hash (rare) every record takes the rank of its k-mer.
+// every bucket's survivors from where k_bucket_count left them to their place in bucket order (a warp per bucket)
+__global__ void __launch_bounds__(256) k_gather_survivors(const uint4* __restrict__ scratch, const uint64_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_cnt,
+                                                          const uint64_t* __restrict__ off, uint32_t n_buckets, uint4* __restrict__ surv)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_buckets; b += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t n = seg_cnt[b];
+        const uint4* src = scratch + seg_base[b];
+        uint4* dst = surv + off[b];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+// surviving k-mers (bucket, hash, k-mer order) -> dictionary entries
 __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 r = surv[i];
-    const uint32_t h = rs_hash(r);
-    uint32_t pos = i;
-    const bool tie_prev = i > 0 && rs_hash(surv[i - 1]) == h, tie_next = i + 1 < n && rs_hash(surv[i + 1]) == h;
-    if (tie_prev || tie_next) {
-        uint32_t a = i, b = i + 1;
-        while (a > 0 && rs_hash(surv[a - 1]) == h) --a;
-        while (b < n && rs_hash(surv[b]) == h) ++b;
-        uint32_t rank = 0;
-        for (uint32_t j = a; j < b; ++j) { const uint4 q = surv[j]; if (q.x != r.x ? q.x < r.x : (q.y != r.y ? q.y < r.y : q.z < r.z)) ++rank; }
-        pos = a + rank;
-    }
     DictEntry e;
-    e.w0 = r.x; e.w1 = r.y; e.w2 = r.z; e.cc = r.w; e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = r.w >> 24; e.h = h;
-    dict[pos] = e;
+    e.w0 = r.x; e.w1 = r.y; e.w2 = r.z; e.cc = r.w; e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = r.w >> 24; e.h = rs_hash(r);
+    dict[i] = e;
 }
+__global__ void __launch_bounds__(256) k_narrow_u64(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out)
+{ const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
+__global__ void __launch_bounds__(256) k_diff_u32(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ cnt)
+{ const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) cnt[i] = off[i + 1] - off[i]; }
 
 }  // namespace sn
 #endif

@@ -80,12 +80,15 @@ SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t*
     while (itr != end) {
         Kmer kmer = kmer_from_packed(rd, itr);
         bool was_rc;
-        uint32_t ent = dict_find(d, kmer, &was_rc);
+        MinState ms = min_state_init(kmer);             // the k-mer's minimizer names its dictionary bucket
+        uint32_t ent = dict_find_min(d, kmer, ms.minval, &was_rc);
         if (ent == SN_NULL_EDGE) {
             uint32_t gap = 1, itr2 = itr + SN_K; ++itr;
             while (itr2 != n) {
-                kmer = kmer_succ(kmer, packed_base(rd, itr2)); ++itr2;
-                ent = dict_find(d, kmer, &was_rc);
+                const uint32_t nb = packed_base(rd, itr2);
+                kmer = kmer_succ(kmer, nb); ++itr2;
+                min_state_slide(ms, kmer, nb);
+                ent = dict_find_min(d, kmer, ms.minval, &was_rc);
                 if (ent != SN_NULL_EDGE) break;
                 ++gap; ++itr;
             }

@@ -89,7 +89,8 @@ struct sn_ctx {
     DevBuf bases, boff, len, quals, qoff, bc, pq, pqoff, goodlen;
     bool have_bc = false, have_pq = false;
     // dictionary
-    DevBuf dict, idx;
+    DevBuf dict, dboff;      // dictionary (bucket, hash, k-mer order) and its bucket offsets (2^dict_bits + 1)
+    int dict_bits = 4;
     // edges (device) + host copy
     DevBuf ebases, eoff, elen;
     snh::Edges hedges;
@@ -119,7 +120,7 @@ void t_begin(sn_ctx* c, const char* name)
     if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
     cudaEventRecord(t.a, c->st); t.used = false;
 }
-void t_end(sn_ctx* c, const char* name) { Timer& t = c->timers[name]; cudaEventRecord(t.b, c->st); t.used = true; }
+void t_end(sn_ctx* c, const char* name) { Timer& t = c->timers[name]; if (!t.a) return; cudaEventRecord(t.b, c->st); t.used = true; }
 
 inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
@@ -350,61 +351,82 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
     return SN_OK;
 }
 // a15 / a4 + a5: per-bucket count + filter of bucket-ordered super-k-mer records (n_seg ranges per
-// bucket, see k_bucket_count); the surviving k-mers land, unordered, in `surv`.
+// bucket, see k_bucket_count).  The surviving k-mers land in `surv` ordered by (bucket, hash,
+// k-mer); surv_off[n_buckets + 1] = first survivor of every bucket.
 // `occ_bound` bounds the k-mer occurrences the records hold.
-static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound, DevBuf& surv, uint64_t* n_surv_out)
+static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound,
+                            DevBuf& surv, DevBuf& surv_off, uint64_t* n_surv_out)
 {
-    unsigned long long* occ = c->counters.as<unsigned long long>();        // [2] distinct, [3] survivor cursor
-    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [3] error flags
+    unsigned long long* occ = c->counters.as<unsigned long long>();        // [2] distinct, [3] scratch cursor
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [3] error flags, [8] bucket ticket
     c->cnt.n_kmers = 0; c->cnt.n_kmers_distinct = 0;
     *n_surv_out = 0;
-    if (!occ_bound) return SN_OK;
+    CU(surv_off.alloc(4ull * (n_buckets + 1)));
+    if (!occ_bound) { CU(cudaMemsetAsync(surv_off.p, 0, 4ull * (n_buckets + 1), c->st)); CU(surv.alloc(64)); return SN_OK; }
     const uint64_t cap = occ_bound / c->params.min_freq + 16;
     if (cap >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 candidate k-mers in one context");
-    CU(surv.alloc(16 * cap));
-    static bool attr_set = false;
-    if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem))); attr_set = true; }
+    DevBuf &scratch = c->pool["surv_scratch"], &seg_base = c->pool["bc_seg_base"], &seg_cnt = c->pool["bc_seg_cnt"], &off64 = c->pool["bc_off64"];
+    CU(surv.alloc(16 * cap)); CU(scratch.alloc(16 * cap)); CU(seg_base.alloc(8ull * n_buckets)); CU(seg_cnt.alloc(4ull * n_buckets)); CU(off64.alloc(8ull * (n_buckets + 1)));
     t_begin(c, "bucket_count");
     CU(cudaMemsetAsync(occ + 2, 0, 16, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
-    k_bucket_count<<<n_buckets, SN_BC_THREADS, sizeof(BcSmem), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0,
-        surv.as<uint4>(), cap, occ + 3, occ + 2, u32c + 3);
+    CU(cudaMemsetAsync(seg_cnt.p, 0, 4ull * n_buckets, c->st));
+    const int variant = getenv("SN_BC_VARIANT") ? atoi(getenv("SN_BC_VARIANT")) : 0;
+#define SN_BC_LAUNCH(T, S, I, M) do { \
+        static bool attr_set = false; \
+        if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem<T, S>))); attr_set = true; } \
+        k_bucket_count<T, S, I, M><<<n_buckets, T, sizeof(BcSmem<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
+            scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3); } while (0)
+    switch (variant) {
+        case 4: SN_BC_LAUNCH(128, 1024, 4, 6); break;
+        case 5: SN_BC_LAUNCH(128, 1024, 2, 8); break;
+        default: SN_BC_LAUNCH(256, 2048, 4, 3); break;
+    }
+#undef SN_BC_LAUNCH
     KCHECK("k_bucket_count");
     t_end(c, "bucket_count");
-    unsigned long long h[2] = {0, 0}; uint32_t h_err = 0;
-    CU(cudaMemcpyAsync(h, occ + 2, 16, cudaMemcpyDeviceToHost, c->st));
+    // the buckets' survivor ranges, in bucket order
+    uint64_t n_surv = 0;
+    int r = scan_u32(c, seg_cnt.as<uint32_t>(), n_buckets, off64.as<uint64_t>(), &n_surv);
+    if (r) return r;
+    unsigned long long h_dist = 0; uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(&h_dist, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(&h_err, u32c + 3, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     if (h_err & 1u) return fail(c, SN_ERR_DATA, "k_bucket_count: more surviving k-mers than occurrences / min_freq (internal error)");
-    if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table after 16 splits (pathological hash collisions)");
-    c->cnt.n_kmers_distinct = h[0];
-    *n_surv_out = h[1];
+    if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table after 20 splits (pathological hash collisions)");
+    t_begin(c, "make_dict");
+    k_gather_survivors<<<std::min(blocks_for((uint64_t)n_buckets * 32, 256), 16u * (unsigned)c->num_sms), 256, 0, c->st>>>(scratch.as<uint4>(), seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(),
+        off64.as<uint64_t>(), n_buckets, surv.as<uint4>());
+    KCHECK("k_gather_survivors");
+    k_narrow_u64<<<blocks_for((uint64_t)n_buckets + 1, 256), 256, 0, c->st>>>(off64.as<uint64_t>(), (uint64_t)n_buckets + 1, surv_off.as<uint32_t>());
+    KCHECK("k_narrow_u64");
+    c->cnt.n_kmers_distinct = h_dist;
+    *n_surv_out = n_surv;
     return SN_OK;
 }
-// the surviving k-mers in `surv`, sorted by hash into c->dict (ordered by (hash, k-mer))
-static int msp_finish_dict(sn_ctx* c, DevBuf& surv, uint64_t n_surv)
+// the surviving k-mers (bucket, hash, k-mer order) become the dictionary; `counts_or_off`: the bucket
+// offsets (is_offsets) or the per-bucket survivor counts of all 2^bits buckets
+static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bits, const uint32_t* counts_or_off, bool is_offsets)
 {
     if (n_surv >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
-    c->cnt.n_kmers = n_surv;
+    const uint64_t nb = 1ull << bits;
+    c->cnt.n_kmers = n_surv; c->dict_bits = bits;
     CU(c->dict.alloc((size_t)n_surv * sizeof(DictEntry) + 64));
-    if (!n_surv) return SN_OK;
-    DevBuf &sb = c->pool["surv_b"], &tmp = c->pool["sort_tmp"];
-    t_begin(c, "sort");
-    CU(sb.alloc(16 * n_surv)); CU(tmp.alloc(radix_sort_tmp_bytes((uint32_t)n_surv)));
-    cudaError_t e = radix_sort<RS_HASH32>(surv.as<uint4>(), sb.as<uint4>(), (uint32_t)n_surv, tmp.p, c->num_sms, c->st);
-    c->launches += 2 + RsMode<RS_HASH32>::PASSES;
-    if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("survivor sort: ") + cudaGetErrorString(e));
-    k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv.as<uint4>(), (uint32_t)n_surv, c->dict.as<DictEntry>());
-    KCHECK("k_make_dict");
-    t_end(c, "sort");
-    return SN_OK;
-}
-static int count_build_index(sn_ctx* c)
-{
-    t_begin(c, "index");
-    CU(c->idx.alloc(((1ull << SN_IDX_BITS) + 1) * 4));
-    k_build_index<<<blocks_for((1ull << SN_IDX_BITS) + 1, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), (uint32_t)c->cnt.n_kmers, c->idx.as<uint32_t>());
-    KCHECK("k_build_index");
-    t_end(c, "index");
+    CU(c->dboff.alloc(4 * (nb + 1)));
+    if (is_offsets) CU(cudaMemcpyAsync(c->dboff.p, counts_or_off, 4 * (nb + 1), cudaMemcpyDeviceToDevice, c->st));
+    else {
+        DevBuf& o64 = c->pool["boff64"];
+        CU(o64.alloc(8 * (nb + 1)));
+        int r = scan_u32(c, counts_or_off, nb, o64.as<uint64_t>(), nullptr);
+        if (r) return r;
+        k_narrow_u64<<<blocks_for(nb + 1, 256), 256, 0, c->st>>>(o64.as<uint64_t>(), nb + 1, c->dboff.as<uint32_t>());
+        KCHECK("k_narrow_u64");
+    }
+    if (n_surv) {
+        k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv, (uint32_t)n_surv, c->dict.as<DictEntry>());
+        KCHECK("k_make_dict");
+    }
+    t_end(c, "make_dict");
     CU(cudaStreamSynchronize(c->st));
     c->stage = 2;
     return SN_OK;
@@ -419,13 +441,14 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if ((r = count_set_params(c, p))) return r;
     if ((r = count_goodlen(c, &n_occ))) return r;
     int bits = msp_bucket_bits(n_occ);
+    if (const char* e = getenv("SN_MSP_OCC")) { int t = atoi(e); if (t >= 64) { bits = 4; while (bits < 24 && (n_occ >> bits) > (uint64_t)t) ++bits; } }
     if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
     if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
     c->cnt.n_superkmers = n_sk;
     uint64_t n_surv = 0;
-    if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, c->pool["surv_a"], &n_surv))) return r;
-    if ((r = msp_finish_dict(c, c->pool["surv_a"], n_surv))) return r;
-    return count_build_index(c);
+    DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
+    if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, surv, surv_off, &n_surv))) return r;
+    return msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true);
 }
 
 // ---- multi-GPU: the super-k-mer stream is range-partitioned by minimizer bucket over the ranks ----
@@ -477,9 +500,9 @@ void* sn_mg_recv_counts(sn_ctx* c, uint64_t n_counts)
     if (b.alloc(std::max<uint64_t>(n_counts, 1) * 4) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
     return b.p;
 }
-int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors)
+int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors, void** dev_bucket_counts)
 {
-    if (!c || !n_survivors || !dev_survivors || !n_seg || !n_buckets) return SN_ERR_ARG;
+    if (!c || !n_survivors || !dev_survivors || !dev_bucket_counts || !n_seg || !n_buckets) return SN_ERR_ARG;
     CU(cudaSetDevice(c->device));
     DevBuf &recs = c->pool["mg_recs"], &cnts = c->pool["mg_counts"], &off = c->pool["mg_off"];
     const uint64_t n_cnt = (uint64_t)n_seg * n_buckets;
@@ -497,9 +520,14 @@ int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t
     CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     uint64_t n_surv = 0;
-    if ((r = msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, c->pool["surv_a"], &n_surv))) return r;
+    DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"], &scnt = c->pool["mg_surv_counts"];
+    if ((r = msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, surv, surv_off, &n_surv))) return r;
+    CU(scnt.alloc(4ull * n_buckets));
+    k_diff_u32<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(surv_off.as<uint32_t>(), n_buckets, scnt.as<uint32_t>());
+    KCHECK("k_diff_u32");
+    CU(cudaStreamSynchronize(c->st));
     c->cnt.n_superkmers = n_records;
-    *n_survivors = n_surv; *dev_survivors = c->pool["surv_a"].p;
+    *n_survivors = n_surv; *dev_survivors = surv.p; *dev_bucket_counts = scnt.p;
     return SN_OK;
 }
 void* sn_mg_survivor_buffer(sn_ctx* c, uint64_t n_total)
@@ -510,15 +538,21 @@ void* sn_mg_survivor_buffer(sn_ctx* c, uint64_t n_total)
     if (b.alloc(std::max<uint64_t>(n_total, 1) * 16) != cudaSuccess) { c->err = "cannot allocate the gathered k-mers"; return nullptr; }
     return b.p;
 }
-int sn_mg_install_survivors(sn_ctx* c, uint64_t n_total)
+void* sn_mg_bucket_count_buffer(sn_ctx* c, int bits)
 {
-    if (!c) return SN_ERR_ARG;
+    if (!c || bits < 1 || bits > 24) return nullptr;
+    cudaSetDevice(c->device);
+    DevBuf& b = c->pool["surv_gcnt"];
+    if (b.alloc(4ull << bits) != cudaSuccess) { c->err = "cannot allocate the gathered bucket counts"; return nullptr; }
+    return b.p;
+}
+int sn_mg_install_survivors(sn_ctx* c, uint64_t n_total, int bits)
+{
+    if (!c || bits < 1 || bits > 24) return SN_ERR_ARG;
     CU(cudaSetDevice(c->device));
-    DevBuf& g = c->pool["surv_g"];
-    if (n_total && (!g.p || g.bytes < 16 * n_total)) return fail(c, SN_ERR_STATE, "call sn_mg_survivor_buffer first");
-    int r = msp_finish_dict(c, g, n_total);
-    if (r) return r;
-    return count_build_index(c);
+    DevBuf &g = c->pool["surv_g"], &gc = c->pool["surv_gcnt"];
+    if ((n_total && (!g.p || g.bytes < 16 * n_total)) || !gc.p || gc.bytes < (4ull << bits)) return fail(c, SN_ERR_STATE, "call sn_mg_survivor_buffer / sn_mg_bucket_count_buffer first");
+    return msp_install_dict(c, g.as<uint4>(), n_total, bits, gc.as<uint32_t>(), false);
 }
 
 // ---------------------------------------------------------------------------
@@ -532,11 +566,11 @@ int sn_build_edges(sn_ctx* c)
     c->hedges = snh::Edges();
     if (!n) { c->hedges.off.assign(1, 0); c->hedges.packed.assign(16, 0); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
-    const uint32_t* idx = c->idx.as<uint32_t>();
+    DictView dv; dv.tab = tab; dv.boff = c->dboff.as<uint32_t>(); dv.n = n; dv.bits = c->dict_bits;
     t_begin(c, "prune");
     DevBuf& links = c->pool["links"];
     CU(links.alloc(8ull * n));
-    k_prune<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>());
+    k_prune<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, dv, links.as<Link2>());
     KCHECK("k_prune");
     t_end(c, "prune");
 
@@ -544,7 +578,7 @@ int sn_build_edges(sn_ctx* c)
     DevBuf &etype = c->pool["etype"], &own_n = c->pool["own_n"], &flag = c->pool["flag"], &stop_pos = c->pool["stop_pos"], &pos = c->pool["pos"],
            &stops = c->pool["stops"], &owners = c->pool["owners"], &segs = c->pool["segs"], &sinfo = c->pool["sinfo"];
     CU(etype.alloc(n)); CU(own_n.alloc(4ull * n)); CU(flag.alloc(4ull * n)); CU(stop_pos.alloc(8ull * (n + 1))); CU(pos.alloc(8ull * (n + 1)));
-    k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, idx, n, links.as<Link2>(), etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
+    k_classify<<<blocks_for(n, 256), 256, 0, c->st>>>(dv, links.as<Link2>(), etype.as<uint8_t>(), own_n.as<uint32_t>(), flag.as<uint32_t>());
     KCHECK("k_classify");
     // stops = edge ends + sampled interiors; segments between neighbouring stops; ends hop to the far end
     uint64_t n_stops = 0;
@@ -803,7 +837,7 @@ int sn_path_reads(sn_ctx* c)
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "sn_path_reads: run sn_build_hbv first");
     CU(cudaSetDevice(c->device));
     const uint64_t n = c->cnt.n_reads;
-    DictView d; d.tab = c->dict.as<DictEntry>(); d.idx = c->idx.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers;
+    DictView d; d.tab = c->dict.as<DictEntry>(); d.boff = c->dboff.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits;
     EdgeStore es; es.bases = c->ebases.as<uint8_t>(); es.off = c->eoff.as<uint64_t>(); es.len = c->elen.as<uint32_t>();
     HbvView h;
     h.fwd_xlat = c->d_fwd.as<int32_t>(); h.rev_xlat = c->d_rev.as<int32_t>();

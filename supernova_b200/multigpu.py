@@ -6,8 +6,9 @@ the two collectives SURVEY.md §8(e) asks for.
     2. super-k-mer records of the local reads in bucket order (MSP)                          [device]
     3. ONE alltoallv routes every record to the owner of its bucket,
        owner(bucket) = bucket * N >> bits (plus the per-bucket counts of the same ranges)    [NCCL / NVLink]
-    4. owner counts and filters its buckets -> its surviving k-mers                           [device]
-    5. ONE allgather of the survivors; every rank sorts them into the dictionary              [NCCL / NVLink]
+    4. owner counts and filters its buckets -> its surviving k-mers, bucket order             [device]
+    5. ONE allgather of the survivors (+ per-bucket counts): rank order is bucket order, so the
+       gathered k-mers ARE the dictionary                                                    [NCCL / NVLink]
     6. prune / unipath edges / HBV replicated on every rank; ReadPaths of the local reads
 
 A super-k-mer record is 32 bytes for ~14 k-mers, so the exchange moves ~2.3 bytes per k-mer
@@ -121,7 +122,7 @@ def build_distributed(ctx, dist, device, params=None, with_paths=False):
     dist.all_to_all_single(cnt_recv, cnt_send, output_split_sizes=[nbl] * n, input_split_sizes=[fb[o + 1] - fb[o] for o in range(n)])
     torch.cuda.synchronize(device)
     # 4. count + filter of this rank's buckets
-    n_s, surv_ptr = ctx.mg_count_received(n, nbl, n_recv)
+    n_s, surv_ptr, scnt_ptr = ctx.mg_count_received(n, nbl, n_recv)
     # 5. the allgather of the surviving k-mers
     sizes_t = torch.zeros(n, dtype=torch.int64, device=device)
     sizes_t[rank] = n_s
@@ -131,8 +132,10 @@ def build_distributed(ctx, dist, device, params=None, with_paths=False):
     full_t = dev_tensor(ctx.mg_survivor_buffer(total), total * SURV_WORDS, device)
     local_t = dev_tensor(surv_ptr, n_s * SURV_WORDS, device)
     gather_slices(dist, local_t, full_t, sizes, SURV_WORDS)
+    gcnt_t = dev_tensor(ctx.mg_bucket_count_buffer(bits), 1 << bits, device)
+    gather_slices(dist, dev_tensor(scnt_ptr, nbl, device), gcnt_t, [fb[o + 1] - fb[o] for o in range(n)], 1)
     torch.cuda.synchronize(device)
-    ctx.mg_install_survivors(total)
+    ctx.mg_install_survivors(total, bits)
     # 6. the graph, replicated
     ctx.build_edges()
     ctx.build_hbv()

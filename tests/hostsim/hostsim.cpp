@@ -19,12 +19,12 @@ using namespace sn;
 struct Sim {
     std::vector<DictEntry> tab;
     std::vector<Link2> cand;
-    std::vector<uint32_t> idx;
+    std::vector<uint32_t> boff; int bits = 4;
     std::vector<uint32_t> perm;      // perm[i] = position in `tab` of the i-th input (k-mer sorted) record
     snh::Edges edges;
     snh::Hbv hbv;
     std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
-    DictView view() const { DictView d; d.tab = tab.data(); d.idx = idx.data(); d.n = (uint32_t)tab.size(); return d; }
+    DictView view() const { DictView d; d.tab = tab.data(); d.boff = boff.data(); d.n = (uint32_t)tab.size(); d.bits = bits; return d; }
 };
 
 extern "C" {
@@ -89,29 +89,28 @@ uint64_t hs_sk_expand(const uint32_t* sk, uint64_t n, uint32_t* out)
     return m;
 }
 
-Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted by k-mer */)
+Sim* hs_new(uint64_t n, const uint32_t* recs /* n x {w0,w1,w2,cc}, sorted by k-mer */, int bits)
 {
     Sim* s = new Sim();
-    // what k_reduce leaves behind: the dictionary in (hash, k-mer) order
-    std::vector<uint32_t> order(n);
-    std::vector<uint32_t> hs(n);
-    for (uint64_t i = 0; i < n; ++i) { Kmer k; k.w0 = recs[4 * i]; k.w1 = recs[4 * i + 1]; k.w2 = recs[4 * i + 2]; hs[i] = kmer_hash(k); order[i] = (uint32_t)i; }
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hs[a] < hs[b]; });
+    s->bits = bits;
+    // what k_bucket_count leaves behind: the dictionary in (minimizer bucket, hash, k-mer) order
+    std::vector<uint32_t> order(n), hs(n), bk(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        Kmer k; k.w0 = recs[4 * i]; k.w1 = recs[4 * i + 1]; k.w2 = recs[4 * i + 2];
+        hs[i] = kmer_hash(k); bk[i] = bucket_hash(kmer_minimizer(k)) >> (32 - bits); order[i] = (uint32_t)i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return bk[a] != bk[b] ? bk[a] < bk[b] : hs[a] < hs[b]; });
     s->tab.resize(n); s->perm.resize(n);
+    s->boff.assign((1u << bits) + 1, 0);
     for (uint64_t p = 0; p < n; ++p) {
         uint64_t i = order[p];
         s->perm[i] = (uint32_t)p;
         DictEntry& e = s->tab[p];
         e.w0 = recs[4 * i]; e.w1 = recs[4 * i + 1]; e.w2 = recs[4 * i + 2]; e.cc = recs[4 * i + 3];
         e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = e.cc >> 24; e.h = hs[i];
+        ++s->boff[bk[i] + 1];
     }
-    s->idx.resize((1u << SN_IDX_BITS) + 1);
-    for (uint32_t b = 0; b <= (1u << SN_IDX_BITS); ++b) {          // k_build_index
-        if (b == (1u << SN_IDX_BITS)) { s->idx[b] = (uint32_t)n; break; }
-        uint32_t key = b << (32 - SN_IDX_BITS), lo = 0, hi = (uint32_t)n;
-        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s->tab[mid].h < key) lo = mid + 1; else hi = mid; }
-        s->idx[b] = lo;
-    }
+    for (uint32_t b = 0; b < (1u << bits); ++b) s->boff[b + 1] += s->boff[b];
     return s;
 }
 void hs_free(Sim* s) { delete s; }

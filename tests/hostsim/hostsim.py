@@ -20,7 +20,7 @@ def lib():
         L = C.CDLL(so)
         vp, u64 = C.c_void_p, C.c_uint64
         L.hs_new.restype = vp
-        L.hs_new.argtypes = [u64, vp]
+        L.hs_new.argtypes = [u64, vp, C.c_int]
         L.hs_free.argtypes = [vp]
         L.hs_prune.argtypes = [vp]
         L.hs_edges.argtypes = [vp]
@@ -43,10 +43,10 @@ def lib():
 
 
 class HostSim:
-    def __init__(self, recs):
+    def __init__(self, recs, bits=10):
         self.recs = np.ascontiguousarray(recs, dtype=np.uint32)
         self.n = len(self.recs)
-        self.h = lib().hs_new(self.n, self.recs.ctypes.data)
+        self.h = lib().hs_new(self.n, self.recs.ctypes.data, bits)
 
     def __del__(self):
         if getattr(self, "h", None):
