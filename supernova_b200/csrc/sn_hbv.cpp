@@ -138,11 +138,10 @@ static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV,
 // their final ids.
 void number_hbv(const HbvComponents& C, GroupRec* groups, ERec* er, uint64_t nE, Hbv& H, unsigned threads)
 {
-    H = Hbv();
     const uint64_t nH = C.n_comp ? C.base_e[C.n_comp] : 0, nV = C.n_comp ? C.base_v[C.n_comp] : 0;
     H.n_vert = (int32_t)nV;
-    H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);
-    H.fwd.assign(nE, -1); H.rev.assign(nE, -1);
+    H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);      // (no reallocation when the caller sized them already)
+    H.fwd.resize(nE); H.rev.resize(nE);
     if (!threads) threads = 1;
     std::atomic<uint64_t> next{0};
     std::atomic<int> bad{0};

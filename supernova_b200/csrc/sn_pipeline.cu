@@ -103,9 +103,29 @@ struct sn_ctx {
     DevBuf counters;     // small scratch of u64 counters
     std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
     std::map<std::string, HostBuf> hpool;    // pinned staging, kept across steps
+    std::map<const void*, size_t> pinned;    // host vectors whose storage is page-locked (result arrays reused across steps)
 };
 
 namespace {
+
+// Result arrays live in std::vectors that keep their storage from step to step; their storage is
+// page-locked once (cudaHostRegister) so that the copies to and from them run at full PCIe speed
+// and asynchronously.  resize_pinned never lets a registered block be freed behind CUDA's back.
+template <class T> void resize_pinned(sn_ctx* c, std::vector<T>& v, size_t n)
+{
+    if (v.capacity() < n) {
+        auto it = c->pinned.find(v.data());
+        if (it != c->pinned.end()) { cudaHostUnregister(const_cast<void*>(it->first)); c->pinned.erase(it); }
+        std::vector<T>().swap(v);
+        v.reserve(n + n / 8 + 16);
+    }
+    v.resize(n);
+    if (v.capacity() && !c->pinned.count(v.data())) {
+        if (cudaHostRegister(v.data(), v.capacity() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) c->pinned[v.data()] = v.capacity() * sizeof(T);
+        else cudaGetLastError();                       // not fatal: the copies fall back to pageable memory
+    }
+}
+void unpin_all(sn_ctx* c) { for (auto& kv : c->pinned) cudaHostUnregister(const_cast<void*>(kv.first)); c->pinned.clear(); }
 
 int fail(sn_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
 
@@ -224,6 +244,7 @@ void sn_ctx_destroy(sn_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     for (auto& kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
+    unpin_all(c);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -563,8 +584,7 @@ int sn_build_edges(sn_ctx* c)
     CU(cudaSetDevice(c->device));
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
-    c->hedges = snh::Edges();
-    if (!n) { c->hedges.off.assign(1, 0); c->hedges.packed.assign(16, 0); c->stage = 3; return SN_OK; }
+    if (!n) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
     DictView dv; dv.tab = tab; dv.boff = c->dboff.as<uint32_t>(); dv.n = n; dv.bits = c->dict_bits;
     t_begin(c, "prune");
@@ -661,7 +681,8 @@ int sn_build_edges(sn_ctx* c)
     t_end(c, "edges");
     // every dictionary entry must now sit on exactly one edge
     c->cnt.n_edges = n_edges; c->cnt.n_edge_bases = total_bases;
-    c->hedges.len.resize(n_edges); c->hedges.off.resize(n_edges + 1); c->hedges.packed.assign(total_bytes + 16, 0);
+    resize_pinned(c, c->hedges.len, n_edges); resize_pinned(c, c->hedges.off, n_edges + 1); resize_pinned(c, c->hedges.packed, total_bytes + 16);
+    memset(c->hedges.packed.data() + total_bytes, 0, 16);
     CU(cudaMemcpyAsync(c->hedges.len.data(), c->elen.p, 4 * n_edges, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->hedges.off.data(), c->eoff.p, 8 * (n_edges + 1), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->hedges.packed.data(), c->ebases.p, total_bytes, cudaMemcpyDeviceToHost, c->st));
@@ -680,11 +701,14 @@ int sn_build_hbv(sn_ctx* c)
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "sn_build_hbv: run sn_build_edges first");
     CU(cudaSetDevice(c->device));
     const uint32_t nE = (uint32_t)c->cnt.n_edges;
-    c->hbv = snh::Hbv();
-    c->hbv.fwd.assign(nE, -1); c->hbv.rev.assign(nE, -1);
-    c->hbv.from_start.assign(1, 0); c->hbv.to_start.assign(1, 0);
     c->cnt.n_hbv_vertices = 0; c->cnt.n_hbv_edges = 0;
-    if (!nE) { c->stage = 4; return SN_OK; }
+    if (!nE) {
+        snh::Hbv& H0 = c->hbv;
+        H0.n_vert = 0; H0.fwd.clear(); H0.rev.clear(); H0.src.clear(); H0.to_left.clear(); H0.to_right.clear(); H0.inv.clear();
+        H0.from_v.clear(); H0.from_e.clear(); H0.to_v.clear(); H0.to_e.clear();
+        H0.from_start.assign(1, 0); H0.to_start.assign(1, 0);
+        c->stage = 4; return SN_OK;
+    }
     if (nE >= (1u << 29)) return fail(c, SN_ERR_ARG, "more than 2^29 unipath edges");
     const uint32_t n4 = 4 * nE, n_items = 2 * nE;
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);        // [6] npal, [7] error flags
@@ -778,6 +802,11 @@ int sn_build_hbv(sn_ctx* c)
     auto t0 = std::chrono::steady_clock::now();
     snh::HbvComponents comps; comps.n_comp = n_comp; comps.start_item = h_cstart; comps.base_v = h_basev; comps.base_e = h_basee;
     static const unsigned hbv_threads = [] { const char* e = getenv("SN_HBV_THREADS"); unsigned n = e ? (unsigned)atoi(e) : std::min(32u, std::thread::hardware_concurrency()); return n ? n : 1u; }();
+    {   // the numbering writes straight into page-locked result arrays
+        snh::Hbv& Hn = c->hbv;
+        resize_pinned(c, Hn.src, tot_h); resize_pinned(c, Hn.to_left, tot_h); resize_pinned(c, Hn.to_right, tot_h);
+        resize_pinned(c, Hn.fwd, nE); resize_pinned(c, Hn.rev, nE);
+    }
     try { snh::number_hbv(comps, h_groups.as<snh::GroupRec>(), h_er.as<snh::ERec>(), nE, c->hbv, hbv_threads); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -812,8 +841,8 @@ int sn_build_hbv(sn_ctx* c)
     k_hbv_inv<<<blocks_for(nE, 256), 256, 0, c->st>>>(c->d_fwd.as<int32_t>(), c->d_rev.as<int32_t>(), nE, dinv.as<int32_t>());
     KCHECK("k_hbv_inv");
     t_end(c, "hbv_csr");
-    H.from_start.resize(nV + 1); H.to_start.resize(nV + 1);
-    H.from_v.resize(nH); H.from_e.resize(nH); H.to_v.resize(nH); H.to_e.resize(nH); H.inv.resize(nH);
+    resize_pinned(c, H.from_start, nV + 1); resize_pinned(c, H.to_start, nV + 1);
+    resize_pinned(c, H.from_v, nH); resize_pinned(c, H.from_e, nH); resize_pinned(c, H.to_v, nH); resize_pinned(c, H.to_e, nH); resize_pinned(c, H.inv, nH);
     CU(cudaMemcpyAsync(H.from_start.data(), c->d_from_start.p, 4ull * (nV + 1), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(H.to_start.data(), c->d_to_start.p, 4ull * (nV + 1), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(H.from_v.data(), c->d_from_v.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
