@@ -132,16 +132,61 @@ static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV,
     }
 }
 
+// The same traversal over the one-line item records the device prepares (product path).  A popped
+// item costs one cache line, and that line was requested when the item was queued: vertex ids,
+// "vertex already expanded" and "item already queued" live in small byte/int arrays that stay
+// cache-resident, so the loop is not a chain of dependent misses even when a component is one long
+// chain of bubbles (queue length 2-4).
+struct NumberState { int32_t* vid; uint8_t* expanded; uint8_t* seen; int32_t* ids; };
+static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& st, uint32_t start, int32_t& nextV, uint32_t& nH,
+                      uint32_t* src, int32_t* to_left, int32_t* to_right, std::vector<uint32_t>& Q)
+{
+    size_t qh = 0, qt = 0;
+    if (Q.size() < 64) Q.resize(64);
+    Q[qt++] = start; st.seen[start] = 1;
+    while (qh < qt) {
+        const uint32_t it = Q[qh++];
+        const ItemRec& r = rec[it];
+        if (r.g1 < 0 || r.g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
+        if (st.vid[r.g1] < 0) st.vid[r.g1] = nextV++;
+        if (st.vid[r.g2] < 0) st.vid[r.g2] = nextV++;
+        const int32_t id = (int32_t)nH++;
+        src[id] = it; to_left[id] = st.vid[r.g1]; to_right[id] = st.vid[r.g2];
+        st.ids[it] = id;
+        if ((r.info >> 8) & 1u) { st.ids[it ^ 1u] = id; st.seen[it ^ 1u] = 1; }
+        if (qt + 24 > Q.size()) {                           // keep the FIFO compact
+            std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
+            if (qt + 24 > Q.size()) Q.resize(2 * Q.size());
+        }
+        for (int side = 0; side < 2; ++side) {
+            const int32_t g = side ? r.g2 : r.g1;
+            if (st.expanded[g]) continue;
+            st.expanded[g] = 1;
+            uint32_t n = (r.info >> (4 * side)) & 15u;
+            const uint32_t* items = side ? r.it2 : r.it1;
+            if (n == 15u) { n = groups[g].n; items = groups[g].items; }          // more than 6 edge ends on this vertex
+            for (uint32_t x = 0; x < n; ++x) {
+                const uint32_t t2 = items[x];
+                if (!st.seen[t2]) { st.seen[t2] = 1; Q[qt++] = t2; __builtin_prefetch(&rec[t2]); }
+            }
+        }
+    }
+}
+
 // The device found the connected components, the item the reference's outer loop
 // (HBVFromEdges.cc:277-285) reaches first in each, and -- from their sizes -- the first vertex and
 // edge id of every component, so the components are numbered independently, in parallel, with
 // their final ids.
-void number_hbv(const HbvComponents& C, GroupRec* groups, ERec* er, uint64_t nE, Hbv& H, unsigned threads)
+void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* groups, uint64_t nV_in, uint64_t nE, Hbv& H, unsigned threads)
 {
     const uint64_t nH = C.n_comp ? C.base_e[C.n_comp] : 0, nV = C.n_comp ? C.base_v[C.n_comp] : 0;
+    if (nV != nV_in) throw std::runtime_error("HBV: component vertex counts do not add up");
     H.n_vert = (int32_t)nV;
     H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);      // (no reallocation when the caller sized them already)
     H.fwd.resize(nE); H.rev.resize(nE);
+    std::vector<int32_t> vid(nV, -1), ids(2 * nE, -1);
+    std::vector<uint8_t> expanded(nV, 0), seen(2 * nE, 0);
+    NumberState st{vid.data(), expanded.data(), seen.data(), ids.data()};
     if (!threads) threads = 1;
     std::atomic<uint64_t> next{0};
     std::atomic<int> bad{0};
@@ -155,7 +200,7 @@ void number_hbv(const HbvComponents& C, GroupRec* groups, ERec* er, uint64_t nE,
                 const uint64_t c1 = std::min<uint64_t>(C.n_comp, c0 + 256);
                 for (uint64_t c = c0; c < c1; ++c) {
                     int32_t nextV = (int32_t)C.base_v[c]; uint32_t nh = (uint32_t)C.base_e[c];
-                    bfs_from(groups, er, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                    bfs_items(items, groups, st, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
                     if ((uint64_t)nextV != C.base_v[c + 1] || (uint64_t)nh != C.base_e[c + 1])
                         throw std::runtime_error("HBV: a component was not numbered completely");
                 }
@@ -169,7 +214,7 @@ void number_hbv(const HbvComponents& C, GroupRec* groups, ERec* er, uint64_t nE,
         for (auto& x : th) x.join();
     }
     if (bad.load()) throw std::runtime_error(what);
-    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { H.fwd[e] = er[2 * e].id; H.rev[e] = er[2 * e + 1].id; } });
+    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { H.fwd[e] = ids[2 * e]; H.rev[e] = ids[2 * e + 1]; } });
 }
 
 // Host-only construction (vertex discovery with a hash table, sequential numbering, adjacency):

@@ -34,6 +34,10 @@ struct Hbv {
 // its two vertices.  On the product path both are produced on the device (sn_hbvdev.cuh).
 struct alignas(64) GroupRec { int32_t vid; uint32_t n; uint32_t items[8]; uint32_t pad[6]; };   // pad[0]: items already pushed
 struct ERec { int32_t g1, g2, id; uint32_t pal; };
+// One oriented unipath with everything the numbering loop needs on ONE cache line: its two
+// vertices and the items (unipath << 1 | rc, EEComp order) of both.  info = n1 | n2 << 4 | pal << 8;
+// a vertex with more than 6 items (n = 15) sends the loop to the vertex records instead.
+struct alignas(64) ItemRec { int32_t g1, g2; uint32_t info; uint32_t it1[6], it2[6]; uint32_t pad; };
 // connected components in the order the reference's outer loop discovers them
 struct HbvComponents {
     uint64_t n_comp = 0;
@@ -43,7 +47,7 @@ struct HbvComponents {
 };
 // numbering (HBVBuilder::processQueue) of all components with `threads` host threads: fills
 // n_vert, src, to_left, to_right, fwd, rev
-void number_hbv(const HbvComponents& comps, GroupRec* groups, ERec* er, uint64_t n_unipaths, Hbv& out, unsigned threads);
+void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads);
 // host-only construction of the whole HBV (tests/hostsim)
 void build_hbv(const Edges& edges, Hbv& out);
 // sequences of the HBV edges (edges_), fastb packing: epacked (padded), eoff[n+1], elen[n]

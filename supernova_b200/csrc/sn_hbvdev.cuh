@@ -88,6 +88,27 @@ __global__ void __launch_bounds__(256) k_hbv_erec(const int32_t* __restrict__ eg
     reinterpret_cast<uint4*>(er)[t] = make_uint4((uint32_t)egrp[4 * e + 2 * rc], (uint32_t)egrp[4 * e + 2 * rc + 1], 0xFFFFFFFFu, pal[e]);
 }
 
+// the numbering loop's record of an oriented unipath: both vertices with their items, one cache line
+__global__ void __launch_bounds__(128) k_hbv_itemrec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, const snh::GroupRec* __restrict__ groups,
+                                                     uint32_t n_items, snh::ItemRec* __restrict__ rec)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const uint32_t e = t >> 1, rc = t & 1u;
+    const int32_t g1 = egrp[4 * e + 2 * rc], g2 = egrp[4 * e + 2 * rc + 1];
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = 0u;
+    w[0] = (uint32_t)g1; w[1] = (uint32_t)g2;
+    uint32_t n1 = 0, n2 = 0;
+    if (g1 >= 0) { const snh::GroupRec& G = groups[g1]; n1 = G.n; if (n1 <= 6) { for (uint32_t i = 0; i < 6; ++i) w[3 + i] = i < n1 ? G.items[i] : 0u; } else n1 = 15; }
+    if (g2 >= 0) { const snh::GroupRec& G = groups[g2]; n2 = G.n; if (n2 <= 6) { for (uint32_t i = 0; i < 6; ++i) w[9 + i] = i < n2 ? G.items[i] : 0u; } else n2 = 15; }
+    w[2] = n1 | (n2 << 4) | ((uint32_t)pal[e] << 8);
+    uint4* o = reinterpret_cast<uint4*>(rec + t);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]); o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    o[2] = make_uint4(w[8], w[9], w[10], w[11]); o[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
 // ---- connected components (lock-free union-find, smaller root wins) --------------------------
 __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x)
 {

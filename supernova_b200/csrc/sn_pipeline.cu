@@ -755,10 +755,14 @@ int sn_build_hbv(sn_ctx* c)
     k_hbv_erec<<<blocks_for(n_items, 256), 256, 0, c->st>>>(egrp.as<int32_t>(), pal.as<uint8_t>(), n_items, er.as<snh::ERec>());
     KCHECK("k_hbv_erec");
     // the numbering loop's records travel to pinned host memory while the components are analysed
-    HostBuf &h_groups = c->hpool["hbv_groups"], &h_er = c->hpool["hbv_er"], &h_comp = c->hpool["hbv_comp"];
-    CU(h_groups.alloc(64ull * nV)); CU(h_er.alloc(16ull * n_items));
+    DevBuf& irec = c->pool["hbv_irec"];
+    CU(irec.alloc(64ull * n_items));
+    k_hbv_itemrec<<<blocks_for(n_items, 128), 128, 0, c->st>>>(egrp.as<int32_t>(), pal.as<uint8_t>(), groups.as<snh::GroupRec>(), n_items, irec.as<snh::ItemRec>());
+    KCHECK("k_hbv_itemrec");
+    HostBuf &h_groups = c->hpool["hbv_groups"], &h_irec = c->hpool["hbv_irec"], &h_comp = c->hpool["hbv_comp"];
+    CU(h_groups.alloc(64ull * nV)); CU(h_irec.alloc(64ull * n_items));
+    CU(cudaMemcpyAsync(h_irec.p, irec.p, 64ull * n_items, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(h_groups.p, groups.p, 64ull * nV, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(h_er.p, er.p, 16ull * n_items, cudaMemcpyDeviceToHost, c->st));
     // ---- connected components, their discovery order and id bases ----------------------------------------
     CU(parent.alloc(4ull * nV)); CU(comp.alloc(4ull * nV)); CU(ckey.alloc(8ull * nV)); CU(cntv.alloc(4ull * nV)); CU(cnte.alloc(4ull * nV));
     k_hbv_uf_init<<<blocks_for(nV, 256), 256, 0, c->st>>>(parent.as<uint32_t>(), nV, ckey.as<unsigned long long>(), cntv.as<uint32_t>(), cnte.as<uint32_t>());
@@ -807,7 +811,7 @@ int sn_build_hbv(sn_ctx* c)
         resize_pinned(c, Hn.src, tot_h); resize_pinned(c, Hn.to_left, tot_h); resize_pinned(c, Hn.to_right, tot_h);
         resize_pinned(c, Hn.fwd, nE); resize_pinned(c, Hn.rev, nE);
     }
-    try { snh::number_hbv(comps, h_groups.as<snh::GroupRec>(), h_er.as<snh::ERec>(), nE, c->hbv, hbv_threads); }
+    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, hbv_threads); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     snh::Hbv& H = c->hbv;
