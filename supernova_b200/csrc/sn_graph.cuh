@@ -26,22 +26,24 @@ SN_HD uint32_t prune_ctx(const DictView& d, uint32_t i, Link2* cand)
     // the neighbours share all but one of k's p-mers: their minimizers (hence their buckets -- nearly
     // always k's own) follow from one pass over k
     const KmerMin km = kmer_minimizer_nb(k);
-    for (uint32_t c = 0; c < 4; ++c)
-        if (ctx & (1u << c)) {
-            Kmer q = kmer_succ(k, c), r;
-            const bool rc = kmer_form(q, &r) == REV;
-            uint32_t j = dict_find_in_bucket(d, succ_minimizer(km, c), rc ? r : q);
-            if (j == SN_NULL_EDGE) ctx &= ~(1u << c); else { ++ns; ls = (j << 1) | (rc ? 1u : 0u); }
-        }
+    // (loops over the SET bits, not over the four bases: the lanes of a warp then look their first,
+    // second, ... neighbour up together whatever base it is)
+    for (uint32_t m = ctx & 0xFu; m; m &= m - 1u) {
+        const uint32_t c = low_bit_index(m);
+        Kmer q = kmer_succ(k, c), r;
+        const bool rc = kmer_form(q, &r) == REV;
+        uint32_t j = dict_find_in_bucket(d, succ_minimizer(km, c), rc ? r : q);
+        if (j == SN_NULL_EDGE) ctx &= ~(1u << c); else { ++ns; ls = (j << 1) | (rc ? 1u : 0u); }
+    }
     // the predecessor side is the successor side of the reverse complement: a walk that leaves
     // through it sees the neighbour in the orientation of succ(rc(k)) = rc(pred(k))
-    for (uint32_t c = 0; c < 4; ++c)
-        if (ctx & (16u << c)) {
-            Kmer q = kmer_pred(k, c), r;
-            const bool rc = kmer_form(q, &r) == REV;
-            uint32_t j = dict_find_in_bucket(d, pred_minimizer(km, c), rc ? r : q);
-            if (j == SN_NULL_EDGE) ctx &= ~(16u << c); else { ++np; lp = (j << 1) | (rc ? 0u : 1u); }
-        }
+    for (uint32_t m = (ctx >> 4) & 0xFu; m; m &= m - 1u) {
+        const uint32_t c = low_bit_index(m);
+        Kmer q = kmer_pred(k, c), r;
+        const bool rc = kmer_form(q, &r) == REV;
+        uint32_t j = dict_find_in_bucket(d, pred_minimizer(km, c), rc ? r : q);
+        if (j == SN_NULL_EDGE) ctx &= ~(16u << c); else { ++np; lp = (j << 1) | (rc ? 0u : 1u); }
+    }
     if (cand) { cand->x = ns == 1 ? ls : SN_NO_LINK; cand->y = np == 1 ? lp : SN_NO_LINK; }
     return ctx;
 }

@@ -77,6 +77,14 @@ SN_HD bool kmer_is_pal(const Kmer& k) { Kmer r = kmer_rc(k); return k == r; }
 SN_HD uint32_t ctx_rc(uint32_t c) { return brev32(c) >> 24; }
 SN_HD uint32_t ctx_pred(uint32_t c) { return (c >> 4) & 0xFu; }
 SN_HD uint32_t ctx_succ(uint32_t c) { return c & 0xFu; }
+SN_HD uint32_t low_bit_index(uint32_t m)       // m != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)m) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(m);
+#endif
+}
 SN_HD bool mask_single(uint32_t m) { return m != 0 && (m & (m - 1)) == 0; }
 SN_HD uint32_t mask_code(uint32_t m) { return (m >> 1) - (m >> 3); }   // 1,2,4,8 -> 0,1,2,3
 

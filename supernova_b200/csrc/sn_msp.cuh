@@ -133,11 +133,14 @@ SN_HD void sk_occurrence(const uint32_t* w, uint32_t i, Kmer* out, uint32_t* ctx
     *out = k; *ctx_out = ctx;
 }
 
-// number of bucket bits for n_occ k-mer occurrences: ~2048 occurrences per bucket
+// number of bucket bits for n_occ k-mer occurrences: 1536..3072 occurrences per bucket.  The
+// shared-memory table of k_bucket_count takes 1536 distinct k-mers per pass; sequencing data has
+// 0.15-0.3 distinct k-mers per occurrence (C2: 0.25), so a bucket normally needs one pass.
+#define SN_MSP_TARGET_OCC 3072
 inline int msp_bucket_bits(uint64_t n_occ)
 {
     int b = 4;
-    while (b < 24 && (n_occ >> b) > 2048) ++b;
+    while (b < 24 && (n_occ >> b) > SN_MSP_TARGET_OCC) ++b;
     return b;
 }
 

@@ -20,7 +20,7 @@ for spec in sys.argv[1:]:
     for rep in range(3):
         ctx.count_kmers(sb.Params())
         st = ctx.stage_ms()
-        t = {k: round(st[k], 3) for k in ("msp_hist", "msp_scatter", "bucket_count", "sort")}
+        t = {k: round(st[k], 3) for k in ("msp_hist", "msp_scatter", "bucket_count", "make_dict")}
         if best is None or t["bucket_count"] < best["bucket_count"]:
             best = t
     c = ctx.counts()
