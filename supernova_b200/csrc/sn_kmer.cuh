@@ -232,9 +232,9 @@ struct __attribute__((aligned(32))) DictEntry {
 
 struct DictView {
     const DictEntry* tab;
-    const uint32_t* boff;     // (1 << bits) + 1: first entry of every minimizer bucket
+    const uint32_t* boff;     // (1 << (bits + sub_bits)) + 1: first entry of every (minimizer bucket, top sub_bits of the hash)
     uint32_t n;
-    int bits;
+    int bits, sub_bits;
 };
 
 // (h,k) < entry ?  /  == entry ?
@@ -247,17 +247,20 @@ SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
     return 0;
 }
 // lookup of a canonical k-mer whose minimizer is known.  Inside the bucket the entries are sorted
-// by a uniform hash, so the search starts where the hash interpolates and walks a step or two.
+// by a uniform hash; the offsets are kept per (bucket, top sub_bits of the hash) -- ~32 entries --
+// and the search starts where the remaining hash bits interpolate, then walks a step or two.
 SN_HD uint32_t dict_find_in_bucket(const DictView& d, uint32_t minimizer, const Kmer& k)
 {
-    const uint32_t b = bucket_hash(minimizer) >> (32 - d.bits);
-    const uint32_t lo = d.boff[b], hi = d.boff[b + 1];
-    if (lo >= hi) return SN_NULL_EDGE;
     const uint32_t h = kmer_hash(k);
-    uint32_t i = lo + (uint32_t)(((uint64_t)h * (hi - lo)) >> 32);      // < hi
+    const uint32_t b = bucket_hash(minimizer) >> (32 - d.bits);
+    const uint32_t cell = d.sub_bits ? ((b << d.sub_bits) | (h >> (32 - d.sub_bits))) : b;
+    const uint32_t lo = d.boff[cell], hi = d.boff[cell + 1];
+    if (lo >= hi) return SN_NULL_EDGE;
+    const uint32_t rem = h << d.sub_bits;
+    uint32_t i = lo + (uint32_t)(((uint64_t)rem * (hi - lo)) >> 32);      // < hi
     if (d.tab[i].h < h) { do ++i; while (i < hi && d.tab[i].h < h); }
     else while (i > lo && d.tab[i - 1].h >= h) --i;
-    // i = first entry of the bucket with hash >= h; equal hashes are ordered by k-mer
+    // i = first entry of the cell with hash >= h; equal hashes are ordered by k-mer
     for (; i < hi; ++i) {
         const int c = dict_cmp(h, k, d.tab[i]);
         if (c == 0) return i;

@@ -614,6 +614,20 @@ __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ sur
     e.w0 = r.x; e.w1 = r.y; e.w2 = r.z; e.cc = r.w; e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = r.w >> 24; e.h = rs_hash(r);
     dict[i] = e;
 }
+// offsets per (bucket, top sub_bits of the hash) from the bucket offsets: a search per cell
+__global__ void __launch_bounds__(256) k_dict_cells(const DictEntry* __restrict__ dict, const uint32_t* __restrict__ bucket_off, uint32_t n_buckets, int sub_bits,
+                                                    uint32_t* __restrict__ cell_off)
+{
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_cells = (uint64_t)n_buckets << sub_bits;
+    if (c > n_cells) return;
+    if (c == n_cells) { cell_off[c] = bucket_off[n_buckets]; return; }
+    const uint32_t b = (uint32_t)(c >> sub_bits), s = (uint32_t)(c & ((1u << sub_bits) - 1u));
+    uint32_t lo = bucket_off[b], hi = bucket_off[b + 1];
+    const uint32_t key = sub_bits ? s << (32 - sub_bits) : 0u;          // first entry of the bucket with hash >= key
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (dict[mid].h < key) lo = mid + 1; else hi = mid; }
+    cell_off[c] = lo;
+}
 __global__ void __launch_bounds__(256) k_narrow_u64(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out)
 { const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
 __global__ void __launch_bounds__(256) k_diff_u32(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ cnt)

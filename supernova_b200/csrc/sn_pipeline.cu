@@ -90,7 +90,7 @@ struct sn_ctx {
     bool have_bc = false, have_pq = false;
     // dictionary
     DevBuf dict, dboff;      // dictionary (bucket, hash, k-mer order) and its bucket offsets (2^dict_bits + 1)
-    int dict_bits = 4;
+    int dict_bits = 4, dict_sub_bits = 0;
     // edges (device) + host copy
     DevBuf ebases, eoff, elen;
     snh::Edges hedges;
@@ -447,6 +447,16 @@ static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int b
         k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv, (uint32_t)n_surv, c->dict.as<DictEntry>());
         KCHECK("k_make_dict");
     }
+    // lookup cells of ~32 entries: (bucket, top sub_bits of the hash)
+    int sub = 0;
+    while (sub < 6 && bits + sub < 26 && (n_surv >> (bits + sub)) > 32) ++sub;
+    c->dict_sub_bits = sub;
+    if (sub) {
+        DevBuf& cells = c->pool["dict_cells"];
+        CU(cells.alloc(4 * ((nb << sub) + 1)));
+        k_dict_cells<<<blocks_for((nb << sub) + 1, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), c->dboff.as<uint32_t>(), (uint32_t)nb, sub, cells.as<uint32_t>());
+        KCHECK("k_dict_cells");
+    }
     t_end(c, "make_dict");
     CU(cudaStreamSynchronize(c->st));
     c->stage = 2;
@@ -586,7 +596,7 @@ int sn_build_edges(sn_ctx* c)
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
     if (!n) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
-    DictView dv; dv.tab = tab; dv.boff = c->dboff.as<uint32_t>(); dv.n = n; dv.bits = c->dict_bits;
+    DictView dv; dv.tab = tab; dv.boff = c->dict_sub_bits ? c->pool["dict_cells"].as<uint32_t>() : c->dboff.as<uint32_t>(); dv.n = n; dv.bits = c->dict_bits; dv.sub_bits = c->dict_sub_bits;
     t_begin(c, "prune");
     DevBuf& links = c->pool["links"];
     CU(links.alloc(8ull * n));
@@ -870,7 +880,7 @@ int sn_path_reads(sn_ctx* c)
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "sn_path_reads: run sn_build_hbv first");
     CU(cudaSetDevice(c->device));
     const uint64_t n = c->cnt.n_reads;
-    DictView d; d.tab = c->dict.as<DictEntry>(); d.boff = c->dboff.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits;
+    DictView d; d.tab = c->dict.as<DictEntry>(); d.boff = c->dict_sub_bits ? c->pool["dict_cells"].as<uint32_t>() : c->dboff.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits; d.sub_bits = c->dict_sub_bits;
     EdgeStore es; es.bases = c->ebases.as<uint8_t>(); es.off = c->eoff.as<uint64_t>(); es.len = c->elen.as<uint32_t>();
     HbvView h;
     h.fwd_xlat = c->d_fwd.as<int32_t>(); h.rev_xlat = c->d_rev.as<int32_t>();
