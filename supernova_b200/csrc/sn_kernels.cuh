@@ -32,32 +32,28 @@ __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const u
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t occ = 0;
     if (r < n_reads) {
+        // One quality per iteration, block headers parsed on the fly: the lanes of a warp (reads of
+        // the same length) then run the same iterations, whatever their block structure is.
         const uint8_t* p = pq + pq_off[r];
         const uint8_t* pend = pq + pq_off[r + 1];
-        uint32_t L = len[r], i = 0, run = 0, gl = 0;
-        while (p < pend) {
-            uint32_t nq = *p++;
-            if (!nq) break;
-            uint32_t b0 = *p++;
-            uint32_t nbits = b0 & 7u, minq = b0 >> 3;
-            uint64_t acc = *p++;
-            minq |= (uint32_t)(acc & 1u) << 5; acc >>= 1;
-            uint32_t have = 7;
-            uint32_t mask = (1u << nbits) - 1u;
-            if (!nbits) {                                   // a block of nq equal quals
-                if (minq >= min_qual) { run += nq; if (run >= SN_K) gl = i + nq; } else run = 0;
-                i += nq;
-            } else {
-                for (uint32_t k = 0; k < nq; ++k) {
-                    if (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
-                    uint32_t q = minq + ((uint32_t)acc & mask); acc >>= nbits; have -= nbits;
-                    run = q >= min_qual ? run + 1 : 0;
-                    ++i;
-                    if (run >= SN_K) gl = i;
-                }
+        const uint32_t L = len[r];
+        uint32_t run = 0, gl = 0, rem = 0, nbits = 0, minq = 0, acc = 0, have = 0, mask = 0;
+        bool bad = false;
+        for (uint32_t i = 0; i < L; ++i) {
+            if (rem == 0) {                                     // next block: [nQs][nBits:3|minQ low 5][minQ bit 5 | 7 data bits]...
+                if (p + 3 > pend) { bad = true; break; }
+                rem = *p++;
+                if (!rem) { bad = true; break; }                // terminator before L quals
+                const uint32_t b0 = *p++, a = *p++;
+                nbits = b0 & 7u; minq = (b0 >> 3) | ((a & 1u) << 5); acc = a >> 1; have = 7; mask = (1u << nbits) - 1u;
             }
+            if (have < nbits) { acc |= (uint32_t)(*p++) << have; have += 8; }
+            const uint32_t q = minq + (acc & mask); acc >>= nbits; have -= nbits; --rem;
+            run = q >= min_qual ? run + 1 : 0;
+            if (run >= SN_K) gl = i + 1;
         }
-        if (i != L) atomicAdd(bad_reads, 1u);      // PQVec length disagrees with the fastb length
+        if (rem != 0 || (p < pend && *p != 0)) bad = true;      // the PQVec holds more quals than the read has bases
+        if (bad) { atomicAdd(bad_reads, 1u); gl = 0; }
         goodlen[r] = gl;
         occ = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
     }
@@ -129,10 +125,10 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2
 // An edge is a chain of unipath links, and following a chain is one dependent random load
 // per k-mer: walking a whole edge from its end costs (edge length) x (DRAM latency), and the
 // longest edge alone would set the run time of the stage.  The chains are therefore cut at
-// STOPS -- the edge ends plus every interior k-mer whose index hashes to 0 mod 64:
-//   k_seg_walk   every stop walks to the next stop on each side (~64 steps, all segments in parallel)
+// STOPS -- the edge ends plus every interior k-mer whose index hashes to 0 mod 16 (a segment then mostly stays inside one dictionary bucket, whose lines the neighbouring threads share):
+//   k_seg_walk   every stop walks to the next stop on each side (~16 steps, all segments in parallel)
 //                and records {next stop, arrival orientation, steps}
-//   k_end_hop    every edge end hops from stop to stop (L/64 steps over a small, L2-resident table)
+//   k_end_hop    every edge end hops from stop to stop (L/16 steps over a small, L2-resident table)
 //                to the far end -> length and owner of the edge
 //   k_owner_hop  after allocation the owner hops again and leaves {edge, offset, orientation} at
 //                every stop of its edge
@@ -140,7 +136,7 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2
 //                bases into the edge scratch, (edge, offset) into the dictionary
 // Interior k-mers that no edge end reaches are circles (k_circle_count, after the edges above).
 // ---------------------------------------------------------------------------
-#define SN_STOP_SHIFT 26          // interior entry i is a stop iff (i * 0x9E3779B1) >> 26 == 0 (1 in 64)
+#define SN_STOP_SHIFT 28          // interior entry i is a stop iff (i * 0x9E3779B1) >> 28 == 0 (1 in 16)
 __device__ __forceinline__ bool stop_sampled(uint32_t i) { return ((i * 0x9E3779B1u) >> SN_STOP_SHIFT) == 0u; }
 struct Seg { uint32_t next; uint32_t steps_o; };        // next stop (stop id, SN_NO_LINK = none on this side); steps << 1 | arrival orientation
 

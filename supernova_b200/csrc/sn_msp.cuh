@@ -344,15 +344,36 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     uint64_t base = 0;                                // the bucket's range in `out`
     for (;;) {
         bool overflowed = false;
-        for (uint32_t sg = 0; sg < n_seg && !overflowed; ++sg) {
-            const uint64_t r0 = bucket_off[(uint64_t)sg * n_buckets + bkt], r1 = bucket_off[(uint64_t)sg * n_buckets + bkt + 1];
-            for (uint64_t c0 = r0; c0 < r1 && !overflowed; c0 += SN_BC_CHUNK) {
-                const uint32_t nc = (uint32_t)min((uint64_t)SN_BC_CHUNK, r1 - c0);
-                if (tid == 0) {
+        // The bucket's records are the concatenation of its ranges in the n_seg segments; they are staged
+        // SN_BC_CHUNK at a time, every contiguous piece by its own bulk copy on the same mbarrier.
+        uint32_t sg = 0;
+        uint64_t rpos = bucket_off[bkt], rend = bucket_off[bkt + 1];
+        for (;;) {
+            while (rpos == rend && ++sg < n_seg) { rpos = bucket_off[(uint64_t)sg * n_buckets + bkt]; rend = bucket_off[(uint64_t)sg * n_buckets + bkt + 1]; }
+            if (sg >= n_seg || overflowed) break;
+            uint32_t nc = 0;
+            {
+                // what the chunk takes (every thread, so that all agree on the new position) ...
+                uint32_t s2 = sg; uint64_t p2 = rpos, e2 = rend;
+                while (nc < (uint32_t)SN_BC_CHUNK && s2 < n_seg) {
+                    const uint32_t take = (uint32_t)min((uint64_t)(SN_BC_CHUNK - nc), e2 - p2);
+                    nc += take; p2 += take;
+                    if (p2 == e2 && ++s2 < n_seg) { p2 = bucket_off[(uint64_t)s2 * n_buckets + bkt]; e2 = bucket_off[(uint64_t)s2 * n_buckets + bkt + 1]; }
+                }
+                if (tid == 0) {                                           // ... and the copies themselves
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the staging buffer finished at the last barrier
                     mbar_expect_tx(&S.mbar, nc * 32u);
-                    tma_load_1d(S.rec, recs + 2 * c0, nc * 32u, &S.mbar);
+                    uint32_t s3 = sg, done = 0; uint64_t p3 = rpos, e3 = rend;
+                    while (done < nc) {
+                        const uint32_t take = (uint32_t)min((uint64_t)(nc - done), e3 - p3);
+                        if (take) tma_load_1d(S.rec + 2 * done, recs + 2 * p3, take * 32u, &S.mbar);
+                        done += take; p3 += take;
+                        if (p3 == e3 && ++s3 < n_seg) { p3 = bucket_off[(uint64_t)s3 * n_buckets + bkt]; e3 = bucket_off[(uint64_t)s3 * n_buckets + bkt + 1]; }
+                    }
                 }
+                sg = s2; rpos = p2; rend = e2;
+            }
+            {
                 mbar_wait(&S.mbar, phase); phase ^= 1u;
                 // exclusive prefix of the k-mers per record
                 {
