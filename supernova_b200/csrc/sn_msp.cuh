@@ -604,6 +604,420 @@ k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ buck
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_bucket_count2: the same reduction (one CTA per bucket, same passes / split rule / output
+// order) with an insert loop that needs no block-wide barrier and a third of the shared-memory
+// wavefronts per occurrence:
+//   slot[s] (16 B) = {k0, k1, k2, tag};  tag = hash[31:12] << 12 | barcode rule settled << 10 | ctx << 2 | state
+//                    (state 0 = empty, 2 = claimed and being written, 1 = published)
+//   acc[s]  (8 B)  = {occurrences, first barcode > 0 | IGN << 24 | MULTI << 25}
+// An occurrence reads its slot with ONE 16-byte load (tag and key together).  Empty: claim the
+// tag by CAS, write key + accumulators, fence, publish the tag.  Published and same key: one
+// atomicAdd on the count, an atomicOr on the tag only while the context still adds a bit, a
+// barcode update only while the barcode state can still change.  Claimed by someone else with
+// the same hash bits: look again in the next round.  The rounds of a warp are convergent
+// (`__any_sync` loop + `__syncwarp`), so a lane never spins on a slot a lane of its own warp is
+// still writing; a claim itself never waits, so the loop cannot deadlock.
+// The cursor keeps the upcoming bases of its record in a register (one shared-memory load per 16
+// occurrences) and takes the preceding base from the k-mer it just left.
+// There is no claim list: validity, the count of distinct k-mers and the clean-up scan the table
+// (SLOTS / THREADS slots per thread, 16-byte loads).  A pass overflows when an occurrence probes
+// SN_BC2_MAXPROBE slots without finding its k-mer or a free slot.
+// ---------------------------------------------------------------------------
+#define SN_BC2_MAXPROBE 64u
+#define SN_BC2_IGN (1u << 24)
+#define SN_BC2_MULTI (1u << 25)
+template <int T, int SLOTS>
+struct BcSmem2 {
+    uint4 rec[2 * T];                 // staging; vs[] + members[] of the survivor ordering afterwards
+    uint32_t pref[T + 1];
+    uint4 slot[SLOTS];
+    uint2 acc[SLOTS];
+    uint32_t dtab[2 * T];             // record de-duplication: hash table of record indices (+1) over the chunk
+    uint32_t mult[T], rsum[T];        // per representative record: copies in the chunk, their barcode summary
+    uint16_t rid[T];                  // the representative records, in chunk order
+    unsigned long long mbar;
+    uint32_t over, wsum[T / 32 + 1], ndist;
+    unsigned long long out_base;
+};
+__device__ __forceinline__ uint4 lds128v(const uint4* p)
+{ uint4 v; asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds32v(const uint32_t* p)
+{ uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
+__device__ __forceinline__ void sts32v(uint32_t* p, uint32_t v)
+{ asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory"); }
+
+struct SkCur2 {
+    const uint32_t* w;
+    uint32_t i, nk, p, hasR, fbv, mult;
+    uint32_t nextw, nleft;      // upcoming bases (base p+K in the low 2 bits), bases left in nextw
+    uint32_t prev;              // context bit of the base before the k-mer, 0 if there is none
+    Kmer f, r;
+};
+__device__ __forceinline__ void skc2_open(SkCur2& c, const uint32_t* w, uint32_t i, uint32_t mult, uint32_t bsum)
+{
+    const uint32_t w0 = w[0];
+    const uint32_t hasL = (w0 >> 30) & 1u;
+    c.w = w; c.i = i; c.nk = sk_nk(w0); c.hasR = w0 >> 31;
+    c.fbv = bsum; c.mult = mult;
+    c.p = hasL + i;
+    const uint32_t q = c.p >> 4, sh = 2 * (c.p & 15);
+    const uint32_t* b = w + 2;
+    const uint32_t l0 = __funnelshift_r(b[q], b[q + 1], sh), l1 = __funnelshift_r(b[q + 1], b[q + 2], sh), l2 = __funnelshift_r(b[q + 2], b[q + 3], sh);   // p <= 47: q + 3 <= 5
+    c.f.w0 = rev2(l0); c.f.w1 = rev2(l1); c.f.w2 = rev2(l2);
+    c.r.w0 = ~l2; c.r.w1 = ~l1; c.r.w2 = ~l0;                // kmer_rc(f): rev2 is an involution, so ~rev2(f.w2) = ~l2
+    c.prev = c.p > 0 ? 16u << sk_base(w, c.p - 1) : 0u;      // p > 0 <=> i > 0 || hasL
+    const uint32_t idx = c.p + SN_K;                          // <= 95
+    c.nextw = b[idx >> 4] >> (2 * (idx & 15)); c.nleft = 16u - (idx & 15u);
+}
+__device__ __forceinline__ void skc2_get(const SkCur2& c, Kmer* key, uint32_t* ctx_out)
+{
+    uint32_t ctx = c.prev;
+    if (c.i + 1 < c.nk || c.hasR) ctx |= 1u << (c.nextw & 3u);
+    if (c.r < c.f) { *key = c.r; ctx = ctx_rc(ctx); } else *key = c.f;
+    *ctx_out = ctx;
+}
+__device__ __forceinline__ void skc2_step(SkCur2& c)
+{
+    const uint32_t nb = c.nextw & 3u;
+    c.prev = 16u << (c.f.w0 >> 30);
+    c.f = kmer_succ(c.f, nb); c.r = kmer_pred(c.r, 3u - nb);
+    ++c.i; ++c.p;
+    c.nextw >>= 2;
+    if (--c.nleft == 0u) { const uint32_t idx = c.p + SN_K; c.nextw = idx < 96u ? c.w[2 + (idx >> 4)] : 0u; c.nleft = 16u; }
+}
+
+template <int T, int SLOTS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(T, MINB)
+k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg,
+                uint32_t min_freq, uint32_t min_bc, int has_bc,
+                uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor,
+                uint64_t* __restrict__ seg_base, uint32_t* __restrict__ seg_cnt,
+                unsigned long long* n_distinct, uint32_t* err)
+{
+    static_assert(4 * SLOTS <= 32 * T, "the survivor ordering parks 2 x SLOTS u16 in the staging buffer");
+    static_assert(SLOTS % T == 0 && SLOTS / T <= 32, "slots per thread");
+    constexpr int CHUNK = T;
+    constexpr int PER = SLOTS / T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BcSmem2<T, SLOTS>& S = *reinterpret_cast<BcSmem2<T, SLOTS>*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t bkt = blockIdx.x;
+    if (bkt >= n_buckets) return;
+    {
+        bool any = false;
+        for (uint32_t sg = 0; sg < n_seg; ++sg) any = any || bucket_off[(uint64_t)sg * n_buckets + bkt] != bucket_off[(uint64_t)sg * n_buckets + bkt + 1];
+        if (!any) return;
+    }
+    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.over = 0; S.ndist = 0; }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) S.slot[j * T + tid].w = 0u;
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
+    uint32_t depth = 0, sub = 0, mode = 0;            // passes: see k_bucket_count
+    uint32_t total = 0, run = 0;
+    uint64_t base = 0;
+    for (;;) {
+        bool overflowed = false;
+        uint32_t sg = 0;
+        uint64_t rpos = bucket_off[bkt], rend = bucket_off[bkt + 1];
+        for (;;) {
+            while (rpos == rend && ++sg < n_seg) { rpos = bucket_off[(uint64_t)sg * n_buckets + bkt]; rend = bucket_off[(uint64_t)sg * n_buckets + bkt + 1]; }
+            if (sg >= n_seg || overflowed) break;
+            uint32_t nc = 0;
+            if (n_seg == 1u) {                                                  // one contiguous range: one bulk copy per chunk
+                nc = (uint32_t)min((uint64_t)CHUNK, rend - rpos);
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.mbar, nc * 32u);
+                    tma_load_1d(S.rec, recs + 2 * rpos, nc * 32u, &S.mbar);
+                }
+                rpos += nc;
+            } else {
+                uint32_t s2 = sg; uint64_t p2 = rpos, e2 = rend;
+                while (nc < (uint32_t)CHUNK && s2 < n_seg) {
+                    const uint32_t take = (uint32_t)min((uint64_t)(CHUNK - nc), e2 - p2);
+                    nc += take; p2 += take;
+                    if (p2 == e2 && ++s2 < n_seg) { p2 = bucket_off[(uint64_t)s2 * n_buckets + bkt]; e2 = bucket_off[(uint64_t)s2 * n_buckets + bkt + 1]; }
+                }
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.mbar, nc * 32u);
+                    uint32_t s3 = sg, done = 0; uint64_t p3 = rpos, e3 = rend;
+                    while (done < nc) {
+                        const uint32_t take = (uint32_t)min((uint64_t)(nc - done), e3 - p3);
+                        if (take) tma_load_1d(S.rec + 2 * done, recs + 2 * p3, take * 32u, &S.mbar);
+                        done += take; p3 += take;
+                        if (p3 == e3 && ++s3 < n_seg) { p3 = bucket_off[(uint64_t)s3 * n_buckets + bkt]; e3 = bucket_off[(uint64_t)s3 * n_buckets + bkt + 1]; }
+                    }
+                }
+                sg = s2; rpos = p2; rend = e2;
+            }
+            // (while the copy is in flight) reset the record de-duplication state of the chunk
+            S.dtab[tid] = 0u; S.dtab[tid + T] = 0u; S.mult[tid] = 1u; S.rsum[tid] = 0u;
+            mbar_wait(&S.mbar, phase); phase ^= 1u;
+            __syncthreads();
+            // ---- identical super-k-mers (same bases, neighbours and flags: reads covering the same stretch
+            // of the genome) are expanded ONCE: the first copy in the table represents the others and
+            // carries their number and the summary of their barcodes (none / one / several / ignored),
+            // which is all Kmerizer::reduce needs from them (BuildReadQGraph48.cc:91-137).
+            uint32_t my_nk = 0;
+            if (tid < nc) {
+                const uint4 ra = S.rec[2 * tid], rb = S.rec[2 * tid + 1];
+                const uint32_t idw = ra.x >> 24;                                 // nk-1, hasL, hasR
+                uint32_t hr = (ra.z * 0x9E3779B1u) ^ (ra.w * 0x85EBCA77u) ^ (rb.x * 0xC2B2AE3Du) ^ (rb.y * 0x27D4EB2Fu) ^ (rb.z * 0x165667B1u) ^ (rb.w * 0x9E3779B9u);
+                hr += idw; hr ^= hr >> 15; hr *= 0x2C1B3C6Du; hr ^= hr >> 12;
+                uint32_t rep = tid, sd = hr & (2u * T - 1u);
+                for (;;) {
+                    uint32_t v = lds32v(&S.dtab[sd]);
+                    if (v == 0u) v = atomicCAS(&S.dtab[sd], 0u, tid + 1u);
+                    if (v == 0u) break;                                          // first of its kind
+                    const uint32_t u = v - 1u;
+                    const uint4 ua = S.rec[2 * u], ub = S.rec[2 * u + 1];
+                    if ((ua.x >> 24) == idw && ua.z == ra.z && ua.w == ra.w && ub.x == rb.x && ub.y == rb.y && ub.z == rb.z && ub.w == rb.w) { rep = u; break; }
+                    sd = (sd + 1u) & (2u * T - 1u);
+                }
+                if (rep != tid) atomicAdd(&S.mult[rep], 1u); else my_nk = sk_nk(ra.x);
+                const uint32_t bv = ra.x & 0xFFFFFFu;
+                if (bv == 0xFFFFFFu) atomicOr(&S.rsum[rep], SN_BC2_IGN);
+                else if (bv != 0u) {
+                    const uint32_t old = atomicCAS(&S.rsum[rep], 0u, bv);
+                    if (!(old & (SN_BC2_MULTI | SN_BC2_IGN)) && old != 0u && old != bv) atomicOr(&S.rsum[rep], SN_BC2_MULTI);   // (an ignored copy decides the rule by itself)
+                }
+            }
+            uint32_t nrep;
+            {                                                                   // representatives in chunk order + exclusive prefix of their k-mers
+                const uint32_t v = my_nk ? (my_nk | 0x10000u) : 0u; uint32_t xsc = v;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, xsc, o); if (lane >= (uint32_t)o) xsc += y; }
+                if (lane == 31) S.wsum[warp] = xsc;
+                __syncthreads();
+                uint32_t wb = 0, all = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < T / 32; ++k) { const uint32_t q = S.wsum[k]; wb += k < warp ? q : 0u; all += q; }
+                const uint32_t incl = wb + xsc;
+                if (my_nk) { const uint32_t pos = (incl >> 16) - 1u; S.pref[pos] = (incl & 0xFFFFu) - my_nk; S.rid[pos] = (uint16_t)tid; }
+                nrep = all >> 16;
+                if (tid == 0) S.pref[nrep] = all & 0xFFFFu;
+                __syncthreads();
+            }
+            const uint32_t Tn = S.pref[nrep];
+            const uint32_t C = (Tn + T - 1) / T;                                 // consecutive occurrences per thread
+            uint32_t x = tid * C;
+            const uint32_t xe = min(x + C, Tn);
+            SkCur2 cur; uint32_t rec_i = 0;
+            if (x < xe) {
+                uint32_t a = 0, b = nrep;                                       // record of occurrence x: largest a with pref[a] <= x
+                while (b - a > 1) { uint32_t m = (a + b) >> 1; if (S.pref[m] <= x) a = m; else b = m; }
+                rec_i = a;
+                const uint32_t r = S.rid[a];
+                skc2_open(cur, recw + 8 * r, x - S.pref[a], S.mult[r], S.rsum[r]);
+            }
+            // every warp walks its threads' ranges on its own: no block barrier until the chunk is done.
+            // ITEMS occurrences per thread are in flight together (independent hash chains and slot loads).
+            for (uint32_t x0 = 0; x0 < C; x0 += ITEMS) {
+                uint32_t act = 0;
+                Kmer key[ITEMS]; uint32_t h[ITEMS], cx[ITEMS], fb[ITEMS], mu[ITEMS], sl[ITEMS];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) {
+                    h[j] = 0; cx[j] = 0; fb[j] = 0; mu[j] = 0; key[j].w0 = key[j].w1 = key[j].w2 = 0;
+                    if (x < xe) {
+                        skc2_get(cur, &key[j], &cx[j]);
+                        h[j] = kmer_hash(key[j]);
+                        fb[j] = cur.fbv; mu[j] = cur.mult;
+                        if (depth == 0u || (h[j] >> (32u - depth)) == sub) act |= 1u << j;
+                        ++x;
+                        if (x < xe) {
+                            if (cur.i + 1 < cur.nk) skc2_step(cur);
+                            else { ++rec_i; const uint32_t r = S.rid[rec_i]; skc2_open(cur, recw + 8 * r, 0, S.mult[r], S.rsum[r]); }
+                        }
+                    }
+                    sl[j] = h[j] & (SLOTS - 1u);                                // slot | probes << 16
+                }
+                if (lds32v(&S.over)) break;                                     // (the pass is abandoned anyway)
+                uint32_t rounds = 0;
+                while (__any_sync(SN_FULL, act != 0u)) {
+                    // probe: a tight loop per item until it stands on (a) an empty slot, (b) the published slot
+                    // of its k-mer, (c) a slot somebody is still writing under its hash bits
+                    uint32_t tg[ITEMS];
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j) {
+                        tg[j] = 0;
+                        if (!(act & (1u << j))) continue;
+                        const uint32_t hb = h[j] & ~4095u;
+                        uint32_t s = sl[j] & 0xFFFFu, probes = sl[j] >> 16;
+                        for (;;) {
+                            const uint4 e = lds128v(&S.slot[s]);
+                            tg[j] = e.w;
+                            if (e.w == 0u) break;
+                            if ((e.w & ~4095u) == hb && ((e.w & 3u) == 2u || (e.x == key[j].w0 && e.y == key[j].w1 && e.z == key[j].w2))) break;
+                            s = (s + 1u) & (SLOTS - 1u);
+                            if (++probes >= SN_BC2_MAXPROBE) { tg[j] = 3u; break; }         // state 3 = gave up
+                        }
+                        sl[j] = s | (probes << 16);
+                    }
+                    // act
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j) {
+                        if (!(act & (1u << j))) continue;
+                        const uint32_t s = sl[j] & 0xFFFFu, hb = h[j] & ~4095u, ctx = cx[j], fbv = fb[j], t = tg[j];
+                        if (t == 0u) {
+                            if (atomicCAS(&S.slot[s].w, 0u, hb | 2u) == 0u) {                  // claimed: key + accumulators, then publish
+                                S.acc[s] = make_uint2(mu[j], fbv);
+                                S.slot[s] = make_uint4(key[j].w0, key[j].w1, key[j].w2, hb | 2u);
+                                __threadfence_block();
+                                sts32v(&S.slot[s].w, hb | ((fbv & (SN_BC2_IGN | SN_BC2_MULTI)) ? 1024u : 0u) | (ctx << 2) | 1u);
+                                act &= ~(1u << j);
+                            }                                                               // (lost the race: probe again from this slot)
+                        } else if ((t & 3u) == 1u) {
+                            atomicAdd(&S.acc[s].x, mu[j]);
+                            if ((((t >> 2) & 0xFFu) & ctx) != ctx) atomicOr(&S.slot[s].w, ctx << 2);
+                            if (fbv != 0u && !(t & 1024u)) {                                // bit 10: the barcode rule is already settled
+                                if (fbv & (SN_BC2_IGN | SN_BC2_MULTI)) { atomicOr(&S.acc[s].y, fbv & (SN_BC2_IGN | SN_BC2_MULTI)); atomicOr(&S.slot[s].w, 1024u); }
+                                else {
+                                    uint32_t b0 = lds32v(&S.acc[s].y);
+                                    if (b0 == 0u) b0 = atomicCAS(&S.acc[s].y, 0u, fbv);
+                                    if (b0 & (SN_BC2_IGN | SN_BC2_MULTI)) atomicOr(&S.slot[s].w, 1024u);
+                                    else if (b0 != 0u && b0 != fbv) { atomicOr(&S.acc[s].y, SN_BC2_MULTI); atomicOr(&S.slot[s].w, 1024u); }
+                                }
+                            }
+                            act &= ~(1u << j);
+                        } else if (t == 3u) { S.over = 1u; act &= ~(1u << j); }
+                        else if (++rounds > (1u << 22)) { atomicOr(err, 4u); S.over = 1u; act = 0; }     // being written (cannot last: a claim never waits)
+                    }
+                    __syncwarp();
+                }
+            }
+            overflowed = __syncthreads_or((int)lds32v(&S.over)) != 0;          // (whoever set it reads it back as set)
+        }
+        // ---- a pass is over: which slots hold valid k-mers? ----
+        uint32_t vmask = 0, nvalid = 0, nfill = 0;
+        if (!overflowed) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const uint32_t s = j * T + tid;
+                if (S.slot[s].w != 0u) {
+                    ++nfill;
+                    const uint2 a = S.acc[s];
+                    const bool enough = min_bc == 0 || (min_bc == 1 ? (a.y & (0xFFFFFFu | SN_BC2_MULTI)) != 0u : (a.y & SN_BC2_MULTI) != 0u);
+                    if (a.x >= min_freq && (!has_bc || (a.y & SN_BC2_IGN) || enough)) { vmask |= 1u << j; ++nvalid; }
+                }
+            }
+        }
+        uint32_t xs = nvalid | (nfill << 16);                                   // both counts in one scan (each <= SLOTS <= 2^15)
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, xs, o); if (lane >= (uint32_t)o) xs += y; }
+        if (lane == 31) S.wsum[warp] = xs;
+        __syncthreads();
+        uint32_t wb = 0, tot = 0, totfill = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < T / 32; ++k) { const uint32_t v = S.wsum[k]; wb += k < warp ? (v & 0xFFFFu) : 0u; tot += v & 0xFFFFu; totfill += v >> 16; }
+        xs &= 0xFFFFu;
+        if (!overflowed) {
+            if (mode != 2u && tid == 0) S.ndist += totfill;
+            if (mode == 0u) {
+                if (tid == 0) S.out_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
+                __syncthreads();
+                base = S.out_base; total = tot;
+            }
+            if (mode == 1u) total += tot;
+            else if (tot) {
+                // ---- order the pass's survivors by (hash, k-mer) and write them (see k_bucket_count) ----
+                constexpr int NB = T, NB_SHIFT = 32 - (T == 128 ? 7 : (T == 256 ? 8 : 9));
+                uint16_t* vs = reinterpret_cast<uint16_t*>(S.rec);
+                uint16_t* members = vs + SLOTS;
+                {
+                    uint32_t p = wb + xs - nvalid;
+#pragma unroll
+                    for (int j = 0; j < PER; ++j)
+                        if (vmask & (1u << j)) {
+                            const uint32_t s = j * T + tid;
+                            const uint4 e = S.slot[s];
+                            Kmer k; k.w0 = e.x; k.w1 = e.y; k.w2 = e.z;
+                            vs[p] = (uint16_t)s; S.acc[s].y = kmer_hash(k); ++p;   // the barcode state is not needed any more
+                        }
+                }
+                S.pref[tid] = 0;
+                __syncthreads();
+                uint32_t rin[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const uint32_t e = j * T + tid; if (e < tot) rin[j] = atomicAdd(&S.pref[S.acc[vs[e]].y >> NB_SHIFT], 1u); }
+                __syncthreads();
+                {
+                    const uint32_t v = S.pref[tid]; uint32_t x = v;
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(SN_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+                    if (lane == 31) S.wsum[warp] = x;
+                    __syncthreads();
+                    uint32_t wbase = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < T / 32; ++k) wbase += k < warp ? S.wsum[k] : 0u;
+                    S.pref[tid] = wbase + x - v;
+                    if (tid == NB - 1) S.pref[NB] = wbase + x;
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const uint32_t e = j * T + tid; if (e < tot) members[S.pref[S.acc[vs[e]].y >> NB_SHIFT] + rin[j]] = (uint16_t)e; }
+                __syncthreads();
+                const uint64_t obase = base + run;
+                if (obase + tot > out_cap) { if (tid == 0) atomicOr(err, 1u); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < PER; ++j) {
+                        const uint32_t e = j * T + tid;
+                        if (e < tot) {
+                            const uint32_t s = vs[e];
+                            const uint4 me = S.slot[s];
+                            const uint2 ma = S.acc[s];
+                            const uint32_t h = ma.y, bin = h >> NB_SHIFT;
+                            const uint32_t m0 = S.pref[bin], m1 = S.pref[bin + 1];
+                            uint32_t rank = m0;
+                            for (uint32_t m = m0; m < m1; ++m) {
+                                const uint32_t u = members[m];
+                                if (u == e) continue;
+                                const uint32_t su = vs[u];
+                                const uint32_t hu = S.acc[su].y;
+                                if (hu < h) ++rank;
+                                else if (hu == h) {                             // same 32-bit hash: the k-mer decides
+                                    const uint4 o = S.slot[su];
+                                    if (o.x != me.x ? o.x < me.x : (o.y != me.y ? o.y < me.y : o.z < me.z)) ++rank;
+                                }
+                            }
+                            out[obase + rank] = make_uint4(me.x, me.y, me.z, min(ma.x, 0xFFFFFFu) | (((me.w >> 2) & 0xFFu) << 24));
+                        }
+                    }
+                }
+                run += tot;
+            }
+            if (mode == 0u) break;
+        }
+        // clean the table for the next pass
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) S.slot[j * T + tid].w = 0u;
+        if (tid == 0) S.over = 0;
+        __syncthreads();
+        if (overflowed) {
+            if (depth >= 20u) { if (tid == 0) atomicOr(err, 2u); total = 0; break; }
+            if (mode == 0u) mode = 1u;
+            ++depth; sub <<= 1;
+            continue;
+        }
+        while (depth > 0u && (sub & 1u)) { --depth; sub >>= 1; }
+        if (depth == 0u) {
+            if (mode == 2u) break;
+            if (tid == 0) S.out_base = total ? atomicAdd(out_cursor, (unsigned long long)total) : 0ull;
+            __syncthreads();
+            base = S.out_base;
+            mode = 2u; run = 0; depth = 1; sub = 0;
+            continue;
+        }
+        sub |= 1u;
+    }
+    if (tid == 0) {
+        seg_base[bkt] = base; seg_cnt[bkt] = total;
+        if (S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
+    }
+}
+
 // k-mer occurrences held by n records
 __global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, uint64_t n, unsigned long long* total)
 {

@@ -397,12 +397,20 @@ static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, u
         if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem<T, S>))); attr_set = true; } \
         k_bucket_count<T, S, I, M><<<n_buckets, T, sizeof(BcSmem<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
             scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3); } while (0)
+#define SN_BC2_LAUNCH(T, S, I, M) do { \
+        static bool attr_set = false; \
+        if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count2<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem2<T, S>))); attr_set = true; } \
+        k_bucket_count2<T, S, I, M><<<n_buckets, T, sizeof(BcSmem2<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
+            scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3); } while (0)
     switch (variant) {
+        case 1: SN_BC_LAUNCH(256, 2048, 4, 3); break;        // the two-phase insert (kept for A/B timing)
         case 4: SN_BC_LAUNCH(128, 1024, 4, 6); break;
-        case 5: SN_BC_LAUNCH(128, 1024, 2, 8); break;
-        default: SN_BC_LAUNCH(256, 2048, 4, 3); break;
+        case 11: SN_BC2_LAUNCH(128, 1024, 1, 6); break;
+        case 12: SN_BC2_LAUNCH(256, 2048, 2, 3); break;
+        default: SN_BC2_LAUNCH(256, 2048, 1, 3); break;     // the kernel is bound by the shared-memory LSU (atomics: 2 cycles/lane), not by latency: more items in flight do not help
     }
 #undef SN_BC_LAUNCH
+#undef SN_BC2_LAUNCH
     KCHECK("k_bucket_count");
     t_end(c, "bucket_count");
     // the buckets' survivor ranges, in bucket order
@@ -415,6 +423,7 @@ static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, u
     CU(cudaStreamSynchronize(c->st));
     if (h_err & 1u) return fail(c, SN_ERR_DATA, "k_bucket_count: more surviving k-mers than occurrences / min_freq (internal error)");
     if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table after 20 splits (pathological hash collisions)");
+    if (h_err & 4u) return fail(c, SN_ERR_DATA, "k_bucket_count: a claimed slot was never published (internal error)");
     t_begin(c, "make_dict");
     k_gather_survivors<<<std::min(blocks_for((uint64_t)n_buckets * 32, 256), 16u * (unsigned)c->num_sms), 256, 0, c->st>>>(scratch.as<uint4>(), seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(),
         off64.as<uint64_t>(), n_buckets, surv.as<uint4>());

@@ -123,3 +123,50 @@ def test_hash_collisions_are_separated(built):
         assert len(np.unique(hk)) < len(hk), "the data set does not exercise a collision"
         assert np.array_equal(km[:, :3], ok[:, :3])
         assert np.array_equal(km[:, 3], ok[:, 3] | (ok[:, 4] << 24))
+
+
+@pytest.mark.parametrize("min_bc", [2, 1, 0])
+def test_duplicate_reads_and_the_barcode_rule(built, min_bc):
+    """Identical reads (the same super-k-mers many times over: the count kernel expands one copy
+    and carries the number of copies and a summary of their barcodes) under every barcode
+    situation Kmerizer::reduce distinguishes: one barcode, two, unbarcoded copies, ignored
+    (-1) copies, and mixtures arriving in different orders."""
+    import supernova_b200 as sb
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(23)
+    groups = [
+        [5, 5, 5, 5, 5],            # one barcode only
+        [5, 5, 6, 6, 5],            # two barcodes
+        [0, 0, 0, 0],               # unbarcoded only
+        [0, 7, 7, 0, 7],            # unbarcoded + one barcode
+        [-1, 8, 8],                 # an ignored copy decides
+        [9, 9, -1, 9],
+        [0, -1, 0],
+        [10, 11, 12, 13, 10, 11],   # many barcodes
+        [14, 14],                   # below minFreq
+        [15, 16, 0, -1, 15, 16, 17],
+        [18, 0, 18, 19],
+    ]
+    reads, bcs = [], []
+    for g, barcodes in enumerate(groups):
+        locus = rng.integers(0, 4, size=220, dtype=np.uint8)
+        for c, b in enumerate(barcodes):
+            rd = locus[:150] if c % 3 != 2 else locus[40:190]          # full copies and a shifted overlapping read
+            reads.append(rd if c % 2 == 0 else (3 - rd[::-1]).astype(np.uint8))
+            bcs.append(b)
+    # shuffle so that copies of one read sit at different places of the bucket
+    perm = rng.permutation(len(reads))
+    codes = np.stack(reads)[perm]
+    bc = np.array(bcs, dtype=np.int32)[perm]
+    quals = np.full_like(codes, 37)
+    n = len(codes)
+    off = np.arange(n + 1, dtype=np.uint64) * 150
+    o = Oracle(codes.ravel(), quals.ravel(), off, bc, min_bc=min_bc).stage("count")
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes.ravel(), quals.ravel(), off)
+    with sb.Context(0) as ctx:
+        ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ctx.count_kmers(sb.Params(min_bc=min_bc))
+        km, ok = ctx.kmers(), o.kmers()
+        assert len(ok) > 0
+        assert np.array_equal(km[:, :3], ok[:, :3])
+        assert np.array_equal(km[:, 3], ok[:, 3] | (ok[:, 4] << 24))
