@@ -77,6 +77,13 @@ int  sn_device_count(void);
  * bc      : per-read barcode ordinal as expanded in 10X/DF.cc:464-469, or NULL.        */
 int sn_load_reads(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
                   const uint32_t* len, const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc);
+/* sn_load_reads with the good-length scan and the first MSP pass running under the copies
+ * (chunked copies on a second stream; host buffers should be page-locked).  params fixes
+ * min_qual for that work; the next sn_count_kmers / sn_build_read_qgraph48 with the same
+ * min_qual continues from there.  with_hist = 0: overlap the good lengths only (multi-GPU).  */
+int sn_load_reads_streamed(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
+                           const uint32_t* len, const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc,
+                           const sn_params* params, int with_hist);
 /* same with one unpacked Phred byte per base (qual_off = n_reads+1 element offsets)   */
 int sn_load_reads_q8(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
                      const uint32_t* len, const uint8_t* quals, const uint64_t* qual_off, const int32_t* bc);

@@ -45,6 +45,7 @@ def lib():
         L.sn_last_error.restype = C.c_char_p
         L.sn_load_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
         L.sn_load_reads_q8.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+        L.sn_load_reads_streamed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.sn_load_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_count_kmers.argtypes = [vp, C.POINTER(Params)]
         for f in ("sn_build_edges", "sn_build_hbv", "sn_path_reads"):
@@ -187,6 +188,11 @@ class Context:
     def load_reads_ptr(self, n, bases, boff, ln, pq, pqoff, bc):
         """Raw host addresses (e.g. pinned torch tensors)."""
         self._ck(self.L.sn_load_reads(self.h, n, bases, boff, ln, pq, pqoff, bc))
+
+    def load_reads_streamed_ptr(self, n, bases, boff, ln, pq, pqoff, bc, params=None, with_hist=True):
+        """sn_load_reads_streamed: chunked copies with the good lengths and the first MSP pass under them."""
+        params = params or Params()
+        self._ck(self.L.sn_load_reads_streamed(self.h, n, bases, boff, ln, pq, pqoff, bc, C.byref(params), 1 if with_hist else 0))
 
     def load_reads_q8(self, bases, boff, ln, quals, qoff, bc):
         a = [np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(boff, np.uint64), np.ascontiguousarray(ln, np.uint32),

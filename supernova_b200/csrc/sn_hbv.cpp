@@ -133,41 +133,58 @@ static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV,
 }
 
 // The same traversal over the one-line item records the device prepares (product path).  A popped
-// item costs one cache line, and that line was requested when the item was queued: vertex ids,
-// "vertex already expanded" and "item already queued" live in small byte/int arrays that stay
-// cache-resident, so the loop is not a chain of dependent misses even when a component is one long
-// chain of bubbles (queue length 2-4).
-struct NumberState { int32_t* vid; uint8_t* expanded; uint8_t* seen; int32_t* ids; };
+// item costs one cache line, and that line was requested when the item was queued.  What the loop
+// branches on -- "vertex already numbered" (the first item to reach a vertex numbers it AND pushes
+// its items, so one flag serves both) and "item already queued" -- lives in two byte arrays that stay
+// in L2 (bytes, not bits: components numbered by different threads share the arrays, never a byte);
+// the vertex ids themselves are only loaded, never branched on.  The
+// pushes are branch-free (store, then advance the tail by 0 or 1): on a long chain of bubbles
+// (queue length 2-4) the loop is otherwise a sequence of mispredicted branches on cache misses.
+struct NumberState { int32_t* vid; uint8_t* vbits; uint8_t* seen; int32_t* ids; };
+static inline bool bit_test_set(uint8_t* b, uint32_t i) { const bool was = b[i] != 0; b[i] = 1; return was; }
 static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& st, uint32_t start, int32_t& nextV, uint32_t& nH,
                       uint32_t* src, int32_t* to_left, int32_t* to_right, std::vector<uint32_t>& Q)
 {
     size_t qh = 0, qt = 0;
     if (Q.size() < 64) Q.resize(64);
-    Q[qt++] = start; st.seen[start] = 1;
+    Q[qt++] = start; bit_test_set(st.seen, start);
     while (qh < qt) {
         const uint32_t it = Q[qh++];
         const ItemRec& r = rec[it];
         if (r.g1 < 0 || r.g2 < 0) throw std::runtime_error("HBV: edge end without a vertex");
-        if (st.vid[r.g1] < 0) st.vid[r.g1] = nextV++;
-        if (st.vid[r.g2] < 0) st.vid[r.g2] = nextV++;
+        const bool new1 = !bit_test_set(st.vbits, (uint32_t)r.g1);
+        if (new1) st.vid[r.g1] = nextV++;
+        const bool new2 = !bit_test_set(st.vbits, (uint32_t)r.g2);         // (g1 == g2: already set)
+        if (new2) st.vid[r.g2] = nextV++;
         const int32_t id = (int32_t)nH++;
         src[id] = it; to_left[id] = st.vid[r.g1]; to_right[id] = st.vid[r.g2];
         st.ids[it] = id;
-        if ((r.info >> 8) & 1u) { st.ids[it ^ 1u] = id; st.seen[it ^ 1u] = 1; }
+        if ((r.info >> 8) & 1u) { st.ids[it ^ 1u] = id; bit_test_set(st.seen, it ^ 1u); }
         if (qt + 24 > Q.size()) {                           // keep the FIFO compact
             std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
             if (qt + 24 > Q.size()) Q.resize(2 * Q.size());
         }
+        uint32_t* q = Q.data();
         for (int side = 0; side < 2; ++side) {
+            if (!(side ? new2 : new1)) continue;            // the vertex pushed its items when it was numbered
             const int32_t g = side ? r.g2 : r.g1;
-            if (st.expanded[g]) continue;
-            st.expanded[g] = 1;
             uint32_t n = (r.info >> (4 * side)) & 15u;
             const uint32_t* items = side ? r.it2 : r.it1;
-            if (n == 15u) { n = groups[g].n; items = groups[g].items; }          // more than 6 edge ends on this vertex
-            for (uint32_t x = 0; x < n; ++x) {
-                const uint32_t t2 = items[x];
-                if (!st.seen[t2]) { st.seen[t2] = 1; Q[qt++] = t2; __builtin_prefetch(&rec[t2]); }
+            if (n == 15u) {                                  // more than 6 edge ends on this vertex
+                n = groups[g].n; items = groups[g].items;
+                for (uint32_t x = 0; x < n; ++x) {
+                    const uint32_t t2 = items[x];
+                    if (!bit_test_set(st.seen, t2)) { q[qt++] = t2; __builtin_prefetch(&rec[t2]); }
+                }
+                continue;
+            }
+#pragma GCC unroll 6
+            for (uint32_t x = 0; x < 6; ++x) {
+                const bool live = x < n;
+                const uint32_t t2 = live ? items[x] : start;                  // (start is queued: a dead lane pushes nothing)
+                __builtin_prefetch(&rec[t2]);
+                const bool was = bit_test_set(st.seen, t2);
+                q[qt] = t2; qt += was ? 0u : 1u;
             }
         }
     }
@@ -185,9 +202,25 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
     H.src.resize(nH); H.to_left.resize(nH); H.to_right.resize(nH);      // (no reallocation when the caller sized them already)
     H.fwd.resize(nE); H.rev.resize(nE);
     std::vector<int32_t> vid(nV, -1), ids(2 * nE, -1);
-    std::vector<uint8_t> expanded(nV, 0), seen(2 * nE, 0);
-    NumberState st{vid.data(), expanded.data(), seen.data(), ids.data()};
+    std::vector<uint8_t> vbits(nV + 1, 0), seen(2 * nE + 1, 0);
+    NumberState st{vid.data(), vbits.data(), seen.data(), ids.data()};
     if (!threads) threads = 1;
+    // Work units: a big component on its own (both strands of a well-covered genome are one giant
+    // component each, and they sit next to each other at the head of the list: they must not share a
+    // thread), small components 256 at a time.
+    std::vector<uint64_t> unit_start;
+    {
+        uint64_t c = 0;
+        while (c < C.n_comp) {
+            unit_start.push_back(c);
+            if (C.base_e[c + 1] - C.base_e[c] >= 4096) { ++c; continue; }
+            uint64_t e = c, lim = std::min<uint64_t>(C.n_comp, c + 256);
+            while (e < lim && C.base_e[e + 1] - C.base_e[e] < 4096) ++e;
+            c = e;
+        }
+        unit_start.push_back(C.n_comp);
+    }
+    const uint64_t n_units = unit_start.size() - 1;
     std::atomic<uint64_t> next{0};
     std::atomic<int> bad{0};
     std::string what;
@@ -195,22 +228,36 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
         std::vector<uint32_t> Q(1024);
         try {
             for (;;) {
-                const uint64_t c0 = next.fetch_add(256);
-                if (c0 >= C.n_comp || bad.load()) break;
-                const uint64_t c1 = std::min<uint64_t>(C.n_comp, c0 + 256);
-                for (uint64_t c = c0; c < c1; ++c) {
+                const uint64_t u = next.fetch_add(1);
+                if (u >= n_units || bad.load()) break;
+                for (uint64_t c = unit_start[u]; c < unit_start[u + 1]; ++c) {
                     int32_t nextV = (int32_t)C.base_v[c]; uint32_t nh = (uint32_t)C.base_e[c];
-                    bfs_items(items, groups, st, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                    if (C.base_e[c + 1] - C.base_e[c] >= 32768 && threads > 1) {
+                        // A giant component works on private state: the items of the two strand components
+                        // interleave in every cache line of the shared arrays, and two threads numbering
+                        // them side by side would spend their time passing those lines back and forth.
+                        std::vector<int32_t> pvid(nV, -1), pids(2 * nE, -1);
+                        std::vector<uint8_t> pvb(nV + 1, 0), pseen(2 * nE + 1, 0);
+                        NumberState ps{pvid.data(), pvb.data(), pseen.data(), pids.data()};
+                        bfs_items(items, groups, ps, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                        for (uint64_t h = C.base_e[c]; h < (uint64_t)nh; ++h) {
+                            const uint32_t it = H.src[h];
+                            ids[it] = (int32_t)h;
+                            if ((items[it].info >> 8) & 1u) ids[it ^ 1u] = (int32_t)h;
+                        }
+                    } else
+                        bfs_items(items, groups, st, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
                     if ((uint64_t)nextV != C.base_v[c + 1] || (uint64_t)nh != C.base_e[c + 1])
                         throw std::runtime_error("HBV: a component was not numbered completely");
                 }
             }
         } catch (const std::exception& ex) { if (!bad.exchange(1)) what = ex.what(); }
     };
-    if (threads <= 1 || C.n_comp < 1024) worker();
+    if (threads <= 1 || n_units < 2) worker();
     else {
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < threads; ++t) th.emplace_back(worker);
+        const unsigned nt = (unsigned)std::min<uint64_t>(threads, n_units);
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(worker);
         for (auto& x : th) x.join();
     }
     if (bad.load()) throw std::runtime_error(what);

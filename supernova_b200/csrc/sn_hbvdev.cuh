@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(256) k_hbv_flatten(uint32_t* parent, uint32_t 
     if (g >= n) return;
     const uint32_t r = uf_find(parent, g);
     comp[g] = r;
-    atomicAdd(cnt_v + r, 1u);
+    // one atomic per component and warp: a well-covered genome is one giant component per strand,
+    // and every vertex adding to the same address serialises in the L2
+    const unsigned m = __match_any_sync(__activemask(), r);
+    if ((threadIdx.x & 31u) == (uint32_t)__ffs((int)m) - 1u) atomicAdd(cnt_v + r, (uint32_t)__popc(m));
 }
 // per component: number of HBV edges, and the first item of the reference's outer loop
 // (pass 0 = forward items in edge order, pass 1 = reverse items): min of (rc, rank)
@@ -158,8 +161,12 @@ __global__ void __launch_bounds__(256) k_hbv_compstats(const snh::ERec* __restri
     const int32_t g1 = er[t].g1;
     if (g1 < 0 || er[t].g2 < 0) return;
     const uint32_t r = comp[g1];
-    atomicMin(ckey + r, ((unsigned long long)(t & 1u) << 32) | rank[t >> 1]);
-    atomicAdd(cnt_e + r, 1u);
+    // aggregated per component inside the warp (see k_hbv_flatten): min of the 33-bit keys, count
+    const unsigned m = __match_any_sync(__activemask(), r);
+    const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)m) - 1u;
+    const uint32_t k32 = __reduce_min_sync(m, ((t & 1u) << 31) | rank[t >> 1]);       // rank < 2^31 unipaths
+    const unsigned long long best = ((unsigned long long)(k32 >> 31) << 32) | (k32 & 0x7FFFFFFFu);
+    if (lane == leader) { atomicMin(ckey + r, best); atomicAdd(cnt_e + r, (uint32_t)__popc(m)); }
 }
 __global__ void __launch_bounds__(256) k_hbv_rootflag(const uint32_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ flag)
 {

@@ -77,6 +77,10 @@ struct Timer { cudaEvent_t a = nullptr, b = nullptr; bool used = false; };
 struct sn_ctx {
     int device = 0, num_sms = 148;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;                 // copy stream of sn_load_reads_streamed
+    cudaEvent_t ev_copy[16] = {};
+    // work sn_load_reads_streamed already did under the copies; consumed by the next count call only
+    bool gl_ready = false; uint32_t gl_min_qual = 0; uint64_t gl_occ = 0; int hist_ready_bits = -1;
     std::string err;
     uint64_t launches = 0;
     std::map<std::string, Timer> timers;
@@ -170,6 +174,7 @@ int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_
     if (!n_reads || !bases || !base_off || !len) return fail(c, SN_ERR_ARG, "sn_load_reads: empty or NULL input");
     if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
     c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->gl_ready = false; c->hist_ready_bits = -1;
     c->cnt.n_reads = n_reads;
     t_begin(c, "h2d");
     int r;
@@ -245,6 +250,8 @@ void sn_ctx_destroy(sn_ctx* c)
     cudaStreamSynchronize(c->st);
     for (auto& kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     unpin_all(c);
+    for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->st2) cudaStreamDestroy(c->st2);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -307,6 +314,13 @@ int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
 
 // ---------------------------------------------------------------------------
 // ---- pieces of the count stage (shared by the single-GPU call and the multi-GPU calls) ----
+static int pick_bucket_bits(uint64_t n_occ)
+{
+    int bits = msp_bucket_bits(n_occ);
+    if (const char* e = getenv("SN_MSP_OCC")) { int t = atoi(e); if (t >= 64) { bits = 4; while (bits < 24 && (n_occ >> bits) > (uint64_t)t) ++bits; } }
+    if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
+    return bits;
+}
 static int count_set_params(sn_ctx* c, const sn_params* p)
 {
     if (p) c->params = *p;
@@ -318,6 +332,11 @@ static int count_set_params(sn_ctx* c, const sn_params* p)
 static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
 {
     const uint64_t n = c->cnt.n_reads;
+    if (c->gl_ready) {                           // computed under the copies of sn_load_reads_streamed (once: a repeated count recomputes)
+        c->gl_ready = false;
+        if (c->gl_min_qual == c->params.min_qual) { c->cnt.n_kmer_occurrences = c->gl_occ; *n_occ_out = c->gl_occ; return SN_OK; }
+    }
+    c->hist_ready_bits = -1;
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [0] occurrences, [1] cursor, [2] distinct
     uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [0] bad reads, [3] reduce overflow
     CU(cudaMemsetAsync(c->counters.p, 0, 256, c->st));
@@ -353,10 +372,13 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
     CU(hist.alloc(4 * nb)); CU(off.alloc(8 * (nb + 1)));
     const int32_t* bc = c->have_bc ? c->bc.as<int32_t>() : nullptr;
     t_begin(c, "msp_hist");
-    CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
-    k_msp_scan<false><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
-    KCHECK("k_msp_scan<hist>");
+    if (c->hist_ready_bits != bits) {            // (else: the histogram was built under the copies of sn_load_reads_streamed)
+        CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
+        k_msp_scan<false><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
+        KCHECK("k_msp_scan<hist>");
+    }
+    c->hist_ready_bits = -1;
     uint64_t n_sk = 0;
     int r = scan_u32(c, hist.as<uint32_t>(), nb, off.as<uint64_t>(), &n_sk);
     if (r) return r;
@@ -472,6 +494,107 @@ static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int b
     return SN_OK;
 }
 
+// sn_load_reads with the first two stages of the count running UNDER the copies: the reads travel
+// in chunks on a copy stream -- quals first, then bases -- and as soon as a chunk has landed its
+// good lengths (a1) and, once those fix the bucket count, its share of the super-k-mer histogram
+// (a14, first pass) are computed on the compute stream.  The PCIe link never waits for a kernel; the
+// next sn_count_kmers (same min_qual) starts at the scatter pass.  with_hist = 0 (multi-GPU: the
+// bucket count comes from an allreduce) overlaps the good lengths only.
+int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,
+                           const uint8_t* pq, const uint64_t* pq_off, const int32_t* bc, const sn_params* p, int with_hist)
+{
+    if (!c) return SN_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (!n_reads || !bases || !base_off || !len || !pq || !pq_off) return fail(c, SN_ERR_ARG, "sn_load_reads_streamed: empty or NULL input");
+    if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
+    int r;
+    if ((r = count_set_params(c, p))) return r;
+    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->gl_ready = false; c->hist_ready_bits = -1;
+    c->cnt.n_reads = n_reads;
+    const uint64_t n = n_reads;
+    constexpr int MAXCH = 8;
+    const int nch = n >= (1u << 16) ? 4 : 1;
+    if (!c->st2) {
+        CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * MAXCH; ++i) CU(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+    }
+    c->have_bc = bc != nullptr; c->have_pq = true; c->quals.release();
+    CU(c->bases.alloc(base_off[n] + 64)); CU(c->boff.alloc(8 * (n + 1))); CU(c->len.alloc(4 * n));
+    if (bc) CU(c->bc.alloc(4 * n));
+    CU(c->pq.alloc(pq_off[n] + 16)); CU(c->pqoff.alloc(8 * (n + 1))); CU(c->goodlen.alloc(4 * n));
+    unsigned long long* occ = c->counters.as<unsigned long long>();
+    uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);
+    unsigned long long* cnt64 = occ + 16;
+    CU(cudaMemsetAsync(c->counters.p, 0, 256, c->st));
+    CU(cudaMemsetAsync((char*)c->bases.p + base_off[n], 0, 64, c->st));
+    CU(cudaMemsetAsync((char*)c->pq.p + pq_off[n], 0, 16, c->st));
+    CU(cudaEventRecord(c->ev_copy[0], c->st));
+    CU(cudaStreamWaitEvent(c->st2, c->ev_copy[0], 0));            // nothing of an earlier step still reads the buffers
+    auto lo = [&](int ch) { return n * (uint64_t)ch / (uint64_t)nch; };
+    auto bail = [&](int rc) { cudaStreamSynchronize(c->st2); cudaStreamSynchronize(c->st); return rc; };
+#define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(c, SN_ERR_CUDA, cudaGetErrorString(e_))); } while (0)
+    t_begin(c, "goodlen");
+    for (int ch = 0; ch < nch; ++ch) {                             // quals -> good lengths
+        const uint64_t r0 = lo(ch), r1 = lo(ch + 1);
+        CUB_(cudaMemcpyAsync(c->pq.as<uint8_t>() + pq_off[r0], pq + pq_off[r0], pq_off[r1] - pq_off[r0], cudaMemcpyHostToDevice, c->st2));
+        CUB_(cudaMemcpyAsync(c->pqoff.as<uint64_t>() + r0, pq_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, c->st2));
+        CUB_(cudaMemcpyAsync(c->len.as<uint32_t>() + r0, len + r0, 4 * (r1 - r0), cudaMemcpyHostToDevice, c->st2));
+        CUB_(cudaEventRecord(c->ev_copy[ch], c->st2));
+        CUB_(cudaStreamWaitEvent(c->st, c->ev_copy[ch], 0));
+        k_pqvec_goodlen<<<blocks_for(r1 - r0, 256), 256, 0, c->st>>>(r1 - r0, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>() + r0, c->len.as<uint32_t>() + r0,
+            c->params.min_qual, c->goodlen.as<uint32_t>() + r0, occ, u32c);
+        ++c->launches;
+    }
+    t_end(c, "goodlen");
+    for (int ch = 0; ch < nch; ++ch) {                             // bases (the copies queue up behind the quals)
+        const uint64_t r0 = lo(ch), r1 = lo(ch + 1);
+        CUB_(cudaMemcpyAsync(c->bases.as<uint8_t>() + base_off[r0], bases + base_off[r0], base_off[r1] - base_off[r0], cudaMemcpyHostToDevice, c->st2));
+        CUB_(cudaMemcpyAsync(c->boff.as<uint64_t>() + r0, base_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, c->st2));
+        if (bc) CUB_(cudaMemcpyAsync(c->bc.as<int32_t>() + r0, bc + r0, 4 * (r1 - r0), cudaMemcpyHostToDevice, c->st2));
+        CUB_(cudaEventRecord(c->ev_copy[MAXCH + ch], c->st2));
+    }
+    unsigned long long h_occ = 0; uint32_t h_bad = 0;
+    CUB_(cudaMemcpyAsync(&h_occ, occ, 8, cudaMemcpyDeviceToHost, c->st));
+    CUB_(cudaMemcpyAsync(&h_bad, u32c, 4, cudaMemcpyDeviceToHost, c->st));
+    CUB_(cudaStreamSynchronize(c->st));                             // the good lengths are done; the bases are still arriving
+    if (h_bad) return bail(fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count"));
+    if (h_occ >= (1ull << 32)) return bail(fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads over more GPUs"));
+    const int bits = pick_bucket_bits(h_occ);
+    const uint64_t nb = 1ull << bits;
+    DevBuf& hist = c->pool["sk_hist"];
+    if (with_hist && h_occ) {
+        CUB_(hist.alloc(4 * nb));
+        CUB_(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+        const uint64_t r0 = lo(ch), r1 = lo(ch + 1);
+        CUB_(cudaStreamWaitEvent(c->st, c->ev_copy[MAXCH + ch], 0));
+        if (with_hist && h_occ) {
+            k_msp_scan<false><<<blocks_for(r1 - r0, SN_MS_READS), SN_MS_READS, 0, c->st>>>(r1 - r0, c->bases.as<uint8_t>(), c->boff.as<uint64_t>() + r0,
+                c->goodlen.as<uint32_t>() + r0, nullptr, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
+            ++c->launches;
+        }
+    }
+    k_read_stats<<<std::min(blocks_for(n, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(n, c->len.as<uint32_t>(), c->have_bc ? c->bc.as<int32_t>() : nullptr,
+        cnt64, reinterpret_cast<uint32_t*>(cnt64 + 1), reinterpret_cast<int32_t*>(cnt64 + 1) + 1);
+    ++c->launches;
+    unsigned long long h[2] = {0, 0};
+    CUB_(cudaMemcpyAsync(h, cnt64, 16, cudaMemcpyDeviceToHost, c->st));
+    CUB_(cudaStreamSynchronize(c->st));                             // (st waited for every copy event: the caller's buffers are free again)
+    CUB_(cudaGetLastError());
+#undef CUB_
+    c->cnt.n_bases = h[0];
+    const uint32_t max_len = (uint32_t)(h[1] & 0xFFFFFFFFu); const int32_t max_bc = (int32_t)(h[1] >> 32);
+    if (max_len > SN_MAX_READ_LEN) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    if (max_bc >= 0xFFFFFF) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
+    c->cnt.n_kmer_occurrences = h_occ;
+    c->gl_ready = true; c->gl_min_qual = c->params.min_qual; c->gl_occ = h_occ;
+    c->hist_ready_bits = (with_hist && h_occ) ? bits : -1;
+    c->stage = 1;
+    return SN_OK;
+}
+
 int sn_count_kmers(sn_ctx* c, const sn_params* p)
 {
     if (!c) return SN_ERR_ARG;
@@ -480,9 +603,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     int r; uint64_t n_occ = 0, n_sk = 0;
     if ((r = count_set_params(c, p))) return r;
     if ((r = count_goodlen(c, &n_occ))) return r;
-    int bits = msp_bucket_bits(n_occ);
-    if (const char* e = getenv("SN_MSP_OCC")) { int t = atoi(e); if (t >= 64) { bits = 4; while (bits < 24 && (n_occ >> bits) > (uint64_t)t) ++bits; } }
-    if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
+    const int bits = pick_bucket_bits(n_occ);
     if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
     c->cnt.n_superkmers = n_sk;
     uint64_t n_surv = 0;

@@ -172,3 +172,34 @@ def test_c2_idempotent(c2, sb):
     assert all(np.array_equal(a, b) for a, b in zip(p0, p1))
     # the edge ORDER may differ between runs (atomics); the set and the HBV built from it do not
     assert np.array_equal(np.sort(e0[0]), np.sort(e1[0]))
+
+
+def test_streamed_load_matches_plain_load(sb, tmp_path):
+    """sn_load_reads_streamed (chunked copies, good lengths + first MSP pass under them) leaves the
+    context exactly where sn_load_reads + the same stages would: identical k-mers, HBV and paths;
+    a second build on the same context recomputes everything and agrees again."""
+    import torch
+    codes, quals, off, bc, _ = datasets.get("mid")
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    with sb.Context(0) as ref:
+        ref.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ref.build_read_qgraph48(None, sb.Params(), with_paths=True)
+        k0, h0, p0, g0 = ref.kmers(), ref.hbv(), ref.paths(), ref.good_lengths()
+    host = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (pb, boff, ln, pq, pqoff, np.ascontiguousarray(bc, np.int32))]
+    ptrs = [t.data_ptr() for t in host]
+    for with_hist in (True, False):
+        with sb.Context(0) as ctx:
+            ctx.load_reads_streamed_ptr(len(ln), *ptrs, params=sb.Params(), with_hist=with_hist)
+            for rep in range(2):
+                ctx.build_read_qgraph48(None, sb.Params(), with_paths=True)
+                assert np.array_equal(ctx.good_lengths(), g0)
+                assert np.array_equal(ctx.kmers(), k0)
+                h1, p1 = ctx.hbv(), ctx.paths()
+                assert all(np.array_equal(h0[x], h1[x]) for x in h0)
+                assert all(np.array_equal(a, b) for a, b in zip(p0, p1))
+            # a different min_qual must not reuse the good lengths computed at load time
+        with sb.Context(0) as ctx:
+            ctx.load_reads_streamed_ptr(len(ln), *ptrs, params=sb.Params(min_qual=20), with_hist=with_hist)
+            ctx.build_read_qgraph48(None, sb.Params(), with_paths=False)
+            assert np.array_equal(ctx.good_lengths(), g0)
+            assert np.array_equal(ctx.kmers(), k0)
