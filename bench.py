@@ -37,6 +37,8 @@ WORKLOADS = {
     "C2": (63_000_000, 4_000_000, 1_000_000, 20261017),
     # BASELINE.json's "56x of a 63 Mbp diploid" taken literally (3.53 Gbp); reported next to C2
     "C2b": (63_000_000, 11_760_000, 1_000_000, 20261017),
+    # 7.2 Gbp on ONE GPU: 4.7 G k-mer occurrences (> 2^32), counted in three passes over bucket ranges
+    "C2x6": (63_000_000, 24_000_000, 1_000_000, 20261017),
     "mid": (2_000_000, 373_333, 50_000, 20261017),
     "C1": (50_000, 10_000, 500, 1234),
 }

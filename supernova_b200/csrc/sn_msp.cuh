@@ -133,10 +133,10 @@ SN_HD void sk_occurrence(const uint32_t* w, uint32_t i, Kmer* out, uint32_t* ctx
     *out = k; *ctx_out = ctx;
 }
 
-// number of bucket bits for n_occ k-mer occurrences: 1536..3072 occurrences per bucket.  The
-// shared-memory table of k_bucket_count takes 1536 distinct k-mers per pass; sequencing data has
-// 0.15-0.3 distinct k-mers per occurrence (C2: 0.25), so a bucket normally needs one pass.
-#define SN_MSP_TARGET_OCC 3072
+// number of bucket bits for n_occ k-mer occurrences: 768..1536 occurrences per bucket.  The
+// shared-memory table of k_bucket_count2 has 1024 slots; sequencing data has 0.15-0.3 distinct
+// k-mers per occurrence (C2: 0.25), so a bucket normally needs one pass at <= 40 % load.
+#define SN_MSP_TARGET_OCC 1536
 inline int msp_bucket_bits(uint64_t n_occ)
 {
     int b = 4;
@@ -163,8 +163,11 @@ namespace sn {
 template <bool EMIT>
 __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                             const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
-                                                            int bits, uint32_t* __restrict__ counter /* hist or cursor, 2^bits */,
-                                                            const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs)
+                                                            int bits, uint32_t* __restrict__ counter /* hist or cursor, one per bucket of the window */,
+                                                            const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
+                                                            uint32_t b_lo = 0u, uint32_t b_n = 0xFFFFFFFFu /* bucket window [b_lo, b_lo + b_n): a count in several passes */,
+                                                            uint2* __restrict__ dsc = nullptr, uint8_t* __restrict__ nruns = nullptr /* out: the runs of every read (see k_msp_place) */,
+                                                            const uint8_t* __restrict__ only_overflow = nullptr /* in: handle only the reads whose runs did not fit the descriptors */)
 {
     __shared__ __align__(16) uint8_t sb[SN_MS_BYTES];
     __shared__ uint32_t ring[SN_W * SN_MS_READS];
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
     if (tid >= nr) return;
     const uint64_t r = r0 + tid;
     const uint32_t gl = goodlen[r];
-    if (gl < SN_K + 1) return;
+    if (only_overflow && only_overflow[r] != 255u) return;
+    if (gl < SN_K + 1) { if (nruns) nruns[r] = 0; return; }
     const uint8_t* rp = sb + (uint32_t)(boff[r] - lo) + shift;
     uint32_t bc24 = 0xFFFFFFu;
     if (EMIT) {
@@ -197,7 +201,8 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
     const int sh = 32 - bits;
     auto process = [&](uint32_t start, uint32_t nk, uint32_t minval) {
         const uint32_t bh = bucket_hash(minval);
-        const uint32_t bkt = bh >> sh;
+        const uint32_t bkt = (bh >> sh) - b_lo;
+        if (bkt >= b_n) return;                            // another pass's bucket
         if (!EMIT) atomicAdd(&counter[bkt], 1u);
         else {
             const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
@@ -209,12 +214,75 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
     };
     // the runs are queued while the read is scanned and handled afterwards, so that the scan loop
     // itself stays free of divergent work (a run ends at a different base in every lane)
-    uint32_t nq = 0;
+    uint32_t nq = 0, nrun = 0;
     msp_scan(rp, gl, ring + tid, SN_MS_READS, [&](uint32_t start, uint32_t nk, uint32_t minval) {
+        ++nrun;
         if (nq < SN_MS_QUEUE) { qv[nq * SN_MS_READS + tid] = minval; qs[nq * SN_MS_READS + tid] = start | (nk << 16); ++nq; }
         else process(start, nk, minval);
     });
+    // the runs of the read, kept for the passes that follow (scatter, further bucket windows): [block][slot][thread],
+    // so that a warp reads and writes them coalesced; a read with more runs than slots is marked and scanned again
+    if (nruns) {
+        nruns[r] = nrun <= SN_MS_QUEUE ? (uint8_t)nrun : (uint8_t)255;
+        uint2* d = dsc + (uint64_t)blockIdx.x * SN_MS_QUEUE * SN_MS_READS + tid;
+        if (nrun <= SN_MS_QUEUE) for (uint32_t e = 0; e < nq; ++e) d[e * SN_MS_READS] = make_uint2(qv[e * SN_MS_READS + tid], qs[e * SN_MS_READS + tid]);
+    }
     for (uint32_t e = 0; e < nq; ++e) { const uint32_t x = qs[e * SN_MS_READS + tid]; process(x & 0xFFFFu, x >> 16, qv[e * SN_MS_READS + tid]); }
+}
+
+// k_msp_place: the histogram (EMIT = false) or the scatter (EMIT = true) of the super-k-mers from the run
+// descriptors the first scan left behind -- no minimizer is computed twice.  Same thread mapping as
+// k_msp_scan (the descriptors are indexed by its blocks); reads marked 255 are left to k_msp_scan.
+template <bool EMIT>
+__global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+                                                             const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
+                                                             int bits, uint32_t* __restrict__ counter, const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
+                                                             uint32_t b_lo, uint32_t b_n, const uint2* __restrict__ dsc, const uint8_t* __restrict__ nruns)
+{
+    __shared__ __align__(16) uint8_t sb[EMIT ? SN_MS_BYTES : 16];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.x * SN_MS_READS;
+    const uint32_t nr = (uint32_t)min((uint64_t)SN_MS_READS, n_reads - r0);
+    uint64_t lo = 0; uint32_t shift = 0;
+    if (EMIT) {
+        lo = boff[r0]; const uint64_t hi = boff[r0 + nr];
+        const uint64_t lo_al = lo & ~15ull;
+        shift = (uint32_t)(lo - lo_al);
+        const uint4* src = reinterpret_cast<const uint4*>(bases + lo_al);
+        uint4* dst = reinterpret_cast<uint4*>(sb);
+        uint32_t nv = (uint32_t)((hi - lo_al + 32 + 15) >> 4);
+        if (nv > SN_MS_BYTES / 16) nv = SN_MS_BYTES / 16;
+        for (uint32_t i = tid; i < nv; i += SN_MS_READS) dst[i] = src[i];
+        __syncthreads();
+    }
+    if (tid >= nr) return;
+    const uint64_t r = r0 + tid;
+    const uint32_t n = nruns[r];
+    if (n == 0u || n == 255u) return;
+    const uint32_t gl = EMIT ? goodlen[r] : 0u;
+    const uint8_t* rp = sb + (uint32_t)(EMIT ? boff[r] - lo : 0) + shift;
+    uint32_t bc24 = 0xFFFFFFu;
+    if (EMIT) {
+        int32_t b = -1;
+        if (bc && (int64_t)r >= ign_bc_below) b = bc[r];
+        bc24 = b < 0 ? 0xFFFFFFu : (uint32_t)b;
+    }
+    const int sh = 32 - bits;
+    const uint2* d = dsc + (uint64_t)blockIdx.x * SN_MS_QUEUE * SN_MS_READS + tid;
+    for (uint32_t e = 0; e < n; ++e) {
+        const uint2 x = d[e * SN_MS_READS];
+        const uint32_t bh = bucket_hash(x.x);
+        const uint32_t bkt = (bh >> sh) - b_lo;
+        if (bkt >= b_n) continue;
+        if (!EMIT) atomicAdd(&counter[bkt], 1u);
+        else {
+            const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
+            uint32_t w[SN_SK_WORDS];
+            sk_build(rp, gl, x.y & 0xFFFFu, x.y >> 16, bc24, bh, w);
+            recs[2 * pos] = make_uint4(w[0], w[1], w[2], w[3]);
+            recs[2 * pos + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -922,7 +990,7 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
             if (mode == 1u) total += tot;
             else if (tot) {
                 // ---- order the pass's survivors by (hash, k-mer) and write them (see k_bucket_count) ----
-                constexpr int NB = T, NB_SHIFT = 32 - (T == 128 ? 7 : (T == 256 ? 8 : 9));
+                constexpr int NB = T, NB_SHIFT = 32 - (T == 64 ? 6 : (T == 128 ? 7 : (T == 256 ? 8 : 9)));
                 uint16_t* vs = reinterpret_cast<uint16_t*>(S.rec);
                 uint16_t* members = vs + SLOTS;
                 {

@@ -314,6 +314,7 @@ int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
 
 // ---------------------------------------------------------------------------
 // ---- pieces of the count stage (shared by the single-GPU call and the multi-GPU calls) ----
+static uint32_t mg_first_bucket(uint32_t owner, uint32_t nparts, int bits) { return (uint32_t)((((uint64_t)owner << bits) + nparts - 1) / nparts); }
 static int pick_bucket_bits(uint64_t n_occ)
 {
     int bits = msp_bucket_bits(n_occ);
@@ -358,16 +359,18 @@ static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
     CU(cudaStreamSynchronize(c->st));
     if (h_bad) return fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count");
     c->cnt.n_kmer_occurrences = h_occ;
-    if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads over more GPUs");
     *n_occ_out = h_occ;
     return SN_OK;
 }
 // a14 (MSP): cuts this context's reads into super-k-mers and groups them by minimizer bucket:
 // pool["sk_recs"] (32-byte records, bucket order) and pool["sk_off"] (2^bits + 1 record offsets).
-static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
+static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo = 0, uint32_t b_n = 0)
 {
     const uint64_t n = c->cnt.n_reads;
-    const uint64_t nb = 1ull << bits;
+    const bool window = b_n != 0;                 // a count in several passes: only the buckets [b_lo, b_lo + b_n)
+    const uint64_t nb = window ? b_n : 1ull << bits;
+    const uint32_t w_lo = window ? b_lo : 0u, w_n = window ? b_n : 0xFFFFFFFFu;
+    if (window) c->hist_ready_bits = -1;
     DevBuf &hist = c->pool["sk_hist"], &off = c->pool["sk_off"], &recs = c->pool["sk_recs"];
     CU(hist.alloc(4 * nb)); CU(off.alloc(8 * (nb + 1)));
     const int32_t* bc = c->have_bc ? c->bc.as<int32_t>() : nullptr;
@@ -375,7 +378,7 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
     if (c->hist_ready_bits != bits) {            // (else: the histogram was built under the copies of sn_load_reads_streamed)
         CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
         k_msp_scan<false><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
+            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n);
         KCHECK("k_msp_scan<hist>");
     }
     c->hist_ready_bits = -1;
@@ -388,7 +391,7 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out)
     t_begin(c, "msp_scatter");
     CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));                 // now the per-bucket cursors
     k_msp_scan<true><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>());
+        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n);
     KCHECK("k_msp_scan<scatter>");
     t_end(c, "msp_scatter");
     return SN_OK;
@@ -427,9 +430,12 @@ static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, u
     switch (variant) {
         case 1: SN_BC_LAUNCH(256, 2048, 4, 3); break;        // the two-phase insert (kept for A/B timing)
         case 4: SN_BC_LAUNCH(128, 1024, 4, 6); break;
-        case 11: SN_BC2_LAUNCH(128, 1024, 1, 6); break;
-        case 12: SN_BC2_LAUNCH(256, 2048, 2, 3); break;
-        default: SN_BC2_LAUNCH(256, 2048, 1, 3); break;     // the kernel is bound by the shared-memory LSU (atomics: 2 cycles/lane), not by latency: more items in flight do not help
+        case 12: SN_BC2_LAUNCH(256, 2048, 1, 3); break;      // with SN_MSP_OCC=3072
+        case 31: SN_BC2_LAUNCH(64, 512, 1, 12); break;       // with SN_MSP_OCC=768
+        // 4 warps per bucket, 6 buckets per SM: the kernel is bound by the shared-memory LSU (atomics: 2 cycles/lane) and
+        // by the barriers around its per-bucket phases, not by latency -- more occurrences in flight per thread do not help,
+        // smaller CTAs do (C2: 256 threads x 2048 slots 13.7 ms, 128 x 1024 12.6 ms, 64 x 512 16.3 ms)
+        default: SN_BC2_LAUNCH(128, 1024, 1, 6); break;
     }
 #undef SN_BC_LAUNCH
 #undef SN_BC2_LAUNCH
@@ -559,8 +565,8 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     CUB_(cudaMemcpyAsync(&h_bad, u32c, 4, cudaMemcpyDeviceToHost, c->st));
     CUB_(cudaStreamSynchronize(c->st));                             // the good lengths are done; the bases are still arriving
     if (h_bad) return bail(fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count"));
-    if (h_occ >= (1ull << 32)) return bail(fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences in one context: shard the reads over more GPUs"));
     const int bits = pick_bucket_bits(h_occ);
+    if (h_occ >= (1ull << 31)) with_hist = 0;                      // counted in several passes: each pass has its own histogram
     const uint64_t nb = 1ull << bits;
     DevBuf& hist = c->pool["sk_hist"];
     if (with_hist && h_occ) {
@@ -604,12 +610,58 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if ((r = count_set_params(c, p))) return r;
     if ((r = count_goodlen(c, &n_occ))) return r;
     const int bits = pick_bucket_bits(n_occ);
-    if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
-    c->cnt.n_superkmers = n_sk;
-    uint64_t n_surv = 0;
+    // One pass holds < 2^32 k-mer occurrences (32-bit positions inside k_bucket_count's output) and its
+    // super-k-mer records in HBM.  More occurrences than 2^31 are counted in several passes over
+    // consecutive bucket ranges: every pass scans the resident reads again (0.25 B/base, cheap next to the
+    // count itself) and keeps only its buckets; the passes' survivors, concatenated, are in bucket order.
+    uint32_t passes = (uint32_t)((n_occ >> 31) + 1);
+    if (const char* e = getenv("SN_COUNT_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 4096) passes = (uint32_t)v; }     // tests
+    if (passes > (1u << bits)) passes = 1u << bits;
     DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
-    if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, surv, surv_off, &n_surv))) return r;
-    return msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true);
+    if (passes == 1) {
+        if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
+        c->cnt.n_superkmers = n_sk;
+        uint64_t n_surv = 0;
+        if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, surv, surv_off, &n_surv))) return r;
+        return msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true);
+    }
+    const uint64_t nb = 1ull << bits;
+    DevBuf &all = c->pool["surv_all"], &all_cnt = c->pool["surv_all_cnt"];
+    CU(all_cnt.alloc(4 * nb));
+    unsigned long long* occ = c->counters.as<unsigned long long>();
+    uint64_t n_total = 0, n_dist = 0, n_sk_total = 0;
+    for (uint32_t ps = 0; ps < passes; ++ps) {
+        const uint32_t b0 = mg_first_bucket(ps, passes, bits), b1 = mg_first_bucket(ps + 1, passes, bits);
+        if (b1 == b0) continue;
+        if ((r = msp_partition(c, bits, &n_sk, b0, b1 - b0))) return r;
+        n_sk_total += n_sk;
+        DevBuf& recs = c->pool["sk_recs"];
+        unsigned long long h_occ = 0;
+        CU(cudaMemsetAsync(occ + 4, 0, 8, c->st));
+        if (n_sk) { k_sum_nk<<<std::min(blocks_for(n_sk, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(recs.as<uint4>(), n_sk, occ + 4); KCHECK("k_sum_nk"); }
+        CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "a count pass holds more than 2^32-1 k-mer occurrences (skewed buckets): raise SN_COUNT_PASSES");
+        uint64_t n_surv = 0;
+        if ((r = msp_bucket_count(c, recs.as<uint4>(), c->pool["sk_off"].as<uint64_t>(), b1 - b0, 1, h_occ, surv, surv_off, &n_surv))) return r;
+        n_dist += c->cnt.n_kmers_distinct;
+        if (16 * (n_total + n_surv) > all.cap) {                   // grow the concatenation (keeps what it holds)
+            DevBuf bigger;
+            const uint64_t want = std::max<uint64_t>(n_total + n_surv, (uint64_t)((n_total + n_surv) * (double)passes / (ps + 1)) + 1024);
+            CU(bigger.alloc(16 * want));
+            if (n_total) CU(cudaMemcpyAsync(bigger.p, all.p, 16 * n_total, cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            std::swap(all.p, bigger.p); std::swap(all.bytes, bigger.bytes); std::swap(all.cap, bigger.cap);
+        }
+        if (n_surv) CU(cudaMemcpyAsync(all.as<uint4>() + n_total, surv.p, 16 * n_surv, cudaMemcpyDeviceToDevice, c->st));
+        k_diff_u32<<<blocks_for(b1 - b0, 256), 256, 0, c->st>>>(surv_off.as<uint32_t>(), b1 - b0, all_cnt.as<uint32_t>() + b0);
+        KCHECK("k_diff_u32");
+        n_total += n_surv;
+    }
+    c->cnt.n_superkmers = n_sk_total;
+    r = msp_install_dict(c, all.as<uint4>(), n_total, bits, all_cnt.as<uint32_t>(), false);
+    c->cnt.n_kmers_distinct = n_dist;
+    return r;
 }
 
 // ---- multi-GPU: the super-k-mer stream is range-partitioned by minimizer bucket over the ranks ----
@@ -617,7 +669,6 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
 // bucket-ordered record array.  The collectives themselves (one alltoallv of super-k-mer records
 // plus their per-bucket counts, one allgather of the surviving k-mers) are issued by the caller on
 // these device buffers (torch.distributed / NCCL in supernova_b200/multigpu.py).
-static uint32_t mg_first_bucket(uint32_t owner, uint32_t nparts, int bits) { return (uint32_t)((((uint64_t)owner << bits) + nparts - 1) / nparts); }
 
 int sn_mg_good_lengths(sn_ctx* c, const sn_params* p, uint64_t* n_occ)
 {
@@ -626,7 +677,9 @@ int sn_mg_good_lengths(sn_ctx* c, const sn_params* p, uint64_t* n_occ)
     CU(cudaSetDevice(c->device));
     int r;
     if ((r = count_set_params(c, p))) return r;
-    return count_goodlen(c, n_occ);
+    if ((r = count_goodlen(c, n_occ))) return r;
+    if (*n_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences on one rank: shard the reads over more GPUs");
+    return SN_OK;
 }
 int sn_mg_partition(sn_ctx* c, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts)
 {

@@ -40,9 +40,9 @@ def kmer_hash(w0, w1, w2):
 
 
 def bucket_bits(n_occ_total):
-    """python twin of sn::msp_bucket_bits: 1536..3072 k-mer occurrences per bucket."""
+    """python twin of sn::msp_bucket_bits: 768..1536 k-mer occurrences per bucket."""
     b = 4
-    while b < 24 and (int(n_occ_total) >> b) > 3072:
+    while b < 24 and (int(n_occ_total) >> b) > 1536:
         b += 1
     return b
 

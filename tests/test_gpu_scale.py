@@ -203,3 +203,26 @@ def test_streamed_load_matches_plain_load(sb, tmp_path):
             ctx.build_read_qgraph48(None, sb.Params(), with_paths=False)
             assert np.array_equal(ctx.good_lengths(), g0)
             assert np.array_equal(ctx.kmers(), k0)
+
+
+@pytest.mark.parametrize("name,passes", [("C1", 2), ("C1", 7), ("stress2", 3), ("mid", 3)])
+def test_count_in_several_passes(sb, name, passes):
+    """More than 2^31 k-mer occurrences are counted in several passes over consecutive bucket
+    ranges (forced here with SN_COUNT_PASSES): same dictionary, same graph, same paths."""
+    codes, quals, off, bc, _ = datasets.get(name)
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    with sb.Context(0) as ctx:
+        ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ctx.build_read_qgraph48(None, sb.Params(), with_paths=True)
+        k0, h0, p0, c0 = ctx.kmers(), ctx.hbv(), ctx.paths(), ctx.counts()
+        os.environ["SN_COUNT_PASSES"] = str(passes)
+        try:
+            ctx.build_read_qgraph48(None, sb.Params(), with_paths=True)
+        finally:
+            del os.environ["SN_COUNT_PASSES"]
+        k1, h1, p1, c1 = ctx.kmers(), ctx.hbv(), ctx.paths(), ctx.counts()
+    assert np.array_equal(k0, k1)
+    assert all(np.array_equal(h0[x], h1[x]) for x in h0)
+    assert all(np.array_equal(a, b) for a, b in zip(p0, p1))
+    for f in ("n_kmers", "n_kmers_distinct", "n_superkmers", "n_kmer_occurrences", "n_edges", "n_hbv_edges"):
+        assert c0[f] == c1[f], f

@@ -147,7 +147,7 @@ def test_bucket_ownership_is_a_balanced_range_partition(built):
     sys.path.insert(0, ROOT)
     import supernova_b200 as sb
     from supernova_b200 import multigpu as mg
-    for n_occ in (0, 1, 3072 << 4, (3072 << 4) + 16, 790_041_546, 1 << 40, 1 << 60):
+    for n_occ in (0, 1, 1536 << 4, (1536 << 4) + 16, 790_041_546, 1 << 40, 1 << 60):
         assert sb.lib().sn_msp_bucket_bits(n_occ) == mg.bucket_bits(n_occ)
     for bits in (4, 10, 19):
         b = np.arange(1 << bits)
@@ -160,4 +160,4 @@ def test_bucket_ownership_is_a_balanced_range_partition(built):
                 assert (o[fb[w]:fb[w + 1]] == w).all()
             cnt = np.bincount(o.astype(np.int64), minlength=n)
             assert cnt.max() - cnt.min() <= 1
-    assert mg.bucket_bits(0) == 4 and mg.bucket_bits(790_041_546) == 18 and mg.bucket_bits(1 << 60) == 24
+    assert mg.bucket_bits(0) == 4 and mg.bucket_bits(790_041_546) == 19 and mg.bucket_bits(1 << 60) == 24
