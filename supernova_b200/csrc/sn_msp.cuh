@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
                                                             const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
                                                             uint32_t b_lo = 0u, uint32_t b_n = 0xFFFFFFFFu /* bucket window [b_lo, b_lo + b_n): a count in several passes */,
                                                             uint2* __restrict__ dsc = nullptr, uint8_t* __restrict__ nruns = nullptr /* out: the runs of every read (see k_msp_place) */,
-                                                            const uint8_t* __restrict__ only_overflow = nullptr /* in: handle only the reads whose runs did not fit the descriptors */)
+                                                            const uint8_t* __restrict__ only_overflow = nullptr /* in: handle only the reads whose runs did not fit the descriptors */,
+                                                            uint32_t* __restrict__ n_overflow = nullptr /* out: how many reads those are */)
 {
     __shared__ __align__(16) uint8_t sb[SN_MS_BYTES];
     __shared__ uint32_t ring[SN_W * SN_MS_READS];
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
     // so that a warp reads and writes them coalesced; a read with more runs than slots is marked and scanned again
     if (nruns) {
         nruns[r] = nrun <= SN_MS_QUEUE ? (uint8_t)nrun : (uint8_t)255;
+        if (nrun > SN_MS_QUEUE && n_overflow) atomicAdd(n_overflow, 1u);
         uint2* d = dsc + (uint64_t)blockIdx.x * SN_MS_QUEUE * SN_MS_READS + tid;
         if (nrun <= SN_MS_QUEUE) for (uint32_t e = 0; e < nq; ++e) d[e * SN_MS_READS] = make_uint2(qv[e * SN_MS_READS + tid], qs[e * SN_MS_READS + tid]);
     }

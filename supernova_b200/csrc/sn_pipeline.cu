@@ -81,6 +81,7 @@ struct sn_ctx {
     cudaEvent_t ev_copy[16] = {};
     // work sn_load_reads_streamed already did under the copies; consumed by the next count call only
     bool gl_ready = false; uint32_t gl_min_qual = 0; uint64_t gl_occ = 0; int hist_ready_bits = -1;
+    bool dsc_ready = false; uint32_t dsc_overflow = 0;      // run descriptors of the loaded reads under the current good lengths (k_msp_place)
     std::string err;
     uint64_t launches = 0;
     std::map<std::string, Timer> timers;
@@ -174,7 +175,7 @@ int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_
     if (!n_reads || !bases || !base_off || !len) return fail(c, SN_ERR_ARG, "sn_load_reads: empty or NULL input");
     if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
     c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
-    c->gl_ready = false; c->hist_ready_bits = -1;
+    c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     c->cnt.n_reads = n_reads;
     t_begin(c, "h2d");
     int r;
@@ -337,7 +338,7 @@ static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
         c->gl_ready = false;
         if (c->gl_min_qual == c->params.min_qual) { c->cnt.n_kmer_occurrences = c->gl_occ; *n_occ_out = c->gl_occ; return SN_OK; }
     }
-    c->hist_ready_bits = -1;
+    c->hist_ready_bits = -1; c->dsc_ready = false;
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [0] occurrences, [1] cursor, [2] distinct
     uint32_t* u32c = reinterpret_cast<uint32_t*>(occ + 8);                  // [0] bad reads, [3] reduce overflow
     CU(cudaMemsetAsync(c->counters.p, 0, 256, c->st));
@@ -371,15 +372,35 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo 
     const uint64_t nb = window ? b_n : 1ull << bits;
     const uint32_t w_lo = window ? b_lo : 0u, w_n = window ? b_n : 0xFFFFFFFFu;
     if (window) c->hist_ready_bits = -1;
-    DevBuf &hist = c->pool["sk_hist"], &off = c->pool["sk_off"], &recs = c->pool["sk_recs"];
+    DevBuf &hist = c->pool["sk_hist"], &off = c->pool["sk_off"], &recs = c->pool["sk_recs"], &dsc = c->pool["sk_dsc"], &nruns = c->pool["sk_nruns"];
     CU(hist.alloc(4 * nb)); CU(off.alloc(8 * (nb + 1)));
     const int32_t* bc = c->have_bc ? c->bc.as<int32_t>() : nullptr;
+    const unsigned grid = blocks_for(n, SN_MS_READS);
+    uint32_t* ovf = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8) + 9;     // reads whose runs did not fit the descriptors
+    // The first scan of the reads under the current good lengths leaves the runs of every read behind
+    // (12 slots of 8 bytes per read); the scatter pass, and every later bucket window, places the
+    // super-k-mers from those instead of computing the minimizers again.
     t_begin(c, "msp_hist");
-    if (c->hist_ready_bits != bits) {            // (else: the histogram was built under the copies of sn_load_reads_streamed)
+    if (c->hist_ready_bits != bits || window) {      // (else: the histogram was built under the copies of sn_load_reads_streamed)
         CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
-        k_msp_scan<false><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n);
-        KCHECK("k_msp_scan<hist>");
+        if (c->dsc_ready) {
+            k_msp_place<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+                bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>());
+            KCHECK("k_msp_place<hist>");
+            if (c->dsc_overflow) {
+                k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+                    bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, nullptr, nullptr, nruns.as<uint8_t>());
+                KCHECK("k_msp_scan<hist, overflow>");
+            }
+        } else {
+            CU(dsc.alloc(8ull * SN_MS_QUEUE * SN_MS_READS * grid)); CU(nruns.alloc(n));
+            CU(cudaMemsetAsync(ovf, 0, 4, c->st));
+            k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+                bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), nullptr, ovf);
+            KCHECK("k_msp_scan<hist>");
+            CU(cudaMemcpyAsync(&c->dsc_overflow, ovf, 4, cudaMemcpyDeviceToHost, c->st));      // (host value valid after the scan's sync below)
+            c->dsc_ready = true;
+        }
     }
     c->hist_ready_bits = -1;
     uint64_t n_sk = 0;
@@ -390,9 +411,16 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo 
     CU(recs.alloc(32 * n_sk + 64));
     t_begin(c, "msp_scatter");
     CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));                 // now the per-bucket cursors
-    k_msp_scan<true><<<blocks_for(n, SN_MS_READS), SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-        bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n);
-    KCHECK("k_msp_scan<scatter>");
+    if (c->dsc_ready) {
+        k_msp_place<true><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>());
+        KCHECK("k_msp_place<scatter>");
+    }
+    if (!c->dsc_ready || c->dsc_overflow) {
+        k_msp_scan<true><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
+            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, nullptr, nullptr, c->dsc_ready ? nruns.as<uint8_t>() : nullptr);
+        KCHECK("k_msp_scan<scatter>");
+    }
     t_end(c, "msp_scatter");
     return SN_OK;
 }
@@ -516,7 +544,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     int r;
     if ((r = count_set_params(c, p))) return r;
     c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
-    c->gl_ready = false; c->hist_ready_bits = -1;
+    c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     c->cnt.n_reads = n_reads;
     const uint64_t n = n_reads;
     constexpr int MAXCH = 8;
@@ -537,7 +565,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     CU(cudaMemsetAsync((char*)c->pq.p + pq_off[n], 0, 16, c->st));
     CU(cudaEventRecord(c->ev_copy[0], c->st));
     CU(cudaStreamWaitEvent(c->st2, c->ev_copy[0], 0));            // nothing of an earlier step still reads the buffers
-    auto lo = [&](int ch) { return n * (uint64_t)ch / (uint64_t)nch; };
+    auto lo = [&](int ch) { return ch >= nch ? n : (n * (uint64_t)ch / (uint64_t)nch) & ~(uint64_t)(SN_MS_READS - 1); };   // whole k_msp_scan blocks per chunk
     auto bail = [&](int rc) { cudaStreamSynchronize(c->st2); cudaStreamSynchronize(c->st); return rc; };
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(c, SN_ERR_CUDA, cudaGetErrorString(e_))); } while (0)
     t_begin(c, "goodlen");
@@ -568,17 +596,21 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     const int bits = pick_bucket_bits(h_occ);
     if (h_occ >= (1ull << 31)) with_hist = 0;                      // counted in several passes: each pass has its own histogram
     const uint64_t nb = 1ull << bits;
-    DevBuf& hist = c->pool["sk_hist"];
+    DevBuf &hist = c->pool["sk_hist"], &dsc = c->pool["sk_dsc"], &nruns = c->pool["sk_nruns"];
+    uint32_t* ovf = u32c + 9;
     if (with_hist && h_occ) {
         CUB_(hist.alloc(4 * nb));
         CUB_(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
+        CUB_(dsc.alloc(8ull * SN_MS_QUEUE * SN_MS_READS * blocks_for(n, SN_MS_READS))); CUB_(nruns.alloc(n));
+        CUB_(cudaMemsetAsync(ovf, 0, 4, c->st));
     }
     for (int ch = 0; ch < nch; ++ch) {
         const uint64_t r0 = lo(ch), r1 = lo(ch + 1);
         CUB_(cudaStreamWaitEvent(c->st, c->ev_copy[MAXCH + ch], 0));
         if (with_hist && h_occ) {
             k_msp_scan<false><<<blocks_for(r1 - r0, SN_MS_READS), SN_MS_READS, 0, c->st>>>(r1 - r0, c->bases.as<uint8_t>(), c->boff.as<uint64_t>() + r0,
-                c->goodlen.as<uint32_t>() + r0, nullptr, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr);
+                c->goodlen.as<uint32_t>() + r0, nullptr, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, 0u, 0xFFFFFFFFu,
+                dsc.as<uint2>() + (r0 / SN_MS_READS) * (uint64_t)(SN_MS_QUEUE * SN_MS_READS), nruns.as<uint8_t>() + r0, nullptr, ovf);
             ++c->launches;
         }
     }
@@ -586,7 +618,9 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
         cnt64, reinterpret_cast<uint32_t*>(cnt64 + 1), reinterpret_cast<int32_t*>(cnt64 + 1) + 1);
     ++c->launches;
     unsigned long long h[2] = {0, 0};
+    uint32_t h_ovf = 0;
     CUB_(cudaMemcpyAsync(h, cnt64, 16, cudaMemcpyDeviceToHost, c->st));
+    CUB_(cudaMemcpyAsync(&h_ovf, ovf, 4, cudaMemcpyDeviceToHost, c->st));
     CUB_(cudaStreamSynchronize(c->st));                             // (st waited for every copy event: the caller's buffers are free again)
     CUB_(cudaGetLastError());
 #undef CUB_
@@ -597,6 +631,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     c->cnt.n_kmer_occurrences = h_occ;
     c->gl_ready = true; c->gl_min_qual = c->params.min_qual; c->gl_occ = h_occ;
     c->hist_ready_bits = (with_hist && h_occ) ? bits : -1;
+    c->dsc_ready = with_hist && h_occ; c->dsc_overflow = h_ovf;
     c->stage = 1;
     return SN_OK;
 }
