@@ -239,14 +239,14 @@ def main():
         return ms, ctx.kernel_launches() - l0, {k: v / steps for k, v in stage.items()}
 
     ctx.load_reads_ptr(n_reads, *ptrs)
+    sampler = ClockSampler(local_rank)          # nvidia-smi every 0.2 s from the warm-up to the end of the e2e leg (all under load)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms, launches, stage = timed(step_resident, args.steps)
-    clocks = sampler.summary()
     counts = ctx.counts()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    clocks = sampler.summary()
     d2h_bytes = int(counts["n_edges"] * 12 + 8 + (counts["n_edge_bases"] + 3) // 4 + counts["n_hbv_edges"] * 28 + counts["n_hbv_vertices"] * 8)
     paths_extra = None
     if not args.no_paths:

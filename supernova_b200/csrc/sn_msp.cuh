@@ -111,6 +111,33 @@ SN_HD void sk_build(const uint8_t* rp, uint32_t gl, uint32_t start, uint32_t nk,
 }
 
 SN_HD uint32_t sk_nk(uint32_t w0) { return ((w0 >> 24) & 0x3Fu) + 1u; }
+#if defined(__CUDACC__)
+// sk_build over a staged block of reads: `sb` is the 16-byte aligned staging buffer, `byte_off` the read's
+// first byte in it.  Seven aligned 32-bit shared-memory loads and six funnel shifts instead of 28 byte loads
+// (the byte loads made the scatter pass wait on the memory-instruction queue).
+__device__ __forceinline__ void sk_build_staged(const uint8_t* sb, uint32_t byte_off, uint32_t gl, uint32_t start, uint32_t nk, uint32_t bc24, uint32_t bhash, uint32_t* w /*8*/)
+{
+    const uint32_t hasL = start > 0 ? 1u : 0u;
+    const uint32_t hasR = start + nk + SN_K - 1 < gl ? 1u : 0u;
+    const uint32_t s0 = start - hasL, nb = nk + SN_K - 1 + hasL + hasR;
+    w[0] = bc24 | ((nk - 1) << 24) | (hasL << 30) | (hasR << 31);
+    w[1] = bhash;
+    const uint32_t a = byte_off + (s0 >> 2);
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(sb) + (a >> 2);
+    const uint32_t S = 8u * (a & 3u) + 2u * (s0 & 3u);          // < 32
+    uint32_t x[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) x[i] = W[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        uint32_t v = __funnelshift_r(x[i], x[i + 1], S);
+        const uint32_t first = 16u * i;
+        if (first >= nb) v = 0;
+        else if (nb - first < 16) v &= (1u << (2 * (nb - first))) - 1u;
+        w[2 + i] = v;
+    }
+}
+#endif
 
 // Occurrence i (0 <= i < nk) of a record: canonical k-mer + context as Kmerizer::map emits them
 // (BuildReadQGraph48.cc:155-172).  `w` = the 8 words of the record.
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
         else {
             const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
             uint32_t w[SN_SK_WORDS];
-            sk_build(rp, gl, start, nk, bc24, bh, w);
+            sk_build_staged(sb, (uint32_t)(rp - sb), gl, start, nk, bc24, bh, w);
             recs[2 * pos] = make_uint4(w[0], w[1], w[2], w[3]);
             recs[2 * pos + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
@@ -280,7 +307,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_reads, con
         else {
             const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
             uint32_t w[SN_SK_WORDS];
-            sk_build(rp, gl, x.y & 0xFFFFu, x.y >> 16, bc24, bh, w);
+            sk_build_staged(sb, (uint32_t)(rp - sb), gl, x.y & 0xFFFFu, x.y >> 16, bc24, bh, w);
             recs[2 * pos] = make_uint4(w[0], w[1], w[2], w[3]);
             recs[2 * pos + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
