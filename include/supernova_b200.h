@@ -87,6 +87,14 @@ int sn_load_reads_streamed(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, 
 /* same with one unpacked Phred byte per base (qual_off = n_reads+1 element offsets)   */
 int sn_load_reads_q8(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off,
                      const uint32_t* len, const uint8_t* quals, const uint64_t* qual_off, const int32_t* bc);
+/* ---- ingest on the device: replaces ParseBarcodedFastqs
+ * (10X/ParseBarcodedFastqs.cc:56-146,284-303) -- the barcoded pseudo-FASTQ of the pipeline, 9 lines per
+ * record (@name, R1, Q1, R2, Q2, BARCODE-gemgroup[,raw], bcQ, SI, SIQ), parsed, 2-bit packed and
+ * PQVec-encoded by CUDA kernels straight into the context.  `text` is the decompressed content.       */
+int sn_load_fasth_text(sn_ctx* ctx, const char* text, uint64_t n_bytes);
+int sn_load_fasth_file(sn_ctx* ctx, const char* path /* plain or .gz */);
+/* the loaded reads as reads.fastb / reads.qualp / reads.bci (any may be NULL)                        */
+int sn_save_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 /* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */
 int sn_load_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
+STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
 
 
 class SnError(RuntimeError):
@@ -45,6 +45,9 @@ def lib():
         L.sn_last_error.restype = C.c_char_p
         L.sn_load_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
         L.sn_load_reads_q8.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+        L.sn_load_fasth_text.argtypes = [vp, vp, u64]
+        L.sn_load_fasth_file.argtypes = [vp, C.c_char_p]
+        L.sn_save_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_load_reads_streamed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.sn_load_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_count_kmers.argtypes = [vp, C.POINTER(Params)]
@@ -193,6 +196,20 @@ class Context:
         """sn_load_reads_streamed: chunked copies with the good lengths and the first MSP pass under them."""
         params = params or Params()
         self._ck(self.L.sn_load_reads_streamed(self.h, n, bases, boff, ln, pq, pqoff, bc, C.byref(params), 1 if with_hist else 0))
+
+    def load_fasth_text(self, text):
+        """sn_load_fasth_text: barcoded pseudo-FASTQ text (bytes or a uint8 array) parsed, packed and PQVec-encoded on the device."""
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
+        self._ck(self.L.sn_load_fasth_text(self.h, _p(a), a.size))
+
+    def load_fasth_ptr(self, ptr, n_bytes):
+        self._ck(self.L.sn_load_fasth_text(self.h, ptr, n_bytes))
+
+    def load_fasth_file(self, path):
+        self._ck(self.L.sn_load_fasth_file(self.h, path.encode()))
+
+    def save_read_files(self, head):
+        self._ck(self.L.sn_save_read_files(self.h, (head + ".fastb").encode(), (head + ".qualp").encode(), (head + ".bci").encode()))
 
     def load_reads_q8(self, bases, boff, ln, quals, qoff, bc):
         a = [np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(boff, np.uint64), np.ascontiguousarray(ln, np.uint32),

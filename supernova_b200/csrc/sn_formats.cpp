@@ -1,4 +1,5 @@
 #include "sn_formats.h"
+#include <zlib.h>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -266,6 +267,23 @@ bool write_vec_int(const std::string& path, const std::vector<int32_t>& v, std::
     if (!fh.open(path, "wb")) { err = "cannot create " + path; return false; }
     uint64_t n = v.size();
     fwrite(MAGIC, 1, 8, fh.f); fwrite(&n, 8, 1, fh.f); if (n) fwrite(v.data(), 4, n, fh.f);
+    return true;
+}
+
+bool read_text_maybe_gz(const std::string& path, std::vector<char>& out, std::string& err)
+{
+    gzFile f = gzopen(path.c_str(), "rb");          // reads plain files transparently
+    if (!f) { err = "cannot open " + path; return false; }
+    gzbuffer(f, 1 << 20);
+    out.clear();
+    std::vector<char> buf(1 << 24);
+    for (;;) {
+        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n < 0) { err = path + ": gzip read error"; gzclose(f); return false; }
+        if (n == 0) break;
+        out.insert(out.end(), buf.begin(), buf.begin() + n);
+    }
+    gzclose(f);
     return true;
 }
 

@@ -44,6 +44,8 @@ bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32
                const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges, std::string& err);
 // feudal ReadPathVec (paths/long/ReadPath.h:61-63, feudal/FeudalFileWriter.cc:100-121)
 bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err);
+// whole file into memory; a gzip file (.gz) is inflated with zlib (the reference pipes it through zcat)
+bool read_text_maybe_gz(const std::string& path, std::vector<char>& out, std::string& err);
 // vec<int> (a.inv)
 bool write_vec_int(const std::string& path, const std::vector<int32_t>& v, std::string& err);
 

@@ -6,6 +6,7 @@
 #include "../../include/supernova_b200.h"
 #include "sn_kernels.cuh"
 #include "sn_msp.cuh"
+#include "sn_ingest.cuh"
 #include "sn_hbvdev.cuh"
 #include "sn_formats.h"
 #include "sn_hbv.h"
@@ -299,6 +300,119 @@ int sn_load_reads_q8(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const ui
     c->pq.release(); c->pqoff.release();
     return finish_load(c);
 }
+// ---- ingest on the device: barcoded pseudo-FASTQ text -> the context's reads (sn_ingest.cuh) ----
+// What ParseBarcodedFastqs does (10X/ParseBarcodedFastqs.cc:56-146,284-303); `text` is the decompressed
+// file content in host memory.  The reads land in the context exactly as sn_load_reads would leave them
+// (unbarcoded reads first, barcode ordinals from 1), so sn_build_read_qgraph48 can follow directly and
+// sn_save_read_files writes the reference's .fastb/.qualp/.bci byte for byte.
+int sn_load_fasth_text(sn_ctx* c, const char* text, uint64_t n_bytes)
+{
+    if (!c || (!text && n_bytes)) return SN_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
+    if (!n_bytes) return fail(c, SN_ERR_ARG, "sn_load_fasth_text: empty input");
+    if (text[n_bytes - 1] != '\n') return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (the text does not end with a newline)");
+    DevBuf &dtext = c->pool["ing_text"], &segc = c->pool["ing_segc"], &sego = c->pool["ing_sego"], &ls = c->pool["ing_lines"];
+    t_begin(c, "ingest_h2d");
+    CU(dtext.alloc(n_bytes + 64));
+    CU(cudaMemcpyAsync(dtext.p, text, n_bytes, cudaMemcpyHostToDevice, c->st));
+    t_end(c, "ingest_h2d");
+    t_begin(c, "ingest_parse");
+    const uint8_t* T = dtext.as<uint8_t>();
+    const uint64_t n_seg = (n_bytes + SN_ING_SEG - 1) / SN_ING_SEG;
+    CU(segc.alloc(4 * n_seg)); CU(sego.alloc(8 * (n_seg + 1)));
+    k_nl_count<<<blocks_for(n_seg, 256), 256, 0, c->st>>>(T, n_bytes, segc.as<uint32_t>(), n_seg);
+    KCHECK("k_nl_count");
+    uint64_t n_lines = 0;
+    int r = scan_u32(c, segc.as<uint32_t>(), n_seg, sego.as<uint64_t>(), &n_lines);
+    if (r) return r;
+    if (n_lines % 9) return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (" + std::to_string(n_lines) + " lines: not 9 per record)");
+    const uint64_t n_rec = n_lines / 9, n = 2 * n_rec;
+    if (!n_rec) return fail(c, SN_ERR_ARG, "sn_load_fasth_text: no records");
+    if (n >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
+    CU(ls.alloc(8 * (n_lines + 1)));
+    k_nl_fill<<<blocks_for(n_seg, 256), 256, 0, c->st>>>(T, n_bytes, sego.as<uint64_t>(), n_seg, ls.as<uint64_t>());
+    KCHECK("k_nl_fill");
+    uint32_t* err = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8) + 10;
+    CU(cudaMemsetAsync(err, 0, 4, c->st));
+    DevBuf &bflag = c->pool["ing_bflag"], &bbefore = c->pool["ing_bbefore"], &blist = c->pool["ing_blist"], &isnew = c->pool["ing_isnew"], &nbefore = c->pool["ing_nbefore"];
+    CU(bflag.alloc(4 * n_rec)); CU(bbefore.alloc(8 * (n_rec + 1)));
+    k_fasth_flags<<<blocks_for(n_rec, 256), 256, 0, c->st>>>(T, ls.as<uint64_t>(), n_rec, bflag.as<uint32_t>(), err);
+    KCHECK("k_fasth_flags");
+    uint64_t n_bc = 0;
+    if ((r = scan_u32(c, bflag.as<uint32_t>(), n_rec, bbefore.as<uint64_t>(), &n_bc))) return r;
+    CU(blist.alloc(4 * n_bc + 16)); CU(isnew.alloc(4 * n_bc + 16)); CU(nbefore.alloc(8 * (n_bc + 1) + 16));
+    uint64_t n_barcodes = 0;
+    if (n_bc) {
+        k_fasth_blist<<<blocks_for(n_rec, 256), 256, 0, c->st>>>(bflag.as<uint32_t>(), bbefore.as<uint64_t>(), n_rec, blist.as<uint32_t>());
+        KCHECK("k_fasth_blist");
+        k_fasth_newbc<<<blocks_for(n_bc, 256), 256, 0, c->st>>>(T, ls.as<uint64_t>(), blist.as<uint32_t>(), n_bc, isnew.as<uint32_t>());
+        KCHECK("k_fasth_newbc");
+        if ((r = scan_u32(c, isnew.as<uint32_t>(), n_bc, nbefore.as<uint64_t>(), &n_barcodes))) return r;
+    }
+    if (n_barcodes >= 0xFFFFFFull) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
+    c->cnt.n_reads = n;
+    DevBuf &bpos = c->pool["ing_bpos"], &qpos = c->pool["ing_qpos"], &nby = c->pool["ing_nbytes"], &cap = c->pool["ing_pqcap"], &slot = c->pool["ing_slot"],
+           &psz = c->pool["ing_pqsize"], &scratch = c->pool["ing_scratch"];
+    CU(c->len.alloc(4 * n)); CU(c->bc.alloc(4 * n)); CU(bpos.alloc(8 * n)); CU(qpos.alloc(8 * n)); CU(nby.alloc(4 * n)); CU(cap.alloc(4 * n));
+    CU(c->boff.alloc(8 * (n + 1))); CU(slot.alloc(8 * (n + 1))); CU(psz.alloc(4 * n)); CU(c->pqoff.alloc(8 * (n + 1)));
+    k_fasth_layout<<<blocks_for(n_rec, 256), 256, 0, c->st>>>(T, ls.as<uint64_t>(), n_rec, bflag.as<uint32_t>(), bbefore.as<uint64_t>(), n_rec - n_bc,
+        nbefore.as<uint64_t>(), isnew.as<uint32_t>(), c->len.as<uint32_t>(), c->bc.as<int32_t>(), bpos.as<uint64_t>(), qpos.as<uint64_t>(),
+        nby.as<uint32_t>(), cap.as<uint32_t>(), err);
+    KCHECK("k_fasth_layout");
+    uint64_t n_base_bytes = 0, n_scratch = 0, n_pq = 0;
+    if ((r = scan_u32(c, nby.as<uint32_t>(), n, c->boff.as<uint64_t>(), &n_base_bytes))) return r;
+    if ((r = scan_u32(c, cap.as<uint32_t>(), n, slot.as<uint64_t>(), &n_scratch))) return r;
+    CU(c->bases.alloc(n_base_bytes + 64)); CU(scratch.alloc(n_scratch + 16));
+    CU(cudaMemsetAsync((char*)c->bases.p + n_base_bytes, 0, 64, c->st));
+    k_fasth_pack<<<blocks_for(n, 128), 128, 0, c->st>>>(T, bpos.as<uint64_t>(), c->len.as<uint32_t>(), c->boff.as<uint64_t>(), n, c->bases.as<uint8_t>(), err);
+    KCHECK("k_fasth_pack");
+    k_fasth_pqvec<<<blocks_for(n, 128), 128, 0, c->st>>>(T, qpos.as<uint64_t>(), c->len.as<uint32_t>(), slot.as<uint64_t>(), n, scratch.as<uint8_t>(), psz.as<uint32_t>());
+    KCHECK("k_fasth_pqvec");
+    if ((r = scan_u32(c, psz.as<uint32_t>(), n, c->pqoff.as<uint64_t>(), &n_pq))) return r;
+    CU(c->pq.alloc(n_pq + 16));
+    CU(cudaMemsetAsync((char*)c->pq.p + n_pq, 0, 16, c->st));
+    k_fasth_pq_compact<<<blocks_for(n * 32, 256), 256, 0, c->st>>>(scratch.as<uint8_t>(), slot.as<uint64_t>(), psz.as<uint32_t>(), c->pqoff.as<uint64_t>(), n, c->pq.as<uint8_t>());
+    KCHECK("k_fasth_pq_compact");
+    t_end(c, "ingest_parse");
+    uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_err & SN_ING_E_NAME) return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (a record does not start with '@')");
+    if (h_err & SN_ING_E_QLEN) return fail(c, SN_ERR_DATA, "fasth: a quality line and its base line differ in length");
+    if (h_err & SN_ING_E_LONG) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    if (h_err & SN_ING_E_BASE) return fail(c, SN_ERR_DATA, "fasth: a base other than ACGTN (the reference draws other ambiguity codes at random: not reproducible)");
+    c->have_bc = true; c->have_pq = true; c->quals.release();
+    return finish_load(c);
+}
+int sn_load_fasth_file(sn_ctx* c, const char* path)
+{
+    if (!c || !path) return SN_ERR_ARG;
+    std::vector<char> text; std::string err;
+    if (!snf::read_text_maybe_gz(path, text, err)) return fail(c, SN_ERR_IO, err);
+    return sn_load_fasth_text(c, text.data(), text.size());
+}
+// the loaded reads as the three files ParseBarcodedFastqs writes
+int sn_save_read_files(sn_ctx* c, const char* fastb, const char* qualp, const char* bci)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 1 || !c->have_pq) return fail(c, SN_ERR_STATE, "sn_save_read_files: no PQVec reads loaded");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = c->cnt.n_reads;
+    std::vector<uint64_t> boff(n + 1), pqoff(n + 1); std::vector<uint32_t> len(n); std::vector<int32_t> bc(n, 0);
+    CU(cudaMemcpy(boff.data(), c->boff.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pqoff.data(), c->pqoff.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(len.data(), c->len.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (c->have_bc) CU(cudaMemcpy(bc.data(), c->bc.p, 4 * n, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> bases(boff[n] + 1), pq(pqoff[n] + 1);
+    if (boff[n]) CU(cudaMemcpy(bases.data(), c->bases.p, boff[n], cudaMemcpyDeviceToHost));
+    if (pqoff[n]) CU(cudaMemcpy(pq.data(), c->pq.p, pqoff[n], cudaMemcpyDeviceToHost));
+    int r = sn_write_read_files(fastb, qualp, bci, n, bases.data(), boff.data(), len.data(), pq.data(), pqoff.data(), bc.data());
+    if (r) return fail(c, r, g_create_error);
+    return SN_OK;
+}
+
 int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const char* bci)
 {
     if (!c || !fastb || !qualp) return SN_ERR_ARG;
