@@ -95,7 +95,7 @@ def gen_workload(name, rank, scale_div=1):
     b, q, bc, ids = synth.make_reads(G, pairs, nbc, seed, workers=workers, shard=rank)
     n, L = b.shape
     off = np.arange(n + 1, dtype=np.uint64) * L
-    return b.ravel(), q.ravel(), off, bc, dict(G=G, pairs=pairs, n_bc=nbc, seed=seed, read_len=L)
+    return b.ravel(), q.ravel(), off, bc, dict(G=G, pairs=pairs, n_bc=nbc, seed=seed, read_len=L, bc_ids=ids)
 
 
 def run_reference(args, rank, world):
@@ -150,6 +150,26 @@ def cpu_baseline(args):
     return {"value": gbp / secs, "unit": "Gbp/s", "cores": 1, "kind": "port", "sample": sample, "seconds": secs}
 
 
+def cpu_ingest_baseline(args):
+    """The reference's own ParseBarcodedFastqs (oracle/_ref) on a bounded sample: 1/48 of the workload."""
+    import gzip
+    import refrun
+    from supernova_b200 import synth
+    if not refrun.have_ref():
+        return None
+    G, pairs, nbc, seed = WORKLOADS[args.workload]
+    b, q, bc, ids = synth.make_reads(G // 48, pairs // 48, max(2, nbc // 48), seed, workers=min(os.cpu_count() or 1, 32))
+    wd = tempfile.mkdtemp(prefix="sn_ing_")
+    p = wd + "/sample.fastq.gz"
+    with gzip.open(p, "wb", compresslevel=1) as f:
+        f.write(synth.fasth_text(b, q, ids).tobytes())
+    t0 = time.time()
+    refrun.parse_fastqs(wd, p)
+    secs = time.time() - t0
+    return {"value": b.size / 1e9 / secs, "unit": "Gbp/s", "cores": 1, "kind": "reference", "seconds": secs,
+            "sample": f"ParseBarcodedFastqs (zcat + parse + PQVec encode + write) on {pairs // 48} pairs = {b.size / 1e9:.4f} Gbp"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +179,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paths", action="store_true", help="skip the extra ReadPath-inclusive measurement")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the extra device-ingest (FASTQ text -> reads) measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,6 +206,11 @@ def main():
     n_bases = int(codes.size)
     gbp = n_bases / 1e9
     pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    text_t = None
+    if world == 1 and not args.no_ingest:      # the same reads as the pipeline's pseudo-FASTQ text (ingest leg below)
+        from supernova_b200 import synth
+        L = meta["read_len"]
+        text_t = torch.from_numpy(synth.fasth_text(codes.reshape(-1, L), quals.reshape(-1, L), meta["bc_ids"])).pin_memory()
     del codes, quals
     host = [torch.from_numpy(x).pin_memory() for x in (pb, boff, ln, pq, pqoff, np.ascontiguousarray(bc, np.int32))]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
@@ -255,6 +281,22 @@ def main():
         paths_extra = {"value": world * gbp * max(1, args.steps // 2) / (ms_p / 1e3), "unit": "Gbp/s", "path_ms": stage_p.get("path"),
                        "n_path_edges": ctx.counts()["n_path_edges"]}
 
+    ingest = None
+    if text_t is not None:
+        # ParseBarcodedFastqs on the device -- text in pinned host memory -> reads resident in the
+        # context (H2D + newline index + parse + 2-bit pack + PQVec encode); checked by counting the reads it produced
+        def step_ingest():
+            ctx.load_fasth_ptr(text_t.data_ptr(), text_t.numel())
+        step_ingest()
+        ms_i, launches_i, _ = timed(step_ingest, max(1, args.steps // 2))
+        st_i = ctx.stage_ms()
+        ctx.count_kmers(params)
+        ok = ctx.counts()["n_kmers"] == counts["n_kmers"] and ctx.counts()["n_bases"] == counts["n_bases"]
+        ingest = {"value": gbp * max(1, args.steps // 2) / (ms_i / 1e3), "unit": "Gbp/s", "ms": ms_i / max(1, args.steps // 2), "text_bytes": int(text_t.numel()),
+                  "h2d_ms": st_i.get("ingest_h2d"), "parse_ms": st_i.get("ingest_parse"), "same_kmers_as_packed_load": bool(ok),
+                  "what": "sn_load_fasth_text: 9-line barcoded pseudo-FASTQ text (host, pinned) -> .fastb/.qualp layout + barcode ordinals in HBM"}
+        if rank == 0 and not args.no_cpu_baseline:
+            ingest["cpu_reference"] = cpu_ingest_baseline(args)
     total_gbp = gbp * world
     value = total_gbp * args.steps / (ms / 1e3)
     e2e = total_gbp * args.steps / (ms_e2e / 1e3)
@@ -297,6 +339,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}
     if paths_extra:
         line["with_readpaths"] = paths_extra
+    if ingest:
+        line["ingest"] = ingest
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     ctx.close()

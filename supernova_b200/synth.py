@@ -223,3 +223,41 @@ def write_fasth_ragged(path: str, bases, quals, off, bc_ids):
             bcs = (barcode_string(int(b)) + "-1").encode() if b >= 0 else b"NNNNNNNNNNNNNNNN"
             f.write(b"@p%d\n" % p + r1 + b"\n" + q1 + b"\n" + r2 + b"\n" + q2 + b"\n" +
                     bcs + b"\n" + bq + b"\nACGTACGT\nIIIIIIII\n")
+
+
+def fasth_text(bases, quals, bc_ids):
+    """The 9-line pseudo-FASTQ text of fixed-length read pairs as one uint8 array (vectorised: the
+    bench builds gigabytes of it).  Same content as write_fasth, names zero-padded to a fixed width."""
+    n_pairs, L = bases.shape[0] // 2, bases.shape[1]
+    name = np.frombuffer(b"@p", np.uint8)
+    digits = 10
+    rec_len = 2 + digits + 1 + 4 * (L + 1) + 19 + 17 + 9 + 9
+    out = np.empty((n_pairs, rec_len), np.uint8)
+    o = 0
+    out[:, 0:2] = name; o = 2
+    idx = np.arange(n_pairs, dtype=np.int64)
+    for d in range(digits):
+        out[:, o + digits - 1 - d] = 48 + (idx // 10 ** d) % 10
+    o += digits
+    out[:, o] = 10; o += 1
+    for m, src, add in ((0, bases, None), (0, quals, 33), (1, bases, None), (1, quals, 33)):
+        blk = src[m::2]
+        out[:, o:o + L] = BASES[blk] if add is None else (blk + add).astype(np.uint8)
+        o += L
+        out[:, o] = 10; o += 1
+    b = np.asarray(bc_ids[0::2], dtype=np.int64)
+    for k in range(16):
+        out[:, o + 15 - k] = np.frombuffer(b"ACGT", np.uint8)[(b >> (2 * k)) & 3]
+    unb = b < 0
+    if unb.any():
+        out[unb, o:o + 16] = ord("N")
+    o += 16
+    out[:, o] = ord("-"); out[:, o + 1] = ord("1"); out[:, o + 2] = 10
+    if unb.any():
+        out[unb, o] = ord("N"); out[unb, o + 1] = ord("N")
+    o += 3
+    out[:, o:o + 16] = ord("I"); out[:, o + 16] = 10; o += 17
+    out[:, o:o + 9] = np.frombuffer(b"ACGTACGT\n", np.uint8); o += 9
+    out[:, o:o + 9] = np.frombuffer(b"IIIIIIII\n", np.uint8); o += 9
+    assert o == rec_len
+    return out.ravel()
