@@ -9,7 +9,7 @@
 // reference sources under /root/reference by oracle/build_ref.sh into
 // oracle/_ref/ (git-ignored).
 //
-// Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [MIN_QUAL=7]
+// Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [INDEX=False|True] [MIN_QUAL=7]
 //                    [MIN_FREQ=3] [MIN_BC=2]
 //   OUT/reads.fastb must exist (re-opened at BuildReadQGraph48.cc:1763).
 // Outputs: OUT/a.hbv, OUT/tmp.paths (PATHS=True), OUT/kmers.kvec (when env
@@ -23,7 +23,14 @@
 #include "paths/HyperBasevector.h"
 #include "paths/long/ReadPath.h"
 #include "paths/long/BuildReadQGraph48.h"
+#include "10X/PathsIndex.h"
 #include <chrono>
+
+// Progress-dot printer declared in 10X/DfTools.h:466 (defined in DfTools.cc:617-635, a translation unit
+// whose closure is most of DF): writePathsIndex only calls it when verbose.  An empty stand-in, so
+// that DfTools.cc need not be linked; it computes nothing.
+template <class T> void MakeDots(T& done, T& ndots, const T total) {}
+template void MakeDots(int& done, int& ndots, const int total);
 
 int main(int argc, char** argv)
 {   RunTime();
@@ -34,6 +41,7 @@ int main(int argc, char** argv)
     CommandArgument_Int_OrDefault(MIN_QUAL, 7);
     CommandArgument_Int_OrDefault(MIN_FREQ, 3);
     CommandArgument_Int_OrDefault(MIN_BC, 2);
+    CommandArgument_Bool_OrDefault(INDEX, False);
     EndCommandArguments;
 
     vecbvec reads(HEAD + ".fastb");
@@ -52,6 +60,15 @@ int main(int argc, char** argv)
                       True, False, &hbv, PATHS ? &paths : nullptr, 0.9, False);
     auto t1 = std::chrono::steady_clock::now();
     BinaryWriter::writeFile(OUT + "/a.hbv", hbv);
+    if (INDEX && PATHS) {
+        // what DF does next (10X/DF.cc:586-590): the involution and the edge -> reads index of the paths
+        // (writePathsIndex, 10X/PathsIndex.cc:23-143) -- the reference's own code, called as DF calls it
+        ReadPathVec rp(OUT + "/tmp.paths");
+        vec<int> inv;
+        hbv.Involution(inv);
+        BinaryWriter::writeFile(OUT + "/a.inv", inv);
+        writePathsIndex(rp, inv, OUT, "a.paths.inv", "a.countsb", 15, false);
+    }
     std::cout << "ORACLE_SECONDS "
               << std::chrono::duration<double>(t1 - t0).count() << std::endl;
     return 0;
