@@ -109,6 +109,13 @@ int sn_build_hbv(sn_ctx* ctx);
 /* pathReads with useNewAligner=True (BuildReadQGraph48.cc:1440-1469)                    */
 int sn_path_reads(sn_ctx* ctx);
 
+/* DF side, SURVEY §8(f) row 1: writePathsIndex (10X/PathsIndex.cc:23-143, called at 10X/DF.cc:588) -- for
+ * every HBV edge the reads whose path crosses it (sorted; twice if it crosses twice) and countsb[e] =
+ * reads on e + reads on inv[e].  After sn_path_reads.                                               */
+int sn_build_paths_index(sn_ctx* ctx);
+int sn_get_paths_index(sn_ctx* ctx, uint64_t* off /* n_hbv_edges+1 */, uint64_t* read_ids /* n_path_edges */, int32_t* countsb /* n_hbv_edges */);
+int sn_write_paths_index(sn_ctx* ctx, const char* paths_inv /* a.paths.inv */, const char* countsb /* a.countsb */);
+
 /* ---- results ------------------------------------------------------------------------- */
 int sn_get_counts(const sn_ctx* ctx, sn_counts* out);
 int sn_get_good_lengths(sn_ctx* ctx, uint32_t* out /* n_reads */);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path")
+STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path", "paths_index")
 
 
 class SnError(RuntimeError):
@@ -45,6 +45,9 @@ def lib():
         L.sn_last_error.restype = C.c_char_p
         L.sn_load_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
         L.sn_load_reads_q8.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+        L.sn_build_paths_index.argtypes = [vp]
+        L.sn_get_paths_index.argtypes = [vp, vp, vp, vp]
+        L.sn_write_paths_index.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.sn_load_fasth_text.argtypes = [vp, vp, u64]
         L.sn_load_fasth_file.argtypes = [vp, C.c_char_p]
         L.sn_save_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
@@ -325,6 +328,18 @@ class Context:
         off = np.zeros(c["n_reads"], np.int32); poff = np.zeros(c["n_reads"] + 1, np.uint64); e = np.zeros(c["n_path_edges"], np.int32)
         self._ck(self.L.sn_get_paths(self.h, _p(off), _p(poff), _p(e)))
         return off, poff, e
+
+    def build_paths_index(self):
+        self._ck(self.L.sn_build_paths_index(self.h))
+
+    def paths_index(self):
+        c = self.counts()
+        off = np.zeros(c["n_hbv_edges"] + 1, np.uint64); ids = np.zeros(c["n_path_edges"], np.uint64); cb = np.zeros(c["n_hbv_edges"], np.int32)
+        self._ck(self.L.sn_get_paths_index(self.h, _p(off), _p(ids), _p(cb)))
+        return off, ids, cb
+
+    def write_paths_index(self, paths_inv, countsb):
+        self._ck(self.L.sn_write_paths_index(self.h, paths_inv.encode(), countsb.encode()))
 
     def write_hbv(self, path):
         self._ck(self.L.sn_write_hbv(self.h, path.encode()))

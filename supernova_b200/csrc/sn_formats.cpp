@@ -270,6 +270,20 @@ bool write_vec_int(const std::string& path, const std::vector<int32_t>& v, std::
     return true;
 }
 
+bool write_ulongvecs(const std::string& path, uint64_t n, const uint64_t* ids, const uint64_t* off, std::string& err)
+{
+    std::vector<uint64_t> rel((size_t)n + 1);
+    for (uint64_t i = 0; i <= n; ++i) rel[i] = 8 * off[i];
+    return write_feudal(path, (uint32_t)n, 0, 16, 8, reinterpret_cast<const uint8_t*>(ids), 8 * off[n], rel.data(), nullptr, 0, err);
+}
+bool write_vec_vec_int(const std::string& path, const std::vector<int32_t>& v, std::string& err)
+{
+    File fh;
+    if (!fh.open(path, "wb")) { err = "cannot create " + path; return false; }
+    uint64_t one = 1, n = v.size();
+    fwrite(MAGIC, 1, 8, fh.f); fwrite(&one, 8, 1, fh.f); fwrite(&n, 8, 1, fh.f); if (n) fwrite(v.data(), 4, n, fh.f);
+    return true;
+}
 bool read_text_maybe_gz(const std::string& path, std::vector<char>& out, std::string& err)
 {
     gzFile f = gzopen(path.c_str(), "rb");          // reads plain files transparently

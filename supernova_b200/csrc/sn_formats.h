@@ -46,6 +46,10 @@ bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32
 bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err);
 // whole file into memory; a gzip file (.gz) is inflated with zlib (the reference pipes it through zcat)
 bool read_text_maybe_gz(const std::string& path, std::vector<char>& out, std::string& err);
+// VecULongVec (a.paths.inv: feudal, FCB sizeofFixed 0, sizeofX 16, sizeofA 8; 10X/PathsIndex.cc:75,107) and
+// vec<vec<int>> with one inner vector (a.countsb, :133)
+bool write_ulongvecs(const std::string& path, uint64_t n, const uint64_t* ids, const uint64_t* off /*n+1, in elements*/, std::string& err);
+bool write_vec_vec_int(const std::string& path, const std::vector<int32_t>& v, std::string& err);
 // vec<int> (a.inv)
 bool write_vec_int(const std::string& path, const std::vector<int32_t>& v, std::string& err);
 

@@ -449,4 +449,34 @@ __global__ void __launch_bounds__(128) k_path_finish(PathInputs in, DictView d, 
     for (uint32_t i = 0; i < path.n; ++i) o[i] = path.e[i];
 }
 
+// ---------------------------------------------------------------------------
+// SURVEY §8(f) row 1 (DF side): writePathsIndex (10X/PathsIndex.cc:23-143) -- the edge -> reads index of the
+// ReadPaths.  One {edge, 0, read, 0} record per path entry, sorted by the device radix sort on (edge, read)
+// (the reference sorts pair<int, unsigned long> the same way: a read that crosses an edge twice is listed
+// twice), per-edge counts by atomics, and countsb[e] = reads on e plus reads on its reverse complement.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pi_records(const int32_t* __restrict__ pedges, const uint64_t* __restrict__ path_off, uint64_t n_reads,
+                                                    uint4* __restrict__ rec, uint32_t* __restrict__ cnt)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    for (uint64_t k = path_off[r]; k < path_off[r + 1]; ++k) {
+        const uint32_t e = (uint32_t)pedges[k];
+        rec[k] = make_uint4(e, 0u, (uint32_t)r, 0u);
+        atomicAdd(cnt + e, 1u);
+    }
+}
+__global__ void __launch_bounds__(256) k_pi_ids(const uint4* __restrict__ rec, uint64_t m, unsigned long long* __restrict__ ids)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) ids[i] = rec[i].z;
+}
+__global__ void __launch_bounds__(256) k_pi_countsb(const uint32_t* __restrict__ cnt, const int32_t* __restrict__ inv, uint32_t n_h, int32_t* __restrict__ countsb)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_h) return;
+    const int32_t re = inv[e];
+    countsb[e] = (int32_t)(cnt[e] + ((uint32_t)re != e ? cnt[re] : 0u));     // (:123-131; a palindromic edge keeps its own count)
+}
+
 }  // namespace sn

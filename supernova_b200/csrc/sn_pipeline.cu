@@ -106,6 +106,7 @@ struct sn_ctx {
     // paths
     DevBuf plen, poffset, path_off, pedges;
     std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
+    std::vector<uint64_t> pi_off, pi_ids; std::vector<int32_t> pi_countsb; bool pi_ready = false;     // paths index (writePathsIndex)
     DevBuf counters;     // small scratch of u64 counters
     std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
     std::map<std::string, HostBuf> hpool;    // pinned staging, kept across steps
@@ -1224,7 +1225,7 @@ int sn_path_reads(sn_ctx* c)
     CU(scratch.alloc(16 * n));
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
     CU(cudaMemsetAsync(u32c + 5, 0, 4, c->st));
-    c->paths_on_host = false;
+    c->paths_on_host = false; c->pi_ready = false;
     PathInputs in;
     in.n_reads = n; in.bases = c->bases.as<uint8_t>(); in.boff = c->boff.as<uint64_t>(); in.len = c->len.as<uint32_t>();
     in.quals = c->have_pq ? nullptr : c->quals.as<uint8_t>(); in.qoff = c->qoff.as<uint64_t>();
@@ -1385,6 +1386,61 @@ int sn_write_edges_bv(sn_ctx* c, const char* path)
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
     std::string err; const snh::Edges& E = c->hedges;
     if (!snf::write_bv(path, E.packed.data(), E.off.data(), E.len.data(), E.n(), err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+// writePathsIndex (10X/PathsIndex.cc:23-143, called from 10X/DF.cc:588): a.paths.inv + a.countsb
+int sn_build_paths_index(sn_ctx* c)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 5) return fail(c, SN_ERR_STATE, "sn_build_paths_index: run sn_path_reads first");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = c->cnt.n_reads, m = c->cnt.n_path_edges, nH = c->cnt.n_hbv_edges;
+    if (m >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 path entries in one context");
+    DevBuf &ra = c->pool["pi_a"], &rb = c->pool["pi_b"], &tmp = c->pool["rs_tmp"], &cnt = c->pool["pi_cnt"], &off = c->pool["pi_off"], &ids = c->pool["pi_ids"], &cb = c->pool["pi_cb"];
+    CU(ra.alloc(16 * m + 16)); CU(rb.alloc(16 * m + 16)); CU(tmp.alloc(radix_sort_tmp_bytes((uint32_t)m))); CU(cnt.alloc(4 * nH + 16)); CU(off.alloc(8 * (nH + 1)));
+    CU(ids.alloc(8 * m + 16)); CU(cb.alloc(4 * nH + 16));
+    t_begin(c, "paths_index");
+    CU(cudaMemsetAsync(cnt.p, 0, 4 * nH + 16, c->st));
+    k_pi_records<<<blocks_for(n, 256), 256, 0, c->st>>>(c->pedges.as<int32_t>(), c->path_off.as<uint64_t>(), n, ra.as<uint4>(), cnt.as<uint32_t>());
+    KCHECK("k_pi_records");
+    if (m) {
+        cudaError_t e = radix_sort<RS_KEY96>(ra.as<uint4>(), rb.as<uint4>(), (uint32_t)m, tmp.p, c->num_sms, c->st);      // 12 passes: the result is back in ra
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, cudaGetErrorString(e));
+        c->launches += 13;
+        k_pi_ids<<<blocks_for(m, 256), 256, 0, c->st>>>(ra.as<uint4>(), m, ids.as<unsigned long long>());
+        KCHECK("k_pi_ids");
+    }
+    int r = scan_u32(c, cnt.as<uint32_t>(), nH, off.as<uint64_t>(), nullptr);
+    if (r) return r;
+    if (nH) {
+        k_pi_countsb<<<blocks_for(nH, 256), 256, 0, c->st>>>(cnt.as<uint32_t>(), c->pool["hbv_inv"].as<int32_t>(), (uint32_t)nH, cb.as<int32_t>());
+        KCHECK("k_pi_countsb");
+    }
+    t_end(c, "paths_index");
+    resize_pinned(c, c->pi_off, nH + 1); resize_pinned(c, c->pi_ids, m); resize_pinned(c, c->pi_countsb, nH);
+    CU(cudaMemcpyAsync(c->pi_off.data(), off.p, 8 * (nH + 1), cudaMemcpyDeviceToHost, c->st));
+    if (m) CU(cudaMemcpyAsync(c->pi_ids.data(), ids.p, 8 * m, cudaMemcpyDeviceToHost, c->st));
+    if (nH) CU(cudaMemcpyAsync(c->pi_countsb.data(), cb.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    c->pi_ready = true;
+    return SN_OK;
+}
+int sn_get_paths_index(sn_ctx* c, uint64_t* off, uint64_t* ids, int32_t* countsb)
+{
+    if (!c) return SN_ERR_ARG;
+    if (!c->pi_ready) return fail(c, SN_ERR_STATE, "run sn_build_paths_index first");
+    if (off) memcpy(off, c->pi_off.data(), 8 * c->pi_off.size());
+    if (ids && !c->pi_ids.empty()) memcpy(ids, c->pi_ids.data(), 8 * c->pi_ids.size());
+    if (countsb && !c->pi_countsb.empty()) memcpy(countsb, c->pi_countsb.data(), 4 * c->pi_countsb.size());
+    return SN_OK;
+}
+int sn_write_paths_index(sn_ctx* c, const char* paths_inv, const char* countsb)
+{
+    if (!c) return SN_ERR_ARG;
+    if (!c->pi_ready) return fail(c, SN_ERR_STATE, "run sn_build_paths_index first");
+    std::string err;
+    if (paths_inv && !snf::write_ulongvecs(paths_inv, c->pi_off.size() - 1, c->pi_ids.data(), c->pi_off.data(), err)) return fail(c, SN_ERR_IO, err);
+    if (countsb && !snf::write_vec_vec_int(countsb, c->pi_countsb, err)) return fail(c, SN_ERR_IO, err);
     return SN_OK;
 }
 int sn_write_inv(sn_ctx* c, const char* path)
