@@ -137,6 +137,7 @@ int sn_write_hbv(sn_ctx* ctx, const char* path);             /* a.hbv           
 int sn_write_paths(sn_ctx* ctx, const char* path);           /* tmp.paths (feudal ReadPathVec)     */
 int sn_write_edges_bv(sn_ctx* ctx, const char* path);        /* vec<basevector> (== MSPEDGES file) */
 int sn_write_inv(sn_ctx* ctx, const char* path);             /* a.inv  (vec<int>)                  */
+int sn_write_to_left_right(sn_ctx* ctx, const char* to_left, const char* to_right);   /* a.to_left, a.to_right (vec<int>) */
 int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_kmer_count.json    */
 
 /* One call == buildReadQGraph48: the four stages, then work_dir/a.hbv (when write_hbv),

@@ -67,6 +67,10 @@ int main(int argc, char** argv)
         vec<int> inv;
         hbv.Involution(inv);
         BinaryWriter::writeFile(OUT + "/a.inv", inv);
+        vec<int> to_left, to_right;                                   // 10X/WriteFiles.cc:16-60 (a.to_left, a.to_right)
+        hbv.ToLeft(to_left); hbv.ToRight(to_right);
+        BinaryWriter::writeFile(OUT + "/a.to_left", to_left);
+        BinaryWriter::writeFile(OUT + "/a.to_right", to_right);
         writePathsIndex(rp, inv, OUT, "a.paths.inv", "a.countsb", 15, false);
     }
     std::cout << "ORACLE_SECONDS "

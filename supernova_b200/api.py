@@ -45,6 +45,7 @@ def lib():
         L.sn_last_error.restype = C.c_char_p
         L.sn_load_reads.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
         L.sn_load_reads_q8.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+        L.sn_write_to_left_right.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.sn_build_paths_index.argtypes = [vp]
         L.sn_get_paths_index.argtypes = [vp, vp, vp, vp]
         L.sn_write_paths_index.argtypes = [vp, C.c_char_p, C.c_char_p]
@@ -328,6 +329,9 @@ class Context:
         off = np.zeros(c["n_reads"], np.int32); poff = np.zeros(c["n_reads"] + 1, np.uint64); e = np.zeros(c["n_path_edges"], np.int32)
         self._ck(self.L.sn_get_paths(self.h, _p(off), _p(poff), _p(e)))
         return off, poff, e
+
+    def write_to_left_right(self, left, right):
+        self._ck(self.L.sn_write_to_left_right(self.h, left.encode(), right.encode()))
 
     def build_paths_index(self):
         self._ck(self.L.sn_build_paths_index(self.h))

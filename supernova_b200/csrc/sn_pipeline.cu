@@ -22,6 +22,7 @@
 #include <thread>
 #include <vector>
 #include <sys/stat.h>
+#include <sys/mman.h>
 
 using namespace sn;
 
@@ -709,7 +710,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     CUB_(cudaStreamSynchronize(c->st));                             // the good lengths are done; the bases are still arriving
     if (h_bad) return bail(fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count"));
     const int bits = pick_bucket_bits(h_occ);
-    if (h_occ >= (1ull << 31)) with_hist = 0;                      // counted in several passes: each pass has its own histogram
+    if (h_occ >= 3600000000ull) with_hist = 0;                     // counted in several passes: each pass has its own histogram
     const uint64_t nb = 1ull << bits;
     DevBuf &hist = c->pool["sk_hist"], &dsc = c->pool["sk_dsc"], &nruns = c->pool["sk_nruns"];
     uint32_t* ovf = u32c + 9;
@@ -761,10 +762,10 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if ((r = count_goodlen(c, &n_occ))) return r;
     const int bits = pick_bucket_bits(n_occ);
     // One pass holds < 2^32 k-mer occurrences (32-bit positions inside k_bucket_count's output) and its
-    // super-k-mer records in HBM.  More occurrences than 2^31 are counted in several passes over
+    // super-k-mer records in HBM.  More occurrences than 3.6e9 are counted in several passes over
     // consecutive bucket ranges: every pass scans the resident reads again (0.25 B/base, cheap next to the
     // count itself) and keeps only its buckets; the passes' survivors, concatenated, are in bucket order.
-    uint32_t passes = (uint32_t)((n_occ >> 31) + 1);
+    uint32_t passes = (uint32_t)(n_occ / 3600000000ull + 1);      // (bucket ranges are even to a fraction of a percent: a pass stays below 2^32)
     if (const char* e = getenv("SN_COUNT_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 4096) passes = (uint32_t)v; }     // tests
     if (passes > (1u << bits)) passes = 1u << bits;
     DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
@@ -1441,6 +1442,17 @@ int sn_write_paths_index(sn_ctx* c, const char* paths_inv, const char* countsb)
     std::string err;
     if (paths_inv && !snf::write_ulongvecs(paths_inv, c->pi_off.size() - 1, c->pi_ids.data(), c->pi_off.data(), err)) return fail(c, SN_ERR_IO, err);
     if (countsb && !snf::write_vec_vec_int(countsb, c->pi_countsb, err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+// a.to_left / a.to_right (HyperBasevector::ToLeft/ToRight, written by 10X/WriteFiles.cc:16-60): source and
+// target vertex of every HBV edge
+int sn_write_to_left_right(sn_ctx* c, const char* to_left, const char* to_right)
+{
+    if (!c) return SN_ERR_ARG;
+    if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    std::string err;
+    if (to_left && !snf::write_vec_int(to_left, c->hbv.to_left, err)) return fail(c, SN_ERR_IO, err);
+    if (to_right && !snf::write_vec_int(to_right, c->hbv.to_right, err)) return fail(c, SN_ERR_IO, err);
     return SN_OK;
 }
 int sn_write_inv(sn_ctx* c, const char* path)

@@ -37,7 +37,8 @@ def test_paths_index_files_match_the_reference(sb, name, tmp_path):
         ctx.build_paths_index()
         ctx.write_paths_index(wd + "/a.paths.inv", wd + "/a.countsb")
         ctx.write_inv(wd + "/a.inv")
-    for f in ("a.inv", "a.countsb", "a.paths.inv"):
+        ctx.write_to_left_right(wd + "/a.to_left", wd + "/a.to_right")
+    for f in ("a.inv", "a.countsb", "a.paths.inv") + (("a.to_left", "a.to_right") if os.path.exists(rd + "/a.to_left") else ()):
         assert open(wd + "/" + f, "rb").read() == open(rd + "/" + f, "rb").read(), f
 
 
