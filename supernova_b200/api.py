@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_host", "hbv_csr", "path", "paths_index")
+STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
 
 
 class SnError(RuntimeError):

@@ -142,6 +142,7 @@ static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV,
 // (queue length 2-4) the loop is otherwise a sequence of mispredicted branches on cache misses.
 struct NumberState { int32_t* vid; uint8_t* vbits; uint8_t* seen; int32_t* ids; };
 static inline bool bit_test_set(uint8_t* b, uint32_t i) { const bool was = b[i] != 0; b[i] = 1; return was; }
+template <bool LAID_OUT>
 static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& st, uint32_t start, int32_t& nextV, uint32_t& nH,
                       uint32_t* src, int32_t* to_left, int32_t* to_right, std::vector<uint32_t>& Q)
 {
@@ -157,9 +158,9 @@ static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& s
         const bool new2 = !bit_test_set(st.vbits, (uint32_t)r.g2);         // (g1 == g2: already set)
         if (new2) st.vid[r.g2] = nextV++;
         const int32_t id = (int32_t)nH++;
-        src[id] = it; to_left[id] = st.vid[r.g1]; to_right[id] = st.vid[r.g2];
-        st.ids[it] = id;
-        if ((r.info >> 8) & 1u) { st.ids[it ^ 1u] = id; bit_test_set(st.seen, it ^ 1u); }
+        src[id] = LAID_OUT ? r.pad : it; to_left[id] = st.vid[r.g1]; to_right[id] = st.vid[r.g2];
+        st.ids[it] = id;                                     // (laid out: indexed by record; number_hbv maps back)
+        if (!LAID_OUT && ((r.info >> 8) & 1u)) { st.ids[it ^ 1u] = id; bit_test_set(st.seen, it ^ 1u); }
         if (qt + 24 > Q.size()) {                           // keep the FIFO compact
             std::copy(Q.begin() + qh, Q.begin() + qt, Q.begin()); qt -= qh; qh = 0;
             if (qt + 24 > Q.size()) Q.resize(2 * Q.size());
@@ -194,7 +195,7 @@ static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& s
 // (HBVFromEdges.cc:277-285) reaches first in each, and -- from their sizes -- the first vertex and
 // edge id of every component, so the components are numbered independently, in parallel, with
 // their final ids.
-void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* groups, uint64_t nV_in, uint64_t nE, Hbv& H, unsigned threads)
+void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* groups, uint64_t nV_in, uint64_t nE, Hbv& H, unsigned threads, const uint32_t* layout)
 {
     const uint64_t nH = C.n_comp ? C.base_e[C.n_comp] : 0, nV = C.n_comp ? C.base_v[C.n_comp] : 0;
     if (nV != nV_in) throw std::runtime_error("HBV: component vertex counts do not add up");
@@ -232,6 +233,7 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
                 if (u >= n_units || bad.load()) break;
                 for (uint64_t c = unit_start[u]; c < unit_start[u + 1]; ++c) {
                     int32_t nextV = (int32_t)C.base_v[c]; uint32_t nh = (uint32_t)C.base_e[c];
+                    const uint32_t start = layout ? layout[C.start_item[c]] : C.start_item[c];
                     if (C.base_e[c + 1] - C.base_e[c] >= 32768 && threads > 1) {
                         // A giant component works on private state: the items of the two strand components
                         // interleave in every cache line of the shared arrays, and two threads numbering
@@ -239,14 +241,16 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
                         std::vector<int32_t> pvid(nV, -1), pids(2 * nE, -1);
                         std::vector<uint8_t> pvb(nV + 1, 0), pseen(2 * nE + 1, 0);
                         NumberState ps{pvid.data(), pvb.data(), pseen.data(), pids.data()};
-                        bfs_items(items, groups, ps, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                        if (layout) bfs_items<true>(items, groups, ps, start, nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                        else bfs_items<false>(items, groups, ps, start, nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
                         for (uint64_t h = C.base_e[c]; h < (uint64_t)nh; ++h) {
-                            const uint32_t it = H.src[h];
-                            ids[it] = (int32_t)h;
-                            if ((items[it].info >> 8) & 1u) ids[it ^ 1u] = (int32_t)h;
+                            const uint32_t it = H.src[h];                    // the item itself, whatever the layout
+                            const uint32_t rec_i = layout ? layout[it] : it;
+                            ids[rec_i] = (int32_t)h;
+                            if (!layout && ((items[it].info >> 8) & 1u)) ids[it ^ 1u] = (int32_t)h;
                         }
-                    } else
-                        bfs_items(items, groups, st, C.start_item[c], nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                    } else if (layout) bfs_items<true>(items, groups, st, start, nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
+                    else bfs_items<false>(items, groups, st, start, nextV, nh, H.src.data(), H.to_left.data(), H.to_right.data(), Q);
                     if ((uint64_t)nextV != C.base_v[c + 1] || (uint64_t)nh != C.base_e[c + 1])
                         throw std::runtime_error("HBV: a component was not numbered completely");
                 }
@@ -261,7 +265,14 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
         for (auto& x : th) x.join();
     }
     if (bad.load()) throw std::runtime_error(what);
-    parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { H.fwd[e] = ids[2 * e]; H.rev[e] = ids[2 * e + 1]; } });
+    if (!layout) parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { H.fwd[e] = ids[2 * e]; H.rev[e] = ids[2 * e + 1]; } });
+    else parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) {
+        for (uint64_t e = e0; e < e1; ++e) {
+            const uint32_t f = layout[2 * e];
+            H.fwd[e] = ids[f];
+            H.rev[e] = ((items[f].info >> 8) & 1u) ? ids[f] : ids[layout[2 * e + 1]];      // a palindromic edge has one HBV edge
+        }
+    });
 }
 
 // Host-only construction (vertex discovery with a hash table, sequential numbering, adjacency):

@@ -47,7 +47,10 @@ struct HbvComponents {
 };
 // numbering (HBVBuilder::processQueue) of all components with `threads` host threads: fills
 // n_vert, src, to_left, to_right, fwd, rev
-void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads);
+// `layout` (or nullptr): the records are laid out along the graph (sn_hbvdev.cuh, k_lay_*): record layout[x] is
+// item x, its lists hold record indices and its pad the item
+void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads,
+                const uint32_t* layout = nullptr);
 // host-only construction of the whole HBV (tests/hostsim)
 void build_hbv(const Edges& edges, Hbv& out);
 // sequences of the HBV edges (edges_), fastb packing: epacked (padded), eoff[n+1], elen[n]

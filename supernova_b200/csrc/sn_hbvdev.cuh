@@ -193,6 +193,89 @@ __global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __restrict_
     cv[i] = cnt_v[r.w]; ce[i] = cnt_e[r.w];
 }
 
+// ---- memory layout for the numbering of a giant component -----------------------------------------
+// The numbering of one component is a sequential FIFO traversal that touches one 64-byte record per item.
+// With the records in unipath order (= dictionary order of the owners: random along the genome) every step
+// is a cache miss.  A well-covered genome is one or two components, so before the records of such a graph
+// travel to the host they are laid out along the graph: a multi-source breadth-first labelling from 1 item
+// in 32 (k_lay_seed / k_lay_round: one launch per round over the frontier, no host round trip), then the
+// records are sorted by (seed, signed distance from the seed: one arm, the seed, the other arm) and their item
+// lists renamed.  The layout changes no result: the traversal order only depends on the lists.
+#define SN_LAY_NONE 0xFFFFFFFFu
+__device__ __forceinline__ bool lay_is_seed(uint32_t item) { return ((item * 0x9E3779B1u) >> 27) == 0u; }      // 1 in 32
+__global__ void __launch_bounds__(256) k_lay_seed(const snh::ItemRec* __restrict__ rec, uint32_t n_items, uint32_t* __restrict__ lab, uint32_t* __restrict__ lev,
+                                                  uint32_t* __restrict__ frontier, uint32_t* __restrict__ cnt /* 3 counters */)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    uint32_t l = SN_LAY_NONE;
+    if (rec[t].g1 >= 0 && rec[t].g2 >= 0 && lay_is_seed(t)) { l = t; frontier[atomicAdd(cnt, 1u)] = t; }
+    lab[t] = l; lev[t] = 0u;
+}
+// round r: every item of frontier (r & 1) labels its unlabelled neighbours (the items on its two vertices)
+__global__ void __launch_bounds__(256) k_lay_round(const snh::ItemRec* __restrict__ rec, const snh::GroupRec* __restrict__ groups, uint32_t round,
+                                                   uint32_t* __restrict__ lab, uint32_t* __restrict__ lev, uint32_t* __restrict__ fa, uint32_t* __restrict__ fb, uint32_t* __restrict__ cnt)
+{
+    const uint32_t* fin = (round & 1u) ? fb : fa;
+    uint32_t* fout = (round & 1u) ? fa : fb;
+    const uint32_t n = cnt[round % 3u];
+    uint32_t* nout = cnt + (round + 1u) % 3u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(round + 2u) % 3u] = 0u;          // the counter of the round after next
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t x = fin[i];
+        const snh::ItemRec r = rec[x];
+        const uint32_t l = lab[x];
+        const uint32_t arm_x = lev[x] & 0x80000000u;        // which side of its seed the item lies on (set at the first hop)
+        for (int side = 0; side < 2; ++side) {
+            uint32_t m = (r.info >> (4 * side)) & 15u;
+            const uint32_t* items = side ? r.it2 : r.it1;
+            if (m == 15u) { const snh::GroupRec& G = groups[side ? r.g2 : r.g1]; m = G.n; items = G.items; }
+            const uint32_t arm = round == 0u ? (side ? 0x80000000u : 0u) : arm_x;
+            for (uint32_t k = 0; k < m; ++k) {
+                const uint32_t y = items[k];
+                if (lab[y] == SN_LAY_NONE && atomicCAS(lab + y, SN_LAY_NONE, l) == SN_LAY_NONE) { lev[y] = (round + 1u) | arm; fout[atomicAdd(nout, 1u)] = y; }
+            }
+        }
+    }
+}
+// sort records {seed, signed distance, item}; what no seed reached is its own seed
+__global__ void __launch_bounds__(256) k_lay_keys(const uint32_t* __restrict__ lab, const uint32_t* __restrict__ lev, uint32_t n_items, uint4* __restrict__ key)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const uint32_t l = lab[t];
+    const uint32_t v = lev[t], d = v & 0x7FFFFFFFu;
+    key[t] = make_uint4(l == SN_LAY_NONE ? t : l, l == SN_LAY_NONE ? 0x40000000u : ((v >> 31) ? 0x40000000u + d : 0x40000000u - d), t, 0u);
+}
+__global__ void __launch_bounds__(256) k_lay_pos(const uint4* __restrict__ key, uint32_t n_items, uint32_t* __restrict__ pos)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_items) pos[key[i].z] = i;
+}
+// record i of the new layout = the record of item key[i].z with its lists renamed; pad = the item it is
+__global__ void __launch_bounds__(128) k_lay_permute(const uint4* __restrict__ key, const uint32_t* __restrict__ pos, const snh::ItemRec* __restrict__ rec, uint32_t n_items,
+                                                     snh::ItemRec* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const uint32_t x = key[i].z;
+    snh::ItemRec r = rec[x];
+    const uint32_t n1 = r.info & 15u, n2 = (r.info >> 4) & 15u;
+    if (n1 != 15u) for (uint32_t k = 0; k < n1 && k < 6u; ++k) r.it1[k] = pos[r.it1[k]];
+    if (n2 != 15u) for (uint32_t k = 0; k < n2 && k < 6u; ++k) r.it2[k] = pos[r.it2[k]];
+    r.pad = x;
+    out[i] = r;
+}
+// the vertex records the numbering loop reads (more than 6 items) with their lists renamed
+__global__ void __launch_bounds__(256) k_lay_groups(const snh::GroupRec* __restrict__ groups, uint32_t n_groups, const uint32_t* __restrict__ pos, snh::GroupRec* __restrict__ out)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    snh::GroupRec r = groups[g];
+    if (r.n > 6u) for (uint32_t k = 0; k < r.n && k < 8u; ++k) r.items[k] = pos[r.items[k]];
+    out[g] = r;
+}
+
 // ---- after the numbering: adjacency lists and involution ----------------------------------------
 __global__ void __launch_bounds__(256) k_hbv_csr_rec(const int32_t* __restrict__ to_left, const int32_t* __restrict__ to_right, uint32_t n_h,
                                                      uint4* __restrict__ rec_from, uint4* __restrict__ rec_to)

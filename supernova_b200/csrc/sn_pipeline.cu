@@ -1146,6 +1146,51 @@ int sn_build_hbv(sn_ctx* c)
     CU(cudaStreamSynchronize(c->st));
     if (h_err) return fail(c, SN_ERR_DATA, "HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
     if (tot_v != nV) return fail(c, SN_ERR_DATA, "HBV: component vertex counts do not add up");
+    // ---- a giant component: lay the records out along the graph first (sn_hbvdev.cuh, k_lay_*) -----------
+    const uint32_t* layout = nullptr;
+    {
+        uint64_t max_comp = 0;
+        for (uint64_t k = 0; k < n_comp; ++k) max_comp = std::max(max_comp, h_basee[k + 1] - h_basee[k]);
+        const bool no_layout = getenv("SN_HBV_NO_LAYOUT") != nullptr;
+        const uint64_t lay_min = getenv("SN_HBV_LAYOUT_MIN") ? (uint64_t)atoll(getenv("SN_HBV_LAYOUT_MIN")) : 262144;      // tests lower it
+        c->host_ms["hbv_layout"] = 0.0;
+        if (max_comp >= lay_min && !no_layout) {
+            auto tl0 = std::chrono::steady_clock::now();
+            DevBuf &lab = c->pool["lay_lab"], &lev = c->pool["lay_lev"], &fa = c->pool["lay_fa"], &fb = c->pool["lay_fb"], &ka = c->pool["lay_ka"], &kb = c->pool["lay_kb"],
+                   &posd = c->pool["lay_pos"], &irec2 = c->pool["lay_irec"], &groups2 = c->pool["lay_groups"];
+            CU(lab.alloc(4ull * n_items)); CU(lev.alloc(4ull * n_items)); CU(fa.alloc(4ull * n_items)); CU(fb.alloc(4ull * n_items));
+            CU(ka.alloc(16ull * n_items)); CU(kb.alloc(16ull * n_items)); CU(posd.alloc(4ull * n_items)); CU(irec2.alloc(64ull * n_items)); CU(groups2.alloc(64ull * nV));
+            uint32_t* cnt3 = u32c + 12;
+            CU(cudaMemsetAsync(cnt3, 0, 12, c->st));
+            k_lay_seed<<<blocks_for(n_items, 256), 256, 0, c->st>>>(irec.as<snh::ItemRec>(), n_items, lab.as<uint32_t>(), lev.as<uint32_t>(), fa.as<uint32_t>(), cnt3);
+            KCHECK("k_lay_seed");
+            const unsigned lay_grid = (unsigned)std::min<uint64_t>(2 * c->num_sms, blocks_for(n_items / 32 + 1, 256));
+            const uint32_t lay_rounds = 64;              // seeds are ~32 items apart: what 64 rounds do not reach becomes its own cluster
+            for (uint32_t round = 0; round < lay_rounds; ++round)
+                k_lay_round<<<lay_grid, 256, 0, c->st>>>(irec.as<snh::ItemRec>(), groups.as<snh::GroupRec>(), round, lab.as<uint32_t>(), lev.as<uint32_t>(),
+                    fa.as<uint32_t>(), fb.as<uint32_t>(), cnt3);
+            c->launches += lay_rounds;
+            k_lay_keys<<<blocks_for(n_items, 256), 256, 0, c->st>>>(lab.as<uint32_t>(), lev.as<uint32_t>(), n_items, ka.as<uint4>());
+            KCHECK("k_lay_keys");
+            e = radix_sort<RS_KEY96>(ka.as<uint4>(), kb.as<uint4>(), n_items, tmp.p, c->num_sms, c->st);
+            c->launches += 2 + RsMode<RS_KEY96>::PASSES;
+            if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("hbv layout sort: ") + cudaGetErrorString(e));
+            k_lay_pos<<<blocks_for(n_items, 256), 256, 0, c->st>>>(ka.as<uint4>(), n_items, posd.as<uint32_t>());
+            KCHECK("k_lay_pos");
+            k_lay_permute<<<blocks_for(n_items, 128), 128, 0, c->st>>>(ka.as<uint4>(), posd.as<uint32_t>(), irec.as<snh::ItemRec>(), n_items, irec2.as<snh::ItemRec>());
+            KCHECK("k_lay_permute");
+            k_lay_groups<<<blocks_for(nV, 256), 256, 0, c->st>>>(groups.as<snh::GroupRec>(), nV, posd.as<uint32_t>(), groups2.as<snh::GroupRec>());
+            KCHECK("k_lay_groups");
+            HostBuf& h_lay = c->hpool["hbv_layout"];
+            CU(h_lay.alloc(4ull * n_items));
+            CU(cudaMemcpyAsync(h_irec.p, irec2.p, 64ull * n_items, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(h_groups.p, groups2.p, 64ull * nV, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(h_lay.p, posd.p, 4ull * n_items, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            layout = h_lay.as<uint32_t>();
+            c->host_ms["hbv_layout"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
+        }
+    }
     // ---- the FIFO numbering, all components in parallel on the host ----------------------------------
     auto t0 = std::chrono::steady_clock::now();
     snh::HbvComponents comps; comps.n_comp = n_comp; comps.start_item = h_cstart; comps.base_v = h_basev; comps.base_e = h_basee;
@@ -1155,7 +1200,7 @@ int sn_build_hbv(sn_ctx* c)
         resize_pinned(c, Hn.src, tot_h); resize_pinned(c, Hn.to_left, tot_h); resize_pinned(c, Hn.to_right, tot_h);
         resize_pinned(c, Hn.fwd, nE); resize_pinned(c, Hn.rev, nE);
     }
-    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, hbv_threads); }
+    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, hbv_threads, layout); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     snh::Hbv& H = c->hbv;

@@ -226,3 +226,30 @@ def test_count_in_several_passes(sb, name, passes):
     assert all(np.array_equal(a, b) for a, b in zip(p0, p1))
     for f in ("n_kmers", "n_kmers_distinct", "n_superkmers", "n_kmer_occurrences", "n_edges", "n_hbv_edges"):
         assert c0[f] == c1[f], f
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1", "stress2", "stress3", "C1", "mid"])
+def test_hbv_numbering_over_laid_out_records(sb, name, tmp_path):
+    """A giant component is numbered over records laid out along the graph (multi-source labelling +
+    sort on the device, sn_hbvdev.cuh k_lay_*); forced here for every component size: the same a.hbv,
+    xlat tables and paths as with the records in unipath order."""
+    codes, quals, off, bc, _ = datasets.get(name)
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    out = {}
+    for mode in ("plain", "laid_out"):
+        if mode == "laid_out":
+            os.environ["SN_HBV_LAYOUT_MIN"] = "1"
+        else:
+            os.environ["SN_HBV_NO_LAYOUT"] = "1"
+        try:
+            with sb.Context(0) as ctx:
+                ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+                ctx.build_read_qgraph48(None, sb.Params(), with_paths=True)
+                ctx.write_hbv(str(tmp_path / (mode + ".hbv")))
+                out[mode] = (ctx.hbv(), ctx.paths(), ctx.stage_ms().get("hbv_layout"))
+        finally:
+            os.environ.pop("SN_HBV_LAYOUT_MIN", None); os.environ.pop("SN_HBV_NO_LAYOUT", None)
+    assert out["laid_out"][2] > 0 and out["plain"][2] == 0
+    assert open(tmp_path / "plain.hbv", "rb").read() == open(tmp_path / "laid_out.hbv", "rb").read()
+    assert all(np.array_equal(out["plain"][0][x], out["laid_out"][0][x]) for x in out["plain"][0])
+    assert all(np.array_equal(a, b) for a, b in zip(out["plain"][1], out["laid_out"][1]))
