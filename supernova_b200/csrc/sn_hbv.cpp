@@ -87,6 +87,7 @@ inline uint64_t mix(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^=
 
 }  // namespace
 
+#ifdef SN_HOSTSIM      // host-only construction: compiled into tests/hostsim only, never into the product library
 // HBVBuilder::add / processQueue (HBVFromEdges.cc:189-228) from one start item: FIFO breadth-first
 // numbering of everything reachable.  Vertices are numbered from nextV, HBV edges from nH (both
 // advanced).  An item is queued at most once (id -2 = queued): the reference queues duplicates
@@ -131,6 +132,8 @@ static void bfs_from(GroupRec* groups, ERec* er, uint32_t start, int32_t& nextV,
         }
     }
 }
+
+#endif
 
 // The same traversal over the one-line item records the device prepares (product path).  A popped
 // item costs one cache line, and that line was requested when the item was queued.  What the loop
@@ -275,6 +278,7 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
     });
 }
 
+#ifdef SN_HOSTSIM
 // Host-only construction (vertex discovery with a hash table, sequential numbering, adjacency):
 // what tests/hostsim runs on a CPU box.  The product uses the device stages of sn_hbvdev.cuh with
 // number_hbv in between.
@@ -400,6 +404,8 @@ void build_hbv(const Edges& E, Hbv& H)
     H.inv.assign(nH, -1);
     for (uint64_t e = 0; e < nE; ++e) { H.inv[H.fwd[e]] = H.rev[e]; H.inv[H.rev[e]] = H.fwd[e]; }
 }
+
+#endif  // SN_HOSTSIM
 
 void hbv_edge_sequences(const Edges& E, const Hbv& H, std::vector<uint8_t>& epacked, std::vector<uint64_t>& eoff, std::vector<uint32_t>& elen)
 {

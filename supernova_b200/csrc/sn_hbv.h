@@ -51,8 +51,10 @@ struct HbvComponents {
 // item x, its lists hold record indices and its pad the item
 void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads,
                 const uint32_t* layout = nullptr);
-// host-only construction of the whole HBV (tests/hostsim)
+#ifdef SN_HOSTSIM
+// host-only construction of the whole HBV: exists in tests/hostsim only (the product library is built without it)
 void build_hbv(const Edges& edges, Hbv& out);
+#endif
 // sequences of the HBV edges (edges_), fastb packing: epacked (padded), eoff[n+1], elen[n]
 void hbv_edge_sequences(const Edges& edges, const Hbv& h, std::vector<uint8_t>& epacked, std::vector<uint64_t>& eoff, std::vector<uint32_t>& elen);
 

@@ -16,7 +16,7 @@ def lib():
         src = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(ROOT, "supernova_b200", "csrc", f) for f in
                                                        ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so] + src[:3])
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DSN_HOSTSIM", "-o", so] + src[:3] + ["-lz"])
         L = C.CDLL(so)
         vp, u64 = C.c_void_p, C.c_uint64
         L.hs_new.restype = vp
