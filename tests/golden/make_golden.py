@@ -2,7 +2,8 @@
 (oracle/_ref, built from /root/reference by oracle/build_ref.sh) in this container.
 For each data set: the input files written by the reference's ParseBarcodedFastqs
 (reads.fastb/.qualp/.bci) and the outputs of its buildReadQGraph48 (kmers.kvec reduced to
-the sorted {k-mer,count,ctx} records, a.hbv, tmp.paths, histogram_kmer_count.json).
+the sorted {k-mer,count,ctx} records, a.hbv, tmp.paths, histogram_kmer_count.json) and of the DF-side
+step that follows (Involution, ToLeft/ToRight, writePathsIndex: a.inv, a.to_left, a.to_right, a.paths.inv, a.countsb).
 
     python tests/golden/make_golden.py        # needs oracle/_ref
 """
@@ -33,10 +34,10 @@ def main():
         wd = tempfile.mkdtemp()
         synth.write_fasth_ragged(wd + "/reads.fastq.gz", codes, quals, off, ids)
         refrun.parse_fastqs(wd, wd + "/reads.fastq.gz")
-        refrun.run_probe(wd)
+        refrun.run_probe(wd, extra=("INDEX=True",))       # + a.inv, a.to_left/right, a.paths.inv, a.countsb (DF side, 10X/DF.cc:586-590)
         out = os.path.join(HERE, name)
         os.makedirs(out, exist_ok=True)
-        for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths"):
+        for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths", "a.inv", "a.to_left", "a.to_right", "a.paths.inv", "a.countsb"):
             with open(os.path.join(wd, f), "rb") as src, gzip.GzipFile(os.path.join(out, f + ".gz"), "wb", mtime=0) as dst:
                 dst.write(src.read())
         shutil.copy(wd + "/stats/histogram_kmer_count.json", out + "/histogram_kmer_count.json")

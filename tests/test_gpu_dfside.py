@@ -42,6 +42,29 @@ def test_paths_index_files_match_the_reference(sb, name, tmp_path):
         assert open(wd + "/" + f, "rb").read() == open(rd + "/" + f, "rb").read(), f
 
 
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_dfside_files_match_golden(sb, name, tmp_path):
+    """The same files against the committed golden ones (written by the reference, tests/golden/make_golden.py)
+    and against the python restatement (oracle/dfside.py): needs no reference binary on the box."""
+    import gzip
+    from oracle import dfside
+    codes, quals, off, bc, _ = datasets.get(name)
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    wd = str(tmp_path)
+    with sb.Context(0) as ctx:
+        ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ctx.build_read_qgraph48(wd, sb.Params(), with_paths=True)
+        ctx.build_paths_index()
+        ctx.write_paths_index(wd + "/a.paths.inv", wd + "/a.countsb")
+        ctx.write_inv(wd + "/a.inv")
+        ctx.write_to_left_right(wd + "/a.to_left", wd + "/a.to_right")
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    for f in ("a.inv", "a.to_left", "a.to_right", "a.countsb", "a.paths.inv"):
+        assert open(wd + "/" + f, "rb").read() == gzip.open(g + "/" + f + ".gz", "rb").read(), f
+    pi, cb = dfside.paths_index(dfside.read_paths(open(wd + "/tmp.paths", "rb").read()), dfside.read_vec_int(open(wd + "/a.inv", "rb").read()))
+    assert pi == open(wd + "/a.paths.inv", "rb").read() and cb == open(wd + "/a.countsb", "rb").read()
+
+
 def test_paths_index_properties_mid(sb):
     codes, quals, off, bc, _ = datasets.get("mid")
     pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)

@@ -125,3 +125,14 @@ def test_ingest_errors_are_loud(sb):
             assert what in str(e.value), (what, str(e.value))
         ctx.load_fasth_text(good)                   # and the context still works afterwards
         assert ctx.counts()["n_reads"] == 24
+
+
+def test_odd_text_matches_the_restatement(sb, tmp_path):
+    """The hand-made text against oracle/dfside.py (the python restatement of ParseBarcodedFastqs, pinned to the
+    golden files in tests/test_oracle_golden.py): needs no reference binary on the box."""
+    from oracle import dfside
+    text = odd_text()
+    with sb.Context(0) as ctx:
+        ctx.load_fasth_text(text)
+        ctx.save_read_files(str(tmp_path / "mine"))
+    assert files(str(tmp_path / "mine")) == list(dfside.parse_fasth(text))

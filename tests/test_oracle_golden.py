@@ -70,3 +70,30 @@ def test_oracle_matches_reference_live(name, tmp_path):
     o.write_paths(wd + "/o.paths")
     assert open(wd + "/o.hbv", "rb").read() == open(wd + "/a.hbv", "rb").read()
     assert open(wd + "/o.paths", "rb").read() == open(wd + "/tmp.paths", "rb").read()
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_paths_index_restatement_matches_golden(name):
+    """oracle/dfside.py (writePathsIndex, 10X/PathsIndex.cc:23-143) on the golden tmp.paths + a.inv
+    reproduces the golden a.paths.inv / a.countsb the reference wrote."""
+    from oracle import dfside
+    g = os.path.join(GOLD, name)
+    paths = dfside.read_paths(gz(g + "/tmp.paths.gz"))
+    inv = dfside.read_vec_int(gz(g + "/a.inv.gz"))
+    pi, cb = dfside.paths_index(paths, inv)
+    assert pi == gz(g + "/a.paths.inv.gz")
+    assert cb == gz(g + "/a.countsb.gz")
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_ingest_restatement_matches_golden(name, tmp_path):
+    """oracle/dfside.py (ParseBarcodedFastqs, 10X/ParseBarcodedFastqs.cc:56-146,284-303; PQVecEncoder,
+    feudal/PQVec.cc:17-127) on the data set's pseudo-FASTQ text reproduces the golden reads.fastb/.qualp/.bci."""
+    from oracle import dfside
+    from supernova_b200 import synth
+    codes, quals, off, bc, ids = datasets.get(name)
+    p = str(tmp_path / "x.fastq.gz")
+    synth.write_fasth_ragged(p, codes, quals, off, ids)
+    fb, qp, bci = dfside.parse_fasth(gz(p))
+    g = os.path.join(GOLD, name)
+    assert fb == gz(g + "/reads.fastb.gz") and qp == gz(g + "/reads.qualp.gz") and bci == gz(g + "/reads.bci.gz")
