@@ -17,6 +17,6 @@ def pytest_configure(config):
 def built():
     import __graft_entry__ as g
     so = os.path.join(ROOT, "supernova_b200", "libsupernova_b200.so")
-    if not os.path.exists(so):
+    if not os.path.exists(so) or not os.path.exists(os.path.join(ROOT, "supernova_b200", "sn_build_graph")):
         g.build()
     return so

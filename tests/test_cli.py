@@ -1,0 +1,48 @@
+"""The C++ host driver over the C ABI (supernova_b200/csrc/sn_cli.cpp -> supernova_b200/sn_build_graph).
+CPU: it builds, prints its usage, and fails LOUDLY without a CUDA device (no CPU fallback).
+GPU: fasth.gz in -> every file the reference leaves behind, against the golden ones."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+import datasets
+from supernova_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "supernova_b200", "sn_build_graph")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_cli_usage_and_loud_failure(built, tmp_path):
+    assert os.access(EXE, os.X_OK)
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: sn_build_graph" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([EXE, "HEAD=" + str(tmp_path / "reads"), "OUT=" + str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_cli_reproduces_the_reference_files(built, name, tmp_path):
+    codes, quals, off, bc, ids = datasets.get(name)
+    wd = str(tmp_path)
+    fq = wd + "/in.fastq.gz"
+    synth.write_fasth_ragged(fq, codes, quals, off, ids)
+    r = subprocess.run([EXE, "FASTH=" + fq, "HEAD=" + wd + "/reads", "OUT=" + wd, "INDEX=True"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "k-mers" in r.stdout
+    g = os.path.join(GOLD, name)
+    for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths", "a.inv", "a.to_left", "a.to_right", "a.paths.inv", "a.countsb"):
+        assert open(wd + "/" + f, "rb").read() == gzip.open(g + "/" + f + ".gz", "rb").read(), f
+    assert open(wd + "/stats/histogram_kmer_count.json").read() == open(g + "/histogram_kmer_count.json").read()
+    # and from the files alone (no FASTH): the same graph
+    out2 = wd + "/again"
+    os.makedirs(out2)
+    r = subprocess.run([EXE, "HEAD=" + wd + "/reads", "OUT=" + out2, "PATHS=False"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out2 + "/a.hbv", "rb").read() == open(wd + "/a.hbv", "rb").read()
+    assert not os.path.exists(out2 + "/tmp.paths")
