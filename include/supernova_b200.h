@@ -93,6 +93,8 @@ int sn_load_reads_q8(sn_ctx* ctx, uint64_t n_reads, const uint8_t* bases, const 
  * PQVec-encoded by CUDA kernels straight into the context.  `text` is the decompressed content.       */
 int sn_load_fasth_text(sn_ctx* ctx, const char* text, uint64_t n_bytes);
 int sn_load_fasth_file(sn_ctx* ctx, const char* path /* plain or .gz */);
+/* FASTQS={a,b,...} (:258-264): several barcode-sorted files; a file never continues the barcode of the one before it */
+int sn_load_fasth_files(sn_ctx* ctx, const char* const* paths, uint32_t n_files);
 /* the loaded reads as reads.fastb / reads.qualp / reads.bci (any may be NULL)                        */
 int sn_save_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 /* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */

@@ -127,33 +127,38 @@ def pqvec_encode(q):
 
 
 def parse_fasth(text):
-    """newUnpackBarcodeSortedFastq + main (:56-146, :284-303) -> (reads.fastb, reads.qualp, reads.bci) bytes."""
-    lines = text.split(b"\n")
-    assert lines[-1] == b"" and (len(lines) - 1) % 9 == 0, "out of sync"
+    """newUnpackBarcodeSortedFastq + main (:56-146, :284-303) -> (reads.fastb, reads.qualp, reads.bci) bytes.
+    `text`: the content of one file, or a list of contents (FASTQS={a,b,...}, :258-264: the barcode ordinal runs on
+    across the files, :66, the comparison string starts empty in each, :67)."""
+    texts = [text] if isinstance(text, (bytes, bytearray)) else list(text)
     code = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("T"): 3}
     b0, bc_reads, bcs = [], [], []
-    barc, lastb = 0, None
-    for r in range((len(lines) - 1) // 9):
-        L = [x.replace(b"n", b"A").replace(b"N", b"A") for x in lines[9 * r:9 * r + 9]]       # :84-85
-        assert L[0].startswith(b"@")
-        pair = []
-        for m in (0, 1):
-            bases = [code[c & 0xDF] for c in L[1 + 2 * m]]
-            quals = [c - 33 for c in L[2 + 2 * m]]                                       # convertPhred :37-44
-            packed = bytearray((len(bases) + 3) // 4)
-            for i, v in enumerate(bases):
-                packed[i >> 2] |= v << (2 * (i & 3))                                     # feudal/FieldVec.h:596-598
-            pair.append((len(bases), bytes(packed), pqvec_encode(quals)))
-        buf = L[5]
-        if b"-" in buf and not buf.startswith(b"-"):                                     # :107
-            key = buf.split(b",")[0]                                                     # SafeBefore(",") :108
-            if key != lastb:
-                barc += 1
-                lastb = key
-            bcs += [barc, barc]
-            bc_reads += pair
-        else:
-            b0 += pair
+    barc = 0
+    for one in texts:
+      lines = one.split(b"\n")
+      assert lines[-1] == b"" and (len(lines) - 1) % 9 == 0, "out of sync"
+      lastb = None
+      for r in range((len(lines) - 1) // 9):
+          L = [x.replace(b"n", b"A").replace(b"N", b"A") for x in lines[9 * r:9 * r + 9]]       # :84-85
+          assert L[0].startswith(b"@")
+          pair = []
+          for m in (0, 1):
+              bases = [code[c & 0xDF] for c in L[1 + 2 * m]]
+              quals = [c - 33 for c in L[2 + 2 * m]]                                       # convertPhred :37-44
+              packed = bytearray((len(bases) + 3) // 4)
+              for i, v in enumerate(bases):
+                  packed[i >> 2] |= v << (2 * (i & 3))                                     # feudal/FieldVec.h:596-598
+              pair.append((len(bases), bytes(packed), pqvec_encode(quals)))
+          buf = L[5]
+          if b"-" in buf and not buf.startswith(b"-"):                                     # :107
+              key = buf.split(b",")[0]                                                     # SafeBefore(",") :108
+              if key != lastb:
+                  barc += 1
+                  lastb = key
+              bcs += [barc, barc]
+              bc_reads += pair
+          else:
+              b0 += pair
     reads = b0 + bc_reads
     n = len(reads)
     bci = [0]

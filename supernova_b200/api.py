@@ -51,6 +51,7 @@ def lib():
         L.sn_write_paths_index.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.sn_load_fasth_text.argtypes = [vp, vp, u64]
         L.sn_load_fasth_file.argtypes = [vp, C.c_char_p]
+        L.sn_load_fasth_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32]
         L.sn_save_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_load_reads_streamed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.sn_load_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
@@ -211,6 +212,10 @@ class Context:
 
     def load_fasth_file(self, path):
         self._ck(self.L.sn_load_fasth_file(self.h, path.encode()))
+
+    def load_fasth_files(self, paths):
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        self._ck(self.L.sn_load_fasth_files(self.h, arr, len(paths)))
 
     def save_read_files(self, head):
         self._ck(self.L.sn_save_read_files(self.h, (head + ".fastb").encode(), (head + ".qualp").encode(), (head + ".bci").encode()))

@@ -49,6 +49,17 @@ __global__ void __launch_bounds__(256) k_nl_fill(const uint8_t* __restrict__ tex
     for (uint64_t i = a; i < b; ++i) if (text[i] == '\n') line_start[++k] = i + 1;
 }
 
+// line index of a byte offset that is a line start (file boundaries): one thread per file
+__global__ void k_fasth_file_lines(const uint64_t* __restrict__ line_start, uint64_t n_lines, const uint64_t* __restrict__ file_first_byte, uint32_t n_files, uint64_t* __restrict__ file_first_line)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files) return;
+    const uint64_t b = file_first_byte[f];
+    uint64_t lo = 0, hi = n_lines;                       // first line with line_start >= b
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (line_start[mid] < b) lo = mid + 1; else hi = mid; }
+    file_first_line[f] = line_start[lo] == b ? lo : ~0ull;
+}
+
 __device__ __forceinline__ uint8_t ing_fold(uint8_t c) { return (c == 'n' || c == 'N') ? (uint8_t)'A' : c; }
 
 // ---- records -----------------------------------------------------------------------------------
@@ -71,11 +82,16 @@ __global__ void __launch_bounds__(256) k_fasth_blist(const uint32_t* __restrict_
 }
 // barcoded record j starts a new barcode iff its key differs from the previous barcoded record's
 // (key = the line after n/N -> A, up to the first ','  -- :108-111)
-__global__ void __launch_bounds__(256) k_fasth_newbc(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, const uint32_t* __restrict__ blist, uint64_t n_bc, uint32_t* __restrict__ isnew)
+// Several input files (FASTQS={a,b,...}, :262-264): the comparison string starts empty in every file (:67), so the
+// first barcoded record of a file always opens a new barcode.  file_first_rec[f] = first record of file f.
+__global__ void __launch_bounds__(256) k_fasth_newbc(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, const uint32_t* __restrict__ blist, uint64_t n_bc, uint32_t* __restrict__ isnew,
+                                                     const uint32_t* __restrict__ file_first_rec, uint32_t n_files)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_bc) return;
     if (j == 0) { isnew[0] = 1u; return; }
+    for (uint32_t f = 1; f < n_files; ++f)
+        if (blist[j] >= file_first_rec[f] && blist[j - 1] < file_first_rec[f]) { isnew[j] = 1u; return; }
     const uint64_t a = ls[9ull * blist[j] + 5], ae = ls[9ull * blist[j] + 6] - 1;
     const uint64_t b = ls[9ull * blist[j - 1] + 5], be = ls[9ull * blist[j - 1] + 6] - 1;
     uint64_t i = 0;

@@ -307,7 +307,28 @@ int sn_load_reads_q8(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const ui
 // file content in host memory.  The reads land in the context exactly as sn_load_reads would leave them
 // (unbarcoded reads first, barcode ordinals from 1), so sn_build_read_qgraph48 can follow directly and
 // sn_save_read_files writes the reference's .fastb/.qualp/.bci byte for byte.
+static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const uint64_t* file_first_byte, uint32_t n_files);
 int sn_load_fasth_text(sn_ctx* c, const char* text, uint64_t n_bytes)
+{
+    const uint64_t zero = 0;
+    return load_fasth_impl(c, text, n_bytes, &zero, 1);
+}
+// several barcode-sorted files, as ParseBarcodedFastqs FASTQS={a,b,...} takes them (:258-264): the unbarcoded reads
+// of all files first, then the barcoded ones in file order; a file never continues the barcode of the one before
+int sn_load_fasth_files(sn_ctx* c, const char* const* paths, uint32_t n_files)
+{
+    if (!c || !paths || !n_files) return SN_ERR_ARG;
+    if (n_files > 4096) return fail(c, SN_ERR_ARG, "sn_load_fasth_files: more than 4096 files");
+    std::vector<char> text, one; std::vector<uint64_t> first; std::string err;
+    for (uint32_t f = 0; f < n_files; ++f) {
+        if (!paths[f] || !snf::read_text_maybe_gz(paths[f], one, err)) return fail(c, SN_ERR_IO, paths[f] ? err : "NULL path");
+        if (!one.empty() && one.back() != '\n') return fail(c, SN_ERR_DATA, std::string("fasth: out of sync reading line (") + paths[f] + " does not end with a newline)");
+        first.push_back(text.size());
+        text.insert(text.end(), one.begin(), one.end());
+    }
+    return load_fasth_impl(c, text.data(), text.size(), first.data(), n_files);
+}
+static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const uint64_t* file_first_byte, uint32_t n_files)
 {
     if (!c || (!text && n_bytes)) return SN_ERR_ARG;
     CU(cudaSetDevice(c->device));
@@ -336,6 +357,23 @@ int sn_load_fasth_text(sn_ctx* c, const char* text, uint64_t n_bytes)
     CU(ls.alloc(8 * (n_lines + 1)));
     k_nl_fill<<<blocks_for(n_seg, 256), 256, 0, c->st>>>(T, n_bytes, sego.as<uint64_t>(), n_seg, ls.as<uint64_t>());
     KCHECK("k_nl_fill");
+    // file boundaries -> first record of every file (each file must hold whole records)
+    DevBuf &ffb = c->pool["ing_ffb"], &ffl = c->pool["ing_ffl"], &ffr = c->pool["ing_ffr"];
+    CU(ffb.alloc(8ull * n_files)); CU(ffl.alloc(8ull * n_files)); CU(ffr.alloc(4ull * n_files));
+    {
+        CU(cudaMemcpyAsync(ffb.p, file_first_byte, 8ull * n_files, cudaMemcpyHostToDevice, c->st));
+        k_fasth_file_lines<<<blocks_for(n_files, 64), 64, 0, c->st>>>(ls.as<uint64_t>(), n_lines, ffb.as<uint64_t>(), n_files, ffl.as<uint64_t>());
+        KCHECK("k_fasth_file_lines");
+        std::vector<uint64_t> h_l(n_files); std::vector<uint32_t> h_r(n_files);
+        CU(cudaMemcpyAsync(h_l.data(), ffl.p, 8ull * n_files, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        for (uint32_t f = 0; f < n_files; ++f) {
+            if (h_l[f] == ~0ull || h_l[f] % 9) return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (input file " + std::to_string(f) + " does not start on a record boundary: the file before it is not 9 lines per record)");
+            h_r[f] = (uint32_t)(h_l[f] / 9);
+        }
+        CU(cudaMemcpyAsync(ffr.p, h_r.data(), 4ull * n_files, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
     uint32_t* err = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8) + 10;
     CU(cudaMemsetAsync(err, 0, 4, c->st));
     DevBuf &bflag = c->pool["ing_bflag"], &bbefore = c->pool["ing_bbefore"], &blist = c->pool["ing_blist"], &isnew = c->pool["ing_isnew"], &nbefore = c->pool["ing_nbefore"];
@@ -349,7 +387,7 @@ int sn_load_fasth_text(sn_ctx* c, const char* text, uint64_t n_bytes)
     if (n_bc) {
         k_fasth_blist<<<blocks_for(n_rec, 256), 256, 0, c->st>>>(bflag.as<uint32_t>(), bbefore.as<uint64_t>(), n_rec, blist.as<uint32_t>());
         KCHECK("k_fasth_blist");
-        k_fasth_newbc<<<blocks_for(n_bc, 256), 256, 0, c->st>>>(T, ls.as<uint64_t>(), blist.as<uint32_t>(), n_bc, isnew.as<uint32_t>());
+        k_fasth_newbc<<<blocks_for(n_bc, 256), 256, 0, c->st>>>(T, ls.as<uint64_t>(), blist.as<uint32_t>(), n_bc, isnew.as<uint32_t>(), ffr.as<uint32_t>(), n_files);
         KCHECK("k_fasth_newbc");
         if ((r = scan_u32(c, isnew.as<uint32_t>(), n_bc, nbefore.as<uint64_t>(), &n_barcodes))) return r;
     }

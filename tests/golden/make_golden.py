@@ -27,6 +27,13 @@ from supernova_b200 import synth  # noqa: E402
 SETS = ["tiny", "stress1"]
 
 
+def split_text(text):
+    """two files out of one: cut at the record boundary just after the middle (inside a barcode's run of records)"""
+    lines = text.split(b"\n")[:-1]
+    cut = 9 * ((len(lines) // 9) // 2 + 1)
+    return b"\n".join(lines[:cut]) + b"\n", b"\n".join(lines[cut:]) + b"\n"
+
+
 def main():
     assert refrun.have_ref(), "build oracle/_ref first (bash oracle/build_ref.sh)"
     for name in SETS:
@@ -41,6 +48,17 @@ def main():
             with open(os.path.join(wd, f), "rb") as src, gzip.GzipFile(os.path.join(out, f + ".gz"), "wb", mtime=0) as dst:
                 dst.write(src.read())
         shutil.copy(wd + "/stats/histogram_kmer_count.json", out + "/histogram_kmer_count.json")
+        if name == "tiny":      # the same text as two input files, cut inside a barcode (FASTQS={a,b}: ParseBarcodedFastqs.cc:258-264)
+            a, b = split_text(gzip.open(wd + "/reads.fastq.gz", "rb").read())
+            sd = wd + "/split"
+            os.makedirs(sd)
+            for nm, t in (("a", a), ("b", b)):
+                with gzip.open(sd + "/" + nm + ".fastq.gz", "wb") as f:
+                    f.write(t)
+            refrun.parse_fastq_set(sd, [sd + "/a.fastq.gz", sd + "/b.fastq.gz"])
+            for f in ("reads.fastb", "reads.qualp", "reads.bci"):
+                with open(os.path.join(sd, f), "rb") as src, gzip.GzipFile(os.path.join(out, "split." + f + ".gz"), "wb", mtime=0) as dst:
+                    dst.write(src.read())
         kv = refrun.read_kvec(wd + "/kmers.kvec")
         np.save(out + "/kvec_sorted.npy", kv)
         shutil.rmtree(wd)

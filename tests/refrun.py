@@ -19,6 +19,12 @@ def parse_fastqs(workdir, fastq):
                           stdout=subprocess.DEVNULL)
 
 
+def parse_fastq_set(workdir, fastqs):
+    """FASTQS={a,b,...}: several barcode-sorted files in one call (ParseBarcodedFastqs.cc:258-264)."""
+    subprocess.check_call([os.path.join(REF, "ParseBarcodedFastqs"), "FASTQS={" + ",".join(fastqs) + "}",
+                           "OUT_HEAD=" + os.path.join(workdir, "reads")], cwd=workdir, stdout=subprocess.DEVNULL)
+
+
 def run_probe(workdir, paths=True, keep_kvec=True, extra=()):
     env = dict(os.environ)
     if keep_kvec:

@@ -136,3 +136,33 @@ def test_odd_text_matches_the_restatement(sb, tmp_path):
         ctx.load_fasth_text(text)
         ctx.save_read_files(str(tmp_path / "mine"))
     assert files(str(tmp_path / "mine")) == list(dfside.parse_fasth(text))
+
+
+def test_two_input_files(sb, tmp_path):
+    """sn_load_fasth_files = ParseBarcodedFastqs FASTQS={a,b}: golden files (the tiny set cut in two inside a barcode),
+    the python restatement, and the reference binary when it is on the box."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden import split_text
+    from oracle import dfside
+    wd = str(tmp_path)
+    _, text = fasth_text("tiny", wd)
+    a, b = split_text(text)
+    pa, pb_ = wd + "/a.fastq.gz", wd + "/b.fasth"
+    with gzip.open(pa, "wb") as f:
+        f.write(a)
+    with open(pb_, "wb") as f:                       # (the second one not compressed)
+        f.write(b)
+    with sb.Context(0) as ctx:
+        ctx.load_fasth_files([pa, pb_])
+        ctx.save_read_files(wd + "/mine")
+    mine = files(wd + "/mine")
+    g = os.path.join(HERE, "golden", "tiny")
+    assert mine == [gzip.open(g + "/split." + f + ".gz", "rb").read() for f in ("reads.fastb", "reads.qualp", "reads.bci")]
+    assert mine == list(dfside.parse_fasth([a, b]))
+    if refrun.have_ref():
+        pb2 = wd + "/b.fastq.gz"
+        with gzip.open(pb2, "wb") as f:
+            f.write(b)
+        refrun.parse_fastq_set(wd, [pa, pb2])
+        assert mine == files(wd + "/reads")

@@ -97,3 +97,21 @@ def test_ingest_restatement_matches_golden(name, tmp_path):
     fb, qp, bci = dfside.parse_fasth(gz(p))
     g = os.path.join(GOLD, name)
     assert fb == gz(g + "/reads.fastb.gz") and qp == gz(g + "/reads.qualp.gz") and bci == gz(g + "/reads.bci.gz")
+
+
+def test_two_file_ingest_restatement_matches_golden(tmp_path):
+    """FASTQS={a,b}: the barcode ordinal runs on across the files, the comparison string starts empty in each
+    (ParseBarcodedFastqs.cc:66-67,258-264) -- oracle/dfside.py against what the reference wrote for the tiny set cut in two."""
+    import sys
+    sys.path.insert(0, os.path.join(GOLD))
+    from make_golden import split_text
+    from oracle import dfside
+    from supernova_b200 import synth
+    codes, quals, off, bc, ids = datasets.get("tiny")
+    p = str(tmp_path / "x.fastq.gz")
+    synth.write_fasth_ragged(p, codes, quals, off, ids)
+    a, b = split_text(gz(p))
+    fb, qp, bci = dfside.parse_fasth([a, b])
+    g = os.path.join(GOLD, "tiny")
+    assert fb == gz(g + "/split.reads.fastb.gz") and qp == gz(g + "/split.reads.qualp.gz") and bci == gz(g + "/split.reads.bci.gz")
+    assert bci != gz(g + "/reads.bci.gz")                  # the cut really opens one more barcode
