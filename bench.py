@@ -15,7 +15,12 @@ Workload at N=1: BASELINE.json configs[1] ("C2"): 1.2 Gbp of synthetic 150 bp li
            inputs and D2H of its results inside the timed region.
 `cpu_baseline`: the reference's own buildReadQGraph48 (oracle/_ref, compiled from the
            reference sources) on a bounded sample of the same workload: the same generator
-           at 1/12 scale (5.25 Mbp genome, 100 Mbp of reads, same 19x coverage).
+           at 1/4 scale (15.75 Mbp genome, 300 Mbp of reads, same 19x coverage).
+`--impl reference`: the same binary on the FULL workload (same config as the GPU arm), with the
+           phase split from its own Date() stamps and the count-once figure.
+`parity_check`: before the timed region every run threads the "mid" set (112 Mbp), split over
+           the ranks, through the same code path and compares k-mer digest, a.hbv and
+           tmp.paths with the golden digests of the reference's run (tests/golden/).
 """
 import argparse
 import json
@@ -42,7 +47,7 @@ WORKLOADS = {
     "mid": (2_000_000, 373_333, 50_000, 20261017),
     "C1": (50_000, 10_000, 500, 1234),
 }
-SAMPLE_DIV = 12          # cpu_baseline sample = the workload's generator at 1/12 scale
+SAMPLE_DIV = 4           # cpu_baseline sample = the workload's generator at 1/4 scale (~10 s of the reference on 16 cores)
 ALG_BYTES_PER_BASE = 24.2  # algorithmic HBM bytes per input base, count+HBV (key-sort model)
 
 
@@ -98,51 +103,81 @@ def gen_workload(name, rank, scale_div=1):
     return b.ravel(), q.ravel(), off, bc, dict(G=G, pairs=pairs, n_bc=nbc, seed=seed, read_len=L, bc_ids=ids)
 
 
+def _prep_files(workload, div, wd):
+    """the reference's input files of a workload, written by a SUBPROCESS (tools/prep_workload.py): the process that
+    times the reference never maps libsupernova_b200.so"""
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "prep_workload.py"), workload, str(div), wd])
+    return json.loads(out.decode().strip().splitlines()[-1])
+
+
+REF_BUDGET_S = 240.0      # wall budget of the reference arm's timed steps (the whole run must end within minutes)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref/OracleProbe =
-    buildReadQGraph48 compiled from /root/reference) on a bounded sample, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/OracleProbe = the unmodified
+    buildReadQGraph48 compiled from /root/reference), all host threads, on THIS arm's config: the full workload
+    (C2: 1.2 Gbp), count + edges + HBV.  One step = one run of the reference binary (a fresh process: there is nothing
+    to warm up but the page cache, so at most one warm-up run is made); the timed steps stop when the wall budget is
+    spent and `steps` reports the steps really run."""
     if rank != 0:
         return
-    import supernova_b200 as sb
     import refrun
     if not refrun.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries are not built (run oracle/build_ref.sh where /root/reference exists)"}))
         return
-    codes, quals, off, bc, meta = gen_workload(args.workload, 0, SAMPLE_DIV)
-    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
-    gbp = codes.size / 1e9
     wd = tempfile.mkdtemp(prefix="sn_ref_")
-    sb.write_read_files(wd + "/reads", pb, boff, ln, pq, pqoff, bc)
-    secs = []
-    for i in range(args.warmup + args.steps):
-        s, _ = refrun.run_probe(wd, paths=False, keep_kvec=False)
-        if i >= args.warmup:
-            secs.append(s)
+    meta = _prep_files(args.workload, 1, wd)
+    gbp = meta["gbp"]
+    cores = refrun.host_threads()
+    secs, phases = [], []
+    s, log = refrun.run_probe(wd, paths=False, keep_kvec=False)            # warm-up (also sizes the budget)
+    n_warm = 1
+    budget_steps = max(1, int(REF_BUDGET_S // max(s, 1e-3)))
+    if args.warmup == 0 or s > REF_BUDGET_S / 2:                            # a run that long IS the measurement
+        secs.append(s); phases.append(refrun.phase_split(log, s)); n_warm = 0
+    while len(secs) < min(args.steps, budget_steps):
+        s, log = refrun.run_probe(wd, paths=False, keep_kvec=False)
+        secs.append(s); phases.append(refrun.phase_split(log, s))
     t = sum(secs)
     val = gbp * len(secs) / t
-    cores = os.cpu_count()
-    sample = f"same generator at 1/{SAMPLE_DIV} scale: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV (PATHS=False)"
+    ph = {k: sum(p.get(k, 0.0) for p in phases) / len(phases) for k in phases[0]}
+    once = ph.get("count_once_seconds")
+    sample = (f"full workload, same config as the GPU arm: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV (PATHS=False); "
+              f"{len(secs)} timed runs of {args.steps} requested (wall budget {REF_BUDGET_S:.0f} s), {n_warm} warm-up")
     line = {"metric": "Gbp reads/sec through k-mer count + DBG (HBV) build", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs), "higher_is_better": True, "scaling": "weak",
+            "steps": len(secs), "steps_requested": args.steps, "warmup": n_warm, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 * t / len(secs), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload + " (bounded sample)", "K": 48, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample},
+            "config": {"workload": f"{args.workload}: {meta['pairs']} pairs x 2 x {meta['read_len']} bp, {meta['G']} bp diploid genome, seed {meta['seed']}",
+                       "K": 48, "min_qual": 7, "min_freq": 3, "min_bc": 2, "gbp_per_gpu": gbp, "same_config_as_gpu_arm": True},
+            "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "omp_num_threads": cores, "phase_seconds": ph,
+                             "count_once": {"seconds": once, "value": (gbp / once) if once else None, "unit": "Gbp/s",
+                                            "what": "the reference runs its k-mer MapReduce twice (count-only, then fill: BuildReadQGraph48.cc:267-286); this is the run minus MapReduce #1"}},
             "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+    for root, _, files in os.walk(wd, topdown=False):
+        for f in files:
+            os.remove(os.path.join(root, f))
+        os.rmdir(root)
 
 
 def cpu_baseline(args):
-    import supernova_b200 as sb
+    """the reported CPU baseline of the GPU arm's line: the reference binary on a bounded sample (the same generator at
+    1/SAMPLE_DIV scale), ~10 s of CPU work; `bench.py --impl reference` times the full workload"""
     import refrun
+    if refrun.have_ref():
+        wd = tempfile.mkdtemp(prefix="sn_cpu_")
+        meta = _prep_files(args.workload, SAMPLE_DIV, wd)
+        gbp = meta["gbp"]
+        sample = f"same generator at 1/{SAMPLE_DIV} scale: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV"
+        secs, log = refrun.run_probe(wd, paths=False, keep_kvec=False)
+        ph = refrun.phase_split(log, secs)
+        return {"value": gbp / secs, "unit": "Gbp/s", "cores": refrun.host_threads(), "kind": "reference", "sample": sample, "seconds": secs,
+                "phase_seconds": ph, "count_once_value": (gbp / ph["count_once_seconds"]) if ph.get("count_once_seconds") else None}
     codes, quals, off, bc, meta = gen_workload(args.workload, 0, SAMPLE_DIV)
     gbp = codes.size / 1e9
     sample = f"same generator at 1/{SAMPLE_DIV} scale: {meta['G']} bp genome, {meta['pairs']} pairs, {gbp:.4f} Gbp, count+edges+HBV"
-    if refrun.have_ref():
-        pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
-        wd = tempfile.mkdtemp(prefix="sn_cpu_")
-        sb.write_read_files(wd + "/reads", pb, boff, ln, pq, pqoff, bc)
-        secs, _ = refrun.run_probe(wd, paths=False, keep_kvec=False)
-        return {"value": gbp / secs, "unit": "Gbp/s", "cores": os.cpu_count(), "kind": "reference", "sample": sample, "seconds": secs}
     from oracle.oracle import Oracle          # the one place bench may execute oracle/: the reported CPU baseline
     t0 = time.time()
     Oracle(codes, quals, off, bc).run(with_paths=False)
@@ -170,6 +205,55 @@ def cpu_ingest_baseline(args):
             "sample": f"ParseBarcodedFastqs (zcat + parse + PQVec encode + write) on {pairs // 48} pairs = {b.size / 1e9:.4f} Gbp"}
 
 
+def parity_check(sb, ctx, run_path, dist, rank, world):
+    """Driver-visible parity of the very code path that is timed next: the "mid" set (112 Mbp; the reference's own
+    buildReadQGraph48 run on it is committed as digests in tests/golden/scale_digests.json) is split over the ranks
+    (rank r takes the r-th slice of the reads), threaded through run_path(with_paths=True), and compared:
+      * k-mer table: order-independent digest of {k-mer, count, ctx} against kmers.kvec -- on every rank
+      * a.hbv: md5 of the file every rank writes
+      * tmp.paths: the ranks' ReadPaths, concatenated in rank order on rank 0, as the feudal file
+    -> "ok" or a list of what differs."""
+    import digests
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "scale_digests.json")))["mid"]
+    codes, quals, off, bc, meta = gen_workload("mid", 0)
+    L = meta["read_len"]
+    n = len(off) - 1
+    lo = (n * rank // world) & ~1
+    hi = n if rank == world - 1 else (n * (rank + 1) // world) & ~1
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes[lo * L:hi * L], quals[lo * L:hi * L], off[lo:hi + 1] - off[lo])
+    ctx.load_reads(pb, boff, ln, pq, pqoff, np.ascontiguousarray(bc[lo:hi], np.int32))
+    run_path(True)
+    bad = []
+    km = ctx.kmers()
+    if digests.kmer_digest(km[:, 0], km[:, 1], km[:, 2], km[:, 3]) != gold["kmers"]:
+        bad.append(f"rank {rank}: k-mer table")
+    wd = tempfile.mkdtemp(prefix="sn_chk_")
+    ctx.write_hbv(wd + "/a.hbv")
+    if digests.file_md5(wd + "/a.hbv") != gold["a.hbv"]:
+        bad.append(f"rank {rank}: a.hbv")
+    os.remove(wd + "/a.hbv"); os.rmdir(wd)
+    po, poff, pe = ctx.paths()
+    parts = [(po, poff, pe)]
+    if dist is not None:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((po, poff, pe), gathered, dst=0)
+        parts = gathered
+    if rank == 0:
+        import hashlib
+        offs = np.concatenate([p[0] for p in parts])
+        plen = np.concatenate([np.diff(p[1].astype(np.int64)) for p in parts])
+        edges = np.concatenate([p[2] for p in parts])
+        poff_all = np.concatenate([[0], np.cumsum(plen)])
+        if hashlib.md5(digests.paths_file_bytes(offs, poff_all, edges)).hexdigest() != gold["tmp.paths"]:
+            bad.append("tmp.paths (ranks concatenated)")
+    if dist is not None:
+        allbad = [None] * world
+        dist.all_gather_object(allbad, bad)
+        bad = [x for b in allbad for x in b]
+    return {"verdict": "ok" if not bad else "FAILED: " + "; ".join(bad), "set": "mid: 373333 pairs, 2 Mbp genome, split over %d rank(s)" % world,
+            "against": "tests/golden/scale_digests.json (reference binary run)", "n_kmers": int(gold["n_kmers"])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +264,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paths", action="store_true", help="skip the extra ReadPath-inclusive measurement")
     ap.add_argument("--no-ingest", action="store_true", help="skip the extra device-ingest (FASTQ text -> reads) measurement")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity check leg (mid set against the reference's golden digests)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +349,7 @@ def main():
             ms = float(t.item())
         return ms, ctx.kernel_launches() - l0, {k: v / steps for k, v in stage.items()}
 
+    parity = None if args.no_check else parity_check(sb, ctx, run_path, dist, rank, world)
     ctx.load_reads_ptr(n_reads, *ptrs)
     sampler = ClockSampler(local_rank)          # nvidia-smi every 0.2 s from the warm-up to the end of the e2e leg (all under load)
     sampler.start()
@@ -337,6 +423,9 @@ def main():
                        "l2": "inputs per step (%.2f GB of packed reads, %.2f GB of super-k-mer records) are larger than L2" % (h2d_bytes / 1e9, 32 * counts["n_superkmers"] / 1e9)},
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}
+    if parity is not None:
+        line["parity_check"] = parity["verdict"]
+        line["parity_detail"] = parity
     if paths_extra:
         line["with_readpaths"] = paths_extra
     if ingest:

@@ -99,6 +99,9 @@ int sn_load_fasth_files(sn_ctx* ctx, const char* const* paths, uint32_t n_files)
 int sn_save_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 /* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */
 int sn_load_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
+/* the same with the per-read barcode ordinals already in memory (the vec<int32_t> buildReadQGraph48's caller
+ * passes as bcp, 10X/runstages/RunStages.cc:405); bc may be NULL (n_bc ignored)            */
+int sn_load_read_files_bc(sn_ctx* ctx, const char* fastb, const char* qualp, const int32_t* bc, uint64_t n_bc);
 
 /* ---- stages (must run in this order) -------------------------------------------------- */
 /* createDict up to the KmerVec (BuildReadQGraph48.cc:218-292): good lengths, k-mer records,
@@ -117,6 +120,13 @@ int sn_path_reads(sn_ctx* ctx);
 int sn_build_paths_index(sn_ctx* ctx);
 int sn_get_paths_index(sn_ctx* ctx, uint64_t* off /* n_hbv_edges+1 */, uint64_t* read_ids /* n_path_edges */, int32_t* countsb /* n_hbv_edges */);
 int sn_write_paths_index(sn_ctx* ctx, const char* paths_inv /* a.paths.inv */, const char* countsb /* a.countsb */);
+
+/* buildGraphFromMSP (paths/long/BuildReadQGraph48.h:24-26, .cc:1631-1684), the production boundary when the
+ * edges come from the tada stages (MSPEDGES = _ASM_SN.asm_graph, mro/_assembler.mro:57): the vec<basevector>
+ * file becomes the edge set (any orientation, any order), the HyperBasevector is built from it
+ * (mspEdgesToHBV) and every edge k-mer enters the dictionary with its (edge, offset) (:1656-1664; a k-mer that
+ * occurs twice keeps the last).  With reads loaded, sn_path_reads + sn_write_paths then do :1680.          */
+int sn_build_graph_from_edges(sn_ctx* ctx, const char* edges_bv);
 
 /* ---- results ------------------------------------------------------------------------- */
 int sn_get_counts(const sn_ctx* ctx, sn_counts* out);

@@ -10,7 +10,12 @@
 // oracle/_ref/ (git-ignored).
 //
 // Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [INDEX=False|True] [MIN_QUAL=7]
-//                    [MIN_FREQ=3] [MIN_BC=2]
+//                    [MIN_FREQ=3] [MIN_BC=2] [IGN_BC_BELOW=0] [MSPEDGES=<edges.bv>]
+//   MSPEDGES given: the reference's buildGraphFromMSP (BuildReadQGraph48.cc:1631-1684) instead -- the
+//   production path, where the edges come from the tada stages -- on HEAD.fastb/.qualp and that edge file.
+// The same source is linked twice by oracle/build_ref.sh: against the reference's BuildReadQGraph48.o
+// (OracleProbe) and against integration/BuildReadQGraph48_b200.cc + libsupernova_b200.so (OracleProbe_b200,
+// the drop-in test: same main, same reference closure, only that one translation unit replaced).
 //   OUT/reads.fastb must exist (re-opened at BuildReadQGraph48.cc:1763).
 // Outputs: OUT/a.hbv, OUT/tmp.paths (PATHS=True), OUT/kmers.kvec (when env
 //   SN_KEEP_KVEC is set; needs the optional guard patch), OUT/stats/*.json,
@@ -42,6 +47,8 @@ int main(int argc, char** argv)
     CommandArgument_Int_OrDefault(MIN_FREQ, 3);
     CommandArgument_Int_OrDefault(MIN_BC, 2);
     CommandArgument_Bool_OrDefault(INDEX, False);
+    CommandArgument_Int_OrDefault(IGN_BC_BELOW, 0);
+    CommandArgument_String_OrDefault(MSPEDGES, "");
     EndCommandArguments;
 
     vecbvec reads(HEAD + ".fastb");
@@ -55,9 +62,12 @@ int main(int argc, char** argv)
     HyperBasevector hbv;
     ReadPathVec paths;
     auto t0 = std::chrono::steady_clock::now();
-    buildReadQGraph48(OUT, "/reads", "", reads, quals, False, False,
-                      MIN_QUAL, MIN_FREQ, 0, MIN_BC, &bc, .75, 0, "",
-                      True, False, &hbv, PATHS ? &paths : nullptr, 0.9, False);
+    if (MSPEDGES != "")
+        buildGraphFromMSP(OUT, HEAD + ".fastb", HEAD + ".qualp", MSPEDGES, hbv, 48, paths);
+    else
+        buildReadQGraph48(OUT, "/reads", "", reads, quals, False, False,
+                          MIN_QUAL, MIN_FREQ, IGN_BC_BELOW, MIN_BC, &bc, .75, 0, "",
+                          True, False, &hbv, PATHS ? &paths : nullptr, 0.9, False);
     auto t1 = std::chrono::steady_clock::now();
     BinaryWriter::writeFile(OUT + "/a.hbv", hbv);
     if (INDEX && PATHS) {

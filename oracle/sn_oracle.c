@@ -946,6 +946,8 @@ sn_oracle_t* sn_oracle_new(uint64_t n_reads, const uint8_t* bases, const uint8_t
     o->min_qual = min_qual; o->min_freq = min_freq; o->min_bc = min_bc; o->ign_bc_below = 0;
     return o;
 }
+/* ignBcBelow of buildReadQGraph48 (BuildReadQGraph48.cc:158-159): reads with id below it count as barcode -1 */
+void sn_oracle_set_ign_bc_below(sn_oracle_t* o, int64_t v) { o->ign_bc_below = v; }
 int sn_oracle_run(sn_oracle_t* o, int with_paths)
 {
     sn_oracle_count(o); sn_oracle_prune(o); sn_oracle_edges(o); sn_oracle_hbv(o);

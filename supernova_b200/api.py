@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
+STAGES = ("edge_dict", "ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
 
 
 class SnError(RuntimeError):
@@ -55,6 +55,8 @@ def lib():
         L.sn_save_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_load_reads_streamed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.sn_load_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.sn_load_read_files_bc.argtypes = [vp, C.c_char_p, C.c_char_p, vp, u64]
+        L.sn_build_graph_from_edges.argtypes = [vp, C.c_char_p]
         L.sn_count_kmers.argtypes = [vp, C.POINTER(Params)]
         for f in ("sn_build_edges", "sn_build_hbv", "sn_path_reads"):
             getattr(L, f).argtypes = [vp]
@@ -228,6 +230,15 @@ class Context:
 
     def load_read_files(self, head):
         self._ck(self.L.sn_load_read_files(self.h, (head + ".fastb").encode(), (head + ".qualp").encode(), (head + ".bci").encode()))
+
+    def load_read_files_bc(self, head, bc):
+        """reads.fastb / reads.qualp + the per-read barcode ordinals held in memory (or None)"""
+        b = None if bc is None else np.ascontiguousarray(bc, np.int32)
+        self._ck(self.L.sn_load_read_files_bc(self.h, (head + ".fastb").encode(), (head + ".qualp").encode(), _p(b), 0 if b is None else len(b)))
+
+    def build_graph_from_edges(self, bv_path):
+        """buildGraphFromMSP up to its pathReads call: edge file -> HBV + dictionary of the edge k-mers"""
+        self._ck(self.L.sn_build_graph_from_edges(self.h, bv_path.encode()))
 
     # ---- stages ---------------------------------------------------------------------
     def count_kmers(self, params=None):

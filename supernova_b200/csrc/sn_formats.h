@@ -31,7 +31,7 @@ void pqvec_encode(const uint8_t* q, uint32_t n, std::vector<uint8_t>& out);
 // decoder (feudal/PQVec.cc:129-187); returns the number of quals written
 uint32_t pqvec_decode(const uint8_t* p, const uint8_t* pend, uint8_t* out, uint32_t cap);
 // expand a .bci barcode index to the per-read ordinal DF passes down (10X/DF.cc:464-469)
-void expand_bci(const std::vector<int64_t>& bci, std::vector<int32_t>& bc);
+bool expand_bci(const std::vector<int64_t>& bci, std::vector<int32_t>& bc);   // false: the index is not sorted / does not start at 0
 
 // vec<basevector> (BINWRITE; feudal/BinaryStream.h:486-493, feudal/FieldVec.h:596-598)
 bool write_bv(const std::string& path, const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n, std::string& err);

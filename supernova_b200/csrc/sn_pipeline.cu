@@ -8,6 +8,7 @@
 #include "sn_msp.cuh"
 #include "sn_ingest.cuh"
 #include "sn_hbvdev.cuh"
+#include "sn_edict.cuh"
 #include "sn_formats.h"
 #include "sn_hbv.h"
 
@@ -91,6 +92,7 @@ struct sn_ctx {
     sn_params params{7, 3, 2, 0};
     sn_counts cnt{};
     int stage = 0;       // 0 none, 1 reads, 2 counted, 3 edges, 4 hbv, 5 paths
+    bool reads_ok = false;   // reads are resident (a graph can also come from an edge file without any)
 
     // reads
     DevBuf bases, boff, len, quals, qoff, bc, pq, pqoff, goodlen;
@@ -177,7 +179,7 @@ int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_
 {
     if (!n_reads || !bases || !base_off || !len) return fail(c, SN_ERR_ARG, "sn_load_reads: empty or NULL input");
     if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
-    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->cnt = sn_counts{}; c->stage = 0; c->reads_ok = false; c->paths_on_host = false;
     c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     c->cnt.n_reads = n_reads;
     t_begin(c, "h2d");
@@ -216,7 +218,7 @@ int finish_load(sn_ctx* c)
     if (max_len > SN_MAX_READ_LEN) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
     // barcode ordinals travel in 24 bits of a super-k-mer record (0xFFFFFF is reserved for "-1")
     if (max_bc >= 0xFFFFFF) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
-    c->stage = 1;
+    c->stage = 1; c->reads_ok = true;
     return SN_OK;
 }
 
@@ -332,7 +334,7 @@ static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const 
 {
     if (!c || (!text && n_bytes)) return SN_ERR_ARG;
     CU(cudaSetDevice(c->device));
-    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->cnt = sn_counts{}; c->stage = 0; c->reads_ok = false; c->paths_on_host = false;
     c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     if (!n_bytes) return fail(c, SN_ERR_ARG, "sn_load_fasth_text: empty input");
     if (text[n_bytes - 1] != '\n') return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (the text does not end with a newline)");
@@ -461,10 +463,21 @@ int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
     if (fb.len.size() + 1 != qp.off.size()) return fail(c, SN_ERR_DATA, "fastb and qualp hold different numbers of reads");
     if (bci) {
         if (!snf::read_bci(bci, bi, err)) return fail(c, SN_ERR_IO, err);
-        snf::expand_bci(bi, bc);
+        if (!snf::expand_bci(bi, bc)) return fail(c, SN_ERR_DATA, std::string(bci) + ": barcode index is not sorted");
         if (bc.size() != fb.len.size()) return fail(c, SN_ERR_DATA, "bci.back() != number of reads");
     }
     return sn_load_reads(c, fb.len.size(), fb.var.data(), fb.off.data(), fb.len.data(), qp.var.data(), qp.off.data(), bci ? bc.data() : nullptr);
+}
+// the same with the per-read barcode ordinals the caller already holds in memory (the vec<int32_t> bc of
+// buildReadQGraph48's caller, 10X/DF.cc:464-469); bc may be NULL
+int sn_load_read_files_bc(sn_ctx* c, const char* fastb, const char* qualp, const int32_t* bc, uint64_t n_bc)
+{
+    if (!c || !fastb || !qualp) return SN_ERR_ARG;
+    snf::Fastb fb; snf::Qualp qp; std::string err;
+    if (!snf::read_fastb(fastb, fb, err) || !snf::read_qualp(qualp, qp, err)) return fail(c, SN_ERR_IO, err);
+    if (fb.len.size() + 1 != qp.off.size()) return fail(c, SN_ERR_DATA, "fastb and qualp hold different numbers of reads");
+    if (bc && n_bc != fb.len.size()) return fail(c, SN_ERR_DATA, "the barcode array and the fastb hold different numbers of reads");
+    return sn_load_reads(c, fb.len.size(), fb.var.data(), fb.off.data(), fb.len.data(), qp.var.data(), qp.off.data(), bc);
 }
 
 // ---------------------------------------------------------------------------
@@ -697,7 +710,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
     int r;
     if ((r = count_set_params(c, p))) return r;
-    c->cnt = sn_counts{}; c->stage = 0; c->paths_on_host = false;
+    c->cnt = sn_counts{}; c->stage = 0; c->reads_ok = false; c->paths_on_host = false;
     c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     c->cnt.n_reads = n_reads;
     const uint64_t n = n_reads;
@@ -786,7 +799,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     c->gl_ready = true; c->gl_min_qual = c->params.min_qual; c->gl_occ = h_occ;
     c->hist_ready_bits = (with_hist && h_occ) ? bits : -1;
     c->dsc_ready = with_hist && h_occ; c->dsc_overflow = h_ovf;
-    c->stage = 1;
+    c->stage = 1; c->reads_ok = true;
     return SN_OK;
 }
 
@@ -1291,10 +1304,99 @@ int sn_build_hbv(sn_ctx* c)
 }
 
 // ---------------------------------------------------------------------------
+// buildGraphFromMSP (paths/long/BuildReadQGraph48.h:24-26, .cc:1631-1684) up to its pathReads call: the edges of
+// an MSPEDGES file (vec<basevector>: tada's asm_graph, or sn_write_edges_bv) become the context's edge set,
+// the HyperBasevector is built from them (mspEdgesToHBV = buildHBVFromEdges) and every edge k-mer enters the
+// dictionary with its (edge, offset) (:1656-1664).  sn_path_reads / sn_write_paths / sn_write_hbv follow as usual.
+static int graph_from_edges(sn_ctx* c, const snf::Fastb& E)
+{
+    CU(cudaSetDevice(c->device));
+    const uint64_t nE = E.len.size();
+    if (nE >= (1ull << 29)) return fail(c, SN_ERR_ARG, "more than 2^29 unipath edges");
+    uint64_t n_bases = 0, n_k64 = 0;
+    for (uint32_t l : E.len) { n_bases += l; n_k64 += l >= SN_K ? l - (SN_K - 1) : 0; }
+    if (n_k64 >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
+    const uint32_t n_k = (uint32_t)n_k64;
+    // the edge set, on the device and on the host (what sn_build_edges leaves behind)
+    const uint64_t total_bytes = E.off[nE];
+    CU(c->ebases.alloc(total_bytes + 64)); CU(c->eoff.alloc(8 * (nE + 1))); CU(c->elen.alloc(4 * nE + 16));
+    CU(cudaMemsetAsync((char*)c->ebases.p + total_bytes, 0, 64, c->st));
+    if (total_bytes) CU(cudaMemcpyAsync(c->ebases.p, E.var.data(), total_bytes, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->eoff.p, E.off.data(), 8 * (nE + 1), cudaMemcpyHostToDevice, c->st));
+    if (nE) CU(cudaMemcpyAsync(c->elen.p, E.len.data(), 4 * nE, cudaMemcpyHostToDevice, c->st));
+    resize_pinned(c, c->hedges.len, nE); resize_pinned(c, c->hedges.off, nE + 1); resize_pinned(c, c->hedges.packed, total_bytes + 16);
+    if (nE) memcpy(c->hedges.len.data(), E.len.data(), 4 * nE);
+    memcpy(c->hedges.off.data(), E.off.data(), 8 * (nE + 1));
+    if (total_bytes) memcpy(c->hedges.packed.data(), E.var.data(), total_bytes);
+    memset(c->hedges.packed.data() + total_bytes, 0, 16);
+    c->cnt.n_edges = nE; c->cnt.n_edge_bases = n_bases;
+    c->cnt.n_kmer_occurrences = 0; c->cnt.n_kmers_distinct = 0; c->cnt.n_superkmers = 0;
+    // ---- dictionary of the edge k-mers ----
+    t_begin(c, "edge_dict");
+    uint32_t* err = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8) + 11;
+    DevBuf &nk = c->pool["ed_nk"], &koff = c->pool["ed_koff"], &ra = c->pool["ed_a"], &rb = c->pool["ed_b"], &tmp = c->pool["rs_tmp"], &flag = c->pool["ed_flag"],
+           &pos = c->pool["ed_pos"], &gids = c->pool["ed_gids"], &bcnt = c->pool["ed_bcnt"], &surv = c->pool["surv_a"], &loc = c->pool["ed_loc"];
+    CU(nk.alloc(4 * nE + 16)); CU(koff.alloc(8 * (nE + 1)));
+    CU(cudaMemsetAsync(err, 0, 4, c->st));
+    if (nE) { k_ed_nk<<<blocks_for(nE, 256), 256, 0, c->st>>>(c->elen.as<uint32_t>(), (uint32_t)nE, nk.as<uint32_t>(), err); KCHECK("k_ed_nk"); }
+    uint64_t tot = 0;
+    int r = scan_u32(c, nk.as<uint32_t>(), nE, koff.as<uint64_t>(), &tot);
+    if (r) return r;
+    uint32_t h_err = 0;
+    CU(cudaMemcpy(&h_err, err, 4, cudaMemcpyDeviceToHost));
+    if (h_err) return fail(c, SN_ERR_DATA, "an edge is shorter than K = 48 bases");
+    uint64_t n_unique = 0;
+    int bits = 4;
+    if (n_k) {
+        CU(ra.alloc(16ull * n_k)); CU(rb.alloc(16ull * n_k)); CU(tmp.alloc(radix_sort_tmp_bytes(n_k))); CU(flag.alloc(4ull * n_k)); CU(pos.alloc(8ull * (n_k + 1)));
+        k_ed_records<<<blocks_for(n_k, 256), 256, 0, c->st>>>(c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(), koff.as<uint64_t>(), (uint32_t)nE, n_k, ra.as<uint4>());
+        KCHECK("k_ed_records");
+        cudaError_t e = radix_sort<RS_KEY96>(ra.as<uint4>(), rb.as<uint4>(), n_k, tmp.p, c->num_sms, c->st);
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("edge dictionary sort: ") + cudaGetErrorString(e));
+        c->launches += 2 + RsMode<RS_KEY96>::PASSES;
+        k_ed_last_of_run<<<blocks_for(n_k, 256), 256, 0, c->st>>>(ra.as<uint4>(), n_k, flag.as<uint32_t>());
+        KCHECK("k_ed_last_of_run");
+        if ((r = scan_u32(c, flag.as<uint32_t>(), n_k, pos.as<uint64_t>(), &n_unique))) return r;
+        while (bits < 24 && (n_unique >> bits) > 128) ++bits;           // ~128 entries per bucket, as the count path leaves them
+        CU(gids.alloc(4 * n_unique + 16)); CU(bcnt.alloc(4ull << bits)); CU(surv.alloc(16 * n_unique + 16)); CU(loc.alloc(8 * n_unique + 16));
+        CU(cudaMemsetAsync(bcnt.p, 0, 4ull << bits, c->st));
+        k_ed_bucket_keys<<<blocks_for(n_k, 256), 256, 0, c->st>>>(ra.as<uint4>(), flag.as<uint32_t>(), pos.as<uint64_t>(), n_k, bits, rb.as<uint4>(), gids.as<uint32_t>(), bcnt.as<uint32_t>());
+        KCHECK("k_ed_bucket_keys");
+        e = radix_sort<RS_KEY96>(rb.as<uint4>(), ra.as<uint4>(), (uint32_t)n_unique, tmp.p, c->num_sms, c->st);
+        if (e != cudaSuccess) return fail(c, SN_ERR_CUDA, std::string("edge dictionary sort: ") + cudaGetErrorString(e));
+        c->launches += 2 + RsMode<RS_KEY96>::PASSES;
+        k_ed_emit<<<blocks_for(n_unique, 256), 256, 0, c->st>>>(rb.as<uint4>(), gids.as<uint32_t>(), (uint32_t)n_unique, c->ebases.as<uint8_t>(), c->eoff.as<uint64_t>(),
+            koff.as<uint64_t>(), (uint32_t)nE, surv.as<uint4>(), loc.as<uint2>());
+        KCHECK("k_ed_emit");
+    } else { CU(bcnt.alloc(4ull << bits)); CU(cudaMemsetAsync(bcnt.p, 0, 4ull << bits, c->st)); CU(surv.alloc(64)); }
+    t_begin(c, "make_dict");
+    if ((r = msp_install_dict(c, surv.as<uint4>(), n_unique, bits, bcnt.as<uint32_t>(), false))) return r;
+    if (n_unique) {
+        k_ed_set_loc<<<blocks_for(n_unique, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), loc.as<uint2>(), (uint32_t)n_unique);
+        KCHECK("k_ed_set_loc");
+    }
+    t_end(c, "edge_dict");
+    CU(cudaStreamSynchronize(c->st));
+    c->stage = 3;
+    return sn_build_hbv(c);
+}
+int sn_build_graph_from_edges(sn_ctx* c, const char* bv_path)
+{
+    if (!c || !bv_path) return SN_ERR_ARG;
+    snf::Fastb E; std::string err;
+    if (!snf::read_bv(bv_path, E, err)) return fail(c, SN_ERR_IO, err);
+    const uint64_t keep_reads = c->cnt.n_reads, keep_bases = c->cnt.n_bases;       // the reads (if loaded) stay for sn_path_reads
+    int r = graph_from_edges(c, E);
+    c->cnt.n_reads = keep_reads; c->cnt.n_bases = keep_bases;
+    return r;
+}
+
+// ---------------------------------------------------------------------------
 int sn_path_reads(sn_ctx* c)
 {
     if (!c) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "sn_path_reads: run sn_build_hbv first");
+    if (!c->reads_ok) return fail(c, SN_ERR_STATE, "sn_path_reads: no reads loaded");
     CU(cudaSetDevice(c->device));
     const uint64_t n = c->cnt.n_reads;
     DictView d; d.tab = c->dict.as<DictEntry>(); d.boff = c->dict_sub_bits ? c->pool["dict_cells"].as<uint32_t>() : c->dboff.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits; d.sub_bits = c->dict_sub_bits;

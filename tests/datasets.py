@@ -18,6 +18,22 @@ def get(name):
     if name == "nobc":               # all reads unbarcoded: nothing passes the barcode rule
         b, q, off, bc, ids = synth.make_stress(9, n_pairs=500)
         return b, q, off, np.zeros_like(bc), ids
+    if name == "onebc":              # every barcoded read carries the same barcode: only ignBcBelow lets a k-mer pass min_bc = 2
+        return synth.make_stress(5, n_pairs=3000, n_bc=1)
+    if name == "fewbc":              # three barcodes: many k-mers are seen under one barcode only
+        return synth.make_stress(6, n_pairs=3000, n_bc=3)
+    if name == "polyA":
+        # one k-mer (A^48) with more than 2^24 occurrences: 84,000 pairs of 150 x A give 17.3 M of them --
+        # the count saturates at 16,777,215 (kmers/ReadPather.h:128-129,145) -- on top of a stress set, with
+        # four barcodes on the homopolymer reads.  Every poly-A super-k-mer lands in ONE minimizer bucket.
+        b, q, off, bc, ids = synth.make_stress(11, n_pairs=1500, n_bc=20)
+        n_a, L = 2 * 84_000, 150
+        b = np.concatenate([b, np.zeros(n_a * L, np.uint8)])
+        q = np.concatenate([q, np.full(n_a * L, 37, np.uint8)])
+        off = np.concatenate([off, off[-1] + np.arange(1, n_a + 1, dtype=np.uint64) * L])
+        top = int(bc.max())
+        bc = np.concatenate([bc, (top + 1 + (np.arange(n_a) // (n_a // 4)).clip(0, 3)).astype(np.int32)])
+        return b, q, off, bc, None
     G, pairs, nbc, seed = synth.CONFIGS[name]
     b, q, bc, ids = synth.make_reads(G, pairs, nbc, seed)
     n, L = b.shape

@@ -1,0 +1,121 @@
+"""-m gpu: the parameters and limits of Kmerizer::reduce the default sets do not reach
+(BuildReadQGraph48.cc:91-137,155-181; kmers/ReadPather.h:128-145): ignBcBelow > 0, thresholds other than the
+pipeline's, the 24-bit count saturation, and the MSPEDGES file writer.  CUDA path through the C ABI against the C
+oracle and against the reference's own binary.  Bar: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import datasets
+import refrun
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb(built):
+    import supernova_b200
+    return supernova_b200
+
+
+def _run(sb, name, wd, **prm):
+    from oracle.oracle import Oracle
+    codes, quals, off, bc, _ = datasets.get(name)
+    o = Oracle(codes, quals, off, bc, **prm).run()
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    ctx = sb.Context(0)
+    ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+    ctx.build_read_qgraph48(wd, sb.Params(**prm), with_paths=True)
+    return ctx, o, (pb, boff, ln, pq, pqoff, bc)
+
+
+def _check(sb, ctx, o, wd, packed, extra):
+    km, ok = ctx.kmers(), o.kmers()
+    assert km.shape[0] == ok.shape[0]
+    assert np.array_equal(km[:, :3], ok[:, :3])
+    assert np.array_equal(km[:, 3], ok[:, 3] | (ok[:, 4] << 24))
+    o.write_hbv(wd + "/oracle.hbv"); o.write_paths(wd + "/oracle.paths")
+    assert open(wd + "/a.hbv", "rb").read() == open(wd + "/oracle.hbv", "rb").read()
+    assert open(wd + "/tmp.paths", "rb").read() == open(wd + "/oracle.paths", "rb").read()
+    if refrun.have_ref():
+        rd = wd + "/ref"
+        os.makedirs(rd)
+        sb.write_read_files(rd + "/reads", *packed)
+        refrun.run_probe(rd, extra=extra)
+        ref = refrun.read_kvec(rd + "/kmers.kvec")
+        mine = np.stack([km[:, 0], km[:, 1], km[:, 2], km[:, 3] & 0xFFFFFF, km[:, 3] >> 24], axis=1)
+        assert np.array_equal(mine, ref)
+        for f in ("a.hbv", "tmp.paths", "stats/histogram_kmer_count.json"):
+            assert open(wd + "/" + f, "rb").read() == open(rd + "/" + f, "rb").read(), f
+
+
+@pytest.mark.parametrize("name,ign", [("onebc", 1), ("onebc", 2500), ("fewbc", 3001), ("fewbc", 6000), ("C1", 9000), ("nobc", 300)])
+def test_ign_bc_below(sb, name, ign, tmp_path):
+    """reads with id < ignBcBelow count as barcode -1: a k-mer they touch passes the barcode rule whatever its barcodes
+    (BuildReadQGraph48.cc:110-112,158-159,176-178)"""
+    wd = str(tmp_path)
+    ctx, o, packed = _run(sb, name, wd, ign_bc_below=ign)
+    try:
+        _check(sb, ctx, o, wd, packed, ("IGN_BC_BELOW=%d" % ign,))
+        # the parameter changes the result (the sets hold k-mers seen under a single barcode)
+        with sb.Context(0) as c0:
+            c0.load_reads(*packed)
+            c0.count_kmers(sb.Params())
+            assert c0.counts()["n_kmers"] <= ctx.counts()["n_kmers"]
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("prm", [dict(min_qual=10, min_freq=2, min_bc=1), dict(min_qual=2, min_freq=5, min_bc=0), dict(min_qual=20, min_freq=1, min_bc=2)])
+def test_other_thresholds_against_reference(sb, prm, tmp_path):
+    wd = str(tmp_path)
+    ctx, o, packed = _run(sb, "stress3", wd, **prm)
+    try:
+        _check(sb, ctx, o, wd, packed, ("MIN_QUAL=%d" % prm["min_qual"], "MIN_FREQ=%d" % prm["min_freq"], "MIN_BC=%d" % prm["min_bc"]))
+    finally:
+        ctx.close()
+
+
+def test_count_saturates_at_24_bits(sb, tmp_path):
+    """A^48 occurs 17.3 M times: KDef::setCount clips at 2^24 - 1 (kmers/ReadPather.h:128-129,145).  All of it sits in
+    one minimizer bucket (one CTA of k_bucket_count2), whose records are nearly all copies of three super-k-mers."""
+    wd = str(tmp_path)
+    ctx, o, packed = _run(sb, "polyA", wd)
+    try:
+        km = ctx.kmers()
+        assert km[0, 0] == 0 and km[0, 1] == 0 and km[0, 2] == 0            # A^48 sorts first
+        assert (km[0, 3] & 0xFFFFFF) == 0xFFFFFF
+        assert ctx.counts()["n_kmer_occurrences"] > (1 << 24)
+        _check(sb, ctx, o, wd, packed, ())
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress2", "C1"])
+def test_write_edges_bv_round_trip(sb, name, tmp_path):
+    """sn_write_edges_bv writes the vec<basevector> MSPEDGES file (feudal/BinaryStream.h:486-493, feudal/FieldVec.h:596-598,762;
+    tada's writer: debruijn.rs:895-929): parsed back, it holds the device edge set; the edge set equals the oracle's."""
+    from oracle.oracle import Oracle
+    codes, quals, off, bc, _ = datasets.get(name)
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    p = str(tmp_path / "edges.bv")
+    with sb.Context(0) as ctx:
+        ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ctx.count_kmers(sb.Params()); ctx.build_edges()
+        ctx.write_edges_bv(p)
+        eln, eoff, packed = ctx.edges()
+    d = open(p, "rb").read()
+    assert d[:8] == b"BINWRITE"
+    n = int(np.frombuffer(d, "<u8", 1, 8)[0])
+    assert n == len(eln)
+    at, got = 16, []
+    for e in range(n):
+        l = int(np.frombuffer(d, "<u4", 1, at)[0]); at += 4
+        nb = (l + 3) // 4
+        b = np.frombuffer(d, np.uint8, nb, at); at += nb
+        got.append(np.stack([(b >> (2 * j)) & 3 for j in range(4)], axis=1).ravel()[:l].astype(np.uint8).tobytes())
+    assert at == len(d)
+    assert got == datasets.unpack_edges(eln, eoff, packed)
+    o = Oracle(codes, quals, off, bc).run(with_paths=False)
+    assert sorted(got) == sorted(o.edges())

@@ -4,21 +4,43 @@
   the reference's own buildReadQGraph48 binary (oracle/_ref) on the same fastb/qualp/bci --
   k-mer table, a.hbv bytes, tmp.paths bytes, k-mer spectrum.  Falls back to the C oracle when the
   reference binary did not travel.
-* C2 (1.2 Gbp, BASELINE.json configs[1]): too big for the oracle in test time, so the
-  size-independent properties the domain offers: sorted distinct canonical k-mers above the
+* C2 (1.2 Gbp, BASELINE.json configs[1]) and C2b (the same genome at 56x, 3.53 Gbp): EXACT parity against the
+  reference's own buildReadQGraph48 through committed golden digests (tests/golden/scale_digests.json, written by
+  tests/golden/make_scale_digests.py from a run of oracle/_ref/OracleProbe on the same seeded reads): the
+  order-independent digest of the {k-mer, count, ctx} table against kmers.kvec, md5 of a.hbv, of tmp.paths and
+  of the k-mer spectrum; the inputs' md5 first, so a generator drift cannot pass for a parity failure.
+* C2 also through the size-independent properties the domain offers: sorted distinct canonical k-mers above the
   thresholds, every valid k-mer in exactly one unipath, edge/HBV bookkeeping, involution,
   graph-consistent ReadPaths, and idempotence (a second run gives the same bytes).
 Bar: bit-exact."""
+import json
 import os
 
 import numpy as np
 import pytest
 
 import datasets
+import digests
 import refrun
 
 pytestmark = pytest.mark.gpu
 K = 48
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_digests.json")))
+
+
+def against_golden(sb, ctx, name, wd, packed, bc):
+    g = GOLD[name]
+    sb.write_read_files(wd + "/reads", *packed, bc)
+    for f in ("fastb", "qualp", "bci"):                      # same inputs as the reference run that made the digests
+        assert digests.file_md5(wd + "/reads." + f) == g["inputs"][f], "generator drift: reads." + f
+        os.remove(wd + "/reads." + f)
+    km = ctx.kmers()
+    assert km.shape[0] == g["n_kmers"]
+    assert digests.kmer_digest(km[:, 0], km[:, 1], km[:, 2], km[:, 3]) == g["kmers"]
+    del km
+    assert os.path.getsize(wd + "/a.hbv") == g["a.hbv_bytes"] and digests.file_md5(wd + "/a.hbv") == g["a.hbv"]
+    assert os.path.getsize(wd + "/tmp.paths") == g["tmp.paths_bytes"] and digests.file_md5(wd + "/tmp.paths") == g["tmp.paths"]
+    assert digests.file_md5(wd + "/stats/histogram_kmer_count.json") == g["histogram_kmer_count.json"]
 
 
 @pytest.fixture(scope="module")
@@ -66,16 +88,22 @@ def _rev2(x):
 
 
 @pytest.fixture(scope="module")
-def c2(sb):
+def c2(sb, tmp_path_factory):
     codes, quals, off, bc, _ = datasets.get("C2")
     pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
     n_bases = int(codes.size)
     del codes, quals
+    wd = str(tmp_path_factory.mktemp("C2"))
     ctx = sb.Context(0)
     ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
-    ctx.build_read_qgraph48(None, sb.Params(), with_paths=True)
-    yield dict(ctx=ctx, n_bases=n_bases, n_reads=len(ln))
+    ctx.build_read_qgraph48(wd, sb.Params(), with_paths=True)
+    yield dict(ctx=ctx, n_bases=n_bases, n_reads=len(ln), wd=wd, packed=(pb, boff, ln, pq, pqoff), bc=bc)
     ctx.close()
+
+
+def test_c2_matches_the_reference_exactly(c2, sb):
+    """BASELINE.json configs[1] at full size against the reference's own run (golden digests)."""
+    against_golden(sb, c2["ctx"], "C2", c2["wd"], c2["packed"], c2["bc"])
 
 
 def test_c2_kmer_table_properties(c2):
