@@ -187,6 +187,29 @@ void* sn_mg_survivor_buffer(sn_ctx* ctx, uint64_t n_total);
 void* sn_mg_bucket_count_buffer(sn_ctx* ctx, int bits);
 int   sn_mg_install_survivors(sn_ctx* ctx, uint64_t n_total, int bits);
 
+/* ---- multi-GPU with the collectives issued by the library (C++ host, NCCL over NVLink / NVSwitch) ---------------
+ * One context per rank (= per GPU).  sn_mg_build_graph is the whole hot path over the ranks of the communicator:
+ *   reads sharded over the ranks -> super-k-mers routed to the owner of their minimizer bucket (ONE alltoallv;
+ *   owner(b) = b * N >> bits, the role of `shard % total_chunks`, lib/tada/src/cmd_shard_asm.rs:40) -> count + filter
+ *   per owner -> the dictionary STAYS sharded: the neighbours of a rank's k-mers on other ranks are resolved by a
+ *   query/answer exchange (cf. fix_sedge_exts, lib/tada/src/debruijn.rs:785-826), the unipath chains are cut where they
+ *   cross ranks and stitched over a gathered table of those cuts, the edge bases are completed by one all-reduce ->
+ *   every rank holds all edges and the whole HyperBasevector; ReadPaths of the rank's own reads (with_paths: the
+ *   finished k-mer table is gathered first).
+ * sn_comm_init_nccl: `unique_id128` = the 128 bytes rank 0 got from sn_nccl_unique_id, handed to every rank by the
+ * launcher (MPI / torch.distributed / a file).  sn_comm_init_local: n ranks as n contexts of ONE process on one
+ * device, one host thread per rank -- test infrastructure for the rank logic on a single-GPU box.                  */
+int   sn_nccl_unique_id(void* out128);
+int   sn_comm_init_nccl(sn_ctx* ctx, int rank, int n_ranks, const void* unique_id128);
+void* sn_local_group_create(int n_ranks);
+void  sn_local_group_destroy(void* group);
+void  sn_local_group_abort(void* group);          /* a rank failed: the other ranks' collectives return an error instead of waiting */
+int   sn_comm_init_local(sn_ctx* ctx, void* group, int rank);
+void  sn_comm_free(sn_ctx* ctx);
+int   sn_mg_build_graph(sn_ctx* ctx, const sn_params* params, int with_paths);
+/* 1 while the context holds only its rank's shard of the k-mer table (sn_get_kmers etc. then return that shard) */
+int   sn_mg_dict_is_sharded(const sn_ctx* ctx);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) of the most recent run of a stage or
  * kernel group, in milliseconds; names: "h2d","goodlen","msp_hist","msp_scatter","bucket_count","make_dict",

@@ -6,4 +6,4 @@ built by ``__graft_entry__.build()`` / ``make -C supernova_b200/csrc``); this pa
 thin ctypes mirror used by the tests and the bench.  There is no CPU fallback: creating a
 ``Context`` without a CUDA device raises.
 """
-from .api import Context, Params, SnError, lib, pack_reads, write_read_files, pqvec_encode, pqvec_decode  # noqa: F401
+from .api import Context, Params, SnError, lib, pack_reads, write_read_files, pqvec_encode, pqvec_decode, nccl_unique_id, run_local_ranks  # noqa: F401

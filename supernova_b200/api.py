@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("edge_dict", "ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
+STAGES = ("exchange", "ghosts", "edge_dict", "ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
 
 
 class SnError(RuntimeError):
@@ -96,8 +96,56 @@ def lib():
         L.sn_mg_bucket_count_buffer.restype = vp
         L.sn_mg_count_received.argtypes = [vp, C.c_uint32, C.c_uint32, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
         L.sn_mg_install_survivors.argtypes = [vp, u64, i32]
+        L.sn_nccl_unique_id.argtypes = [vp]
+        L.sn_comm_init_nccl.argtypes = [vp, i32, i32, vp]
+        L.sn_local_group_create.argtypes = [i32]
+        L.sn_local_group_create.restype = vp
+        L.sn_local_group_destroy.argtypes = [vp]
+        L.sn_local_group_abort.argtypes = [vp]
+        L.sn_comm_init_local.argtypes = [vp, vp, i32]
+        L.sn_comm_free.argtypes = [vp]
+        L.sn_mg_build_graph.argtypes = [vp, C.POINTER(Params), i32]
+        L.sn_mg_dict_is_sharded.argtypes = [vp]
         _LIB = L
     return _LIB
+
+
+def nccl_unique_id():
+    """the 128 bytes of ncclGetUniqueId (rank 0 makes it, the launcher hands it to every rank)"""
+    buf = (C.c_char * 128)()
+    if lib().sn_nccl_unique_id(buf):
+        raise SnError("sn_nccl_unique_id: " + lib().sn_last_error(None).decode())
+    return bytes(buf)
+
+
+def run_local_ranks(n_ranks, fn, device=0):
+    """Test infrastructure: n ranks as n contexts of this process on ONE device, a host thread per rank
+    (sn_comm_init_local).  fn(rank, ctx) runs on every rank; returns the list of its results."""
+    import threading
+    L = lib()
+    group = L.sn_local_group_create(n_ranks)
+    ctxs = [Context(device) for _ in range(n_ranks)]
+    out, errs = [None] * n_ranks, [None] * n_ranks
+
+    def work(r):
+        try:
+            ctxs[r].comm_init_local(group, r)
+            out[r] = fn(r, ctxs[r])
+        except BaseException as e:          # noqa: BLE001  (a failing rank must not leave the others waiting in a collective)
+            errs[r] = e
+            L.sn_local_group_abort(group)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n_ranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in ctxs:
+        c.close()
+    L.sn_local_group_destroy(group)
+    first = [e for e in errs if e is not None and "another rank of the local group failed" not in str(e)] or [e for e in errs if e is not None]
+    if first:
+        raise first[0]
+    return out
 
 
 def _p(a):
@@ -299,6 +347,21 @@ class Context:
 
     def mg_install_survivors(self, n_total, bits):
         self._ck(self.L.sn_mg_install_survivors(self.h, n_total, bits))
+
+    # ---- multi-GPU, collectives inside the library (sn_multi.cu) -----------------------------
+    def comm_init_nccl(self, rank, n_ranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.sn_comm_init_nccl(self.h, rank, n_ranks, buf))
+
+    def comm_init_local(self, group, rank):
+        self._ck(self.L.sn_comm_init_local(self.h, group, rank))
+
+    def mg_build_graph(self, params=None, with_paths=False):
+        p = params or Params()
+        self._ck(self.L.sn_mg_build_graph(self.h, C.byref(p), int(with_paths)))
+
+    def dict_is_sharded(self):
+        return bool(self.L.sn_mg_dict_is_sharded(self.h))
 
     # ---- results ----------------------------------------------------------------------
     def counts(self):

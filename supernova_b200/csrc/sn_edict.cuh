@@ -11,7 +11,7 @@
 namespace sn {
 
 // k-mers per edge (0 for an edge shorter than K: flagged)
-__global__ void __launch_bounds__(256) k_ed_nk(const uint32_t* __restrict__ elen, uint32_t n_edges, uint32_t* __restrict__ nk, uint32_t* err)
+static __global__ void __launch_bounds__(256) k_ed_nk(const uint32_t* __restrict__ elen, uint32_t n_edges, uint32_t* __restrict__ nk, uint32_t* err)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t ed_edge_of(const uint64_t* __restrict__ koff
     return a;
 }
 // record {canonical k-mer, g}
-__global__ void __launch_bounds__(256) k_ed_records(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint64_t* __restrict__ koff,
+static __global__ void __launch_bounds__(256) k_ed_records(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint64_t* __restrict__ koff,
                                                     uint32_t n_edges, uint32_t n_k, uint4* __restrict__ rec)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_ed_records(const uint8_t* __restrict__ 
     rec[g] = make_uint4(k.w0, k.w1, k.w2, g);
 }
 // sorted by k-mer (stable: equal k-mers in increasing g): the last of every run stays
-__global__ void __launch_bounds__(256) k_ed_last_of_run(const uint4* __restrict__ rec, uint32_t n, uint32_t* __restrict__ flag)
+static __global__ void __launch_bounds__(256) k_ed_last_of_run(const uint4* __restrict__ rec, uint32_t n, uint32_t* __restrict__ flag)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_ed_last_of_run(const uint4* __restrict_
     flag[i] = last ? 1u : 0u;
 }
 // second key: {minimizer bucket, hash, rank by k-mer}; per-bucket counts
-__global__ void __launch_bounds__(256) k_ed_bucket_keys(const uint4* __restrict__ rec, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, int bits,
+static __global__ void __launch_bounds__(256) k_ed_bucket_keys(const uint4* __restrict__ rec, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, int bits,
                                                         uint4* __restrict__ key, uint32_t* __restrict__ gids, uint32_t* __restrict__ bucket_cnt)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_ed_bucket_keys(const uint4* __restrict_
     atomicAdd(&bucket_cnt[b], 1u);
 }
 // final order -> 16-byte dictionary seeds {w0,w1,w2,0} (k_make_dict turns them into entries) + (edge, offset) per entry
-__global__ void __launch_bounds__(256) k_ed_emit(const uint4* __restrict__ key, const uint32_t* __restrict__ gids, uint32_t n,
+static __global__ void __launch_bounds__(256) k_ed_emit(const uint4* __restrict__ key, const uint32_t* __restrict__ gids, uint32_t n,
                                                  const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint64_t* __restrict__ koff, uint32_t n_edges,
                                                  uint4* __restrict__ surv, uint2* __restrict__ loc)
 {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_ed_emit(const uint4* __restrict__ key, 
     surv[i] = make_uint4(k.w0, k.w1, k.w2, 0u);
     loc[i] = make_uint2(e, off);
 }
-__global__ void __launch_bounds__(256) k_ed_set_loc(DictEntry* __restrict__ dict, const uint2* __restrict__ loc, uint32_t n)
+static __global__ void __launch_bounds__(256) k_ed_set_loc(DictEntry* __restrict__ dict, const uint2* __restrict__ loc, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

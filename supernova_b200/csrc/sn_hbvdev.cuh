@@ -29,7 +29,7 @@ __device__ __forceinline__ int cmp_packed_dev(const uint8_t* x, const uint8_t* y
 }
 // ord: records {~len, first 16 bases, next 16 bases, edge} sorted by key.  Ties (same length, same
 // first 32 bases -- the two branches of a SNP bubble, for one) are ordered by the full sequence.
-__global__ void __launch_bounds__(128) k_hbv_rank(const uint4* __restrict__ ord, uint32_t n, const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff,
+static __global__ void __launch_bounds__(128) k_hbv_rank(const uint4* __restrict__ ord, uint32_t n, const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff,
                                                   const uint32_t* __restrict__ elen, uint32_t* __restrict__ order, uint32_t* __restrict__ rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) k_hbv_rank(const uint4* __restrict__ ord,
 }
 
 // items: edge<<2 | rc<<1 | distal, grouped by vertex (gstart).  EEComp order = (edge rank, rc, pos).
-__global__ void __launch_bounds__(128) k_hbv_groups(const uint32_t* __restrict__ items, const uint32_t* __restrict__ gstart, uint32_t n_groups, uint32_t n_valid,
+static __global__ void __launch_bounds__(128) k_hbv_groups(const uint32_t* __restrict__ items, const uint32_t* __restrict__ gstart, uint32_t n_groups, uint32_t n_valid,
                                                     const uint32_t* __restrict__ rank, snh::GroupRec* __restrict__ groups, uint32_t* err)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) k_hbv_groups(const uint32_t* __restrict__
     o[2] = make_uint4(n > 6 ? it[6] >> 1 : 0u, n > 7 ? it[7] >> 1 : 0u, 0u, 0u);
     o[3] = make_uint4(0u, 0u, 0u, 0u);
 }
-__global__ void __launch_bounds__(256) k_hbv_erec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, uint32_t n_items, snh::ERec* __restrict__ er)
+static __global__ void __launch_bounds__(256) k_hbv_erec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, uint32_t n_items, snh::ERec* __restrict__ er)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_hbv_erec(const int32_t* __restrict__ eg
 }
 
 // the numbering loop's record of an oriented unipath: both vertices with their items, one cache line
-__global__ void __launch_bounds__(128) k_hbv_itemrec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, const snh::GroupRec* __restrict__ groups,
+static __global__ void __launch_bounds__(128) k_hbv_itemrec(const int32_t* __restrict__ egrp, const uint8_t* __restrict__ pal, const snh::GroupRec* __restrict__ groups,
                                                      uint32_t n_items, snh::ItemRec* __restrict__ rec)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,13 +120,13 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x)
         x = p;
     }
 }
-__global__ void __launch_bounds__(256) k_hbv_uf_init(uint32_t* parent, uint32_t n, unsigned long long* ckey, uint32_t* cnt_v, uint32_t* cnt_e)
+static __global__ void __launch_bounds__(256) k_hbv_uf_init(uint32_t* parent, uint32_t n, unsigned long long* ckey, uint32_t* cnt_v, uint32_t* cnt_e)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     parent[g] = g; ckey[g] = ~0ull; cnt_v[g] = 0; cnt_e[g] = 0;
 }
-__global__ void __launch_bounds__(256) k_hbv_union(const snh::ERec* __restrict__ er, uint32_t n_items, uint32_t* parent)
+static __global__ void __launch_bounds__(256) k_hbv_union(const snh::ERec* __restrict__ er, uint32_t n_items, uint32_t* parent)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_hbv_union(const snh::ERec* __restrict__
         if (atomicCAS(parent + a, a, b) == a) break;   // hang the larger root under the smaller
     }
 }
-__global__ void __launch_bounds__(256) k_hbv_flatten(uint32_t* parent, uint32_t n, uint32_t* __restrict__ comp, uint32_t* cnt_v)
+static __global__ void __launch_bounds__(256) k_hbv_flatten(uint32_t* parent, uint32_t n, uint32_t* __restrict__ comp, uint32_t* cnt_v)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_hbv_flatten(uint32_t* parent, uint32_t 
 }
 // per component: number of HBV edges, and the first item of the reference's outer loop
 // (pass 0 = forward items in edge order, pass 1 = reverse items): min of (rc, rank)
-__global__ void __launch_bounds__(256) k_hbv_compstats(const snh::ERec* __restrict__ er, uint32_t n_items, const uint32_t* __restrict__ comp,
+static __global__ void __launch_bounds__(256) k_hbv_compstats(const snh::ERec* __restrict__ er, uint32_t n_items, const uint32_t* __restrict__ comp,
                                                        const uint32_t* __restrict__ rank, unsigned long long* ckey, uint32_t* cnt_e)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,12 +168,12 @@ __global__ void __launch_bounds__(256) k_hbv_compstats(const snh::ERec* __restri
     const unsigned long long best = ((unsigned long long)(k32 >> 31) << 32) | (k32 & 0x7FFFFFFFu);
     if (lane == leader) { atomicMin(ckey + r, best); atomicAdd(cnt_e + r, (uint32_t)__popc(m)); }
 }
-__global__ void __launch_bounds__(256) k_hbv_rootflag(const uint32_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ flag)
+static __global__ void __launch_bounds__(256) k_hbv_rootflag(const uint32_t* __restrict__ comp, uint32_t n, uint32_t* __restrict__ flag)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n) flag[g] = comp[g] == g ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) k_hbv_roots(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n,
+static __global__ void __launch_bounds__(256) k_hbv_roots(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n,
                                                    const unsigned long long* __restrict__ ckey, uint4* __restrict__ rec)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_hbv_roots(const uint32_t* __restrict__ 
     rec[pos[g]] = make_uint4(0u, (uint32_t)(k >> 32), (uint32_t)k, g);
 }
 // rec sorted by (rc, rank): component i -> its start item (edge << 1 | rc) and sizes
-__global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __restrict__ rec, uint32_t n_comp, const uint32_t* __restrict__ order,
+static __global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __restrict__ rec, uint32_t n_comp, const uint32_t* __restrict__ order,
                                                         const uint32_t* __restrict__ cnt_v, const uint32_t* __restrict__ cnt_e,
                                                         uint32_t* __restrict__ start_item, uint32_t* __restrict__ cv, uint32_t* __restrict__ ce)
 {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __restrict_
 // lists renamed.  The layout changes no result: the traversal order only depends on the lists.
 #define SN_LAY_NONE 0xFFFFFFFFu
 __device__ __forceinline__ bool lay_is_seed(uint32_t item) { return ((item * 0x9E3779B1u) >> 27) == 0u; }      // 1 in 32
-__global__ void __launch_bounds__(256) k_lay_seed(const snh::ItemRec* __restrict__ rec, uint32_t n_items, uint32_t* __restrict__ lab, uint32_t* __restrict__ lev,
+static __global__ void __launch_bounds__(256) k_lay_seed(const snh::ItemRec* __restrict__ rec, uint32_t n_items, uint32_t* __restrict__ lab, uint32_t* __restrict__ lev,
                                                   uint32_t* __restrict__ frontier, uint32_t* __restrict__ cnt /* 3 counters */)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) k_lay_seed(const snh::ItemRec* __restrict
     lab[t] = l; lev[t] = 0u;
 }
 // round r: every item of frontier (r & 1) labels its unlabelled neighbours (the items on its two vertices)
-__global__ void __launch_bounds__(256) k_lay_round(const snh::ItemRec* __restrict__ rec, const snh::GroupRec* __restrict__ groups, uint32_t round,
+static __global__ void __launch_bounds__(256) k_lay_round(const snh::ItemRec* __restrict__ rec, const snh::GroupRec* __restrict__ groups, uint32_t round,
                                                    uint32_t* __restrict__ lab, uint32_t* __restrict__ lev, uint32_t* __restrict__ fa, uint32_t* __restrict__ fb, uint32_t* __restrict__ cnt)
 {
     const uint32_t* fin = (round & 1u) ? fb : fa;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) k_lay_round(const snh::ItemRec* __restric
     }
 }
 // sort records {seed, signed distance, item}; what no seed reached is its own seed
-__global__ void __launch_bounds__(256) k_lay_keys(const uint32_t* __restrict__ lab, const uint32_t* __restrict__ lev, uint32_t n_items, uint4* __restrict__ key)
+static __global__ void __launch_bounds__(256) k_lay_keys(const uint32_t* __restrict__ lab, const uint32_t* __restrict__ lev, uint32_t n_items, uint4* __restrict__ key)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_items) return;
@@ -247,13 +247,13 @@ __global__ void __launch_bounds__(256) k_lay_keys(const uint32_t* __restrict__ l
     const uint32_t v = lev[t], d = v & 0x7FFFFFFFu;
     key[t] = make_uint4(l == SN_LAY_NONE ? t : l, l == SN_LAY_NONE ? 0x40000000u : ((v >> 31) ? 0x40000000u + d : 0x40000000u - d), t, 0u);
 }
-__global__ void __launch_bounds__(256) k_lay_pos(const uint4* __restrict__ key, uint32_t n_items, uint32_t* __restrict__ pos)
+static __global__ void __launch_bounds__(256) k_lay_pos(const uint4* __restrict__ key, uint32_t n_items, uint32_t* __restrict__ pos)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_items) pos[key[i].z] = i;
 }
 // record i of the new layout = the record of item key[i].z with its lists renamed; pad = the item it is
-__global__ void __launch_bounds__(128) k_lay_permute(const uint4* __restrict__ key, const uint32_t* __restrict__ pos, const snh::ItemRec* __restrict__ rec, uint32_t n_items,
+static __global__ void __launch_bounds__(128) k_lay_permute(const uint4* __restrict__ key, const uint32_t* __restrict__ pos, const snh::ItemRec* __restrict__ rec, uint32_t n_items,
                                                      snh::ItemRec* __restrict__ out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) k_lay_permute(const uint4* __restrict__ k
     out[i] = r;
 }
 // the vertex records the numbering loop reads (more than 6 items) with their lists renamed
-__global__ void __launch_bounds__(256) k_lay_groups(const snh::GroupRec* __restrict__ groups, uint32_t n_groups, const uint32_t* __restrict__ pos, snh::GroupRec* __restrict__ out)
+static __global__ void __launch_bounds__(256) k_lay_groups(const snh::GroupRec* __restrict__ groups, uint32_t n_groups, const uint32_t* __restrict__ pos, snh::GroupRec* __restrict__ out)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_lay_groups(const snh::GroupRec* __restr
 }
 
 // ---- after the numbering: adjacency lists and involution ----------------------------------------
-__global__ void __launch_bounds__(256) k_hbv_csr_rec(const int32_t* __restrict__ to_left, const int32_t* __restrict__ to_right, uint32_t n_h,
+static __global__ void __launch_bounds__(256) k_hbv_csr_rec(const int32_t* __restrict__ to_left, const int32_t* __restrict__ to_right, uint32_t n_h,
                                                      uint4* __restrict__ rec_from, uint4* __restrict__ rec_to)
 {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) k_hbv_csr_rec(const int32_t* __restrict__
     rec_from[h] = make_uint4(l, r, h, 0u);             // from_[l] gets (r, h), lists sorted by (neighbour, id)
     rec_to[h] = make_uint4(r, l, h, 0u);
 }
-__global__ void __launch_bounds__(256) k_hbv_csr_emit(const uint4* __restrict__ rec, uint32_t n_h, uint32_t n_v, uint32_t* __restrict__ start,
+static __global__ void __launch_bounds__(256) k_hbv_csr_emit(const uint4* __restrict__ rec, uint32_t n_h, uint32_t n_v, uint32_t* __restrict__ start,
                                                       int32_t* __restrict__ nb, int32_t* __restrict__ eo)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) k_hbv_csr_emit(const uint4* __restrict__ 
         start[i] = lo;
     }
 }
-__global__ void __launch_bounds__(256) k_hbv_inv(const int32_t* __restrict__ fwd, const int32_t* __restrict__ rev, uint32_t n_e, int32_t* __restrict__ inv)
+static __global__ void __launch_bounds__(256) k_hbv_inv(const int32_t* __restrict__ fwd, const int32_t* __restrict__ rev, uint32_t n_e, int32_t* __restrict__ inv)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_e) return;

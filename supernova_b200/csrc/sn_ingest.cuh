@@ -23,7 +23,7 @@ namespace sn {
 #define SN_ING_E_LONG 8u             // read longer than SN_ING_MAXLEN
 
 // ---- lines -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_nl_count(const uint8_t* __restrict__ text, uint64_t n, uint32_t* __restrict__ cnt, uint64_t n_seg)
+static __global__ void __launch_bounds__(256) k_nl_count(const uint8_t* __restrict__ text, uint64_t n, uint32_t* __restrict__ cnt, uint64_t n_seg)
 {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_nl_count(const uint8_t* __restrict__ te
     } else for (uint64_t i = a; i < b; ++i) c += text[i] == '\n';
     cnt[s] = c;
 }
-__global__ void __launch_bounds__(256) k_nl_fill(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ seg_off, uint64_t n_seg, uint64_t* __restrict__ line_start)
+static __global__ void __launch_bounds__(256) k_nl_fill(const uint8_t* __restrict__ text, uint64_t n, const uint64_t* __restrict__ seg_off, uint64_t n_seg, uint64_t* __restrict__ line_start)
 {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_nl_fill(const uint8_t* __restrict__ tex
 }
 
 // line index of a byte offset that is a line start (file boundaries): one thread per file
-__global__ void k_fasth_file_lines(const uint64_t* __restrict__ line_start, uint64_t n_lines, const uint64_t* __restrict__ file_first_byte, uint32_t n_files, uint64_t* __restrict__ file_first_line)
+static __global__ void k_fasth_file_lines(const uint64_t* __restrict__ line_start, uint64_t n_lines, const uint64_t* __restrict__ file_first_byte, uint32_t n_files, uint64_t* __restrict__ file_first_line)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_files) return;
@@ -64,7 +64,7 @@ __device__ __forceinline__ uint8_t ing_fold(uint8_t c) { return (c == 'n' || c =
 
 // ---- records -----------------------------------------------------------------------------------
 // thread per record: barcoded?  (hasGemGroup(buf) && buf[0] != '-', ParseBarcodedFastqs.cc:107)
-__global__ void __launch_bounds__(256) k_fasth_flags(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, uint64_t n_rec, uint32_t* __restrict__ barcoded, uint32_t* err)
+static __global__ void __launch_bounds__(256) k_fasth_flags(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, uint64_t n_rec, uint32_t* __restrict__ barcoded, uint32_t* err)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_fasth_flags(const uint8_t* __restrict__
     for (uint64_t i = s; i < e; ++i) dash = dash || text[i] == '-';
     barcoded[r] = (dash && e > s && text[s] != '-') ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) k_fasth_blist(const uint32_t* __restrict__ barcoded, const uint64_t* __restrict__ nbc_before, uint64_t n_rec, uint32_t* __restrict__ blist)
+static __global__ void __launch_bounds__(256) k_fasth_blist(const uint32_t* __restrict__ barcoded, const uint64_t* __restrict__ nbc_before, uint64_t n_rec, uint32_t* __restrict__ blist)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n_rec && barcoded[r]) blist[nbc_before[r]] = (uint32_t)r;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_fasth_blist(const uint32_t* __restrict_
 // (key = the line after n/N -> A, up to the first ','  -- :108-111)
 // Several input files (FASTQS={a,b,...}, :262-264): the comparison string starts empty in every file (:67), so the
 // first barcoded record of a file always opens a new barcode.  file_first_rec[f] = first record of file f.
-__global__ void __launch_bounds__(256) k_fasth_newbc(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, const uint32_t* __restrict__ blist, uint64_t n_bc, uint32_t* __restrict__ isnew,
+static __global__ void __launch_bounds__(256) k_fasth_newbc(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, const uint32_t* __restrict__ blist, uint64_t n_bc, uint32_t* __restrict__ isnew,
                                                      const uint32_t* __restrict__ file_first_rec, uint32_t n_files)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_fasth_newbc(const uint8_t* __restrict__
     isnew[j] = differ;
 }
 // thread per record: where its two reads go and what they are
-__global__ void __launch_bounds__(256) k_fasth_layout(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, uint64_t n_rec, const uint32_t* __restrict__ barcoded,
+static __global__ void __launch_bounds__(256) k_fasth_layout(const uint8_t* __restrict__ text, const uint64_t* __restrict__ ls, uint64_t n_rec, const uint32_t* __restrict__ barcoded,
                                                       const uint64_t* __restrict__ nbc_before, uint64_t n_un_rec, const uint64_t* __restrict__ new_before, const uint32_t* __restrict__ isnew,
                                                       uint32_t* __restrict__ len, int32_t* __restrict__ bc, uint64_t* __restrict__ bpos, uint64_t* __restrict__ qpos,
                                                       uint32_t* __restrict__ nbytes, uint32_t* __restrict__ pqcap, uint32_t* err)
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_fasth_layout(const uint8_t* __restrict_
 }
 // ---- reads -----------------------------------------------------------------------------------
 // thread per read: bases -> fastb packing (4 per byte, LSB first)
-__global__ void __launch_bounds__(128) k_fasth_pack(const uint8_t* __restrict__ text, const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ len, const uint64_t* __restrict__ boff,
+static __global__ void __launch_bounds__(128) k_fasth_pack(const uint8_t* __restrict__ text, const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ len, const uint64_t* __restrict__ boff,
                                                     uint64_t n_reads, uint8_t* __restrict__ bases, uint32_t* err)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t pq_block_size(uint32_t nqs, uint32_t nbits) 
 // thread per read: PQVecEncoder (feudal/PQVec.cc:17-127) -- the dynamic programme over block ends
 // (`costs`), the block stack it maintains, then the bit packing.  The encoding goes to the read's slot
 // of a scratch array; its size to pqsize.
-__global__ void __launch_bounds__(128) k_fasth_pqvec(const uint8_t* __restrict__ text, const uint64_t* __restrict__ qpos, const uint32_t* __restrict__ len, const uint64_t* __restrict__ slot_off,
+static __global__ void __launch_bounds__(128) k_fasth_pqvec(const uint8_t* __restrict__ text, const uint64_t* __restrict__ qpos, const uint32_t* __restrict__ len, const uint64_t* __restrict__ slot_off,
                                                      uint64_t n_reads, uint8_t* __restrict__ scratch, uint32_t* __restrict__ pqsize)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) k_fasth_pqvec(const uint8_t* __restrict__
     out[o++] = 0;
     pqsize[r] = o;
 }
-__global__ void __launch_bounds__(256) k_fasth_pq_compact(const uint8_t* __restrict__ scratch, const uint64_t* __restrict__ slot_off, const uint32_t* __restrict__ pqsize,
+static __global__ void __launch_bounds__(256) k_fasth_pq_compact(const uint8_t* __restrict__ scratch, const uint64_t* __restrict__ slot_off, const uint32_t* __restrict__ pqsize,
                                                           const uint64_t* __restrict__ pqoff, uint64_t n_reads, uint8_t* __restrict__ pq)
 {
     // a warp per read

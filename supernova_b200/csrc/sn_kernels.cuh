@@ -25,7 +25,7 @@ namespace sn {
 // of the reference finds first).  Also accumulates the number of k-mer occurrences
 // Kmerizer::map will emit.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
+static __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
                                                        const uint32_t* __restrict__ len, uint32_t min_qual,
                                                        uint32_t* __restrict__ goodlen, unsigned long long* occ_total, uint32_t* bad_reads)
 {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const u
 }
 
 // input limits checked on the device: total bases, longest read, largest barcode ordinal
-__global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, const uint32_t* __restrict__ len, const int32_t* __restrict__ bc,
+static __global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, const uint32_t* __restrict__ len, const int32_t* __restrict__ bc,
                                                     unsigned long long* total_bases, uint32_t* max_len, int32_t* max_bc)
 {
     uint64_t sum = 0; uint32_t ml = 0; int32_t mb = 0;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, const uint
 }
 
 // same, for callers that already hold one u8 per base
-__global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
+static __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
                                                     const uint32_t* __restrict__ len, uint32_t min_qual,
                                                     uint32_t* __restrict__ goodlen, unsigned long long* occ_total)
 {
@@ -106,7 +106,7 @@ __device__ __forceinline__ bool same_kmer(const uint4& a, const uint4& b) { retu
 // ---------------------------------------------------------------------------
 // a6. recomputeAdjacencies
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2* __restrict__ cand)
+static __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2* __restrict__ cand)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = d.n;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_prune(DictEntry* tab, DictView d, Link2
 __device__ __forceinline__ bool stop_sampled(uint32_t i) { return ((i * 0x9E3779B1u) >> SN_STOP_SHIFT) == 0u; }
 struct Seg { uint32_t next; uint32_t steps_o; };        // next stop (stop id, SN_NO_LINK = none on this side); steps << 1 | arrival orientation
 
-__global__ void __launch_bounds__(256) k_classify(DictView d,
+static __global__ void __launch_bounds__(256) k_classify(DictView d,
                                                   Link2* links, uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* __restrict__ is_stop)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(256) k_classify(DictView d,
     own_n[i] = t == T_SINGLE ? 1u : 0u;
     is_stop[i] = (t == T_END_DOWN || t == T_END_UP || (t == T_INTERIOR && stop_sampled(i))) ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) k_scatter_flagged(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ list)
+static __global__ void __launch_bounds__(256) k_scatter_flagged(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ list)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) list[pos[i]] = i;
 }
 // thread per (stop, side): side 0 leaves through the down link, side 1 through the up link
-__global__ void __launch_bounds__(128) k_seg_walk(const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
+static __global__ void __launch_bounds__(128) k_seg_walk(const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
                                                   const uint64_t* __restrict__ stop_pos, Seg* __restrict__ segs)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) k_seg_walk(const Link2* __restrict__ link
     segs[t] = out;
 }
 // thread per stop that is an edge end: hop to the far end of the edge
-__global__ void __launch_bounds__(128) k_end_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ stops, uint32_t n_stops,
+static __global__ void __launch_bounds__(128) k_end_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ stops, uint32_t n_stops,
                                                  const uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n)
 {
     const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_end_hop(const Seg* __restrict__ segs, c
     }
     if (i <= stops[cur]) own_n[i] = nk;                  // the other end walks the same edge; the smaller index owns it
 }
-__global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const Link2* __restrict__ links, uint32_t n,
+static __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restrict__ tab, const Link2* __restrict__ links, uint32_t n,
                                                      uint8_t* __restrict__ etype, uint32_t* __restrict__ own_n, uint32_t* n_circle_members)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(128) k_circle_count(const DictEntry* __restric
     if (nk) { own_n[m] = nk; etype[m] = T_CIRCLE; }
 }
 // counts the interior entries no edge end reached (cheap: one byte + one sector per interior entry)
-__global__ void __launch_bounds__(256) k_count_unreached(const DictEntry* __restrict__ tab, const uint8_t* __restrict__ etype, uint32_t n, uint32_t* count)
+static __global__ void __launch_bounds__(256) k_count_unreached(const DictEntry* __restrict__ tab, const uint8_t* __restrict__ etype, uint32_t n, uint32_t* count)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool u = i < n && etype[i] == T_INTERIOR && tab[i].edge == SN_NULL_EDGE;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) k_count_unreached(const DictEntry* __rest
     if (m && lane_id() == 0) atomicAdd(count, (uint32_t)__popc(m));
 }
 // phase 0: every owner so far (singles, edges with ends); phase 1: the circle owners only
-__global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ etype, int circles_only, uint32_t n,
+static __global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ etype, int circles_only, uint32_t n,
                                                     uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) k_edge_sizes(const uint32_t* __restrict__
 // its owner -- circles are rare); the owner of an edge with ends hops over its stops and leaves
 // {edge, offset, walk orientation} at each for k_seg_emit.
 struct StopInfo { uint32_t edge, off_o; };               // off_o = offset << 1 | orientation
-__global__ void __launch_bounds__(128) k_owner_hop(DictEntry* tab, const Link2* __restrict__ links, const Seg* __restrict__ segs,
+static __global__ void __launch_bounds__(128) k_owner_hop(DictEntry* tab, const Link2* __restrict__ links, const Seg* __restrict__ segs,
                                                    const uint64_t* __restrict__ stop_pos, const uint32_t* __restrict__ owners, uint32_t n_owners, uint32_t edge0,
                                                    const uint8_t* __restrict__ etype, const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint64_t base_shift,
                                                    uint8_t* __restrict__ tmp, uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, StopInfo* __restrict__ sinfo)
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128) k_owner_hop(DictEntry* tab, const Link2* 
         walk_circle_links(links, i, false, [&](uint32_t step, uint32_t j, uint32_t o) { s[SN_K - 1 + step] = (uint8_t)step_base(tab[j], o); tab[j].edge = e; tab[j].off = step; });
 }
 // thread per stop on an edge with ends: its own k-mer, then the k-mers up to (not including) the next stop
-__global__ void __launch_bounds__(128) k_seg_emit(DictEntry* tab, const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
+static __global__ void __launch_bounds__(128) k_seg_emit(DictEntry* tab, const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
                                                   const StopInfo* __restrict__ sinfo, const Seg* __restrict__ segs, const uint64_t* __restrict__ etmp_off, uint8_t* __restrict__ tmp)
 {
     const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,26 +292,26 @@ __global__ void __launch_bounds__(128) k_seg_emit(DictEntry* tab, const Link2* _
     }
 }
 // whole-edge canonical form (EdgeBuilder::addEdge :480-485 / extend :457-464): is the edge stored reverse-complemented?
-__global__ void __launch_bounds__(128) k_edge_form(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
+static __global__ void __launch_bounds__(128) k_edge_form(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
                                                    uint32_t n_edges, uint8_t* __restrict__ eflip)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n_edges) eflip[e] = seq_form_u8(tmp + etmp_off[e], elen[e]) == REV ? 1 : 0;
 }
-__global__ void __launch_bounds__(256) k_fix_offsets(DictEntry* tab, uint32_t n, const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip)
+static __global__ void __launch_bounds__(256) k_fix_offsets(DictEntry* tab, uint32_t n, const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t e = tab[i].edge;
     if (e != SN_NULL_EDGE && eflip[e]) tab[i].off = (elen[e] - (SN_K - 1)) - 1 - tab[i].off;
 }
-__global__ void __launch_bounds__(256) k_edge_bytes(const uint32_t* __restrict__ elen, uint32_t n_edges, uint32_t* __restrict__ ebytes)
+static __global__ void __launch_bounds__(256) k_edge_bytes(const uint32_t* __restrict__ elen, uint32_t n_edges, uint32_t* __restrict__ ebytes)
 {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n_edges) ebytes[e] = (elen[e] + 3) >> 2;
 }
 // one thread per output byte of the packed edge store (fastb layout)
-__global__ void __launch_bounds__(256) k_pack_edges(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off,
+static __global__ void __launch_bounds__(256) k_pack_edges(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off,
                                                     const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip,
                                                     const uint64_t* __restrict__ eoff, uint32_t n_edges, uint64_t total_bytes, uint8_t* __restrict__ packed)
 {
@@ -349,7 +349,7 @@ __device__ __forceinline__ int seq_form_packed(const uint8_t* s, uint32_t len)
     }
     return PAL;
 }
-__global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ elen,
+static __global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ ebases, const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ elen,
                                                   uint32_t n_edges, uint4* __restrict__ order_rec, uint4* __restrict__ end_rec, uint8_t* __restrict__ pal, uint32_t* n_pal)
 {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(128) k_hbv_keys(const uint8_t* __restrict__ eb
     end_rec[4ull * e + 2] = p ? inval : make_uint4(rl.w0, rl.w1, rl.w2, (e << 2) | 2u);
     end_rec[4ull * e + 3] = p ? inval : make_uint4(rf.w0, rf.w1, rf.w2, (e << 2) | 3u);
 }
-__global__ void __launch_bounds__(256) k_hbv_mark(const uint4* __restrict__ rec, uint32_t n, uint32_t* __restrict__ flag)
+static __global__ void __launch_bounds__(256) k_hbv_mark(const uint4* __restrict__ rec, uint32_t n, uint32_t* __restrict__ flag)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) k_hbv_mark(const uint4* __restrict__ rec,
     bool valid = r.w != 0xFFFFFFFFu;
     flag[i] = (valid && (i == 0 || !same_kmer(rec[i - 1], r))) ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) k_hbv_assign(const uint4* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos,
+static __global__ void __launch_bounds__(256) k_hbv_assign(const uint4* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag, const uint64_t* __restrict__ pos,
                                                     int32_t* __restrict__ end_group, uint32_t* __restrict__ items, uint32_t* __restrict__ gstart)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,7 +414,7 @@ __device__ __forceinline__ void thread_path(const PathInputs& in, uint64_t r, co
     else q = in.quals + in.qoff[r];
     path_one_read(d, es, h, in.bases + in.boff[r], q, in.len[r], parts, path);
 }
-__global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, EdgeStore es, HbvView h,
+static __global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, EdgeStore es, HbvView h,
                                                     uint32_t* __restrict__ plen, int32_t* __restrict__ poffset, int32_t* __restrict__ scratch, uint32_t* overflow)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, E
     int4 v = make_int4(path.n > 0 ? path.e[0] : 0, path.n > 1 ? path.e[1] : 0, path.n > 2 ? path.e[2] : 0, path.n > 3 ? path.e[3] : 0);
     reinterpret_cast<int4*>(scratch)[r] = v;
 }
-__global__ void __launch_bounds__(128) k_path_finish(PathInputs in, DictView d, EdgeStore es, HbvView h,
+static __global__ void __launch_bounds__(128) k_path_finish(PathInputs in, DictView d, EdgeStore es, HbvView h,
                                                      const uint32_t* __restrict__ plen, const int32_t* __restrict__ scratch,
                                                      const uint64_t* __restrict__ path_off, int32_t* __restrict__ pedges)
 {
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128) k_path_finish(PathInputs in, DictView d, 
 // (the reference sorts pair<int, unsigned long> the same way: a read that crosses an edge twice is listed
 // twice), per-edge counts by atomics, and countsb[e] = reads on e plus reads on its reverse complement.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pi_records(const int32_t* __restrict__ pedges, const uint64_t* __restrict__ path_off, uint64_t n_reads,
+static __global__ void __launch_bounds__(256) k_pi_records(const int32_t* __restrict__ pedges, const uint64_t* __restrict__ path_off, uint64_t n_reads,
                                                     uint4* __restrict__ rec, uint32_t* __restrict__ cnt)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,12 +466,12 @@ __global__ void __launch_bounds__(256) k_pi_records(const int32_t* __restrict__ 
         atomicAdd(cnt + e, 1u);
     }
 }
-__global__ void __launch_bounds__(256) k_pi_ids(const uint4* __restrict__ rec, uint64_t m, unsigned long long* __restrict__ ids)
+static __global__ void __launch_bounds__(256) k_pi_ids(const uint4* __restrict__ rec, uint64_t m, unsigned long long* __restrict__ ids)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) ids[i] = rec[i].z;
 }
-__global__ void __launch_bounds__(256) k_pi_countsb(const uint32_t* __restrict__ cnt, const int32_t* __restrict__ inv, uint32_t n_h, int32_t* __restrict__ countsb)
+static __global__ void __launch_bounds__(256) k_pi_countsb(const uint32_t* __restrict__ cnt, const int32_t* __restrict__ inv, uint32_t n_h, int32_t* __restrict__ countsb)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_h) return;

@@ -232,10 +232,18 @@ struct __attribute__((aligned(32))) DictEntry {
 
 struct DictView {
     const DictEntry* tab;
-    const uint32_t* boff;     // (1 << (bits + sub_bits)) + 1: first entry of every (minimizer bucket, top sub_bits of the hash)
+    const uint32_t* boff;     // (b_n << sub_bits) + 1: first entry of every (minimizer bucket of the window, top sub_bits of the hash)
     uint32_t n;
     int bits, sub_bits;
+    // A rank of the sharded multi-GPU path holds the buckets [b_lo, b_lo + b_n) of the 2^bits; one GPU holds all
+    // (b_lo = 0, b_n = 2^bits).  k-mers of other buckets that are neighbours of local ones are GHOSTS: an
+    // open-addressed table of g_cap (power of two, 0 = none) entries right behind the local ones, tab[n + slot].
+    uint32_t b_lo, b_n;
+    uint32_t g_cap;
 };
+// ghost entry (a DictEntry behind the table): w0..w2 = k-mer, h = its hash, cc = owner rank, edge = index in the
+// owner's table, ctx = its context there AFTER recomputeAdjacencies, off = state
+enum GhostState { GH_EMPTY = 0, GH_PENDING = 1, GH_PRESENT = 2, GH_ABSENT = 3, GH_WRITING = 4 };
 
 // (h,k) < entry ?  /  == entry ?
 SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
@@ -249,10 +257,22 @@ SN_HD int dict_cmp(uint32_t h, const Kmer& k, const DictEntry& e)
 // lookup of a canonical k-mer whose minimizer is known.  Inside the bucket the entries are sorted
 // by a uniform hash; the offsets are kept per (bucket, top sub_bits of the hash) -- ~32 entries --
 // and the search starts where the remaining hash bits interpolate, then walks a step or two.
+SN_HD uint32_t ghost_find(const DictView& d, uint32_t h, const Kmer& k)
+{
+    uint32_t s = h & (d.g_cap - 1u);
+    for (uint32_t probes = 0; probes < d.g_cap; ++probes) {
+        const DictEntry& e = d.tab[d.n + s];
+        if (e.off == GH_EMPTY) return SN_NULL_EDGE;
+        if (e.h == h && e.w0 == k.w0 && e.w1 == k.w1 && e.w2 == k.w2) return e.off == GH_PRESENT ? d.n + s : SN_NULL_EDGE;
+        s = (s + 1u) & (d.g_cap - 1u);
+    }
+    return SN_NULL_EDGE;
+}
 SN_HD uint32_t dict_find_in_bucket(const DictView& d, uint32_t minimizer, const Kmer& k)
 {
     const uint32_t h = kmer_hash(k);
-    const uint32_t b = bucket_hash(minimizer) >> (32 - d.bits);
+    const uint32_t b = (bucket_hash(minimizer) >> (32 - d.bits)) - d.b_lo;
+    if (b >= d.b_n) return d.g_cap ? ghost_find(d, h, k) : SN_NULL_EDGE;       // another rank's bucket
     const uint32_t cell = d.sub_bits ? ((b << d.sub_bits) | (h >> (32 - d.sub_bits))) : b;
     const uint32_t lo = d.boff[cell], hi = d.boff[cell + 1];
     if (lo >= hi) return SN_NULL_EDGE;

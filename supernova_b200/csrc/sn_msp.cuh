@@ -188,7 +188,7 @@ namespace sn {
 #define SN_MS_QUEUE 12
 
 template <bool EMIT>
-__global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                             const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
                                                             int bits, uint32_t* __restrict__ counter /* hist or cursor, one per bucket of the window */,
                                                             const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, cons
 // descriptors the first scan left behind -- no minimizer is computed twice.  Same thread mapping as
 // k_msp_scan (the descriptors are indexed by its blocks); reads marked 255 are left to k_msp_scan.
 template <bool EMIT>
-__global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
+static __global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                              const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
                                                              int bits, uint32_t* __restrict__ counter, const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
                                                              uint32_t b_lo, uint32_t b_n, const uint2* __restrict__ dsc, const uint8_t* __restrict__ nruns)
@@ -403,7 +403,7 @@ __device__ __forceinline__ void skc_step(SkCursor& c, uint32_t next_base)
 }
 
 template <int SN_BC_THREADS, int SN_BC_SLOTS, int SN_BC_ITEMS, int MINB>
-__global__ void __launch_bounds__(SN_BC_THREADS, MINB)
+static __global__ void __launch_bounds__(SN_BC_THREADS, MINB)
 k_bucket_count(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg,
                uint32_t min_freq, uint32_t min_bc, int has_bc,
                uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor,
@@ -785,7 +785,7 @@ __device__ __forceinline__ void skc2_step(SkCur2& c)
 }
 
 template <int T, int SLOTS, int ITEMS, int MINB>
-__global__ void __launch_bounds__(T, MINB)
+static __global__ void __launch_bounds__(T, MINB)
 k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg,
                 uint32_t min_freq, uint32_t min_bc, int has_bc,
                 uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor,
@@ -1116,7 +1116,7 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
 }
 
 // k-mer occurrences held by n records
-__global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, uint64_t n, unsigned long long* total)
+static __global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, uint64_t n, unsigned long long* total)
 {
     unsigned long long s = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += sk_nk(recs[2 * i].x);
@@ -1125,7 +1125,7 @@ __global__ void __launch_bounds__(256) k_sum_nk(const uint4* __restrict__ recs, 
 }
 
 // every bucket's survivors from where k_bucket_count left them to their place in bucket order (a warp per bucket)
-__global__ void __launch_bounds__(256) k_gather_survivors(const uint4* __restrict__ scratch, const uint64_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_cnt,
+static __global__ void __launch_bounds__(256) k_gather_survivors(const uint4* __restrict__ scratch, const uint64_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_cnt,
                                                           const uint64_t* __restrict__ off, uint32_t n_buckets, uint4* __restrict__ surv)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -1137,7 +1137,7 @@ __global__ void __launch_bounds__(256) k_gather_survivors(const uint4* __restric
     }
 }
 // surviving k-mers (bucket, hash, k-mer order) -> dictionary entries
-__global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict)
+static __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ sur
     dict[i] = e;
 }
 // offsets per (bucket, top sub_bits of the hash) from the bucket offsets: a search per cell
-__global__ void __launch_bounds__(256) k_dict_cells(const DictEntry* __restrict__ dict, const uint32_t* __restrict__ bucket_off, uint32_t n_buckets, int sub_bits,
+static __global__ void __launch_bounds__(256) k_dict_cells(const DictEntry* __restrict__ dict, const uint32_t* __restrict__ bucket_off, uint32_t n_buckets, int sub_bits,
                                                     uint32_t* __restrict__ cell_off)
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1160,9 +1160,9 @@ __global__ void __launch_bounds__(256) k_dict_cells(const DictEntry* __restrict_
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (dict[mid].h < key) lo = mid + 1; else hi = mid; }
     cell_off[c] = lo;
 }
-__global__ void __launch_bounds__(256) k_narrow_u64(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out)
+static __global__ void __launch_bounds__(256) k_narrow_u64(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out)
 { const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i]; }
-__global__ void __launch_bounds__(256) k_diff_u32(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ cnt)
+static __global__ void __launch_bounds__(256) k_diff_u32(const uint32_t* __restrict__ off, uint32_t n, uint32_t* __restrict__ cnt)
 { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) cnt[i] = off[i + 1] - off[i]; }
 
 }  // namespace sn

@@ -9,8 +9,7 @@
 #include "sn_ingest.cuh"
 #include "sn_hbvdev.cuh"
 #include "sn_edict.cuh"
-#include "sn_formats.h"
-#include "sn_hbv.h"
+#include "sn_ctx.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -27,153 +26,9 @@
 
 using namespace sn;
 
-namespace {
-
-std::string g_create_error;
-
-// Device buffer that keeps its allocation across steps: alloc() only goes to cudaMalloc when
-// the request outgrows the capacity (cudaMalloc/cudaFree of multi-GB buffers cost
-// milliseconds each and serialise the device).
-struct DevBuf {
-    void* p = nullptr; size_t bytes = 0, cap = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; cap = 0; }
-    cudaError_t alloc(size_t n)
-    {
-        if (!n) n = 16;
-        if (p && cap >= n) { bytes = n; return cudaSuccess; }
-        release();
-        size_t want = n + n / 16;                      // a little headroom so step-to-step jitter does not reallocate
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { cudaGetLastError(); want = n; e = cudaMalloc(&p, want); }
-        if (e == cudaSuccess) { bytes = n; cap = want; }
-        return e;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-// pinned host buffer, kept across steps like DevBuf
-struct HostBuf {
-    void* p = nullptr; size_t cap = 0;
-    HostBuf() = default;
-    HostBuf(const HostBuf&) = delete; HostBuf& operator=(const HostBuf&) = delete;
-    ~HostBuf() { if (p) cudaFreeHost(p); }
-    cudaError_t alloc(size_t n)
-    {
-        if (!n) n = 64;
-        if (p && cap >= n) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(&p, n + n / 8);
-        if (e == cudaSuccess) cap = n + n / 8;
-        return e;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct Timer { cudaEvent_t a = nullptr, b = nullptr; bool used = false; };
-
-}  // namespace
-
-struct sn_ctx {
-    int device = 0, num_sms = 148;
-    cudaStream_t st = nullptr;
-    cudaStream_t st2 = nullptr;                 // copy stream of sn_load_reads_streamed
-    cudaEvent_t ev_copy[16] = {};
-    // work sn_load_reads_streamed already did under the copies; consumed by the next count call only
-    bool gl_ready = false; uint32_t gl_min_qual = 0; uint64_t gl_occ = 0; int hist_ready_bits = -1;
-    bool dsc_ready = false; uint32_t dsc_overflow = 0;      // run descriptors of the loaded reads under the current good lengths (k_msp_place)
-    std::string err;
-    uint64_t launches = 0;
-    std::map<std::string, Timer> timers;
-    std::map<std::string, double> host_ms;
-    sn_params params{7, 3, 2, 0};
-    sn_counts cnt{};
-    int stage = 0;       // 0 none, 1 reads, 2 counted, 3 edges, 4 hbv, 5 paths
-    bool reads_ok = false;   // reads are resident (a graph can also come from an edge file without any)
-
-    // reads
-    DevBuf bases, boff, len, quals, qoff, bc, pq, pqoff, goodlen;
-    bool have_bc = false, have_pq = false;
-    // dictionary
-    DevBuf dict, dboff;      // dictionary (bucket, hash, k-mer order) and its bucket offsets (2^dict_bits + 1)
-    int dict_bits = 4, dict_sub_bits = 0;
-    // edges (device) + host copy
-    DevBuf ebases, eoff, elen;
-    snh::Edges hedges;
-    // hbv
-    snh::Hbv hbv;
-    DevBuf d_fwd, d_rev, d_toleft, d_toright, d_src, d_from_start, d_from_v, d_from_e, d_to_start, d_to_v, d_to_e;
-    // paths
-    DevBuf plen, poffset, path_off, pedges;
-    std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
-    std::vector<uint64_t> pi_off, pi_ids; std::vector<int32_t> pi_countsb; bool pi_ready = false;     // paths index (writePathsIndex)
-    DevBuf counters;     // small scratch of u64 counters
-    std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
-    std::map<std::string, HostBuf> hpool;    // pinned staging, kept across steps
-    std::map<const void*, size_t> pinned;    // host vectors whose storage is page-locked (result arrays reused across steps)
-};
+std::string g_sn_create_error;
 
 namespace {
-
-// Result arrays live in std::vectors that keep their storage from step to step; their storage is
-// page-locked once (cudaHostRegister) so that the copies to and from them run at full PCIe speed
-// and asynchronously.  resize_pinned never lets a registered block be freed behind CUDA's back.
-template <class T> void resize_pinned(sn_ctx* c, std::vector<T>& v, size_t n)
-{
-    if (v.capacity() < n) {
-        auto it = c->pinned.find(v.data());
-        if (it != c->pinned.end()) { cudaHostUnregister(const_cast<void*>(it->first)); c->pinned.erase(it); }
-        std::vector<T>().swap(v);
-        v.reserve(n + n / 8 + 16);
-    }
-    v.resize(n);
-    if (v.capacity() && !c->pinned.count(v.data())) {
-        if (cudaHostRegister(v.data(), v.capacity() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) c->pinned[v.data()] = v.capacity() * sizeof(T);
-        else cudaGetLastError();                       // not fatal: the copies fall back to pageable memory
-    }
-}
-void unpin_all(sn_ctx* c) { for (auto& kv : c->pinned) cudaHostUnregister(const_cast<void*>(kv.first)); c->pinned.clear(); }
-
-int fail(sn_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
-
-#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
-    return fail(c, SN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
-#define KCHECK(name) do { ++c->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
-    return fail(c, SN_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); } while (0)
-
-void t_begin(sn_ctx* c, const char* name)
-{
-    Timer& t = c->timers[name];
-    if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
-    cudaEventRecord(t.a, c->st); t.used = false;
-}
-void t_end(sn_ctx* c, const char* name) { Timer& t = c->timers[name]; if (!t.a) return; cudaEventRecord(t.b, c->st); t.used = true; }
-
-inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
-
-// exclusive scan helper that owns its temporaries; out has n+1 entries; total returned through *total (host, after sync)
-int scan_u32(sn_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
-{
-    DevBuf& tmp = c->pool["scan_tmp"];
-    CU(tmp.alloc(scan_tmp_words(n) * 8 + 16));
-    exclusive_scan_u32_u64(in, n, out, tmp.as<uint64_t>(), c->st);
-    c->launches += n ? 3 : 0;
-    CU(cudaGetLastError());
-    if (total) { CU(cudaMemcpyAsync(total, out + n, 8, cudaMemcpyDeviceToHost, c->st)); }
-    CU(cudaStreamSynchronize(c->st));
-    return SN_OK;
-}
-
-int upload(sn_ctx* c, DevBuf& b, const void* src, size_t bytes, size_t pad = 0)
-{
-    CU(b.alloc(bytes + pad));
-    if (pad) CU(cudaMemsetAsync((char*)b.p + bytes, 0, pad, c->st));
-    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->st));
-    return SN_OK;
-}
 
 int load_common(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, const uint64_t* base_off, const uint32_t* len, const int32_t* bc)
 {
@@ -259,9 +114,10 @@ void sn_ctx_destroy(sn_ctx* c)
     for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
     if (c->st2) cudaStreamDestroy(c->st2);
     cudaStreamDestroy(c->st);
+    delete c->comm;
     delete c;
 }
-const char* sn_last_error(const sn_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+const char* sn_last_error(const sn_ctx* c) { return c ? c->err.c_str() : g_sn_create_error.c_str(); }
 uint64_t sn_kernel_launches(const sn_ctx* c) { return c ? c->launches : 0; }
 void* sn_stream(const sn_ctx* c) { return c ? (void*)c->st : nullptr; }
 double sn_stage_ms(const sn_ctx* c, const char* name)
@@ -451,7 +307,7 @@ int sn_save_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
     if (boff[n]) CU(cudaMemcpy(bases.data(), c->bases.p, boff[n], cudaMemcpyDeviceToHost));
     if (pqoff[n]) CU(cudaMemcpy(pq.data(), c->pq.p, pqoff[n], cudaMemcpyDeviceToHost));
     int r = sn_write_read_files(fastb, qualp, bci, n, bases.data(), boff.data(), len.data(), pq.data(), pqoff.data(), bc.data());
-    if (r) return fail(c, r, g_create_error);
+    if (r) return fail(c, r, g_sn_create_error);
     return SN_OK;
 }
 
@@ -482,15 +338,15 @@ int sn_load_read_files_bc(sn_ctx* c, const char* fastb, const char* qualp, const
 
 // ---------------------------------------------------------------------------
 // ---- pieces of the count stage (shared by the single-GPU call and the multi-GPU calls) ----
-static uint32_t mg_first_bucket(uint32_t owner, uint32_t nparts, int bits) { return (uint32_t)((((uint64_t)owner << bits) + nparts - 1) / nparts); }
-static int pick_bucket_bits(uint64_t n_occ)
+uint32_t sn_i_first_bucket(uint32_t owner, uint32_t nparts, int bits) { return (uint32_t)((((uint64_t)owner << bits) + nparts - 1) / nparts); }
+int sn_i_pick_bucket_bits(uint64_t n_occ)
 {
     int bits = msp_bucket_bits(n_occ);
     if (const char* e = getenv("SN_MSP_OCC")) { int t = atoi(e); if (t >= 64) { bits = 4; while (bits < 24 && (n_occ >> bits) > (uint64_t)t) ++bits; } }
     if (const char* e = getenv("SN_MSP_BITS")) { int b = atoi(e); if (b >= 1 && b <= 24) bits = b; }     // tests: few huge buckets force the split passes
     return bits;
 }
-static int count_set_params(sn_ctx* c, const sn_params* p)
+int sn_i_count_set_params(sn_ctx* c, const sn_params* p)
 {
     if (p) c->params = *p;
     if (c->params.min_bc > 2) return fail(c, SN_ERR_ARG, "min_bc > 2 is not supported (the reference pipeline fixes MIN_BC=2, 10X/DF.cc:140)");
@@ -498,7 +354,7 @@ static int count_set_params(sn_ctx* c, const sn_params* p)
     return SN_OK;
 }
 // a1: good lengths and the number of k-mer occurrences Kmerizer::map will emit
-static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
+int sn_i_count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
 {
     const uint64_t n = c->cnt.n_reads;
     if (c->gl_ready) {                           // computed under the copies of sn_load_reads_streamed (once: a repeated count recomputes)
@@ -532,7 +388,7 @@ static int count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
 }
 // a14 (MSP): cuts this context's reads into super-k-mers and groups them by minimizer bucket:
 // pool["sk_recs"] (32-byte records, bucket order) and pool["sk_off"] (2^bits + 1 record offsets).
-static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo = 0, uint32_t b_n = 0)
+int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, uint32_t b_n)
 {
     const uint64_t n = c->cnt.n_reads;
     const bool window = b_n != 0;                 // a count in several passes: only the buckets [b_lo, b_lo + b_n)
@@ -595,7 +451,7 @@ static int msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo 
 // bucket, see k_bucket_count).  The surviving k-mers land in `surv` ordered by (bucket, hash,
 // k-mer); surv_off[n_buckets + 1] = first survivor of every bucket.
 // `occ_bound` bounds the k-mer occurrences the records hold.
-static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound,
+int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound,
                             DevBuf& surv, DevBuf& surv_off, uint64_t* n_surv_out)
 {
     unsigned long long* occ = c->counters.as<unsigned long long>();        // [2] distinct, [3] scratch cursor
@@ -659,12 +515,12 @@ static int msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, u
 }
 // the surviving k-mers (bucket, hash, k-mer order) become the dictionary; `counts_or_off`: the bucket
 // offsets (is_offsets) or the per-bucket survivor counts of all 2^bits buckets
-static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bits, const uint32_t* counts_or_off, bool is_offsets)
+int sn_i_msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bits, const uint32_t* counts_or_off, bool is_offsets, uint32_t nb_window, uint64_t extra_entries)
 {
-    if (n_surv >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
-    const uint64_t nb = 1ull << bits;
+    if (n_surv + extra_entries >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 dictionary k-mers in one context");
+    const uint64_t nb = nb_window ? nb_window : 1ull << bits;      // buckets this table holds
     c->cnt.n_kmers = n_surv; c->dict_bits = bits;
-    CU(c->dict.alloc((size_t)n_surv * sizeof(DictEntry) + 64));
+    CU(c->dict.alloc((size_t)(n_surv + extra_entries) * sizeof(DictEntry) + 64));
     CU(c->dboff.alloc(4 * (nb + 1)));
     if (is_offsets) CU(cudaMemcpyAsync(c->dboff.p, counts_or_off, 4 * (nb + 1), cudaMemcpyDeviceToDevice, c->st));
     else {
@@ -681,7 +537,7 @@ static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int b
     }
     // lookup cells of ~32 entries: (bucket, top sub_bits of the hash)
     int sub = 0;
-    while (sub < 6 && bits + sub < 26 && (n_surv >> (bits + sub)) > 32) ++sub;
+    while (sub < 6 && (nb << sub) < (1ull << 26) && n_surv / (nb << sub) > 32) ++sub;
     c->dict_sub_bits = sub;
     if (sub) {
         DevBuf& cells = c->pool["dict_cells"];
@@ -691,6 +547,7 @@ static int msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int b
     }
     t_end(c, "make_dict");
     CU(cudaStreamSynchronize(c->st));
+    c->dict_b_lo = 0; c->dict_b_n = 0; c->ghost_cap = 0; c->dict_sharded = false;      // (the sharded path sets its window after this call)
     c->stage = 2;
     return SN_OK;
 }
@@ -709,7 +566,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     if (!n_reads || !bases || !base_off || !len || !pq || !pq_off) return fail(c, SN_ERR_ARG, "sn_load_reads_streamed: empty or NULL input");
     if (n_reads >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_load_reads: more than 2^32-1 reads per context");
     int r;
-    if ((r = count_set_params(c, p))) return r;
+    if ((r = sn_i_count_set_params(c, p))) return r;
     c->cnt = sn_counts{}; c->stage = 0; c->reads_ok = false; c->paths_on_host = false;
     c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
     c->cnt.n_reads = n_reads;
@@ -760,7 +617,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     CUB_(cudaMemcpyAsync(&h_bad, u32c, 4, cudaMemcpyDeviceToHost, c->st));
     CUB_(cudaStreamSynchronize(c->st));                             // the good lengths are done; the bases are still arriving
     if (h_bad) return bail(fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count"));
-    const int bits = pick_bucket_bits(h_occ);
+    const int bits = sn_i_pick_bucket_bits(h_occ);
     if (h_occ >= 3600000000ull) with_hist = 0;                     // counted in several passes: each pass has its own histogram
     const uint64_t nb = 1ull << bits;
     DevBuf &hist = c->pool["sk_hist"], &dsc = c->pool["sk_dsc"], &nruns = c->pool["sk_nruns"];
@@ -809,9 +666,9 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_count_kmers: no reads loaded");
     CU(cudaSetDevice(c->device));
     int r; uint64_t n_occ = 0, n_sk = 0;
-    if ((r = count_set_params(c, p))) return r;
-    if ((r = count_goodlen(c, &n_occ))) return r;
-    const int bits = pick_bucket_bits(n_occ);
+    if ((r = sn_i_count_set_params(c, p))) return r;
+    if ((r = sn_i_count_goodlen(c, &n_occ))) return r;
+    const int bits = sn_i_pick_bucket_bits(n_occ);
     // One pass holds < 2^32 k-mer occurrences (32-bit positions inside k_bucket_count's output) and its
     // super-k-mer records in HBM.  More occurrences than 3.6e9 are counted in several passes over
     // consecutive bucket ranges: every pass scans the resident reads again (0.25 B/base, cheap next to the
@@ -821,11 +678,11 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     if (passes > (1u << bits)) passes = 1u << bits;
     DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
     if (passes == 1) {
-        if (n_occ && (r = msp_partition(c, bits, &n_sk))) return r;
+        if (n_occ && (r = sn_i_msp_partition(c, bits, &n_sk))) return r;
         c->cnt.n_superkmers = n_sk;
         uint64_t n_surv = 0;
-        if ((r = msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, surv, surv_off, &n_surv))) return r;
-        return msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true);
+        if ((r = sn_i_msp_bucket_count(c, c->pool["sk_recs"].as<uint4>(), c->pool["sk_off"].as<uint64_t>(), 1u << bits, 1, n_occ, surv, surv_off, &n_surv))) return r;
+        return sn_i_msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true);
     }
     const uint64_t nb = 1ull << bits;
     DevBuf &all = c->pool["surv_all"], &all_cnt = c->pool["surv_all_cnt"];
@@ -833,9 +690,9 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     unsigned long long* occ = c->counters.as<unsigned long long>();
     uint64_t n_total = 0, n_dist = 0, n_sk_total = 0;
     for (uint32_t ps = 0; ps < passes; ++ps) {
-        const uint32_t b0 = mg_first_bucket(ps, passes, bits), b1 = mg_first_bucket(ps + 1, passes, bits);
+        const uint32_t b0 = sn_i_first_bucket(ps, passes, bits), b1 = sn_i_first_bucket(ps + 1, passes, bits);
         if (b1 == b0) continue;
-        if ((r = msp_partition(c, bits, &n_sk, b0, b1 - b0))) return r;
+        if ((r = sn_i_msp_partition(c, bits, &n_sk, b0, b1 - b0))) return r;
         n_sk_total += n_sk;
         DevBuf& recs = c->pool["sk_recs"];
         unsigned long long h_occ = 0;
@@ -845,7 +702,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         CU(cudaStreamSynchronize(c->st));
         if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "a count pass holds more than 2^32-1 k-mer occurrences (skewed buckets): raise SN_COUNT_PASSES");
         uint64_t n_surv = 0;
-        if ((r = msp_bucket_count(c, recs.as<uint4>(), c->pool["sk_off"].as<uint64_t>(), b1 - b0, 1, h_occ, surv, surv_off, &n_surv))) return r;
+        if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), c->pool["sk_off"].as<uint64_t>(), b1 - b0, 1, h_occ, surv, surv_off, &n_surv))) return r;
         n_dist += c->cnt.n_kmers_distinct;
         if (16 * (n_total + n_surv) > all.cap) {                   // grow the concatenation (keeps what it holds)
             DevBuf bigger;
@@ -861,7 +718,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         n_total += n_surv;
     }
     c->cnt.n_superkmers = n_sk_total;
-    r = msp_install_dict(c, all.as<uint4>(), n_total, bits, all_cnt.as<uint32_t>(), false);
+    r = sn_i_msp_install_dict(c, all.as<uint4>(), n_total, bits, all_cnt.as<uint32_t>(), false);
     c->cnt.n_kmers_distinct = n_dist;
     return r;
 }
@@ -878,8 +735,8 @@ int sn_mg_good_lengths(sn_ctx* c, const sn_params* p, uint64_t* n_occ)
     if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_good_lengths: no reads loaded");
     CU(cudaSetDevice(c->device));
     int r;
-    if ((r = count_set_params(c, p))) return r;
-    if ((r = count_goodlen(c, n_occ))) return r;
+    if ((r = sn_i_count_set_params(c, p))) return r;
+    if ((r = sn_i_count_goodlen(c, n_occ))) return r;
     if (*n_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences on one rank: shard the reads over more GPUs");
     return SN_OK;
 }
@@ -889,11 +746,11 @@ int sn_mg_partition(sn_ctx* c, int bits, uint32_t nparts, uint64_t* part_records
     if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition: no reads loaded");
     CU(cudaSetDevice(c->device));
     uint64_t n_sk = 0;
-    int r = msp_partition(c, bits, &n_sk);
+    int r = sn_i_msp_partition(c, bits, &n_sk);
     if (r) return r;
     const uint64_t* off = c->pool["sk_off"].as<uint64_t>();
     std::vector<uint64_t> cut(nparts + 1);
-    for (uint32_t o = 0; o <= nparts; ++o) CU(cudaMemcpyAsync(&cut[o], off + mg_first_bucket(o, nparts, bits), 8, cudaMemcpyDeviceToHost, c->st));
+    for (uint32_t o = 0; o <= nparts; ++o) CU(cudaMemcpyAsync(&cut[o], off + sn_i_first_bucket(o, nparts, bits), 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     for (uint32_t o = 0; o < nparts; ++o) part_records[o] = cut[o + 1] - cut[o];
     *dev_records = c->pool["sk_recs"].p;
@@ -937,7 +794,7 @@ int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t
     CU(cudaStreamSynchronize(c->st));
     uint64_t n_surv = 0;
     DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"], &scnt = c->pool["mg_surv_counts"];
-    if ((r = msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, surv, surv_off, &n_surv))) return r;
+    if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, surv, surv_off, &n_surv))) return r;
     CU(scnt.alloc(4ull * n_buckets));
     k_diff_u32<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(surv_off.as<uint32_t>(), n_buckets, scnt.as<uint32_t>());
     KCHECK("k_diff_u32");
@@ -968,7 +825,7 @@ int sn_mg_install_survivors(sn_ctx* c, uint64_t n_total, int bits)
     CU(cudaSetDevice(c->device));
     DevBuf &g = c->pool["surv_g"], &gc = c->pool["surv_gcnt"];
     if ((n_total && (!g.p || g.bytes < 16 * n_total)) || !gc.p || gc.bytes < (4ull << bits)) return fail(c, SN_ERR_STATE, "call sn_mg_survivor_buffer / sn_mg_bucket_count_buffer first");
-    return msp_install_dict(c, g.as<uint4>(), n_total, bits, gc.as<uint32_t>(), false);
+    return sn_i_msp_install_dict(c, g.as<uint4>(), n_total, bits, gc.as<uint32_t>(), false);
 }
 
 // ---------------------------------------------------------------------------
@@ -977,11 +834,15 @@ int sn_build_edges(sn_ctx* c)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 2) return fail(c, SN_ERR_STATE, "sn_build_edges: run sn_count_kmers first");
     CU(cudaSetDevice(c->device));
+    {   // the stop-indexed stage of the sharded path (sn_multi.cu) also runs on one rank; SN_EDGES2=0 keeps the first implementation for A/B runs
+        const char* e2 = getenv("SN_EDGES2");
+        if ((e2 && atoi(e2) != 0) || c->dict_sharded) return sn_i_build_edges2(c);
+    }
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
     if (!n) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
-    DictView dv; dv.tab = tab; dv.boff = c->dict_sub_bits ? c->pool["dict_cells"].as<uint32_t>() : c->dboff.as<uint32_t>(); dv.n = n; dv.bits = c->dict_bits; dv.sub_bits = c->dict_sub_bits;
+    const DictView dv = dict_view(c);
     t_begin(c, "prune");
     DevBuf& links = c->pool["links"];
     CU(links.alloc(8ull * n));
@@ -1370,7 +1231,7 @@ static int graph_from_edges(sn_ctx* c, const snf::Fastb& E)
         KCHECK("k_ed_emit");
     } else { CU(bcnt.alloc(4ull << bits)); CU(cudaMemsetAsync(bcnt.p, 0, 4ull << bits, c->st)); CU(surv.alloc(64)); }
     t_begin(c, "make_dict");
-    if ((r = msp_install_dict(c, surv.as<uint4>(), n_unique, bits, bcnt.as<uint32_t>(), false))) return r;
+    if ((r = sn_i_msp_install_dict(c, surv.as<uint4>(), n_unique, bits, bcnt.as<uint32_t>(), false))) return r;
     if (n_unique) {
         k_ed_set_loc<<<blocks_for(n_unique, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), loc.as<uint2>(), (uint32_t)n_unique);
         KCHECK("k_ed_set_loc");
@@ -1399,7 +1260,7 @@ int sn_path_reads(sn_ctx* c)
     if (!c->reads_ok) return fail(c, SN_ERR_STATE, "sn_path_reads: no reads loaded");
     CU(cudaSetDevice(c->device));
     const uint64_t n = c->cnt.n_reads;
-    DictView d; d.tab = c->dict.as<DictEntry>(); d.boff = c->dict_sub_bits ? c->pool["dict_cells"].as<uint32_t>() : c->dboff.as<uint32_t>(); d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits; d.sub_bits = c->dict_sub_bits;
+    const DictView d = dict_view(c);
     EdgeStore es; es.bases = c->ebases.as<uint8_t>(); es.off = c->eoff.as<uint64_t>(); es.len = c->elen.as<uint32_t>();
     HbvView h;
     h.fwd_xlat = c->d_fwd.as<int32_t>(); h.rev_xlat = c->d_rev.as<int32_t>();
@@ -1742,11 +1603,11 @@ int sn_write_read_files(const char* fastb, const char* qualp, const char* bci, u
     std::string err;
     if (fastb) {
         snf::Fastb fb; fb.var.assign(bases, bases + base_off[n]); fb.off.assign(base_off, base_off + n + 1); fb.len.assign(len, len + n);
-        if (!snf::write_fastb(fastb, fb, err)) { g_create_error = err; return SN_ERR_IO; }
+        if (!snf::write_fastb(fastb, fb, err)) { g_sn_create_error = err; return SN_ERR_IO; }
     }
     if (qualp) {
         snf::Qualp qp; qp.var.assign(pq, pq + pq_off[n]); qp.off.assign(pq_off, pq_off + n + 1);
-        if (!snf::write_qualp(qualp, qp, err)) { g_create_error = err; return SN_ERR_IO; }
+        if (!snf::write_qualp(qualp, qp, err)) { g_sn_create_error = err; return SN_ERR_IO; }
     }
     if (bci) {
         // inverse of the expansion in 10X/DF.cc:464-469: bci[b] = first read of barcode ordinal b
@@ -1754,11 +1615,11 @@ int sn_write_read_files(const char* fastb, const char* qualp, const char* bci, u
         int32_t cur = 0;
         for (uint64_t r = 0; r < n; ++r) {
             int32_t b = bc ? bc[r] : 0;
-            if (b < cur) { g_create_error = "barcode ordinals are not sorted"; return SN_ERR_DATA; }
+            if (b < cur) { g_sn_create_error = "barcode ordinals are not sorted"; return SN_ERR_DATA; }
             while (cur < b) { bi.push_back((int64_t)r); ++cur; }
         }
         bi.push_back((int64_t)n);
-        if (!snf::write_bci(bci, bi, err)) { g_create_error = err; return SN_ERR_IO; }
+        if (!snf::write_bci(bci, bi, err)) { g_sn_create_error = err; return SN_ERR_IO; }
     }
     return SN_OK;
 }

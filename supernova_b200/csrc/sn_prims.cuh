@@ -106,7 +106,7 @@ __device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t* to
     return r;
 }
 
-__global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ tile_sums)
+static __global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ tile_sums)
 {
     __shared__ uint64_t sm[33];
     uint64_t base = (uint64_t)blockIdx.x * SN_SCAN_TILE;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_tile_sums(const uint32
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 // single block: exclusive scan of tile sums in place; total written to tile_sums[ntiles]
-__global__ void __launch_bounds__(1024) k_scan_spine(uint64_t* tile_sums, uint64_t ntiles)
+static __global__ void __launch_bounds__(1024) k_scan_spine(uint64_t* tile_sums, uint64_t ntiles)
 {
     __shared__ uint64_t sm[33];
     __shared__ uint64_t carry;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(1024) k_scan_spine(uint64_t* tile_sums, uint64
     }
     if (threadIdx.x == 0) tile_sums[ntiles] = carry;
 }
-__global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ out)
+static __global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_sums, uint64_t* __restrict__ out)
 {
     __shared__ uint64_t sm[33];
     uint64_t base = (uint64_t)blockIdx.x * SN_SCAN_TILE + (uint64_t)threadIdx.x * SN_SCAN_ITEMS;   // blocked
@@ -180,7 +180,7 @@ __device__ __forceinline__ uint32_t rs_digit(const uint4& k, int pass)
 // all digit histograms in one pass over the records (they are invariant under the
 // permutations the later passes apply).  hist[pass*256 + digit], u32 counts.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist, int arg)
+static __global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist, int arg)
 {
     constexpr int P = RsMode<MODE>::PASSES;
     __shared__ uint32_t sh[P * 256];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) k_rs_histogram(const uint4* __restrict__ 
     for (int i = threadIdx.x; i < P * 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 // exclusive scan of each pass's 256 bins, in place (one block of 256 threads per pass)
-__global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
+static __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t* hist)
 {
     __shared__ uint32_t sm[256];
     uint32_t* h = hist + blockIdx.x * 256;
@@ -229,7 +229,7 @@ struct RsSmem {
 
 // One digit pass: read each record once, write it once.
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+static __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, int pass,
              const uint32_t* __restrict__ ghist /* exclusive starts, this pass */, uint64_t* status, uint32_t* tile_counter)
 {
@@ -273,6 +273,7 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
         if (lane == leader) { base = S.warp_cnt[warp][d]; S.warp_cnt[warp][d] = base + __popc(peers); }
         base = __shfl_sync(SN_FULL, base, leader);
         dr[j] = d | ((base + __popc(peers & lanemask_lt())) << 8);
+        __syncwarp();                                // the next item's leader may be another lane reading the same counter
     }
     __syncthreads();
     // thread d (< 256): exclusive scan of digit d over the warps -> tile total, published at once

@@ -24,7 +24,7 @@ struct Sim {
     snh::Edges edges;
     snh::Hbv hbv;
     std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
-    DictView view() const { DictView d; d.tab = tab.data(); d.boff = boff.data(); d.n = (uint32_t)tab.size(); d.bits = bits; d.sub_bits = 0; return d; }
+    DictView view() const { DictView d; d.tab = tab.data(); d.boff = boff.data(); d.n = (uint32_t)tab.size(); d.bits = bits; d.sub_bits = 0; d.b_lo = 0; d.b_n = 1u << bits; d.g_cap = 0; return d; }
 };
 
 extern "C" {

@@ -30,7 +30,7 @@ def _run(sb, name, wd, **prm):
     return ctx, o, (pb, boff, ln, pq, pqoff, bc)
 
 
-def _check(sb, ctx, o, wd, packed, extra):
+def _check(sb, ctx, o, wd, packed, extra, overflow_expected=False):
     km, ok = ctx.kmers(), o.kmers()
     assert km.shape[0] == ok.shape[0]
     assert np.array_equal(km[:, :3], ok[:, :3])
@@ -42,9 +42,24 @@ def _check(sb, ctx, o, wd, packed, extra):
         rd = wd + "/ref"
         os.makedirs(rd)
         sb.write_read_files(rd + "/reads", *packed)
-        refrun.run_probe(rd, extra=extra)
+        _, log = refrun.run_probe(rd, extra=extra)
         ref = refrun.read_kvec(rd + "/kmers.kvec")
         mine = np.stack([km[:, 0], km[:, 1], km[:, 2], km[:, 3] & 0xFFFFFF, km[:, 3] >> 24], axis=1)
+        if "buffer overflows" in log:
+            # on a MapReduce buffer overflow the reference pre-summarises groups and LOSES their
+            # per-occurrence barcodes (BuildReadQGraph48.cc:183-184, MapReduceEngine.h:538-541), so it drops k-mers
+            # that pass the barcode rule -- how many depends on its thread count.  What it keeps must be ours, with
+            # the same count and context; the oracle above (no overflow mode) pins the rest.
+            assert overflow_expected, "unexpected MapReduce buffer overflow in the reference run"
+            key = lambda a: (a[:, 0].astype(np.uint64) << np.uint64(32) | a[:, 1].astype(np.uint64)), a[:, 2]
+            mh, ml = key(mine); rh, rl = key(ref)
+            mv = np.empty(len(mine), dtype=[("h", np.uint64), ("l", np.uint32)]); mv["h"], mv["l"] = mh, ml
+            rv = np.empty(len(ref), dtype=[("h", np.uint64), ("l", np.uint32)]); rv["h"], rv["l"] = rh, rl
+            at = np.searchsorted(mv, rv)
+            assert bool((at < len(mv)).all()) and np.array_equal(mv[at], rv)
+            assert np.array_equal(mine[at, 3:], ref[:, 3:])
+            assert 0 < len(ref) <= len(mine)
+            return
         assert np.array_equal(mine, ref)
         for f in ("a.hbv", "tmp.paths", "stats/histogram_kmer_count.json"):
             assert open(wd + "/" + f, "rb").read() == open(rd + "/" + f, "rb").read(), f
@@ -67,8 +82,10 @@ def test_ign_bc_below(sb, name, ign, tmp_path):
         ctx.close()
 
 
-@pytest.mark.parametrize("prm", [dict(min_qual=10, min_freq=2, min_bc=1), dict(min_qual=2, min_freq=5, min_bc=0), dict(min_qual=20, min_freq=1, min_bc=2)])
+@pytest.mark.parametrize("prm", [dict(min_qual=10, min_freq=2, min_bc=1), dict(min_qual=2, min_freq=5, min_bc=0), dict(min_qual=20, min_freq=2, min_bc=2), dict(min_qual=20, min_freq=1, min_bc=0)])
 def test_other_thresholds_against_reference(sb, prm, tmp_path):
+    # (MIN_FREQ=1 together with the barcode rule is left out: the reference binary itself dies on it with
+    # ForceAssert(result) in EdgeBuilder::lookup, BuildReadQGraph48.cc:470-474)
     wd = str(tmp_path)
     ctx, o, packed = _run(sb, "stress3", wd, **prm)
     try:
@@ -87,7 +104,7 @@ def test_count_saturates_at_24_bits(sb, tmp_path):
         assert km[0, 0] == 0 and km[0, 1] == 0 and km[0, 2] == 0            # A^48 sorts first
         assert (km[0, 3] & 0xFFFFFF) == 0xFFFFFF
         assert ctx.counts()["n_kmer_occurrences"] > (1 << 24)
-        _check(sb, ctx, o, wd, packed, ())
+        _check(sb, ctx, o, wd, packed, (), overflow_expected=True)
     finally:
         ctx.close()
 

@@ -11,7 +11,7 @@ EXE=supernova_b200/sn_build_graph
 $EXE HEAD=$D/in/reads OUT=$D/plain INDEX=True > $D/plain.log 2>&1 || { echo "plain run failed"; cat $D/plain.log; exit 1; }
 for tool in memcheck racecheck synccheck; do
   case $tool in memcheck) out=$D/mem;; racecheck) out=$D/race;; synccheck) out=$D/sync;; esac
-  /usr/bin/time -f "%e s" timeout 600 compute-sanitizer --tool $tool --print-limit 20 $EXE HEAD=$D/in/reads OUT=$out INDEX=True > gpurun_out/${TAG}_sanitize_$tool.log 2>&1
+  timeout 600 compute-sanitizer --tool $tool --print-limit 20 $EXE HEAD=$D/in/reads OUT=$out INDEX=True > gpurun_out/${TAG}_sanitize_$tool.log 2>&1
   echo "rc=$? tool=$tool workload=$WL/$DIV $(cat $D/meta.json)" >> gpurun_out/${TAG}_sanitize_$tool.log
   same=yes; for f in a.hbv tmp.paths a.paths.inv; do cmp -s $D/plain/$f $out/$f || same=no; done
   echo "outputs identical to the plain run: $same" >> gpurun_out/${TAG}_sanitize_$tool.log
