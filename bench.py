@@ -91,12 +91,15 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def gen_workload(name, rank, scale_div=1):
+def gen_workload(name, rank, scale_div=1, genome_mult=1, workers=None):
     from supernova_b200 import synth
     G, pairs, nbc, seed = WORKLOADS[name]
     G, pairs, nbc = G // scale_div, pairs // scale_div, max(2, nbc // scale_div)
-    workers = min(os.cpu_count() or 1, 32)
-    # ranks > 0 draw different read pairs from the same genome (weak scaling: fixed work per GPU)
+    workers = workers or min(os.cpu_count() or 1, 32)
+    # Weak scaling: fixed work per GPU.  genome_mult = N (default with N ranks): the genome grows with the job (G x N at
+    # the same coverage: BASELINE configs 3-5 are bigger GENOMES, not deeper ones), every rank draws its own pairs from
+    # it.  genome_mult = 1: every rank draws different pairs from the SAME genome (coverage grows with N).
+    G *= genome_mult
     b, q, bc, ids = synth.make_reads(G, pairs, nbc, seed, workers=workers, shard=rank)
     n, L = b.shape
     off = np.arange(n + 1, dtype=np.uint64) * L
@@ -247,6 +250,25 @@ def parity_check(sb, ctx, run_path, dist, rank, world):
         if hashlib.md5(digests.paths_file_bytes(offs, poff_all, edges)).hexdigest() != gold["tmp.paths"]:
             bad.append("tmp.paths (ranks concatenated)")
     if dist is not None:
+        # the same once more without ReadPaths: the k-mer table then STAYS sharded -- the shards' digests add up
+        run_path(False)
+        km = ctx.kmers()
+        d = digests.kmer_digest(km[:, 0], km[:, 1], km[:, 2], km[:, 3])
+        parts = [None] * world
+        dist.all_gather_object(parts, (d, bool(ctx.dict_is_sharded())))
+        tot = {"n": sum(p[0]["n"] for p in parts), "sum": "%016x" % (sum(int(p[0]["sum"], 16) for p in parts) & (2 ** 64 - 1)), "xor": "%016x" % 0}
+        x = 0
+        for p in parts:
+            x ^= int(p[0]["xor"], 16)
+        tot["xor"] = "%016x" % x
+        if not all(p[1] for p in parts):
+            bad.append(f"rank {rank}: the dictionary is not sharded")
+        elif tot != gold["kmers"]:
+            bad.append("sharded k-mer table (digests of the shards combined)")
+        ctx.write_hbv(wd2 := tempfile.mkdtemp(prefix="sn_chk_") + "/a.hbv")
+        if digests.file_md5(wd2) != gold["a.hbv"]:
+            bad.append(f"rank {rank}: a.hbv (sharded run)")
+        os.remove(wd2); os.rmdir(os.path.dirname(wd2))
         allbad = [None] * world
         dist.all_gather_object(allbad, bad)
         bad = [x for b in allbad for x in b]
@@ -265,6 +287,7 @@ def main():
     ap.add_argument("--no-paths", action="store_true", help="skip the extra ReadPath-inclusive measurement")
     ap.add_argument("--no-ingest", action="store_true", help="skip the extra device-ingest (FASTQ text -> reads) measurement")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check leg (mid set against the reference's golden digests)")
+    ap.add_argument("--same-genome", action="store_true", help="N > 1: every rank samples the same genome (coverage grows with N) instead of a genome N times as big")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -285,7 +308,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- inputs: synthetic reads in the reference's in-memory layout, pinned ----------------
-    codes, quals, off, bc, meta = gen_workload(args.workload, rank)
+    genome_mult = 1 if (world == 1 or args.same_genome) else world
+    codes, quals, off, bc, meta = gen_workload(args.workload, rank, genome_mult=genome_mult, workers=max(2, min(os.cpu_count() or 1, 32) // world))
     if world > 1:
         bc = np.where(bc > 0, bc + rank * meta["n_bc"], 0).astype(np.int32)     # barcode ordinals are global across shards
     n_bases = int(codes.size)
@@ -419,7 +443,8 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {meta['pairs']} pairs x 2 x {meta['read_len']} bp per GPU, {meta['G']} bp diploid genome, seed {meta['seed']}",
                        "K": 48, "min_qual": 7, "min_freq": 3, "min_bc": 2, "gbp_per_gpu": gbp,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks: reads sharded, super-k-mers routed by minimizer bucket range with one NCCL alltoallv, surviving k-mers allgathered, graph replicated",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks, collectives issued by the C++ host on NCCL: reads sharded, super-k-mers routed by minimizer bucket range with one alltoallv, dictionary sharded by bucket range (ghost exchange for neighbours on other ranks), unipath chains stitched over the gathered stop table, edge bases by all-reduce, HBV on every rank (numbering split over the ranks)",
+                       "weak_scaling": "1 GPU" if world == 1 else (f"every rank samples the same {meta['G']} bp genome: coverage x{world}" if args.same_genome else f"genome x{world} ({meta['G']} bp) at the single-GPU coverage: each rank brings {meta['pairs']} pairs of it"),
                        "l2": "inputs per step (%.2f GB of packed reads, %.2f GB of super-k-mer records) are larger than L2" % (h2d_bytes / 1e9, 32 * counts["n_superkmers"] / 1e9)},
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stage_ms": stage, "counts": counts}

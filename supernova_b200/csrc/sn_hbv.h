@@ -49,8 +49,10 @@ struct HbvComponents {
 // n_vert, src, to_left, to_right, fwd, rev
 // `layout` (or nullptr): the records are laid out along the graph (sn_hbvdev.cuh, k_lay_*): record layout[x] is
 // item x, its lists hold record indices and its pad the item
+// `part` of `n_parts` (multi-GPU): only every n_parts-th work unit is numbered here; out.src / to_left / to_right must come in
+// zeroed, and what other parts number stays 0 (fwd / rev included), so the parts' arrays ADD UP to the complete ones
 void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads,
-                const uint32_t* layout = nullptr);
+                const uint32_t* layout = nullptr, unsigned part = 0, unsigned n_parts = 1);
 #ifdef SN_HOSTSIM
 // host-only construction of the whole HBV: exists in tests/hostsim only (the product library is built without it)
 void build_hbv(const Edges& edges, Hbv& out);

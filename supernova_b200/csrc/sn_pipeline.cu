@@ -1112,7 +1112,15 @@ int sn_build_hbv(sn_ctx* c)
         resize_pinned(c, Hn.src, tot_h); resize_pinned(c, Hn.to_left, tot_h); resize_pinned(c, Hn.to_right, tot_h);
         resize_pinned(c, Hn.fwd, nE); resize_pinned(c, Hn.rev, nE);
     }
-    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, hbv_threads, layout); }
+    // several ranks (sn_multi.cu): the graph is the same on all of them, so every rank numbers 1/N of the work units
+    // (components carry their final id bases) and the arrays are summed below, on the device, by one all-reduce each
+    const unsigned n_parts = c->comm && c->comm->n > 1 ? (unsigned)c->comm->n : 1u, part = n_parts > 1 ? (unsigned)c->comm->rank : 0u;
+    if (n_parts > 1) {
+        snh::Hbv& Hn = c->hbv;
+        memset(Hn.src.data(), 0, 4 * tot_h); memset(Hn.to_left.data(), 0, 4 * tot_h); memset(Hn.to_right.data(), 0, 4 * tot_h);
+    }
+    const unsigned nthreads = n_parts > 1 ? std::max(2u, hbv_threads / n_parts) : hbv_threads;      // (the ranks of one box share its cores)
+    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, nthreads, layout, part, n_parts); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     snh::Hbv& H = c->hbv;
@@ -1126,6 +1134,14 @@ int sn_build_hbv(sn_ctx* c)
     if ((r = upload(c, c->d_toleft, H.to_left.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_toright, H.to_right.data(), 4 * nH, 16))) return r;
     if ((r = upload(c, c->d_src, H.src.data(), 4 * nH, 16))) return r;
+    if (n_parts > 1) {
+        struct { DevBuf* d; void* h; size_t n; } parts[5] = {{&c->d_fwd, H.fwd.data(), nE}, {&c->d_rev, H.rev.data(), nE}, {&c->d_toleft, H.to_left.data(), nH},
+                                                              {&c->d_toright, H.to_right.data(), nH}, {&c->d_src, H.src.data(), nH}};
+        for (auto& q : parts) {
+            if (c->comm->allreduce_sum(q.d->p, q.n, 4, c->st)) return fail(c, SN_ERR_CUDA, "allreduce (HBV numbering): " + c->comm->err);
+            CU(cudaMemcpyAsync(q.h, q.d->p, 4 * q.n, cudaMemcpyDeviceToHost, c->st));
+        }
+    }
     CU(c->d_from_start.alloc(4ull * (nV + 1) + 16)); CU(c->d_to_start.alloc(4ull * (nV + 1) + 16));
     CU(c->d_from_v.alloc(4 * nH + 16)); CU(c->d_from_e.alloc(4 * nH + 16)); CU(c->d_to_v.alloc(4 * nH + 16)); CU(c->d_to_e.alloc(4 * nH + 16));
     DevBuf &ra = c->pool["hbv_csr_a"], &rb = c->pool["hbv_csr_b"], &rs = c->pool["hbv_csr_s"], &dinv = c->pool["hbv_inv"];

@@ -1,19 +1,18 @@
-"""Multi-GPU driver of the hot path: one process per GPU (torchrun), `torch.distributed` for
-the two collectives SURVEY.md §8(e) asks for.
+"""Multi-GPU launcher glue: one process per GPU (torchrun).  The data path is csrc/sn_multi.cu -- the C++ host issues
+every collective on NCCL (sn_comm.cu); `torch.distributed` is used here only to hand the NCCL unique id to the ranks
+(and by bench.py for its barrier and the max-over-ranks of the timings).
 
     rank r holds 1/N of the reads
-    1. good lengths; the k-mer occurrences of all ranks fix the number of minimizer buckets  [allreduce of one number]
-    2. super-k-mer records of the local reads in bucket order (MSP)                          [device]
-    3. ONE alltoallv routes every record to the owner of its bucket,
-       owner(bucket) = bucket * N >> bits (plus the per-bucket counts of the same ranges)    [NCCL / NVLink]
-    4. owner counts and filters its buckets -> its surviving k-mers, bucket order             [device]
-    5. ONE allgather of the survivors (+ per-bucket counts): rank order is bucket order, so the
-       gathered k-mers ARE the dictionary                                                    [NCCL / NVLink]
-    6. prune / unipath edges / HBV replicated on every rank; ReadPaths of the local reads
+    1. good lengths; the k-mer occurrences of all ranks fix the number of minimizer buckets
+    2. super-k-mer records of the local reads in bucket order (MSP)
+    3. ONE alltoallv routes every record to the owner of its bucket, owner(bucket) = bucket * N >> bits
+    4. owner counts and filters its buckets -> its shard of the dictionary (it STAYS sharded)
+    5. neighbours on other ranks: ghost query/answer exchange; recomputeAdjacencies; links; chains cut at rank borders
+    6. the stop table of all ranks is gathered, every rank derives all edge lengths / ids / offsets; bases by all-reduce
+    7. HyperBasevector on every rank; ReadPaths of the local reads (the finished k-mer table is gathered for them)
 
-A super-k-mer record is 32 bytes for ~14 k-mers, so the exchange moves ~2.3 bytes per k-mer
-occurrence (a k-mer record would be 16).  The exchange helpers are backend agnostic (NCCL on
-GPUs, gloo on CPU tensors in the tests).
+The helpers below (bucket ownership, exchange with uneven sizes) are the numpy/torch twins of the C++ logic, used by the
+world-size-2 gloo tests on CPU (tests/test_multi_gloo.py).
 """
 from __future__ import annotations
 
@@ -96,49 +95,27 @@ def gather_slices(dist, local, full, sizes, words):
         off += n
 
 
-def build_distributed(ctx, dist, device, params=None, with_paths=False):
-    """Runs the hot path for this rank's context; returns the per-rank counts dict."""
-    from .api import Params
-    params = params or Params()
+def init_comm(ctx, dist, device):
+    """One NCCL communicator per context, created by the library itself (csrc/sn_comm.cu: ncclCommInitRank): rank 0
+    makes the unique id, `torch.distributed` only carries those 128 bytes to the other ranks."""
+    if getattr(ctx, "_comm_world", None) == dist.get_world_size():
+        return
+    from .api import nccl_unique_id
     n, rank = dist.get_world_size(), dist.get_rank()
-    # 1. good lengths; global number of k-mer occurrences -> bucket bits (equal on every rank)
-    occ = torch.tensor([ctx.mg_good_lengths(params)], dtype=torch.int64, device=device)
-    dist.all_reduce(occ)
-    bits = bucket_bits(int(occ.item()))
-    while (1 << bits) < n:
-        bits += 1
-    # 2. super-k-mers of the local reads, bucket order
-    send_counts, rec_ptr, cnt_ptr = ctx.mg_partition(bits, n)
-    fb = [first_bucket(o, n, bits) for o in range(n + 1)]
-    nbl = fb[rank + 1] - fb[rank]
-    # 3. the alltoallv (records + the per-bucket counts of the same bucket ranges)
-    recv_counts = exchange_counts(dist, send_counts, device)
-    n_send, n_recv = sum(send_counts), sum(recv_counts)
-    send_t = dev_tensor(rec_ptr, n_send * SK_WORDS, device)
-    recv_t = dev_tensor(ctx.mg_recv_records(n_recv), n_recv * SK_WORDS, device)
-    exchange_records(dist, send_t, send_counts, recv_t, recv_counts, SK_WORDS)
-    cnt_send = dev_tensor(cnt_ptr, 1 << bits, device)
-    cnt_recv = dev_tensor(ctx.mg_recv_counts(n * nbl), n * nbl, device)
-    dist.all_to_all_single(cnt_recv, cnt_send, output_split_sizes=[nbl] * n, input_split_sizes=[fb[o + 1] - fb[o] for o in range(n)])
-    torch.cuda.synchronize(device)
-    # 4. count + filter of this rank's buckets
-    n_s, surv_ptr, scnt_ptr = ctx.mg_count_received(n, nbl, n_recv)
-    # 5. the allgather of the surviving k-mers
-    sizes_t = torch.zeros(n, dtype=torch.int64, device=device)
-    sizes_t[rank] = n_s
-    dist.all_reduce(sizes_t)
-    sizes = [int(x) for x in sizes_t.tolist()]
-    total = sum(sizes)
-    full_t = dev_tensor(ctx.mg_survivor_buffer(total), total * SURV_WORDS, device)
-    local_t = dev_tensor(surv_ptr, n_s * SURV_WORDS, device)
-    gather_slices(dist, local_t, full_t, sizes, SURV_WORDS)
-    gcnt_t = dev_tensor(ctx.mg_bucket_count_buffer(bits), 1 << bits, device)
-    gather_slices(dist, dev_tensor(scnt_ptr, nbl, device), gcnt_t, [fb[o + 1] - fb[o] for o in range(n)], 1)
-    torch.cuda.synchronize(device)
-    ctx.mg_install_survivors(total, bits)
-    # 6. the graph, replicated
-    ctx.build_edges()
-    ctx.build_hbv()
-    if with_paths:
-        ctx.path_reads()
-    return dict(bits=bits, n_send=n_send, n_recv=n_recv, survivors=n_s, total=total)
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(uid, src=0)
+    ctx.comm_init_nccl(rank, n, bytes(uid.cpu().numpy().tobytes()))
+    ctx._comm_world = n
+
+
+def build_distributed(ctx, dist, device, params=None, with_paths=False):
+    """The hot path for this rank's context over all ranks: sn_mg_build_graph (csrc/sn_multi.cu) -- every collective
+    (the alltoallv of super-k-mer records, the ghost query/answer exchanges, the gathers of the stop table, the
+    all-reduce of the edge bases) is issued by the C++ host on NCCL; nothing of the data path runs through Python."""
+    from .api import Params
+    init_comm(ctx, dist, device)
+    ctx.mg_build_graph(params or Params(), with_paths=with_paths)
+    c = ctx.counts()
+    return dict(sharded=ctx.dict_is_sharded(), n_kmers_local=c["n_kmers"], n_edges=c["n_edges"])
