@@ -31,7 +31,8 @@ __device__ __forceinline__ uint32_t bucket_owner(uint32_t bucket, uint32_t n_ran
 // ghost table (once: equal k-mers meet in the same slot).  Insertion is claim (CAS on the state) / write / fence /
 // publish; a lane that finds a slot being written looks again in the next round, and the rounds of a warp are
 // convergent, so no lane ever spins on a lane of its own warp.
-static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, DictView d, uint32_t n_ranks, uint32_t* n_ghosts, uint32_t* overflow)
+static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, DictView d, uint32_t n_ranks, uint32_t* n_ghosts, uint32_t* overflow,
+                                                              uint32_t* __restrict__ glist /* g_cap / 4 * 3 + 1: the slots taken, in no particular order */, uint32_t* __restrict__ per_owner)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < d.n;
@@ -62,7 +63,8 @@ static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, Di
                     e->w0 = q.w0; e->w1 = q.w1; e->w2 = q.w2; e->h = h; e->cc = owner; e->edge = SN_NULL_EDGE; e->ctx = 0;
                     __threadfence();
                     *reinterpret_cast<volatile uint32_t*>(&e->off) = GH_PENDING;
-                    if (atomicAdd(n_ghosts, 1u) + 1u > (d.g_cap / 4u) * 3u) *overflow = 1u;
+                    const uint32_t at = atomicAdd(n_ghosts, 1u);
+                    if (at >= (d.g_cap / 4u) * 3u) *overflow = 1u; else { glist[at] = slot; atomicAdd(&per_owner[owner], 1u); }
                     have = false;
                 }                                               // (lost the race: the slot is looked at again)
             } else if (st != GH_WRITING) {
@@ -75,16 +77,13 @@ static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, Di
     }
 }
 // ---- ghosts: queries grouped by owner -----------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) k_ghost_count(const DictEntry* __restrict__ gh, uint32_t cap, uint32_t* __restrict__ cnt)
-{
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < cap && gh[s].off == GH_PENDING) atomicAdd(&cnt[gh[s].cc], 1u);
-}
-static __global__ void __launch_bounds__(256) k_ghost_fill(const DictEntry* __restrict__ gh, uint32_t cap, const uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
+static __global__ void __launch_bounds__(256) k_ghost_fill(const DictEntry* __restrict__ gh, const uint32_t* __restrict__ glist, uint32_t n_ghosts,
+                                                           const uint32_t* __restrict__ base, uint32_t* __restrict__ cursor,
                                                            uint32_t* __restrict__ qk /* 3 words per query */, uint32_t* __restrict__ qslot)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= cap || gh[s].off != GH_PENDING) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ghosts) return;
+    const uint32_t s = glist[t];
     const DictEntry e = gh[s];
     const uint32_t p = base[e.cc] + atomicAdd(&cursor[e.cc], 1u);
     qk[3 * p] = e.w0; qk[3 * p + 1] = e.w1; qk[3 * p + 2] = e.w2; qslot[p] = s;

@@ -199,7 +199,7 @@ static void bfs_items(const ItemRec* rec, const GroupRec* groups, NumberState& s
 // edge id of every component, so the components are numbered independently, in parallel, with
 // their final ids.
 void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* groups, uint64_t nV_in, uint64_t nE, Hbv& H, unsigned threads, const uint32_t* layout,
-                unsigned part, unsigned n_parts)
+                unsigned part, unsigned n_parts, uint64_t min_items)
 {
     const uint64_t nH = C.n_comp ? C.base_e[C.n_comp] : 0, nV = C.n_comp ? C.base_v[C.n_comp] : 0;
     if (nV != nV_in) throw std::runtime_error("HBV: component vertex counts do not add up");
@@ -237,6 +237,7 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
                 if (u >= n_units || bad.load()) break;
                 if (n_parts > 1 && u % n_parts != part) continue;          // another rank numbers this unit (ids are final: the results add up)
                 for (uint64_t c = unit_start[u]; c < unit_start[u + 1]; ++c) {
+                    if (C.base_e[c + 1] - C.base_e[c] < min_items) continue;           // numbered on the device (k_hbv_number_small)
                     int32_t nextV = (int32_t)C.base_v[c]; uint32_t nh = (uint32_t)C.base_e[c];
                     const uint32_t start = layout ? layout[C.start_item[c]] : C.start_item[c];
                     if (C.base_e[c + 1] - C.base_e[c] >= 32768 && threads > 1) {
@@ -279,7 +280,7 @@ void number_hbv(const HbvComponents& C, const ItemRec* items, const GroupRec* gr
         }
     });
     // one part of several: what the other parts number stays 0, so that the parts' arrays add up to the whole
-    if (n_parts > 1) parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { if (H.fwd[e] < 0) H.fwd[e] = 0; if (H.rev[e] < 0) H.rev[e] = 0; } });
+    if (n_parts > 1 || min_items > 0) parallel_ranges(nE, [&](uint64_t e0, uint64_t e1) { for (uint64_t e = e0; e < e1; ++e) { if (H.fwd[e] < 0) H.fwd[e] = 0; if (H.rev[e] < 0) H.rev[e] = 0; } });
 }
 
 #ifdef SN_HOSTSIM

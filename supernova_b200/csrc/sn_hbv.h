@@ -52,7 +52,8 @@ struct HbvComponents {
 // `part` of `n_parts` (multi-GPU): only every n_parts-th work unit is numbered here; out.src / to_left / to_right must come in
 // zeroed, and what other parts number stays 0 (fwd / rev included), so the parts' arrays ADD UP to the complete ones
 void number_hbv(const HbvComponents& comps, const ItemRec* items, const GroupRec* groups, uint64_t n_vertices, uint64_t n_unipaths, Hbv& out, unsigned threads,
-                const uint32_t* layout = nullptr, unsigned part = 0, unsigned n_parts = 1);
+                const uint32_t* layout = nullptr, unsigned part = 0, unsigned n_parts = 1, uint64_t min_items = 0);
+// (min_items: components with fewer oriented edges are skipped -- the device numbered them -- and read as 0 like another part's)
 #ifdef SN_HOSTSIM
 // host-only construction of the whole HBV: exists in tests/hostsim only (the product library is built without it)
 void build_hbv(const Edges& edges, Hbv& out);

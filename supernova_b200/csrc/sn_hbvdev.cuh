@@ -193,6 +193,73 @@ static __global__ void __launch_bounds__(256) k_hbv_compgather(const uint4* __re
     cv[i] = cnt_v[r.w]; ce[i] = cnt_e[r.w];
 }
 
+// ---- the FIFO numbering (HBVBuilder::processQueue, HBVFromEdges.cc:199-228) of the SMALL components on the device --------
+// A component is numbered by a sequential breadth-first traversal, and the components carry their final id bases, so
+// they are independent: one thread per component runs the traversal over the item records (its queue in local memory).
+// A sparsely covered genome is 10^5-10^6 components of a few edges each -- all of them take this path and nothing of the
+// numbering touches the host.  Components above SN_HBV_GPU_MAX oriented edges (a well-covered genome: one giant
+// component per strand) are left to the host loop (sn_hbv.cpp), which is then the faster of the two.
+#define SN_HBV_GPU_MAX 512
+static __global__ void __launch_bounds__(64) k_hbv_number_small(const snh::ItemRec* __restrict__ rec, const snh::GroupRec* __restrict__ groups, uint32_t n_comp,
+                                                                const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ce,
+                                                                const uint64_t* __restrict__ basev, const uint64_t* __restrict__ basee, uint32_t max_items,
+                                                                uint8_t* seen /* n_items, zeroed */, uint8_t* vbits /* n_vertices, zeroed */, int32_t* vid,
+                                                                uint32_t* src, int32_t* to_left, int32_t* to_right, int32_t* fwd, int32_t* rev,
+                                                                uint32_t* n_big, uint32_t* err)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_comp) return;
+    const uint32_t size = ce[c];
+    if (size > max_items) { atomicAdd(n_big, 1u); return; }
+    uint32_t Q[SN_HBV_GPU_MAX];
+    uint32_t qh = 0, qt = 0;
+    int32_t nextV = (int32_t)basev[c]; uint32_t nh = (uint32_t)basee[c];
+    const uint32_t start = cstart[c];
+    Q[qt++] = start; seen[start] = 1;
+    while (qh < qt) {
+        const uint32_t it = Q[qh++];
+        const uint4* rp = reinterpret_cast<const uint4*>(rec + it);
+        const uint4 a = rp[0], b = rp[1], cc = rp[2], d = rp[3];
+        const uint32_t w[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y, cc.z, cc.w, d.x, d.y, d.z, d.w};
+        const int32_t g1 = (int32_t)w[0], g2 = (int32_t)w[1];
+        const uint32_t info = w[2];
+        if (g1 < 0 || g2 < 0) { atomicOr(err, 2u); return; }
+        const bool new1 = vbits[g1] == 0;
+        if (new1) { vbits[g1] = 1; vid[g1] = nextV++; }
+        const bool new2 = vbits[g2] == 0;                          // (g1 == g2: already set)
+        if (new2) { vbits[g2] = 1; vid[g2] = nextV++; }
+        const uint32_t id = nh++;
+        src[id] = it; to_left[id] = vid[g1]; to_right[id] = vid[g2];
+        if (it & 1u) rev[it >> 1] = (int32_t)id; else fwd[it >> 1] = (int32_t)id;
+        if ((info >> 8) & 1u) { rev[it >> 1] = (int32_t)id; seen[it ^ 1u] = 1; }       // a palindromic edge: one HBV edge, processed as its forward item
+        for (int side = 0; side < 2; ++side) {
+            if (!(side ? new2 : new1)) continue;                   // the vertex pushed its items when it was numbered
+            const int32_t g = side ? g2 : g1;
+            uint32_t n = (info >> (4 * side)) & 15u;
+            if (n == 15u) {                                        // more than 6 edge ends on this vertex: the vertex record has them
+                const snh::GroupRec& G = groups[g];
+                n = G.n;
+                for (uint32_t x = 0; x < n; ++x) {
+                    const uint32_t t2 = G.items[x];
+                    if (!seen[t2]) { seen[t2] = 1; if (qt < SN_HBV_GPU_MAX) Q[qt++] = t2; else { atomicOr(err, 4u); return; } }
+                }
+                continue;
+            }
+            for (uint32_t x = 0; x < n; ++x) {
+                const uint32_t t2 = w[3 + 6 * side + x];
+                if (!seen[t2]) { seen[t2] = 1; if (qt < SN_HBV_GPU_MAX) Q[qt++] = t2; else { atomicOr(err, 4u); return; } }
+            }
+        }
+    }
+    if ((uint64_t)nextV != basev[c + 1] || (uint64_t)nh != basee[c + 1]) atomicOr(err, 8u);
+}
+// the host's share (big components; zero elsewhere) joins what the device numbered
+static __global__ void __launch_bounds__(256) k_add_u32(uint32_t* __restrict__ acc, const uint32_t* __restrict__ add, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += add[i];
+}
+
 // ---- memory layout for the numbering of a giant component -----------------------------------------
 // The numbering of one component is a sequential FIFO traversal that touches one 64-byte record per item.
 // With the records in unipath order (= dictionary order of the owners: random along the genome) every step

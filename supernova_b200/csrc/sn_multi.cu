@@ -104,7 +104,7 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     const int NR = c->comm ? c->comm->n : 1, rank = c->comm ? c->comm->rank : 0;
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
-    DictEntry* tab = c->dict.as<DictEntry>();
+    DictEntry* tab = c->dict.as<DictEntry>();         // (re-read after the ghost table has grown)
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);        // [4] circles found, [20..23] ghost counters / errors
     int r;
     // ---- ghosts: the neighbours that live on other ranks ----------------------------------------------------------
@@ -115,19 +115,31 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     uint64_t nq_send = 0, nq_recv = 0;
     if (NR > 1) {
         if (!c->ghost_cap) return fail(c, SN_ERR_STATE, "sharded dictionary without a ghost region");
-        DictView dv = dict_view(c);
-        CU(cudaMemsetAsync(tab + n, 0, (size_t)c->ghost_cap * sizeof(DictEntry), c->st));
-        CU(cudaMemsetAsync(u32c + 20, 0, 16, c->st));
-        if (n) { k_ghost_collect<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, dv, (uint32_t)NR, u32c + 20, u32c + 21); KCHECK("k_ghost_collect"); }
         CU(gcnt.alloc(8ull * NR)); CU(gbase.alloc(4ull * NR));
-        CU(cudaMemsetAsync(gcnt.p, 0, 8ull * NR, c->st));
-        k_ghost_count<<<blocks_for(c->ghost_cap, 256), 256, 0, c->st>>>(tab + n, c->ghost_cap, gcnt.as<uint32_t>());
-        KCHECK("k_ghost_count");
+        DevBuf& glist = c->pool["gh_list"];
         std::vector<uint32_t> h_cnt(NR); uint32_t h_g[2] = {0, 0};
-        CU(cudaMemcpyAsync(h_cnt.data(), gcnt.p, 4ull * NR, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaMemcpyAsync(h_g, u32c + 20, 8, cudaMemcpyDeviceToHost, c->st));
-        CU(cudaStreamSynchronize(c->st));
-        if (h_g[1]) return fail(c, SN_ERR_DATA, "the ghost table overflowed (" + std::to_string(h_g[0]) + " remote neighbours for " + std::to_string(c->ghost_cap) + " slots)");
+        for (int attempt = 0;; ++attempt) {
+            DictView dv = dict_view(c);
+            CU(glist.alloc(4ull * (c->ghost_cap / 4 * 3 + 1)));
+            CU(cudaMemsetAsync(c->dict.as<DictEntry>() + n, 0, (size_t)c->ghost_cap * sizeof(DictEntry), c->st));
+            CU(cudaMemsetAsync(u32c + 20, 0, 16, c->st));
+            CU(cudaMemsetAsync(gcnt.p, 0, 8ull * NR, c->st));
+            if (n) {
+                k_ghost_collect<<<blocks_for(n, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), dv, (uint32_t)NR, u32c + 20, u32c + 21, glist.as<uint32_t>(), gcnt.as<uint32_t>());
+                KCHECK("k_ghost_collect");
+            }
+            CU(cudaMemcpyAsync(h_cnt.data(), gcnt.p, 4ull * NR, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(h_g, u32c + 20, 8, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            if (!h_g[1]) break;
+            // more neighbours on other ranks than the table was sized for: a bigger one (the local entries move along)
+            if (attempt >= 3 || getenv("SN_GHOST_CAP") || (uint64_t)n + 4ull * c->ghost_cap >= (1ull << 31))
+                return fail(c, SN_ERR_DATA, "the ghost table overflowed (" + std::to_string(h_g[0]) + " remote neighbours for " + std::to_string(c->ghost_cap) + " slots)");
+            if ((r = grow_keep(c, c->dict, (size_t)n * sizeof(DictEntry), ((size_t)n + 4ull * c->ghost_cap) * sizeof(DictEntry) + 64))) return r;
+            c->ghost_cap *= 4;
+        }
+        tab = c->dict.as<DictEntry>();
+        const uint32_t n_gh = h_g[0];
         std::vector<uint32_t> h_base(NR);
         for (int d = 0; d < NR; ++d) { h_base[d] = (uint32_t)nq_send; q_sb[d] = h_cnt[d]; q_so[d] = nq_send; nq_send += h_cnt[d]; }
         // who asks me how much: every rank's per-destination counts
@@ -138,14 +150,13 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         CU(qk.alloc(12 * nq_send + 16)); CU(qslot.alloc(4 * nq_send + 16)); CU(rk.alloc(12 * nq_recv + 16)); CU(rans.alloc(4 * nq_recv + 16)); CU(ans.alloc(4 * nq_send + 16));
         CU(cudaMemcpyAsync(gbase.p, h_base.data(), 4ull * NR, cudaMemcpyHostToDevice, c->st));
         CU(cudaMemsetAsync(gcnt.as<uint32_t>() + NR, 0, 4ull * NR, c->st));
-        k_ghost_fill<<<blocks_for(c->ghost_cap, 256), 256, 0, c->st>>>(tab + n, c->ghost_cap, gbase.as<uint32_t>(), gcnt.as<uint32_t>() + NR, qk.as<uint32_t>(), qslot.as<uint32_t>());
-        KCHECK("k_ghost_fill");
+        if (n_gh) { k_ghost_fill<<<blocks_for(n_gh, 256), 256, 0, c->st>>>(tab + n, glist.as<uint32_t>(), n_gh, gbase.as<uint32_t>(), gcnt.as<uint32_t>() + NR, qk.as<uint32_t>(), qslot.as<uint32_t>()); KCHECK("k_ghost_fill"); }
         auto scaled = [&](const std::vector<size_t>& v, size_t f) { std::vector<size_t> o(v.size()); for (size_t i = 0; i < v.size(); ++i) o[i] = v[i] * f; return o; };
         {   // queries out (12 bytes each) ...
             auto sb = scaled(q_sb, 12), so = scaled(q_so, 12), rb = scaled(q_rb, 12), ro = scaled(q_ro, 12);
             if (c->comm->alltoallv(qk.p, sb.data(), so.data(), rk.p, rb.data(), ro.data(), c->st)) return comm_fail(c, "alltoallv (ghost queries)");
         }
-        DictView own = dv; own.g_cap = 0;
+        DictView own = dict_view(c); own.g_cap = 0;
         if (nq_recv) { k_ghost_answer<<<blocks_for(nq_recv, 256), 256, 0, c->st>>>(own, rk.as<uint32_t>(), (uint32_t)nq_recv, rans.as<uint32_t>()); KCHECK("k_ghost_answer"); }
         {   // ... answers back (4 bytes each, the same sizes reversed)
             auto sb = scaled(q_rb, 4), so = scaled(q_ro, 4), rb = scaled(q_sb, 4), ro = scaled(q_so, 4);
@@ -427,10 +438,10 @@ int mg_count_sharded(sn_ctx* c)
     DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
     if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), roff.as<uint64_t>(), nbl, (uint32_t)NR, h_occ, surv, surv_off, &n_surv))) return r;
     c->cnt.n_superkmers = n_recv;
-    // the rank's shard of the dictionary, with room for its ghosts: the neighbours in other buckets are ~6 % of 8 per
-    // k-mer at most, in practice ~0.1 per k-mer; the table is sized for a load below 1/4 and checked
+    // the rank's shard of the dictionary, with room for its ghosts: ~0.1 neighbours per k-mer live in other buckets
+    // (those whose minimizer differs), (N-1)/N of them on other ranks; the table starts at n/4 slots and grows if it must
     uint32_t cap = 1024;
-    while (cap < n_surv / 2 + 1024) cap <<= 1;
+    while (cap < n_surv / 4 + 1024) cap <<= 1;
     if (const char* e = getenv("SN_GHOST_CAP")) { uint32_t v = (uint32_t)atoll(e); if (v >= 64 && !(v & (v - 1))) cap = v; }     // tests: force overflow handling
     if ((r = sn_i_msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true, nbl, cap))) return r;
     c->dict_b_lo = fb[rank]; c->dict_b_n = nbl; c->ghost_cap = cap; c->dict_sharded = true;

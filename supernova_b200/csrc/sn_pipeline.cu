@@ -1016,9 +1016,6 @@ int sn_build_hbv(sn_ctx* c)
     k_hbv_itemrec<<<blocks_for(n_items, 128), 128, 0, c->st>>>(egrp.as<int32_t>(), pal.as<uint8_t>(), groups.as<snh::GroupRec>(), n_items, irec.as<snh::ItemRec>());
     KCHECK("k_hbv_itemrec");
     HostBuf &h_groups = c->hpool["hbv_groups"], &h_irec = c->hpool["hbv_irec"], &h_comp = c->hpool["hbv_comp"];
-    CU(h_groups.alloc(64ull * nV)); CU(h_irec.alloc(64ull * n_items));
-    CU(cudaMemcpyAsync(h_irec.p, irec.p, 64ull * n_items, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(h_groups.p, groups.p, 64ull * nV, cudaMemcpyDeviceToHost, c->st));
     // ---- connected components, their discovery order and id bases ----------------------------------------
     CU(parent.alloc(4ull * nV)); CU(comp.alloc(4ull * nV)); CU(ckey.alloc(8ull * nV)); CU(cntv.alloc(4ull * nV)); CU(cnte.alloc(4ull * nV));
     k_hbv_uf_init<<<blocks_for(nV, 256), 256, 0, c->st>>>(parent.as<uint32_t>(), nV, ckey.as<unsigned long long>(), cntv.as<uint32_t>(), cnte.as<uint32_t>());
@@ -1047,17 +1044,49 @@ int sn_build_hbv(sn_ctx* c)
     uint64_t tot_v = 0, tot_h = 0;
     if ((r0 = scan_u32(c, cv.as<uint32_t>(), n_comp, basev.as<uint64_t>(), &tot_v))) return r0;
     if ((r0 = scan_u32(c, ce.as<uint32_t>(), n_comp, basee.as<uint64_t>(), &tot_h))) return r0;
+    // ---- the FIFO numbering: small components on the device, one thread each (k_hbv_number_small) -------------------
+    const uint64_t nH = tot_h;
+    if (tot_h >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 HBV edges");
+    uint32_t max_items = SN_HBV_GPU_MAX;
+    if (getenv("SN_HBV_LAYOUT_MIN")) max_items = 0;                 // tests of the host path: every component goes there
+    if (const char* e = getenv("SN_HBV_GPU_MAX")) { const int v = atoi(e); if (v >= 0 && v <= SN_HBV_GPU_MAX) max_items = (uint32_t)v; }
+    DevBuf &seen = c->pool["hbv_seen"], &vbits = c->pool["hbv_vbits"], &vid = c->pool["hbv_vid"];
+    CU(seen.alloc(n_items + 16)); CU(vbits.alloc(nV + 16)); CU(vid.alloc(4ull * nV + 16));
+    CU(c->d_fwd.alloc(4ull * nE + 16)); CU(c->d_rev.alloc(4ull * nE + 16)); CU(c->d_toleft.alloc(4 * nH + 16)); CU(c->d_toright.alloc(4 * nH + 16)); CU(c->d_src.alloc(4 * nH + 16));
+    CU(cudaMemsetAsync(seen.p, 0, n_items + 16, c->st)); CU(cudaMemsetAsync(vbits.p, 0, nV + 16, c->st));
+    CU(cudaMemsetAsync(c->d_fwd.p, 0, 4ull * nE + 16, c->st)); CU(cudaMemsetAsync(c->d_rev.p, 0, 4ull * nE + 16, c->st));
+    CU(cudaMemsetAsync(c->d_toleft.p, 0, 4 * nH + 16, c->st)); CU(cudaMemsetAsync(c->d_toright.p, 0, 4 * nH + 16, c->st)); CU(cudaMemsetAsync(c->d_src.p, 0, 4 * nH + 16, c->st));
+    CU(cudaMemsetAsync(u32c + 16, 0, 8, c->st));
+    if (n_comp) {
+        k_hbv_number_small<<<blocks_for(n_comp, 64), 64, 0, c->st>>>(irec.as<snh::ItemRec>(), groups.as<snh::GroupRec>(), (uint32_t)n_comp, cstart.as<uint32_t>(), ce.as<uint32_t>(),
+            basev.as<uint64_t>(), basee.as<uint64_t>(), max_items, seen.as<uint8_t>(), vbits.as<uint8_t>(), vid.as<int32_t>(),
+            c->d_src.as<uint32_t>(), c->d_toleft.as<int32_t>(), c->d_toright.as<int32_t>(), c->d_fwd.as<int32_t>(), c->d_rev.as<int32_t>(), u32c + 16, u32c + 17);
+        KCHECK("k_hbv_number_small");
+    }
     t_end(c, "hbv_dev");
+    uint32_t h_err = 0, h_big[2] = {0, 0};
+    CU(cudaMemcpyAsync(&h_err, u32c + 7, 4, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(h_big, u32c + 16, 8, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (h_err) return fail(c, SN_ERR_DATA, "HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
+    if (h_big[1]) return fail(c, SN_ERR_DATA, "HBV: the device numbering of a component failed (flags " + std::to_string(h_big[1]) + ")");
+    if (tot_v != nV) return fail(c, SN_ERR_DATA, "HBV: component vertex counts do not add up");
+    c->host_ms["hbv_layout"] = 0.0; c->host_ms["hbv_host"] = 0.0;
+    snh::Hbv& H = c->hbv;
+    H.n_vert = (int32_t)nV;
+    c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
+    int r;
+    if (h_big[0]) {
+    // ---- big components: the host loop (sn_hbv.cpp) over the records, which travel to pinned host memory ---------------
+    CU(h_groups.alloc(64ull * nV)); CU(h_irec.alloc(64ull * n_items));
+    CU(cudaMemcpyAsync(h_irec.p, irec.p, 64ull * n_items, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(h_groups.p, groups.p, 64ull * nV, cudaMemcpyDeviceToHost, c->st));
     CU(h_comp.alloc(4 * n_comp + 16 * (n_comp + 1) + 64));
     uint64_t* h_basev = h_comp.as<uint64_t>(); uint64_t* h_basee = h_basev + (n_comp + 1); uint32_t* h_cstart = reinterpret_cast<uint32_t*>(h_basee + (n_comp + 1));
     CU(cudaMemcpyAsync(h_basev, basev.p, 8 * (n_comp + 1), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(h_basee, basee.p, 8 * (n_comp + 1), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(h_cstart, cstart.p, 4 * n_comp, cudaMemcpyDeviceToHost, c->st));
-    uint32_t h_err = 0;
-    CU(cudaMemcpyAsync(&h_err, u32c + 7, 4, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
-    if (h_err) return fail(c, SN_ERR_DATA, "HBV: a vertex has more than 8 edge ends (HBVFromEdges.cc:83)");
-    if (tot_v != nV) return fail(c, SN_ERR_DATA, "HBV: component vertex counts do not add up");
     // ---- a giant component: lay the records out along the graph first (sn_hbvdev.cuh, k_lay_*) -----------
     const uint32_t* layout = nullptr;
     {
@@ -1103,45 +1132,32 @@ int sn_build_hbv(sn_ctx* c)
             c->host_ms["hbv_layout"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
         }
     }
-    // ---- the FIFO numbering, all components in parallel on the host ----------------------------------
     auto t0 = std::chrono::steady_clock::now();
     snh::HbvComponents comps; comps.n_comp = n_comp; comps.start_item = h_cstart; comps.base_v = h_basev; comps.base_e = h_basee;
     static const unsigned hbv_threads = [] { const char* e = getenv("SN_HBV_THREADS"); unsigned n = e ? (unsigned)atoi(e) : std::min(32u, std::thread::hardware_concurrency()); return n ? n : 1u; }();
-    {   // the numbering writes straight into page-locked result arrays
-        snh::Hbv& Hn = c->hbv;
-        resize_pinned(c, Hn.src, tot_h); resize_pinned(c, Hn.to_left, tot_h); resize_pinned(c, Hn.to_right, tot_h);
-        resize_pinned(c, Hn.fwd, nE); resize_pinned(c, Hn.rev, nE);
-    }
-    // several ranks (sn_multi.cu): the graph is the same on all of them, so every rank numbers 1/N of the work units
-    // (components carry their final id bases) and the arrays are summed below, on the device, by one all-reduce each
+    snh::Hbv Hh;                                                   // the host's share: zero where the device (or another rank) numbers
+    Hh.src.assign(tot_h, 0); Hh.to_left.assign(tot_h, 0); Hh.to_right.assign(tot_h, 0); Hh.fwd.assign(nE, 0); Hh.rev.assign(nE, 0);
+    // several ranks (sn_multi.cu): the graph is the same on all of them, so every rank numbers 1/N of the big components
+    // (components carry their final id bases) and the arrays are summed on the device by one all-reduce each
     const unsigned n_parts = c->comm && c->comm->n > 1 ? (unsigned)c->comm->n : 1u, part = n_parts > 1 ? (unsigned)c->comm->rank : 0u;
-    if (n_parts > 1) {
-        snh::Hbv& Hn = c->hbv;
-        memset(Hn.src.data(), 0, 4 * tot_h); memset(Hn.to_left.data(), 0, 4 * tot_h); memset(Hn.to_right.data(), 0, 4 * tot_h);
-    }
     const unsigned nthreads = n_parts > 1 ? std::max(2u, hbv_threads / n_parts) : hbv_threads;      // (the ranks of one box share its cores)
-    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, c->hbv, nthreads, layout, part, n_parts); }
+    try { snh::number_hbv(comps, h_irec.as<snh::ItemRec>(), h_groups.as<snh::GroupRec>(), nV, nE, Hh, nthreads, layout, part, n_parts, (uint64_t)max_items + 1); }
     catch (const std::exception& ex) { return fail(c, SN_ERR_DATA, ex.what()); }
     c->host_ms["hbv_host"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    snh::Hbv& H = c->hbv;
-    const size_t nH = H.src.size();
-    c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
+    DevBuf& hs = c->pool["hbv_hostshare"];
+    CU(hs.alloc(4 * std::max<uint64_t>(nH, nE) + 16));
+    struct { DevBuf* d; const void* h; size_t n; } parts[5] = {{&c->d_fwd, Hh.fwd.data(), nE}, {&c->d_rev, Hh.rev.data(), nE}, {&c->d_toleft, Hh.to_left.data(), nH},
+                                                                {&c->d_toright, Hh.to_right.data(), nH}, {&c->d_src, Hh.src.data(), nH}};
+    for (auto& q : parts) {
+        CU(cudaMemcpyAsync(hs.p, q.h, 4 * q.n, cudaMemcpyHostToDevice, c->st));
+        if (n_parts > 1 && c->comm->allreduce_sum(hs.p, q.n, 4, c->st)) return fail(c, SN_ERR_CUDA, "allreduce (HBV numbering): " + c->comm->err);
+        k_add_u32<<<blocks_for(q.n, 256), 256, 0, c->st>>>(q.d->as<uint32_t>(), hs.as<uint32_t>(), q.n);
+        KCHECK("k_add_u32");
+        CU(cudaStreamSynchronize(c->st));                          // (hs and the pageable host vectors are reused)
+    }
+    }
     // ---- adjacency lists and involution on the device; the graph stays there for the pathing stage ----
     t_begin(c, "hbv_csr");
-    int r;
-    if ((r = upload(c, c->d_fwd, H.fwd.data(), 4ull * nE, 16))) return r;
-    if ((r = upload(c, c->d_rev, H.rev.data(), 4ull * nE, 16))) return r;
-    if ((r = upload(c, c->d_toleft, H.to_left.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_toright, H.to_right.data(), 4 * nH, 16))) return r;
-    if ((r = upload(c, c->d_src, H.src.data(), 4 * nH, 16))) return r;
-    if (n_parts > 1) {
-        struct { DevBuf* d; void* h; size_t n; } parts[5] = {{&c->d_fwd, H.fwd.data(), nE}, {&c->d_rev, H.rev.data(), nE}, {&c->d_toleft, H.to_left.data(), nH},
-                                                              {&c->d_toright, H.to_right.data(), nH}, {&c->d_src, H.src.data(), nH}};
-        for (auto& q : parts) {
-            if (c->comm->allreduce_sum(q.d->p, q.n, 4, c->st)) return fail(c, SN_ERR_CUDA, "allreduce (HBV numbering): " + c->comm->err);
-            CU(cudaMemcpyAsync(q.h, q.d->p, 4 * q.n, cudaMemcpyDeviceToHost, c->st));
-        }
-    }
     CU(c->d_from_start.alloc(4ull * (nV + 1) + 16)); CU(c->d_to_start.alloc(4ull * (nV + 1) + 16));
     CU(c->d_from_v.alloc(4 * nH + 16)); CU(c->d_from_e.alloc(4 * nH + 16)); CU(c->d_to_v.alloc(4 * nH + 16)); CU(c->d_to_e.alloc(4 * nH + 16));
     DevBuf &ra = c->pool["hbv_csr_a"], &rb = c->pool["hbv_csr_b"], &rs = c->pool["hbv_csr_s"], &dinv = c->pool["hbv_inv"];
@@ -1162,6 +1178,12 @@ int sn_build_hbv(sn_ctx* c)
     k_hbv_inv<<<blocks_for(nE, 256), 256, 0, c->st>>>(c->d_fwd.as<int32_t>(), c->d_rev.as<int32_t>(), nE, dinv.as<int32_t>());
     KCHECK("k_hbv_inv");
     t_end(c, "hbv_csr");
+    resize_pinned(c, H.src, nH); resize_pinned(c, H.to_left, nH); resize_pinned(c, H.to_right, nH); resize_pinned(c, H.fwd, nE); resize_pinned(c, H.rev, nE);
+    CU(cudaMemcpyAsync(H.src.data(), c->d_src.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.to_left.data(), c->d_toleft.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.to_right.data(), c->d_toright.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.fwd.data(), c->d_fwd.p, 4ull * nE, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(H.rev.data(), c->d_rev.p, 4ull * nE, cudaMemcpyDeviceToHost, c->st));
     resize_pinned(c, H.from_start, nV + 1); resize_pinned(c, H.to_start, nV + 1);
     resize_pinned(c, H.from_v, nH); resize_pinned(c, H.from_e, nH); resize_pinned(c, H.to_v, nH); resize_pinned(c, H.to_e, nH); resize_pinned(c, H.inv, nH);
     CU(cudaMemcpyAsync(H.from_start.data(), c->d_from_start.p, 4ull * (nV + 1), cudaMemcpyDeviceToHost, c->st));

@@ -51,7 +51,8 @@ def _check(sb, ctx, o, wd, packed, extra, overflow_expected=False):
             # that pass the barcode rule -- how many depends on its thread count.  What it keeps must be ours, with
             # the same count and context; the oracle above (no overflow mode) pins the rest.
             assert overflow_expected, "unexpected MapReduce buffer overflow in the reference run"
-            key = lambda a: (a[:, 0].astype(np.uint64) << np.uint64(32) | a[:, 1].astype(np.uint64)), a[:, 2]
+            def key(a):
+                return (a[:, 0].astype(np.uint64) << np.uint64(32)) | a[:, 1].astype(np.uint64), a[:, 2]
             mh, ml = key(mine); rh, rl = key(ref)
             mv = np.empty(len(mine), dtype=[("h", np.uint64), ("l", np.uint32)]); mv["h"], mv["l"] = mh, ml
             rv = np.empty(len(ref), dtype=[("h", np.uint64), ("l", np.uint32)]); rv["h"], rv["l"] = rh, rl

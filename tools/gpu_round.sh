@@ -5,7 +5,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 for what in "$@"; do
 case $what in
-tests) timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/${TAG}_tests.log;;
+tests) timeout 1500 python -m pytest tests -m gpu -q --durations=15 > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/${TAG}_tests.log;;
 tests:*) timeout 1500 python -m pytest ${what#tests:} -m gpu -x -q --durations=10 > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/${TAG}_tests.log;;
 sanitize) bash tools/sanitize.sh $TAG C1 1;;
 bench) timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
