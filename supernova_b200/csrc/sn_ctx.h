@@ -103,6 +103,9 @@ struct sn_ctx {
     uint32_t ghost_cap = 0;                  // ghost region behind the dictionary: remote neighbours of the local k-mers (open addressing, power of two)
     uint64_t mg_n_kmers_total = 0;           // dictionary size over all ranks
     bool dict_sharded = false;
+    // Results a rank other than 0 leaves on the device until somebody asks for them (every rank computes the whole edge
+    // set and HBV; the job needs them in host memory once): sn_i_fetch_edges_host / sn_i_fetch_hbv_host bring them over.
+    bool edges_host_stale = false, hbv_host_stale = false;
 };
 
 namespace {
@@ -193,4 +196,6 @@ int sn_i_msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bit
                           uint32_t nb_window = 0, uint64_t extra_entries = 0);
 // recomputeAdjacencies + buildEdges over this context's (possibly sharded) dictionary: sn_multi.cu
 int sn_i_build_edges2(sn_ctx* c);
+int sn_i_fetch_edges_host(sn_ctx* c);
+int sn_i_fetch_hbv_host(sn_ctx* c);
 }

@@ -165,7 +165,7 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         if (nq_send) { k_ghost_apply<<<blocks_for(nq_send, 256), 256, 0, c->st>>>(tab + n, qslot.as<uint32_t>(), ans.as<uint32_t>(), (uint32_t)nq_send); KCHECK("k_ghost_apply"); }
     }
     t_end(c, "ghosts");
-    if (!n && NR == 1) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
+    if (!n && NR == 1) { c->edges_host_stale = false; resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     const DictView dv = dict_view(c);
     // ---- recomputeAdjacencies ---------------------------------------------------------------------------------------
     t_begin(c, "prune");
@@ -364,12 +364,10 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     }
     t_end(c, "edges");
     c->cnt.n_edges = E; c->cnt.n_edge_bases = all_bases;
-    resize_pinned(c, c->hedges.len, E); resize_pinned(c, c->hedges.off, E + 1); resize_pinned(c, c->hedges.packed, total_bytes + 16);
-    memset(c->hedges.packed.data() + total_bytes, 0, 16);
-    if (E) CU(cudaMemcpyAsync(c->hedges.len.data(), c->elen.p, 4 * E, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(c->hedges.off.data(), c->eoff.p, 8 * (E + 1), cudaMemcpyDeviceToHost, c->st));
-    if (total_bytes) CU(cudaMemcpyAsync(c->hedges.packed.data(), c->ebases.p, total_bytes, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
+    // the edges in host memory: on one rank of a multi-GPU job; the others keep them on the device until asked
+    c->edges_host_stale = true;
+    if (NR == 1 || rank == 0) { if ((r = sn_i_fetch_edges_host(c))) return r; }
+    else CU(cudaStreamSynchronize(c->st));
     // every dictionary k-mer of every rank sits on exactly one edge
     std::vector<uint64_t> nk_all, nk_mine(1, n);
     if ((r = allgather_u64(c, nk_mine.data(), 1, nk_all))) return r;

@@ -840,6 +840,7 @@ int sn_build_edges(sn_ctx* c)
     }
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
+    c->edges_host_stale = false;
     if (!n) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
     const DictView dv = dict_view(c);
@@ -963,6 +964,7 @@ int sn_build_hbv(sn_ctx* c)
         H0.n_vert = 0; H0.fwd.clear(); H0.rev.clear(); H0.src.clear(); H0.to_left.clear(); H0.to_right.clear(); H0.inv.clear();
         H0.from_v.clear(); H0.from_e.clear(); H0.to_v.clear(); H0.to_e.clear();
         H0.from_start.assign(1, 0); H0.to_start.assign(1, 0);
+        c->hbv_host_stale = false;
         c->stage = 4; return SN_OK;
     }
     if (nE >= (1u << 29)) return fail(c, SN_ERR_ARG, "more than 2^29 unipath edges");
@@ -1178,6 +1180,20 @@ int sn_build_hbv(sn_ctx* c)
     k_hbv_inv<<<blocks_for(nE, 256), 256, 0, c->st>>>(c->d_fwd.as<int32_t>(), c->d_rev.as<int32_t>(), nE, dinv.as<int32_t>());
     KCHECK("k_hbv_inv");
     t_end(c, "hbv_csr");
+    // the graph in host memory: on one rank of a multi-GPU job; the others keep it on the device until asked (sn_get_hbv, sn_write_hbv ...)
+    c->hbv_host_stale = true;
+    c->stage = 4;
+    if (!(c->comm && c->comm->n > 1 && c->comm->rank != 0)) { int rf = sn_i_fetch_hbv_host(c); if (rf) { c->stage = 3; return rf; } }
+    else CU(cudaStreamSynchronize(c->st));
+    return SN_OK;
+}
+int sn_i_fetch_hbv_host(sn_ctx* c)
+{
+    if (!c->hbv_host_stale) return SN_OK;
+    CU(cudaSetDevice(c->device));
+    snh::Hbv& H = c->hbv;
+    const uint64_t nH = c->cnt.n_hbv_edges, nV = c->cnt.n_hbv_vertices, nE = c->cnt.n_edges;
+    DevBuf& dinv = c->pool["hbv_inv"];
     resize_pinned(c, H.src, nH); resize_pinned(c, H.to_left, nH); resize_pinned(c, H.to_right, nH); resize_pinned(c, H.fwd, nE); resize_pinned(c, H.rev, nE);
     CU(cudaMemcpyAsync(H.src.data(), c->d_src.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(H.to_left.data(), c->d_toleft.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
@@ -1194,11 +1210,28 @@ int sn_build_hbv(sn_ctx* c)
     CU(cudaMemcpyAsync(H.to_e.data(), c->d_to_e.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(H.inv.data(), dinv.p, 4 * nH, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    c->hbv_host_stale = false;
     // every side of a vertex holds at most 4 edges (one per base)
-    for (uint32_t v = 0; v < nV; ++v)
+    for (uint64_t v = 0; v < nV; ++v)
         if (H.from_start[v + 1] - H.from_start[v] > 4 || H.to_start[v + 1] - H.to_start[v] > 4)
             return fail(c, SN_ERR_DATA, "HBV: more than 4 edges on one side of a vertex");
-    c->stage = 4;
+    return SN_OK;
+}
+int sn_i_fetch_edges_host(sn_ctx* c)
+{
+    if (!c->edges_host_stale) return SN_OK;
+    CU(cudaSetDevice(c->device));
+    const uint64_t E = c->cnt.n_edges;
+    uint64_t total_bytes = 0;
+    CU(cudaMemcpyAsync(&total_bytes, c->eoff.as<uint64_t>() + E, 8, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    resize_pinned(c, c->hedges.len, E); resize_pinned(c, c->hedges.off, E + 1); resize_pinned(c, c->hedges.packed, total_bytes + 16);
+    memset(c->hedges.packed.data() + total_bytes, 0, 16);
+    if (E) CU(cudaMemcpyAsync(c->hedges.len.data(), c->elen.p, 4 * E, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->hedges.off.data(), c->eoff.p, 8 * (E + 1), cudaMemcpyDeviceToHost, c->st));
+    if (total_bytes) CU(cudaMemcpyAsync(c->hedges.packed.data(), c->ebases.p, total_bytes, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    c->edges_host_stale = false;
     return SN_OK;
 }
 
@@ -1228,7 +1261,7 @@ static int graph_from_edges(sn_ctx* c, const snf::Fastb& E)
     memcpy(c->hedges.off.data(), E.off.data(), 8 * (nE + 1));
     if (total_bytes) memcpy(c->hedges.packed.data(), E.var.data(), total_bytes);
     memset(c->hedges.packed.data() + total_bytes, 0, 16);
-    c->cnt.n_edges = nE; c->cnt.n_edge_bases = n_bases;
+    c->cnt.n_edges = nE; c->cnt.n_edge_bases = n_bases; c->edges_host_stale = false;
     c->cnt.n_kmer_occurrences = 0; c->cnt.n_kmers_distinct = 0; c->cnt.n_superkmers = 0;
     // ---- dictionary of the edge k-mers ----
     t_begin(c, "edge_dict");
@@ -1389,6 +1422,7 @@ int sn_get_kmer_graph_info(sn_ctx* c, uint8_t* ctx_pruned, uint32_t* edge, uint3
 int sn_get_edges_bytes(const sn_ctx* c, uint64_t* packed_bytes)
 {
     if (!c || !packed_bytes) return SN_ERR_ARG;
+    if (c->edges_host_stale) { int r = sn_i_fetch_edges_host(const_cast<sn_ctx*>(c)); if (r) return r; }
     *packed_bytes = c->hedges.off.empty() ? 0 : c->hedges.off.back();
     return SN_OK;
 }
@@ -1396,6 +1430,7 @@ int sn_get_edges(sn_ctx* c, uint32_t* len, uint64_t* off, uint8_t* packed)
 {
     if (!c) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
+    { int r = sn_i_fetch_edges_host(c); if (r) return r; }
     const snh::Edges& E = c->hedges;
     if (len && E.n()) memcpy(len, E.len.data(), 4 * E.n());
     if (off) memcpy(off, E.off.data(), 8 * E.off.size());
@@ -1407,6 +1442,7 @@ int sn_get_hbv(sn_ctx* c, uint32_t* from_start, int32_t* from_v, int32_t* from_e
 {
     if (!c) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    { int r = sn_i_fetch_hbv_host(c); if (r) return r; }
     const snh::Hbv& H = c->hbv;
     size_t nV = (size_t)H.n_vert, nH = H.src.size();
     if (from_start) memcpy(from_start, H.from_start.data(), 4 * (nV + 1));
@@ -1449,6 +1485,7 @@ int sn_write_hbv(sn_ctx* c, const char* path)
 {
     if (!c || !path) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    { int r = sn_i_fetch_edges_host(c); if (r) return r; if ((r = sn_i_fetch_hbv_host(c))) return r; }
     std::string err; const snh::Hbv& H = c->hbv;
     std::vector<uint8_t> ep; std::vector<uint64_t> eo; std::vector<uint32_t> el;
     snh::hbv_edge_sequences(c->hedges, H, ep, eo, el);
@@ -1469,6 +1506,7 @@ int sn_write_edges_bv(sn_ctx* c, const char* path)
 {
     if (!c || !path) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "run sn_build_edges first");
+    { int r = sn_i_fetch_edges_host(c); if (r) return r; }
     std::string err; const snh::Edges& E = c->hedges;
     if (!snf::write_bv(path, E.packed.data(), E.off.data(), E.len.data(), E.n(), err)) return fail(c, SN_ERR_IO, err);
     return SN_OK;
@@ -1534,6 +1572,7 @@ int sn_write_to_left_right(sn_ctx* c, const char* to_left, const char* to_right)
 {
     if (!c) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    { int r = sn_i_fetch_hbv_host(c); if (r) return r; }
     std::string err;
     if (to_left && !snf::write_vec_int(to_left, c->hbv.to_left, err)) return fail(c, SN_ERR_IO, err);
     if (to_right && !snf::write_vec_int(to_right, c->hbv.to_right, err)) return fail(c, SN_ERR_IO, err);
@@ -1543,6 +1582,7 @@ int sn_write_inv(sn_ctx* c, const char* path)
 {
     if (!c || !path) return SN_ERR_ARG;
     if (c->stage < 4) return fail(c, SN_ERR_STATE, "run sn_build_hbv first");
+    { int r = sn_i_fetch_hbv_host(c); if (r) return r; }
     std::string err;
     if (!snf::write_vec_int(path, c->hbv.inv, err)) return fail(c, SN_ERR_IO, err);
     return SN_OK;
