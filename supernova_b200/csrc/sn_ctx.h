@@ -106,6 +106,8 @@ struct sn_ctx {
     // Results a rank other than 0 leaves on the device until somebody asks for them (every rank computes the whole edge
     // set and HBV; the job needs them in host memory once): sn_i_fetch_edges_host / sn_i_fetch_hbv_host bring them over.
     bool edges_host_stale = false, hbv_host_stale = false;
+    bool edges_copy_inflight = false;        // the edges are on their way to the host on st2 (under the HBV stage); ev_edges marks the end
+    cudaEvent_t ev_edges = nullptr, ev_edges_go = nullptr;
 };
 
 namespace {
@@ -197,5 +199,6 @@ int sn_i_msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bit
 // recomputeAdjacencies + buildEdges over this context's (possibly sharded) dictionary: sn_multi.cu
 int sn_i_build_edges2(sn_ctx* c);
 int sn_i_fetch_edges_host(sn_ctx* c);
+int sn_i_start_edges_copy(sn_ctx* c, uint64_t total_bytes);      // the same, asynchronously on the copy stream (sn_i_fetch_edges_host completes it)
 int sn_i_fetch_hbv_host(sn_ctx* c);
 }

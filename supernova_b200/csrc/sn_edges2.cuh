@@ -34,6 +34,9 @@ __device__ __forceinline__ uint32_t bucket_owner(uint32_t bucket, uint32_t n_ran
 static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, DictView d, uint32_t n_ranks, uint32_t* n_ghosts, uint32_t* overflow,
                                                               uint32_t* __restrict__ glist /* g_cap / 4 * 3 + 1: the slots taken, in no particular order */, uint32_t* __restrict__ per_owner)
 {
+    __shared__ uint32_t blk_owner[64];                        // per-owner counts of this block (a few owners: global atomics on them would serialise)
+    if (threadIdx.x < 64) blk_owner[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < d.n;
     Kmer k; k.w0 = k.w1 = k.w2 = 0; KmerMin km; uint32_t todo = 0;
@@ -63,8 +66,13 @@ static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, Di
                     e->w0 = q.w0; e->w1 = q.w1; e->w2 = q.w2; e->h = h; e->cc = owner; e->edge = SN_NULL_EDGE; e->ctx = 0;
                     __threadfence();
                     *reinterpret_cast<volatile uint32_t*>(&e->off) = GH_PENDING;
-                    const uint32_t at = atomicAdd(n_ghosts, 1u);
-                    if (at >= (d.g_cap / 4u) * 3u) *overflow = 1u; else { glist[at] = slot; atomicAdd(&per_owner[owner], 1u); }
+                    // (one atomic on the shared counter per warp and round, not per ghost)
+                    const unsigned am = __activemask();
+                    const uint32_t lane = threadIdx.x & 31u, ldr = (uint32_t)__ffs((int)am) - 1u;
+                    uint32_t at = 0;
+                    if (lane == ldr) at = atomicAdd(n_ghosts, (uint32_t)__popc(am));
+                    at = __shfl_sync(am, at, (int)ldr) + (uint32_t)__popc(am & ((1u << lane) - 1u));
+                    if (at >= (d.g_cap / 4u) * 3u) *overflow = 1u; else { glist[at] = slot; if (owner < 64u) atomicAdd(&blk_owner[owner], 1u); else atomicAdd(&per_owner[owner], 1u); }
                     have = false;
                 }                                               // (lost the race: the slot is looked at again)
             } else if (st != GH_WRITING) {
@@ -75,6 +83,8 @@ static __global__ void __launch_bounds__(256) k_ghost_collect(DictEntry* tab, Di
         }
         __syncwarp();
     }
+    __syncthreads();
+    if (threadIdx.x < 64 && threadIdx.x < n_ranks && blk_owner[threadIdx.x]) atomicAdd(&per_owner[threadIdx.x], blk_owner[threadIdx.x]);
 }
 // ---- ghosts: queries grouped by owner -----------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) k_ghost_fill(const DictEntry* __restrict__ gh, const uint32_t* __restrict__ glist, uint32_t n_ghosts,
@@ -82,10 +92,17 @@ static __global__ void __launch_bounds__(256) k_ghost_fill(const DictEntry* __re
                                                            uint32_t* __restrict__ qk /* 3 words per query */, uint32_t* __restrict__ qslot)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_ghosts) return;
-    const uint32_t s = glist[t];
-    const DictEntry e = gh[s];
-    const uint32_t p = base[e.cc] + atomicAdd(&cursor[e.cc], 1u);
+    const bool live = t < n_ghosts;
+    uint32_t s = 0; DictEntry e; e.cc = 0xFFFFFFFFu; e.w0 = e.w1 = e.w2 = 0;
+    if (live) { s = glist[t]; e = gh[s]; }
+    // a handful of owners: one atomic per owner and warp
+    const unsigned m = __match_any_sync(SN_FULL, e.cc);
+    const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)m) - 1u;
+    uint32_t first = 0;
+    if (live && lane == leader) first = atomicAdd(&cursor[e.cc], (uint32_t)__popc(m));
+    first = __shfl_sync(SN_FULL, first, (int)leader);
+    if (!live) return;
+    const uint32_t p = base[e.cc] + first + (uint32_t)__popc(m & ((1u << lane) - 1u));
     qk[3 * p] = e.w0; qk[3 * p + 1] = e.w1; qk[3 * p + 2] = e.w2; qslot[p] = s;
 }
 // owner side: index of every queried k-mer in the local table, or SN_NULL_EDGE

@@ -101,6 +101,7 @@ int grow_keep(sn_ctx* c, DevBuf& b, size_t used, size_t want)
 extern "C" int sn_i_build_edges2(sn_ctx* c)
 {
     CU(cudaSetDevice(c->device));
+    if (c->edges_copy_inflight) { cudaEventSynchronize(c->ev_edges); c->edges_copy_inflight = false; }     // (an earlier step's edges still on their way)
     const int NR = c->comm ? c->comm->n : 1, rank = c->comm ? c->comm->rank : 0;
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
@@ -365,9 +366,10 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     t_end(c, "edges");
     c->cnt.n_edges = E; c->cnt.n_edge_bases = all_bases;
     // the edges in host memory: on one rank of a multi-GPU job; the others keep them on the device until asked
+    // (the copy runs on the second stream, under the HBV stage; sn_build_hbv / the getters complete it)
     c->edges_host_stale = true;
-    if (NR == 1 || rank == 0) { if ((r = sn_i_fetch_edges_host(c))) return r; }
-    else CU(cudaStreamSynchronize(c->st));
+    if (NR == 1 || rank == 0) { if ((r = sn_i_start_edges_copy(c, total_bytes))) return r; }
+    CU(cudaStreamSynchronize(c->st));
     // every dictionary k-mer of every rank sits on exactly one edge
     std::vector<uint64_t> nk_all, nk_mine(1, n);
     if ((r = allgather_u64(c, nk_mine.data(), 1, nk_all))) return r;

@@ -112,6 +112,7 @@ void sn_ctx_destroy(sn_ctx* c)
     for (auto& kv : c->timers) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     unpin_all(c);
     for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->ev_edges) { cudaEventDestroy(c->ev_edges); cudaEventDestroy(c->ev_edges_go); }
     if (c->st2) cudaStreamDestroy(c->st2);
     cudaStreamDestroy(c->st);
     delete c->comm;
@@ -573,10 +574,8 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     const uint64_t n = n_reads;
     constexpr int MAXCH = 8;
     const int nch = n >= (1u << 16) ? 4 : 1;
-    if (!c->st2) {
-        CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
-        for (int i = 0; i < 2 * MAXCH; ++i) CU(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
-    }
+    if (!c->st2) CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    if (!c->ev_copy[0]) for (int i = 0; i < 2 * MAXCH; ++i) CU(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
     c->have_bc = bc != nullptr; c->have_pq = true; c->quals.release();
     CU(c->bases.alloc(base_off[n] + 64)); CU(c->boff.alloc(8 * (n + 1))); CU(c->len.alloc(4 * n));
     if (bc) CU(c->bc.alloc(4 * n));
@@ -834,12 +833,13 @@ int sn_build_edges(sn_ctx* c)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 2) return fail(c, SN_ERR_STATE, "sn_build_edges: run sn_count_kmers first");
     CU(cudaSetDevice(c->device));
-    {   // the stop-indexed stage of the sharded path (sn_multi.cu) also runs on one rank; SN_EDGES2=0 keeps the first implementation for A/B runs
+    {   // the stop-indexed stage of the sharded path (sn_multi.cu) also runs on one rank; it is the default; SN_EDGES2=0 runs the first implementation below for A/B timing
         const char* e2 = getenv("SN_EDGES2");
-        if ((e2 && atoi(e2) != 0) || c->dict_sharded) return sn_i_build_edges2(c);
+        if (!(e2 && atoi(e2) == 0) || c->dict_sharded) return sn_i_build_edges2(c);
     }
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
     c->cnt.n_edges = 0; c->cnt.n_edge_bases = 0;
+    if (c->edges_copy_inflight) { cudaEventSynchronize(c->ev_edges); c->edges_copy_inflight = false; }
     c->edges_host_stale = false;
     if (!n) { resize_pinned(c, c->hedges.len, 0); resize_pinned(c, c->hedges.off, 1); c->hedges.off[0] = 0; resize_pinned(c, c->hedges.packed, 16); c->stage = 3; return SN_OK; }
     DictEntry* tab = c->dict.as<DictEntry>();
@@ -1183,7 +1183,7 @@ int sn_build_hbv(sn_ctx* c)
     // the graph in host memory: on one rank of a multi-GPU job; the others keep it on the device until asked (sn_get_hbv, sn_write_hbv ...)
     c->hbv_host_stale = true;
     c->stage = 4;
-    if (!(c->comm && c->comm->n > 1 && c->comm->rank != 0)) { int rf = sn_i_fetch_hbv_host(c); if (rf) { c->stage = 3; return rf; } }
+    if (!(c->comm && c->comm->n > 1 && c->comm->rank != 0)) { int rf = sn_i_fetch_hbv_host(c); if (!rf) rf = sn_i_fetch_edges_host(c); if (rf) { c->stage = 3; return rf; } }
     else CU(cudaStreamSynchronize(c->st));
     return SN_OK;
 }
@@ -1217,10 +1217,28 @@ int sn_i_fetch_hbv_host(sn_ctx* c)
             return fail(c, SN_ERR_DATA, "HBV: more than 4 edges on one side of a vertex");
     return SN_OK;
 }
+int sn_i_start_edges_copy(sn_ctx* c, uint64_t total_bytes)
+{
+    CU(cudaSetDevice(c->device));
+    if (!c->st2) CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    if (!c->ev_edges) { CU(cudaEventCreateWithFlags(&c->ev_edges, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_edges_go, cudaEventDisableTiming)); }
+    const uint64_t E = c->cnt.n_edges;
+    resize_pinned(c, c->hedges.len, E); resize_pinned(c, c->hedges.off, E + 1); resize_pinned(c, c->hedges.packed, total_bytes + 16);
+    memset(c->hedges.packed.data() + total_bytes, 0, 16);
+    CU(cudaEventRecord(c->ev_edges_go, c->st));
+    CU(cudaStreamWaitEvent(c->st2, c->ev_edges_go, 0));
+    if (E) CU(cudaMemcpyAsync(c->hedges.len.data(), c->elen.p, 4 * E, cudaMemcpyDeviceToHost, c->st2));
+    CU(cudaMemcpyAsync(c->hedges.off.data(), c->eoff.p, 8 * (E + 1), cudaMemcpyDeviceToHost, c->st2));
+    if (total_bytes) CU(cudaMemcpyAsync(c->hedges.packed.data(), c->ebases.p, total_bytes, cudaMemcpyDeviceToHost, c->st2));
+    CU(cudaEventRecord(c->ev_edges, c->st2));
+    c->edges_copy_inflight = true; c->edges_host_stale = true;
+    return SN_OK;
+}
 int sn_i_fetch_edges_host(sn_ctx* c)
 {
     if (!c->edges_host_stale) return SN_OK;
     CU(cudaSetDevice(c->device));
+    if (c->edges_copy_inflight) { CU(cudaEventSynchronize(c->ev_edges)); c->edges_copy_inflight = false; c->edges_host_stale = false; return SN_OK; }
     const uint64_t E = c->cnt.n_edges;
     uint64_t total_bytes = 0;
     CU(cudaMemcpyAsync(&total_bytes, c->eoff.as<uint64_t>() + E, 8, cudaMemcpyDeviceToHost, c->st));
@@ -1261,6 +1279,7 @@ static int graph_from_edges(sn_ctx* c, const snf::Fastb& E)
     memcpy(c->hedges.off.data(), E.off.data(), 8 * (nE + 1));
     if (total_bytes) memcpy(c->hedges.packed.data(), E.var.data(), total_bytes);
     memset(c->hedges.packed.data() + total_bytes, 0, 16);
+    if (c->edges_copy_inflight) { cudaEventSynchronize(c->ev_edges); c->edges_copy_inflight = false; }
     c->cnt.n_edges = nE; c->cnt.n_edge_bases = n_bases; c->edges_host_stale = false;
     c->cnt.n_kmer_occurrences = 0; c->cnt.n_kmers_distinct = 0; c->cnt.n_superkmers = 0;
     // ---- dictionary of the edge k-mers ----

@@ -45,8 +45,9 @@ def _slice(sb, data, rank, n_ranks):
 
 @pytest.mark.parametrize("name", SETS)
 def test_stop_indexed_edge_stage_on_one_rank(sb, name, tmp_path):
+    """the default edge stage (stop-indexed, shared with the sharded path) against the first implementation (SN_EDGES2=0)"""
     ref, data = _single(sb, name, str(tmp_path))
-    os.environ["SN_EDGES2"] = "1"
+    os.environ["SN_EDGES2"] = "0"
     try:
         wd = str(tmp_path / "v2"); os.makedirs(wd)
         with sb.Context(0) as ctx:
