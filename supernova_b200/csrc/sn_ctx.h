@@ -82,6 +82,7 @@ struct sn_ctx {
     bool have_bc = false, have_pq = false;
     // dictionary
     DevBuf dict, dboff;      // dictionary (bucket, hash, k-mer order) and its bucket offsets (2^dict_bits + 1)
+    DevBuf dict_hs;          // the entries' hashes on their own (DictView::hs)
     int dict_bits = 4, dict_sub_bits = 0;
     // edges (device) + host copy
     DevBuf ebases, eoff, elen;
@@ -155,6 +156,7 @@ inline sn::DictView dict_view(sn_ctx* c)
     d.n = (uint32_t)c->cnt.n_kmers; d.bits = c->dict_bits; d.sub_bits = c->dict_sub_bits;
     d.b_lo = c->dict_b_lo; d.b_n = c->dict_b_n ? c->dict_b_n : (1u << c->dict_bits);
     d.g_cap = c->ghost_cap;
+    d.hs = c->dict_hs.as<uint32_t>();
     return d;
 }
 

@@ -406,13 +406,24 @@ struct PathInputs {
     const uint8_t* quals; const uint64_t* qoff;          // unpacked quals, or
     const uint8_t* pq; const uint64_t* pq_off;           // PQVec stream
 };
+// the quals of a read, decoded from its PQVec stream on first use
+struct LazyQuals {
+    const uint8_t* q8; const uint8_t* pq; const uint8_t* pq_end; uint8_t* buf; bool ready;
+    __device__ __forceinline__ const uint8_t* get()
+    {
+        if (q8) return q8;
+        if (!ready) { pqvec_decode(pq, pq_end, buf, SN_MAX_READ_LEN); ready = true; }
+        return buf;
+    }
+};
 __device__ __forceinline__ void thread_path(const PathInputs& in, uint64_t r, const DictView& d, const EdgeStore& es, const HbvView& h,
                                             Part* parts, RPath& path, uint8_t* qbuf)
 {
-    const uint8_t* q;
-    if (in.pq) { pqvec_decode(in.pq + in.pq_off[r], in.pq + in.pq_off[r + 1], qbuf, SN_MAX_READ_LEN); q = qbuf; }
-    else q = in.quals + in.qoff[r];
-    path_one_read(d, es, h, in.bases + in.boff[r], q, in.len[r], parts, path);
+    LazyQuals qs;
+    qs.q8 = in.pq ? nullptr : in.quals + in.qoff[r];
+    qs.pq = in.pq ? in.pq + in.pq_off[r] : nullptr; qs.pq_end = in.pq ? in.pq + in.pq_off[r + 1] : nullptr;
+    qs.buf = qbuf; qs.ready = false;
+    path_one_read_q(d, es, h, in.bases + in.boff[r], qs, in.len[r], parts, path);
 }
 static __global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, EdgeStore es, HbvView h,
                                                     uint32_t* __restrict__ plen, int32_t* __restrict__ poffset, int32_t* __restrict__ scratch, uint32_t* overflow)

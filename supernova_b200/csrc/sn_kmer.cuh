@@ -106,6 +106,42 @@ SN_HD Kmer kmer_from_packed(const uint8_t* p, uint64_t pos)
     return k;
 }
 
+// 16 bases starting at base `pos` of a fastb-packed sequence, base pos in bits 1..0 (the buffers are padded: reading a
+// few bytes past the sequence is allowed).  Device: two aligned 32-bit loads + one funnel shift.
+SN_HD uint32_t packed_window16(const uint8_t* p, uint64_t pos)
+{
+#if defined(__CUDA_ARCH__)
+    const uint8_t* q = p + (pos >> 2);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(q - mis);
+    const uint32_t sh = 8u * mis + 2u * (uint32_t)(pos & 3u);          // <= 30
+    return __funnelshift_r(w[0], w[1], sh);
+#else
+    const uint8_t* q = p + (pos >> 2);
+    uint64_t v = 0;
+    for (int i = 0; i < 5; ++i) v |= (uint64_t)q[i] << (8 * i);
+    return (uint32_t)(v >> (2 * (pos & 3)));
+#endif
+}
+SN_HD Kmer kmer_from_packed_w(const uint8_t* p, uint64_t pos)
+{
+    Kmer k;
+    k.w0 = rev2(packed_window16(p, pos)); k.w1 = rev2(packed_window16(p, pos + 16)); k.w2 = rev2(packed_window16(p, pos + 32));
+    return k;
+}
+// number of leading equal bases (<= m <= 16) of two 16-base windows
+SN_HD uint32_t window_match(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t x = a ^ b;
+    if (m < 16) x |= 1u << (2 * m);                                    // a sentinel difference right after the m-th base
+    if (!x) return 16;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs((int)x) - 1) >> 1;
+#else
+    return (uint32_t)__builtin_ctz(x) >> 1;
+#endif
+}
+
 // --- minimizers (MSP, lib/tada/src/msp/mod.rs) ---------------------------------------------------
 // The minimizer of a k-mer is the smallest of its W = K-P+1 canonical p-mers under a hashed order;
 // k-mer and reverse complement share it, so it names one bucket for every occurrence of a
@@ -240,6 +276,9 @@ struct DictView {
     // open-addressed table of g_cap (power of two, 0 = none) entries right behind the local ones, tab[n + slot].
     uint32_t b_lo, b_n;
     uint32_t g_cap;
+    // the hashes of the n local entries on their own (hs[i] == tab[i].h), 4 bytes each: a lookup walks these -- the
+    // ~32 hashes of a cell are one or two cache lines -- and touches a 32-byte entry only where the hash matches
+    const uint32_t* hs;
 };
 // ghost entry (a DictEntry behind the table): w0..w2 = k-mer, h = its hash, cc = owner rank, edge = index in the
 // owner's table, ctx = its context there AFTER recomputeAdjacencies, off = state
@@ -278,10 +317,11 @@ SN_HD uint32_t dict_find_in_bucket(const DictView& d, uint32_t minimizer, const 
     if (lo >= hi) return SN_NULL_EDGE;
     const uint32_t rem = h << d.sub_bits;
     uint32_t i = lo + (uint32_t)(((uint64_t)rem * (hi - lo)) >> 32);      // < hi
-    if (d.tab[i].h < h) { do ++i; while (i < hi && d.tab[i].h < h); }
-    else while (i > lo && d.tab[i - 1].h >= h) --i;
+    const uint32_t* H = d.hs;
+    if (H[i] < h) { do ++i; while (i < hi && H[i] < h); }
+    else while (i > lo && H[i - 1] >= h) --i;
     // i = first entry of the cell with hash >= h; equal hashes are ordered by k-mer
-    for (; i < hi; ++i) {
+    for (; i < hi && H[i] == h; ++i) {
         const int c = dict_cmp(h, k, d.tab[i]);
         if (c == 0) return i;
         if (c < 0) break;

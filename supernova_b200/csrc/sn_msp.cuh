@@ -1137,7 +1137,7 @@ static __global__ void __launch_bounds__(256) k_gather_survivors(const uint4* __
     }
 }
 // surviving k-mers (bucket, hash, k-mer order) -> dictionary entries
-static __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict)
+static __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restrict__ surv, uint32_t n, DictEntry* __restrict__ dict, uint32_t* __restrict__ hs)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1145,6 +1145,13 @@ static __global__ void __launch_bounds__(256) k_make_dict(const uint4* __restric
     DictEntry e;
     e.w0 = r.x; e.w1 = r.y; e.w2 = r.z; e.cc = r.w; e.edge = SN_NULL_EDGE; e.off = 0; e.ctx = r.w >> 24; e.h = rs_hash(r);
     dict[i] = e;
+    hs[i] = e.h;
+}
+// the hashes of a finished table on their own (DictView::hs)
+static __global__ void __launch_bounds__(256) k_dict_hs(const DictEntry* __restrict__ dict, uint32_t n, uint32_t* __restrict__ hs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hs[i] = dict[i].h;
 }
 // offsets per (bucket, top sub_bits of the hash) from the bucket offsets: a search per cell
 static __global__ void __launch_bounds__(256) k_dict_cells(const DictEntry* __restrict__ dict, const uint32_t* __restrict__ bucket_off, uint32_t n_buckets, int sub_bits,

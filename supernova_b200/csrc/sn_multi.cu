@@ -475,6 +475,8 @@ int mg_replicate_dict(sn_ctx* c)
     // swap the full table in (the shard is not needed any more: its entries are in the full table)
     std::swap(c->dict.p, full.p); std::swap(c->dict.bytes, full.bytes); std::swap(c->dict.cap, full.cap);
     c->cnt.n_kmers = total; c->dict_b_lo = 0; c->dict_b_n = 0; c->ghost_cap = 0; c->dict_sharded = false;
+    CU(c->dict_hs.alloc(4 * total + 64));
+    if (total) { k_dict_hs<<<blocks_for(total, 256), 256, 0, c->st>>>(c->dict.as<DictEntry>(), (uint32_t)total, c->dict_hs.as<uint32_t>()); KCHECK("k_dict_hs"); }
     CU(c->dboff.alloc(4 * (nb + 1)));
     DevBuf& o64 = c->pool["boff64"];
     CU(o64.alloc(8 * (nb + 1)));

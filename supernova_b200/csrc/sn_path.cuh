@@ -78,7 +78,7 @@ SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t*
     if (n < SN_K) { parts[np++] = mk_gap(n); return np; }
     uint32_t itr = 0, end = n - SN_K + 1;
     while (itr != end) {
-        Kmer kmer = kmer_from_packed(rd, itr);
+        Kmer kmer = kmer_from_packed_w(rd, itr);
         bool was_rc;
         MinState ms = min_state_init(kmer);             // the k-mer's minimizer names its dictionary bucket
         uint32_t ent = dict_find_min(d, kmer, ms.minval, &was_rc);
@@ -101,16 +101,33 @@ SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t*
             // CF<K>::isRC (dna/CanonicalForm.h:84-91): is the read k-mer the RC of the edge
             // k-mer at `offset`?  The edge k-mer is the stored canonical k-mer or its RC.
             // Palindromes compare equal to themselves => not RC.
-            Kmer ek = kmer_from_packed(es.bases + es.off[u], (uint32_t)offset);
+            const uint8_t* eb = es.bases + es.off[u];
+            Kmer ek = kmer_from_packed_w(eb, (uint32_t)offset);
             bool rc = !(ek == kmer);
             uint32_t len = 1;
+            // matchLen: 16 bases per step (both sequences packed 2 bits per base)
             if (!rc) {
                 uint32_t a = itr + SN_K, b = (uint32_t)offset + SN_K;
-                while (a < n && b < esz && packed_base(rd, a) == edge_base(es, u, 0, b)) { ++len; ++a; ++b; }
+                while (a < n && b < esz) {
+                    uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
+                    const uint32_t eq = window_match(packed_window16(rd, a), packed_window16(eb, b), m);
+                    const uint32_t adv = eq < m ? eq : m;
+                    len += adv; a += adv; b += adv;
+                    if (eq < m) break;
+                }
             } else {
                 offset = (int32_t)esz - offset;
                 uint32_t a = itr + SN_K, b = (uint32_t)offset;
-                while (a < n && b < esz && packed_base(rd, a) == edge_base(es, u, 1, b)) { ++len; ++a; ++b; }
+                // the edge read backwards and complemented: base b of the RC is 3 - edge[esz - 1 - b]
+                while (a < n && b < esz) {
+                    uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
+                    const uint32_t w = packed_window16(eb, esz - b - m);                 // edge[esz-b-m .. esz-b-1] in the low 2m bits
+                    const uint32_t r = ~(rev2(w) >> (2 * (16 - m)));                     // reversed and complemented: RC bases b .. b+m-1
+                    const uint32_t eq = window_match(packed_window16(rd, a), r, m);
+                    const uint32_t adv = eq < m ? eq : m;
+                    len += adv; a += adv; b += adv;
+                    if (eq < m) break;
+                }
                 offset -= SN_K;
             }
             Part p; p.edge = u; p.off = (uint32_t)offset; p.len = len; p.elen_rc = ((esz - SN_K + 1) << 1) | (rc ? 1u : 0u);
@@ -205,7 +222,13 @@ SN_HD uint32_t score_left(const EdgeStore& es, const HbvView& h, const uint8_t* 
 
 // attemptLeftwardExtension (:133-236) / attemptRightwardExtension (:239-358).
 // `left` selects which; the two differ only in which adjacency (to_/from_) is walked.
-SN_HD bool extend_once(const EdgeStore& es, const HbvView& h, RPath& p, const uint8_t* rd, const uint8_t* q, uint32_t n, bool left)
+// `qs.get()` hands out the read's Phred bytes; it is only called when an extension is really scored (a PQVec stream is
+// decoded then, not for every read: most reads are placed end to end and never get here)
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class QS>
+SN_HD bool extend_once(const EdgeStore& es, const HbvView& h, RPath& p, const uint8_t* rd, QS& qs, uint32_t n, bool left)
 {
     if (!p.n) return false;
     uint32_t last_gap;
@@ -243,6 +266,7 @@ SN_HD bool extend_once(const EdgeStore& es, const HbvView& h, RPath& p, const ui
         if (far_in[sd + 1] - far_in[sd] != 1) return false;
     }
     int32_t least_edge = -1; uint32_t least = 0xFFFFFFFFu;
+    const uint8_t* q = qs.get();
     for (uint32_t i = 0; i < ne; ++i) if (!hanging[i] || ne == 1) {
         int32_t e = in_e[beg + i];
         uint32_t sc = left ? score_left(es, h, rd, q, last_gap, e) : score_right(es, h, rd, q, n, last_gap, e);
@@ -262,8 +286,13 @@ SN_HD bool extend_once(const EdgeStore& es, const HbvView& h, RPath& p, const ui
 }
 
 // HBVPather::algorithmTwo (:1217-1336).  `parts` is scratch of SN_MAX_PARTS.
-SN_HD void path_one_read(const DictView& d, const EdgeStore& es, const HbvView& h,
-                         const uint8_t* rd, const uint8_t* q, uint32_t n, Part* parts, RPath& path)
+struct PlainQuals { const uint8_t* q; SN_HD const uint8_t* get() { return q; } };
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class QS>
+SN_HD void path_one_read_q(const DictView& d, const EdgeStore& es, const HbvView& h,
+                           const uint8_t* rd, QS& qs, uint32_t n, Part* parts, RPath& path)
 {
     path.n = 0; path.offset = 0; path.overflow = false;
     uint32_t np = path_parts(d, es, rd, n, parts);
@@ -318,8 +347,14 @@ SN_HD void path_one_read(const DictView& d, const EdgeStore& es, const HbvView& 
         for (uint32_t i = 0; i + 1 < path.n; ++i)
             if (h.to_right[path.e[i]] != h.to_left[path.e[i + 1]]) { path.n = i + 1; break; }
     // ExtendReadPath::attemptLeftRightExtension (ExtendReadPath.cc:121-129)
-    while (extend_once(es, h, path, rd, q, n, true)) {}
-    while (extend_once(es, h, path, rd, q, n, false)) {}
+    while (extend_once(es, h, path, rd, qs, n, true)) {}
+    while (extend_once(es, h, path, rd, qs, n, false)) {}
+}
+SN_HD void path_one_read(const DictView& d, const EdgeStore& es, const HbvView& h,
+                         const uint8_t* rd, const uint8_t* q, uint32_t n, Part* parts, RPath& path)
+{
+    PlainQuals qs; qs.q = q;
+    path_one_read_q(d, es, h, rd, qs, n, parts, path);
 }
 
 }  // namespace sn

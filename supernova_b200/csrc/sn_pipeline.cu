@@ -532,8 +532,9 @@ int sn_i_msp_install_dict(sn_ctx* c, const uint4* surv, uint64_t n_surv, int bit
         k_narrow_u64<<<blocks_for(nb + 1, 256), 256, 0, c->st>>>(o64.as<uint64_t>(), nb + 1, c->dboff.as<uint32_t>());
         KCHECK("k_narrow_u64");
     }
+    CU(c->dict_hs.alloc(4 * n_surv + 64));
     if (n_surv) {
-        k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv, (uint32_t)n_surv, c->dict.as<DictEntry>());
+        k_make_dict<<<blocks_for(n_surv, 256), 256, 0, c->st>>>(surv, (uint32_t)n_surv, c->dict.as<DictEntry>(), c->dict_hs.as<uint32_t>());
         KCHECK("k_make_dict");
     }
     // lookup cells of ~32 entries: (bucket, top sub_bits of the hash)

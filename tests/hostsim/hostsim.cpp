@@ -20,11 +20,14 @@ struct Sim {
     std::vector<DictEntry> tab;
     std::vector<Link2> cand;
     std::vector<uint32_t> boff; int bits = 4;
+    mutable std::vector<uint32_t> hs;   // the entries' hashes on their own (DictView::hs)
     std::vector<uint32_t> perm;      // perm[i] = position in `tab` of the i-th input (k-mer sorted) record
     snh::Edges edges;
     snh::Hbv hbv;
     std::vector<int32_t> poffset, pedges; std::vector<uint64_t> poff;
-    DictView view() const { DictView d; d.tab = tab.data(); d.boff = boff.data(); d.n = (uint32_t)tab.size(); d.bits = bits; d.sub_bits = 0; d.b_lo = 0; d.b_n = 1u << bits; d.g_cap = 0; return d; }
+    DictView view() const { DictView d; d.tab = tab.data(); d.boff = boff.data(); d.n = (uint32_t)tab.size(); d.bits = bits; d.sub_bits = 0; d.b_lo = 0; d.b_n = 1u << bits; d.g_cap = 0;
+        if (hs.size() != tab.size()) { hs.resize(tab.size()); for (size_t i = 0; i < tab.size(); ++i) hs[i] = tab[i].h; }
+        d.hs = hs.data(); return d; }
 };
 
 extern "C" {
