@@ -224,19 +224,21 @@ static __global__ void __launch_bounds__(256) k_gs_sizes(const uint32_t* __restr
     if (s >= n_stops) return;
     uint32_t k = own_n[s];
     if (circles_only ? stype[s] != T_CIRCLE : stype[s] == T_CIRCLE) k = 0;
-    ebases[s] = k ? k + (SN_K - 1) : 0u;
+    ebases[s] = k ? (k + (SN_K - 1) + 3u) >> 2 : 0u;          // bytes of the edge in the packed store (4 bases per byte, byte aligned)
     eflag[s] = k ? 1u : 0u;
 }
 // thread per edge: the owner stop hops over the stops of its edge and leaves {edge, offset, walk orientation} at each
 static __global__ void __launch_bounds__(128) k_gs_owner_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ owners, uint32_t n_owners, uint32_t edge0,
                                                              const uint8_t* __restrict__ stype, const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint64_t base_shift,
-                                                             uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, StopInfo* __restrict__ sinfo)
+                                                             uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, StopInfo* __restrict__ sinfo,
+                                                             unsigned long long* n_kmers_on_edges)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_owners) return;
     const uint32_t sid = owners[k], e = edge0 + k;
     const int t = stype[sid];
     elen[e] = own_n[sid] + SN_K - 1;
+    atomicAdd(n_kmers_on_edges, (unsigned long long)own_n[sid]);
     etmp_off[e] = base_off[sid] + base_shift;
     uint32_t cur = sid, o = t == T_END_UP ? 1u : 0u, off = 0;
     for (;;) {
@@ -268,33 +270,49 @@ static __global__ void __launch_bounds__(128) k_gs_circle_elect(const Seg* __res
 }
 
 // ---- bases ------------------------------------------------------------------------------------------------------
+// The edge store is PACKED from the start (fastb layout: 4 bases per byte, every edge byte aligned, walk orientation):
+// a rank ORs the bases of its own segments into a zeroed store, 16 bases per atomic; the stores of all ranks add up
+// (all-reduce) to the complete one.  `slot` = 4 * byte offset of the edge + base index.
+struct PkWriter {
+    uint32_t* W; uint64_t word; uint32_t acc; bool any;
+    __device__ __forceinline__ void put(uint64_t slot, uint32_t code)
+    {
+        const uint64_t w = slot >> 4;
+        if (any && w != word) { if (acc) atomicOr(W + word, acc); acc = 0; }
+        word = w; any = true; acc |= code << (2u * (uint32_t)(slot & 15u));
+    }
+    __device__ __forceinline__ void flush() { if (any && acc) atomicOr(W + word, acc); acc = 0; }
+};
 // thread per LOCAL stop: its own k-mer, then the k-mers up to (not including) the next stop; `sinfo` is this rank's
 // slice of the global stop information, `segs` its local segments
 static __global__ void __launch_bounds__(128) k_seg_emit2(DictEntry* tab, const Link2* __restrict__ links, const uint32_t* __restrict__ stops, uint32_t n_stops,
-                                                          const StopInfo* __restrict__ sinfo, const Seg* __restrict__ segs, const uint64_t* __restrict__ etmp_off, uint8_t* __restrict__ tmp)
+                                                          const StopInfo* __restrict__ sinfo, const Seg* __restrict__ segs, const uint64_t* __restrict__ etmp_off, uint32_t* __restrict__ store)
 {
     const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
     if (sid >= n_stops) return;
     const StopInfo si = sinfo[sid];
     if (si.edge == SN_NULL_EDGE) return;
     uint32_t cur = stops[sid], o = si.off_o & 1u, off = si.off_o >> 1;
-    uint8_t* s = tmp + etmp_off[si.edge];
+    const uint64_t s0 = 4ull * etmp_off[si.edge];
+    PkWriter pw; pw.W = store; pw.word = 0; pw.acc = 0; pw.any = false;
     if (off == 0) {                                               // the owner: all K bases of its k-mer, in walk orientation
         Kmer km = entry_kmer(tab[cur]);
         if (o) km = kmer_rc(km);
-        for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(km, b);
-    } else s[SN_K - 1 + off] = (uint8_t)step_base(tab[cur], o);
+        for (int b = 0; b < SN_K; ++b) pw.put(s0 + b, kmer_base(km, b));
+    } else pw.put(s0 + SN_K - 1 + off, step_base(tab[cur], o));
     tab[cur].edge = si.edge; tab[cur].off = off;
     const Seg sg = segs[2 * sid + o];
-    if (sg.next == SN_NO_LINK) return;
-    const uint32_t steps = sg.steps_o >> 1;
-    for (uint32_t k = 1; k < steps; ++k) {
-        const Link2 lk = links[cur];
-        const uint32_t l = o ? lk.y : lk.x;
-        cur = l >> 1; o = l & 1u;
-        s[SN_K - 1 + off + k] = (uint8_t)step_base(tab[cur], o);
-        tab[cur].edge = si.edge; tab[cur].off = off + k;
+    if (sg.next != SN_NO_LINK) {
+        const uint32_t steps = sg.steps_o >> 1;
+        for (uint32_t k = 1; k < steps; ++k) {
+            const Link2 lk = links[cur];
+            const uint32_t l = o ? lk.y : lk.x;
+            cur = l >> 1; o = l & 1u;
+            pw.put(s0 + SN_K - 1 + off + k, step_base(tab[cur], o));
+            tab[cur].edge = si.edge; tab[cur].off = off + k;
+        }
     }
+    pw.flush();
 }
 // ---- circles without any stop: a few k-mers, all on this rank (a link to another rank makes a stop) -----------------
 // the walker with the smallest table index completes the loop; the circle is owned by its smallest K-MER, where
@@ -318,53 +336,89 @@ static __global__ void __launch_bounds__(128) k_lc_count(const DictEntry* __rest
     }
     own_n[m] = nk; etype[m] = T_CIRCLE;
 }
-// thread per such circle: its owner walks it; bases into this rank's private store, final edge ids into the dictionary
+static __global__ void __launch_bounds__(256) k_lc_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ etype, uint32_t n, uint32_t* __restrict__ ebytes, uint32_t* __restrict__ eflag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = etype[i] == T_CIRCLE ? own_n[i] : 0u;
+    ebytes[i] = k ? (k + (SN_K - 1) + 3u) >> 2 : 0u;
+    eflag[i] = k ? 1u : 0u;
+}
+// thread per such circle: its owner walks it; packed bases into this rank's private store, final edge ids into the dictionary
 static __global__ void __launch_bounds__(64) k_lc_emit(DictEntry* tab, const Link2* __restrict__ links, const uint32_t* __restrict__ owners, uint32_t n_owners, uint32_t edge0,
-                                                       const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint8_t* __restrict__ tmp, uint32_t* __restrict__ len_out)
+                                                       const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint8_t* __restrict__ store /* zeroed */, uint32_t* __restrict__ len_out)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_owners) return;
     const uint32_t i = owners[k], e = edge0 + k;
     len_out[k] = own_n[i] + SN_K - 1;
-    uint8_t* s = tmp + base_off[i];
+    uint8_t* s = store + base_off[i];
     const Kmer km = entry_kmer(tab[i]);
-    for (int b = 0; b < SN_K; ++b) s[b] = (uint8_t)kmer_base(km, b);
+    for (int b = 0; b < SN_K; ++b) s[b >> 2] |= (uint8_t)(kmer_base(km, b) << (2 * (b & 3)));
     tab[i].edge = e; tab[i].off = 0;
-    walk_circle_links(links, i, false, [&](uint32_t step, uint32_t j, uint32_t o) { s[SN_K - 1 + step] = (uint8_t)step_base(tab[j], o); tab[j].edge = e; tab[j].off = step; });
+    walk_circle_links(links, i, false, [&](uint32_t step, uint32_t j, uint32_t o) {
+        const uint32_t p = SN_K - 1 + step;
+        s[p >> 2] |= (uint8_t)(step_base(tab[j], o) << (2 * (p & 3)));
+        tab[j].edge = e; tab[j].off = step; });
 }
 // offsets of edges [e0, e0 + m) laid out back to back from `at` (m is tiny)
 static __global__ void k_lc_offsets(const uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, uint32_t e0, uint32_t m, uint64_t at)
 {
     if (blockIdx.x || threadIdx.x) return;
-    for (uint32_t k = 0; k < m; ++k) { etmp_off[e0 + k] = at; at += elen[e0 + k]; }
+    for (uint32_t k = 0; k < m; ++k) { etmp_off[e0 + k] = at; at += (elen[e0 + k] + 3u) >> 2; }
 }
 
 // canonicalizeCircle (BuildReadQGraph48.cc:375-397) on an assembled circle: the edge must start at the smallest
 // canonical k-mer of the circle, read in that k-mer's canonical orientation.  Thread per circle (circles are rare).
 // rot[c] = offset of that k-mer in the sequence as assembled | (it is seen reverse-complemented) << 31.
-static __global__ void __launch_bounds__(64) k_circle_canon(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
-                                                            uint32_t edge0, uint32_t n_circles, uint8_t* __restrict__ out /* same layout, offsets relative to the first circle */,
+static __global__ void __launch_bounds__(64) k_circle_canon(const uint8_t* __restrict__ store, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
+                                                            uint32_t edge0, uint32_t n_circles, uint8_t* __restrict__ out /* same layout, offsets relative to the first circle; zeroed */,
                                                             uint32_t* __restrict__ rot)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_circles) return;
     const uint32_t e = edge0 + c, n = elen[e] - (SN_K - 1);
-    const uint8_t* S = tmp + etmp_off[e];
+    const uint8_t* S = store + etmp_off[e];
     Kmer f; f.w0 = f.w1 = f.w2 = 0;
-    for (int b = 0; b < SN_K; ++b) f = kmer_succ(f, S[b]);
+    for (int b = 0; b < SN_K; ++b) f = kmer_succ(f, packed_base(S, b));
     Kmer best = f; uint32_t p = 0, rev = 0;
     { Kmer r; if (kmer_form(f, &r) == REV) { best = r; rev = 1; } }
     for (uint32_t j = 1; j < n; ++j) {
-        f = kmer_succ(f, S[SN_K - 1 + j]);
+        f = kmer_succ(f, packed_base(S, SN_K - 1 + j));
         Kmer r; const bool isrev = kmer_form(f, &r) == REV;
         const Kmer& cand = isrev ? r : f;
         if (cand < best) { best = cand; p = j; rev = isrev ? 1u : 0u; }
     }
     rot[c] = p | (rev << 31);
     uint8_t* T = out + (etmp_off[e] - etmp_off[edge0]);
-    const uint32_t len = n + SN_K - 1;
-    if (!rev) for (uint32_t i = 0; i < len; ++i) T[i] = S[(p + i) % n];
-    else { const uint32_t q = n - 1 - p; for (uint32_t i = 0; i < len; ++i) { const uint32_t x = (q + i) % n; T[i] = (uint8_t)(3u - S[n + SN_K - 2 - x]); } }
+    const uint32_t len = n + SN_K - 1, q = n - 1 - p;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t code = !rev ? packed_base(S, (p + i) % n) : 3u - packed_base(S, n + SN_K - 2 - (q + i) % n);
+        T[i >> 2] |= (uint8_t)(code << (2 * (i & 3)));
+    }
+}
+// whole-edge canonical form over the packed store
+static __global__ void __launch_bounds__(128) k_edge_form_pk(const uint8_t* __restrict__ store, const uint64_t* __restrict__ etmp_off, const uint32_t* __restrict__ elen,
+                                                             uint32_t n_edges, uint8_t* __restrict__ eflip)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges) eflip[e] = seq_form_packed(store + etmp_off[e], elen[e]) == REV ? 1 : 0;
+}
+// the final edge store: same layout, every edge in its canonical orientation (one thread per output byte)
+static __global__ void __launch_bounds__(256) k_orient_edges(const uint8_t* __restrict__ store, const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ elen,
+                                                             const uint8_t* __restrict__ eflip, uint32_t n_edges, uint64_t total_bytes, uint8_t* __restrict__ packed)
+{
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total_bytes) return;
+    uint32_t lo = 0, hi = n_edges;                     // largest e with eoff[e] <= x
+    while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (eoff[m] <= x) lo = m; else hi = m; }
+    const uint32_t e = lo;
+    if (!eflip[e]) { packed[x] = store[x]; return; }
+    const uint32_t len = elen[e], b0 = (uint32_t)(x - eoff[e]) * 4;
+    const uint8_t* s = store + eoff[e];
+    uint32_t v = 0;
+    for (uint32_t j = 0; j < 4 && b0 + j < len; ++j) v |= (packed_base(s, len - 1 - (b0 + j)) ^ 3u) << (2 * j);
+    packed[x] = (uint8_t)v;
 }
 // offsets of the members of rotated circles, then of the edges stored reverse-complemented
 static __global__ void __launch_bounds__(256) k_fix_offsets2(DictEntry* tab, uint32_t n, const uint32_t* __restrict__ elen, const uint8_t* __restrict__ eflip,

@@ -229,8 +229,11 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
            &owners = c->pool["owners"], &sinfo = c->pool["sinfo"];
     CU(own_n.alloc(4 * S + 16)); CU(eb32.alloc(4 * S + 16)); CU(eflag.alloc(4 * S + 16)); CU(base_off.alloc(8 * (S + 1))); CU(pos.alloc(8 * (S + 1))); CU(sinfo.alloc(8 * S + 16));
     const Seg* SG = g_segs->as<Seg>(); uint8_t* ST = g_stype->as<uint8_t>();
-    uint64_t total_bases = 0, n_edges = 0, circle_bases = 0, n_circles = 0;
-    DevBuf &tmpb = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"], &ebytes = c->pool["ebytes"];
+    // (sizes below are BYTES of the packed edge store: 4 bases per byte, every edge byte aligned)
+    uint64_t total_bytes_main = 0, n_edges = 0, circle_bytes = 0, n_circles = 0;
+    DevBuf &store = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"];
+    unsigned long long* n_on_edges = c->counters.as<unsigned long long>() + 5;
+    CU(cudaMemsetAsync(n_on_edges, 0, 8, c->st));
     if (S) {
         CU(cudaMemsetAsync(sinfo.p, 0xFF, 8 * S, c->st));
         k_gs_end_hop<<<blocks_for(S, 128), 128, 0, c->st>>>(SG, ST, (uint32_t)S, own_n.as<uint32_t>());
@@ -238,18 +241,18 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         k_gs_sizes<<<blocks_for(S, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), ST, 0, (uint32_t)S, eb32.as<uint32_t>(), eflag.as<uint32_t>());
         KCHECK("k_gs_sizes");
     }
-    if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &total_bases))) return r;
+    if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &total_bytes_main))) return r;
     if ((r = scan_u32(c, eflag.as<uint32_t>(), S, pos.as<uint64_t>(), &n_edges))) return r;
     // (every circle that holds a stop is owned by one of its interior stops: at most S more edges; circles without a stop come later)
     const uint64_t edge_cap = n_edges + S + 1;
     if (edge_cap >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
-    CU(owners.alloc(4 * edge_cap + 16)); CU(eflip.alloc(edge_cap + 16)); CU(etmp_off.alloc(8 * edge_cap + 16)); CU(ebytes.alloc(4 * edge_cap + 16));
+    CU(owners.alloc(4 * edge_cap + 16)); CU(eflip.alloc(edge_cap + 16)); CU(etmp_off.alloc(8 * (edge_cap + 1) + 16));
     CU(c->elen.alloc(4 * edge_cap + 16)); CU(c->eoff.alloc(8 * (edge_cap + 1)));
     if (n_edges) {
         k_scatter_flagged<<<blocks_for(S, 256), 256, 0, c->st>>>(eflag.as<uint32_t>(), pos.as<uint64_t>(), (uint32_t)S, owners.as<uint32_t>());
         KCHECK("k_scatter_flagged");
         k_gs_owner_hop<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(SG, owners.as<uint32_t>(), (uint32_t)n_edges, 0u, ST, own_n.as<uint32_t>(), base_off.as<uint64_t>(), 0ull,
-            c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>());
+            c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>(), n_on_edges);
         KCHECK("k_gs_owner_hop");
     }
     // circles that hold a stop (simpleCircle, BuildReadQGraph48.cc:348-372): numbered after the edges above
@@ -263,25 +266,25 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         if (h_found) {
             k_gs_sizes<<<blocks_for(S, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), ST, 1, (uint32_t)S, eb32.as<uint32_t>(), eflag.as<uint32_t>());
             KCHECK("k_gs_sizes");
-            if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &circle_bases))) return r;
+            if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &circle_bytes))) return r;
             if ((r = scan_u32(c, eflag.as<uint32_t>(), S, pos.as<uint64_t>(), &n_circles))) return r;
             k_scatter_flagged<<<blocks_for(S, 256), 256, 0, c->st>>>(eflag.as<uint32_t>(), pos.as<uint64_t>(), (uint32_t)S, owners.as<uint32_t>() + n_edges);
             KCHECK("k_scatter_flagged");
             k_gs_owner_hop<<<blocks_for(n_circles, 128), 128, 0, c->st>>>(SG, owners.as<uint32_t>() + n_edges, (uint32_t)n_circles, (uint32_t)n_edges, ST, own_n.as<uint32_t>(),
-                base_off.as<uint64_t>(), total_bases, c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>());
+                base_off.as<uint64_t>(), total_bytes_main, c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>(), n_on_edges);
             KCHECK("k_gs_owner_hop");
         }
     }
     const uint64_t circle0 = n_edges;                        // the circles with stops are the edges [circle0, circle0 + n_circles)
-    const uint64_t main_bases = total_bases + circle_bases;
+    const uint64_t main_bytes = total_bytes_main + circle_bytes;
+    const uint64_t main_words = (main_bytes + 3) / 4;
     // ---- bases of the local segments; (edge, offset) of the local k-mers ---------------------------------------------------
-    // (k-mers on circles WITHOUT any stop -- a handful of k-mers, all on this rank -- are found afterwards; room for them)
     uint32_t h_unreached = 0;
-    CU(tmpb.alloc(main_bases + 64));
-    CU(cudaMemsetAsync(tmpb.p, 0, main_bases + 64, c->st));
+    CU(store.alloc(4 * main_words + 64));
+    CU(cudaMemsetAsync(store.p, 0, 4 * main_words + 64, c->st));
     if (n_stops) {
         k_seg_emit2<<<blocks_for(n_stops, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), stops.as<uint32_t>(), (uint32_t)n_stops, sinfo.as<StopInfo>() + sbase[rank], segs.as<Seg>(),
-            etmp_off.as<uint64_t>(), tmpb.as<uint8_t>());
+            etmp_off.as<uint64_t>(), store.as<uint32_t>());
         KCHECK("k_seg_emit2");
     }
     if (n) {
@@ -290,40 +293,43 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         KCHECK("k_count_unreached");
         CU(cudaMemcpyAsync(&h_unreached, u32c + 23, 4, cudaMemcpyDeviceToHost, c->st));
     }
-    if (NR > 1 && c->comm->allreduce_sum(tmpb.p, main_bases, 1, c->st)) return comm_fail(c, "allreduce (edge bases)");
+    if (NR > 1 && c->comm->allreduce_sum(store.p, main_words, 4, c->st)) return comm_fail(c, "allreduce (edge bases)");     // disjoint bits: the sum is the union
+    unsigned long long h_on_edges = 0;
+    CU(cudaMemcpyAsync(&h_on_edges, n_on_edges, 8, cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     // ---- circles without a stop: local by construction (a link to another rank makes a stop) --------------------------------
-    std::vector<uint64_t> lc_all, lc_mine(2, 0);          // per rank: {circles, bases}
+    std::vector<uint64_t> lc_all, lc_mine(3, 0);          // per rank: {circles, bytes, k-mers}
     DevBuf &lc_own = c->pool["lc_own_n"], &lc_eb = c->pool["lc_eb"], &lc_flag = c->pool["lc_flag"], &lc_boff = c->pool["lc_boff"], &lc_pos = c->pool["lc_pos"],
            &lc_owners = c->pool["lc_owners"], &lc_tmp = c->pool["lc_tmp"], &lc_len = c->pool["lc_len"];
-    uint64_t lc_n = 0, lc_bases = 0;
+    uint64_t lc_n = 0, lc_bytes = 0;
     if (h_unreached) {
         CU(lc_own.alloc(4ull * n)); CU(lc_eb.alloc(4ull * n)); CU(lc_flag.alloc(4ull * n)); CU(lc_boff.alloc(8ull * (n + 1))); CU(lc_pos.alloc(8ull * (n + 1)));
         CU(cudaMemsetAsync(lc_own.p, 0, 4ull * n, c->st));
         k_lc_count<<<blocks_for(n, 128), 128, 0, c->st>>>(tab, links.as<Link2>(), n, etype.as<uint8_t>(), lc_own.as<uint32_t>());
         KCHECK("k_lc_count");
-        k_edge_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(lc_own.as<uint32_t>(), etype.as<uint8_t>(), 1, n, lc_eb.as<uint32_t>(), lc_flag.as<uint32_t>());
-        KCHECK("k_edge_sizes");
-        if ((r = scan_u32(c, lc_eb.as<uint32_t>(), n, lc_boff.as<uint64_t>(), &lc_bases))) return r;
+        k_lc_sizes<<<blocks_for(n, 256), 256, 0, c->st>>>(lc_own.as<uint32_t>(), etype.as<uint8_t>(), n, lc_eb.as<uint32_t>(), lc_flag.as<uint32_t>());
+        KCHECK("k_lc_sizes");
+        if ((r = scan_u32(c, lc_eb.as<uint32_t>(), n, lc_boff.as<uint64_t>(), &lc_bytes))) return r;
         if ((r = scan_u32(c, lc_flag.as<uint32_t>(), n, lc_pos.as<uint64_t>(), &lc_n))) return r;
         if (!lc_n) return fail(c, SN_ERR_DATA, "k-mers on no edge and on no circle (internal error)");
     }
-    lc_mine[0] = lc_n; lc_mine[1] = lc_bases;
-    if ((r = allgather_u64(c, lc_mine.data(), 2, lc_all))) return r;
-    uint64_t lc_tot_n = 0, lc_tot_b = 0, lc_e0 = 0;
+    lc_mine[0] = lc_n; lc_mine[1] = lc_bytes; lc_mine[2] = h_unreached;
+    if ((r = allgather_u64(c, lc_mine.data(), 3, lc_all))) return r;
+    uint64_t lc_tot_n = 0, lc_tot_b = 0, lc_tot_k = 0, lc_e0 = 0;
     std::vector<uint64_t> lc_cnt(NR), lc_bcnt(NR);
-    for (int q = 0; q < NR; ++q) { if (q == rank) lc_e0 = lc_tot_n; lc_cnt[q] = lc_all[2 * q]; lc_bcnt[q] = lc_all[2 * q + 1]; lc_tot_n += lc_cnt[q]; lc_tot_b += lc_bcnt[q]; }
-    const uint64_t E = n_edges + n_circles + lc_tot_n, all_bases = main_bases + lc_tot_b;
+    for (int q = 0; q < NR; ++q) { if (q == rank) lc_e0 = lc_tot_n; lc_cnt[q] = lc_all[3 * q]; lc_bcnt[q] = lc_all[3 * q + 1]; lc_tot_n += lc_cnt[q]; lc_tot_b += lc_bcnt[q]; lc_tot_k += lc_all[3 * q + 2]; }
+    const uint64_t E = n_edges + n_circles + lc_tot_n, all_bytes = main_bytes + lc_tot_b;
     if (E >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
     if (E + 1 > edge_cap) {        // the per-edge arrays were sized before the stop-less circles were known
         const uint64_t used = n_edges + n_circles;
-        if ((r = grow_keep(c, c->elen, 4 * used, 4 * (E + 1) + 16)) || (r = grow_keep(c, etmp_off, 8 * used, 8 * (E + 1) + 16))) return r;
-        CU(owners.alloc(4 * (E + 1) + 16)); CU(eflip.alloc(E + 17)); CU(ebytes.alloc(4 * (E + 1) + 16)); CU(c->eoff.alloc(8 * (E + 2)));
+        if ((r = grow_keep(c, c->elen, 4 * used, 4 * (E + 1) + 16)) || (r = grow_keep(c, etmp_off, 8 * used, 8 * (E + 2) + 16))) return r;
+        CU(owners.alloc(4 * (E + 1) + 16)); CU(eflip.alloc(E + 17)); CU(c->eoff.alloc(8 * (E + 2)));
     }
     if (lc_tot_n) {
         // the local circles' bases and lengths are gathered behind the rest of the edge store
-        if ((r = grow_keep(c, tmpb, main_bases, all_bases + 64))) return r;
-        CU(lc_tmp.alloc(lc_bases + 64)); CU(lc_len.alloc(4 * (lc_n + 1))); CU(lc_owners.alloc(4 * (lc_n + 1)));
+        if ((r = grow_keep(c, store, main_bytes, all_bytes + 64))) return r;
+        CU(lc_tmp.alloc(lc_bytes + 64)); CU(lc_len.alloc(4 * (lc_n + 1))); CU(lc_owners.alloc(4 * (lc_n + 1)));
+        CU(cudaMemsetAsync(lc_tmp.p, 0, lc_bytes + 64, c->st));
         if (lc_n) {
             k_scatter_flagged<<<blocks_for(n, 256), 256, 0, c->st>>>(lc_flag.as<uint32_t>(), lc_pos.as<uint64_t>(), n, lc_owners.as<uint32_t>());
             KCHECK("k_scatter_flagged");
@@ -331,40 +337,39 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
                 lc_own.as<uint32_t>(), lc_boff.as<uint64_t>(), lc_tmp.as<uint8_t>(), lc_len.as<uint32_t>());
             KCHECK("k_lc_emit");
         }
-        if ((r = allgatherv_dev(c, lc_tmp.p, tmpb.as<uint8_t>() + main_bases, lc_bcnt, 1))) return r;
+        if ((r = allgatherv_dev(c, lc_tmp.p, store.as<uint8_t>() + main_bytes, lc_bcnt, 1))) return r;
         if ((r = allgatherv_dev(c, lc_len.p, c->elen.as<uint32_t>() + n_edges + n_circles, lc_cnt, 4))) return r;
-        k_lc_offsets<<<1, 1, 0, c->st>>>(c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), (uint32_t)(n_edges + n_circles), (uint32_t)lc_tot_n, main_bases);
+        k_lc_offsets<<<1, 1, 0, c->st>>>(c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), (uint32_t)(n_edges + n_circles), (uint32_t)lc_tot_n, main_bytes);
         KCHECK("k_lc_offsets");
     }
     // ---- circles with stops start where canonicalizeCircle starts them ------------------------------------------------------
     DevBuf &crot = c->pool["crot"], &ctmp = c->pool["ctmp"];
     CU(crot.alloc(4 * n_circles + 16));
     if (n_circles) {
-        CU(ctmp.alloc(circle_bases + 64));
-        k_circle_canon<<<blocks_for(n_circles, 64), 64, 0, c->st>>>(tmpb.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), (uint32_t)circle0, (uint32_t)n_circles,
+        CU(ctmp.alloc(circle_bytes + 64));
+        CU(cudaMemsetAsync(ctmp.p, 0, circle_bytes + 64, c->st));
+        k_circle_canon<<<blocks_for(n_circles, 64), 64, 0, c->st>>>(store.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), (uint32_t)circle0, (uint32_t)n_circles,
             ctmp.as<uint8_t>(), crot.as<uint32_t>());
         KCHECK("k_circle_canon");
-        CU(cudaMemcpyAsync(tmpb.as<uint8_t>() + total_bases, ctmp.p, circle_bases, cudaMemcpyDeviceToDevice, c->st));
+        CU(cudaMemcpyAsync(store.as<uint8_t>() + total_bytes_main, ctmp.p, circle_bytes, cudaMemcpyDeviceToDevice, c->st));
     }
-    // ---- canonical orientation of every edge, offsets, packed store --------------------------------------------------------
-    if (E) {
-        k_edge_form<<<blocks_for(E, 128), 128, 0, c->st>>>(tmpb.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), (uint32_t)E, eflip.as<uint8_t>());
-        KCHECK("k_edge_form");
-        if (n) { k_fix_offsets2<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, n, c->elen.as<uint32_t>(), eflip.as<uint8_t>(), (uint32_t)circle0, (uint32_t)n_circles, crot.as<uint32_t>()); KCHECK("k_fix_offsets2"); }
-        k_edge_bytes<<<blocks_for(E, 256), 256, 0, c->st>>>(c->elen.as<uint32_t>(), (uint32_t)E, ebytes.as<uint32_t>());
-        KCHECK("k_edge_bytes");
-    }
-    uint64_t total_bytes = 0;
-    if ((r = scan_u32(c, ebytes.as<uint32_t>(), E, c->eoff.as<uint64_t>(), &total_bytes))) return r;
+    // ---- canonical orientation of every edge, offsets, final store (same layout as the walk-orientation store) --------------------
+    const uint64_t total_bytes = all_bytes;
+    CU(cudaMemcpyAsync(etmp_off.as<uint64_t>() + E, &total_bytes, 8, cudaMemcpyHostToDevice, c->st));
     CU(c->ebases.alloc(total_bytes + 64));
     CU(cudaMemsetAsync((char*)c->ebases.p + total_bytes, 0, 64, c->st));
-    if (total_bytes) {
-        k_pack_edges<<<blocks_for(total_bytes, 256), 256, 0, c->st>>>(tmpb.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(),
-            c->eoff.as<uint64_t>(), (uint32_t)E, total_bytes, c->ebases.as<uint8_t>());
-        KCHECK("k_pack_edges");
+    if (E) {
+        k_edge_form_pk<<<blocks_for(E, 128), 128, 0, c->st>>>(store.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), (uint32_t)E, eflip.as<uint8_t>());
+        KCHECK("k_edge_form_pk");
+        if (n) { k_fix_offsets2<<<blocks_for(n, 256), 256, 0, c->st>>>(tab, n, c->elen.as<uint32_t>(), eflip.as<uint8_t>(), (uint32_t)circle0, (uint32_t)n_circles, crot.as<uint32_t>()); KCHECK("k_fix_offsets2"); }
+        k_orient_edges<<<blocks_for(total_bytes, 256), 256, 0, c->st>>>(store.as<uint8_t>(), etmp_off.as<uint64_t>(), c->elen.as<uint32_t>(), eflip.as<uint8_t>(),
+            (uint32_t)E, total_bytes, c->ebases.as<uint8_t>());
+        KCHECK("k_orient_edges");
     }
+    CU(cudaMemcpyAsync(c->eoff.p, etmp_off.p, 8 * (E + 1), cudaMemcpyDeviceToDevice, c->st));
     t_end(c, "edges");
-    c->cnt.n_edges = E; c->cnt.n_edge_bases = all_bases;
+    const uint64_t kmers_on_edges = (uint64_t)h_on_edges + lc_tot_k;
+    c->cnt.n_edges = E; c->cnt.n_edge_bases = kmers_on_edges + (uint64_t)(SN_K - 1) * E;
     // the edges in host memory: on one rank of a multi-GPU job; the others keep them on the device until asked
     // (the copy runs on the second stream, under the HBV stage; sn_build_hbv / the getters complete it)
     c->edges_host_stale = true;
@@ -375,7 +380,6 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     if ((r = allgather_u64(c, nk_mine.data(), 1, nk_all))) return r;
     uint64_t n_total = 0; for (uint64_t v : nk_all) n_total += v;
     c->mg_n_kmers_total = n_total;
-    const uint64_t kmers_on_edges = all_bases - (uint64_t)(SN_K - 1) * E;
     if (kmers_on_edges != n_total)
         return fail(c, SN_ERR_DATA, "edge stage covered " + std::to_string(kmers_on_edges) + " of " + std::to_string(n_total) + " dictionary k-mers");
     c->stage = 3;
