@@ -199,14 +199,16 @@ static __global__ void __launch_bounds__(256) k_seg_globalize(const Seg* __restr
 }
 
 // ---- the gathered stop table: lengths, owners, edge ids, offsets (identical on every rank) --------------------
-static __global__ void __launch_bounds__(128) k_gs_end_hop(const Seg* __restrict__ segs, const uint8_t* __restrict__ stype, uint32_t n_stops, uint32_t* __restrict__ own_n)
+// (a rank does this for ITS stops [first, first + count) only: 1/N of the hops; `own_n` is indexed by local stop)
+static __global__ void __launch_bounds__(128) k_gs_end_hop(const Seg* __restrict__ segs, const uint8_t* __restrict__ stype, uint32_t first, uint32_t count, uint32_t* __restrict__ own_n)
 {
-    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sid >= n_stops) return;
-    const int t = stype[sid];
-    uint32_t mine = t == T_SINGLE ? 1u : 0u;
-    if (t == T_END_DOWN || t == T_END_UP) {
-        uint32_t cur = sid, o = t == T_END_UP ? 1u : 0u, nk = 1;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t sid = first + t;
+    const int ty = stype[sid];
+    uint32_t mine = ty == T_SINGLE ? 1u : 0u;
+    if (ty == T_END_DOWN || ty == T_END_UP) {
+        uint32_t cur = sid, o = ty == T_END_UP ? 1u : 0u, nk = 1;
         for (;;) {
             const Seg sg = segs[2 * cur + o];
             if (sg.next == SN_NO_LINK) break;
@@ -214,10 +216,10 @@ static __global__ void __launch_bounds__(128) k_gs_end_hop(const Seg* __restrict
         }
         if (sid <= cur) mine = nk;                               // the other end walks the same edge; the smaller stop owns it
     }
-    own_n[sid] = mine;
+    own_n[t] = mine;
 }
 // phase 0: singles and edges with ends; phase 1: circles
-static __global__ void __launch_bounds__(256) k_gs_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ stype, int circles_only, uint32_t n_stops,
+static __global__ void __launch_bounds__(256) k_gs_sizes(const uint32_t* __restrict__ own_n, const uint8_t* __restrict__ stype /* of the same stops */, int circles_only, uint32_t n_stops,
                                                          uint32_t* __restrict__ ebases, uint32_t* __restrict__ eflag)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,22 +229,23 @@ static __global__ void __launch_bounds__(256) k_gs_sizes(const uint32_t* __restr
     ebases[s] = k ? (k + (SN_K - 1) + 3u) >> 2 : 0u;          // bytes of the edge in the packed store (4 bases per byte, byte aligned)
     eflag[s] = k ? 1u : 0u;
 }
-// thread per edge: the owner stop hops over the stops of its edge and leaves {edge, offset, walk orientation} at each
-static __global__ void __launch_bounds__(128) k_gs_owner_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ owners, uint32_t n_owners, uint32_t edge0,
+// thread per edge OWNED BY A LOCAL STOP: the owner hops over the stops of its edge -- wherever they live -- and leaves
+// {edge + 1, offset, walk orientation} for each in `sinfo` (indexed by global stop; zeroed: the ranks' arrays add up)
+static __global__ void __launch_bounds__(128) k_gs_owner_hop(const Seg* __restrict__ segs, const uint32_t* __restrict__ owners /* local stop ids */, uint32_t n_owners, uint32_t edge0, uint32_t first,
                                                              const uint8_t* __restrict__ stype, const uint32_t* __restrict__ own_n, const uint64_t* __restrict__ base_off, uint64_t base_shift,
                                                              uint32_t* __restrict__ elen, uint64_t* __restrict__ etmp_off, StopInfo* __restrict__ sinfo,
                                                              unsigned long long* n_kmers_on_edges)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_owners) return;
-    const uint32_t sid = owners[k], e = edge0 + k;
+    const uint32_t ls = owners[k], sid = first + ls, e = edge0 + k;    // e: the edge's global id; elen / etmp_off are this rank's slices (indexed by k)
     const int t = stype[sid];
-    elen[e] = own_n[sid] + SN_K - 1;
-    atomicAdd(n_kmers_on_edges, (unsigned long long)own_n[sid]);
-    etmp_off[e] = base_off[sid] + base_shift;
+    elen[k] = own_n[ls] + SN_K - 1;
+    atomicAdd(n_kmers_on_edges, (unsigned long long)own_n[ls]);
+    etmp_off[k] = base_off[ls] + base_shift;
     uint32_t cur = sid, o = t == T_END_UP ? 1u : 0u, off = 0;
     for (;;) {
-        StopInfo si; si.edge = e; si.off_o = (off << 1) | o;
+        StopInfo si; si.edge = e + 1u; si.off_o = (off << 1) | o;
         sinfo[cur] = si;
         const Seg sg = segs[2 * cur + o];
         if (sg.next == SN_NO_LINK) break;
@@ -251,12 +254,13 @@ static __global__ void __launch_bounds__(128) k_gs_owner_hop(const Seg* __restri
     }
 }
 // interior stops no edge end reached lie on circles: the smallest stop of each becomes its owner
-static __global__ void __launch_bounds__(128) k_gs_circle_elect(const Seg* __restrict__ segs, uint8_t* __restrict__ stype, const StopInfo* __restrict__ sinfo, uint32_t n_stops,
-                                                                uint32_t* __restrict__ own_n, uint32_t* n_found)
+static __global__ void __launch_bounds__(128) k_gs_circle_elect(const Seg* __restrict__ segs, uint8_t* __restrict__ stype, const StopInfo* __restrict__ sinfo, uint32_t first, uint32_t count,
+                                                                uint32_t* __restrict__ own_n /* local */, uint32_t* n_found)
 {
-    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sid >= n_stops) return;
-    if (stype[sid] != T_INTERIOR || sinfo[sid].edge != SN_NULL_EDGE) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t sid = first + t;
+    if (stype[sid] != T_INTERIOR || sinfo[sid].edge != 0u) return;
     uint32_t cur = sid, o = 0, nk = 0;
     for (;;) {
         const Seg sg = segs[2 * cur + o];
@@ -265,8 +269,14 @@ static __global__ void __launch_bounds__(128) k_gs_circle_elect(const Seg* __res
         if (cur == sid) break;
         if (cur < sid) return;                                   // a smaller stop owns this circle
     }
-    own_n[sid] = nk; stype[sid] = T_CIRCLE;
+    own_n[t] = nk; stype[sid] = T_CIRCLE;
     atomicAdd(n_found, 1u);
+}
+// sinfo += add over a range (the circle phase is reduced separately: the first phase's sums must not be added twice)
+static __global__ void __launch_bounds__(256) k_sinfo_add(StopInfo* __restrict__ acc, const StopInfo* __restrict__ add, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { acc[i].edge += add[i].edge; acc[i].off_o += add[i].off_o; }
 }
 
 // ---- bases ------------------------------------------------------------------------------------------------------
@@ -290,8 +300,9 @@ static __global__ void __launch_bounds__(128) k_seg_emit2(DictEntry* tab, const 
 {
     const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
     if (sid >= n_stops) return;
-    const StopInfo si = sinfo[sid];
-    if (si.edge == SN_NULL_EDGE) return;
+    StopInfo si = sinfo[sid];
+    if (si.edge == 0u) return;                                    // (edge + 1; 0 = on no edge yet)
+    si.edge -= 1u;
     uint32_t cur = stops[sid], o = si.off_o & 1u, off = si.off_o >> 1;
     const uint64_t s0 = 4ull * etmp_off[si.edge];
     PkWriter pw; pw.W = store; pw.word = 0; pw.acc = 0; pw.any = false;

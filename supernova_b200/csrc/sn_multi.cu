@@ -224,57 +224,75 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         if (h_err) return fail(c, SN_ERR_DATA, "a chain continues on a k-mer its owner does not list as a stop (internal error)");
         g_segs = &gsegs; g_stype = &gstype;
     }
-    // ---- lengths, owners, edge ids and offsets: the same on every rank ----------------------------------------------------
+    // ---- lengths, owners, edge ids and offsets -------------------------------------------------------------------------------
+    // Every rank hops only for the edges whose OWNER (the smaller end stop) is one of its stops -- 1/N of the hops over the
+    // gathered table.  Edge ids are global by construction (owners in stop order = rank order): a rank's edges are one
+    // contiguous id range; lengths and store offsets are gathered, the {edge, offset} of the stops is summed (all-reduce of
+    // arrays that are zero wherever another rank's edge passes).
+    const uint32_t L = (uint32_t)n_stops, first = (uint32_t)sbase[rank];
     DevBuf &own_n = c->pool["g_own_n"], &eb32 = c->pool["g_eb32"], &eflag = c->pool["g_eflag"], &base_off = c->pool["g_base_off"], &pos = c->pool["g_pos"],
-           &owners = c->pool["owners"], &sinfo = c->pool["sinfo"];
-    CU(own_n.alloc(4 * S + 16)); CU(eb32.alloc(4 * S + 16)); CU(eflag.alloc(4 * S + 16)); CU(base_off.alloc(8 * (S + 1))); CU(pos.alloc(8 * (S + 1))); CU(sinfo.alloc(8 * S + 16));
+           &owners = c->pool["owners"], &sinfo = c->pool["sinfo"], &sinfo2 = c->pool["sinfo2"], &elen_l = c->pool["g_elen_l"], &eoff_l = c->pool["g_eoff_l"];
+    CU(own_n.alloc(4ull * L + 16)); CU(eb32.alloc(4ull * L + 16)); CU(eflag.alloc(4ull * L + 16)); CU(base_off.alloc(8ull * (L + 1))); CU(pos.alloc(8ull * (L + 1)));
+    CU(sinfo.alloc(8 * S + 16)); CU(owners.alloc(4ull * L + 16));
     const Seg* SG = g_segs->as<Seg>(); uint8_t* ST = g_stype->as<uint8_t>();
     // (sizes below are BYTES of the packed edge store: 4 bases per byte, every edge byte aligned)
     uint64_t total_bytes_main = 0, n_edges = 0, circle_bytes = 0, n_circles = 0;
     DevBuf &store = c->pool["tmpb"], &eflip = c->pool["eflip"], &etmp_off = c->pool["etmp_off"];
     unsigned long long* n_on_edges = c->counters.as<unsigned long long>() + 5;
     CU(cudaMemsetAsync(n_on_edges, 0, 8, c->st));
-    if (S) {
-        CU(cudaMemsetAsync(sinfo.p, 0xFF, 8 * S, c->st));
-        k_gs_end_hop<<<blocks_for(S, 128), 128, 0, c->st>>>(SG, ST, (uint32_t)S, own_n.as<uint32_t>());
-        KCHECK("k_gs_end_hop");
-        k_gs_sizes<<<blocks_for(S, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), ST, 0, (uint32_t)S, eb32.as<uint32_t>(), eflag.as<uint32_t>());
-        KCHECK("k_gs_sizes");
-    }
-    if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &total_bytes_main))) return r;
-    if ((r = scan_u32(c, eflag.as<uint32_t>(), S, pos.as<uint64_t>(), &n_edges))) return r;
-    // (every circle that holds a stop is owned by one of its interior stops: at most S more edges; circles without a stop come later)
-    const uint64_t edge_cap = n_edges + S + 1;
-    if (edge_cap >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
-    CU(owners.alloc(4 * edge_cap + 16)); CU(eflip.alloc(edge_cap + 16)); CU(etmp_off.alloc(8 * (edge_cap + 1) + 16));
-    CU(c->elen.alloc(4 * edge_cap + 16)); CU(c->eoff.alloc(8 * (edge_cap + 1)));
-    if (n_edges) {
-        k_scatter_flagged<<<blocks_for(S, 256), 256, 0, c->st>>>(eflag.as<uint32_t>(), pos.as<uint64_t>(), (uint32_t)S, owners.as<uint32_t>());
-        KCHECK("k_scatter_flagged");
-        k_gs_owner_hop<<<blocks_for(n_edges, 128), 128, 0, c->st>>>(SG, owners.as<uint32_t>(), (uint32_t)n_edges, 0u, ST, own_n.as<uint32_t>(), base_off.as<uint64_t>(), 0ull,
-            c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>(), n_on_edges);
-        KCHECK("k_gs_owner_hop");
-    }
+    CU(cudaMemsetAsync(sinfo.p, 0, 8 * S + 16, c->st));
+    // one phase: sizes of the edges my stops own -> their global ids and store offsets -> hop -> gather / sum
+    auto phase = [&](int circles, uint64_t edge_base, uint64_t byte_base, DevBuf& si, uint64_t* n_out, uint64_t* bytes_out) -> int {
+        uint64_t my_bytes = 0, my_n = 0;
+        if (L) { k_gs_sizes<<<blocks_for(L, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), ST + first, circles, L, eb32.as<uint32_t>(), eflag.as<uint32_t>()); KCHECK("k_gs_sizes"); }
+        int rr;
+        if ((rr = scan_u32(c, eb32.as<uint32_t>(), L, base_off.as<uint64_t>(), &my_bytes))) return rr;
+        if ((rr = scan_u32(c, eflag.as<uint32_t>(), L, pos.as<uint64_t>(), &my_n))) return rr;
+        std::vector<uint64_t> all, mine = {my_n, my_bytes};
+        if ((rr = allgather_u64(c, mine.data(), 2, all))) return rr;
+        uint64_t tot_n = 0, tot_b = 0, e0 = 0, b0 = 0;
+        std::vector<uint64_t> cnt(NR);
+        for (int q = 0; q < NR; ++q) { if (q == rank) { e0 = tot_n; b0 = tot_b; } cnt[q] = all[2 * q]; tot_n += all[2 * q]; tot_b += all[2 * q + 1]; }
+        *n_out = tot_n; *bytes_out = tot_b;
+        if (edge_base + tot_n + 1 >= (1ull << 31)) return fail(c, SN_ERR_ARG, "more than 2^31 edges");
+        // room for the global per-edge arrays (keeps what earlier phases wrote)
+        if ((rr = grow_keep(c, c->elen, 4 * edge_base, 4 * (edge_base + tot_n + 1) + 16)) || (rr = grow_keep(c, etmp_off, 8 * edge_base, 8 * (edge_base + tot_n + 2) + 16))) return rr;
+        CU(elen_l.alloc(4 * my_n + 16)); CU(eoff_l.alloc(8 * my_n + 16));
+        if (my_n) {
+            k_scatter_flagged<<<blocks_for(L, 256), 256, 0, c->st>>>(eflag.as<uint32_t>(), pos.as<uint64_t>(), L, owners.as<uint32_t>());
+            KCHECK("k_scatter_flagged");
+            k_gs_owner_hop<<<blocks_for(my_n, 128), 128, 0, c->st>>>(SG, owners.as<uint32_t>(), (uint32_t)my_n, (uint32_t)(edge_base + e0), first, ST, own_n.as<uint32_t>(), base_off.as<uint64_t>(),
+                byte_base + b0, elen_l.as<uint32_t>(), eoff_l.as<uint64_t>(), si.as<StopInfo>(), n_on_edges);
+            KCHECK("k_gs_owner_hop");
+        }
+        if ((rr = allgatherv_dev(c, elen_l.p, c->elen.as<uint32_t>() + edge_base, cnt, 4))) return rr;
+        if ((rr = allgatherv_dev(c, eoff_l.p, etmp_off.as<uint64_t>() + edge_base, cnt, 8))) return rr;
+        if (NR > 1 && tot_n && c->comm->allreduce_sum(si.p, 2 * S, 4, c->st)) return comm_fail(c, "allreduce (stop info)");
+        return SN_OK;
+    };
+    if (L) { k_gs_end_hop<<<blocks_for(L, 128), 128, 0, c->st>>>(SG, ST, first, L, own_n.as<uint32_t>()); KCHECK("k_gs_end_hop"); }
+    CU(c->elen.alloc(16)); CU(etmp_off.alloc(16));
+    if ((r = phase(0, 0, 0, sinfo, &n_edges, &total_bytes_main))) return r;
     // circles that hold a stop (simpleCircle, BuildReadQGraph48.cc:348-372): numbered after the edges above
-    if (S) {
+    {
         CU(cudaMemsetAsync(u32c + 4, 0, 4, c->st));
-        k_gs_circle_elect<<<blocks_for(S, 128), 128, 0, c->st>>>(SG, ST, sinfo.as<StopInfo>(), (uint32_t)S, own_n.as<uint32_t>(), u32c + 4);
-        KCHECK("k_gs_circle_elect");
+        if (L) { k_gs_circle_elect<<<blocks_for(L, 128), 128, 0, c->st>>>(SG, ST, sinfo.as<StopInfo>(), first, L, own_n.as<uint32_t>(), u32c + 4); KCHECK("k_gs_circle_elect"); }
         uint32_t h_found = 0;
         CU(cudaMemcpyAsync(&h_found, u32c + 4, 4, cudaMemcpyDeviceToHost, c->st));
         CU(cudaStreamSynchronize(c->st));
-        if (h_found) {
-            k_gs_sizes<<<blocks_for(S, 256), 256, 0, c->st>>>(own_n.as<uint32_t>(), ST, 1, (uint32_t)S, eb32.as<uint32_t>(), eflag.as<uint32_t>());
-            KCHECK("k_gs_sizes");
-            if ((r = scan_u32(c, eb32.as<uint32_t>(), S, base_off.as<uint64_t>(), &circle_bytes))) return r;
-            if ((r = scan_u32(c, eflag.as<uint32_t>(), S, pos.as<uint64_t>(), &n_circles))) return r;
-            k_scatter_flagged<<<blocks_for(S, 256), 256, 0, c->st>>>(eflag.as<uint32_t>(), pos.as<uint64_t>(), (uint32_t)S, owners.as<uint32_t>() + n_edges);
-            KCHECK("k_scatter_flagged");
-            k_gs_owner_hop<<<blocks_for(n_circles, 128), 128, 0, c->st>>>(SG, owners.as<uint32_t>() + n_edges, (uint32_t)n_circles, (uint32_t)n_edges, ST, own_n.as<uint32_t>(),
-                base_off.as<uint64_t>(), total_bytes_main, c->elen.as<uint32_t>(), etmp_off.as<uint64_t>(), sinfo.as<StopInfo>(), n_on_edges);
-            KCHECK("k_gs_owner_hop");
+        std::vector<uint64_t> all, mine(1, h_found);
+        if ((r = allgather_u64(c, mine.data(), 1, all))) return r;
+        uint64_t any = 0; for (uint64_t v : all) any += v;
+        if (any) {
+            CU(sinfo2.alloc(8 * S + 16));
+            CU(cudaMemsetAsync(sinfo2.p, 0, 8 * S + 16, c->st));
+            if ((r = phase(1, n_edges, total_bytes_main, sinfo2, &n_circles, &circle_bytes))) return r;
+            k_sinfo_add<<<blocks_for(S, 256), 256, 0, c->st>>>(sinfo.as<StopInfo>(), sinfo2.as<StopInfo>(), (uint32_t)S);
+            KCHECK("k_sinfo_add");
         }
     }
+    const uint64_t edge_cap = n_edges + n_circles + 1;
+    CU(eflip.alloc(edge_cap + 16)); CU(c->eoff.alloc(8 * (edge_cap + 1)));
     const uint64_t circle0 = n_edges;                        // the circles with stops are the edges [circle0, circle0 + n_circles)
     const uint64_t main_bytes = total_bytes_main + circle_bytes;
     const uint64_t main_words = (main_bytes + 3) / 4;
@@ -313,7 +331,7 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
         if ((r = scan_u32(c, lc_flag.as<uint32_t>(), n, lc_pos.as<uint64_t>(), &lc_n))) return r;
         if (!lc_n) return fail(c, SN_ERR_DATA, "k-mers on no edge and on no circle (internal error)");
     }
-    lc_mine[0] = lc_n; lc_mine[1] = lc_bytes; lc_mine[2] = h_unreached;
+    lc_mine[0] = lc_n; lc_mine[1] = lc_bytes; lc_mine[2] = (uint64_t)h_unreached + (uint64_t)h_on_edges;      // k-mers this rank's edges and circles hold
     if ((r = allgather_u64(c, lc_mine.data(), 3, lc_all))) return r;
     uint64_t lc_tot_n = 0, lc_tot_b = 0, lc_tot_k = 0, lc_e0 = 0;
     std::vector<uint64_t> lc_cnt(NR), lc_bcnt(NR);
@@ -323,7 +341,7 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     if (E + 1 > edge_cap) {        // the per-edge arrays were sized before the stop-less circles were known
         const uint64_t used = n_edges + n_circles;
         if ((r = grow_keep(c, c->elen, 4 * used, 4 * (E + 1) + 16)) || (r = grow_keep(c, etmp_off, 8 * used, 8 * (E + 2) + 16))) return r;
-        CU(owners.alloc(4 * (E + 1) + 16)); CU(eflip.alloc(E + 17)); CU(c->eoff.alloc(8 * (E + 2)));
+        CU(eflip.alloc(E + 17)); CU(c->eoff.alloc(8 * (E + 2)));
     }
     if (lc_tot_n) {
         // the local circles' bases and lengths are gathered behind the rest of the edge store
@@ -368,7 +386,7 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     }
     CU(cudaMemcpyAsync(c->eoff.p, etmp_off.p, 8 * (E + 1), cudaMemcpyDeviceToDevice, c->st));
     t_end(c, "edges");
-    const uint64_t kmers_on_edges = (uint64_t)h_on_edges + lc_tot_k;
+    const uint64_t kmers_on_edges = lc_tot_k;
     c->cnt.n_edges = E; c->cnt.n_edge_bases = kmers_on_edges + (uint64_t)(SN_K - 1) * E;
     // the edges in host memory: on one rank of a multi-GPU job; the others keep them on the device until asked
     // (the copy runs on the second stream, under the HBV stage; sn_build_hbv / the getters complete it)
