@@ -790,7 +790,8 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
                 uint32_t min_freq, uint32_t min_bc, int has_bc,
                 uint4* __restrict__ out, uint64_t out_cap, unsigned long long* out_cursor,
                 uint64_t* __restrict__ seg_base, uint32_t* __restrict__ seg_cnt,
-                unsigned long long* n_distinct, uint32_t* err)
+                unsigned long long* n_distinct, uint32_t* err,
+                const uint2* __restrict__ vbucket /* {bucket, depth0 | prefix0 << 8} per CTA: a heavy bucket is shared out by hash prefix */, uint32_t n_virtual)
 {
     static_assert(4 * SLOTS <= 32 * T, "the survivor ordering parks 2 x SLOTS u16 in the staging buffer");
     static_assert(SLOTS % T == 0 && SLOTS / T <= 32, "slots per thread");
@@ -799,7 +800,14 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BcSmem2<T, SLOTS>& S = *reinterpret_cast<BcSmem2<T, SLOTS>*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t bkt = blockIdx.x;
+    // A bucket with many records (low-complexity sequence, a repeat family: 10^5..10^7 k-mers under one minimizer) is shared
+    // out over 2^d0 CTAs: CTA j counts the k-mers whose hash starts with the d0-bit prefix j (every CTA streams all of the
+    // bucket's records, but its table only takes its own share), so the passes a big bucket needs run side by side
+    // instead of one after the other on one CTA.  Prefix order is hash order: the CTAs' outputs concatenate.
+    if (blockIdx.x >= n_virtual) return;
+    const uint2 vb = vbucket[blockIdx.x];
+    const uint32_t bkt = vb.x, d0 = vb.y & 0xFFu, s0 = vb.y >> 8;
+    const uint32_t vslot = blockIdx.x;
     if (bkt >= n_buckets) return;
     {
         bool any = false;
@@ -812,7 +820,7 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
     __syncthreads();
     uint32_t phase = 0;
     const uint32_t* recw = reinterpret_cast<const uint32_t*>(S.rec);
-    uint32_t depth = 0, sub = 0, mode = 0;            // passes: see k_bucket_count
+    uint32_t depth = d0, sub = s0, mode = 0;          // passes: see k_bucket_count (this CTA's root is the prefix s0 of d0 bits)
     uint32_t total = 0, run = 0;
     uint64_t base = 0;
     for (;;) {
@@ -1093,26 +1101,61 @@ k_bucket_count2(const uint4* __restrict__ recs, const uint64_t* __restrict__ buc
         if (tid == 0) S.over = 0;
         __syncthreads();
         if (overflowed) {
-            if (depth >= 20u) { if (tid == 0) atomicOr(err, 2u); total = 0; break; }
+            if (depth >= 30u) { if (tid == 0) atomicOr(err, 2u); total = 0; break; }
             if (mode == 0u) mode = 1u;
             ++depth; sub <<= 1;
             continue;
         }
-        while (depth > 0u && (sub & 1u)) { --depth; sub >>= 1; }
-        if (depth == 0u) {
+        while (depth > d0 && (sub & 1u)) { --depth; sub >>= 1; }
+        if (depth == d0) {
             if (mode == 2u) break;
             if (tid == 0) S.out_base = total ? atomicAdd(out_cursor, (unsigned long long)total) : 0ull;
             __syncthreads();
             base = S.out_base;
-            mode = 2u; run = 0; depth = 1; sub = 0;
+            mode = 2u; run = 0; depth = d0 + 1u; sub = s0 << 1;
             continue;
         }
         sub |= 1u;
     }
     if (tid == 0) {
-        seg_base[bkt] = base; seg_cnt[bkt] = total;
+        seg_base[vslot] = base; seg_cnt[vslot] = total;
         if (S.ndist) atomicAdd(n_distinct, (unsigned long long)S.ndist);
     }
+}
+
+// ---- virtual buckets: how many CTAs a bucket gets (1, or 2^d for a heavy one) and the CTA table ------------------------
+#define SN_BC_HEAVY_RECORDS 192u         // a bucket holds ~100 records; above this it is shared out, one CTA per `heavy` records (repeat-family test set: 748 ms unshared, 31.6 ms at 1024, 7.0 ms at 64)
+__device__ __forceinline__ uint32_t vb_depth(uint64_t n_rec, uint32_t heavy)
+{
+    uint32_t d = 0;
+    while (d < 12u && (n_rec >> d) > heavy) ++d;
+    return d;
+}
+static __global__ void __launch_bounds__(256) k_vb_count(const uint64_t* __restrict__ bucket_off, uint32_t n_buckets, uint32_t n_seg, uint32_t heavy, uint32_t* __restrict__ nv)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint64_t r = 0;
+    for (uint32_t sg = 0; sg < n_seg; ++sg) r += bucket_off[(uint64_t)sg * n_buckets + b + 1] - bucket_off[(uint64_t)sg * n_buckets + b];
+    nv[b] = 1u << vb_depth(r, heavy);
+}
+static __global__ void __launch_bounds__(256) k_vb_fill(const uint32_t* __restrict__ nv, const uint64_t* __restrict__ first, uint32_t n_buckets, uint2* __restrict__ vbucket)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint32_t n = nv[b]; uint32_t d = 0;
+    while ((1u << d) < n) ++d;
+    uint2* o = vbucket + first[b];
+    for (uint32_t j = 0; j < n; ++j) o[j] = make_uint2(b, d | (j << 8));
+}
+// survivors per real bucket = sum over its virtual buckets
+static __global__ void __launch_bounds__(256) k_vb_sum(const uint32_t* __restrict__ vcnt, const uint64_t* __restrict__ first, uint32_t n_buckets, uint32_t* __restrict__ cnt)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t s = 0;
+    for (uint64_t v = first[b]; v < first[b + 1]; ++v) s += vcnt[v];
+    cnt[b] = s;
 }
 
 // k-mer occurrences held by n records

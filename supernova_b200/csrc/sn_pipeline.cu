@@ -463,11 +463,25 @@ int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uin
     if (!occ_bound) { CU(cudaMemsetAsync(surv_off.p, 0, 4ull * (n_buckets + 1), c->st)); CU(surv.alloc(64)); return SN_OK; }
     const uint64_t cap = occ_bound / c->params.min_freq + 16;
     if (cap >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 candidate k-mers in one context");
-    DevBuf &scratch = c->pool["surv_scratch"], &seg_base = c->pool["bc_seg_base"], &seg_cnt = c->pool["bc_seg_cnt"], &off64 = c->pool["bc_off64"];
-    CU(surv.alloc(16 * cap)); CU(scratch.alloc(16 * cap)); CU(seg_base.alloc(8ull * n_buckets)); CU(seg_cnt.alloc(4ull * n_buckets)); CU(off64.alloc(8ull * (n_buckets + 1)));
+    DevBuf &scratch = c->pool["surv_scratch"], &seg_base = c->pool["bc_seg_base"], &seg_cnt = c->pool["bc_seg_cnt"], &off64 = c->pool["bc_off64"],
+           &vnv = c->pool["bc_vnv"], &vfirst = c->pool["bc_vfirst"], &vbucket = c->pool["bc_vbucket"], &bcnt = c->pool["bc_cnt"], &boff64 = c->pool["bc_boff64"];
+    CU(surv.alloc(16 * cap)); CU(scratch.alloc(16 * cap));
     t_begin(c, "bucket_count");
+    // the CTA table: one CTA per bucket, 2^d CTAs for a heavy one (k_bucket_count2)
+    uint32_t heavy = SN_BC_HEAVY_RECORDS;
+    if (const char* e = getenv("SN_BC_HEAVY")) { const int v = atoi(e); if (v >= 1) heavy = (uint32_t)v; }      // tests
+    CU(vnv.alloc(4ull * n_buckets + 16)); CU(vfirst.alloc(8ull * (n_buckets + 1)));
+    k_vb_count<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(off, n_buckets, n_seg, heavy, vnv.as<uint32_t>());
+    KCHECK("k_vb_count");
+    uint64_t n_virtual = 0;
+    { int rv = scan_u32(c, vnv.as<uint32_t>(), n_buckets, vfirst.as<uint64_t>(), &n_virtual); if (rv) return rv; }
+    if (n_virtual >= (1ull << 31)) return fail(c, SN_ERR_ARG, "too many virtual buckets");
+    CU(vbucket.alloc(8 * n_virtual + 16)); CU(seg_base.alloc(8 * n_virtual + 16)); CU(seg_cnt.alloc(4 * n_virtual + 16)); CU(off64.alloc(8 * (n_virtual + 1)));
+    CU(bcnt.alloc(4ull * n_buckets + 16)); CU(boff64.alloc(8ull * (n_buckets + 1)));
+    k_vb_fill<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(vnv.as<uint32_t>(), vfirst.as<uint64_t>(), n_buckets, vbucket.as<uint2>());
+    KCHECK("k_vb_fill");
     CU(cudaMemsetAsync(occ + 2, 0, 16, c->st)); CU(cudaMemsetAsync(u32c + 3, 0, 4, c->st));
-    CU(cudaMemsetAsync(seg_cnt.p, 0, 4ull * n_buckets, c->st));
+    CU(cudaMemsetAsync(seg_cnt.p, 0, 4 * n_virtual + 16, c->st));
     const int variant = getenv("SN_BC_VARIANT") ? atoi(getenv("SN_BC_VARIANT")) : 0;
 #define SN_BC_LAUNCH(T, S, I, M) do { \
         static bool attr_set = false; \
@@ -477,8 +491,9 @@ int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uin
 #define SN_BC2_LAUNCH(T, S, I, M) do { \
         static bool attr_set = false; \
         if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count2<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem2<T, S>))); attr_set = true; } \
-        k_bucket_count2<T, S, I, M><<<n_buckets, T, sizeof(BcSmem2<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
-            scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3); } while (0)
+        k_bucket_count2<T, S, I, M><<<(unsigned)n_virtual, T, sizeof(BcSmem2<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
+            scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3, vbucket.as<uint2>(), (uint32_t)n_virtual); } while (0)
+    if ((variant == 1 || variant == 4) && n_virtual != n_buckets) return fail(c, SN_ERR_ARG, "SN_BC_VARIANT 1/4 (first count kernel) cannot share out heavy buckets: set SN_BC_HEAVY high");
     switch (variant) {
         case 1: SN_BC_LAUNCH(256, 2048, 4, 3); break;        // the two-phase insert (kept for A/B timing)
         case 4: SN_BC_LAUNCH(128, 1024, 4, 6); break;
@@ -495,7 +510,7 @@ int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uin
     t_end(c, "bucket_count");
     // the buckets' survivor ranges, in bucket order
     uint64_t n_surv = 0;
-    int r = scan_u32(c, seg_cnt.as<uint32_t>(), n_buckets, off64.as<uint64_t>(), &n_surv);
+    int r = scan_u32(c, seg_cnt.as<uint32_t>(), n_virtual, off64.as<uint64_t>(), &n_surv);
     if (r) return r;
     unsigned long long h_dist = 0; uint32_t h_err = 0;
     CU(cudaMemcpyAsync(&h_dist, occ + 2, 8, cudaMemcpyDeviceToHost, c->st));
@@ -505,11 +520,20 @@ int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uin
     if (h_err & 2u) return fail(c, SN_ERR_DATA, "k_bucket_count: a bucket does not fit the shared-memory table after 20 splits (pathological hash collisions)");
     if (h_err & 4u) return fail(c, SN_ERR_DATA, "k_bucket_count: a claimed slot was never published (internal error)");
     t_begin(c, "make_dict");
-    k_gather_survivors<<<std::min(blocks_for((uint64_t)n_buckets * 32, 256), 16u * (unsigned)c->num_sms), 256, 0, c->st>>>(scratch.as<uint4>(), seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(),
-        off64.as<uint64_t>(), n_buckets, surv.as<uint4>());
+    // (virtual buckets are in bucket order, a heavy bucket's in hash-prefix order: the gathered array is in (bucket, hash, k-mer) order)
+    k_gather_survivors<<<std::min(blocks_for(n_virtual * 32, 256), 16u * (unsigned)c->num_sms), 256, 0, c->st>>>(scratch.as<uint4>(), seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(),
+        off64.as<uint64_t>(), (uint32_t)n_virtual, surv.as<uint4>());
     KCHECK("k_gather_survivors");
-    k_narrow_u64<<<blocks_for((uint64_t)n_buckets + 1, 256), 256, 0, c->st>>>(off64.as<uint64_t>(), (uint64_t)n_buckets + 1, surv_off.as<uint32_t>());
-    KCHECK("k_narrow_u64");
+    if (n_virtual == n_buckets) {
+        k_narrow_u64<<<blocks_for((uint64_t)n_buckets + 1, 256), 256, 0, c->st>>>(off64.as<uint64_t>(), (uint64_t)n_buckets + 1, surv_off.as<uint32_t>());
+        KCHECK("k_narrow_u64");
+    } else {       // survivors per real bucket, then their offsets
+        k_vb_sum<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(seg_cnt.as<uint32_t>(), vfirst.as<uint64_t>(), n_buckets, bcnt.as<uint32_t>());
+        KCHECK("k_vb_sum");
+        if ((r = scan_u32(c, bcnt.as<uint32_t>(), n_buckets, boff64.as<uint64_t>(), nullptr))) return r;
+        k_narrow_u64<<<blocks_for((uint64_t)n_buckets + 1, 256), 256, 0, c->st>>>(boff64.as<uint64_t>(), (uint64_t)n_buckets + 1, surv_off.as<uint32_t>());
+        KCHECK("k_narrow_u64");
+    }
     c->cnt.n_kmers_distinct = h_dist;
     *n_surv_out = n_surv;
     return SN_OK;

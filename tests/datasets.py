@@ -22,6 +22,29 @@ def get(name):
         return synth.make_stress(5, n_pairs=3000, n_bc=1)
     if name == "fewbc":              # three barcodes: many k-mers are seen under one barcode only
         return synth.make_stress(6, n_pairs=3000, n_bc=3)
+    if name == "repeats":
+        # a repeat family: 4,000 copies of a 300-bp element, every copy diverged by 8 % substitutions, back to back with
+        # 60-bp unique spacers; plus poly-A and a (CA)n microsatellite.  The element's minimizers name a handful of buckets
+        # that receive ~10^5 distinct k-mers each (heavy buckets: k_bucket_count2 shares them out over many CTAs).
+        rng = np.random.Generator(np.random.Philox(key=77))
+        elem = rng.integers(0, 4, size=300, dtype=np.uint8)
+        parts = []
+        for _ in range(4000):
+            e = elem.copy()
+            m = rng.random(300) < 0.08
+            e[m] = (e[m] + rng.integers(1, 4, size=int(m.sum()))) & 3
+            parts += [e, rng.integers(0, 4, size=60, dtype=np.uint8)]
+        parts += [np.zeros(400, np.uint8), rng.integers(0, 4, size=200, dtype=np.uint8), np.tile(np.array([1, 0], np.uint8), 300), rng.integers(0, 4, size=500, dtype=np.uint8)]
+        hap = np.concatenate(parts)
+        G = len(hap)
+        synth._HAP = np.stack([hap, hap])
+        n_pairs = 20 * G // 300
+        blk, q = synth._gen_chunk((G, 5, 150, 0, n_pairs, 0))
+        synth._HAP = None
+        bcid = np.sort(rng.integers(0, 2000, size=n_pairs))
+        new = np.ones(n_pairs, bool); new[1:] = bcid[1:] != bcid[:-1]
+        bc = np.repeat(np.cumsum(new).astype(np.int32), 2)
+        return blk.ravel(), q.ravel(), np.arange(2 * n_pairs + 1, dtype=np.uint64) * 150, bc, None
     if name == "polyA":
         # one k-mer (A^48) with more than 2^24 occurrences: 84,000 pairs of 150 x A give 17.3 M of them --
         # the count saturates at 16,777,215 (kmers/ReadPather.h:128-129,145) -- on top of a stress set, with

@@ -137,3 +137,32 @@ def test_write_edges_bv_round_trip(sb, name, tmp_path):
     assert got == datasets.unpack_edges(eln, eoff, packed)
     o = Oracle(codes, quals, off, bc).run(with_paths=False)
     assert sorted(got) == sorted(o.edges())
+
+
+def test_repeat_family_heavy_buckets(sb, tmp_path):
+    """Low-complexity / repeat-family input: a few minimizer buckets receive 10^5 distinct k-mers.  k_bucket_count2 shares
+    such a bucket out over 2^d CTAs by hash prefix (sn_msp.cuh); the table must equal the oracle's, and sharing out with
+    other thresholds (SN_BC_HEAVY) must give the same bytes.  Prints the count time (-s shows it)."""
+    from oracle.oracle import Oracle
+    codes, quals, off, bc, _ = datasets.get("repeats")
+    o = Oracle(codes, quals, off, bc).run(with_paths=False)
+    ok = o.kmers()
+    packed = sb.pack_reads(codes, quals, off)
+    ref = None
+    for heavy in (None, "64", "1000000"):
+        if heavy:
+            os.environ["SN_BC_HEAVY"] = heavy
+        try:
+            with sb.Context(0) as ctx:
+                ctx.load_reads(*packed, bc)
+                ctx.build_read_qgraph48(None, sb.Params(), with_paths=False)
+                ctx.build_read_qgraph48(None, sb.Params(), with_paths=False)
+                km = ctx.kmers(); ms = ctx.stage_ms()["bucket_count"]; h = ctx.hbv()
+        finally:
+            os.environ.pop("SN_BC_HEAVY", None)
+        print("repeats: SN_BC_HEAVY=%s bucket_count %.2f ms, %d k-mers, %d occurrences" % (heavy, ms, km.shape[0], o.n_occ))
+        assert np.array_equal(km[:, :3], ok[:, :3]) and np.array_equal(km[:, 3], ok[:, 3] | (ok[:, 4] << 24))
+        if ref is None:
+            ref = h
+        else:
+            assert all(np.array_equal(ref[x], h[x]) for x in ref)
