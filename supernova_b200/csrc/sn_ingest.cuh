@@ -21,6 +21,7 @@ namespace sn {
 #define SN_ING_E_QLEN 2u             // qual line and base line differ in length
 #define SN_ING_E_BASE 4u             // a base character outside ACGTNacgtn (the reference draws ambiguity codes at random)
 #define SN_ING_E_LONG 8u             // read longer than SN_ING_MAXLEN
+#define SN_ING_E_QUAL 16u            // a quality character below '!' or above Q63 (PQVecEncoder::init refuses it, feudal/PQVec.cc:30-35)
 
 // ---- lines -----------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) k_nl_count(const uint8_t* __restrict__ text, uint64_t n, uint32_t* __restrict__ cnt, uint64_t n_seg)
@@ -157,7 +158,7 @@ __device__ __forceinline__ uint32_t pq_block_size(uint32_t nqs, uint32_t nbits) 
 // (`costs`), the block stack it maintains, then the bit packing.  The encoding goes to the read's slot
 // of a scratch array; its size to pqsize.
 static __global__ void __launch_bounds__(128) k_fasth_pqvec(const uint8_t* __restrict__ text, const uint64_t* __restrict__ qpos, const uint32_t* __restrict__ len, const uint64_t* __restrict__ slot_off,
-                                                     uint64_t n_reads, uint8_t* __restrict__ scratch, uint32_t* __restrict__ pqsize)
+                                                     uint64_t n_reads, uint8_t* __restrict__ scratch, uint32_t* __restrict__ pqsize, uint32_t* err)
 {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -166,7 +167,15 @@ static __global__ void __launch_bounds__(128) k_fasth_pqvec(const uint8_t* __res
     uint16_t costs[SN_ING_MAXLEN + 1];
     uint8_t b_nqs[SN_ING_MAXLEN], b_bits[SN_ING_MAXLEN], b_minq[SN_ING_MAXLEN];
     const uint8_t* s = text + qpos[r];
-    for (uint32_t i = 0; i < n; ++i) q[i] = (uint8_t)(s[i] - 33u);           // convertPhred (:37-44)
+    // n/N -> A on EVERY line of a record, the quality lines included (ParseBarcodedFastqs.cc:84-85), then convertPhred (:37-44):
+    // a quality character 'N' (Q45) is read as 'A' (Q32) by the reference
+    bool badq = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ch = ing_fold(s[i]);
+        badq = badq || ch < 33u || ch > 33u + 63u;
+        q[i] = (uint8_t)min(63u, ch - 33u);
+    }
+    if (badq) atomicOr(err, SN_ING_E_QUAL);
     uint32_t nblk = 0;
     costs[0] = 1;
     for (uint32_t i = 0; i < n; ++i) {                                       // PQVecEncoder::init :17-85

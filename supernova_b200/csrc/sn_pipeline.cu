@@ -267,7 +267,7 @@ static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const 
     CU(cudaMemsetAsync((char*)c->bases.p + n_base_bytes, 0, 64, c->st));
     k_fasth_pack<<<blocks_for(n, 128), 128, 0, c->st>>>(T, bpos.as<uint64_t>(), c->len.as<uint32_t>(), c->boff.as<uint64_t>(), n, c->bases.as<uint8_t>(), err);
     KCHECK("k_fasth_pack");
-    k_fasth_pqvec<<<blocks_for(n, 128), 128, 0, c->st>>>(T, qpos.as<uint64_t>(), c->len.as<uint32_t>(), slot.as<uint64_t>(), n, scratch.as<uint8_t>(), psz.as<uint32_t>());
+    k_fasth_pqvec<<<blocks_for(n, 128), 128, 0, c->st>>>(T, qpos.as<uint64_t>(), c->len.as<uint32_t>(), slot.as<uint64_t>(), n, scratch.as<uint8_t>(), psz.as<uint32_t>(), err);
     KCHECK("k_fasth_pqvec");
     if ((r = scan_u32(c, psz.as<uint32_t>(), n, c->pqoff.as<uint64_t>(), &n_pq))) return r;
     CU(c->pq.alloc(n_pq + 16));
@@ -281,6 +281,7 @@ static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const 
     if (h_err & SN_ING_E_NAME) return fail(c, SN_ERR_DATA, "fasth: out of sync reading line (a record does not start with '@')");
     if (h_err & SN_ING_E_QLEN) return fail(c, SN_ERR_DATA, "fasth: a quality line and its base line differ in length");
     if (h_err & SN_ING_E_LONG) return fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported");
+    if (h_err & SN_ING_E_QUAL) return fail(c, SN_ERR_DATA, "fasth: a quality character outside '!'..'`' (Q0..Q63): PQVec cannot hold it (the reference's PQVecEncoder gives up on it too)");
     if (h_err & SN_ING_E_BASE) return fail(c, SN_ERR_DATA, "fasth: a base other than ACGTN (the reference draws other ambiguity codes at random: not reproducible)");
     c->have_bc = true; c->have_pq = true; c->quals.release();
     return finish_load(c);
@@ -643,6 +644,17 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     if (h_bad) return bail(fail(c, SN_ERR_DATA, std::to_string(h_bad) + " reads whose PQVec length differs from their base count"));
     const int bits = sn_i_pick_bucket_bits(h_occ);
     if (h_occ >= 3600000000ull) with_hist = 0;                     // counted in several passes: each pass has its own histogram
+    {   // the MSP scan stages 128 reads of at most SN_MAX_READ_LEN bases in shared memory: check the lengths (all on the device by now:
+        // they travelled with the quals) before it runs, not after
+        unsigned long long* c64 = occ + 16;
+        k_read_stats<<<std::min(blocks_for(n, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(n, c->len.as<uint32_t>(), nullptr, c64, reinterpret_cast<uint32_t*>(c64 + 1), reinterpret_cast<int32_t*>(c64 + 1) + 1);
+        ++c->launches;
+        unsigned long long hh[2] = {0, 0};
+        CUB_(cudaMemcpyAsync(hh, c64, 16, cudaMemcpyDeviceToHost, c->st));
+        CUB_(cudaStreamSynchronize(c->st));
+        if ((uint32_t)(hh[1] & 0xFFFFFFFFu) > SN_MAX_READ_LEN) return bail(fail(c, SN_ERR_ARG, "reads longer than " + std::to_string(SN_MAX_READ_LEN) + " bases are not supported"));
+        CUB_(cudaMemsetAsync(c64, 0, 16, c->st));
+    }
     const uint64_t nb = 1ull << bits;
     DevBuf &hist = c->pool["sk_hist"], &dsc = c->pool["sk_dsc"], &nruns = c->pool["sk_nruns"];
     uint32_t* ovf = u32c + 9;
@@ -768,6 +780,7 @@ int sn_mg_partition(sn_ctx* c, int bits, uint32_t nparts, uint64_t* part_records
 {
     if (!c || !part_records || !dev_records || !dev_counts || nparts == 0 || bits < 1 || bits > 24 || nparts > (1u << bits)) return SN_ERR_ARG;
     if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition: no reads loaded");
+    if (!c->goodlen.p || c->goodlen.bytes < 4 * c->cnt.n_reads) return fail(c, SN_ERR_STATE, "sn_mg_partition: run sn_mg_good_lengths first");
     CU(cudaSetDevice(c->device));
     uint64_t n_sk = 0;
     int r = sn_i_msp_partition(c, bits, &n_sk);

@@ -60,7 +60,10 @@ def odd_text():
             return s.lower() if lower else s
 
         def qual(n):
-            return "".join(chr(33 + int(x)) for x in rng.choice([2, 12, 20, 30, 37, 41], size=n))
+            q = "".join(chr(33 + int(x)) for x in rng.choice([2, 12, 20, 30, 37, 41], size=n))
+            if with_n and n > 20:       # 'N' (Q45) and 'n' (Q77) in a QUALITY line: the reference folds them to 'A' = Q32 like everywhere else (:84-85)
+                q = q[:5] + "N" + q[6:12] + "n" + q[13:]
+            return q
         return "@r%d some name\n%s\n%s\n%s\n%s\n%s\n%s\nACGTACGT\nIIIIIIII\n" % (i, seq(n1), qual(n1), seq(n2), qual(n2), barcode, "I" * 16)
     recs = [
         rec(0, 150, 150, "NNNNNNNNNNNNNNNN"),                 # no gem group: unbarcoded
@@ -119,7 +122,7 @@ def test_ingest_errors_are_loud(sb):
     with sb.Context(0) as ctx:
         i = good.index(b"\n") + 5
         for bad, what in ((good[:-1], "newline"), (good + b"@x\nACGT\n", "9 per record"), (good.replace(b"@r3", b"#r3"), "'@'"),
-                          (good[:i] + b"R" + good[i + 1:], "ACGTN")):
+                          (good[:i] + b"R" + good[i + 1:], "ACGTN"), (good.replace(b"#", b"~", 1), "quality character")):
             with pytest.raises(sb.SnError) as e:
                 ctx.load_fasth_text(bad)
             assert what in str(e.value), (what, str(e.value))
