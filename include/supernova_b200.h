@@ -99,6 +99,8 @@ int sn_load_fasth_files(sn_ctx* ctx, const char* const* paths, uint32_t n_files)
 int sn_save_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 /* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */
 int sn_load_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
+/* reads [first_read, first_read + n_reads) of the files (n_reads = 0: to the end): one rank's shard; bci may be NULL */
+int sn_load_read_files_range(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci, uint64_t first_read, uint64_t n_reads);
 /* the same with the per-read barcode ordinals already in memory (the vec<int32_t> buildReadQGraph48's caller
  * passes as bcp, 10X/runstages/RunStages.cc:405); bc may be NULL (n_bc ignored)            */
 int sn_load_read_files_bc(sn_ctx* ctx, const char* fastb, const char* qualp, const int32_t* bc, uint64_t n_bc);
@@ -230,6 +232,8 @@ uint32_t sn_pqvec_decode(const uint8_t* pq, uint64_t pq_bytes, uint8_t* out, uin
 int sn_pack_reads(uint64_t n_reads, const uint8_t* codes, const uint8_t* quals, const uint64_t* off, int threads,
                   uint8_t** bases, uint64_t** base_off, uint32_t** len, uint8_t** pq, uint64_t** pq_off);
 void sn_free(void* p);
+/* tmp.paths (feudal ReadPathVec) from arrays: the ranks' ReadPaths of a multi-GPU job, concatenated in read order by the caller */
+int sn_write_paths_arrays(const char* path, uint64_t n_reads, const int32_t* offset, const uint64_t* path_off, const int32_t* edges);
 /* write the reference's input files from the in-memory layout above */
 int sn_write_read_files(const char* fastb, const char* qualp, const char* bci, uint64_t n_reads,
                         const uint8_t* bases, const uint64_t* base_off, const uint32_t* len,

@@ -56,6 +56,8 @@ def lib():
         L.sn_load_reads_streamed.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.sn_load_read_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
         L.sn_load_read_files_bc.argtypes = [vp, C.c_char_p, C.c_char_p, vp, u64]
+        L.sn_load_read_files_range.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, u64, u64]
+        L.sn_write_paths_arrays.argtypes = [C.c_char_p, u64, vp, vp, vp]
         L.sn_build_graph_from_edges.argtypes = [vp, C.c_char_p]
         L.sn_count_kmers.argtypes = [vp, C.POINTER(Params)]
         for f in ("sn_build_edges", "sn_build_hbv", "sn_path_reads"):

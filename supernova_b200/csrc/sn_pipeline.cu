@@ -326,6 +326,27 @@ int sn_load_read_files(sn_ctx* c, const char* fastb, const char* qualp, const ch
     }
     return sn_load_reads(c, fb.len.size(), fb.var.data(), fb.off.data(), fb.len.data(), qp.var.data(), qp.off.data(), bci ? bc.data() : nullptr);
 }
+// a slice of the read files: reads [first_read, first_read + n_reads) (n_reads = 0: to the end) -- the shard of one rank
+int sn_load_read_files_range(sn_ctx* c, const char* fastb, const char* qualp, const char* bci, uint64_t first_read, uint64_t n_reads)
+{
+    if (!c || !fastb || !qualp) return SN_ERR_ARG;
+    snf::Fastb fb; snf::Qualp qp; std::vector<int64_t> bi; std::vector<int32_t> bc; std::string err;
+    if (!snf::read_fastb(fastb, fb, err) || !snf::read_qualp(qualp, qp, err)) return fail(c, SN_ERR_IO, err);
+    if (fb.len.size() + 1 != qp.off.size()) return fail(c, SN_ERR_DATA, "fastb and qualp hold different numbers of reads");
+    if (bci) {
+        if (!snf::read_bci(bci, bi, err)) return fail(c, SN_ERR_IO, err);
+        if (!snf::expand_bci(bi, bc)) return fail(c, SN_ERR_DATA, std::string(bci) + ": barcode index is not sorted");
+        if (bc.size() != fb.len.size()) return fail(c, SN_ERR_DATA, "bci.back() != number of reads");
+    }
+    const uint64_t N = fb.len.size();
+    if (first_read > N) return fail(c, SN_ERR_ARG, "sn_load_read_files_range: first_read beyond the file");
+    if (!n_reads || first_read + n_reads > N) n_reads = N - first_read;
+    if (!n_reads) return fail(c, SN_ERR_ARG, "sn_load_read_files_range: empty range");
+    std::vector<uint64_t> bo(n_reads + 1), qo(n_reads + 1);
+    for (uint64_t i = 0; i <= n_reads; ++i) { bo[i] = fb.off[first_read + i] - fb.off[first_read]; qo[i] = qp.off[first_read + i] - qp.off[first_read]; }
+    return sn_load_reads(c, n_reads, fb.var.data() + fb.off[first_read], bo.data(), fb.len.data() + first_read, qp.var.data() + qp.off[first_read], qo.data(),
+                         bci ? bc.data() + first_read : nullptr);
+}
 // the same with the per-read barcode ordinals the caller already holds in memory (the vec<int32_t> bc of
 // buildReadQGraph48's caller, 10X/DF.cc:464-469); bc may be NULL
 int sn_load_read_files_bc(sn_ctx* c, const char* fastb, const char* qualp, const int32_t* bc, uint64_t n_bc)
@@ -1557,6 +1578,14 @@ int sn_write_paths(sn_ctx* c, const char* path)
     int r = fetch_paths(c); if (r) return r;
     std::string err;
     if (!snf::write_paths(path, c->cnt.n_reads, c->h_poffset.data(), c->h_path_off.data(), c->h_pedges.data(), err)) return fail(c, SN_ERR_IO, err);
+    return SN_OK;
+}
+// tmp.paths from arrays (host helper: the ranks' paths of a multi-GPU job, concatenated by the caller)
+int sn_write_paths_arrays(const char* path, uint64_t n_reads, const int32_t* offset, const uint64_t* path_off, const int32_t* edges)
+{
+    if (!path || !offset || !path_off) return SN_ERR_ARG;
+    std::string err;
+    if (!snf::write_paths(path, n_reads, offset, path_off, edges, err)) { g_sn_create_error = err; return SN_ERR_IO; }
     return SN_OK;
 }
 int sn_write_edges_bv(sn_ctx* c, const char* path)

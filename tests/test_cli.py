@@ -46,3 +46,27 @@ def test_cli_reproduces_the_reference_files(built, name, tmp_path):
     assert r.returncode == 0, r.stderr
     assert open(out2 + "/a.hbv", "rb").read() == open(wd + "/a.hbv", "rb").read()
     assert not os.path.exists(out2 + "/tmp.paths")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "stress1"])
+def test_cli_multi_gpu_without_python(built, name, tmp_path):
+    """NGPU=2: the sharded path driven by the C++ host alone -- a thread and a context per GPU, NCCL inside the library,
+    no launcher, no torch.  The files equal the golden ones of the reference."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    codes, quals, off, bc, ids = datasets.get(name)
+    wd = str(tmp_path)
+    fq = wd + "/in.fastq.gz"
+    synth.write_fasth_ragged(fq, codes, quals, off, ids)
+    r = subprocess.run([EXE, "FASTH=" + fq, "HEAD=" + wd + "/reads", "OUT=" + wd, "NGPU=2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("2 GPUs:")
+    g = os.path.join(GOLD, name)
+    for f in ("a.hbv", "tmp.paths"):
+        assert open(wd + "/" + f, "rb").read() == gzip.open(g + "/" + f + ".gz", "rb").read(), f
+    assert open(wd + "/stats/histogram_kmer_count.json").read() == open(g + "/histogram_kmer_count.json").read()
+    r = subprocess.run([EXE, "HEAD=" + wd + "/reads", "OUT=" + wd, "NGPU=2", "PATHS=False"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(wd + "/a.hbv", "rb").read() == gzip.open(g + "/a.hbv.gz", "rb").read()
