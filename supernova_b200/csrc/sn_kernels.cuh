@@ -428,12 +428,20 @@ __device__ __forceinline__ void thread_path(const PathInputs& in, uint64_t r, co
 static __global__ void __launch_bounds__(128) k_path_reads(PathInputs in, DictView d, EdgeStore es, HbvView h,
                                                     uint32_t* __restrict__ plen, int32_t* __restrict__ poffset, int32_t* __restrict__ scratch, uint32_t* overflow)
 {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= in.n_reads) return;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < in.n_reads;                            // (no early return: the warp threads its 32 reads together, path_parts_warp)
     Part parts[SN_MAX_PARTS];
     RPath path;
     uint8_t qbuf[SN_MAX_READ_LEN];
-    thread_path(in, r, d, es, h, parts, path, qbuf);
+    const uint8_t* rd = live ? in.bases + in.boff[r] : in.bases;
+    const uint32_t n = live ? in.len[r] : 0u;
+    const uint32_t np = path_parts_warp(d, es, rd, n, parts, live);
+    if (!live) return;
+    LazyQuals qs;
+    qs.q8 = in.pq ? nullptr : in.quals + in.qoff[r];
+    qs.pq = in.pq ? in.pq + in.pq_off[r] : nullptr; qs.pq_end = in.pq ? in.pq + in.pq_off[r + 1] : nullptr;
+    qs.buf = qbuf; qs.ready = false;
+    path_from_parts(es, h, rd, qs, n, parts, np, path);
     if (path.overflow) atomicAdd(overflow, 1u);
     plen[r] = path.n; poffset[r] = path.offset;
     int4 v = make_int4(path.n > 0 ? path.e[0] : 0, path.n > 1 ? path.e[1] : 0, path.n > 2 ? path.e[2] : 0, path.n > 3 ? path.e[3] : 0);

@@ -71,6 +71,48 @@ SN_HD uint32_t pqvec_decode(const uint8_t* p, const uint8_t* pend, uint8_t* out,
     return i;
 }
 
+// the seed at read position itr hit dictionary entry `ent`: extend the exact match along its edge (matchLen), -> the part
+SN_HD Part seed_part(const DictView& d, const EdgeStore& es, const uint8_t* rd, uint32_t n, uint32_t itr, const Kmer& kmer, uint32_t ent)
+{
+    const DictEntry& e = d.tab[ent];
+    uint32_t u = e.edge, esz = es.len[u];
+    int32_t offset = (int32_t)e.off;
+    // CF<K>::isRC (dna/CanonicalForm.h:84-91): is the read k-mer the RC of the edge
+    // k-mer at `offset`?  The edge k-mer is the stored canonical k-mer or its RC.
+    // Palindromes compare equal to themselves => not RC.
+    const uint8_t* eb = es.bases + es.off[u];
+    Kmer ek = kmer_from_packed_w(eb, (uint32_t)offset);
+    bool rc = !(ek == kmer);
+    uint32_t len = 1;
+    // matchLen: 16 bases per step (both sequences packed 2 bits per base)
+    if (!rc) {
+        uint32_t a = itr + SN_K, b = (uint32_t)offset + SN_K;
+        while (a < n && b < esz) {
+            uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
+            const uint32_t eq = window_match(packed_window16(rd, a), packed_window16(eb, b), m);
+            const uint32_t adv = eq < m ? eq : m;
+            len += adv; a += adv; b += adv;
+            if (eq < m) break;
+        }
+    } else {
+        offset = (int32_t)esz - offset;
+        uint32_t a = itr + SN_K, b = (uint32_t)offset;
+        // the edge read backwards and complemented: base b of the RC is 3 - edge[esz - 1 - b]
+        while (a < n && b < esz) {
+            uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
+            const uint32_t w = packed_window16(eb, esz - b - m);                 // edge[esz-b-m .. esz-b-1] in the low 2m bits
+            const uint32_t r = ~(rev2(w) >> (2 * (16 - m)));                     // reversed and complemented: RC bases b .. b+m-1
+            const uint32_t eq = window_match(packed_window16(rd, a), r, m);
+            const uint32_t adv = eq < m ? eq : m;
+            len += adv; a += adv; b += adv;
+            if (eq < m) break;
+        }
+        offset -= SN_K;
+    }
+    Part p; p.edge = u; p.off = (uint32_t)offset; p.len = len; p.elen_rc = ((esz - SN_K + 1) << 1) | (rc ? 1u : 0u);
+    return p;
+}
+
 // a10 Pather::path (:705-747).  Returns the number of parts.
 SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t* rd, uint32_t n, Part* parts)
 {
@@ -95,48 +137,58 @@ SN_HD uint32_t path_parts(const DictView& d, const EdgeStore& es, const uint8_t*
             parts[np++] = mk_gap(gap);
         }
         if (ent != SN_NULL_EDGE) {
-            const DictEntry& e = d.tab[ent];
-            uint32_t u = e.edge, esz = es.len[u];
-            int32_t offset = (int32_t)e.off;
-            // CF<K>::isRC (dna/CanonicalForm.h:84-91): is the read k-mer the RC of the edge
-            // k-mer at `offset`?  The edge k-mer is the stored canonical k-mer or its RC.
-            // Palindromes compare equal to themselves => not RC.
-            const uint8_t* eb = es.bases + es.off[u];
-            Kmer ek = kmer_from_packed_w(eb, (uint32_t)offset);
-            bool rc = !(ek == kmer);
-            uint32_t len = 1;
-            // matchLen: 16 bases per step (both sequences packed 2 bits per base)
-            if (!rc) {
-                uint32_t a = itr + SN_K, b = (uint32_t)offset + SN_K;
-                while (a < n && b < esz) {
-                    uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
-                    const uint32_t eq = window_match(packed_window16(rd, a), packed_window16(eb, b), m);
-                    const uint32_t adv = eq < m ? eq : m;
-                    len += adv; a += adv; b += adv;
-                    if (eq < m) break;
-                }
-            } else {
-                offset = (int32_t)esz - offset;
-                uint32_t a = itr + SN_K, b = (uint32_t)offset;
-                // the edge read backwards and complemented: base b of the RC is 3 - edge[esz - 1 - b]
-                while (a < n && b < esz) {
-                    uint32_t m = n - a < esz - b ? n - a : esz - b; if (m > 16) m = 16;
-                    const uint32_t w = packed_window16(eb, esz - b - m);                 // edge[esz-b-m .. esz-b-1] in the low 2m bits
-                    const uint32_t r = ~(rev2(w) >> (2 * (16 - m)));                     // reversed and complemented: RC bases b .. b+m-1
-                    const uint32_t eq = window_match(packed_window16(rd, a), r, m);
-                    const uint32_t adv = eq < m ? eq : m;
-                    len += adv; a += adv; b += adv;
-                    if (eq < m) break;
-                }
-                offset -= SN_K;
-            }
-            Part p; p.edge = u; p.off = (uint32_t)offset; p.len = len; p.elen_rc = ((esz - SN_K + 1) << 1) | (rc ? 1u : 0u);
+            const Part p = seed_part(d, es, rd, n, itr, kmer, ent);
             parts[np++] = p;
-            itr += len;
+            itr += p.len;
         }
     }
     return np;
 }
+
+#if defined(__CUDACC__)
+// Pather::path for the 32 reads of a warp together.  A read whose seed k-mer is not in the dictionary (a sequencing error
+// under it) has to try the following positions one by one -- up to K look-ups per error, while the lanes of reads without
+// errors wait.  Here a lane that misses asks the WARP: its next 32 positions are looked up side by side, the first hit
+// (ballot) ends the gap.  Same parts as path_parts (the first position that hits is the same); 32 lanes busy instead of one.
+// Every lane of the warp must call this (live = false for a lane without a read).
+__device__ __forceinline__ uint32_t path_parts_warp(const DictView& d, const EdgeStore& es, const uint8_t* rd, uint32_t n, Part* parts, bool live)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t np = 0, itr = 0, end = 0;
+    bool done = !live;
+    if (live) { if (n < SN_K) { parts[np++] = mk_gap(n); done = true; } else end = n - SN_K + 1; }
+    while (!__all_sync(0xFFFFFFFFu, done)) {
+        uint32_t ent = SN_NULL_EDGE; Kmer kmer; kmer.w0 = kmer.w1 = kmer.w2 = 0;
+        if (!done) { kmer = kmer_from_packed_w(rd, itr); bool rc; ent = dict_find(d, kmer, &rc); }
+        const bool need = !done && ent == SN_NULL_EDGE;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+        uint32_t my_pos = 0xFFFFFFFFu, my_ent = SN_NULL_EDGE;
+        while (m) {                                              // serve the lanes that missed, one after the other
+            const int src = __ffs((int)m) - 1; m &= m - 1u;
+            const uint8_t* rrd = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uintptr_t>(rd), src));
+            const uint32_t ritr = __shfl_sync(0xFFFFFFFFu, itr, src), rend = __shfl_sync(0xFFFFFFFFu, end, src);
+            uint32_t hit_pos = 0xFFFFFFFFu, hit_ent = SN_NULL_EDGE;
+            for (uint32_t base = ritr + 1; base < rend; base += 32) {
+                const uint32_t q = base + lane;
+                uint32_t e = SN_NULL_EDGE;
+                if (q < rend) { const Kmer k = kmer_from_packed_w(rrd, q); bool rc; e = dict_find(d, k, &rc); }
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, e != SN_NULL_EDGE);
+                if (hm) { const int hl = __ffs((int)hm) - 1; hit_pos = base + (uint32_t)hl; hit_ent = __shfl_sync(0xFFFFFFFFu, e, hl); break; }
+            }
+            if ((int)lane == src) { my_pos = hit_pos; my_ent = hit_ent; }
+        }
+        if (!done) {
+            if (need) {
+                if (my_pos == 0xFFFFFFFFu) { parts[np++] = mk_gap(end - itr); itr = end; }       // nothing hits up to the end of the read
+                else { parts[np++] = mk_gap(my_pos - itr); itr = my_pos; ent = my_ent; kmer = kmer_from_packed_w(rd, itr); }
+            }
+            if (ent != SN_NULL_EDGE) { const Part p = seed_part(d, es, rd, n, itr, kmer, ent); parts[np++] = p; itr += p.len; }
+            if (itr == end) done = true;
+        }
+    }
+    return np;
+}
+#endif
 
 // PathPart::isConformingCapturedGap (:669-676)
 SN_HD bool conforming_gap(const Part* p, uint32_t max_jitter)
@@ -290,12 +342,11 @@ struct PlainQuals { const uint8_t* q; SN_HD const uint8_t* get() { return q; } }
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
+// everything of algorithmTwo after Pather::path: `parts[0..np)` -> the ReadPath
 template <class QS>
-SN_HD void path_one_read_q(const DictView& d, const EdgeStore& es, const HbvView& h,
-                           const uint8_t* rd, QS& qs, uint32_t n, Part* parts, RPath& path)
+SN_HD void path_from_parts(const EdgeStore& es, const HbvView& h, const uint8_t* rd, QS& qs, uint32_t n, Part* parts, uint32_t np, RPath& path)
 {
     path.n = 0; path.offset = 0; path.overflow = false;
-    uint32_t np = path_parts(d, es, rd, n, parts);
     // seeds on short hanging edges become gaps; adjacent gaps merge (:1236-1258); in place
     uint32_t nn = 0;
     for (uint32_t i = 0; i < np; ++i) {
@@ -349,6 +400,16 @@ SN_HD void path_one_read_q(const DictView& d, const EdgeStore& es, const HbvView
     // ExtendReadPath::attemptLeftRightExtension (ExtendReadPath.cc:121-129)
     while (extend_once(es, h, path, rd, qs, n, true)) {}
     while (extend_once(es, h, path, rd, qs, n, false)) {}
+}
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class QS>
+SN_HD void path_one_read_q(const DictView& d, const EdgeStore& es, const HbvView& h,
+                           const uint8_t* rd, QS& qs, uint32_t n, Part* parts, RPath& path)
+{
+    const uint32_t np = path_parts(d, es, rd, n, parts);
+    path_from_parts(es, h, rd, qs, n, parts, np, path);
 }
 SN_HD void path_one_read(const DictView& d, const EdgeStore& es, const HbvView& h,
                          const uint8_t* rd, const uint8_t* q, uint32_t n, Part* parts, RPath& path)
