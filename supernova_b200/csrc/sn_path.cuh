@@ -170,8 +170,20 @@ __device__ __forceinline__ uint32_t path_parts_warp(const DictView& d, const Edg
             uint32_t hit_pos = 0xFFFFFFFFu, hit_ent = SN_NULL_EDGE;
             for (uint32_t base = ritr + 1; base < rend; base += 32) {
                 const uint32_t q = base + lane;
+                // the minimizers of the 32 k-mers at base .. base+31 from 64 p-mer values, two per lane: k-mer base+l holds the
+                // p-mers base+l .. base+l+32 = a suffix of the first 32 values and a prefix of the second 32
+                // (W = 33; the read buffer is padded, positions past the read feed only k-mers past its end)
+                const uint32_t wa = packed_window16(rrd, q), wb = packed_window16(rrd, q + 32);
+                uint32_t sa = pmer_value(rev2(wa), ~wa), pb = pmer_value(rev2(wb), ~wb);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t ta = __shfl_down_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, pb, o);
+                    if (lane + (uint32_t)o < 32u) sa = ta < sa ? ta : sa;
+                    if (lane >= (uint32_t)o) pb = tb < pb ? tb : pb;
+                }
+                const uint32_t minimizer = sa < pb ? sa : pb;
                 uint32_t e = SN_NULL_EDGE;
-                if (q < rend) { const Kmer k = kmer_from_packed_w(rrd, q); bool rc; e = dict_find(d, k, &rc); }
+                if (q < rend) { const Kmer k = kmer_from_packed_w(rrd, q); bool rc; e = dict_find_min(d, k, minimizer, &rc); }
                 const unsigned hm = __ballot_sync(0xFFFFFFFFu, e != SN_NULL_EDGE);
                 if (hm) { const int hl = __ffs((int)hm) - 1; hit_pos = base + (uint32_t)hl; hit_ent = __shfl_sync(0xFFFFFFFFu, e, hl); break; }
             }
