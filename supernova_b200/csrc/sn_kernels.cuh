@@ -32,25 +32,38 @@ static __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, 
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t occ = 0;
     if (r < n_reads) {
-        // One quality per iteration, block headers parsed on the fly: the lanes of a warp (reads of
-        // the same length) then run the same iterations, whatever their block structure is.
+        // Block by block.  A block whose base quality is already >= minQual holds only good quals (every qual is
+        // base + a non-negative delta): its packed deltas are skipped unread -- on sequencing data that is nearly every
+        // block (a block boundary sits wherever a low quality starts or ends), so a read costs a few header parses instead
+        // of one decode step per base.  Only blocks that start below minQual are unpacked qual by qual.
         const uint8_t* p = pq + pq_off[r];
         const uint8_t* pend = pq + pq_off[r + 1];
         const uint32_t L = len[r];
-        uint32_t run = 0, gl = 0, rem = 0, nbits = 0, minq = 0, acc = 0, have = 0, mask = 0;
+        uint32_t run = 0, gl = 0, i = 0, rem = 0;
         bool bad = false;
-        for (uint32_t i = 0; i < L; ++i) {
-            if (rem == 0) {                                     // next block: [nQs][nBits:3|minQ low 5][minQ bit 5 | 7 data bits]...
-                if (p + 3 > pend) { bad = true; break; }
-                rem = *p++;
-                if (!rem) { bad = true; break; }                // terminator before L quals
-                const uint32_t b0 = *p++, a = *p++;
-                nbits = b0 & 7u; minq = (b0 >> 3) | ((a & 1u) << 5); acc = a >> 1; have = 7; mask = (1u << nbits) - 1u;
+        while (i < L) {
+            if (p + 3 > pend) { bad = true; break; }            // [nQs][nBits:3|minQ low 5][minQ bit 5 | 7 data bits]...
+            rem = *p++;
+            if (!rem || rem > L - i) { bad = true; break; }      // terminator before L quals / more quals than bases
+            const uint32_t b0 = *p++, a = *p++;
+            const uint32_t nbits = b0 & 7u, minq = (b0 >> 3) | ((a & 1u) << 5);
+            if (minq >= min_qual) {
+                run += rem; i += rem;
+                if (run >= SN_K) gl = i;
+                p += ((1u + rem * nbits + 7u) >> 3) - 1u;        // the block's data bytes beyond the one the header shares
+                rem = 0;
+                if (p > pend) { bad = true; break; }
+                continue;
             }
-            if (have < nbits) { acc |= (uint32_t)(*p++) << have; have += 8; }
-            const uint32_t q = minq + (acc & mask); acc >>= nbits; have -= nbits; --rem;
-            run = q >= min_qual ? run + 1 : 0;
-            if (run >= SN_K) gl = i + 1;
+            uint32_t acc = a >> 1, have = 7;
+            const uint32_t mask = (1u << nbits) - 1u;
+            for (; rem; --rem) {
+                if (have < nbits) { acc |= (uint32_t)(*p++) << have; have += 8; }
+                const uint32_t q = minq + (acc & mask); acc >>= nbits; have -= nbits;
+                run = q >= min_qual ? run + 1 : 0;
+                ++i;
+                if (run >= SN_K) gl = i;
+            }
         }
         if (rem != 0 || (p < pend && *p != 0)) bad = true;      // the PQVec holds more quals than the read has bases
         if (bad) { atomicAdd(bad_reads, 1u); gl = 0; }
