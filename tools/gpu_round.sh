@@ -27,7 +27,7 @@ print('paths',d.get('with_readpaths'))
 PY
 ;;
 ref) timeout 1200 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err; echo "ref rc=$?"; cut -c1-1500 gpurun_out/${TAG}_ref.json; tail -3 gpurun_out/${TAG}_ref.err;;
-ncu) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-ingest --no-cpu-baseline --no-check > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?";;
+ncu) timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-ingest --no-cpu-baseline --no-check --no-paths > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?";;
 ncufull:*) K=${what#ncufull:}; timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$K" -c 2 -o gpurun_out/${TAG}_full_$(echo $K | tr -c 'a-zA-Z0-9_' '_') -f python bench.py --steps 1 --warmup 1 --no-ingest --no-cpu-baseline --no-check > gpurun_out/${TAG}_ncufull.log 2>&1; echo "ncufull rc=$?";;
 esac
 done
