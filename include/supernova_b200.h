@@ -158,36 +158,8 @@ int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_
  * work_dir/tmp.paths (when with_paths) and work_dir/stats/histogram_kmer_count.json.      */
 int sn_build_read_qgraph48(sn_ctx* ctx, const char* work_dir, const sn_params* params, int with_paths, int write_files);
 
-/* ---- multi-GPU (one context per rank; the caller issues the collectives) ------------------------
- * Reads are sharded over the ranks; the super-k-mer stream (MSP, lib/tada/src/msp/mod.rs) is
- * range-partitioned by minimizer bucket: owner(bucket) = (bucket * nparts) >> bits, the role of
- * `shard % total_chunks` in lib/tada/src/cmd_shard_asm.rs:40.
- *   1. sn_mg_good_lengths  : a1 on this rank's reads; *n_occ = its k-mer occurrences.  The caller
- *      sums n_occ over the ranks and derives `bits` (sn_msp_bucket_bits) -- equal on every rank.
- *   2. sn_mg_partition     : super-k-mer records of this rank's reads in bucket order;
- *      part_records[nparts] records per owner, *dev_records the DEVICE buffer holding them back
- *      to back (32 bytes per record), *dev_counts the DEVICE u32 count of every bucket (2^bits).
- *   3. caller: alltoallv of the records into sn_mg_recv_records(total received) and of the
- *      per-bucket counts of each owner's bucket range into sn_mg_recv_counts(nparts * range).
- *   4. sn_mg_count_received: per-bucket count + filter of the received records (n_seg = nparts
- *      source segments, n_buckets = this rank's bucket range) -> its surviving k-mers in (bucket,
- *      hash, k-mer) order (*dev_survivors, 16 bytes each: w0,w1,w2,count:24|ctx<<24, DEVICE) and
- *      how many each bucket kept (*dev_bucket_counts, u32[n_buckets], DEVICE).
- *   5. caller: allgather, in rank order, of the survivors into sn_mg_survivor_buffer(total) and of
- *      the bucket counts into sn_mg_bucket_count_buffer(bits) -- rank order is bucket order.
- *   6. sn_mg_install_survivors: the gathered k-mers become the dictionary (no sort needed);
- *      sn_build_edges / sn_build_hbv / sn_path_reads then run as on one GPU (graph replicated,
- *      reads stay sharded).                                                                    */
+/* number of minimizer-bucket bits for a job with that many k-mer occurrences in total (768..1536 occurrences per bucket) */
 int   sn_msp_bucket_bits(uint64_t n_occ_total);
-int   sn_mg_good_lengths(sn_ctx* ctx, const sn_params* params, uint64_t* n_occ);
-int   sn_mg_partition(sn_ctx* ctx, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts);
-void* sn_mg_recv_records(sn_ctx* ctx, uint64_t n_records);
-void* sn_mg_recv_counts(sn_ctx* ctx, uint64_t n_counts);
-int   sn_mg_count_received(sn_ctx* ctx, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors,
-                           void** dev_survivors, void** dev_bucket_counts);
-void* sn_mg_survivor_buffer(sn_ctx* ctx, uint64_t n_total);
-void* sn_mg_bucket_count_buffer(sn_ctx* ctx, int bits);
-int   sn_mg_install_survivors(sn_ctx* ctx, uint64_t n_total, int bits);
 
 /* ---- multi-GPU with the collectives issued by the library (C++ host, NCCL over NVLink / NVSwitch) ---------------
  * One context per rank (= per GPU).  sn_mg_build_graph is the whole hot path over the ranks of the communicator:

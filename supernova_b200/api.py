@@ -89,15 +89,6 @@ def lib():
         L.sn_device_count.restype = i32
         L.sn_msp_bucket_bits.argtypes = [u64]
         L.sn_msp_bucket_bits.restype = i32
-        L.sn_mg_good_lengths.argtypes = [vp, C.POINTER(Params), C.POINTER(u64)]
-        L.sn_mg_partition.argtypes = [vp, i32, C.c_uint32, vp, C.POINTER(vp), C.POINTER(vp)]
-        for f in ("sn_mg_recv_records", "sn_mg_recv_counts", "sn_mg_survivor_buffer"):
-            getattr(L, f).argtypes = [vp, u64]
-            getattr(L, f).restype = vp
-        L.sn_mg_bucket_count_buffer.argtypes = [vp, i32]
-        L.sn_mg_bucket_count_buffer.restype = vp
-        L.sn_mg_count_received.argtypes = [vp, C.c_uint32, C.c_uint32, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(vp)]
-        L.sn_mg_install_survivors.argtypes = [vp, u64, i32]
         L.sn_nccl_unique_id.argtypes = [vp]
         L.sn_comm_init_nccl.argtypes = [vp, i32, i32, vp]
         L.sn_local_group_create.argtypes = [i32]
@@ -309,46 +300,6 @@ class Context:
         wf = (work_dir is not None) if write_files is None else write_files
         self._ck(self.L.sn_build_read_qgraph48(self.h, None if work_dir is None else work_dir.encode(), C.byref(p),
                                                int(with_paths), int(wf)))
-
-    # ---- multi-GPU pieces (see supernova_b200/multigpu.py) --------------------------------
-    def mg_good_lengths(self, params=None):
-        p = params or Params()
-        n = C.c_uint64()
-        self._ck(self.L.sn_mg_good_lengths(self.h, C.byref(p), C.byref(n)))
-        return int(n.value)
-
-    def mg_partition(self, bits, nparts):
-        counts = (C.c_uint64 * nparts)()
-        rec, cnt = C.c_void_p(), C.c_void_p()
-        self._ck(self.L.sn_mg_partition(self.h, bits, nparts, counts, C.byref(rec), C.byref(cnt)))
-        return [int(x) for x in counts], int(rec.value or 0), int(cnt.value or 0)
-
-    def _mg_buf(self, fn, n):
-        p = getattr(self.L, fn)(self.h, n)
-        if not p:
-            raise SnError(self.L.sn_last_error(self.h).decode())
-        return int(p)
-
-    def mg_recv_records(self, n_records):
-        return self._mg_buf("sn_mg_recv_records", n_records)
-
-    def mg_recv_counts(self, n_counts):
-        return self._mg_buf("sn_mg_recv_counts", n_counts)
-
-    def mg_count_received(self, n_seg, n_buckets, n_records):
-        ns = C.c_uint64()
-        ptr, cnt = C.c_void_p(), C.c_void_p()
-        self._ck(self.L.sn_mg_count_received(self.h, n_seg, n_buckets, n_records, C.byref(ns), C.byref(ptr), C.byref(cnt)))
-        return int(ns.value), int(ptr.value or 0), int(cnt.value or 0)
-
-    def mg_survivor_buffer(self, n_total):
-        return self._mg_buf("sn_mg_survivor_buffer", n_total)
-
-    def mg_bucket_count_buffer(self, bits):
-        return self._mg_buf("sn_mg_bucket_count_buffer", bits)
-
-    def mg_install_survivors(self, n_total, bits):
-        self._ck(self.L.sn_mg_install_survivors(self.h, n_total, bits))
 
     # ---- multi-GPU, collectives inside the library (sn_multi.cu) -----------------------------
     def comm_init_nccl(self, rank, n_ranks, unique_id):

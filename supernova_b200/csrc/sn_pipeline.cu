@@ -780,111 +780,7 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
     return r;
 }
 
-// ---- multi-GPU: the super-k-mer stream is range-partitioned by minimizer bucket over the ranks ----
-// owner(bucket) = (bucket * nparts) >> bits, so a rank's buckets are one contiguous range of the
-// bucket-ordered record array.  The collectives themselves (one alltoallv of super-k-mer records
-// plus their per-bucket counts, one allgather of the surviving k-mers) are issued by the caller on
-// these device buffers (torch.distributed / NCCL in supernova_b200/multigpu.py).
-
-int sn_mg_good_lengths(sn_ctx* c, const sn_params* p, uint64_t* n_occ)
-{
-    if (!c || !n_occ) return SN_ERR_ARG;
-    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_good_lengths: no reads loaded");
-    CU(cudaSetDevice(c->device));
-    int r;
-    if ((r = sn_i_count_set_params(c, p))) return r;
-    if ((r = sn_i_count_goodlen(c, n_occ))) return r;
-    if (*n_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences on one rank: shard the reads over more GPUs");
-    return SN_OK;
-}
-int sn_mg_partition(sn_ctx* c, int bits, uint32_t nparts, uint64_t* part_records, void** dev_records, void** dev_counts)
-{
-    if (!c || !part_records || !dev_records || !dev_counts || nparts == 0 || bits < 1 || bits > 24 || nparts > (1u << bits)) return SN_ERR_ARG;
-    if (c->stage < 1) return fail(c, SN_ERR_STATE, "sn_mg_partition: no reads loaded");
-    if (!c->goodlen.p || c->goodlen.bytes < 4 * c->cnt.n_reads) return fail(c, SN_ERR_STATE, "sn_mg_partition: run sn_mg_good_lengths first");
-    CU(cudaSetDevice(c->device));
-    uint64_t n_sk = 0;
-    int r = sn_i_msp_partition(c, bits, &n_sk);
-    if (r) return r;
-    const uint64_t* off = c->pool["sk_off"].as<uint64_t>();
-    std::vector<uint64_t> cut(nparts + 1);
-    for (uint32_t o = 0; o <= nparts; ++o) CU(cudaMemcpyAsync(&cut[o], off + sn_i_first_bucket(o, nparts, bits), 8, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    for (uint32_t o = 0; o < nparts; ++o) part_records[o] = cut[o + 1] - cut[o];
-    *dev_records = c->pool["sk_recs"].p;
-    *dev_counts = c->pool["sk_hist"].p;           // after the scatter the per-bucket cursors equal the per-bucket counts
-    return SN_OK;
-}
-void* sn_mg_recv_records(sn_ctx* c, uint64_t n_records)
-{
-    if (!c) return nullptr;
-    cudaSetDevice(c->device);
-    DevBuf& b = c->pool["mg_recs"];
-    if (b.alloc(std::max<uint64_t>(n_records, 1) * 32 + 64) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
-    return b.p;
-}
-void* sn_mg_recv_counts(sn_ctx* c, uint64_t n_counts)
-{
-    if (!c) return nullptr;
-    cudaSetDevice(c->device);
-    DevBuf& b = c->pool["mg_counts"];
-    if (b.alloc(std::max<uint64_t>(n_counts, 1) * 4) != cudaSuccess) { c->err = "cannot allocate the receive buffer"; return nullptr; }
-    return b.p;
-}
-int sn_mg_count_received(sn_ctx* c, uint32_t n_seg, uint32_t n_buckets, uint64_t n_records, uint64_t* n_survivors, void** dev_survivors, void** dev_bucket_counts)
-{
-    if (!c || !n_survivors || !dev_survivors || !dev_bucket_counts || !n_seg || !n_buckets) return SN_ERR_ARG;
-    CU(cudaSetDevice(c->device));
-    DevBuf &recs = c->pool["mg_recs"], &cnts = c->pool["mg_counts"], &off = c->pool["mg_off"];
-    const uint64_t n_cnt = (uint64_t)n_seg * n_buckets;
-    if (!recs.p || !cnts.p || cnts.bytes < 4 * n_cnt) return fail(c, SN_ERR_STATE, "sn_mg_count_received: receive buffers not set");
-    CU(off.alloc(8 * (n_cnt + 1)));
-    uint64_t total = 0;
-    int r = scan_u32(c, cnts.as<uint32_t>(), n_cnt, off.as<uint64_t>(), &total);
-    if (r) return r;
-    if (total != n_records) return fail(c, SN_ERR_DATA, "received per-bucket counts do not add up to the received records");
-    // k-mer occurrences held by the received records (bounds the survivors)
-    unsigned long long* occ = c->counters.as<unsigned long long>();
-    CU(cudaMemsetAsync(occ + 4, 0, 8, c->st));
-    if (n_records) { k_sum_nk<<<std::min(blocks_for(n_records, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(recs.as<uint4>(), n_records, occ + 4); KCHECK("k_sum_nk"); }
-    unsigned long long h_occ = 0;
-    CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    uint64_t n_surv = 0;
-    DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"], &scnt = c->pool["mg_surv_counts"];
-    if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), off.as<uint64_t>(), n_buckets, n_seg, h_occ, surv, surv_off, &n_surv))) return r;
-    CU(scnt.alloc(4ull * n_buckets));
-    k_diff_u32<<<blocks_for(n_buckets, 256), 256, 0, c->st>>>(surv_off.as<uint32_t>(), n_buckets, scnt.as<uint32_t>());
-    KCHECK("k_diff_u32");
-    CU(cudaStreamSynchronize(c->st));
-    c->cnt.n_superkmers = n_records;
-    *n_survivors = n_surv; *dev_survivors = surv.p; *dev_bucket_counts = scnt.p;
-    return SN_OK;
-}
-void* sn_mg_survivor_buffer(sn_ctx* c, uint64_t n_total)
-{
-    if (!c) return nullptr;
-    cudaSetDevice(c->device);
-    DevBuf& b = c->pool["surv_g"];
-    if (b.alloc(std::max<uint64_t>(n_total, 1) * 16) != cudaSuccess) { c->err = "cannot allocate the gathered k-mers"; return nullptr; }
-    return b.p;
-}
-void* sn_mg_bucket_count_buffer(sn_ctx* c, int bits)
-{
-    if (!c || bits < 1 || bits > 24) return nullptr;
-    cudaSetDevice(c->device);
-    DevBuf& b = c->pool["surv_gcnt"];
-    if (b.alloc(4ull << bits) != cudaSuccess) { c->err = "cannot allocate the gathered bucket counts"; return nullptr; }
-    return b.p;
-}
-int sn_mg_install_survivors(sn_ctx* c, uint64_t n_total, int bits)
-{
-    if (!c || bits < 1 || bits > 24) return SN_ERR_ARG;
-    CU(cudaSetDevice(c->device));
-    DevBuf &g = c->pool["surv_g"], &gc = c->pool["surv_gcnt"];
-    if ((n_total && (!g.p || g.bytes < 16 * n_total)) || !gc.p || gc.bytes < (4ull << bits)) return fail(c, SN_ERR_STATE, "call sn_mg_survivor_buffer / sn_mg_bucket_count_buffer first");
-    return sn_i_msp_install_dict(c, g.as<uint4>(), n_total, bits, gc.as<uint32_t>(), false);
-}
+// (the multi-GPU path -- reads sharded, super-k-mers routed by bucket range, the dictionary kept sharded -- is sn_multi.cu)
 
 // ---------------------------------------------------------------------------
 int sn_build_edges(sn_ctx* c)
