@@ -9,8 +9,11 @@
 // reference sources under /root/reference by oracle/build_ref.sh into
 // oracle/_ref/ (git-ignored).
 //
-// Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [INDEX=False|True] [MIN_QUAL=7]
+// Usage: OracleProbe HEAD=<dir>/reads OUT=<dir> [PATHS=True|False] [INDEX=False|True] [DFSIDE=False|True] [MIN_QUAL=7]
 //                    [MIN_FREQ=3] [MIN_BC=2] [IGN_BC_BELOW=0] [MSPEDGES=<edges.bv>]
+//   DFSIDE=True (with INDEX and PATHS): also the other files DF leaves in a.48/ right after the hot path
+//   (10X/DF.cc:573-600, 10X/WriteFiles.cc:16-60): a.k, a.hbx, a.fastb, a.kmers, a.pathsX, a.dup -- each
+//   written by the reference's own code (HyperBasevectorX, ReadPathVecX, MarkDups).
 //   MSPEDGES given: the reference's buildGraphFromMSP (BuildReadQGraph48.cc:1631-1684) instead -- the
 //   production path, where the edges come from the tada stages -- on HEAD.fastb/.qualp and that edge file.
 // The same source is linked twice by oracle/build_ref.sh: against the reference's BuildReadQGraph48.o
@@ -29,6 +32,9 @@
 #include "paths/long/ReadPath.h"
 #include "paths/long/BuildReadQGraph48.h"
 #include "10X/PathsIndex.h"
+#include "10X/SecretOps.h"
+#include "10X/DfTools.h"
+#include "10X/paths/ReadPathVecX.h"
 #include <chrono>
 
 // Progress-dot printer declared in 10X/DfTools.h:466 (defined in DfTools.cc:617-635, a translation unit
@@ -36,6 +42,9 @@
 // that DfTools.cc need not be linked; it computes nothing.
 template <class T> void MakeDots(T& done, T& ndots, const T total) {}
 template void MakeDots(int& done, int& ndots, const int total);
+// The statistics sink MarkDups reports its percentages to (10X/DfTools.h:47; its one instance is defined in
+// DfTools.cc:21, the same unlinked translation unit).  The instance, nothing more.
+StatLogger StatLogger::gInst;
 
 int main(int argc, char** argv)
 {   RunTime();
@@ -47,6 +56,7 @@ int main(int argc, char** argv)
     CommandArgument_Int_OrDefault(MIN_FREQ, 3);
     CommandArgument_Int_OrDefault(MIN_BC, 2);
     CommandArgument_Bool_OrDefault(INDEX, False);
+    CommandArgument_Bool_OrDefault(DFSIDE, False);
     CommandArgument_Int_OrDefault(IGN_BC_BELOW, 0);
     CommandArgument_String_OrDefault(MSPEDGES, "");
     EndCommandArguments;
@@ -82,6 +92,27 @@ int main(int argc, char** argv)
         BinaryWriter::writeFile(OUT + "/a.to_left", to_left);
         BinaryWriter::writeFile(OUT + "/a.to_right", to_right);
         writePathsIndex(rp, inv, OUT, "a.paths.inv", "a.countsb", 15, false);
+        if (DFSIDE) {
+            Echo(ToString(hbv.K()), OUT + "/a.k");                     // WriteFiles.cc:33
+            HyperBasevectorX hbx(hbv);                                  // DF.cc:576, WriteFiles.cc:40-41
+            BinaryWriter::writeFile(OUT + "/a.hbx", hbx);
+            {   vecbvec edges(hbv.Edges().begin(), hbv.Edges().end()); // WriteFiles.cc:46-47
+                edges.WriteAll(OUT + "/a.fastb");   }
+            {   vec<int> kmers(hbv.E());                               // WriteFiles.cc:48-51
+                for (int e = 0; e < hbv.E(); e++) kmers[e] = hbv.Kmers(e);
+                BinaryWriter::writeFile(OUT + "/a.kmers", kmers);   }
+            ReadPathVecX pathsX;                                        // DF.cc:577-579 (InitializePathsXFromPaths, DfTools.cc:24-78,
+            pathsX.append(rp, hbx);                                     //  appends the reads in order, piece by piece)
+            pathsX.WriteAll(OUT + "/a.pathsX");                         // WriteFiles.cc:28
+            vecbvec bases(HEAD + ".fastb");                             // DF.cc:594-600 (frag_reads_orig.fastb = the reads)
+            VirtualMasterVec<PQVec> vmv(HEAD + ".qualp");
+            vec<int32_t> bcd(bci.back(), -1);
+            for (int b = 0; b < bci.isize() - 1; b++)
+                for (int64_t j = bci[b]; j < bci[b + 1]; j++) bcd[j] = b;
+            vec<Bool> dup; double interdup_rate;
+            MarkDups(bases, vmv, pathsX, hbx, bcd, dup, interdup_rate);
+            BinaryWriter::writeFile(OUT + "/a.dup", dup);
+        }
     }
     std::cout << "ORACLE_SECONDS "
               << std::chrono::duration<double>(t1 - t0).count() << std::endl;

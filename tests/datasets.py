@@ -45,6 +45,8 @@ def get(name):
         new = np.ones(n_pairs, bool); new[1:] = bcid[1:] != bcid[:-1]
         bc = np.repeat(np.cumsum(new).astype(np.int32), 2)
         return blk.ravel(), q.ravel(), np.arange(2 * n_pairs + 1, dtype=np.uint64) * 150, bc, None
+    if name == "dupes":
+        return _dupes()
     if name == "polyA":
         # one k-mer (A^48) with more than 2^24 occurrences: 84,000 pairs of 150 x A give 17.3 M of them --
         # the count saturates at 16,777,215 (kmers/ReadPather.h:128-129,145) -- on top of a stress set, with
@@ -61,6 +63,62 @@ def get(name):
     b, q, bc, ids = synth.make_reads(G, pairs, nbc, seed)
     n, L = b.shape
     return b.ravel(), q.ravel(), np.arange(n + 1, dtype=np.uint64) * L, bc, ids
+
+
+def _dupes():
+    """Duplicate read pairs for MarkDups (10X/SecretOps.cc:599-774), on one 70-kb unique contig tiled by error-free reads
+    (run with MIN_FREQ=1, MIN_BC=0: DUPES_PARAMS): exact copies (equal quality sums: the tie and 'artifactual duplicate'
+    branches), copies with better or worse qualities, copies whose partner differs after its first five bases, a triple,
+    and two placements 65,536 bases apart on the same edge whose partners start alike -- ReadPathX keeps the offset in 16 bits
+    (10X/paths/ReadPathParser.cc:31), so the reference calls them duplicates."""
+    rng = np.random.Generator(np.random.Philox(key=4242))
+    C = rng.integers(0, 4, size=70_000, dtype=np.uint8)
+
+    def rc(x):
+        return (3 - x[::-1]).astype(np.uint8)
+
+    def q_of(n):
+        return np.where(rng.random(n) < 0.05, 30, 37).astype(np.uint8)
+    pairs = []                                       # (r1, q1, r2, q2)
+    for i in range(0, 70_000 - 150 + 1, 100):
+        j = i + 200 if i + 350 <= 70_000 else int(rng.integers(0, 69_000))
+        pairs.append([C[i:i + 150].copy(), q_of(150), rc(C[j:j + 150]), q_of(150)])
+    extra = []
+    for t in range(40):                              # exact copies: ties
+        a = pairs[5 + 7 * t]
+        extra.append([x.copy() for x in a])
+    for t in range(20):                              # the copy is better / worse by one quality value
+        a = [x.copy() for x in pairs[300 + 3 * t]]
+        a[1][10] = 38 if t % 2 == 0 else 20
+        extra.append(a)
+    for t in range(20):                              # partner read differs after its first five bases
+        a = [x.copy() for x in pairs[400 + 5 * t]]
+        a[2] = np.concatenate([a[2][:5], rng.integers(0, 4, size=145, dtype=np.uint8)])   # (unrelated sequence: no branch off the contig)
+        extra.append(a)
+    for t in range(5):                               # a triple: two more exact copies
+        a = pairs[600 + 4 * t]
+        extra += [[x.copy() for x in a], [x.copy() for x in a]]
+    for t in range(6):                               # 65,536 apart, partners starting with the same five bases
+        p0 = 1000 + 500 * t
+        head = rc(C[p0 + 200:p0 + 350])[:5]
+        k = next(k for k in range(p0 + 65_536 + 160, 69_850) if np.array_equal(rc(C[k:k + 150])[:5], head))
+        extra.append([C[p0:p0 + 150].copy(), q_of(150), rc(C[p0 + 200:p0 + 350]), q_of(150)])
+        extra.append([C[p0 + 65_536:p0 + 65_686].copy(), q_of(150), rc(C[k:k + 150]), q_of(150)])
+    n0 = len(pairs)
+    bcid = np.sort(rng.integers(0, 30, size=n0))
+    bcid[:25] = -1                                   # some unbarcoded pairs (they stay in front: sorted input)
+    bcid = np.concatenate([bcid, 30 + np.arange(len(extra)) // 3])
+    allp = pairs + extra
+    new = np.ones(len(allp), bool); new[1:] = bcid[1:] != bcid[:-1]
+    new &= bcid >= 0
+    ordinal = np.cumsum(new).astype(np.int32); ordinal[bcid < 0] = 0
+    codes = np.concatenate([x for a in allp for x in (a[0], a[2])])
+    quals = np.concatenate([x for a in allp for x in (a[1], a[3])])
+    off = np.arange(2 * len(allp) + 1, dtype=np.uint64) * 150
+    return codes, quals, off, np.repeat(ordinal, 2), np.repeat(bcid, 2)
+
+
+DUPES_PARAMS = dict(min_qual=7, min_freq=1, min_bc=0)
 
 
 def unpack_edges(ln, off, packed):

@@ -85,6 +85,30 @@ def test_paths_index_restatement_matches_golden(name):
     assert cb == gz(g + "/a.countsb.gz")
 
 
+@pytest.mark.parametrize("name", ["tiny", "stress1", "dupes"])
+def test_df_files_restatement_matches_golden(name):
+    """oracle/dfside.py on the golden a.hbv / tmp.paths / reads.* reproduces what the reference's own HyperBasevectorX,
+    vecbvec / vec<int> writers, ReadPathVecX and MarkDups wrote next (10X/WriteFiles.cc:16-60, 10X/DF.cc:573-600):
+    a.hbx, a.fastb, a.kmers, a.pathsX, a.dup and the three percentages MarkDups prints."""
+    import json
+    from oracle import dfside
+    g = os.path.join(GOLD, name)
+    h = dfside.read_hbv(gz(g + "/a.hbv.gz"))
+    paths = dfside.read_paths(gz(g + "/tmp.paths.gz"))
+    assert dfside.hbx_file(h) == gz(g + "/a.hbx.gz")
+    assert dfside.edges_fastb_file(h) == gz(g + "/a.fastb.gz")
+    assert dfside.kmers_file(h) == gz(g + "/a.kmers.gz")
+    assert dfside.pathsx_file(paths, h) == gz(g + "/a.pathsX.gz")
+    bases = dfside.read_fastb(gz(g + "/reads.fastb.gz"))
+    quals = dfside.read_qualp(gz(g + "/reads.qualp.gz"))
+    bc = dfside.expand_bci(gz(g + "/reads.bci.gz"))
+    dup, ndups, interdups, art = dfside.mark_dups(paths, bases, quals, bc)
+    assert dfside.dup_file(dup) == gz(g + "/a.dup.gz")
+    assert dfside.dup_percentages(dup, ndups, interdups, art) == json.load(open(g + "/dup_stats.json"))
+    if name == "dupes":          # the set has what it is for: ties, artifactual duplicates, and offsets that only collide in 16 bits
+        assert sum(art) > 0 and max(o for o, _ in paths) > 65536
+
+
 @pytest.mark.parametrize("name", ["tiny", "stress1"])
 def test_ingest_restatement_matches_golden(name, tmp_path):
     """oracle/dfside.py (ParseBarcodedFastqs, 10X/ParseBarcodedFastqs.cc:56-146,284-303; PQVecEncoder,
