@@ -394,6 +394,23 @@ def main():
         paths_extra = {"value": world * gbp * max(1, args.steps // 2) / (ms_p / 1e3), "unit": "Gbp/s", "path_ms": stage_p.get("path"),
                        "n_path_edges": ctx.counts()["n_path_edges"]}
 
+    # what DF does with the paths next (10X/DF.cc:573-600) -- writePathsIndex, the ReadPathVecX, MarkDups --
+    # on the paths of the step above, results in host memory; checked in tests/test_gpu_dfside.py against the reference's files
+    dfside = None
+    if not args.no_paths and world == 1:
+        dres = {}
+
+        def step_df():
+            ctx.build_paths_index()
+            ctx.build_pathsx()
+            dres.update(ctx.mark_dups())
+        step_df()
+        kd = max(1, args.steps // 2)
+        ms_d, _, st_d = timed(step_df, kd)
+        dfside = {"ms": ms_d / kd, "paths_index_ms": st_d.get("paths_index"), "pathsx_ms": st_d.get("pathsx"), "mark_dups_ms": st_d.get("mark_dups"),
+                  "n_dup_pairs": dres.get("n_dup_pairs"), "n_pairs": dres.get("n_pairs"),
+                  "what": "sn_build_paths_index + sn_build_pathsx + sn_mark_dups on the step's ReadPaths, results in host memory (ms: wall incl. D2H; *_ms: kernels)"}
+
     ingest = None
     if text_t is not None:
         # ParseBarcodedFastqs on the device -- text in pinned host memory -> reads resident in the
@@ -459,6 +476,8 @@ def main():
         line["parity_detail"] = parity
     if paths_extra:
         line["with_readpaths"] = paths_extra
+    if dfside:
+        line["dfside"] = dfside
     if ingest:
         line["ingest"] = ingest
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -123,6 +123,22 @@ int sn_build_paths_index(sn_ctx* ctx);
 int sn_get_paths_index(sn_ctx* ctx, uint64_t* off /* n_hbv_edges+1 */, uint64_t* read_ids /* n_path_edges */, int32_t* countsb /* n_hbv_edges */);
 int sn_write_paths_index(sn_ctx* ctx, const char* paths_inv /* a.paths.inv */, const char* countsb /* a.countsb */);
 
+/* DF side, the rest of what DF does with the graph and the paths before it goes on (10X/DF.cc:573-600):
+ * -- the ReadPathVecX DF keeps the paths in (InitializePathsXFromPaths, 10X/DfTools.cc:24-78; record format
+ *    10X/paths/ReadPathParser.cc:17-50): per read [edge count u8][offset i16][first edge u32][2 bits per further edge],
+ *    every 10th record indexed.  After sn_path_reads; the buffers stay owned by the context.
+ * -- MarkDups, version 2 (10X/SecretOps.cc:599-774): read pairs placed alike (first edge, offset, first five bases of
+ *    the partner read) are duplicates of each other, the one with the highest quality sum stays.  dup[p] / art[p] per PAIR
+ *    p = read / 2 (`art`: the "artifactual duplicates" it only counts).  After sn_path_reads; needs an even number of
+ *    reads.  The percentages it prints are n_dup_pairs / n_pairs, n_interdups / n_dups, n_art_pairs / n_pairs.       */
+typedef struct sn_dup_stats { uint64_t n_pairs, n_dup_pairs, n_dups, n_interdups, n_art_pairs; } sn_dup_stats;
+int sn_build_pathsx(sn_ctx* ctx);
+int sn_get_pathsx(sn_ctx* ctx, uint64_t* n_index, const int64_t** zip_index, uint64_t* n_bytes, const uint8_t** zipped_data);
+int sn_write_pathsx(sn_ctx* ctx, const char* path);          /* a.pathsX */
+int sn_mark_dups(sn_ctx* ctx, sn_dup_stats* stats /* may be NULL */);
+int sn_get_dups(sn_ctx* ctx, uint8_t* dup /* n_reads / 2 */, uint8_t* art /* n_reads / 2, may be NULL */);
+int sn_write_dup(sn_ctx* ctx, const char* path);             /* a.dup (vec<Bool>) */
+
 /* buildGraphFromMSP (paths/long/BuildReadQGraph48.h:24-26, .cc:1631-1684), the production boundary when the
  * edges come from the tada stages (MSPEDGES = _ASM_SN.asm_graph, mro/_assembler.mro:57): the vec<basevector>
  * file becomes the edge set (any orientation, any order), the HyperBasevector is built from it
@@ -153,6 +169,11 @@ int sn_write_edges_bv(sn_ctx* ctx, const char* path);        /* vec<basevector> 
 int sn_write_inv(sn_ctx* ctx, const char* path);             /* a.inv  (vec<int>)                  */
 int sn_write_to_left_right(sn_ctx* ctx, const char* to_left, const char* to_right);   /* a.to_left, a.to_right (vec<int>) */
 int sn_write_kmer_spectrum(sn_ctx* ctx, const char* json);   /* stats/histogram_kmer_count.json    */
+/* the other files WriteAssemblyFiles leaves next to a.hbv (10X/WriteFiles.cc:33-51)                    */
+int sn_write_hbx(sn_ctx* ctx, const char* path);             /* a.hbx   (HyperBasevectorX)         */
+int sn_write_edges_fastb(sn_ctx* ctx, const char* path);     /* a.fastb (the HBV edges, feudal)    */
+int sn_write_kmers(sn_ctx* ctx, const char* path);           /* a.kmers (vec<int>: k-mers per edge) */
+int sn_write_k(sn_ctx* ctx, const char* path);               /* a.k     ("48")                     */
 
 /* One call == buildReadQGraph48: the four stages, then work_dir/a.hbv (when write_hbv),
  * work_dir/tmp.paths (when with_paths) and work_dir/stats/histogram_kmer_count.json.      */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libsupernova_b200.so")
 _LIB = None
 
-STAGES = ("exchange", "ghosts", "edge_dict", "ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index")
+STAGES = ("exchange", "ghosts", "edge_dict", "ingest_h2d", "ingest_parse", "h2d", "goodlen", "msp_hist", "msp_scatter", "bucket_count", "make_dict", "prune", "edges", "hbv_dev", "hbv_layout", "hbv_host", "hbv_csr", "path", "paths_index", "pathsx", "mark_dups")
 
 
 class SnError(RuntimeError):
@@ -24,6 +24,10 @@ class Params(C.Structure):
 
     def __init__(self, min_qual=7, min_freq=3, min_bc=2, ign_bc_below=0):
         super().__init__(min_qual, min_freq, min_bc, ign_bc_below)
+
+
+class DupStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_dup_pairs", "n_dups", "n_interdups", "n_art_pairs")]
 
 
 class Counts(C.Structure):
@@ -70,7 +74,12 @@ def lib():
         L.sn_get_edges_bytes.argtypes = [vp, C.POINTER(u64)]
         L.sn_get_hbv.argtypes = [vp] + [vp] * 9
         L.sn_get_paths.argtypes = [vp, vp, vp, vp]
-        for f in ("sn_write_hbv", "sn_write_paths", "sn_write_edges_bv", "sn_write_inv", "sn_write_kmer_spectrum"):
+        L.sn_build_pathsx.argtypes = [vp]
+        L.sn_get_pathsx.argtypes = [vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
+        L.sn_mark_dups.argtypes = [vp, C.POINTER(DupStats)]
+        L.sn_get_dups.argtypes = [vp, vp, vp]
+        for f in ("sn_write_hbv", "sn_write_paths", "sn_write_edges_bv", "sn_write_inv", "sn_write_kmer_spectrum", "sn_write_pathsx", "sn_write_dup",
+                  "sn_write_hbx", "sn_write_edges_fastb", "sn_write_kmers", "sn_write_k"):
             getattr(L, f).argtypes = [vp, C.c_char_p]
         L.sn_build_read_qgraph48.argtypes = [vp, C.c_char_p, C.POINTER(Params), i32, i32]
         L.sn_stage_ms.argtypes = [vp, C.c_char_p]
@@ -376,6 +385,47 @@ class Context:
 
     def write_paths_index(self, paths_inv, countsb):
         self._ck(self.L.sn_write_paths_index(self.h, paths_inv.encode(), countsb.encode()))
+
+    # ---- DF side: ReadPathVecX, MarkDups, the files next to a.hbv (10X/DF.cc:573-600, 10X/WriteFiles.cc:16-60) ----
+    def build_pathsx(self):
+        self._ck(self.L.sn_build_pathsx(self.h))
+
+    def pathsx(self):
+        """-> (zip_index i64[ceil(n_reads/10)], zipped_data u8[]) -- copies of the context's buffers"""
+        ni, nb, pi, pd = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.sn_get_pathsx(self.h, C.byref(ni), C.byref(pi), C.byref(nb), C.byref(pd)))
+        idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int64)), shape=(ni.value,)).copy() if ni.value else np.zeros(0, np.int64)
+        dat = np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy() if nb.value else np.zeros(0, np.uint8)
+        return idx, dat
+
+    def write_pathsx(self, path):
+        self._ck(self.L.sn_write_pathsx(self.h, path.encode()))
+
+    def mark_dups(self):
+        st = DupStats()
+        self._ck(self.L.sn_mark_dups(self.h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in DupStats._fields_}
+
+    def dups(self):
+        n = self.counts()["n_reads"] // 2
+        dup = np.zeros(n, np.uint8); art = np.zeros(n, np.uint8)
+        self._ck(self.L.sn_get_dups(self.h, _p(dup), _p(art)))
+        return dup, art
+
+    def write_dup(self, path):
+        self._ck(self.L.sn_write_dup(self.h, path.encode()))
+
+    def write_hbx(self, path):
+        self._ck(self.L.sn_write_hbx(self.h, path.encode()))
+
+    def write_edges_fastb(self, path):
+        self._ck(self.L.sn_write_edges_fastb(self.h, path.encode()))
+
+    def write_kmers(self, path):
+        self._ck(self.L.sn_write_kmers(self.h, path.encode()))
+
+    def write_k(self, path):
+        self._ck(self.L.sn_write_k(self.h, path.encode()))
 
     def write_hbv(self, path):
         self._ck(self.L.sn_write_hbv(self.h, path.encode()))

@@ -1,6 +1,6 @@
 // sn_build_graph -- the C++ host side of the hot path as one command, over the C ABI only
 // (include/supernova_b200.h): what StageBuildGraph + the start of DF do around buildReadQGraph48
-// (10X/runstages/RunStages.cc:404-413, 10X/DF.cc:579-590), for a maintainer who wants to try the
+// (10X/runstages/RunStages.cc:404-413, 10X/DF.cc:573-600), for a maintainer who wants to try the
 // library without touching DF, and for the parity tests (tests/test_cli.py).
 //
 //   sn_build_graph HEAD=<dir>/reads OUT=<dir> [FASTH=<file[.gz]>] [MIN_QUAL=7] [MIN_FREQ=3] [MIN_BC=2]
@@ -9,7 +9,9 @@
 // HEAD   : reads.fastb / reads.qualp / reads.bci as ParseBarcodedFastqs writes them; with FASTH= they are
 //          produced first, on the device, from the barcoded pseudo-FASTQ (and written to HEAD.*).
 // OUT    : a.hbv, tmp.paths, stats/histogram_kmer_count.json as the reference leaves them; with INDEX=True
-//          also a.inv, a.to_left, a.to_right, a.paths.inv, a.countsb.
+//          also what DF leaves in a.48/ before it goes on (10X/WriteFiles.cc:16-60, 10X/DF.cc:573-600): a.k, a.inv, a.to_left,
+//          a.to_right, a.hbx, a.fastb, a.kmers and, from the paths, a.paths.inv, a.countsb, a.pathsX, a.dup (MarkDups; its
+//          three percentages go to stdout as the reference prints them).
 // NGPU   : > 1 = the sharded multi-GPU path (sn_mg_build_graph): one host thread and one context per GPU of this
 //          box, reads split evenly (whole pairs), every collective issued by the library on NCCL -- no Python, no
 //          launcher.  Rank 0 writes a.hbv; tmp.paths is the ranks' ReadPaths in read order.  (INDEX=True: one GPU.)
@@ -120,7 +122,18 @@ int main(int argc, char** argv)
     if (sn_build_read_qgraph48(ctx, out.c_str(), &prm, paths ? 1 : 0, /*write_files=*/1)) return die("buildReadQGraph48");
     if (index) {
         if (sn_write_inv(ctx, (out + "/a.inv").c_str()) || sn_write_to_left_right(ctx, (out + "/a.to_left").c_str(), (out + "/a.to_right").c_str())) return die("a.inv / a.to_left / a.to_right");
+        if (sn_write_k(ctx, (out + "/a.k").c_str()) || sn_write_hbx(ctx, (out + "/a.hbx").c_str()) || sn_write_edges_fastb(ctx, (out + "/a.fastb").c_str())
+            || sn_write_kmers(ctx, (out + "/a.kmers").c_str())) return die("a.k / a.hbx / a.fastb / a.kmers");
         if (paths && (sn_build_paths_index(ctx) || sn_write_paths_index(ctx, (out + "/a.paths.inv").c_str(), (out + "/a.countsb").c_str()))) return die("writePathsIndex");
+        if (paths && (sn_build_pathsx(ctx) || sn_write_pathsx(ctx, (out + "/a.pathsX").c_str()))) return die("a.pathsX");
+        if (paths) {
+            sn_dup_stats ds;
+            if (sn_mark_dups(ctx, &ds) || sn_write_dup(ctx, (out + "/a.dup").c_str())) return die("MarkDups");
+            const double np = ds.n_pairs ? (double)ds.n_pairs : 1.0;                     // (SecretOps.cc:757-770)
+            printf("%.2f%% of pairs appear to be duplicates\n", 100.0 * ds.n_dup_pairs / np);
+            printf("%.2f%% of duplicates involve multiple barcodes\n", (100.0 * ds.n_interdups) / (double)ds.n_dups);
+            printf("%.2f%% of pairs appear to be artifactual duplicates\n", 100.0 * ds.n_art_pairs / np);
+        }
     }
     sn_counts c;
     sn_get_counts(ctx, &c);

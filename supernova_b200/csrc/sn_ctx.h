@@ -94,6 +94,9 @@ struct sn_ctx {
     DevBuf plen, poffset, path_off, pedges;
     std::vector<int32_t> h_poffset, h_pedges; std::vector<uint64_t> h_path_off; bool paths_on_host = false;
     std::vector<uint64_t> pi_off, pi_ids; std::vector<int32_t> pi_countsb; bool pi_ready = false;     // paths index (writePathsIndex)
+    // DF side (sn_dfside.cu): the ReadPathVecX of the paths and MarkDups' flags, in host memory once built
+    std::vector<uint8_t> px_data; std::vector<int64_t> px_index; bool px_ready = false;
+    std::vector<uint8_t> md_dup, md_art; sn_dup_stats md_stats{}; bool md_ready = false;
     DevBuf counters;     // small scratch of u64 counters
     std::map<std::string, DevBuf> pool;      // stage temporaries, kept across steps
     std::map<std::string, HostBuf> hpool;    // pinned staging, kept across steps

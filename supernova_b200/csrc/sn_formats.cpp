@@ -318,6 +318,49 @@ bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32
     put_basevectors(o, packed, off, len, n_edges);
     return o.commit(err);
 }
+static void put_serfvecs(Out& o, uint64_t n, const uint32_t* start, const int32_t* vals)
+{   // MasterVec<SerfVec<int>>: u64 count, then per inner vector u32 count + ints (feudal/OuterVec.h:377-379, feudal/SmallVec.h:355-357)
+    std::vector<uint8_t> buf; buf.reserve(8 + n * 4 + 4ull * start[n]);
+    auto put = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; buf.insert(buf.end(), b, b + k); };
+    put(&n, 8);
+    for (uint64_t v = 0; v < n; ++v) { uint32_t m = start[v + 1] - start[v]; put(&m, 4); if (m) put(vals + start[v], 4ull * m); }
+    o.put(buf.data(), buf.size());
+}
+bool write_hbx(const std::string& path, int32_t K, uint64_t n_vert, const uint32_t* from_start, const int32_t* from_v, const int32_t* from_e,
+               const uint32_t* to_start, const int32_t* to_v, const int32_t* to_e,
+               const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges,
+               const int32_t* to_left, const int32_t* to_right, std::string& err)
+{
+    Out o(path);
+    o.put(MAGIC, 8); o.pod(K);
+    put_serfvecs(o, n_vert, from_start, from_v); put_serfvecs(o, n_vert, to_start, to_v);
+    put_serfvecs(o, n_vert, from_start, from_e); put_serfvecs(o, n_vert, to_start, to_e);
+    put_basevectors(o, packed, off, len, n_edges);
+    o.pod(n_edges); o.put(to_left, 4 * n_edges);
+    o.pod(n_edges); o.put(to_right, 4 * n_edges);
+    return o.commit(err);
+}
+bool write_pathsx(const std::string& path, uint64_t n_reads, const int64_t* index, uint64_t n_index, const uint8_t* data, uint64_t n_bytes, std::string& err)
+{
+    Out o(path);
+    const int64_t hdr[5] = {10, 0, (int64_t)n_reads, (int64_t)n_index, (int64_t)n_bytes};     // skip, start_rid, next_start_rid, sizes
+    o.put(hdr, sizeof hdr);
+    o.put(index, 8 * n_index);
+    o.put(data, n_bytes);
+    return o.commit(err);
+}
+bool write_vec_u8(const std::string& path, const uint8_t* v, uint64_t n, std::string& err)
+{
+    Out o(path);
+    o.put(MAGIC, 8); o.pod(n); o.put(v, n);
+    return o.commit(err);
+}
+bool write_text(const std::string& path, const std::string& text, std::string& err)
+{
+    Out o(path);
+    o.put(text.data(), text.size());
+    return o.commit(err);
+}
 bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err)
 {
     Out o(path);

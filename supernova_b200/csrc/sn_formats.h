@@ -42,6 +42,18 @@ bool read_bv(const std::string& path, Fastb& out, std::string& err);
 bool write_hbv(const std::string& path, int32_t K, uint64_t n_vert, const uint32_t* from_start, const int32_t* from_v,
                const int32_t* from_e, const uint32_t* to_start, const int32_t* to_e,
                const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges, std::string& err);
+// a.hbx (HyperBasevectorX: paths/HyperBasevector.cc:133-137, graph/Digraph.h:435-437, graph/DigraphTemplate.h:3107-3113):
+// K, from_, to_, from_edge_obj_, to_edge_obj_ as MasterVec<SerfVec<int>>, edges_, to_left_, to_right_
+bool write_hbx(const std::string& path, int32_t K, uint64_t n_vert, const uint32_t* from_start, const int32_t* from_v, const int32_t* from_e,
+               const uint32_t* to_start, const int32_t* to_v, const int32_t* to_e,
+               const uint8_t* packed, const uint64_t* off, const uint32_t* len, uint64_t n_edges,
+               const int32_t* to_left, const int32_t* to_right, std::string& err);
+// a.pathsX (ReadPathVecX::writeBinary, 10X/paths/ReadPathVecX.cc:976-996): skip = 10, start_rid = 0, next_start_rid,
+// the two sizes, ZipIndex (i64), ZippedData
+bool write_pathsx(const std::string& path, uint64_t n_reads, const int64_t* index, uint64_t n_index, const uint8_t* data, uint64_t n_bytes, std::string& err);
+// vec<unsigned char> (a.dup: vec<Bool>) and a plain text file (a.k)
+bool write_vec_u8(const std::string& path, const uint8_t* v, uint64_t n, std::string& err);
+bool write_text(const std::string& path, const std::string& text, std::string& err);
 // feudal ReadPathVec (paths/long/ReadPath.h:61-63, feudal/FeudalFileWriter.cc:100-121)
 bool write_paths(const std::string& path, uint64_t n, const int32_t* offset, const uint64_t* poff, const int32_t* edges, std::string& err);
 // whole file into memory; a gzip file (.gz) is inflated with zlib (the reference pipes it through zcat)

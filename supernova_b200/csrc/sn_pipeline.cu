@@ -506,13 +506,11 @@ int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uin
     CU(cudaMemsetAsync(seg_cnt.p, 0, 4 * n_virtual + 16, c->st));
     const int variant = getenv("SN_BC_VARIANT") ? atoi(getenv("SN_BC_VARIANT")) : 0;
 #define SN_BC_LAUNCH(T, S, I, M) do { \
-        static bool attr_set = false; \
-        if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem<T, S>))); attr_set = true; } \
+        CU(cudaFuncSetAttribute(k_bucket_count<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem<T, S>)));   /* (per device: every call) */ \
         k_bucket_count<T, S, I, M><<<n_buckets, T, sizeof(BcSmem<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
             scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3); } while (0)
 #define SN_BC2_LAUNCH(T, S, I, M) do { \
-        static bool attr_set = false; \
-        if (!attr_set) { CU(cudaFuncSetAttribute(k_bucket_count2<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem2<T, S>))); attr_set = true; } \
+        CU(cudaFuncSetAttribute(k_bucket_count2<T, S, I, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BcSmem2<T, S>))); \
         k_bucket_count2<T, S, I, M><<<(unsigned)n_virtual, T, sizeof(BcSmem2<T, S>), c->st>>>(recs, off, n_buckets, n_seg, c->params.min_freq, c->params.min_bc, c->have_bc ? 1 : 0, \
             scratch.as<uint4>(), cap, occ + 3, seg_base.as<uint64_t>(), seg_cnt.as<uint32_t>(), occ + 2, u32c + 3, vbucket.as<uint2>(), (uint32_t)n_virtual); } while (0)
     if ((variant == 1 || variant == 4) && n_virtual != n_buckets) return fail(c, SN_ERR_ARG, "SN_BC_VARIANT 1/4 (first count kernel) cannot share out heavy buckets: set SN_BC_HEAVY high");
@@ -1032,7 +1030,7 @@ int sn_build_hbv(sn_ctx* c)
     snh::Hbv& H = c->hbv;
     H.n_vert = (int32_t)nV;
     c->cnt.n_hbv_vertices = nV; c->cnt.n_hbv_edges = nH;
-    int r;
+
     if (h_big[0]) {
     // ---- big components: the host loop (sn_hbv.cpp) over the records, which travel to pinned host memory ---------------
     CU(h_groups.alloc(64ull * nV)); CU(h_irec.alloc(64ull * n_items));
@@ -1317,7 +1315,7 @@ int sn_path_reads(sn_ctx* c)
     CU(scratch.alloc(16 * n));
     uint32_t* u32c = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8);
     CU(cudaMemsetAsync(u32c + 5, 0, 4, c->st));
-    c->paths_on_host = false; c->pi_ready = false;
+    c->paths_on_host = false; c->pi_ready = false; c->px_ready = false; c->md_ready = false;
     PathInputs in;
     in.n_reads = n; in.bases = c->bases.as<uint8_t>(); in.boff = c->boff.as<uint64_t>(); in.len = c->len.as<uint32_t>();
     in.quals = c->have_pq ? nullptr : c->quals.as<uint8_t>(); in.qoff = c->qoff.as<uint64_t>();

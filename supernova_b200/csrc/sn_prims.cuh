@@ -145,8 +145,8 @@ static __global__ void __launch_bounds__(SN_SCAN_THREADS) k_scan_apply(const uin
 }
 
 // out[i] = sum_{j<i} in[j]; out[n] = total.  `tmp` needs (ceil(n/TILE)+1) u64.
-inline uint64_t scan_tmp_words(uint64_t n) { return (n + SN_SCAN_TILE - 1) / SN_SCAN_TILE + 1; }
-inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* tmp, cudaStream_t st)
+static inline uint64_t scan_tmp_words(uint64_t n) { return (n + SN_SCAN_TILE - 1) / SN_SCAN_TILE + 1; }
+static inline void exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* tmp, cudaStream_t st)
 {
     if (n == 0) { cudaMemsetAsync(out, 0, sizeof(uint64_t), st); return; }
     uint64_t nt = (n + SN_SCAN_TILE - 1) / SN_SCAN_TILE;
@@ -322,7 +322,7 @@ k_rs_scatter(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t n, 
     }
 }
 
-inline size_t radix_sort_tmp_bytes(uint32_t n)
+static inline size_t radix_sort_tmp_bytes(uint32_t n)
 {
     uint32_t nt = (n + SN_RS_MIN_TILE - 1) / SN_RS_MIN_TILE;
     return (size_t)SN_RS_MAX_PASSES * 256 * 4 + 64 + (size_t)nt * 256 * 8;
@@ -331,7 +331,7 @@ inline size_t radix_sort_tmp_bytes(uint32_t n)
 // radix_sort_histograms (one read of the records) then radix_sort_passes (PASSES digit passes,
 // each one read + one write).  The result ends in `a` (even number of ping-pong passes).
 template <int MODE>
-inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+static inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     uint32_t* hist = (uint32_t*)tmp;
@@ -340,25 +340,24 @@ inline cudaError_t radix_sort_histograms(const uint4* a, uint32_t n, void* tmp, 
     k_rs_scan_hist<<<RsMode<MODE>::PASSES, 256, 0, st>>>(hist);
     return cudaGetLastError();
 }
-inline int rs_threads()
+static inline int rs_threads()
 {
     static int t = 0;
     if (!t) { const char* e = getenv("SN_RS_THREADS"); t = e ? atoi(e) : 512; if (t != 256 && t != 512) t = 512; }
     return t;
 }
 template <int MODE, int THREADS>
-inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
+static inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
 {
     constexpr int TILE = THREADS * SN_RS_ITEMS;
     uint32_t nt = (n + TILE - 1) / TILE;
     uint32_t* hist = (uint32_t*)tmp;
     uint32_t* counters = hist + SN_RS_MAX_PASSES * 256;
     uint64_t* status = (uint64_t*)(counters + 16);
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // every call: the kernels have internal linkage (one copy per translation unit that sorts) and the attribute
+        // belongs to the copy and to the current device; the call costs microseconds
         cudaError_t e = cudaFuncSetAttribute(k_rs_scatter<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<THREADS>));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     uint4* src = a; uint4* dst = b;
     for (int p = 0; p < RsMode<MODE>::PASSES; ++p) {
@@ -369,13 +368,13 @@ inline cudaError_t radix_sort_passes_t(uint4* a, uint4* b, uint32_t n, void* tmp
     return cudaGetLastError();
 }
 template <int MODE>
-inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
+static inline cudaError_t radix_sort_passes(uint4* a, uint4* b, uint32_t n, void* tmp, int arg, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     return rs_threads() == 512 ? radix_sort_passes_t<MODE, 512>(a, b, n, tmp, arg, st) : radix_sort_passes_t<MODE, 256>(a, b, n, tmp, arg, st);
 }
 template <int MODE>
-inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
+static inline cudaError_t radix_sort(uint4* a, uint4* b, uint32_t n, void* tmp, int num_sms, cudaStream_t st)
 {
     cudaError_t e = radix_sort_histograms<MODE>(a, n, tmp, num_sms, st);
     if (e != cudaSuccess) return e;

@@ -7,6 +7,7 @@
 #include "../../supernova_b200/csrc/sn_graph.cuh"
 #include "../../supernova_b200/csrc/sn_path.cuh"
 #include "../../supernova_b200/csrc/sn_msp.cuh"
+#include "../../supernova_b200/csrc/sn_dfside.cuh"
 #include "../../supernova_b200/csrc/sn_hbv.h"
 #include "../../supernova_b200/csrc/sn_formats.h"
 #include <algorithm>
@@ -233,6 +234,81 @@ int hs_paths(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t* bof
         if (!snf::write_paths(paths_file, n_reads, s->poffset.data(), s->poff.data(), s->pedges.data(), err)) return -1;
     }
     return overflow ? -2 : 0;
+}
+
+static HbvView hbv_view_of(const snh::Hbv& H)
+{
+    HbvView h; h.fwd_xlat = H.fwd.data(); h.rev_xlat = H.rev.data(); h.to_left = H.to_left.data(); h.to_right = H.to_right.data();
+    h.src = H.src.data(); h.from_start = H.from_start.data(); h.from_v = H.from_v.data(); h.from_e = H.from_e.data();
+    h.to_start = H.to_start.data(); h.to_v = H.to_v.data(); h.to_e = H.to_e.data();
+    return h;
+}
+
+// k_rpx_sizes, the scan, k_rpx_encode over the paths hs_paths left: a.pathsX
+int hs_pathsx(Sim* s, const char* file)
+{
+    const uint64_t n = s->poffset.size();
+    const HbvView h = hbv_view_of(s->hbv);
+    std::vector<uint64_t> zoff(n + 1, 0);
+    for (uint64_t r = 0; r < n; ++r) zoff[r + 1] = zoff[r] + rpx_size((uint32_t)(s->poff[r + 1] - s->poff[r]));
+    std::vector<uint8_t> data(zoff[n] + 16, 0xEE);                       // (junk: the encoder must write every byte of a record)
+    std::vector<int64_t> index((n + 9) / 10);
+    for (uint64_t r = 0; r < n; ++r) {
+        rpx_encode(data.data() + zoff[r], s->pedges.data() + s->poff[r], (uint32_t)(s->poff[r + 1] - s->poff[r]), s->poffset[r], h);
+        if (r % 10 == 0) index[r / 10] = (int64_t)zoff[r];
+    }
+    std::string err;
+    return snf::write_pathsx(file, n, index.data(), index.size(), data.data(), zoff[n], err) ? 0 : -1;
+}
+
+// k_md_records, the sort, k_md_members, k_md_groups, k_md_art_records, the sort, k_md_art; counts = {ndups, interdups}
+int hs_mark_dups(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t* boff, const uint32_t* len, const uint8_t* quals, const uint64_t* qoff,
+                 const int32_t* bc, uint8_t* dup, uint8_t* art, uint64_t* counts)
+{
+    const uint32_t n = (uint32_t)n_reads;
+    if (n & 1) return -1;
+    std::vector<uint4> rec(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint32_t m = r ^ 1u, np = (uint32_t)(s->poff[r + 1] - s->poff[r]);
+        rec[r] = dup_record(np, np ? s->pedges[s->poff[r]] : 0, s->poffset[r], bases + boff[m], len[m], r);
+    }
+    auto key_less = [](const uint4& a, const uint4& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); };
+    std::sort(rec.begin(), rec.end(), key_less);
+    std::vector<uint32_t> qsum(n, 0), tiegrp(n, 0); std::vector<uint8_t> flags(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (rec[i].x == SN_DUP_NONE) continue;
+        const bool prev = i > 0 && dup_same_key(rec[i - 1], rec[i]), next = i + 1 < n && dup_same_key(rec[i + 1], rec[i]);
+        if (!prev) flags[i] |= 1;
+        if (prev || next) {
+            flags[i] |= 2;
+            for (uint32_t t = 0; t < 2; ++t) { const uint32_t r = rec[i].z ^ t; for (uint32_t b = 0; b < len[r]; ++b) qsum[i] += quals[qoff[r] + b]; }
+        }
+    }
+    memset(dup, 0, n / 2); memset(art, 0, n / 2);
+    counts[0] = counts[1] = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        if ((flags[j] & 3) != 3) continue;
+        uint32_t k = j + 1;
+        while (k < n && !(flags[k] & 1) && rec[k].x != SN_DUP_NONE) ++k;
+        const DupGroupOut o = dup_group(rec.data(), qsum.data(), j, k, [&](uint32_t id) -> int32_t { return bc ? bc[id] : 0; });
+        for (uint32_t l = j; l < k; ++l) { if (l != o.best) dup[rec[l].z >> 1] = 1; if (o.tie) tiegrp[l] = j + 1; }
+        counts[0] += k - j - 1; if (o.inter) counts[1] += k - j - 1;
+    }
+    std::vector<uint4> ar(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        ar[i].x = ar[i].y = SN_DUP_NONE; ar[i].z = rec[i].z; ar[i].w = 0;
+        if (tiegrp[i]) { const uint32_t r = rec[i].z; ar[i].x = tiegrp[i]; ar[i].y = read_content_hash(bases + boff[r], quals + qoff[r], len[r]); }
+    }
+    std::sort(ar.begin(), ar.end(), key_less);
+    for (uint32_t i = 1; i < n; ++i) {
+        if (ar[i].x == SN_DUP_NONE || !dup_same_key(ar[i], ar[i - 1])) continue;
+        const uint32_t a = ar[i].z;
+        for (uint32_t p = i; p-- > 0 && dup_same_key(ar[p], ar[i]);) {
+            const uint32_t b = ar[p].z;
+            if (read_content_equal(bases + boff[a], quals + qoff[a], len[a], bases + boff[b], quals + qoff[b], len[b])) { art[a >> 1] = 1; break; }
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -14,7 +14,7 @@ def lib():
     if _L is None:
         so = os.path.join(HERE, "libhostsim.so")
         src = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(ROOT, "supernova_b200", "csrc", f) for f in
-                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh")]
+                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh", "sn_dfside.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DSN_HOSTSIM", "-o", so] + src[:3] + ["-lz"])
         L = C.CDLL(so)
@@ -32,6 +32,8 @@ def lib():
         L.hs_get_graph_info.argtypes = [vp, vp, vp, vp]
         L.hs_hbv.argtypes = [vp, C.c_char_p]
         L.hs_paths.argtypes = [vp, u64, vp, vp, vp, vp, vp, C.c_char_p]
+        L.hs_pathsx.argtypes = [vp, C.c_char_p]
+        L.hs_mark_dups.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.hs_extract_read.argtypes = [vp, C.c_uint32, C.c_int32, vp]
         L.hs_extract_read.restype = C.c_uint32
         L.hs_msp_read.argtypes = [vp, C.c_uint32, C.c_int32, vp, vp, vp, vp]
@@ -76,3 +78,15 @@ class HostSim:
         rc = lib().hs_paths(self.h, len(ln), bases.ctypes.data, boff.ctypes.data, ln.ctypes.data, quals.ctypes.data, qoff.ctypes.data,
                             path.encode())
         assert rc == 0, rc
+
+    def pathsx(self, path):
+        assert lib().hs_pathsx(self.h, path.encode()) == 0
+
+    def mark_dups(self, bases, boff, ln, quals, qoff, bc):
+        n = len(ln)
+        dup = np.zeros(n // 2, np.uint8); art = np.zeros(n // 2, np.uint8); counts = np.zeros(2, np.uint64)
+        bc = np.ascontiguousarray(bc, dtype=np.int32)
+        rc = lib().hs_mark_dups(self.h, n, bases.ctypes.data, boff.ctypes.data, ln.ctypes.data, quals.ctypes.data, qoff.ctypes.data,
+                                bc.ctypes.data, dup.ctypes.data, art.ctypes.data, counts.ctypes.data)
+        assert rc == 0, rc
+        return dup, art, int(counts[0]), int(counts[1])

@@ -36,8 +36,15 @@ def test_cli_reproduces_the_reference_files(built, name, tmp_path):
     assert r.returncode == 0, r.stderr
     assert "k-mers" in r.stdout
     g = os.path.join(GOLD, name)
-    for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths", "a.inv", "a.to_left", "a.to_right", "a.paths.inv", "a.countsb"):
+    for f in ("reads.fastb", "reads.qualp", "reads.bci", "a.hbv", "tmp.paths", "a.inv", "a.to_left", "a.to_right", "a.paths.inv", "a.countsb",
+              "a.hbx", "a.fastb", "a.kmers", "a.pathsX", "a.dup"):
         assert open(wd + "/" + f, "rb").read() == gzip.open(g + "/" + f + ".gz", "rb").read(), f
+    assert open(wd + "/a.k").read() == "48\n"
+    import json
+    st = json.load(open(g + "/dup_stats.json"))
+    assert st["dup_perc"] + "% of pairs appear to be duplicates" in r.stdout
+    assert st["art_dup_perc"] + "% of pairs appear to be artifactual duplicates" in r.stdout
+    assert st["interdup_perc"] + "% of duplicates involve multiple barcodes" in r.stdout
     assert open(wd + "/stats/histogram_kmer_count.json").read() == open(g + "/histogram_kmer_count.json").read()
     # and from the files alone (no FASTH): the same graph
     out2 = wd + "/again"

@@ -118,3 +118,31 @@ def test_msp_superkmers_expand_to_the_extract_records(sb, name):
     same = (recs[1:] == recs[:-1]).all(axis=1)
     assert np.array_equal(bhs[1:][same], bhs[:-1][same]), "a canonical k-mer was sent to two buckets"
     assert tot_sk * 6 < len(recs)            # super-k-mers are much fewer than k-mers (~17 k-mers each on clean reads)
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1", "dupes"])
+def test_df_side_logic_matches_golden(sb, name, tmp_path):
+    """The per-read logic of sn_dfside.cuh (ReadPathX records, MarkDups), applied kernel by kernel as sn_dfside.cu does,
+    against the files the reference's ReadPathVecX and MarkDups wrote (tests/golden: a.pathsX, a.dup, dup_stats.json)."""
+    import json
+    from hostsim import HostSim
+    from oracle import dfside
+    codes, quals, off, bc, _ = datasets.get(name)
+    P = datasets.DUPES_PARAMS if name == "dupes" else {}
+    o = Oracle(codes, quals, off, bc, **P).run()
+    km = o.kmers()
+    recs = np.stack([km[:, 0], km[:, 1], km[:, 2], km[:, 3] | (km[:, 4] << 24)], axis=1).astype(np.uint32)
+    hs = HostSim(recs)
+    hs.prune()
+    hs.edges()
+    hs.hbv(str(tmp_path / "h.hbv"))
+    pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=2)
+    hs.paths(pb, boff, pl, quals, off, str(tmp_path / "h.paths"))
+    g = os.path.join(GOLD, name)
+    gz = lambda f: gzip.open(os.path.join(g, f + ".gz"), "rb").read()
+    assert open(tmp_path / "h.paths", "rb").read() == gz("tmp.paths")
+    hs.pathsx(str(tmp_path / "h.pathsX"))
+    assert open(tmp_path / "h.pathsX", "rb").read() == gz("a.pathsX")
+    dup, art, ndups, inter = hs.mark_dups(pb, boff, pl, quals, off, bc)
+    assert dfside.dup_file(dup.tolist()) == gz("a.dup")
+    assert dfside.dup_percentages(dup.tolist(), ndups, inter, art.tolist()) == json.load(open(os.path.join(g, "dup_stats.json")))
