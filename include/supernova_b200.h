@@ -105,6 +105,14 @@ int sn_load_read_files_range(sn_ctx* ctx, const char* fastb, const char* qualp, 
  * passes as bcp, 10X/runstages/RunStages.cc:405); bc may be NULL (n_bc ignored)            */
 int sn_load_read_files_bc(sn_ctx* ctx, const char* fastb, const char* qualp, const int32_t* bc, uint64_t n_bc);
 
+/* Which of the reference's two implementations of the count the context follows where they differ (SURVEY §8 a14-a16,
+ * equivalence note): SN_SEM_CXX (default) = the C++ path, a read needs goodLen >= K + 1 (BuildReadQGraph48.cc:160);
+ * SN_SEM_TADA = the Rust stages (lib/tada), a read trimmed to exactly K bases still gives its one k-mer, without
+ * neighbours (cmd_msp.rs:109-110, find_trim_len :129-146).  Thresholds and barcode rule are the same in both
+ * (min_kmer_obs = MIN_FREQ, num_bcs > 1 = MIN_BC 2; utils.rs:322-408).  Set before sn_count_kmers / a streamed load.  */
+enum { SN_SEM_CXX = 0, SN_SEM_TADA = 1 };
+int sn_set_semantics(sn_ctx* ctx, int semantics);
+
 /* ---- stages (must run in this order) -------------------------------------------------- */
 /* createDict up to the KmerVec (BuildReadQGraph48.cc:218-292): good lengths, k-mer records,
  * sort, count, filter.                                                                  */

@@ -30,6 +30,7 @@ def lib():
             getattr(L, "sn_oracle_" + f).argtypes = [vp]
         L.sn_oracle_run.argtypes = [vp, C.c_int]
         L.sn_oracle_set_ign_bc_below.argtypes = [vp, C.c_int64]
+        L.sn_oracle_set_count_len_k.argtypes = [vp, C.c_int]
         L.sn_oracle_free.argtypes = [vp]
         for f, rt in (("n_occ", u64), ("n_kmers", u64), ("n_edges", u64), ("n_vert", i32), ("n_hbv_edges", i32)):
             getattr(L, "sn_oracle_" + f).restype = rt
@@ -59,7 +60,7 @@ def _arr(ptr, n, dtype):
 class Oracle:
     """Runs the restated reference pipeline on ragged reads given as base codes."""
 
-    def __init__(self, bases, quals, off, bc, min_qual=7, min_freq=3, min_bc=2, ign_bc_below=0):
+    def __init__(self, bases, quals, off, bc, min_qual=7, min_freq=3, min_bc=2, ign_bc_below=0, count_len_k=False):
         self.bases = np.ascontiguousarray(bases, dtype=np.uint8).ravel()
         self.quals = np.ascontiguousarray(quals, dtype=np.uint8).ravel()
         self.off = np.ascontiguousarray(off, dtype=np.uint64)
@@ -70,6 +71,8 @@ class Oracle:
                                  None if self.bc is None else self.bc.ctypes.data, min_qual, min_freq, min_bc)
         if ign_bc_below:
             L.sn_oracle_set_ign_bc_below(self.h, int(ign_bc_below))
+        if count_len_k:        # the tada variant: reads trimmed to exactly K bases are counted
+            L.sn_oracle_set_count_len_k(self.h, 1)
 
     @classmethod
     def from_matrix(cls, bases2d, quals2d, bc, **kw):

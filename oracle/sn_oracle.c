@@ -146,6 +146,7 @@ typedef struct {
     const int32_t*  bc;      /* per-read barcode ordinal (10X/DF.cc:464-469) or NULL */
     unsigned min_qual, min_freq, min_bc;
     int64_t ign_bc_below;
+    int count_len_k;          /* tada variant (lib/tada/src/cmd_msp.rs:109-110): a read trimmed to exactly K bases gives its one k-mer */
     /* stage outputs */
     uint32_t* good_len;
     uint64_t  n_occ;         /* k-mer occurrences emitted by Kmerizer::map */
@@ -188,8 +189,13 @@ static inline void emit_occ(occ_t* o, const kmer_t* k, uint8_t ctx, int32_t bc)
     else { o->kmer = *k; o->ctx = ctx; }
     o->bc = bc;
 }
-static uint64_t kmerize_read(const uint8_t* b, uint32_t len, int32_t bc, occ_t* out)
+static uint64_t kmerize_read(const uint8_t* b, uint32_t len, int32_t bc, occ_t* out, int count_len_k)
 {
+    if (count_len_k && len == K) {                                /* msp_read, cmd_msp.rs:109-110: one k-mer, no neighbour on either side */
+        kmer_t one = kmer_from_codes(b);
+        emit_occ(&out[0], &one, 0, bc);
+        return 1;
+    }
     if (len < K + 1) return 0;
     uint64_t n = 0;
     kmer_t kkk = kmer_from_codes(b);
@@ -247,7 +253,7 @@ int sn_oracle_count(sn_oracle_t* o)
         uint32_t len = (uint32_t)(o->off[r + 1] - o->off[r]);
         uint32_t g = good_len(o->quals + o->off[r], len, o->min_qual);
         o->good_len[r] = g;
-        if (g >= K + 1) tot += g - K + 1;
+        if (g >= K + 1 || (o->count_len_k && g == K)) tot += g - K + 1;
     }
     o->n_occ = tot;
     occ_t* occ = (occ_t*)malloc(sizeof(occ_t) * (tot ? tot : 1));
@@ -255,7 +261,7 @@ int sn_oracle_count(sn_oracle_t* o)
     for (uint64_t r = 0; r < n; ++r) {
         int32_t bc = -1;                                        /* :158-159 */
         if ((int64_t)r >= o->ign_bc_below && o->bc) bc = o->bc[r];
-        p += kmerize_read(o->bases + o->off[r], o->good_len[r], bc, occ + p);
+        p += kmerize_read(o->bases + o->off[r], o->good_len[r], bc, occ + p, o->count_len_k);
     }
     qsort(occ, tot, sizeof(occ_t), occ_cmp);
     /* group */
@@ -943,11 +949,12 @@ sn_oracle_t* sn_oracle_new(uint64_t n_reads, const uint8_t* bases, const uint8_t
 {
     sn_oracle_t* o = (sn_oracle_t*)calloc(1, sizeof(sn_oracle_t));
     o->n_reads = n_reads; o->bases = bases; o->quals = quals; o->off = off; o->bc = bc;
-    o->min_qual = min_qual; o->min_freq = min_freq; o->min_bc = min_bc; o->ign_bc_below = 0;
+    o->min_qual = min_qual; o->min_freq = min_freq; o->min_bc = min_bc; o->ign_bc_below = 0; o->count_len_k = 0;
     return o;
 }
 /* ignBcBelow of buildReadQGraph48 (BuildReadQGraph48.cc:158-159): reads with id below it count as barcode -1 */
 void sn_oracle_set_ign_bc_below(sn_oracle_t* o, int64_t v) { o->ign_bc_below = v; }
+void sn_oracle_set_count_len_k(sn_oracle_t* o, int v) { o->count_len_k = v; }
 int sn_oracle_run(sn_oracle_t* o, int with_paths)
 {
     sn_oracle_count(o); sn_oracle_prune(o); sn_oracle_edges(o); sn_oracle_hbv(o);

@@ -75,6 +75,7 @@ def lib():
         L.sn_get_hbv.argtypes = [vp] + [vp] * 9
         L.sn_get_paths.argtypes = [vp, vp, vp, vp]
         L.sn_build_pathsx.argtypes = [vp]
+        L.sn_set_semantics.argtypes = [vp, i32]
         L.sn_get_pathsx.argtypes = [vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
         L.sn_mark_dups.argtypes = [vp, C.POINTER(DupStats)]
         L.sn_get_dups.argtypes = [vp, vp, vp]
@@ -385,6 +386,10 @@ class Context:
 
     def write_paths_index(self, paths_inv, countsb):
         self._ck(self.L.sn_write_paths_index(self.h, paths_inv.encode(), countsb.encode()))
+
+    def set_semantics(self, tada=False):
+        """SN_SEM_TADA: reads trimmed to exactly K bases are counted (lib/tada/src/cmd_msp.rs:109-110)"""
+        self._ck(self.L.sn_set_semantics(self.h, 1 if tada else 0))
 
     # ---- DF side: ReadPathVecX, MarkDups, the files next to a.hbv (10X/DF.cc:573-600, 10X/WriteFiles.cc:16-60) ----
     def build_pathsx(self):

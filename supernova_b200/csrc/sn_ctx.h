@@ -73,6 +73,7 @@ struct sn_ctx {
     std::map<std::string, Timer> timers;
     std::map<std::string, double> host_ms;
     sn_params params{7, 3, 2, 0};
+    uint32_t min_gl = SN_K + 1;      // reads trimmed below this give no k-mer: K + 1 (BuildReadQGraph48.cc:160), K with sn_set_semantics(SN_SEM_TADA)
     sn_counts cnt{};
     int stage = 0;       // 0 none, 1 reads, 2 counted, 3 edges, 4 hbv, 5 paths
     bool reads_ok = false;   // reads are resident (a graph can also come from an edge file without any)

@@ -26,7 +26,7 @@ namespace sn {
 // Kmerizer::map will emit.
 // ---------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, const uint8_t* __restrict__ pq, const uint64_t* __restrict__ pq_off,
-                                                       const uint32_t* __restrict__ len, uint32_t min_qual,
+                                                       const uint32_t* __restrict__ len, uint32_t min_qual, uint32_t min_gl /* reads trimmed below it give no k-mer */,
                                                        uint32_t* __restrict__ goodlen, unsigned long long* occ_total, uint32_t* bad_reads)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +68,7 @@ static __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, 
         if (rem != 0 || (p < pend && *p != 0)) bad = true;      // the PQVec holds more quals than the read has bases
         if (bad) { atomicAdd(bad_reads, 1u); gl = 0; }
         goodlen[r] = gl;
-        occ = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
+        occ = gl >= min_gl ? gl - SN_K + 1 : 0;
     }
     // block reduce, one atomic per block
     __shared__ uint32_t sm[8];
@@ -95,7 +95,7 @@ static __global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, con
 
 // same, for callers that already hold one u8 per base
 static __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, const uint8_t* __restrict__ quals, const uint64_t* __restrict__ qoff,
-                                                    const uint32_t* __restrict__ len, uint32_t min_qual,
+                                                    const uint32_t* __restrict__ len, uint32_t min_qual, uint32_t min_gl,
                                                     uint32_t* __restrict__ goodlen, unsigned long long* occ_total)
 {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,7 @@ static __global__ void __launch_bounds__(256) k_q8_goodlen(uint64_t n_reads, con
         uint32_t L = len[r], run = 0, gl = 0;
         for (uint32_t i = 0; i < L; ++i) { run = q[i] >= min_qual ? run + 1 : 0; if (run >= SN_K) gl = i + 1; }
         goodlen[r] = gl;
-        occ = gl >= SN_K + 1 ? gl - SN_K + 1 : 0;
+        occ = gl >= min_gl ? gl - SN_K + 1 : 0;
     }
     __shared__ uint32_t sm[8];
     for (int o = 16; o > 0; o >>= 1) occ += __shfl_down_sync(SN_FULL, occ, o);

@@ -51,9 +51,9 @@ namespace sn {
 #pragma nv_exec_check_disable
 #endif
 template <class F>
-SN_HD void msp_scan(const uint8_t* rp, uint32_t gl, uint32_t* ring, uint32_t ring_stride, F&& emit)
+SN_HD void msp_scan(const uint8_t* rp, uint32_t gl, uint32_t* ring, uint32_t ring_stride, F&& emit, uint32_t min_gl = SN_K + 1)
 {
-    if (gl < SN_K + 1) return;
+    if (gl < min_gl) return;                         // (min_gl = K + 1: BuildReadQGraph48.cc:160; K in the tada variant, cmd_msp.rs:109-110)
     uint32_t fwd = 0, rc = 0, byte = 0;
     uint32_t r = 0;                                  // index of the current p-mer inside its block
     uint32_t pm = 0;                                 // prefix minimum of the current block
@@ -189,7 +189,7 @@ namespace sn {
 
 template <bool EMIT>
 static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
-                                                            const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
+                                                            const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below, uint32_t min_gl,
                                                             int bits, uint32_t* __restrict__ counter /* hist or cursor, one per bucket of the window */,
                                                             const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
                                                             uint32_t b_lo = 0u, uint32_t b_n = 0xFFFFFFFFu /* bucket window [b_lo, b_lo + b_n): a count in several passes */,
@@ -218,7 +218,7 @@ static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_read
     const uint64_t r = r0 + tid;
     const uint32_t gl = goodlen[r];
     if (only_overflow && only_overflow[r] != 255u) return;
-    if (gl < SN_K + 1) { if (nruns) nruns[r] = 0; return; }
+    if (gl < min_gl) { if (nruns) nruns[r] = 0; return; }
     const uint8_t* rp = sb + (uint32_t)(boff[r] - lo) + shift;
     uint32_t bc24 = 0xFFFFFFu;
     if (EMIT) {
@@ -247,7 +247,7 @@ static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_read
         ++nrun;
         if (nq < SN_MS_QUEUE) { qv[nq * SN_MS_READS + tid] = minval; qs[nq * SN_MS_READS + tid] = start | (nk << 16); ++nq; }
         else process(start, nk, minval);
-    });
+    }, min_gl);
     // the runs of the read, kept for the passes that follow (scatter, further bucket windows): [block][slot][thread],
     // so that a warp reads and writes them coalesced; a read with more runs than slots is marked and scanned again
     if (nruns) {

@@ -392,11 +392,11 @@ int sn_i_count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
     t_begin(c, "goodlen");
     if (c->have_pq) {
         k_pqvec_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->params.min_qual, c->goodlen.as<uint32_t>(), occ, u32c);
+            c->params.min_qual, c->min_gl, c->goodlen.as<uint32_t>(), occ, u32c);
         KCHECK("k_pqvec_goodlen");
     } else {
         k_q8_goodlen<<<blocks_for(n, 256), 256, 0, c->st>>>(n, c->quals.as<uint8_t>(), c->qoff.as<uint64_t>(), c->len.as<uint32_t>(),
-            c->params.min_qual, c->goodlen.as<uint32_t>(), occ);
+            c->params.min_qual, c->min_gl, c->goodlen.as<uint32_t>(), occ);
         KCHECK("k_q8_goodlen");
     }
     t_end(c, "goodlen");
@@ -435,14 +435,14 @@ int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, u
             KCHECK("k_msp_place<hist>");
             if (c->dsc_overflow) {
                 k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-                    bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, nullptr, nullptr, nruns.as<uint8_t>());
+                    bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, nullptr, nullptr, nruns.as<uint8_t>());
                 KCHECK("k_msp_scan<hist, overflow>");
             }
         } else {
             CU(dsc.alloc(8ull * SN_MS_QUEUE * SN_MS_READS * grid)); CU(nruns.alloc(n));
             CU(cudaMemsetAsync(ovf, 0, 4, c->st));
             k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-                bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), nullptr, ovf);
+                bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), nullptr, ovf);
             KCHECK("k_msp_scan<hist>");
             CU(cudaMemcpyAsync(&c->dsc_overflow, ovf, 4, cudaMemcpyDeviceToHost, c->st));      // (host value valid after the scan's sync below)
             c->dsc_ready = true;
@@ -464,7 +464,7 @@ int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, u
     }
     if (!c->dsc_ready || c->dsc_overflow) {
         k_msp_scan<true><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, nullptr, nullptr, c->dsc_ready ? nruns.as<uint8_t>() : nullptr);
+            bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, nullptr, nullptr, c->dsc_ready ? nruns.as<uint8_t>() : nullptr);
         KCHECK("k_msp_scan<scatter>");
     }
     t_end(c, "msp_scatter");
@@ -645,7 +645,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
         CUB_(cudaEventRecord(c->ev_copy[ch], c->st2));
         CUB_(cudaStreamWaitEvent(c->st, c->ev_copy[ch], 0));
         k_pqvec_goodlen<<<blocks_for(r1 - r0, 256), 256, 0, c->st>>>(r1 - r0, c->pq.as<uint8_t>(), c->pqoff.as<uint64_t>() + r0, c->len.as<uint32_t>() + r0,
-            c->params.min_qual, c->goodlen.as<uint32_t>() + r0, occ, u32c);
+            c->params.min_qual, c->min_gl, c->goodlen.as<uint32_t>() + r0, occ, u32c);
         ++c->launches;
     }
     t_end(c, "goodlen");
@@ -688,7 +688,7 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
         CUB_(cudaStreamWaitEvent(c->st, c->ev_copy[MAXCH + ch], 0));
         if (with_hist && h_occ) {
             k_msp_scan<false><<<blocks_for(r1 - r0, SN_MS_READS), SN_MS_READS, 0, c->st>>>(r1 - r0, c->bases.as<uint8_t>(), c->boff.as<uint64_t>() + r0,
-                c->goodlen.as<uint32_t>() + r0, nullptr, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, 0u, 0xFFFFFFFFu,
+                c->goodlen.as<uint32_t>() + r0, nullptr, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, 0u, 0xFFFFFFFFu,
                 dsc.as<uint2>() + (r0 / SN_MS_READS) * (uint64_t)(SN_MS_QUEUE * SN_MS_READS), nruns.as<uint8_t>() + r0, nullptr, ovf);
             ++c->launches;
         }
@@ -712,6 +712,14 @@ int sn_load_reads_streamed(sn_ctx* c, uint64_t n_reads, const uint8_t* bases, co
     c->hist_ready_bits = (with_hist && h_occ) ? bits : -1;
     c->dsc_ready = with_hist && h_occ; c->dsc_overflow = h_ovf;
     c->stage = 1; c->reads_ok = true;
+    return SN_OK;
+}
+
+int sn_set_semantics(sn_ctx* c, int semantics)
+{
+    if (!c || (semantics != SN_SEM_CXX && semantics != SN_SEM_TADA)) return SN_ERR_ARG;
+    const uint32_t want = semantics == SN_SEM_TADA ? SN_K : SN_K + 1;
+    if (want != c->min_gl) { c->min_gl = want; c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false; }    // (work a streamed load did under the other rule is void)
     return SN_OK;
 }
 

@@ -166,3 +166,48 @@ def test_repeat_family_heavy_buckets(sb, tmp_path):
             ref = h
         else:
             assert all(np.array_equal(ref[x], h[x]) for x in ref)
+
+
+@pytest.mark.parametrize("name", ["stress1", "stress4", "C1"])
+@pytest.mark.parametrize("streamed", [False, True])
+def test_tada_semantics_count_reads_trimmed_to_k(sb, name, streamed, tmp_path):
+    """SN_SEM_TADA (SURVEY a14/a15 and the equivalence note): a read whose trimmed length is exactly K gives its one k-mer,
+    without neighbours (lib/tada/src/cmd_msp.rs:109-110; the C++ path drops it, BuildReadQGraph48.cc:160).  The oracle carries
+    the same switch (pinned on the CPU against an independent restatement of the Rust rule, tests/test_oracle_golden.py);
+    table, a.hbv and tmp.paths must equal the oracle's.  The stress sets hold reads of 48 bases."""
+    from oracle.oracle import Oracle
+    codes, quals, off, bc, _ = datasets.get(name)
+    if name == "C1":          # (fixed-length reads: trim some of them to exactly K by a low quality right behind base K)
+        quals = quals.copy()
+        rng = np.random.default_rng(5)
+        for r in rng.choice(len(off) - 1, 400, replace=False):
+            quals[int(off[r]) + 48:int(off[r + 1])] = 2
+            quals[int(off[r]):int(off[r]) + 48] = 37
+    o = Oracle(codes, quals, off, bc, count_len_k=True).run()
+    o0 = Oracle(codes, quals, off, bc).stage("count")
+    gl = o.good_len()
+    assert int((gl == 48).sum()) > 0 and o.kmers().shape[0] >= o0.kmers().shape[0]
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    wd = str(tmp_path)
+    with sb.Context(0) as ctx:
+        ctx.set_semantics(tada=True)
+        if streamed:
+            import ctypes as C
+            a = [np.ascontiguousarray(x) for x in (pb, boff, ln, pq, pqoff, bc.astype(np.int32))]
+            ctx.load_reads_streamed_ptr(len(ln), *[x.ctypes.data_as(C.c_void_p) for x in a])
+        else:
+            ctx.load_reads(pb, boff, ln, pq, pqoff, bc)
+        ctx.build_read_qgraph48(wd, sb.Params(), with_paths=True)
+        km, ok = ctx.kmers(), o.kmers()
+        assert ctx.counts()["n_kmer_occurrences"] == int(np.where(gl >= 48, gl - 47, 0).sum())
+        assert km.shape[0] == ok.shape[0] and np.array_equal(km[:, :3], ok[:, :3])
+        assert np.array_equal(km[:, 3], ok[:, 3] | (ok[:, 4] << 24))
+        o.write_hbv(wd + "/oracle.hbv"); o.write_paths(wd + "/oracle.paths")
+        assert open(wd + "/a.hbv", "rb").read() == open(wd + "/oracle.hbv", "rb").read()
+        assert open(wd + "/tmp.paths", "rb").read() == open(wd + "/oracle.paths", "rb").read()
+        # and back: the default rule on the same context
+        ctx.set_semantics(tada=False)
+        ctx.count_kmers(sb.Params())
+        k0 = o0.kmers()
+        km = ctx.kmers()
+        assert km.shape[0] == k0.shape[0] and np.array_equal(km[:, :3], k0[:, :3])

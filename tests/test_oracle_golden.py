@@ -139,3 +139,47 @@ def test_two_file_ingest_restatement_matches_golden(tmp_path):
     g = os.path.join(GOLD, "tiny")
     assert fb == gz(g + "/split.reads.fastb.gz") and qp == gz(g + "/split.reads.qualp.gz") and bci == gz(g + "/split.reads.bci.gz")
     assert bci != gz(g + "/reads.bci.gz")                  # the cut really opens one more barcode
+
+
+@pytest.mark.parametrize("name", ["tiny", "stress1", "stress4"])
+def test_oracle_tada_switch_against_an_independent_restatement(name):
+    """count_len_k (the tada rule, lib/tada/src/cmd_msp.rs:109-146, utils.rs:322-408): every k-mer of every read trimmed to
+    >= K bases by find_trim_len, canonical (min of k-mer and reverse complement), valid iff seen >= min_kmer_obs times and
+    under more than one barcode (bc 0 = none).  Restated here with python dicts, independently of the C oracle's sort.
+    PARITY UNPINNED against the Rust binary (no rustc in this image); pinned against this restatement only."""
+    codes, quals, off, bc, _ = datasets.get(name)
+    K = 48
+    obs, bcs = {}, {}
+    n_len_k = 0
+    for r in range(len(off) - 1):
+        b = codes[int(off[r]):int(off[r + 1])]
+        q = quals[int(off[r]):int(off[r + 1])]
+        good, trim = 0, 0
+        for i in range(len(q) - 1, -1, -1):                     # find_trim_len
+            if q[i] < 7:
+                good = 0
+            else:
+                good += 1
+                if good == K:
+                    trim = i + K
+                    break
+        if trim < K:
+            continue
+        n_len_k += trim == K
+        s = bytes(b[:trim])
+        rc = bytes(3 - x for x in reversed(s))
+        for i in range(trim - K + 1):
+            f, v = s[i:i + K], rc[trim - K - i:trim - i]
+            k = min(f, v)
+            obs[k] = obs.get(k, 0) + 1
+            if bc[r] > 0:
+                bcs.setdefault(k, set()).add(int(bc[r]))
+    valid = {k: c for k, c in obs.items() if c >= 3 and len(bcs.get(k, ())) > 1}
+    o = Oracle(codes, quals, off, bc, count_len_k=True).stage("count")
+    km = o.kmers()
+    mine = {}
+    for row in km:
+        w = (int(row[0]) << 64) | (int(row[1]) << 32) | int(row[2])
+        mine[bytes((w >> (2 * (K - 1 - i))) & 3 for i in range(K))] = int(row[3])
+    assert mine == valid
+    assert n_len_k > 0 or name == "tiny"
