@@ -97,6 +97,15 @@ int sn_load_fasth_file(sn_ctx* ctx, const char* path /* plain or .gz */);
 int sn_load_fasth_files(sn_ctx* ctx, const char* const* paths, uint32_t n_files);
 /* the loaded reads as reads.fastb / reads.qualp / reads.bci (any may be NULL)                        */
 int sn_save_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
+/* synthetic linked reads generated ON the device (counter-based: every base is a pure function of seed and
+ * index; no genome in memory), for workloads a host generator cannot produce in reasonable time.  The context receives the
+ * reads of pairs [first_pair, first_pair + n_pairs) of a job of spec->total_pairs pairs (a rank's slice), 2 x 150 bases each,
+ * barcode ordinals ascending, quals PQVec-encoded on the device.  err_thresholds: 150 integers, substitution probability at
+ * position j in units of 2^-24 (supernova_b200/synth.py: cb_error_thresholds).  The numpy twin (synth.make_reads_cb) gives
+ * the same reads bit for bit.                                                                                          */
+typedef struct sn_synth { uint64_t genome_bases, total_pairs, seed; uint32_t n_barcodes; } sn_synth;
+int sn_generate_reads(sn_ctx* ctx, const sn_synth* spec, uint64_t first_pair, uint64_t n_pairs, const uint32_t* err_thresholds);
+
 /* the three files ParseBarcodedFastqs writes (10X/ParseBarcodedFastqs.cc:284-303)      */
 int sn_load_read_files(sn_ctx* ctx, const char* fastb, const char* qualp, const char* bci);
 /* reads [first_read, first_read + n_reads) of the files (n_reads = 0: to the end): one rank's shard; bci may be NULL */

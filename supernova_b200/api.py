@@ -26,6 +26,10 @@ class Params(C.Structure):
         super().__init__(min_qual, min_freq, min_bc, ign_bc_below)
 
 
+class SynthSpec(C.Structure):
+    _fields_ = [("genome_bases", C.c_uint64), ("total_pairs", C.c_uint64), ("seed", C.c_uint64), ("n_barcodes", C.c_uint32)]
+
+
 class DupStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_dup_pairs", "n_dups", "n_interdups", "n_art_pairs")]
 
@@ -75,6 +79,7 @@ def lib():
         L.sn_get_hbv.argtypes = [vp] + [vp] * 9
         L.sn_get_paths.argtypes = [vp, vp, vp, vp]
         L.sn_build_pathsx.argtypes = [vp]
+        L.sn_generate_reads.argtypes = [vp, C.POINTER(SynthSpec), u64, u64, vp]
         L.sn_set_semantics.argtypes = [vp, i32]
         L.sn_get_pathsx.argtypes = [vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
         L.sn_mark_dups.argtypes = [vp, C.POINTER(DupStats)]
@@ -386,6 +391,14 @@ class Context:
 
     def write_paths_index(self, paths_inv, countsb):
         self._ck(self.L.sn_write_paths_index(self.h, paths_inv.encode(), countsb.encode()))
+
+    def generate_reads(self, G, total_pairs, n_bc, seed, first_pair=0, n_pairs=None):
+        """sn_generate_reads: the counter-based synthetic reads (csrc/sn_synth.cuh; twin: synth.make_reads_cb) made on the device"""
+        from . import synth
+        spec = SynthSpec(int(G), int(total_pairs), int(seed), int(n_bc))
+        T = np.ascontiguousarray(synth.cb_error_thresholds(), np.uint32)
+        n_pairs = total_pairs - first_pair if n_pairs is None else n_pairs
+        self._ck(self.L.sn_generate_reads(self.h, C.byref(spec), int(first_pair), int(n_pairs), _p(T)))
 
     def set_semantics(self, tada=False):
         """SN_SEM_TADA: reads trimmed to exactly K bases are counted (lib/tada/src/cmd_msp.rs:109-110)"""

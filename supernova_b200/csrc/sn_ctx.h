@@ -10,6 +10,9 @@
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <vector>
@@ -163,6 +166,23 @@ inline sn::DictView dict_view(sn_ctx* c)
     d.hs = c->dict_hs.as<uint32_t>();
     return d;
 }
+
+// SN_POOL_REPORT=1: the device buffers above 64 MB at a stage boundary, to stderr (sizing big jobs)
+inline void pool_report(sn_ctx* c, const char* when)
+{
+    static const bool on = getenv("SN_POOL_REPORT") != nullptr;
+    if (!on) return;
+    size_t total = 0; std::string line;
+    auto add = [&](const char* name, const DevBuf& b) { total += b.cap; if (b.cap >= (64u << 20)) line += std::string(" ") + name + "=" + std::to_string(b.cap >> 20); };
+    add("bases", c->bases); add("boff", c->boff); add("len", c->len); add("quals", c->quals); add("bc", c->bc); add("pq", c->pq); add("pqoff", c->pqoff); add("goodlen", c->goodlen);
+    add("dict", c->dict); add("dboff", c->dboff); add("dict_hs", c->dict_hs); add("ebases", c->ebases); add("eoff", c->eoff); add("elen", c->elen);
+    add("plen", c->plen); add("poffset", c->poffset); add("path_off", c->path_off); add("pedges", c->pedges);
+    for (auto& kv : c->pool) add(kv.first.c_str(), kv.second);
+    fprintf(stderr, "[pools %s] total %zu MB:%s\n", when, total >> 20, line.c_str());
+}
+// frees stage temporaries by name (big jobs: what a finished stage leaves behind is not needed by the next)
+inline void pool_release(sn_ctx* c, std::initializer_list<const char*> names)
+{ for (const char* n : names) { auto it = c->pool.find(n); if (it != c->pool.end()) it->second.release(); } }
 
 inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 

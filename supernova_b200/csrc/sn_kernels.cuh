@@ -78,6 +78,12 @@ static __global__ void __launch_bounds__(256) k_pqvec_goodlen(uint64_t n_reads, 
     if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < 8; ++w) t += sm[w]; if (t) atomicAdd(occ_total, (unsigned long long)t); }
 }
 
+// out[i] = in[i] + add
+static __global__ void __launch_bounds__(256) k_add_u64(const uint64_t* __restrict__ in, uint64_t n, uint64_t add, uint64_t* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + add;
+}
 // input limits checked on the device: total bases, longest read, largest barcode ordinal
 static __global__ void __launch_bounds__(256) k_read_stats(uint64_t n_reads, const uint32_t* __restrict__ len, const int32_t* __restrict__ bc,
                                                     unsigned long long* total_bases, uint32_t* max_len, int32_t* max_bc)

@@ -401,6 +401,8 @@ extern "C" int sn_i_build_edges2(sn_ctx* c)
     if (kmers_on_edges != n_total)
         return fail(c, SN_ERR_DATA, "edge stage covered " + std::to_string(kmers_on_edges) + " of " + std::to_string(n_total) + " dictionary k-mers");
     c->stage = 3;
+    // a job counted in several passes is a big one: what this stage leaves behind per k-mer is not needed again
+    if (c->cnt.n_kmer_occurrences >= 3600000000ull) pool_release(c, {"links", "stop_pos", "flag", "etype"});
     return SN_OK;
 }
 

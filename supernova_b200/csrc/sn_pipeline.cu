@@ -7,6 +7,7 @@
 #include "sn_kernels.cuh"
 #include "sn_msp.cuh"
 #include "sn_ingest.cuh"
+#include "sn_synth.cuh"
 #include "sn_hbvdev.cuh"
 #include "sn_edict.cuh"
 #include "sn_ctx.h"
@@ -284,6 +285,68 @@ static int load_fasth_impl(sn_ctx* c, const char* text, uint64_t n_bytes, const 
     if (h_err & SN_ING_E_QUAL) return fail(c, SN_ERR_DATA, "fasth: a quality character outside '!'..'`' (Q0..Q63): PQVec cannot hold it (the reference's PQVecEncoder gives up on it too)");
     if (h_err & SN_ING_E_BASE) return fail(c, SN_ERR_DATA, "fasth: a base other than ACGTN (the reference draws other ambiguity codes at random: not reproducible)");
     c->have_bc = true; c->have_pq = true; c->quals.release();
+    return finish_load(c);
+}
+// the synthetic linked reads of pairs [first_pair, first_pair + n_pairs) of a job of spec->total_pairs pairs,
+// generated in place (sn_synth.cuh); quals go through the ingest path's PQVec encoder chunk by chunk
+int sn_generate_reads(sn_ctx* c, const sn_synth* spec, uint64_t first_pair, uint64_t n_pairs, const uint32_t* err_thresholds /* 150 */)
+{
+    if (!c || !spec || !err_thresholds) return SN_ERR_ARG;
+    if (!n_pairs || first_pair + n_pairs > spec->total_pairs || spec->genome_bases < 1000 || !spec->n_barcodes) return fail(c, SN_ERR_ARG, "sn_generate_reads: empty slice, slice beyond total_pairs, genome below 1000 bases or no barcodes");
+    if (spec->n_barcodes >= 0xFFFFFEu) return fail(c, SN_ERR_ARG, "more than 2^24-2 distinct barcodes in one context");
+    const uint64_t n = 2 * n_pairs;
+    if (n >= (1ull << 32)) return fail(c, SN_ERR_ARG, "sn_generate_reads: more than 2^32-1 reads per context");
+    CU(cudaSetDevice(c->device));
+    c->cnt = sn_counts{}; c->stage = 0; c->reads_ok = false; c->paths_on_host = false;
+    c->gl_ready = false; c->hist_ready_bits = -1; c->dsc_ready = false;
+    c->cnt.n_reads = n;
+    SynSpec sp; sp.genome_bases = spec->genome_bases; sp.total_pairs = spec->total_pairs; sp.seed = spec->seed; sp.n_barcodes = spec->n_barcodes;
+    constexpr uint64_t NB = (SN_SYN_L + 3) / 4, CAP = SN_SYN_L + 8;
+    uint64_t CH = std::min<uint64_t>(n, 4ull << 20);                            // reads per PQVec chunk
+    if (const char* e = getenv("SN_SYN_CHUNK")) { const long long v = atoll(e); if (v >= 2) CH = std::min<uint64_t>(n, (uint64_t)v); }   // tests: many chunks on a small set
+    DevBuf &T = c->pool["syn_T"], &qtext = c->pool["syn_qtext"], &qpos = c->pool["ing_qpos"], &slot = c->pool["ing_slot"], &psz = c->pool["ing_pqsize"],
+           &scratch = c->pool["ing_scratch"], &coff = c->pool["syn_coff"];
+    uint32_t* err = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + 8) + 10;
+    CU(cudaMemsetAsync(err, 0, 4, c->st));
+    CU(T.alloc(4 * SN_SYN_L)); CU(cudaMemcpyAsync(T.p, err_thresholds, 4 * SN_SYN_L, cudaMemcpyHostToDevice, c->st));
+    CU(c->bases.alloc(n * NB + 64)); CU(c->boff.alloc(8 * (n + 1))); CU(c->len.alloc(4 * n)); CU(c->bc.alloc(4 * n)); CU(c->pqoff.alloc(8 * (n + 1)));
+    CU(qtext.alloc(CH * SN_SYN_L)); CU(qpos.alloc(8 * CH)); CU(slot.alloc(8 * (CH + 1))); CU(psz.alloc(4 * CH)); CU(scratch.alloc(CH * CAP + 16)); CU(coff.alloc(8 * (CH + 1)));
+    CU(cudaMemsetAsync((char*)c->bases.p + n * NB, 0, 64, c->st));
+    // the PQVec stream grows chunk by chunk: ~0.31 bytes per qual on these reads, a quarter more to start with
+    uint64_t pq_cap = n * 60 + 1024, pq_used = 0;
+    CU(c->pq.alloc(pq_cap));
+    c->have_bc = true; c->have_pq = true; c->quals.release();
+    t_begin(c, "h2d");
+    for (uint64_t r0 = 0; r0 < n; r0 += CH) {
+        const uint64_t m = std::min(CH, n - r0);
+        k_synth_reads<<<blocks_for(m, 128), 128, 0, c->st>>>(sp, T.as<uint32_t>(), first_pair, r0, m, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->len.as<uint32_t>(),
+            c->bc.as<int32_t>(), qtext.as<uint8_t>(), qpos.as<uint64_t>(), slot.as<uint64_t>());
+        KCHECK("k_synth_reads");
+        k_fasth_pqvec<<<blocks_for(m, 128), 128, 0, c->st>>>(qtext.as<uint8_t>(), qpos.as<uint64_t>(), c->len.as<uint32_t>() + r0, slot.as<uint64_t>(), m, scratch.as<uint8_t>(), psz.as<uint32_t>(), err);
+        KCHECK("k_fasth_pqvec");
+        uint64_t bytes = 0;
+        { int r = scan_u32(c, psz.as<uint32_t>(), m, coff.as<uint64_t>(), &bytes); if (r) return r; }
+        if (pq_used + bytes + 16 > pq_cap) {                                  // grow, keeping what is there
+            DevBuf bigger;
+            pq_cap = std::max<uint64_t>(pq_used + bytes + 16, (uint64_t)((double)(pq_used + bytes) * (double)n / (double)(r0 + m)) + (64ull << 20));
+            CU(bigger.alloc(pq_cap));
+            if (pq_used) CU(cudaMemcpyAsync(bigger.p, c->pq.p, pq_used, cudaMemcpyDeviceToDevice, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            std::swap(c->pq.p, bigger.p); std::swap(c->pq.bytes, bigger.bytes); std::swap(c->pq.cap, bigger.cap);
+        }
+        k_add_u64<<<blocks_for(m + 1, 256), 256, 0, c->st>>>(coff.as<uint64_t>(), m + 1, pq_used, c->pqoff.as<uint64_t>() + r0);
+        KCHECK("k_add_u64");
+        k_fasth_pq_compact<<<blocks_for(m * 32, 256), 256, 0, c->st>>>(scratch.as<uint8_t>(), slot.as<uint64_t>(), psz.as<uint32_t>(), c->pqoff.as<uint64_t>() + r0, m, c->pq.as<uint8_t>());
+        KCHECK("k_fasth_pq_compact");
+        pq_used += bytes;
+    }
+    CU(cudaMemsetAsync((char*)c->pq.p + pq_used, 0, 16, c->st));
+    {   // boff[n]
+        const uint64_t endb = n * NB;
+        CU(cudaMemcpyAsync(c->boff.as<uint64_t>() + n, &endb, 8, cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    pool_release(c, {"syn_qtext", "syn_coff", "ing_scratch", "ing_qpos", "ing_slot", "ing_pqsize"});
     return finish_load(c);
 }
 int sn_load_fasth_file(sn_ctx* c, const char* path)
@@ -781,7 +844,10 @@ int sn_count_kmers(sn_ctx* c, const sn_params* p)
         n_total += n_surv;
     }
     c->cnt.n_superkmers = n_sk_total;
+    // (a job this size needs the room: the passes' temporaries go before the dictionary is laid out, the survivors after)
+    pool_release(c, {"sk_recs", "sk_off", "sk_dsc", "sk_nruns", "sk_hist", "surv_a", "surv_off", "surv_scratch"});
     r = sn_i_msp_install_dict(c, all.as<uint4>(), n_total, bits, all_cnt.as<uint32_t>(), false);
+    pool_release(c, {"surv_all", "surv_all_cnt"});
     c->cnt.n_kmers_distinct = n_dist;
     return r;
 }
@@ -796,6 +862,7 @@ int sn_build_edges(sn_ctx* c)
     CU(cudaSetDevice(c->device));
     {   // the stop-indexed stage of the sharded path (sn_multi.cu) also runs on one rank; it is the default; SN_EDGES2=0 runs the first implementation below for A/B timing
         const char* e2 = getenv("SN_EDGES2");
+        pool_report(c, "before edges");
         if (!(e2 && atoi(e2) == 0) || c->dict_sharded) return sn_i_build_edges2(c);
     }
     const uint32_t n = (uint32_t)c->cnt.n_kmers;
@@ -918,6 +985,7 @@ int sn_build_hbv(sn_ctx* c)
     if (!c) return SN_ERR_ARG;
     if (c->stage < 3) return fail(c, SN_ERR_STATE, "sn_build_hbv: run sn_build_edges first");
     CU(cudaSetDevice(c->device));
+    pool_report(c, "before hbv");
     const uint32_t nE = (uint32_t)c->cnt.n_edges;
     c->cnt.n_hbv_vertices = 0; c->cnt.n_hbv_edges = 0;
     if (!nE) {

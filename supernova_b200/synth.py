@@ -261,3 +261,75 @@ def fasth_text(bases, quals, bc_ids):
     out[:, o:o + 9] = np.frombuffer(b"IIIIIIII\n", np.uint8); o += 9
     assert o == rec_len
     return out.ravel()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Counter-based generator: the numpy twin of csrc/sn_synth.cuh -- every value is a pure function of
+# (seed, stream, index), all integer arithmetic, so the device generator (sn_generate_reads) and this one agree bit for bit.
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _key(seed, stream):
+    return _mix64(np.array([(int(seed) ^ ((stream * 0xD6E8FEB86659FD93) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64))[0]
+
+
+def _h(key, a, b):
+    with np.errstate(over="ignore"):
+        return _mix64(_mix64(key ^ a) ^ b)
+
+
+def cb_error_thresholds(L=150):
+    """substitution probability at position j in units of 2^-24: floor(2^24 * (0.001 + 0.02 (j/L)^3)), exact integers"""
+    return np.array([(2 ** 24 * (L ** 3 * 100 + 2 * 1000 * j ** 3)) // (1000 * 100 * L ** 3) for j in range(L)], dtype=np.uint32)
+
+
+def _hap_base(kg, ks, hap, i):
+    """base i of haplotype hap (arrays broadcast)"""
+    with np.errstate(over="ignore"):
+        b = (_h(kg, i >> np.uint64(5), np.uint64(0)) >> (np.uint64(2) * (i & np.uint64(31)))) & np.uint64(3)
+        w = i // np.uint64(1000)
+        s = _h(ks, w, np.uint64(0))
+        snp = (hap != 0) & (i == w * np.uint64(1000) + (s & np.uint64(0xFFFFFFFF)) % np.uint64(1000))
+        alt = (b + np.uint64(1) + (s >> np.uint64(32)) % np.uint64(3)) & np.uint64(3)
+    return np.where(snp, alt, b)
+
+
+def make_reads_cb(G, total_pairs, n_bc, seed, first_pair=0, n_pairs=None, L=150):
+    """pairs [first_pair, first_pair + n_pairs) of the job -> (bases u8 [2n, L], quals u8 [2n, L], bc i32 [2n])"""
+    assert L == 150
+    n_pairs = total_pairs - first_pair if n_pairs is None else n_pairs
+    with np.errstate(over="ignore"):
+        kg, ks, kp, ke = (_key(seed, k) for k in (1, 2, 3, 4))
+        p = np.arange(first_pair, first_pair + n_pairs, dtype=np.uint64)
+        u = _h(kp, p, np.uint64(0))
+        hap = (u & np.uint64(1))[:, None]
+        flip = ((u >> np.uint64(1)) & np.uint64(1)).astype(bool)
+        insert = (np.uint64(300) + ((u >> np.uint64(8)) & np.uint64(0xFFFFFF)) % np.uint64(200))
+        start = _h(kp, p, np.uint64(1)) % (np.uint64(G) - insert)
+        j = np.arange(L, dtype=np.uint64)[None, :]
+        fwd = _hap_base(kg, ks, hap, start[:, None] + j)
+        rev = np.uint64(3) - _hap_base(kg, ks, hap, (start + insert - np.uint64(1))[:, None] - j)
+        r1 = np.where(flip[:, None], rev, fwd)
+        r2 = np.where(flip[:, None], fwd, rev)
+        bases = np.empty((2 * n_pairs, L), np.uint64)
+        bases[0::2], bases[1::2] = r1, r2
+        rid = np.arange(2 * first_pair, 2 * (first_pair + n_pairs), dtype=np.uint64)
+        kr = _mix64(ke ^ rid)[:, None]
+        e = _mix64(kr ^ j)
+        T = cb_error_thresholds(L).astype(np.uint64)[None, :]
+        err = (e & np.uint64(0xFFFFFF)) < T
+        sub = (bases + np.uint64(1) + ((e >> np.uint64(24)) & np.uint64(0xFF)) % np.uint64(3)) & np.uint64(3)
+        bases = np.where(err, sub, bases).astype(np.uint8)
+        eq = np.array([2, 12, 20], np.uint8)[(((e >> np.uint64(32)) & np.uint64(0xFF)) % np.uint64(3)).astype(np.int64)]
+        good = np.where(((e >> np.uint64(40)) & np.uint64(0xFFFF)) % np.uint64(100) < np.uint64(5), 30, 37).astype(np.uint8)
+        quals = np.where(err, eq, good).astype(np.uint8)
+    bc = (1 + (np.arange(first_pair, first_pair + n_pairs, dtype=object) * n_bc) // total_pairs).astype(np.int32)
+    return bases, quals, np.repeat(bc, 2)

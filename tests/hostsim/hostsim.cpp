@@ -8,6 +8,7 @@
 #include "../../supernova_b200/csrc/sn_path.cuh"
 #include "../../supernova_b200/csrc/sn_msp.cuh"
 #include "../../supernova_b200/csrc/sn_dfside.cuh"
+#include "../../supernova_b200/csrc/sn_synth.cuh"
 #include "../../supernova_b200/csrc/sn_hbv.h"
 #include "../../supernova_b200/csrc/sn_formats.h"
 #include <algorithm>
@@ -309,6 +310,18 @@ int hs_mark_dups(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t*
         }
     }
     return 0;
+}
+
+// sn_synth.cuh: reads [2 * first_pair, 2 * (first_pair + n_pairs)) of the counter-based generator, as k_synth_reads makes them
+void hs_synth_reads(uint64_t G, uint64_t total_pairs, uint32_t n_bc, uint64_t seed, const uint32_t* T, uint64_t first_pair, uint64_t n_pairs,
+                    uint8_t* bases, uint8_t* quals, int32_t* bc)
+{
+    SynSpec sp; sp.genome_bases = G; sp.total_pairs = total_pairs; sp.seed = seed; sp.n_barcodes = n_bc;
+    for (uint64_t r = 0; r < 2 * n_pairs; ++r) {
+        const uint64_t p = first_pair + (r >> 1);
+        syn_read(sp, T, p, (uint32_t)(r & 1), bases + r * SN_SYN_L, quals + r * SN_SYN_L);
+        bc[r] = syn_barcode(sp, p);
+    }
 }
 
 }  // extern "C"

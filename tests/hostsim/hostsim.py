@@ -14,7 +14,7 @@ def lib():
     if _L is None:
         so = os.path.join(HERE, "libhostsim.so")
         src = [os.path.join(HERE, "hostsim.cpp")] + [os.path.join(ROOT, "supernova_b200", "csrc", f) for f in
-                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh", "sn_dfside.cuh")]
+                                                       ("sn_hbv.cpp", "sn_formats.cpp", "sn_kmer.cuh", "sn_graph.cuh", "sn_path.cuh", "sn_hbv.h", "sn_msp.cuh", "sn_dfside.cuh", "sn_synth.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DSN_HOSTSIM", "-o", so] + src[:3] + ["-lz"])
         L = C.CDLL(so)
@@ -33,6 +33,7 @@ def lib():
         L.hs_hbv.argtypes = [vp, C.c_char_p]
         L.hs_paths.argtypes = [vp, u64, vp, vp, vp, vp, vp, C.c_char_p]
         L.hs_pathsx.argtypes = [vp, C.c_char_p]
+        L.hs_synth_reads.argtypes = [u64, u64, C.c_uint32, u64, vp, u64, u64, vp, vp, vp]
         L.hs_mark_dups.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.hs_extract_read.argtypes = [vp, C.c_uint32, C.c_int32, vp]
         L.hs_extract_read.restype = C.c_uint32
