@@ -216,7 +216,7 @@ int sn_i_pick_bucket_bits(uint64_t n_occ);
 uint32_t sn_i_first_bucket(uint32_t owner, uint32_t nparts, int bits);
 int sn_i_count_set_params(sn_ctx* c, const sn_params* p);
 int sn_i_count_goodlen(sn_ctx* c, uint64_t* n_occ_out);
-int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo = 0, uint32_t b_n = 0);
+int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo = 0, uint32_t b_n = 0, uint32_t pcfg = 0 /* interleaved pass: msp_window_bucket */);
 int sn_i_msp_bucket_count(sn_ctx* c, const uint4* recs, const uint64_t* off, uint32_t n_buckets, uint32_t n_seg, uint64_t occ_bound,
                           DevBuf& surv, DevBuf& surv_off, uint64_t* n_surv_out);
 // nb_window != 0: the table holds that many buckets only (a rank's shard); extra_entries: room behind the table (ghosts)

@@ -187,6 +187,23 @@ namespace sn {
 #define SN_MS_BYTES (SN_MS_READS * (256 / 4) + 64)
 #define SN_MS_QUEUE 12
 
+// The bucket of the current pass's window a super-k-mer goes to, or 0xFFFFFFFF when it belongs to another pass.
+//   plain window   : bucket - b_lo, inside [0, b_n)  (one GPU counting in several passes over bucket ranges)
+//   interleaved    : pcfg = wb | lp << 8 | pass << 16 (sharded count in passes, sn_multi.cu): the global bucket is
+//                    owner (top bits) | within (wb bits); the top lp bits of `within` name the pass.  The buckets of one pass
+//                    are renumbered owner | rest, so that every owner's share of the pass is one contiguous range.
+SN_HD uint32_t msp_window_bucket(uint32_t b, uint32_t b_lo, uint32_t b_n, uint32_t pcfg)
+{
+    if (pcfg) {
+        const uint32_t wb = pcfg & 0xFFu, lp = (pcfg >> 8) & 0xFFu, ps = pcfg >> 16, rest = wb - lp;
+        const uint32_t within = b & ((1u << wb) - 1u);
+        if ((within >> rest) != ps) return 0xFFFFFFFFu;
+        b = ((b >> wb) << rest) | (within & ((1u << rest) - 1u));
+    }
+    b -= b_lo;
+    return b < b_n ? b : 0xFFFFFFFFu;
+}
+
 template <bool EMIT>
 static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                             const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below, uint32_t min_gl,
@@ -195,7 +212,7 @@ static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_read
                                                             uint32_t b_lo = 0u, uint32_t b_n = 0xFFFFFFFFu /* bucket window [b_lo, b_lo + b_n): a count in several passes */,
                                                             uint2* __restrict__ dsc = nullptr, uint8_t* __restrict__ nruns = nullptr /* out: the runs of every read (see k_msp_place) */,
                                                             const uint8_t* __restrict__ only_overflow = nullptr /* in: handle only the reads whose runs did not fit the descriptors */,
-                                                            uint32_t* __restrict__ n_overflow = nullptr /* out: how many reads those are */)
+                                                            uint32_t* __restrict__ n_overflow = nullptr /* out: how many reads those are */, uint32_t pcfg = 0u)
 {
     __shared__ __align__(16) uint8_t sb[SN_MS_BYTES];
     __shared__ uint32_t ring[SN_W * SN_MS_READS];
@@ -229,8 +246,8 @@ static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_read
     const int sh = 32 - bits;
     auto process = [&](uint32_t start, uint32_t nk, uint32_t minval) {
         const uint32_t bh = bucket_hash(minval);
-        const uint32_t bkt = (bh >> sh) - b_lo;
-        if (bkt >= b_n) return;                            // another pass's bucket
+        const uint32_t bkt = msp_window_bucket(bh >> sh, b_lo, b_n, pcfg);
+        if (bkt == 0xFFFFFFFFu) return;                    // another pass's bucket
         if (!EMIT) atomicAdd(&counter[bkt], 1u);
         else {
             const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);
@@ -266,7 +283,7 @@ template <bool EMIT>
 static __global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,
                                                              const uint32_t* __restrict__ goodlen, const int32_t* __restrict__ bc, int64_t ign_bc_below,
                                                              int bits, uint32_t* __restrict__ counter, const uint64_t* __restrict__ bucket_off, uint4* __restrict__ recs,
-                                                             uint32_t b_lo, uint32_t b_n, const uint2* __restrict__ dsc, const uint8_t* __restrict__ nruns)
+                                                             uint32_t b_lo, uint32_t b_n, const uint2* __restrict__ dsc, const uint8_t* __restrict__ nruns, uint32_t pcfg = 0u)
 {
     __shared__ __align__(16) uint8_t sb[EMIT ? SN_MS_BYTES : 16];
     const uint32_t tid = threadIdx.x;
@@ -301,8 +318,8 @@ static __global__ void __launch_bounds__(SN_MS_READS) k_msp_place(uint64_t n_rea
     for (uint32_t e = 0; e < n; ++e) {
         const uint2 x = d[e * SN_MS_READS];
         const uint32_t bh = bucket_hash(x.x);
-        const uint32_t bkt = (bh >> sh) - b_lo;
-        if (bkt >= b_n) continue;
+        const uint32_t bkt = msp_window_bucket(bh >> sh, b_lo, b_n, pcfg);
+        if (bkt == 0xFFFFFFFFu) continue;
         if (!EMIT) atomicAdd(&counter[bkt], 1u);
         else {
             const uint64_t pos = bucket_off[bkt] + atomicAdd(&counter[bkt], 1u);

@@ -420,55 +420,87 @@ int mg_count_sharded(sn_ctx* c)
     const int NR = c->comm->n, rank = c->comm->rank;
     int r; uint64_t n_occ = 0, n_sk = 0;
     if ((r = sn_i_count_goodlen(c, &n_occ))) return r;
-    if (n_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "more than 2^32-1 k-mer occurrences on one rank: shard the reads over more GPUs");
     std::vector<uint64_t> all, mine(1, n_occ);
     if ((r = allgather_u64(c, mine.data(), 1, all))) return r;
     uint64_t occ_total = 0; for (uint64_t v : all) occ_total += v;
     int bits = sn_i_pick_bucket_bits(occ_total);
     while ((1u << bits) < (uint32_t)NR) ++bits;
-    // super-k-mers of the local reads, bucket order: an owner's buckets are one contiguous range of the record array
-    if ((r = sn_i_msp_partition(c, bits, &n_sk))) return r;
-    const uint64_t* off = c->pool["sk_off"].as<uint64_t>();
-    std::vector<uint64_t> cut(NR + 1);
+    // A rank counts what it RECEIVES: about occ_total / NR occurrences.  Above 2^32 of them the count runs in passes, like on one
+    // GPU -- but every pass must take a slice of EVERY owner's bucket range, so the passes interleave: the global bucket is
+    // owner | within, the top bits of `within` name the pass (msp_window_bucket).  That needs a power-of-two number of ranks.
+    uint32_t lp = 0;
+    while ((occ_total / (uint64_t)NR + 1) / (1ull << lp) >= 3400000000ull) ++lp;
+    if (const char* e = getenv("SN_MG_PASSES")) { int v = atoi(e); lp = 0; while ((1 << lp) < v) ++lp; }     // tests
+    uint32_t lnr = 0; while ((1u << lnr) < (uint32_t)NR) ++lnr;
+    if (lp && (1u << lnr) != (uint32_t)NR) return fail(c, SN_ERR_ARG, "a sharded count in passes (more than 2^32 k-mer occurrences per rank) needs a power-of-two number of ranks");
+    if (lp) while ((uint32_t)bits < lnr + lp + 1) ++bits;
+    const uint32_t P = 1u << lp, wb = (uint32_t)bits - lnr;
+    // this pass's buckets, renumbered so that owner o's share is [fb[o], fb[o + 1])
     std::vector<uint32_t> fb(NR + 1);
-    for (int o = 0; o <= NR; ++o) { fb[o] = sn_i_first_bucket((uint32_t)o, (uint32_t)NR, bits); CU(cudaMemcpyAsync(&cut[o], off + fb[o], 8, cudaMemcpyDeviceToHost, c->st)); }
-    CU(cudaStreamSynchronize(c->st));
-    std::vector<uint64_t> send_n(NR);
-    for (int o = 0; o < NR; ++o) send_n[o] = cut[o + 1] - cut[o];
-    if ((r = allgather_u64(c, send_n.data(), (uint32_t)NR, all))) return r;
-    const uint32_t nbl = fb[rank + 1] - fb[rank];
-    std::vector<size_t> sb(NR), so(NR), rb(NR), ro(NR);
-    uint64_t n_recv = 0;
-    for (int s = 0; s < NR; ++s) { sb[s] = 32 * send_n[s]; so[s] = 32 * cut[s]; rb[s] = 32 * all[(size_t)s * NR + rank]; ro[s] = 32 * n_recv; n_recv += all[(size_t)s * NR + rank]; }
-    t_begin(c, "exchange");
+    for (int o = 0; o <= NR; ++o) fb[o] = lp ? (uint32_t)o << (wb - lp) : sn_i_first_bucket((uint32_t)o, (uint32_t)NR, bits);
+    const uint32_t nbl = fb[rank + 1] - fb[rank];                       // buckets this rank receives per pass
     DevBuf &recs = c->pool["mg_recs"], &cnts = c->pool["mg_counts"], &roff = c->pool["mg_off"];
-    CU(recs.alloc(std::max<uint64_t>(n_recv, 1) * 32 + 64)); CU(cnts.alloc(4ull * NR * nbl + 16)); CU(roff.alloc(8ull * ((uint64_t)NR * nbl + 1)));
-    if (c->comm->alltoallv(c->pool["sk_recs"].p, sb.data(), so.data(), recs.p, rb.data(), ro.data(), c->st)) return comm_fail(c, "alltoallv (super-k-mer records)");
-    // the per-bucket record counts of the same ranges (after the scatter the per-bucket cursors equal the counts)
-    for (int s = 0; s < NR; ++s) { sb[s] = 4ull * (fb[s + 1] - fb[s]); so[s] = 4ull * fb[s]; rb[s] = 4ull * nbl; ro[s] = 4ull * nbl * s; }
-    if (c->comm->alltoallv(c->pool["sk_hist"].p, sb.data(), so.data(), cnts.p, rb.data(), ro.data(), c->st)) return comm_fail(c, "alltoallv (bucket counts)");
-    t_end(c, "exchange");
-    const uint64_t n_cnt = (uint64_t)NR * nbl;
-    uint64_t total = 0;
-    if ((r = scan_u32(c, cnts.as<uint32_t>(), n_cnt, roff.as<uint64_t>(), &total))) return r;
-    if (total != n_recv) return fail(c, SN_ERR_DATA, "received per-bucket counts do not add up to the received records");
+    DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"], &acc = c->pool["surv_all"], &acc_cnt = c->pool["surv_all_cnt"];
+    if (lp) CU(acc_cnt.alloc(4ull * P * nbl + 16));
+    uint64_t n_acc = 0, n_dist = 0, n_recv_total = 0, n_surv = 0;
     unsigned long long* occ = c->counters.as<unsigned long long>();
-    CU(cudaMemsetAsync(occ + 4, 0, 8, c->st));
-    if (n_recv) { k_sum_nk<<<std::min(blocks_for(n_recv, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(recs.as<uint4>(), n_recv, occ + 4); KCHECK("k_sum_nk"); }
-    unsigned long long h_occ = 0;
-    CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    uint64_t n_surv = 0;
-    DevBuf &surv = c->pool["surv_a"], &surv_off = c->pool["surv_off"];
-    if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), roff.as<uint64_t>(), nbl, (uint32_t)NR, h_occ, surv, surv_off, &n_surv))) return r;
-    c->cnt.n_superkmers = n_recv;
+    for (uint32_t ps = 0; ps < P; ++ps) {
+        // super-k-mers of the local reads for this pass, bucket order: an owner's buckets are one contiguous range of the record array
+        if ((r = sn_i_msp_partition(c, bits, &n_sk, 0, 0, lp ? (wb | lp << 8 | ps << 16) : 0u))) return r;
+        const uint64_t* off = c->pool["sk_off"].as<uint64_t>();
+        std::vector<uint64_t> cut(NR + 1);
+        for (int o = 0; o <= NR; ++o) CU(cudaMemcpyAsync(&cut[o], off + fb[o], 8, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        std::vector<uint64_t> send_n(NR);
+        for (int o = 0; o < NR; ++o) send_n[o] = cut[o + 1] - cut[o];
+        if ((r = allgather_u64(c, send_n.data(), (uint32_t)NR, all))) return r;
+        std::vector<size_t> sb(NR), so(NR), rb(NR), ro(NR);
+        uint64_t n_recv = 0;
+        for (int s2 = 0; s2 < NR; ++s2) { sb[s2] = 32 * send_n[s2]; so[s2] = 32 * cut[s2]; rb[s2] = 32 * all[(size_t)s2 * NR + rank]; ro[s2] = 32 * n_recv; n_recv += all[(size_t)s2 * NR + rank]; }
+        t_begin(c, "exchange");
+        CU(recs.alloc(std::max<uint64_t>(n_recv, 1) * 32 + 64)); CU(cnts.alloc(4ull * NR * nbl + 16)); CU(roff.alloc(8ull * ((uint64_t)NR * nbl + 1)));
+        if (c->comm->alltoallv(c->pool["sk_recs"].p, sb.data(), so.data(), recs.p, rb.data(), ro.data(), c->st)) return comm_fail(c, "alltoallv (super-k-mer records)");
+        // the per-bucket record counts of the same ranges (after the scatter the per-bucket cursors equal the counts)
+        for (int s2 = 0; s2 < NR; ++s2) { sb[s2] = 4ull * (fb[s2 + 1] - fb[s2]); so[s2] = 4ull * fb[s2]; rb[s2] = 4ull * nbl; ro[s2] = 4ull * nbl * s2; }
+        if (c->comm->alltoallv(c->pool["sk_hist"].p, sb.data(), so.data(), cnts.p, rb.data(), ro.data(), c->st)) return comm_fail(c, "alltoallv (bucket counts)");
+        t_end(c, "exchange");
+        const uint64_t n_cnt = (uint64_t)NR * nbl;
+        uint64_t total = 0;
+        if ((r = scan_u32(c, cnts.as<uint32_t>(), n_cnt, roff.as<uint64_t>(), &total))) return r;
+        if (total != n_recv) return fail(c, SN_ERR_DATA, "received per-bucket counts do not add up to the received records");
+        CU(cudaMemsetAsync(occ + 4, 0, 8, c->st));
+        if (n_recv) { k_sum_nk<<<std::min(blocks_for(n_recv, 256), 8u * (unsigned)c->num_sms), 256, 0, c->st>>>(recs.as<uint4>(), n_recv, occ + 4); KCHECK("k_sum_nk"); }
+        unsigned long long h_occ = 0;
+        CU(cudaMemcpyAsync(&h_occ, occ + 4, 8, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        if (h_occ >= (1ull << 32)) return fail(c, SN_ERR_ARG, "a rank received more than 2^32-1 k-mer occurrences in one pass (skewed buckets): raise SN_MG_PASSES");
+        if ((r = sn_i_msp_bucket_count(c, recs.as<uint4>(), roff.as<uint64_t>(), nbl, (uint32_t)NR, h_occ, surv, surv_off, &n_surv))) return r;
+        n_recv_total += n_recv; n_dist += c->cnt.n_kmers_distinct;
+        if (!lp) break;
+        if (16 * (n_acc + n_surv) + 64 > acc.cap) {                    // grow towards the expected final size, keeping what is there
+            const uint64_t guess = (uint64_t)((double)(n_acc + n_surv) * (double)P / (double)(ps + 1) * 1.03) + 1024;
+            if ((r = grow_keep(c, acc, 16 * n_acc, 16 * std::max<uint64_t>(n_acc + n_surv, guess) + 64))) return r;
+        }
+        if (n_surv) CU(cudaMemcpyAsync(acc.as<uint4>() + n_acc, surv.p, 16 * n_surv, cudaMemcpyDeviceToDevice, c->st));
+        k_diff_u32<<<blocks_for(nbl, 256), 256, 0, c->st>>>(surv_off.as<uint32_t>(), nbl, acc_cnt.as<uint32_t>() + (uint64_t)ps * nbl);
+        KCHECK("k_diff_u32");
+        n_acc += n_surv;
+    }
+    c->cnt.n_superkmers = n_recv_total;
+    const uint64_t n_mine = lp ? n_acc : n_surv;
+    const uint32_t nb_mine = P * nbl;                                    // the rank's whole bucket window (the passes' slices in order ARE bucket order)
     // the rank's shard of the dictionary, with room for its ghosts: ~0.1 neighbours per k-mer live in other buckets
     // (those whose minimizer differs), (N-1)/N of them on other ranks; the table starts at n/4 slots and grows if it must
     uint32_t cap = 1024;
-    while (cap < n_surv / 4 + 1024) cap <<= 1;
+    while (cap < n_mine / 4 + 1024) cap <<= 1;
     if (const char* e = getenv("SN_GHOST_CAP")) { uint32_t v = (uint32_t)atoll(e); if (v >= 64 && !(v & (v - 1))) cap = v; }     // tests: force overflow handling
-    if ((r = sn_i_msp_install_dict(c, surv.as<uint4>(), n_surv, bits, surv_off.as<uint32_t>(), true, nbl, cap))) return r;
-    c->dict_b_lo = fb[rank]; c->dict_b_n = nbl; c->ghost_cap = cap; c->dict_sharded = true;
+    if (lp) {
+        pool_release(c, {"sk_recs", "sk_off", "sk_dsc", "sk_nruns", "sk_hist", "surv_a", "surv_off", "surv_scratch", "mg_recs", "mg_counts", "mg_off"});
+        if ((r = sn_i_msp_install_dict(c, acc.as<uint4>(), n_mine, bits, acc_cnt.as<uint32_t>(), false, nb_mine, cap))) return r;
+        pool_release(c, {"surv_all", "surv_all_cnt"});
+        c->cnt.n_kmers_distinct = n_dist;
+    } else if ((r = sn_i_msp_install_dict(c, surv.as<uint4>(), n_mine, bits, surv_off.as<uint32_t>(), true, nbl, cap))) return r;
+    c->dict_b_lo = lp ? (uint32_t)rank << wb : fb[rank]; c->dict_b_n = nb_mine; c->ghost_cap = cap; c->dict_sharded = true;
     return SN_OK;
 }
 

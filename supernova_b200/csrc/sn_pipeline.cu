@@ -474,9 +474,10 @@ int sn_i_count_goodlen(sn_ctx* c, uint64_t* n_occ_out)
 }
 // a14 (MSP): cuts this context's reads into super-k-mers and groups them by minimizer bucket:
 // pool["sk_recs"] (32-byte records, bucket order) and pool["sk_off"] (2^bits + 1 record offsets).
-int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, uint32_t b_n)
+int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, uint32_t b_n, uint32_t pcfg)
 {
     const uint64_t n = c->cnt.n_reads;
+    if (pcfg) { b_lo = 0; b_n = (1u << bits) >> ((pcfg >> 8) & 0xFFu); }      // an interleaved pass (msp_window_bucket): all of its renumbered buckets
     const bool window = b_n != 0;                 // a count in several passes: only the buckets [b_lo, b_lo + b_n)
     const uint64_t nb = window ? b_n : 1ull << bits;
     const uint32_t w_lo = window ? b_lo : 0u, w_n = window ? b_n : 0xFFFFFFFFu;
@@ -494,18 +495,18 @@ int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, u
         CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));
         if (c->dsc_ready) {
             k_msp_place<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-                bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>());
+                bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), pcfg);
             KCHECK("k_msp_place<hist>");
             if (c->dsc_overflow) {
                 k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-                    bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, nullptr, nullptr, nruns.as<uint8_t>());
+                    bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, nullptr, nullptr, nruns.as<uint8_t>(), nullptr, pcfg);
                 KCHECK("k_msp_scan<hist, overflow>");
             }
         } else {
             CU(dsc.alloc(8ull * SN_MS_QUEUE * SN_MS_READS * grid)); CU(nruns.alloc(n));
             CU(cudaMemsetAsync(ovf, 0, 4, c->st));
             k_msp_scan<false><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-                bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), nullptr, ovf);
+                bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), nullptr, nullptr, w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), nullptr, ovf, pcfg);
             KCHECK("k_msp_scan<hist>");
             CU(cudaMemcpyAsync(&c->dsc_overflow, ovf, 4, cudaMemcpyDeviceToHost, c->st));      // (host value valid after the scan's sync below)
             c->dsc_ready = true;
@@ -522,12 +523,12 @@ int sn_i_msp_partition(sn_ctx* c, int bits, uint64_t* n_sk_out, uint32_t b_lo, u
     CU(cudaMemsetAsync(hist.p, 0, 4 * nb, c->st));                 // now the per-bucket cursors
     if (c->dsc_ready) {
         k_msp_place<true><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>());
+            bc, c->params.ign_bc_below, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, dsc.as<uint2>(), nruns.as<uint8_t>(), pcfg);
         KCHECK("k_msp_place<scatter>");
     }
     if (!c->dsc_ready || c->dsc_overflow) {
         k_msp_scan<true><<<grid, SN_MS_READS, 0, c->st>>>(n, c->bases.as<uint8_t>(), c->boff.as<uint64_t>(), c->goodlen.as<uint32_t>(),
-            bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, nullptr, nullptr, c->dsc_ready ? nruns.as<uint8_t>() : nullptr);
+            bc, c->params.ign_bc_below, c->min_gl, bits, hist.as<uint32_t>(), off.as<uint64_t>(), recs.as<uint4>(), w_lo, w_n, nullptr, nullptr, c->dsc_ready ? nruns.as<uint8_t>() : nullptr, nullptr, pcfg);
         KCHECK("k_msp_scan<scatter>");
     }
     t_end(c, "msp_scatter");

@@ -65,6 +65,31 @@ def test_stop_indexed_edge_stage_on_one_rank(sb, name, tmp_path):
 
 @pytest.mark.parametrize("name,n_ranks", [(s, n) for s in SETS for n in (2, 3, 8)] + [("mid", 4), ("empty_kmers", 2), ("nobc", 2)])
 def test_local_ranks_match_the_single_gpu_run(sb, name, n_ranks, tmp_path):
+    _check_local_ranks(sb, name, n_ranks, tmp_path)
+
+
+@pytest.mark.parametrize("name,n_ranks,passes", [("stress1", 2, 2), ("stress3", 8, 2), ("C1", 4, 4), ("C1", 2, 8), ("mid", 4, 2), ("empty_kmers", 2, 2)])
+def test_sharded_count_in_passes(sb, name, n_ranks, passes, tmp_path, monkeypatch):
+    """A rank that would receive more than 2^32 k-mer occurrences (BASELINE config 3: 15 G per GPU) counts in passes; every
+    pass takes a slice of EVERY owner's bucket range (interleaved passes, msp_window_bucket).  Forced here on small sets:
+    the result must not change."""
+    monkeypatch.setenv("SN_MG_PASSES", str(passes))
+    _check_local_ranks(sb, name, n_ranks, tmp_path)
+
+
+def test_sharded_passes_need_a_power_of_two_ranks(sb, tmp_path, monkeypatch):
+    monkeypatch.setenv("SN_MG_PASSES", "2")
+    _, data = _single(sb, "C1", str(tmp_path))
+
+    def fn(rank, ctx):
+        packed, bc = _slice(sb, data, rank, 3)
+        ctx.load_reads(*packed, bc)
+        ctx.mg_build_graph(sb.Params(), with_paths=False)
+    with pytest.raises(sb.SnError, match="power-of-two number of ranks"):
+        sb.run_local_ranks(3, fn)
+
+
+def _check_local_ranks(sb, name, n_ranks, tmp_path):
     ref, data = _single(sb, name, str(tmp_path))
 
     def rank_fn(with_paths):
