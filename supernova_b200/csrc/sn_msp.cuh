@@ -173,20 +173,6 @@ inline int msp_bucket_bits(uint64_t n_occ)
 
 }  // namespace sn
 
-#if defined(__CUDACC__)
-#include "sn_prims.cuh"
-namespace sn {
-
-// ---------------------------------------------------------------------------
-// k_msp_scan: one read per thread; a CTA stages the packed bases of its 128 reads in shared
-// memory with 16-byte loads (as k_extract does).  EMIT = false: histogram of the super-k-mers
-// per bucket.  EMIT = true: every super-k-mer record goes straight to its place in the
-// bucket-ordered record array (bucket start + a per-bucket cursor).
-// ---------------------------------------------------------------------------
-#define SN_MS_READS 128
-#define SN_MS_BYTES (SN_MS_READS * (256 / 4) + 64)
-#define SN_MS_QUEUE 12
-
 // The bucket of the current pass's window a super-k-mer goes to, or 0xFFFFFFFF when it belongs to another pass.
 //   plain window   : bucket - b_lo, inside [0, b_n)  (one GPU counting in several passes over bucket ranges)
 //   interleaved    : pcfg = wb | lp << 8 | pass << 16 (sharded count in passes, sn_multi.cu): the global bucket is
@@ -203,6 +189,20 @@ SN_HD uint32_t msp_window_bucket(uint32_t b, uint32_t b_lo, uint32_t b_n, uint32
     b -= b_lo;
     return b < b_n ? b : 0xFFFFFFFFu;
 }
+
+#if defined(__CUDACC__)
+#include "sn_prims.cuh"
+namespace sn {
+
+// ---------------------------------------------------------------------------
+// k_msp_scan: one read per thread; a CTA stages the packed bases of its 128 reads in shared
+// memory with 16-byte loads (as k_extract does).  EMIT = false: histogram of the super-k-mers
+// per bucket.  EMIT = true: every super-k-mer record goes straight to its place in the
+// bucket-ordered record array (bucket start + a per-bucket cursor).
+// ---------------------------------------------------------------------------
+#define SN_MS_READS 128
+#define SN_MS_BYTES (SN_MS_READS * (256 / 4) + 64)
+#define SN_MS_QUEUE 12
 
 template <bool EMIT>
 static __global__ void __launch_bounds__(SN_MS_READS) k_msp_scan(uint64_t n_reads, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ boff,

@@ -312,6 +312,9 @@ int hs_mark_dups(Sim* s, uint64_t n_reads, const uint8_t* bases, const uint64_t*
     return 0;
 }
 
+// sn_msp.cuh: the window / interleaved-pass bucket mapping of the MSP partition kernels
+uint32_t hs_window_bucket(uint32_t b, uint32_t b_lo, uint32_t b_n, uint32_t pcfg) { return msp_window_bucket(b, b_lo, b_n, pcfg); }
+
 // sn_synth.cuh: reads [2 * first_pair, 2 * (first_pair + n_pairs)) of the counter-based generator, as k_synth_reads makes them
 void hs_synth_reads(uint64_t G, uint64_t total_pairs, uint32_t n_bc, uint64_t seed, const uint32_t* T, uint64_t first_pair, uint64_t n_pairs,
                     uint8_t* bases, uint8_t* quals, int32_t* bc)

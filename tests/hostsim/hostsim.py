@@ -33,6 +33,8 @@ def lib():
         L.hs_hbv.argtypes = [vp, C.c_char_p]
         L.hs_paths.argtypes = [vp, u64, vp, vp, vp, vp, vp, C.c_char_p]
         L.hs_pathsx.argtypes = [vp, C.c_char_p]
+        L.hs_window_bucket.argtypes = [C.c_uint32] * 4
+        L.hs_window_bucket.restype = C.c_uint32
         L.hs_synth_reads.argtypes = [u64, u64, C.c_uint32, u64, vp, u64, u64, vp, vp, vp]
         L.hs_mark_dups.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.hs_extract_read.argtypes = [vp, C.c_uint32, C.c_int32, vp]

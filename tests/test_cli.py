@@ -25,6 +25,36 @@ def test_cli_usage_and_loud_failure(built, tmp_path):
         assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
 
 
+def test_scale_tool_usage_and_loud_failure(built):
+    """supernova_b200/sn_scale (csrc/sn_scale.cpp: scale runs on device-generated reads): builds, and refuses to run without a GPU"""
+    exe = os.path.join(ROOT, "supernova_b200", "sn_scale")
+    assert os.access(exe, os.X_OK)
+    r = subprocess.run([exe, "bogus"], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: sn_scale" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "NGPU=1", "MULT=0.01"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_scale_tool_one_gpu_matches_the_library(built, tmp_path):
+    """sn_scale NGPU=1 on a small job: its a.hbv is the one the library writes for the same generated reads through Python"""
+    import json
+    import supernova_b200 as sb
+    exe = os.path.join(ROOT, "supernova_b200", "sn_scale")
+    hbv = str(tmp_path / "scale.hbv")
+    r = subprocess.run([exe, "NGPU=1", "G=500000", "PAIRS=40000", "NBC=2000", "SEED=11", "HBV=" + hbv, "PASSES=3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["ok"] and out["reads"] == 80000 and out["kmers"] > 400000
+    with sb.Context(0) as ctx:
+        ctx.generate_reads(500000, 40000, 2000, 11)
+        ctx.build_read_qgraph48(str(tmp_path), sb.Params(), with_paths=False)
+        assert ctx.counts()["n_kmers"] == out["kmers"] and ctx.counts()["n_edges"] == out["unipaths"]
+    assert open(hbv, "rb").read() == open(str(tmp_path / "a.hbv"), "rb").read()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["tiny", "stress1"])
 def test_cli_reproduces_the_reference_files(built, name, tmp_path):

@@ -146,3 +146,31 @@ def test_df_side_logic_matches_golden(sb, name, tmp_path):
     dup, art, ndups, inter = hs.mark_dups(pb, boff, pl, quals, off, bc)
     assert dfside.dup_file(dup.tolist()) == gz("a.dup")
     assert dfside.dup_percentages(dup.tolist(), ndups, inter, art.tolist()) == json.load(open(os.path.join(g, "dup_stats.json")))
+
+
+@pytest.mark.parametrize("bits,lnr,lp", [(6, 1, 1), (8, 2, 2), (10, 3, 3), (9, 0, 2), (7, 3, 1)])
+def test_interleaved_pass_bucket_mapping(sb, bits, lnr, lp):
+    """msp_window_bucket (sn_msp.cuh), the mapping behind the sharded count in passes (sn_multi.cu: mg_count_sharded): the global
+    bucket is owner | within; the top lp bits of `within` name the pass.  Every bucket belongs to exactly one pass; inside a pass
+    the renumbered buckets are owner-major (an owner's share is one contiguous range, owner o at o << (wb - lp)) and keep their
+    order; a rank's slices of the passes, in pass order, are its buckets in bucket order."""
+    from hostsim import lib
+    L = lib()
+    nb, wb, P = 1 << bits, bits - lnr, 1 << lp
+    per_pass = nb >> lp
+    seen = np.zeros(nb, np.int64)
+    for ps in range(P):
+        pcfg = wb | (lp << 8) | (ps << 16)
+        comp = np.array([L.hs_window_bucket(b, 0, per_pass, pcfg) for b in range(nb)], np.int64)
+        mine = comp != 0xFFFFFFFF
+        seen += mine
+        b = np.nonzero(mine)[0]
+        assert len(b) == per_pass and np.array_equal(np.sort(comp[b]), np.arange(per_pass))
+        assert (np.diff(comp[b]) > 0).all()                                   # order kept
+        owner = b >> wb
+        assert np.array_equal(comp[b] >> (wb - lp), owner)                    # owner-major: owner o holds [o << (wb-lp), (o+1) << (wb-lp))
+        assert np.array_equal((b & ((1 << wb) - 1)) >> (wb - lp), np.full(len(b), ps))
+    assert (seen == 1).all()
+    # plain windows (one GPU in passes) and no window at all
+    assert L.hs_window_bucket(5, 4, 8, 0) == 1 and L.hs_window_bucket(3, 4, 8, 0) == 0xFFFFFFFF and L.hs_window_bucket(12, 4, 8, 0) == 0xFFFFFFFF
+    assert L.hs_window_bucket(123456, 0, 0xFFFFFFFF, 0) == 123456
