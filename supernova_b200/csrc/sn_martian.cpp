@@ -378,9 +378,14 @@ int main(int argc, char** argv)
     }
     Metadata md;
     md.stage_name = argv[2]; md.stage_type = argv[3]; md.metadata_path = argv[4]; md.files_path = argv[5]; md.run_file = argv[6];
-    md.update_jobinfo(argv[0]);
-    md.log("time", "__start__");
-    md.journal("stdout"); md.journal("stderr");
+    try {
+        md.update_jobinfo(argv[0]);
+        md.log("time", "__start__");
+        md.journal("stdout"); md.journal("stderr");
+    } catch (const std::exception& e) {                       // (a metadata directory that cannot be written: nothing can be reported there)
+        fprintf(stderr, "sn_martian: %s\n", e.what());
+        return 1;
+    }
     // heartbeat: Martian declares a chunk dead without it (lib.rs:537-543)
     std::mutex hm; std::condition_variable hcv; bool done = false;
     std::thread heart([&] { std::unique_lock<std::mutex> lk(hm); while (!done) { md.journal("heartbeat", true); hcv.wait_for(lk, std::chrono::seconds(60)); } });
