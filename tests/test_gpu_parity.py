@@ -99,3 +99,18 @@ def test_against_reference_binary(run, sb):
     assert open(run["wd"] + "/tmp.paths", "rb").read() == open(wd + "/tmp.paths", "rb").read()
     spec_ref = open(wd + "/stats/histogram_kmer_count.json").read()
     assert open(run["wd"] + "/stats/histogram_kmer_count.json").read() == spec_ref
+
+
+def test_trim_rule_against_the_references_known_answers(sb):
+    """k_pqvec_goodlen / k_q8_goodlen on the reference's own known-answer vectors for the trim rule (lib/tada/src/cmd_msp.rs:329-350)"""
+    from test_oracle_golden import _qv_trim_vectors
+    codes, quals, off, expect = _qv_trim_vectors()
+    pb, boff, ln, pq, pqoff = sb.pack_reads(codes, quals, off)
+    for raw in (False, True):
+        with sb.Context(0) as ctx:
+            if raw:
+                ctx.load_reads_q8(pb, boff, ln, quals, off, None)
+            else:
+                ctx.load_reads(pb, boff, ln, pq, pqoff, None)
+            ctx.count_kmers(sb.Params(min_qual=10))
+            assert np.array_equal(ctx.good_lengths(), expect)

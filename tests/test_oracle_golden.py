@@ -183,3 +183,27 @@ def test_oracle_tada_switch_against_an_independent_restatement(name):
         mine[bytes((w >> (2 * (K - 1 - i))) & 3 for i in range(K))] = int(row[3])
     assert mine == valid
     assert n_len_k > 0 or name == "tiny"
+
+
+def _qv_trim_vectors():
+    """The reference's own known-answer test for the trim rule, lib/tada/src/cmd_msp.rs:329-350 (test_qv_trim_read): an 88-base
+    read whose quals all pass min_qual = 10; one qual at a time is set to Q1; expected length = 88 if i < 88 - K, else i if
+    i >= K, else 0.  Returned as reads (codes, quals, off) with the expected lengths."""
+    seq = "TAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAACCCTAAC"
+    q = "FFFFFFFFIFFFFFFFFFFIIIFFBFIFFFFIFBFFIBFIFBBFFIFFIFFFFFFFFFFFBBBBBBBBBB07BB7BB<BBBBBBBBBB"
+    assert len(seq) == len(q) == 88
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    b = np.array([code[c] for c in seq], np.uint8)
+    base_q = np.array([ord(c) - 33 for c in q], np.uint8)
+    n = len(seq)
+    codes = np.tile(b, n)
+    quals = np.tile(base_q, n).reshape(n, n).copy()
+    quals[np.arange(n), np.arange(n)] = 1                      # (myquals[i] = 34 as u8)
+    expect = np.array([n if i < n - 48 else (i if i >= 48 else 0) for i in range(n)], np.uint32)
+    return codes, quals.ravel(), np.arange(n + 1, dtype=np.uint64) * n, expect
+
+
+def test_trim_rule_against_the_references_known_answers():
+    codes, quals, off, expect = _qv_trim_vectors()
+    o = Oracle(codes, quals, off, None, min_qual=10).stage("count")
+    assert np.array_equal(o.good_len(), expect)
