@@ -1656,13 +1656,13 @@ int sn_write_kmer_spectrum(sn_ctx* c, const char* json)
     std::vector<int64_t> spec;
     for (uint32_t v : cc) { uint32_t k = v & 0xFFFFFFu; if (spec.size() <= k) spec.resize(k + 1, 0); spec[k]++; }
     int64_t maxc = (int64_t)spec.size() - 1;
-    FILE* f = fopen(json, "w");
-    if (!f) return fail(c, SN_ERR_IO, std::string("cannot create ") + json);
-    fprintf(f, "{\n\t\"description\": \"kmer_count\",\n\t\"stage\": \"DF\",\n\t\"binsize\": 1,\n\t\"min\": 0,\n\t\"max\": %lld,\n\t\"numbins\": %zu,\n\t\"vals\": [",
-            (long long)maxc, spec.size());
-    for (size_t i = 0; i < spec.size(); ++i) fprintf(f, "%lld%s", (long long)spec[i], i + 1 == spec.size() ? "" : ",");
-    fprintf(f, "]\n}\n");
-    fclose(f);
+    // (through the checked writer: a failed write or close is SN_ERR_IO, and the file appears only when complete)
+    std::string text = "{\n\t\"description\": \"kmer_count\",\n\t\"stage\": \"DF\",\n\t\"binsize\": 1,\n\t\"min\": 0,\n\t\"max\": " + std::to_string((long long)maxc) +
+                       ",\n\t\"numbins\": " + std::to_string(spec.size()) + ",\n\t\"vals\": [";
+    for (size_t i = 0; i < spec.size(); ++i) { text += std::to_string((long long)spec[i]); if (i + 1 != spec.size()) text += ","; }
+    text += "]\n}\n";
+    std::string err;
+    if (!snf::write_text(json, text, err)) return fail(c, SN_ERR_IO, err);
     return SN_OK;
 }
 
