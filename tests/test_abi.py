@@ -39,3 +39,16 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "sn_oracle" not in txt and "oracle." not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/supernova_b200.h must compile as C99 (no C++ in the signatures, no torch types), and a C
+    caller can name every struct and constant it declares."""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "supernova_b200.h"\n'
+                   "int main(void) { sn_params p; sn_counts c; sn_synth s; sn_dup_stats d; sn_kmer_rec k; sn_ctx* x = 0;\n"
+                   "  (void)p; (void)c; (void)s; (void)d; (void)k; (void)x; return SN_OK + SN_ERR_CUDA + SN_SEM_TADA; }\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
