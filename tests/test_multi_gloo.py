@@ -127,6 +127,97 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_passes(rank, world, port, q, lp):
+    """The sharded count in 2^lp interleaved passes (sn_multi.cu: mg_count_sharded), host arithmetic only: per pass the records of
+    msp_window_bucket's window, renumbered owner-major, exchanged and reduced; a rank's per-pass results in pass order must be in
+    global bucket order, and the union over the ranks the oracle's dictionary."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "hostsim"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import datasets
+    import supernova_b200 as sb
+    from supernova_b200 import multigpu as mg
+    from hostsim import lib
+    from oracle.oracle import Oracle
+    codes, quals, off, bc, _ = datasets.get("stress1")
+    n = len(off) - 1
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    o = Oracle(codes, quals, off, bc).stage("count")
+    gl = o.good_len()
+    pb, boff, pl, pq, pqoff = sb.pack_reads(codes, quals, off, threads=1)
+    padded = np.concatenate([pb, np.zeros(64, np.uint8)])
+    buf = np.zeros((256, 4), np.uint32); bh = np.zeros(256, np.uint32); skb = np.zeros((256, 8), np.uint32); nsk = np.zeros(1, np.uint32)
+    sk = [np.zeros((0, 8), np.uint32)]
+    for r in range(lo, hi):
+        m = lib().hs_msp_read(padded.ctypes.data + int(boff[r]), int(gl[r]), int(bc[r]), buf.ctypes.data, bh.ctypes.data, skb.ctypes.data, nsk.ctypes.data)
+        if m:
+            sk.append(skb[:int(nsk[0])].copy())
+    sk = np.concatenate(sk)
+    lnr = world.bit_length() - 1
+    bits = max(mg.bucket_bits(o.n_occ), lnr + lp + 1)
+    wb = bits - lnr
+    gbkt = (sk[:, 1] >> np.uint32(32 - bits)).astype(np.int64)
+    per_pass = (1 << bits) >> lp
+    nbl = 1 << (wb - lp)                                              # buckets a rank receives per pass
+    mine, mine_bucket = [], []
+    for ps in range(1 << lp):
+        pcfg = wb | (lp << 8) | (ps << 16)
+        table = np.array([lib().hs_window_bucket(b, 0, per_pass, pcfg) for b in range(1 << bits)], np.int64)
+        comp = table[gbkt]
+        sel = comp != 0xFFFFFFFF
+        s_p, c_p, g_p = sk[sel], comp[sel], gbkt[sel]
+        order = np.argsort(c_p, kind="stable")
+        s_p, c_p, g_p = s_p[order], c_p[order], g_p[order]
+        send_counts = [int(((c_p >> (wb - lp)) == w).sum()) for w in range(world)]
+        recv_counts = mg.exchange_counts(dist, send_counts, "cpu")
+        send_t = torch.from_numpy(s_p.astype(np.int32).ravel().copy())
+        recv_t = torch.empty(sum(recv_counts) * mg.SK_WORDS, dtype=torch.int32)
+        mg.exchange_records(dist, send_t, send_counts, recv_t, recv_counts, mg.SK_WORDS)
+        got = recv_t.numpy().view(np.uint32).reshape(-1, 8)
+        gb = (got[:, 1] >> np.uint32(32 - bits)).astype(np.int64)
+        # everything received belongs to this rank (owner = top bits) and to this pass (next lp bits)
+        assert ((gb >> wb) == rank).all() and (((gb & ((1 << wb) - 1)) >> (wb - lp)) == ps).all()
+        krec = np.zeros((int((((got[:, 0] >> 24) & 0x3F) + 1).sum()), 4), np.uint32)
+        m = lib().hs_sk_expand(np.ascontiguousarray(got).ctypes.data, len(got), krec.ctypes.data) if len(got) else 0
+        assert m == len(krec)
+        mine.append(_reduce_numpy(krec))
+        mine_bucket.append((rank << wb) + (ps << (wb - lp)))          # first global bucket of this slice
+    assert mine_bucket == sorted(mine_bucket) and mine_bucket[0] == rank << wb      # pass order is bucket order inside the rank's window
+    sl = np.concatenate(mine)
+    sizes_t = torch.zeros(world, dtype=torch.int64)
+    sizes_t[rank] = len(sl)
+    dist.all_reduce(sizes_t)
+    sizes = [int(x) for x in sizes_t.tolist()]
+    full_t = torch.empty(sum(sizes) * mg.SURV_WORDS, dtype=torch.int32)
+    mg.gather_slices(dist, torch.from_numpy(sl.astype(np.int32).ravel().copy()), full_t, sizes, mg.SURV_WORDS)
+    full = full_t.numpy().view(np.uint32).reshape(-1, 4)
+    ok = o.kmers()
+    idx = np.lexsort((full[:, 2], full[:, 1], full[:, 0]))
+    res = len(full) == len(ok) and np.array_equal(full[idx][:, :3], ok[:, :3]) and np.array_equal(full[idx][:, 3], ok[:, 3] | (ok[:, 4] << 24))
+    q.put((rank, bool(res), len(full), nbl))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lp", [1, 2])
+def test_two_rank_count_in_interleaved_passes_matches_oracle(built, lp):
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_passes, args=(r, world, port, q, lp)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in out), out
+    assert out[0][2] == out[1][2] > 0
+
+
 def test_two_rank_exchange_matches_oracle(built):
     world = 2
     port = _free_port()
